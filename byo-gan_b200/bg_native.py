@@ -1,0 +1,86 @@
+"""ctypes binding of libbg_b200.so (include/bg_b200.h).
+
+This is the only place the Python host touches the C ABI.  There is no fallback: if the library is
+missing or a kernel reports an error the call raises.  Tensors are passed as raw device pointers;
+the stream is torch's current CUDA stream.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libbg_b200.so")
+_lib = None
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+_F = ctypes.c_float
+_Z = ctypes.c_size_t
+
+# name -> argtypes, mirrors include/bg_b200.h one to one
+SIGNATURES = {
+    "bg_pack_weight": [_P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "bg_unpack_wgrad": [_P, _P, _I, _I, _I, _I, _F, _I, _P],
+    "bg_conv_fprop": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _F, _P],
+    "bg_conv_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "bg_act_gate": [_P, _P, _P, _Z, _F, _P],
+    "bg_axpby": [_P, _P, _P, _Z, _F, _F, _P],
+    "bg_pool_act_fwd": [_P, _P, _P, _I, _I, _I, _I, _F, _I, _P],
+    "bg_pool_act_bwd": [_P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "bg_upsample2x_fwd": [_P, _P, _I, _I, _I, _I, _P],
+    "bg_upsample2x_bwd": [_P, _P, _I, _I, _I, _I, _P],
+    "bg_channel_wsum": [_P, _P, _P, _Z, _I, _I, _Z, _Z, _I, _P],
+    "bg_planes3_to_nhwc": [_P, _P, _P, _P, _Z, _I, _I, _I, _I, _F, _I, _F, _P],
+    "bg_nhwc_to_planes3": [_P, _P, _P, _P, _Z, _I, _I, _I, _I, _F, _P],
+    "bg_in_stats": [_P, _P, _I, _I, _I, _P],
+    "bg_adain_apply": [_P, _P, _P, _P, _I, _I, _I, _F, _P],
+    "bg_adain_bwd_reduce": [_P, _P, _P, _P, _I, _I, _I, _F, _P],
+    "bg_adain_bwd_apply": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _I, _P],
+}
+
+launch_count = 0  # kernels launched through this binding (bench.py reports it as gpu_launches)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise RuntimeError(
+                f"{_LIB_PATH} is missing: build it with `python byo-gan_b200/build.py` "
+                "(there is no CPU or eager fallback for the hot path)"
+            )
+        l = ctypes.CDLL(_LIB_PATH)
+        l.bg_last_error.restype = ctypes.c_char_p
+        l.bg_abi_version.restype = _I
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.argtypes = argtypes
+            fn.restype = _I
+        _lib = l
+    return _lib
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("bg_b200 kernels need CUDA tensors (no CPU fallback exists)")
+    if not t.is_contiguous():
+        raise RuntimeError("bg_b200 kernels need contiguous tensors")
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    """Invoke a C-ABI entry point; tensors -> device pointers, stream appended."""
+    global launch_count
+    l = lib()
+    conv = [(_ptr(a) if (a is None or isinstance(a, torch.Tensor)) else a) for a in args]
+    rc = getattr(l, name)(*conv, _stream())
+    launch_count += 1
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {l.bg_last_error().decode()}")

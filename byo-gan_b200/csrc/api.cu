@@ -1,0 +1,98 @@
+// extern "C" surface declared in include/bg_b200.h: thin forwarding to the launchers.
+#include "common.cuh"
+#include "../../include/bg_b200.h"
+
+namespace bg {
+int launch_conv_fprop(const void*, const void*, void*, int, int, int, int, int, int, const float*, const float*,
+                      const float*, const void*, int, float, cudaStream_t);
+int launch_conv_wgrad(const void*, const void*, float*, int, int, int, int, int, cudaStream_t);
+int launch_pack_weight(const float*, void*, void*, int, int, int, int, float, cudaStream_t);
+int launch_unpack_wgrad(const float*, float*, int, int, int, int, float, int, cudaStream_t);
+int launch_act_gate(const void*, const void*, void*, size_t, float, cudaStream_t);
+int launch_axpby(const void*, const void*, void*, size_t, float, float, cudaStream_t);
+int launch_pool_act_fwd(const void*, const void*, void*, int, int, int, int, float, int, cudaStream_t);
+int launch_pool_act_bwd(const void*, const void*, void*, int, int, int, int, float, cudaStream_t);
+int launch_upsample2x_fwd(const void*, void*, int, int, int, int, cudaStream_t);
+int launch_upsample2x_bwd(const void*, void*, int, int, int, int, cudaStream_t);
+int launch_channel_wsum(const void*, const float*, float*, size_t, int, int, size_t, size_t, int, cudaStream_t);
+int launch_planes3_to_nhwc(const float*, const float*, const float*, void*, size_t, int, int, int, int, float, int,
+                           float, cudaStream_t);
+int launch_nhwc_to_planes3(const void*, const float*, const float*, float*, size_t, int, int, int, int, float,
+                           cudaStream_t);
+int launch_in_stats(const void*, float*, int, int, int, cudaStream_t);
+int launch_adain_apply(const void*, const float*, const float*, void*, int, int, int, float, cudaStream_t);
+int launch_adain_bwd_reduce(const void*, const void*, const float*, float*, int, int, int, float, cudaStream_t);
+int launch_adain_bwd_apply(const void*, const void*, const float*, const float*, const float*, void*, int, int, int,
+                           float, float, int, cudaStream_t);
+}  // namespace bg
+
+#define S(stream) reinterpret_cast<cudaStream_t>(stream)
+
+extern "C" {
+
+int bg_pack_weight(const float* w, void* wf, void* wd, int Cout, int Cin, int Cin_pad, int ks, float coef,
+                   void* stream) {
+  return bg::launch_pack_weight(w, wf, wd, Cout, Cin, Cin_pad, ks, coef, S(stream));
+}
+int bg_unpack_wgrad(const float* dwp, float* dw, int Cout, int Cin, int Cin_pad, int ks, float coef, int accumulate,
+                    void* stream) {
+  return bg::launch_unpack_wgrad(dwp, dw, Cout, Cin, Cin_pad, ks, coef, accumulate, S(stream));
+}
+int bg_conv_fprop(const void* x, const void* wpack, void* out, int N, int H, int W, int Cin, int Cout, int ksize,
+                  const float* bias, const float* noise, const float* noise_w, const void* gate_src, int act,
+                  float slope, void* stream) {
+  return bg::launch_conv_fprop(x, wpack, out, N, H, W, Cin, Cout, ksize, bias, noise, noise_w, gate_src, act, slope,
+                               S(stream));
+}
+int bg_conv_wgrad(const void* x, const void* g, float* dwp, int N, int H, int W, int Cin, int Cout, void* stream) {
+  return bg::launch_conv_wgrad(x, g, dwp, N, H, W, Cin, Cout, S(stream));
+}
+int bg_act_gate(const void* g, const void* y, void* out, size_t n, float slope, void* stream) {
+  return bg::launch_act_gate(g, y, out, n, slope, S(stream));
+}
+int bg_axpby(const void* a, const void* b, void* out, size_t n, float ca, float cb, void* stream) {
+  return bg::launch_axpby(a, b, out, n, ca, cb, S(stream));
+}
+int bg_pool_act_fwd(const void* u, const void* gate_src, void* y, int N, int Ho, int Wo, int C, float slope, int mode,
+                    void* stream) {
+  return bg::launch_pool_act_fwd(u, gate_src, y, N, Ho, Wo, C, slope, mode, S(stream));
+}
+int bg_pool_act_bwd(const void* gy, const void* y, void* gu, int N, int Ho, int Wo, int C, float slope,
+                    void* stream) {
+  return bg::launch_pool_act_bwd(gy, y, gu, N, Ho, Wo, C, slope, S(stream));
+}
+int bg_upsample2x_fwd(const void* x, void* y, int N, int H, int W, int C, void* stream) {
+  return bg::launch_upsample2x_fwd(x, y, N, H, W, C, S(stream));
+}
+int bg_upsample2x_bwd(const void* gy, void* gx, int N, int H, int W, int C, void* stream) {
+  return bg::launch_upsample2x_bwd(gy, gx, N, H, W, C, S(stream));
+}
+int bg_channel_wsum(const void* g, const float* planes, float* out, size_t P, int C, int HW, size_t img_stride,
+                    size_t plane_stride, int nplanes, void* stream) {
+  return bg::launch_channel_wsum(g, planes, out, P, C, HW, img_stride, plane_stride, nplanes, S(stream));
+}
+int bg_planes3_to_nhwc(const float* img, const float* Wm, const float* bias, void* out, size_t P, int HW, int C,
+                       int ws_c, int ws_j, float coef, int act, float slope, void* stream) {
+  return bg::launch_planes3_to_nhwc(img, Wm, bias, out, P, HW, C, ws_c, ws_j, coef, act, slope, S(stream));
+}
+int bg_nhwc_to_planes3(const void* x, const float* Wm, const float* bias, float* out, size_t P, int HW, int C,
+                       int ws_c, int ws_j, float coef, void* stream) {
+  return bg::launch_nhwc_to_planes3(x, Wm, bias, out, P, HW, C, ws_c, ws_j, coef, S(stream));
+}
+int bg_in_stats(const void* a, float* stats, int N, int HW, int C, void* stream) {
+  return bg::launch_in_stats(a, stats, N, HW, C, S(stream));
+}
+int bg_adain_apply(const void* a, const float* stats, const float* style, void* x, int N, int HW, int C, float eps,
+                   void* stream) {
+  return bg::launch_adain_apply(a, stats, style, x, N, HW, C, eps, S(stream));
+}
+int bg_adain_bwd_reduce(const void* g, const void* a, const float* stats, float* bsums, int N, int HW, int C,
+                        float eps, void* stream) {
+  return bg::launch_adain_bwd_reduce(g, a, stats, bsums, N, HW, C, eps, S(stream));
+}
+int bg_adain_bwd_apply(const void* g, const void* a, const float* stats, const float* style, const float* bsums,
+                       void* out, int N, int HW, int C, float eps, float slope, int gate, void* stream) {
+  return bg::launch_adain_bwd_apply(g, a, stats, style, bsums, out, N, HW, C, eps, slope, gate, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,670 @@
+// HBM-bound helper kernels around the tensor-core convolutions.  All feature maps are NHWC bf16 with
+// C a multiple of 8, processed as 16-byte vectors (8 channels) per thread, coalesced along C.
+// Images at the module boundary are NCHW fp32 exactly as the reference passes them (gan.py:183,331).
+#include "common.cuh"
+
+namespace bg {
+
+namespace {
+
+constexpr int kBlock = 256;
+
+struct F8 {
+  float v[8];
+};
+__device__ __forceinline__ F8 ld8(const __nv_bfloat16* p) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  F8 r;
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y;
+  r.v[4] = c.x; r.v[5] = c.y; r.v[6] = d.x; r.v[7] = d.y;
+  return r;
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const F8& r) {
+  uint4 u;
+  u.x = pack_bf16x2(r.v[0], r.v[1]);
+  u.y = pack_bf16x2(r.v[2], r.v[3]);
+  u.z = pack_bf16x2(r.v[4], r.v[5]);
+  u.w = pack_bf16x2(r.v[6], r.v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+inline int grid_for(size_t work, int cap_mult = 8) {
+  size_t blocks = (work + kBlock - 1) / kBlock;
+  size_t cap = (size_t)num_sms() * cap_mult;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight pack / unpack (equalized-lr coefficient folded in, gan.py:14,27,32)
+// ---------------------------------------------------------------------------------------------
+// w: fp32 (Cout, Cin, ks, ks).  wf: bf16 [tap][Cout][Cin_pad];  wd: bf16 [tap'][Cin_pad][Cout] with
+// tap' = flipped tap, so that the dgrad pass is the same forward kernel run on the gradient.
+__global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
+                                   __nv_bfloat16* __restrict__ wd, int Cout, int Cin, int Cin_pad, int ks, float coef) {
+  const int taps = ks * ks;
+  const size_t total = (size_t)taps * Cout * Cin_pad;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin_pad);
+    const int co = (int)((i / Cin_pad) % Cout);
+    const int tap = (int)(i / ((size_t)Cin_pad * Cout));
+    float v = 0.f;
+    if (ci < Cin) v = w[((size_t)co * Cin + ci) * taps + tap] * coef;
+    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+    if (wf) wf[i] = b;
+    if (wd) wd[((size_t)(taps - 1 - tap) * Cin_pad + ci) * Cout + co] = b;
+  }
+}
+
+// dwp: fp32 [tap][Cout][Cin_pad] -> dw: fp32 (Cout, Cin, ks, ks), scaled by coef; optionally accumulates.
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Cout, int Cin,
+                                    int Cin_pad, int ks, float coef, int accumulate) {
+  const int taps = ks * ks;
+  const size_t total = (size_t)Cout * Cin * taps;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % taps);
+    const int ci = (int)((i / taps) % Cin);
+    const int co = (int)(i / ((size_t)taps * Cin));
+    const float v = dwp[((size_t)tap * Cout + co) * Cin_pad + ci] * coef;
+    dw[i] = accumulate ? dw[i] + v : v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LeakyReLU gate:  out = g * (y > 0 ? 1 : slope)      (backward of nn.LeakyReLU(0.2), gan.py:86,241...)
+// ---------------------------------------------------------------------------------------------
+__global__ void act_gate_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y,
+                                __nv_bfloat16* __restrict__ out, size_t nvec, float slope) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+    F8 a = ld8(g + i * 8);
+    const F8 b = ld8(y + i * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a.v[j] *= b.v[j] > 0.f ? 1.f : slope;
+    st8(out + i * 8, a);
+  }
+}
+
+// out = ca * a + cb * b  (torch.lerp on feature maps, gan.py:347, and its gradient scalings)
+__global__ void axpby_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                             __nv_bfloat16* __restrict__ out, size_t nvec, float ca, float cb) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+    F8 x = ld8(a + i * 8);
+    if (b != nullptr) {
+      const F8 y = ld8(b + i * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x.v[j] = ca * x.v[j] + cb * y.v[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x.v[j] = ca * x.v[j];
+    }
+    st8(out + i * 8, x);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// AvgPool2d(2) + LeakyReLU (critic block tail, gan.py:258-262) and its adjoint
+// ---------------------------------------------------------------------------------------------
+// mode 0: y = lrelu(avg4(u));  mode 1: y = avg4(u) * gate(gate_src)   (tangent pass of the backward)
+__global__ void pool_act_fwd_kernel(const __nv_bfloat16* __restrict__ u, const __nv_bfloat16* __restrict__ gate_src,
+                                    __nv_bfloat16* __restrict__ y, int N, int Ho, int Wo, int C, float slope,
+                                    int mode) {
+  const int cv = C / 8;
+  const size_t total = (size_t)N * Ho * Wo * cv;
+  const int W = Wo * 2;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * 8;
+    const size_t po = i / cv;
+    const int wo = (int)(po % Wo);
+    const int ho = (int)((po / Wo) % Ho);
+    const int n = (int)(po / ((size_t)Wo * Ho));
+    const size_t base = (((size_t)n * Ho * 2 + ho * 2) * W + wo * 2) * C + c;
+    const F8 a = ld8(u + base), b = ld8(u + base + C), d = ld8(u + base + (size_t)W * C),
+             e = ld8(u + base + (size_t)W * C + C);
+    F8 r;
+    if (mode == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float s = 0.25f * (a.v[j] + b.v[j] + d.v[j] + e.v[j]);
+        r.v[j] = s > 0.f ? s : s * slope;
+      }
+    } else {
+      const F8 gt = ld8(gate_src + po * C + c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float s = 0.25f * (a.v[j] + b.v[j] + d.v[j] + e.v[j]);
+        r.v[j] = s * (gt.v[j] > 0.f ? 1.f : slope);
+      }
+    }
+    st8(y + po * C + c, r);
+  }
+}
+
+// gu[2h+dy, 2w+dx] = 0.25 * gy[h, w] * gate(y[h, w])
+__global__ void pool_act_bwd_kernel(const __nv_bfloat16* __restrict__ gy, const __nv_bfloat16* __restrict__ y,
+                                    __nv_bfloat16* __restrict__ gu, int N, int Ho, int Wo, int C, float slope) {
+  const int cv = C / 8;
+  const size_t total = (size_t)N * Ho * Wo * cv;
+  const int W = Wo * 2;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * 8;
+    const size_t po = i / cv;
+    const int wo = (int)(po % Wo);
+    const int ho = (int)((po / Wo) % Ho);
+    const int n = (int)(po / ((size_t)Wo * Ho));
+    F8 g = ld8(gy + po * C + c);
+    const F8 yy = ld8(y + po * C + c);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g.v[j] *= 0.25f * (yy.v[j] > 0.f ? 1.f : slope);
+    const size_t base = (((size_t)n * Ho * 2 + ho * 2) * W + wo * 2) * C + c;
+    st8(gu + base, g);
+    st8(gu + base + C, g);
+    st8(gu + base + (size_t)W * C, g);
+    st8(gu + base + (size_t)W * C + C, g);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// bilinear x2 upsample, align_corners=False (nn.Upsample, gan.py:112,123): taps .75/.25, edge clamp
+// ---------------------------------------------------------------------------------------------
+__global__ void upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N,
+                                      int H, int W, int C) {
+  const int cv = C / 8;
+  const int Ho = 2 * H, Wo = 2 * W;
+  const size_t total = (size_t)N * Ho * Wo * cv;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * 8;
+    const size_t po = i / cv;
+    const int wo = (int)(po % Wo);
+    const int ho = (int)((po / Wo) % Ho);
+    const int n = (int)(po / ((size_t)Wo * Ho));
+    // source rows: ho even -> (h-1: .25, h: .75); ho odd -> (h: .75, h+1: .25)
+    const int h = ho >> 1, w = wo >> 1;
+    const int h2 = (ho & 1) ? min(h + 1, H - 1) : max(h - 1, 0);
+    const int w2 = (wo & 1) ? min(w + 1, W - 1) : max(w - 1, 0);
+    const __nv_bfloat16* xb = x + (size_t)n * H * W * C + c;
+    const F8 a = ld8(xb + ((size_t)h * W + w) * C), b = ld8(xb + ((size_t)h * W + w2) * C),
+             d = ld8(xb + ((size_t)h2 * W + w) * C), e = ld8(xb + ((size_t)h2 * W + w2) * C);
+    F8 r;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      r.v[j] = 0.5625f * a.v[j] + 0.1875f * (b.v[j] + d.v[j]) + 0.0625f * e.v[j];
+    st8(y + po * C + c, r);
+  }
+}
+
+// weight with which hi-res index r (0..2L-1) reads lo-res index l, after the edge clamp
+__device__ __forceinline__ float up_weight(int r, int l, int L) {
+  const int h = r >> 1;
+  const int h2 = (r & 1) ? min(h + 1, L - 1) : max(h - 1, 0);
+  float wgt = 0.f;
+  if (h == l) wgt += 0.75f;
+  if (h2 == l) wgt += 0.25f;
+  return wgt;
+}
+
+// adjoint of the above: gx[h,w] = sum_{r,s} up_weight(r,h) up_weight(s,w) gy[r,s]
+__global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ gy, __nv_bfloat16* __restrict__ gx, int N,
+                                      int H, int W, int C) {
+  const int cv = C / 8;
+  const int Ho = 2 * H, Wo = 2 * W;
+  const size_t total = (size_t)N * H * W * cv;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * 8;
+    const size_t p = i / cv;
+    const int w = (int)(p % W);
+    const int h = (int)((p / W) % H);
+    const int n = (int)(p / ((size_t)W * H));
+    F8 acc;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc.v[j] = 0.f;
+    const __nv_bfloat16* gb = gy + (size_t)n * Ho * Wo * C + c;
+    for (int r = 2 * h - 1; r <= 2 * h + 2; ++r) {
+      if (r < 0 || r >= Ho) continue;
+      const float wr = up_weight(r, h, H);
+      if (wr == 0.f) continue;
+      for (int s = 2 * w - 1; s <= 2 * w + 2; ++s) {
+        if (s < 0 || s >= Wo) continue;
+        const float ws = up_weight(s, w, W) * wr;
+        if (ws == 0.f) continue;
+        const F8 g = ld8(gb + ((size_t)r * Wo + s) * C);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc.v[j] += ws * g.v[j];
+      }
+    }
+    st8(gx + p * C + c, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-channel weighted sums over pixels:
+//   out[0][c] = sum_p g[p,c];   out[1+j][c] = sum_p g[p,c] * plane_j[p]   (j < nplanes <= 3)
+// plane_j[p] = planes[(p / HW) * img_stride + j * plane_stride + (p % HW)]  (fp32)
+// Serves: bias grads, noise-weight grads (gan.py:52), fromRGB / toRGB weight grads.
+// ---------------------------------------------------------------------------------------------
+__global__ void channel_wsum_kernel(const __nv_bfloat16* __restrict__ g, const float* __restrict__ planes,
+                                    float* __restrict__ out, size_t P, int C, int HW, size_t img_stride,
+                                    size_t plane_stride, int nplanes, int pix_per_block) {
+  extern __shared__ float red[];  // [rows][4][C]
+  const int cv = C / 8;
+  const int rows = blockDim.x / cv;  // pixel lanes per block
+  const int tc = threadIdx.x % cv;
+  const int tr = threadIdx.x / cv;
+  float acc[4][8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
+  const size_t p0 = (size_t)blockIdx.x * pix_per_block;
+  size_t p1 = p0 + pix_per_block;
+  if (p1 > P) p1 = P;
+  if (tr < rows) {
+    for (size_t p = p0 + tr; p < p1; p += rows) {
+      const F8 v = ld8(g + p * C + tc * 8);
+      float s[3] = {0.f, 0.f, 0.f};
+      if (nplanes > 0) {
+        const size_t b = (p / HW) * img_stride + (p % HW);
+        for (int j = 0; j < nplanes; ++j) s[j] = planes[b + j * plane_stride];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[0][j] += v.v[j];
+        acc[1][j] += v.v[j] * s[0];
+        acc[2][j] += v.v[j] * s[1];
+        acc[3][j] += v.v[j] * s[2];
+      }
+    }
+  }
+  const int nk = 1 + nplanes;
+  if (tr < rows) {
+    for (int k = 0; k < nk; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[((size_t)tr * 4 + k) * C + tc * 8 + j] = acc[k][j];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < nk * C; idx += blockDim.x) {
+    const int k = idx / C, c = idx % C;
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s += red[((size_t)r * 4 + k) * C + c];
+    atomicAdd(out + (size_t)k * C + c, s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3-plane NCHW fp32 image  <->  NHWC bf16 features through a (C x 3) matrix
+// ---------------------------------------------------------------------------------------------
+// out[p, c] = act( coef * sum_j img[n, j, hw] * Wm[c * ws_c + j * ws_j] + bias[c] )
+//   fromRGB forward (gan.py:351-355): Wm = weight (C,3,1,1) -> ws_c = 3, ws_j = 1, bias, act
+//   toRGB input-grad:                 Wm = weight (3,C,1,1) -> ws_c = 1, ws_j = C, no bias, no act
+__global__ void planes3_to_nhwc_kernel(const float* __restrict__ img, const float* __restrict__ Wm,
+                                       const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, size_t P,
+                                       int HW, int C, int ws_c, int ws_j, float coef, int act, float slope) {
+  extern __shared__ float sw[];  // [C][3] + [C]
+  for (int i = threadIdx.x; i < C * 3; i += blockDim.x) {
+    const int c = i / 3, j = i % 3;
+    sw[i] = Wm[(size_t)c * ws_c + (size_t)j * ws_j] * coef;
+  }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sw[C * 3 + i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int cv = C / 8;
+  const size_t total = P * cv;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * 8;
+    const size_t p = i / cv;
+    const size_t b = (p / HW) * (size_t)(3 * HW) + (p % HW);
+    const float i0 = img[b], i1 = img[b + HW], i2 = img[b + 2 * (size_t)HW];
+    F8 r;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float* w = sw + (c + j) * 3;
+      float v = i0 * w[0] + i1 * w[1] + i2 * w[2] + sw[C * 3 + c + j];
+      if (act) v = v > 0.f ? v : v * slope;
+      r.v[j] = v;
+    }
+    st8(out + p * C + c, r);
+  }
+}
+
+// out[n, j, hw] = coef * sum_c x[p, c] * Wm[c * ws_c + j * ws_j] + bias[j]
+//   toRGB forward (gan.py:172-179,218,222): Wm = weight (3,C,1,1) -> ws_c = 1, ws_j = C, bias
+//   fromRGB input-grad:                     Wm = weight (C,3,1,1) -> ws_c = 3, ws_j = 1, no bias
+// One warp per pixel group: lanes split the channel vectors, shuffle-reduce the 3 dot products.
+__global__ void nhwc_to_planes3_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ Wm,
+                                       const float* __restrict__ bias, float* __restrict__ out, size_t P, int HW,
+                                       int C, int ws_c, int ws_j, float coef) {
+  extern __shared__ float sw[];  // [3][C]
+  for (int i = threadIdx.x; i < C * 3; i += blockDim.x) {
+    const int j = i / C, c = i % C;
+    sw[i] = Wm[(size_t)c * ws_c + (size_t)j * ws_j] * coef;
+  }
+  __syncthreads();
+  const int cv = C / 8;
+  const int lanes_per_pix = cv < 32 ? cv : 32;   // 2,4,8,16,32
+  const int pix_per_warp = 32 / lanes_per_pix;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % lanes_per_pix;
+  const int pw = lane / lanes_per_pix;
+  const size_t warp_global = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const size_t groups = (P + pix_per_warp - 1) / pix_per_warp;
+  const float b0 = bias ? bias[0] : 0.f, b1 = bias ? bias[1] : 0.f, b2 = bias ? bias[2] : 0.f;
+  for (size_t gidx = warp_global; gidx < groups; gidx += nwarps) {
+    const size_t p = gidx * pix_per_warp + pw;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    if (p < P) {
+      for (int v = sub; v < cv; v += lanes_per_pix) {
+        const F8 a = ld8(x + p * C + v * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = v * 8 + j;
+          s0 += a.v[j] * sw[c];
+          s1 += a.v[j] * sw[C + c];
+          s2 += a.v[j] * sw[2 * C + c];
+        }
+      }
+    }
+    for (int o = lanes_per_pix >> 1; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (p < P && sub == 0) {
+      const size_t b = (p / HW) * (size_t)(3 * HW) + (p % HW);
+      out[b] = s0 + b0;
+      out[b + HW] = s1 + b1;
+      out[b + 2 * (size_t)HW] = s2 + b2;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// instance norm + AdaIN (gan.py:55-71): statistics, apply, and backward
+// ---------------------------------------------------------------------------------------------
+// sums[n][c][0] += sum_hw a (* b if b given);  sums[n][c][1] += sum_hw a*a   (mode 0: statistics)
+// mode 1 (backward): sums[n][c][0] += sum g, sums[n][c][1] += sum g * ahat, ahat = (a - mean) * rstd
+__global__ void in_reduce_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ g,
+                                 const float* __restrict__ stats, float* __restrict__ sums, int HW, int C,
+                                 int pix_per_block, int blocks_per_img, float eps, int mode) {
+  extern __shared__ float red[];  // [rows][2][C]
+  const int n = blockIdx.x / blocks_per_img;
+  const int chunk = blockIdx.x % blocks_per_img;
+  const int cv = C / 8;
+  const int rows = blockDim.x / cv;
+  const int tc = threadIdx.x % cv;
+  const int tr = threadIdx.x / cv;
+  float s1[8], s2[8], mean[8], rstd[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  if (mode == 1 && tr < rows) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float* st = stats + ((size_t)n * C + tc * 8 + j) * 2;
+      const float m = st[0] / HW;
+      const float var = fmaxf(st[1] / HW - m * m, 0.f);
+      mean[j] = m;
+      rstd[j] = rsqrtf(var + eps);
+    }
+  }
+  const int p0 = chunk * pix_per_block;
+  const int p1 = min(p0 + pix_per_block, HW);
+  if (tr < rows) {
+    for (int p = p0 + tr; p < p1; p += rows) {
+      const size_t off = ((size_t)n * HW + p) * C + tc * 8;
+      const F8 av = ld8(a + off);
+      if (mode == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s1[j] += av.v[j];
+          s2[j] += av.v[j] * av.v[j];
+        }
+      } else {
+        const F8 gv = ld8(g + off);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s1[j] += gv.v[j];
+          s2[j] += gv.v[j] * (av.v[j] - mean[j]) * rstd[j];
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      red[((size_t)tr * 2 + 0) * C + tc * 8 + j] = s1[j];
+      red[((size_t)tr * 2 + 1) * C + tc * 8 + j] = s2[j];
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 2 * C; idx += blockDim.x) {
+    const int k = idx / C, c = idx % C;
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s += red[((size_t)r * 2 + k) * C + c];
+    atomicAdd(sums + ((size_t)n * C + c) * 2 + k, s);
+  }
+}
+
+// x = gamma * (a - mean) * rstd + beta;   style = [gamma (C) | beta (C)] per sample (gan.py:66-69)
+__global__ void adain_apply_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ stats,
+                                   const float* __restrict__ style, __nv_bfloat16* __restrict__ x, int N, int HW,
+                                   int C, float eps) {
+  const int cv = C / 8;
+  const size_t total = (size_t)N * HW * cv;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * 8;
+    const size_t p = i / cv;
+    const int n = (int)(p / HW);
+    F8 v = ld8(a + p * C + c);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float* st = stats + ((size_t)n * C + c + j) * 2;
+      const float m = st[0] / HW;
+      const float var = fmaxf(st[1] / HW - m * m, 0.f);
+      const float r = rsqrtf(var + eps);
+      const float ga = style[(size_t)n * 2 * C + c + j];
+      const float be = style[(size_t)n * 2 * C + C + c + j];
+      v.v[j] = ga * (v.v[j] - m) * r + be;
+    }
+    st8(x + p * C + c, v);
+  }
+}
+
+// gpre = gate(a) * gamma * rstd * (g - S1/HW - ahat * S2/HW)   (instance-norm backward + LeakyReLU gate)
+__global__ void adain_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ a,
+                                       const float* __restrict__ stats, const float* __restrict__ style,
+                                       const float* __restrict__ bsums, __nv_bfloat16* __restrict__ out, int N,
+                                       int HW, int C, float eps, float slope, int gate) {
+  const int cv = C / 8;
+  const size_t total = (size_t)N * HW * cv;
+  const float inv = 1.f / HW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * 8;
+    const size_t p = i / cv;
+    const int n = (int)(p / HW);
+    const F8 av = ld8(a + p * C + c);
+    const F8 gv = ld8(g + p * C + c);
+    F8 r;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const size_t sc = ((size_t)n * C + c + j) * 2;
+      const float m = stats[sc] * inv;
+      const float var = fmaxf(stats[sc + 1] * inv - m * m, 0.f);
+      const float rs = rsqrtf(var + eps);
+      const float ga = style[(size_t)n * 2 * C + c + j];
+      const float ah = (av.v[j] - m) * rs;
+      float v = ga * rs * (gv.v[j] - bsums[sc] * inv - ah * bsums[sc + 1] * inv);
+      if (gate) v *= av.v[j] > 0.f ? 1.f : slope;
+      r.v[j] = v;
+    }
+    st8(out + p * C + c, r);
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+int launch_pack_weight(const float* w, void* wf, void* wd, int Cout, int Cin, int Cin_pad, int ks, float coef,
+                       cudaStream_t s) {
+  BG_REQUIRE(ks == 1 || ks == 3, "pack_weight: ks must be 1 or 3");
+  BG_REQUIRE(Cin_pad >= Cin, "pack_weight: Cin_pad < Cin");
+  const size_t total = (size_t)ks * ks * Cout * Cin_pad;
+  pack_weight_kernel<<<grid_for(total), kBlock, 0, s>>>(w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wd, Cout, Cin, Cin_pad,
+                                                       ks, coef);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_unpack_wgrad(const float* dwp, float* dw, int Cout, int Cin, int Cin_pad, int ks, float coef,
+                        int accumulate, cudaStream_t s) {
+  const size_t total = (size_t)ks * ks * Cout * Cin;
+  unpack_wgrad_kernel<<<grid_for(total), kBlock, 0, s>>>(dwp, dw, Cout, Cin, Cin_pad, ks, coef, accumulate);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_act_gate(const void* g, const void* y, void* out, size_t n, float slope, cudaStream_t s) {
+  BG_REQUIRE(n % 8 == 0, "act_gate: element count must be a multiple of 8");
+  act_gate_kernel<<<grid_for(n / 8), kBlock, 0, s>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)y,
+                                                    (__nv_bfloat16*)out, n / 8, slope);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_axpby(const void* a, const void* b, void* out, size_t n, float ca, float cb, cudaStream_t s) {
+  BG_REQUIRE(n % 8 == 0, "axpby: element count must be a multiple of 8");
+  axpby_kernel<<<grid_for(n / 8), kBlock, 0, s>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b,
+                                                 (__nv_bfloat16*)out, n / 8, ca, cb);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_pool_act_fwd(const void* u, const void* gate_src, void* y, int N, int Ho, int Wo, int C, float slope,
+                        int mode, cudaStream_t s) {
+  BG_REQUIRE(C % 8 == 0, "pool_act_fwd: C must be a multiple of 8");
+  BG_REQUIRE(mode == 0 || gate_src != nullptr, "pool_act_fwd: mode 1 needs gate_src");
+  const size_t total = (size_t)N * Ho * Wo * (C / 8);
+  pool_act_fwd_kernel<<<grid_for(total), kBlock, 0, s>>>((const __nv_bfloat16*)u, (const __nv_bfloat16*)gate_src,
+                                                        (__nv_bfloat16*)y, N, Ho, Wo, C, slope, mode);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_pool_act_bwd(const void* gy, const void* y, void* gu, int N, int Ho, int Wo, int C, float slope,
+                        cudaStream_t s) {
+  BG_REQUIRE(C % 8 == 0, "pool_act_bwd: C must be a multiple of 8");
+  const size_t total = (size_t)N * Ho * Wo * (C / 8);
+  pool_act_bwd_kernel<<<grid_for(total), kBlock, 0, s>>>((const __nv_bfloat16*)gy, (const __nv_bfloat16*)y,
+                                                        (__nv_bfloat16*)gu, N, Ho, Wo, C, slope);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_upsample2x_fwd(const void* x, void* y, int N, int H, int W, int C, cudaStream_t s) {
+  BG_REQUIRE(C % 8 == 0, "upsample2x_fwd: C must be a multiple of 8");
+  const size_t total = (size_t)N * H * W * 4 * (C / 8);
+  upsample2x_fwd_kernel<<<grid_for(total), kBlock, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_upsample2x_bwd(const void* gy, void* gx, int N, int H, int W, int C, cudaStream_t s) {
+  BG_REQUIRE(C % 8 == 0, "upsample2x_bwd: C must be a multiple of 8");
+  const size_t total = (size_t)N * H * W * (C / 8);
+  upsample2x_bwd_kernel<<<grid_for(total), kBlock, 0, s>>>((const __nv_bfloat16*)gy, (__nv_bfloat16*)gx, N, H, W, C);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_channel_wsum(const void* g, const float* planes, float* out, size_t P, int C, int HW, size_t img_stride,
+                        size_t plane_stride, int nplanes, cudaStream_t s) {
+  BG_REQUIRE(C % 8 == 0 && C <= 1024, "channel_wsum: unsupported C %d", C);
+  BG_REQUIRE(nplanes >= 0 && nplanes <= 3, "channel_wsum: nplanes must be 0..3");
+  const int cv = C / 8;
+  const int threads = cv >= 256 ? cv : 256;
+  const int rows = threads / cv;
+  BG_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)(1 + nplanes) * C * sizeof(float), s));
+  // enough blocks to fill the chip, but at least `rows * 8` pixels each
+  size_t ppb = (P + (size_t)num_sms() * 4 - 1) / ((size_t)num_sms() * 4);
+  if (ppb < (size_t)rows * 8) ppb = (size_t)rows * 8;
+  const size_t blocks = (P + ppb - 1) / ppb;
+  const size_t smem = (size_t)rows * 4 * C * sizeof(float);
+  BG_REQUIRE(smem <= 48 * 1024, "channel_wsum: shared memory %zu too large", smem);
+  channel_wsum_kernel<<<(int)blocks, threads, smem, s>>>((const __nv_bfloat16*)g, planes, out, P, C, HW, img_stride,
+                                                        plane_stride, nplanes, (int)ppb);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_planes3_to_nhwc(const float* img, const float* Wm, const float* bias, void* out, size_t P, int HW, int C,
+                           int ws_c, int ws_j, float coef, int act, float slope, cudaStream_t s) {
+  BG_REQUIRE(C % 8 == 0 && C <= 1024, "planes3_to_nhwc: unsupported C %d", C);
+  const size_t total = P * (C / 8);
+  planes3_to_nhwc_kernel<<<grid_for(total), kBlock, (size_t)C * 4 * sizeof(float), s>>>(
+      img, Wm, bias, (__nv_bfloat16*)out, P, HW, C, ws_c, ws_j, coef, act, slope);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_nhwc_to_planes3(const void* x, const float* Wm, const float* bias, float* out, size_t P, int HW, int C,
+                           int ws_c, int ws_j, float coef, cudaStream_t s) {
+  BG_REQUIRE(C % 16 == 0 && C <= 1024, "nhwc_to_planes3: unsupported C %d", C);
+  const int cv = C / 8;
+  const int lanes_per_pix = cv < 32 ? cv : 32;
+  const size_t groups = (P + (32 / lanes_per_pix) - 1) / (32 / lanes_per_pix);
+  nhwc_to_planes3_kernel<<<grid_for(groups * 32), kBlock, (size_t)C * 3 * sizeof(float), s>>>(
+      (const __nv_bfloat16*)x, Wm, bias, out, P, HW, C, ws_c, ws_j, coef);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int in_reduce_launch(const void* a, const void* g, const float* stats, float* sums, int N, int HW, int C,
+                            float eps, int mode, cudaStream_t s) {
+  BG_REQUIRE(C % 8 == 0 && C <= 1024, "in_reduce: unsupported C %d", C);
+  const int cv = C / 8;
+  const int threads = cv >= 256 ? cv : 256;
+  const int rows = threads / cv;
+  BG_CHECK_CUDA(cudaMemsetAsync(sums, 0, (size_t)N * C * 2 * sizeof(float), s));
+  int blocks_per_img = (num_sms() * 4 + N - 1) / N;
+  int max_bpi = (HW + rows * 4 - 1) / (rows * 4);
+  if (blocks_per_img > max_bpi) blocks_per_img = max_bpi;
+  if (blocks_per_img < 1) blocks_per_img = 1;
+  const int ppb = (HW + blocks_per_img - 1) / blocks_per_img;
+  blocks_per_img = (HW + ppb - 1) / ppb;
+  const size_t smem = (size_t)rows * 2 * C * sizeof(float);
+  BG_REQUIRE(smem <= 48 * 1024, "in_reduce: shared memory %zu too large", smem);
+  in_reduce_kernel<<<N * blocks_per_img, threads, smem, s>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)g, stats,
+                                                            sums, HW, C, ppb, blocks_per_img, eps, mode);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_in_stats(const void* a, float* sums, int N, int HW, int C, cudaStream_t s) {
+  return in_reduce_launch(a, nullptr, nullptr, sums, N, HW, C, 0.f, 0, s);
+}
+
+int launch_adain_bwd_reduce(const void* g, const void* a, const float* stats, float* bsums, int N, int HW, int C,
+                            float eps, cudaStream_t s) {
+  return in_reduce_launch(a, g, stats, bsums, N, HW, C, eps, 1, s);
+}
+
+int launch_adain_apply(const void* a, const float* stats, const float* style, void* x, int N, int HW, int C, float eps,
+                       cudaStream_t s) {
+  BG_REQUIRE(C % 8 == 0, "adain_apply: C must be a multiple of 8");
+  const size_t total = (size_t)N * HW * (C / 8);
+  adain_apply_kernel<<<grid_for(total), kBlock, 0, s>>>((const __nv_bfloat16*)a, stats, style, (__nv_bfloat16*)x, N, HW,
+                                                       C, eps);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_adain_bwd_apply(const void* g, const void* a, const float* stats, const float* style, const float* bsums,
+                           void* out, int N, int HW, int C, float eps, float slope, int gate, cudaStream_t s) {
+  BG_REQUIRE(C % 8 == 0, "adain_bwd_apply: C must be a multiple of 8");
+  const size_t total = (size_t)N * HW * (C / 8);
+  adain_bwd_apply_kernel<<<grid_for(total), kBlock, 0, s>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)a, stats,
+                                                           style, bsums, (__nv_bfloat16*)out, N, HW, C, eps, slope,
+                                                           gate);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace bg

@@ -1,0 +1,104 @@
+/*
+ * bg_b200.h — C ABI of the B200-native StyleGAN hot path behind BYO-GAN's gan.py interface.
+ *
+ * The reference has no FFI layer: its hot path is torch library calls inside gan.py.  Each entry point
+ * below replaces one such call site (cited as gan.py:line) with a hand-written sm_100a kernel.  The
+ * Python host (byo-gan_b200/gan.py) binds these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise;
+ *   - the caller owns every buffer (including workspaces); nothing is allocated or freed here;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - feature maps are NHWC bf16 (C multiple of 16 for convolutions, 8 elsewhere);
+ *     images at the module boundary are NCHW fp32 as the reference passes them;
+ *   - return 0 on success, non-zero on error; bg_last_error() returns a thread-local message;
+ *   - re-entrant: no global mutable state besides per-device attribute caches.
+ */
+#ifndef BG_B200_H_
+#define BG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* bg_last_error(void);
+int bg_abi_version(void);
+
+/* ---- equalized-lr weight staging (gan.py:14,27,32: weight * sqrt(2/fan_in) every forward) -------------
+ * w: fp32 (Cout,Cin,ks,ks).  w_fprop: bf16 [ks*ks][Cout][Cin_pad] or NULL.
+ * w_dgrad: bf16 [ks*ks flipped][Cin_pad][Cout] or NULL (same forward kernel then computes dL/dx). */
+int bg_pack_weight(const float* w, void* w_fprop, void* w_dgrad, int Cout, int Cin, int Cin_pad, int ks, float coef,
+                   void* stream);
+/* dw_packed: fp32 [ks*ks][Cout][Cin_pad] -> dw: fp32 (Cout,Cin,ks,ks) * coef (+= if accumulate). */
+int bg_unpack_wgrad(const float* dw_packed, float* dw, int Cout, int Cin, int Cin_pad, int ks, float coef,
+                    int accumulate, void* stream);
+
+/* ---- EqualizedConv2d.forward, 3x3 pad 1 / 1x1 (gan.py:29-38 via :83,:240,:254,:259) ------------------
+ * tcgen05 implicit GEMM.  out = gate(act(conv(x, wpack) + bias + noise_w[c] * noise[n,h,w]))
+ *   bias, noise, noise_w, gate_src may be NULL.  noise: fp32 (N,1,H,W) (InjectSecondaryNoise, gan.py:52).
+ *   act: 0 none, 1 LeakyReLU(slope) (gan.py:86,241,255).  gate_src: bf16 (N,H,W,Cout); the output is
+ *   multiplied by (gate_src > 0 ? 1 : slope) — the LeakyReLU backward gate fused into a dgrad pass.
+ * Run with w_dgrad as wpack (Cin/Cout swapped) this is autograd's conv input-gradient. */
+int bg_conv_fprop(const void* x, const void* wpack, void* out, int N, int H, int W, int Cin, int Cout, int ksize,
+                  const float* bias, const float* noise, const float* noise_w, const void* gate_src, int act,
+                  float slope, void* stream);
+
+/* ---- weight gradient of the 3x3 conv (autograd convolution_backward / _convolution_double_backward) ---
+ * dw_packed: fp32 [9][Cout][Cin] (overwritten) = sum_pixels g[p,co] * x[p+tap,ci]. */
+int bg_conv_wgrad(const void* x, const void* g, float* dw_packed, int N, int H, int W, int Cin, int Cout,
+                  void* stream);
+
+/* ---- LeakyReLU backward gate (gan.py:86,145,241...): out = g * (y > 0 ? 1 : slope); n elements -------- */
+int bg_act_gate(const void* g, const void* y, void* out, size_t n, float slope, void* stream);
+/* ---- out = ca*a + cb*b (b may be NULL): torch.lerp on feature maps (gan.py:347) and its gradients ----- */
+int bg_axpby(const void* a, const void* b, void* out, size_t n, float ca, float cb, void* stream);
+
+/* ---- AvgPool2d(2) -> LeakyReLU (CriticBlock tail, gan.py:258-262) --------------------------------------
+ * fwd mode 0: y = lrelu(avg4(u)); mode 1: y = avg4(u) * gate(gate_src) (tangent of the backward).
+ * bwd: gu = 0.25 * gate(y) * gy broadcast to the 2x2 window.  u,gu: (N,2Ho,2Wo,C); y,gy: (N,Ho,Wo,C). */
+int bg_pool_act_fwd(const void* u, const void* gate_src, void* y, int N, int Ho, int Wo, int C, float slope,
+                    int mode, void* stream);
+int bg_pool_act_bwd(const void* gy, const void* y, void* gu, int N, int Ho, int Wo, int C, float slope,
+                    void* stream);
+
+/* ---- nn.Upsample(scale_factor=2, bilinear) (gan.py:112,123) and its adjoint; x: (N,H,W,C) -------------- */
+int bg_upsample2x_fwd(const void* x, void* y, int N, int H, int W, int C, void* stream);
+int bg_upsample2x_bwd(const void* gy, void* gx, int N, int H, int W, int C, void* stream);
+
+/* ---- per-channel weighted pixel sums (bias / noise-weight / fromRGB / toRGB weight gradients) ----------
+ * out: fp32 [(1+nplanes)][C] (overwritten): out[0][c] = sum_p g[p,c]; out[1+j][c] = sum_p g[p,c]*plane_j[p],
+ * plane_j[p] = planes[(p/HW)*img_stride + j*plane_stride + p%HW]. */
+int bg_channel_wsum(const void* g, const float* planes, float* out, size_t P, int C, int HW, size_t img_stride,
+                    size_t plane_stride, int nplanes, void* stream);
+
+/* ---- fromRGB / toRGB 1x1 convolutions (gan.py:172-179, 351-355) ----------------------------------------
+ * planes3_to_nhwc: out[p,c] = act(coef * sum_j img[n,j,hw] * Wm[c*ws_c + j*ws_j] + bias[c])
+ * nhwc_to_planes3: out[n,j,hw] = coef * sum_c x[p,c] * Wm[c*ws_c + j*ws_j] + bias[j]
+ * (weight (C,3,1,1): ws_c=3, ws_j=1;  weight (3,C,1,1): ws_c=1, ws_j=C) */
+int bg_planes3_to_nhwc(const float* img, const float* Wm, const float* bias, void* out, size_t P, int HW, int C,
+                       int ws_c, int ws_j, float coef, int act, float slope, void* stream);
+int bg_nhwc_to_planes3(const void* x, const float* Wm, const float* bias, float* out, size_t P, int HW, int C,
+                       int ws_c, int ws_j, float coef, void* stream);
+
+/* ---- AdaINBlock (gan.py:55-71): InstanceNorm2d(eps=1e-8, biased var) then gamma*x+beta -----------------
+ * stats: fp32 (N,C,2) = [sum a, sum a^2] over H*W (overwritten by bg_in_stats).
+ * style: fp32 (N,2C) = [gamma | beta] (output of the style EqualizedLinear, gan.py:66-67).
+ * bsums: fp32 (N,C,2) = [sum g, sum g*ahat] (these ARE dL/dbeta and dL/dgamma).
+ * bwd_apply: out = gate(a) * gamma*rstd*(g - bsums0/HW - ahat*bsums1/HW); gate!=0 fuses the LeakyReLU
+ * backward that precedes AdaIN in StyleConvBlock.forward (gan.py:96-98). */
+int bg_in_stats(const void* a, float* stats, int N, int HW, int C, void* stream);
+int bg_adain_apply(const void* a, const float* stats, const float* style, void* x, int N, int HW, int C, float eps,
+                   void* stream);
+int bg_adain_bwd_reduce(const void* g, const void* a, const float* stats, float* bsums, int N, int HW, int C,
+                        float eps, void* stream);
+int bg_adain_bwd_apply(const void* g, const void* a, const float* stats, const float* style, const float* bsums,
+                       void* out, int N, int HW, int C, float eps, float slope, int gate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* BG_B200_H_ */

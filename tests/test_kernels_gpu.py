@@ -1,0 +1,160 @@
+"""Kernel-level parity (GPU): every C-ABI entry point against a plain torch fp32 restatement of the
+reference op it replaces (gan.py line cited per test).  bf16 operands / fp32 accumulate, so the
+tolerance is stated per test: outputs are compared after rounding the *inputs* to bf16 exactly as the
+kernel sees them, leaving only accumulation-order and output-rounding differences.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+import bg_native as bgn  # noqa: E402
+
+DEV = "cuda"
+
+
+def nhwc(x):  # (N,C,H,W) fp32 -> (N,H,W,C) bf16 contiguous
+    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def nchw(x):  # (N,H,W,C) bf16 -> (N,C,H,W) fp32
+    return x.float().permute(0, 3, 1, 2).contiguous()
+
+
+def relerr(a, b):
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+def pack(w, coef, cin_pad=None):
+    co, ci, ks, _ = w.shape
+    cin_pad = cin_pad or ci
+    wf = torch.empty(ks * ks, co, cin_pad, dtype=torch.bfloat16, device=DEV)
+    wd = torch.empty(ks * ks, cin_pad, co, dtype=torch.bfloat16, device=DEV)
+    bgn.call("bg_pack_weight", w, wf, wd, co, ci, cin_pad, ks, float(coef))
+    return wf, wd
+
+
+CONV_SHAPES = [
+    # N, H, W, Cin, Cout
+    (2, 16, 16, 64, 64),
+    (3, 4, 4, 512, 512),
+    (8, 4, 4, 64, 128),
+    (5, 8, 8, 128, 256),
+    (2, 32, 32, 256, 128),
+    (1, 64, 64, 32, 32),
+    (1, 64, 64, 16, 32),
+    (2, 32, 32, 32, 16),
+    (1, 128, 128, 16, 16),
+    (2, 16, 16, 512, 256),
+    (1, 32, 32, 64, 48),
+]
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_pack_weight(shape):
+    _, _, _, ci, co = shape
+    torch.manual_seed(1)
+    w = torch.randn(co, ci, 3, 3, device=DEV)
+    coef = math.sqrt(2 / (ci * 9))
+    wf, wd = pack(w, coef)
+    ref = (w * coef).to(torch.bfloat16)
+    assert torch.equal(wf, ref.permute(2, 3, 0, 1).reshape(9, co, ci))
+    assert torch.equal(wd, ref.flip(2, 3).permute(2, 3, 1, 0).reshape(9, ci, co))
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+@pytest.mark.parametrize("fused", [False, True])
+def test_conv3x3_fprop(shape, fused):
+    """EqualizedConv2d.forward (gan.py:29-38) [+ InjectSecondaryNoise gan.py:52 + LeakyReLU gan.py:86]."""
+    n, h, w_, ci, co = shape
+    torch.manual_seed(0)
+    x = nhwc(torch.randn(n, ci, h, w_, device=DEV))
+    w = torch.randn(co, ci, 3, 3, device=DEV)
+    coef = math.sqrt(2 / (ci * 9))
+    wf, _ = pack(w, coef)
+    bias = torch.randn(co, device=DEV) * 0.1 if fused else None
+    noise = torch.randn(n, 1, h, w_, device=DEV) if fused else None
+    nw = torch.randn(co, device=DEV) * 0.1 if fused else None
+    out = torch.empty(n, h, w_, co, dtype=torch.bfloat16, device=DEV)
+    bgn.call("bg_conv_fprop", x, wf, out, n, h, w_, ci, co, 3, bias, noise, nw, None, 1 if fused else 0, 0.2)
+    torch.cuda.synchronize()
+    ref = F.conv2d(nchw(x), (w * coef).to(torch.bfloat16).float(), None, padding=1)
+    if fused:
+        ref = ref + bias.view(1, -1, 1, 1) + nw.view(1, -1, 1, 1) * noise
+        ref = F.leaky_relu(ref, 0.2)
+    err = relerr(nchw(out), ref)
+    assert err < 6e-3, f"conv3x3 fprop {shape} fused={fused}: rel-L2 {err:.3e}"
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64, 64), (1, 64, 64, 16, 32), (4, 8, 8, 256, 128), (2, 32, 32, 32, 16)])
+def test_conv3x3_dgrad_via_fprop(shape):
+    """autograd convolution_backward w.r.t. input == the forward kernel on the flipped/transposed pack."""
+    n, h, w_, ci, co = shape
+    torch.manual_seed(0)
+    g = nhwc(torch.randn(n, co, h, w_, device=DEV))
+    w = torch.randn(co, ci, 3, 3, device=DEV)
+    coef = math.sqrt(2 / (ci * 9))
+    _, wd = pack(w, coef)
+    gx = torch.empty(n, h, w_, ci, dtype=torch.bfloat16, device=DEV)
+    bgn.call("bg_conv_fprop", g, wd, gx, n, h, w_, co, ci, 3, None, None, None, None, 0, 0.2)
+    torch.cuda.synchronize()
+    wq = (w * coef).to(torch.bfloat16).float()
+    ref = torch.nn.grad.conv2d_input((n, ci, h, w_), wq, nchw(g), padding=1)
+    err = relerr(nchw(gx), ref)
+    assert err < 6e-3, f"dgrad {shape}: rel-L2 {err:.3e}"
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES[:-1])
+def test_conv3x3_wgrad(shape):
+    """autograd convolution_backward w.r.t. weight (and the weight half of the R1 double-backward)."""
+    n, h, w_, ci, co = shape
+    torch.manual_seed(0)
+    x = nhwc(torch.randn(n, ci, h, w_, device=DEV))
+    g = nhwc(torch.randn(n, co, h, w_, device=DEV))
+    dwp = torch.empty(9, co, ci, dtype=torch.float32, device=DEV)
+    bgn.call("bg_conv_wgrad", x, g, dwp, n, h, w_, ci, co)
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv2d_weight(nchw(x), (co, ci, 3, 3), nchw(g), padding=1)
+    got = dwp.reshape(3, 3, co, ci).permute(2, 3, 0, 1)
+    err = relerr(got, ref)
+    assert err < 2e-3, f"wgrad {shape}: rel-L2 {err:.3e}"
+
+
+def test_upsample_pool_adain_aux():
+    """nn.Upsample bilinear x2 (gan.py:112), AvgPool2d+LeakyReLU (gan.py:260-261), AdaIN (gan.py:65-71)."""
+    torch.manual_seed(0)
+    n, c, h, w_ = 3, 32, 8, 8
+    xf = torch.randn(n, c, h, w_, device=DEV)
+    x = nhwc(xf)
+    y = torch.empty(n, 2 * h, 2 * w_, c, dtype=torch.bfloat16, device=DEV)
+    bgn.call("bg_upsample2x_fwd", x, y, n, h, w_, c)
+    ref = F.interpolate(nchw(x), scale_factor=2, mode="bilinear")
+    assert relerr(nchw(y), ref) < 4e-3
+    # adjoint
+    gy = nhwc(torch.randn(n, c, 2 * h, 2 * w_, device=DEV))
+    gx = torch.empty(n, h, w_, c, dtype=torch.bfloat16, device=DEV)
+    bgn.call("bg_upsample2x_bwd", gy, gx, n, h, w_, c)
+    xr = nchw(x).requires_grad_()
+    F.interpolate(xr, scale_factor=2, mode="bilinear").backward(nchw(gy))
+    assert relerr(nchw(gx), xr.grad) < 4e-3
+    # pool + lrelu
+    u = nhwc(torch.randn(n, c, 2 * h, 2 * w_, device=DEV))
+    yo = torch.empty(n, h, w_, c, dtype=torch.bfloat16, device=DEV)
+    bgn.call("bg_pool_act_fwd", u, None, yo, n, h, w_, c, 0.2, 0)
+    ref = F.leaky_relu(F.avg_pool2d(nchw(u), 2), 0.2)
+    assert relerr(nchw(yo), ref) < 4e-3
+    # instance-norm statistics + AdaIN apply
+    stats = torch.empty(n, c, 2, device=DEV)
+    a = nhwc(torch.randn(n, c, h, w_, device=DEV) * 2 + 0.5)
+    bgn.call("bg_in_stats", a, stats, n, h * w_, c)
+    af = nchw(a)
+    assert torch.allclose(stats[..., 0], af.sum((2, 3)), rtol=1e-4, atol=1e-3)
+    assert torch.allclose(stats[..., 1], (af * af).sum((2, 3)), rtol=1e-4, atol=1e-3)
+    style = torch.randn(n, 2 * c, device=DEV)
+    xo = torch.empty_like(a)
+    bgn.call("bg_adain_apply", a, stats, style, xo, n, h * w_, c, 1e-8)
+    ref = style[:, :c, None, None] * F.instance_norm(af, eps=1e-8) + style[:, c:, None, None]
+    assert relerr(nchw(xo), ref) < 5e-3
