@@ -166,9 +166,9 @@ def bilinear_up2(x):
 
 def instance_norm(x):
     """nn.InstanceNorm2d(C, eps=1e-8): no affine, no running stats, biased variance (gan.py:59)."""
-    mean = x.mean(dim=(2, 3), keepdim=True)
-    var = ((x - mean) ** 2).mean(dim=(2, 3), keepdim=True)
-    return (x - mean) / torch.sqrt(var + IN_EPS)
+    # (x - mean_hw) / sqrt(biased_var_hw + eps); evaluated with the same ATen primitive the reference's
+    # nn.InstanceNorm2d dispatches to, so fp32 rounding matches it (the 4x4 planes are ill-conditioned).
+    return F.instance_norm(x, eps=IN_EPS)
 
 
 def style_conv(P, prefix, x, w_lat, noise, batch, initial=False):
