@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""Benchmark of the BYO-GAN hot path on B200: G+D training iterations at 256x256 (BASELINE.json configs[2]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload train256|...]
+
+One "step" is one full reference iteration (train.py:135-219): critic step with the R1 gradient penalty
+(double-backward) and its Adam update, then generator step and its Adam update, driven through the public
+drop-in API of byo-gan_b200/gan.py.  Prints ONE JSON line (see the task contract): `value` is img/s with inputs
+resident in HBM, `e2e` the same iteration fed from pinned HOST buffers with the losses read back every step,
+`roofline` the tcgen05 implicit-GEMM conv kernel against the measured bf16 peak, `cpu_baseline` the oracle
+port of the reference timed on this box's host cores on a bounded sample.
+
+--impl reference runs only that CPU leg (the reference is pure PyTorch; /root/reference is not on the GPU box,
+so its arithmetic is timed through oracle/gan_oracle.py, which is pinned to the real gan.py by tests/golden).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "byo-gan_b200"))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+# step FLOPs per image in the reference's formulation: 4*G_fwd + 11*D_fwd
+WORKLOADS = {
+    # name: (steps, alpha, per-GPU batch, GFLOP/img/iteration, description)
+    "train64": (5, 0.5, 64, 235.09, "64x64 stage with fade-in alpha=0.5, batch 64 (BASELINE configs[1])"),
+    "train256": (7, None, 32, 423.65, "256x256 stage, batch 32 per GPU, R1 every step (BASELINE configs[2])"),
+    "train512": (8, None, 16, 518.06, "512x512 stage, batch 16 per GPU, R1 every step (BASELINE configs[3])"),
+}
+LAMBDA = 10.0          # config.txt gradient_lambda
+LR, BETAS = 0.002, (0.0, 0.99)   # config.txt lr / beta_1 / beta_2
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm": p["hbm_gbs"], "tf_burst": p["bf16_tflops"], "tf_sustained": p["bf16_tflops_sustained"],
+                "src": "measured (MEASURED_PEAKS.json)"}
+    except Exception:
+        return {"hbm": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# the B200 arm
+# ------------------------------------------------------------------------------------------------------
+class Trainer:
+    """train.py:58-80 (models + the two Adam optimizers) and one iteration of train.py:135-219."""
+
+    def __init__(self, steps, alpha, batch, device, sync_cls):
+        import gan
+        import dist as bdist
+
+        torch.manual_seed(0)
+        self.gen, self.critic = gan.Generator().to(device), gan.Critic().to(device)
+        # reference init leaves biases / noise weights at zero; give them small values so no path is dead
+        with torch.no_grad():
+            for n, p in list(self.gen.named_parameters()) + list(self.critic.named_parameters()):
+                if n.endswith("bias") or n.endswith("inject_noise.weights"):
+                    p.add_(0.05 * torch.randn_like(p))
+        bdist.broadcast_parameters(self.gen)
+        bdist.broadcast_parameters(self.critic)
+        g = self.gen
+        self.gen_opt = torch.optim.Adam([{"params": g.to_w_noise.parameters(), "lr": LR * 0.01},
+                                         {"params": g.gen_blocks.parameters()}, {"params": g.to_rgbs.parameters()}],
+                                        lr=LR, betas=BETAS)
+        self.critic_opt = torch.optim.Adam(self.critic.parameters(), lr=LR, betas=BETAS)
+        self.steps, self.alpha, self.batch, self.device = steps, alpha, batch, device
+        self.sync = sync_cls()
+        self.critic._grad_ready_hook = self.sync.ready
+
+    @staticmethod
+    def _set_requires_grad(model, flag):                     # helper.py:48-50
+        for p in model.parameters():
+            p.requires_grad = flag
+
+    def iteration(self, real, z_d, z_g, read_losses):
+        gen, critic, steps, alpha = self.gen, self.critic, self.steps, self.alpha
+        # ---- critic step (train.py:135-191)
+        self._set_requires_grad(critic, True)
+        self._set_requires_grad(gen, False)
+        z = z_d.requires_grad_()
+        fake = gen(z, steps=steps, alpha=alpha)
+        real_im = real.requires_grad_()
+        pf = critic(fake.detach(), steps, alpha)
+        pr = critic(real_im, steps, alpha)
+        critic.zero_grad()
+        self.sync.begin()
+        c_loss = critic.get_r1_loss(pf, pr, real_im, fake, steps, alpha, LAMBDA)
+        self.sync.finish()
+        self.critic_opt.step()
+        c_val = c_loss.item() if read_losses else None
+        # ---- generator step (train.py:193-219)
+        self._set_requires_grad(critic, False)
+        self._set_requires_grad(gen, True)
+        z2 = z_g.requires_grad_()
+        fake2 = gen(z2, steps=steps, alpha=alpha)
+        pred = critic(fake2, steps, alpha)
+        g_loss = gen.get_r1_loss(pred)
+        gen.zero_grad()
+        self.sync.begin()
+        g_loss.backward()
+        self.sync.ready_all(p for p in gen.parameters() if p.grad is not None)
+        self.sync.finish()
+        self.gen_opt.step()
+        g_val = g_loss.item() if read_losses else None
+        return c_val, g_val
+
+
+def conv_flops(args):
+    # bg_conv_fprop scalar args: N,H,W,Cin,Cout,ksize,act,slope ; bg_conv_wgrad: N,H,W,Cin,Cout,accumulate
+    n, h, w, ci, co = args[:5]
+    ks = args[5] if len(args) >= 8 else 3
+    return 2.0 * n * h * w * ks * ks * ci * co
+
+
+def run_b200(args):
+    import bg_native as bgn
+    import dist as bdist
+
+    rank, world, local = bdist.init_from_env()
+    if args.gpus != world:
+        if rank == 0 and world > 1:
+            print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    steps, alpha, batch, gflop_img, desc = WORKLOADS[args.workload]
+    if args.batch:
+        batch = args.batch
+    R = 4 * 2 ** (steps - 1)
+    tr = Trainer(steps, alpha, batch, device, bdist.GradSync)
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    POOL = 4
+    host_real = [torch.rand(batch, 3, R, R, generator=g).mul_(2).sub_(1).pin_memory() for _ in range(POOL)]
+    host_z = [torch.randn(2, batch, 512, generator=g).clamp_(-0.75, 0.75).pin_memory() for _ in range(POOL)]
+    dev_real = [t.to(device) for t in host_real]
+    dev_z = [t.to(device) for t in host_z]
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n_steps, from_host):
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for i in range(n_steps):
+            j = i % POOL
+            if from_host:
+                real = host_real[j].to(device, non_blocking=True)
+                zz = host_z[j].to(device, non_blocking=True)
+                tr.iteration(real, zz[0], zz[1], read_losses=True)
+            else:
+                tr.iteration(dev_real[j].clone(), dev_z[j][0].clone(), dev_z[j][1].clone(), read_losses=False)
+        t1.record()
+        barrier()
+        ms = torch.tensor([t0.elapsed_time(t1)], device=device)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return ms.item()
+
+    timed(args.warmup, from_host=False)                      # warm-up (also builds the weight packs)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    n0 = bgn.launch_count
+    ms = timed(args.steps, from_host=False)
+    launches = bgn.launch_count - n0
+    clk = clocks.stop() if rank == 0 else None
+    timed(1, from_host=True)
+    ms_e2e = timed(args.steps, from_host=True)
+    imgs = batch * world * args.steps
+    value = imgs / (ms / 1e3)
+    e2e_value = imgs / (ms_e2e / 1e3)
+
+    # ---- roofline leg: CUDA-event pair around every C-ABI call of one more iteration (rank 0's numbers)
+    peaks = load_peaks()
+    barrier()
+    bgn.start_timing()
+    tr.iteration(dev_real[0].clone(), dev_z[0][0].clone(), dev_z[0][1].clone(), read_losses=False)
+    rec = bgn.stop_timing()
+    fam = {}
+    for name, a, t in rec:
+        f = fam.setdefault(name, [0, 0.0, 0.0])
+        f[0] += 1
+        f[1] += t
+        if name in ("bg_conv_fprop", "bg_conv_wgrad"):
+            f[2] += conv_flops(a)
+    tot_ms = sum(v[1] for v in fam.values())
+    dom = fam.get("bg_conv_fprop", [0, 1e-9, 0.0])
+    achieved = dom[2] / (dom[1] / 1e3) / 1e12 if dom[0] else 0.0
+    shares = {k: round(v[1] / tot_ms, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1][1])[:8]}
+    roofline = {"kernel": "conv_fprop_kernel (tcgen05 implicit GEMM: fprop, dgrad, R1 tangent pass)", "bound": "tensor",
+                "achieved": round(achieved, 1), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                "frac": round(achieved / peaks["tf_sustained"], 4), "traffic": None,
+                "peak_source": peaks["src"] + ", sustained bf16 (kernel timed inside a long step)",
+                "launches_per_step": dom[0], "share_of_step": shares.get("bg_conv_fprop"),
+                "wgrad_tflops": round(fam["bg_conv_wgrad"][2] / (fam["bg_conv_wgrad"][1] / 1e3) / 1e12, 1)
+                if "bg_conv_wgrad" in fam else None,
+                "step_share_by_call": shares,
+                "step_model_flops_frac": round(value / world * gflop_img * 1e9 / (peaks["tf_sustained"] * 1e12), 4)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_leg(args.workload, max_seconds=40.0, steps_cap=1)
+
+    if rank == 0:
+        h2d = host_real[0].numel() * 4 + host_z[0].numel() * 4
+        line = {
+            "metric": "G+D train img/s at 256x256" if args.workload == "train256" else f"G+D train img/s ({args.workload})",
+            "value": round(value, 2), "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "resolution": R, "progressive_steps": steps, "alpha": alpha,
+                       "batch_per_gpu": batch, "global_batch": batch * world, "parallelism": f"dp{world}",
+                       "optimizer": "Adam(lr=0.002, betas=(0,0.99)), both updates inside the step",
+                       "loss": "non-saturating logistic + R1 (lambda=10) with double-backward every step",
+                       "l2_policy": "inputs rotate over 4 batches; per-step working set (GBs of activations) >> 126 MB L2"},
+            "clocks": clk,
+            "e2e": {"value": round(e2e_value, 2), "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+                    "ms_per_step": round(ms_e2e / args.steps, 3)},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "grad_allreduce_bytes_per_step": tr.sync.bytes_reduced // max(1, args.steps * 2 + args.warmup + 2) if world > 1 else 0,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------------
+# the CPU leg (oracle port of the reference on the host cores)
+# ------------------------------------------------------------------------------------------------------
+def cpu_leg(workload, max_seconds, steps_cap, warmup=0):
+    from oracle import gan_oracle as O
+
+    steps, alpha, _, gflop_img, _ = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    batch = 4                                   # smallest batch the minibatch-stddev groups allow (gan.py:269)
+    G, D = O.make_state("gen", 0), O.make_state("critic", 0)
+    done, t_total = 0, 0.0
+    for i in range(warmup + steps_cap):
+        args = (O.make_latents(batch, i), O.make_latents(batch, 100 + i), O.make_images(batch, steps, i),
+                O.make_noise(batch, steps, i), O.make_noise(batch, steps, 100 + i))
+        t0 = time.perf_counter()
+        O.train_iteration(G, D, *args, steps, alpha, LAMBDA)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            done += 1
+            t_total += dt
+        if t_total > max_seconds:
+            break
+    return {"value": round(batch * done / t_total, 3), "unit": "img/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{done} iteration(s) of the same workload at batch {batch} (fp32, torch CPU, {cores} host threads; "
+                      f"forward+R1 double-backward+G backward, Adam excluded)",
+            "gflops": round(batch * done * gflop_img / t_total, 1)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, alpha, batch, gflop_img, desc = WORKLOADS[args.workload]
+    cpu = cpu_leg(args.workload, max_seconds=240.0, steps_cap=max(1, args.steps), warmup=min(args.warmup, 1))
+    R = 4 * 2 ** (steps - 1)
+    line = {"impl": "reference",
+            "metric": "G+D train img/s at 256x256" if args.workload == "train256" else f"G+D train img/s ({args.workload})",
+            "value": cpu["value"], "unit": "img/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(4 / cpu["value"] * 1e3, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "resolution": R, "progressive_steps": steps, "alpha": alpha,
+                       "batch_per_gpu": batch},
+            "cpu_baseline": cpu,
+            "e2e": {"value": cpu["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="train256", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (debugging only)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

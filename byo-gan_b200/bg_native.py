@@ -23,7 +23,7 @@ SIGNATURES = {
     "bg_pack_weight": [_P, _P, _P, _I, _I, _I, _I, _F, _P],
     "bg_unpack_wgrad": [_P, _P, _I, _I, _I, _I, _F, _I, _P],
     "bg_conv_fprop": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _F, _P],
-    "bg_conv_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "bg_conv_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "bg_act_gate": [_P, _P, _P, _Z, _F, _P],
     "bg_axpby": [_P, _P, _P, _Z, _F, _F, _P],
     "bg_pool_act_fwd": [_P, _P, _P, _I, _I, _I, _I, _F, _I, _P],
@@ -31,15 +31,48 @@ SIGNATURES = {
     "bg_upsample2x_fwd": [_P, _P, _I, _I, _I, _I, _P],
     "bg_upsample2x_bwd": [_P, _P, _I, _I, _I, _I, _P],
     "bg_channel_wsum": [_P, _P, _P, _Z, _I, _I, _Z, _Z, _I, _P],
-    "bg_planes3_to_nhwc": [_P, _P, _P, _P, _Z, _I, _I, _I, _I, _F, _I, _F, _P],
+    "bg_planes3_to_nhwc": [_P, _P, _P, _P, _P, _Z, _I, _I, _I, _I, _F, _I, _F, _P],
     "bg_nhwc_to_planes3": [_P, _P, _P, _P, _Z, _I, _I, _I, _I, _F, _P],
     "bg_in_stats": [_P, _P, _I, _I, _I, _P],
     "bg_adain_apply": [_P, _P, _P, _P, _I, _I, _I, _F, _P],
     "bg_adain_bwd_reduce": [_P, _P, _P, _P, _I, _I, _I, _F, _P],
     "bg_adain_bwd_apply": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _I, _P],
+    "bg_linear_fwd": [_P, _P, _P, _P, _I, _I, _I, _F, _I, _F, _P],
+    "bg_linear_bwd_weight": [_P, _P, _P, _P, _I, _I, _I, _F, _I, _P],
+    "bg_transpose_f32": [_P, _P, _I, _I, _P],
+    "bg_act_gate_f32": [_P, _P, _P, _Z, _F, _P],
+    "bg_axpby_f32": [_P, _P, _P, _Z, _F, _F, _P],
+    "bg_const_noise_act": [_P, _P, _P, _P, _I, _I, _I, _F, _P],
+    "bg_const_bwd": [_P, _P, _I, _I, _I, _P],
+    "bg_img_avgpool2": [_P, _P, _I, _I, _I, _P],
+    "bg_img_avgpool2_bwd": [_P, _P, _I, _I, _I, _F, _I, _P],
+    "bg_img_up2_lerp": [_P, _P, _P, _I, _I, _I, _F, _P],
+    "bg_img_up2_bwd": [_P, _P, _I, _I, _I, _F, _P],
+    "bg_plane_sums": [_P, _P, _I, _I, _P],
+    "bg_nhwc_to_nchw_f32": [_P, _P, _I, _I, _I, _P],
+    "bg_nchw_f32_to_nhwc": [_P, _P, _P, _I, _I, _I, _F, _P],
+    "bg_mbstd_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
+    "bg_mbstd_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
+    "bg_logistic_loss": [_P, _I, _F, _P, _P, _F, _P],
+    "bg_sumsq": [_P, _Z, _F, _P, _P],
 }
 
-launch_count = 0  # kernels launched through this binding (bench.py reports it as gpu_launches)
+launch_count = 0  # C-ABI calls made through this binding; each launches >= 1 kernel (bench.py: gpu_launches)
+_timing = None    # when a list: (name, args, start_event, end_event) per call, for bench.py's roofline leg
+
+
+def start_timing():
+    """Record a CUDA-event pair around every subsequent call (on the launching stream)."""
+    global _timing
+    _timing = []
+
+
+def stop_timing():
+    """Returns [(name, args, milliseconds)] for the calls since start_timing()."""
+    global _timing
+    rec, _timing = _timing or [], None
+    torch.cuda.synchronize()
+    return [(n, a, s.elapsed_time(e)) for (n, a, s, e) in rec]
 
 
 def lib():
@@ -80,7 +113,14 @@ def call(name, *args):
     global launch_count
     l = lib()
     conv = [(_ptr(a) if (a is None or isinstance(a, torch.Tensor)) else a) for a in args]
-    rc = getattr(l, name)(*conv, _stream())
+    if _timing is not None:
+        s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_ev.record()
+        rc = getattr(l, name)(*conv, _stream())
+        e_ev.record()
+        _timing.append((name, tuple(a for a in args if not isinstance(a, torch.Tensor) and a is not None), s_ev, e_ev))
+    else:
+        rc = getattr(l, name)(*conv, _stream())
     launch_count += 1
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {l.bg_last_error().decode()}")

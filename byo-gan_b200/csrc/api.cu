@@ -5,7 +5,7 @@
 namespace bg {
 int launch_conv_fprop(const void*, const void*, void*, int, int, int, int, int, int, const float*, const float*,
                       const float*, const void*, int, float, cudaStream_t);
-int launch_conv_wgrad(const void*, const void*, float*, int, int, int, int, int, cudaStream_t);
+int launch_conv_wgrad(const void*, const void*, float*, int, int, int, int, int, int, cudaStream_t);
 int launch_pack_weight(const float*, void*, void*, int, int, int, int, float, cudaStream_t);
 int launch_unpack_wgrad(const float*, float*, int, int, int, int, float, int, cudaStream_t);
 int launch_act_gate(const void*, const void*, void*, size_t, float, cudaStream_t);
@@ -15,8 +15,27 @@ int launch_pool_act_bwd(const void*, const void*, void*, int, int, int, int, flo
 int launch_upsample2x_fwd(const void*, void*, int, int, int, int, cudaStream_t);
 int launch_upsample2x_bwd(const void*, void*, int, int, int, int, cudaStream_t);
 int launch_channel_wsum(const void*, const float*, float*, size_t, int, int, size_t, size_t, int, cudaStream_t);
-int launch_planes3_to_nhwc(const float*, const float*, const float*, void*, size_t, int, int, int, int, float, int,
-                           float, cudaStream_t);
+int launch_planes3_to_nhwc(const float*, const float*, const float*, const void*, void*, size_t, int, int, int, int,
+                           float, int, float, cudaStream_t);
+int launch_linear_fwd(const float*, const float*, const float*, float*, int, int, int, float, int, float, cudaStream_t);
+int launch_linear_bwd_weight(const float*, const float*, float*, float*, int, int, int, float, int, cudaStream_t);
+int launch_transpose_f32(const float*, float*, int, int, cudaStream_t);
+int launch_act_gate_f32(const float*, const float*, float*, size_t, float, cudaStream_t);
+int launch_axpby_f32(const float*, const float*, float*, size_t, float, float, cudaStream_t);
+int launch_const_noise_act(const float*, const float*, const float*, void*, int, int, int, float, cudaStream_t);
+int launch_const_bwd(const void*, float*, int, int, int, cudaStream_t);
+int launch_img_avgpool2(const float*, float*, int, int, int, cudaStream_t);
+int launch_img_avgpool2_bwd(const float*, float*, int, int, int, float, int, cudaStream_t);
+int launch_img_up2_lerp(const float*, const float*, float*, int, int, int, float, cudaStream_t);
+int launch_img_up2_bwd(const float*, float*, int, int, int, float, cudaStream_t);
+int launch_plane_sums(const float*, float*, int, int, cudaStream_t);
+int launch_nhwc_to_nchw_f32(const void*, float*, int, int, int, cudaStream_t);
+int launch_nchw_f32_to_nhwc(const float*, const void*, void*, int, int, int, float, cudaStream_t);
+int launch_mbstd_fwd(const void*, const void*, float*, void*, int, int, int, int, int, float, cudaStream_t);
+int launch_mbstd_bwd(const void*, const void*, const void*, const void*, float*, void*, int, int, int, int, int, float,
+                     cudaStream_t);
+int launch_logistic_loss(const float*, int, float, float*, float*, float, cudaStream_t);
+int launch_sumsq(const float*, size_t, float, float*, cudaStream_t);
 int launch_nhwc_to_planes3(const void*, const float*, const float*, float*, size_t, int, int, int, int, float,
                            cudaStream_t);
 int launch_in_stats(const void*, float*, int, int, int, cudaStream_t);
@@ -44,8 +63,9 @@ int bg_conv_fprop(const void* x, const void* wpack, void* out, int N, int H, int
   return bg::launch_conv_fprop(x, wpack, out, N, H, W, Cin, Cout, ksize, bias, noise, noise_w, gate_src, act, slope,
                                S(stream));
 }
-int bg_conv_wgrad(const void* x, const void* g, float* dwp, int N, int H, int W, int Cin, int Cout, void* stream) {
-  return bg::launch_conv_wgrad(x, g, dwp, N, H, W, Cin, Cout, S(stream));
+int bg_conv_wgrad(const void* x, const void* g, float* dwp, int N, int H, int W, int Cin, int Cout, int accumulate,
+                  void* stream) {
+  return bg::launch_conv_wgrad(x, g, dwp, N, H, W, Cin, Cout, accumulate, S(stream));
 }
 int bg_act_gate(const void* g, const void* y, void* out, size_t n, float slope, void* stream) {
   return bg::launch_act_gate(g, y, out, n, slope, S(stream));
@@ -71,9 +91,9 @@ int bg_channel_wsum(const void* g, const float* planes, float* out, size_t P, in
                     size_t plane_stride, int nplanes, void* stream) {
   return bg::launch_channel_wsum(g, planes, out, P, C, HW, img_stride, plane_stride, nplanes, S(stream));
 }
-int bg_planes3_to_nhwc(const float* img, const float* Wm, const float* bias, void* out, size_t P, int HW, int C,
-                       int ws_c, int ws_j, float coef, int act, float slope, void* stream) {
-  return bg::launch_planes3_to_nhwc(img, Wm, bias, out, P, HW, C, ws_c, ws_j, coef, act, slope, S(stream));
+int bg_planes3_to_nhwc(const float* img, const float* Wm, const float* bias, const void* gate_src, void* out, size_t P,
+                       int HW, int C, int ws_c, int ws_j, float coef, int act, float slope, void* stream) {
+  return bg::launch_planes3_to_nhwc(img, Wm, bias, gate_src, out, P, HW, C, ws_c, ws_j, coef, act, slope, S(stream));
 }
 int bg_nhwc_to_planes3(const void* x, const float* Wm, const float* bias, float* out, size_t P, int HW, int C,
                        int ws_c, int ws_j, float coef, void* stream) {
@@ -93,6 +113,69 @@ int bg_adain_bwd_reduce(const void* g, const void* a, const float* stats, float*
 int bg_adain_bwd_apply(const void* g, const void* a, const float* stats, const float* style, const float* bsums,
                        void* out, int N, int HW, int C, float eps, float slope, int gate, void* stream) {
   return bg::launch_adain_bwd_apply(g, a, stats, style, bsums, out, N, HW, C, eps, slope, gate, S(stream));
+}
+
+int bg_linear_fwd(const float* x, const float* W, const float* bias, float* y, int M, int N, int K, float coef, int act,
+                  float slope, void* stream) {
+  return bg::launch_linear_fwd(x, W, bias, y, M, N, K, coef, act, slope, S(stream));
+}
+int bg_linear_bwd_weight(const float* gy, const float* x, float* dW, float* db, int M, int N, int K, float coef,
+                         int accumulate, void* stream) {
+  return bg::launch_linear_bwd_weight(gy, x, dW, db, M, N, K, coef, accumulate, S(stream));
+}
+int bg_transpose_f32(const float* in, float* out, int R, int C, void* stream) {
+  return bg::launch_transpose_f32(in, out, R, C, S(stream));
+}
+int bg_act_gate_f32(const float* g, const float* y, float* out, size_t n, float slope, void* stream) {
+  return bg::launch_act_gate_f32(g, y, out, n, slope, S(stream));
+}
+int bg_axpby_f32(const float* a, const float* b, float* out, size_t n, float ca, float cb, void* stream) {
+  return bg::launch_axpby_f32(a, b, out, n, ca, cb, S(stream));
+}
+int bg_const_noise_act(const float* cst, const float* noise, const float* nw, void* a, int N, int HW, int C,
+                       float slope, void* stream) {
+  return bg::launch_const_noise_act(cst, noise, nw, a, N, HW, C, slope, S(stream));
+}
+int bg_const_bwd(const void* g, float* dconst, int N, int HW, int C, void* stream) {
+  return bg::launch_const_bwd(g, dconst, N, HW, C, S(stream));
+}
+int bg_img_avgpool2(const float* img, float* out, int P, int Ho, int Wo, void* stream) {
+  return bg::launch_img_avgpool2(img, out, P, Ho, Wo, S(stream));
+}
+int bg_img_avgpool2_bwd(const float* g, float* gimg, int P, int Ho, int Wo, float scale, int accumulate,
+                        void* stream) {
+  return bg::launch_img_avgpool2_bwd(g, gimg, P, Ho, Wo, scale, accumulate, S(stream));
+}
+int bg_img_up2_lerp(const float* small, const float* large, float* out, int P, int H, int W, float alpha,
+                    void* stream) {
+  return bg::launch_img_up2_lerp(small, large, out, P, H, W, alpha, S(stream));
+}
+int bg_img_up2_bwd(const float* g, float* gsmall, int P, int H, int W, float scale, void* stream) {
+  return bg::launch_img_up2_bwd(g, gsmall, P, H, W, scale, S(stream));
+}
+int bg_plane_sums(const float* g, float* sums, int B, int HW, void* stream) {
+  return bg::launch_plane_sums(g, sums, B, HW, S(stream));
+}
+int bg_nhwc_to_nchw_f32(const void* x, float* out, int N, int HW, int C, void* stream) {
+  return bg::launch_nhwc_to_nchw_f32(x, out, N, HW, C, S(stream));
+}
+int bg_nchw_f32_to_nhwc(const float* g, const void* gate_src, void* out, int N, int HW, int C, float slope,
+                        void* stream) {
+  return bg::launch_nchw_f32_to_nhwc(g, gate_src, out, N, HW, C, slope, S(stream));
+}
+int bg_mbstd_fwd(const void* x, const void* v, float* plane, void* xpad, int B, int G, int HW, int C, int Cpad,
+                 float eps, void* stream) {
+  return bg::launch_mbstd_fwd(x, v, plane, xpad, B, G, HW, C, Cpad, eps, S(stream));
+}
+int bg_mbstd_bwd(const void* x, const void* v, const void* gpad, const void* gpad2, float* gs_ws, void* gx, int B, int G,
+                 int HW, int C, int Cpad, float eps, void* stream) {
+  return bg::launch_mbstd_bwd(x, v, gpad, gpad2, gs_ws, gx, B, G, HW, C, Cpad, eps, S(stream));
+}
+int bg_logistic_loss(const float* pred, int n, float sign, float* loss, float* seed, float seed_scale, void* stream) {
+  return bg::launch_logistic_loss(pred, n, sign, loss, seed, seed_scale, S(stream));
+}
+int bg_sumsq(const float* x, size_t n, float scale, float* out, void* stream) {
+  return bg::launch_sumsq(x, n, scale, out, S(stream));
 }
 
 }  // extern "C"

@@ -297,8 +297,9 @@ __global__ void channel_wsum_kernel(const __nv_bfloat16* __restrict__ g, const f
 //   fromRGB forward (gan.py:351-355): Wm = weight (C,3,1,1) -> ws_c = 3, ws_j = 1, bias, act
 //   toRGB input-grad:                 Wm = weight (3,C,1,1) -> ws_c = 1, ws_j = C, no bias, no act
 __global__ void planes3_to_nhwc_kernel(const float* __restrict__ img, const float* __restrict__ Wm,
-                                       const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, size_t P,
-                                       int HW, int C, int ws_c, int ws_j, float coef, int act, float slope) {
+                                       const float* __restrict__ bias, const __nv_bfloat16* __restrict__ gate_src,
+                                       __nv_bfloat16* __restrict__ out, size_t P, int HW, int C, int ws_c, int ws_j,
+                                       float coef, int act, float slope) {
   extern __shared__ float sw[];  // [C][3] + [C]
   for (int i = threadIdx.x; i < C * 3; i += blockDim.x) {
     const int c = i / 3, j = i % 3;
@@ -320,6 +321,11 @@ __global__ void planes3_to_nhwc_kernel(const float* __restrict__ img, const floa
       float v = i0 * w[0] + i1 * w[1] + i2 * w[2] + sw[C * 3 + c + j];
       if (act) v = v > 0.f ? v : v * slope;
       r.v[j] = v;
+    }
+    if (gate_src != nullptr) {
+      const F8 gt = ld8(gate_src + p * C + c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r.v[j] *= gt.v[j] > 0.f ? 1.f : slope;
     }
     st8(out + p * C + c, r);
   }
@@ -594,12 +600,13 @@ int launch_channel_wsum(const void* g, const float* planes, float* out, size_t P
   return 0;
 }
 
-int launch_planes3_to_nhwc(const float* img, const float* Wm, const float* bias, void* out, size_t P, int HW, int C,
-                           int ws_c, int ws_j, float coef, int act, float slope, cudaStream_t s) {
+int launch_planes3_to_nhwc(const float* img, const float* Wm, const float* bias, const void* gate_src, void* out,
+                           size_t P, int HW, int C, int ws_c, int ws_j, float coef, int act, float slope,
+                           cudaStream_t s) {
   BG_REQUIRE(C % 8 == 0 && C <= 1024, "planes3_to_nhwc: unsupported C %d", C);
   const size_t total = P * (C / 8);
   planes3_to_nhwc_kernel<<<grid_for(total), kBlock, (size_t)C * 4 * sizeof(float), s>>>(
-      img, Wm, bias, (__nv_bfloat16*)out, P, HW, C, ws_c, ws_j, coef, act, slope);
+      img, Wm, bias, (const __nv_bfloat16*)gate_src, (__nv_bfloat16*)out, P, HW, C, ws_c, ws_j, coef, act, slope);
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -175,9 +175,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
 
 }  // namespace
 
-// x: (N,H,W,Cin) bf16, g: (N,H,W,Cout) bf16, dw: [9][Cout][Cin] fp32 (overwritten).
+// x: (N,H,W,Cin) bf16, g: (N,H,W,Cout) bf16, dw: [9][Cout][Cin] fp32 (overwritten, or += if accumulate).
 int launch_conv_wgrad(const void* x, const void* g, float* dw, int N, int H, int W, int Cin, int Cout,
-                      cudaStream_t stream) {
+                      int accumulate, cudaStream_t stream) {
   BG_REQUIRE(Cin % 16 == 0 && Cout % 16 == 0, "conv_wgrad: channels must be multiples of 16 (Cin %d Cout %d)", Cin,
              Cout);
   BG_REQUIRE(Cin < 64 ? (Cin == 16 || Cin == 32) : Cin % 64 == 0, "conv_wgrad: unsupported Cin %d", Cin);
@@ -228,7 +228,7 @@ int launch_conv_wgrad(const void* x, const void* g, float* dw, int N, int H, int
     if (make_tmap_bf16(&tmx, x, 4, dims, str, box, (int)p.b_row_bytes) != 0) return 1;
   }
 
-  BG_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)9 * Cout * Cin * sizeof(float), stream));
+  if (!accumulate) BG_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)9 * Cout * Cin * sizeof(float), stream));
   const size_t smem_bytes = (size_t)kStages * kStageBytes + 256 + 1024;
   BG_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   conv_wgrad_kernel<<<units * splits, kThreads, smem_bytes, stream>>>(tmg, tmx, p);

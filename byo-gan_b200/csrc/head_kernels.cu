@@ -1,0 +1,653 @@
+// Small fp32 kernels around the convolution stack: EqualizedLinear (mapping network, style FCs, critic
+// head), the learned constant, image-plane fade ops, minibatch-stddev (forward / tangent / backward /
+// second order) and the loss terms.  All of these touch KBs..MBs; they are latency- and launch-bound, so
+// the design goal is one launch per logical op with enough CTAs to cover the chip, fp32 throughout.
+#include "common.cuh"
+
+namespace bg {
+
+namespace {
+
+__device__ __forceinline__ float lrelu_f(float v, float slope) { return v > 0.f ? v : v * slope; }
+__device__ __forceinline__ float gate_f(float y, float slope) { return y > 0.f ? 1.f : slope; }
+
+// ---------------------------------------------------------------------------------------------
+// EqualizedLinear.forward (gan.py:16-17):  y[m,n] = act(coef * sum_k x[m,k] W[n,k] + b[n])
+// One warp per (n, group of MT rows): W[n,:] is streamed once per warp with float4 loads.
+// ---------------------------------------------------------------------------------------------
+constexpr int kLinMT = 8;
+
+__global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                  const float* __restrict__ bias, float* __restrict__ y, int M, int N, int K,
+                                  float coef, int act, float slope) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int mgroups = (M + kLinMT - 1) / kLinMT;
+  if (warp >= N * mgroups) return;
+  const int n = warp % N;
+  const int m0 = (warp / N) * kLinMT;
+  float acc[kLinMT];
+#pragma unroll
+  for (int i = 0; i < kLinMT; ++i) acc[i] = 0.f;
+  const float* wrow = W + (size_t)n * K;
+  if ((K & 3) == 0) {
+    for (int k = lane * 4; k < K; k += 128) {
+      const float4 wv = *reinterpret_cast<const float4*>(wrow + k);
+#pragma unroll
+      for (int i = 0; i < kLinMT; ++i) {
+        if (m0 + i < M) {
+          const float4 xv = *reinterpret_cast<const float4*>(x + (size_t)(m0 + i) * K + k);
+          acc[i] += xv.x * wv.x + xv.y * wv.y + xv.z * wv.z + xv.w * wv.w;
+        }
+      }
+    }
+  } else {
+    for (int k = lane; k < K; k += 32) {
+      const float wv = wrow[k];
+#pragma unroll
+      for (int i = 0; i < kLinMT; ++i)
+        if (m0 + i < M) acc[i] += x[(size_t)(m0 + i) * K + k] * wv;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kLinMT; ++i) acc[i] = warp_sum(acc[i]);
+  if (lane == 0) {
+    const float b = bias ? bias[n] : 0.f;
+#pragma unroll
+    for (int i = 0; i < kLinMT; ++i) {
+      if (m0 + i < M) {
+        float v = acc[i] * coef + b;
+        if (act) v = lrelu_f(v, slope);
+        y[(size_t)(m0 + i) * N + n] = v;
+      }
+    }
+  }
+}
+
+// dW[n,k] (+)= coef * sum_m gy[m,n] x[m,k];  db[n] (+)= sum_m gy[m,n]
+constexpr int kLbwNT = 8;
+__global__ void linear_bwd_weight_kernel(const float* __restrict__ gy, const float* __restrict__ x,
+                                         float* __restrict__ dW, float* __restrict__ db, int M, int N, int K,
+                                         float coef, int accumulate) {
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int n0 = blockIdx.y * kLbwNT;
+  float acc[kLbwNT][4];
+#pragma unroll
+  for (int i = 0; i < kLbwNT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  if (k < K) {
+    for (int m = 0; m < M; ++m) {
+      const float4 xv = *reinterpret_cast<const float4*>(x + (size_t)m * K + k);
+#pragma unroll
+      for (int i = 0; i < kLbwNT; ++i) {
+        const float g = (n0 + i < N) ? gy[(size_t)m * N + n0 + i] : 0.f;
+        acc[i][0] += g * xv.x;
+        acc[i][1] += g * xv.y;
+        acc[i][2] += g * xv.z;
+        acc[i][3] += g * xv.w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kLbwNT; ++i) {
+      if (n0 + i < N) {
+        float4* dst = reinterpret_cast<float4*>(dW + (size_t)(n0 + i) * K + k);
+        float4 v = make_float4(acc[i][0] * coef, acc[i][1] * coef, acc[i][2] * coef, acc[i][3] * coef);
+        if (accumulate) {
+          const float4 o = *dst;
+          v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+        }
+        *dst = v;
+      }
+    }
+  }
+  if (db != nullptr && blockIdx.x == 0 && threadIdx.x < kLbwNT && n0 + threadIdx.x < N) {
+    float s = 0.f;
+    for (int m = 0; m < M; ++m) s += gy[(size_t)m * N + n0 + threadIdx.x];
+    db[n0 + threadIdx.x] = accumulate ? db[n0 + threadIdx.x] + s : s;
+  }
+}
+
+// out[c][r] = in[r][c]  (fp32), 32x32 smem tiles
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int C) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < C) ? in[(size_t)r * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < C) out[(size_t)c * R + r] = tile[threadIdx.x][i];
+  }
+}
+
+// out = g * gate(y) (+ add)   fp32 vectors (LeakyReLU backward on the small fp32 paths)
+__global__ void act_gate_f32_kernel(const float* __restrict__ g, const float* __restrict__ y,
+                                    float* __restrict__ out, size_t n, float slope) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = g[i] * gate_f(y[i], slope);
+}
+
+// out = ca*a + cb*b  fp32 (b may be null)
+__global__ void axpby_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                                 size_t n, float ca, float cb) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = ca * a[i] + (b ? cb * b[i] : 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// learned constant + noise + LeakyReLU (StyleConvBlock with is_initial, gan.py:81,92,96-97)
+//   a[n,h,w,c] = lrelu(const[c,h,w] + nw[c] * noise[n,h,w]);   HW = 16
+// ---------------------------------------------------------------------------------------------
+__global__ void const_noise_act_kernel(const float* __restrict__ cst, const float* __restrict__ noise,
+                                       const float* __restrict__ nw, __nv_bfloat16* __restrict__ a, int N, int HW,
+                                       int C, float slope) {
+  const size_t total = (size_t)N * HW * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const size_t p = i / C;
+    const int hw = (int)(p % HW);
+    const float v = cst[(size_t)c * HW + hw] + nw[c] * noise[p];
+    a[i] = __float2bfloat16_rn(lrelu_f(v, slope));
+  }
+}
+// dconst[c,hw] = sum_n g[n,hw,c]
+__global__ void const_bwd_kernel(const __nv_bfloat16* __restrict__ g, float* __restrict__ dconst, int N, int HW,
+                                 int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= HW * C) return;
+  const int c = i % C, hw = i / C;
+  float s = 0.f;
+  for (int n = 0; n < N; ++n) s += __bfloat162float(g[((size_t)n * HW + hw) * C + c]);
+  dconst[(size_t)c * HW + hw] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// image-plane ops, NCHW fp32 (B,3,R,R) viewed as P = B*3 planes
+// ---------------------------------------------------------------------------------------------
+// F.avg_pool2d(images, 2) (gan.py:345)
+__global__ void img_avgpool2_kernel(const float* __restrict__ img, float* __restrict__ out, int P, int Ho, int Wo) {
+  const size_t total = (size_t)P * Ho * Wo;
+  const int W = 2 * Wo;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int wo = (int)(i % Wo);
+    const int ho = (int)((i / Wo) % Ho);
+    const size_t pl = i / ((size_t)Wo * Ho);
+    const float* b = img + (pl * 2 * Ho + 2 * ho) * W + 2 * wo;
+    out[i] = 0.25f * (b[0] + b[1] + b[W] + b[W + 1]);
+  }
+}
+// gimg[2h+dy,2w+dx] (+)= 0.25 * scale * g[h,w]
+__global__ void img_avgpool2_bwd_kernel(const float* __restrict__ g, float* __restrict__ gimg, int P, int Ho, int Wo,
+                                        float scale, int accumulate) {
+  const int W = 2 * Wo, H = 2 * Ho;
+  const size_t total = (size_t)P * H * W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    const int h = (int)((i / W) % H);
+    const size_t pl = i / ((size_t)W * H);
+    const float v = 0.25f * scale * g[(pl * Ho + (h >> 1)) * Wo + (w >> 1)];
+    gimg[i] = accumulate ? gimg[i] + v : v;
+  }
+}
+__device__ __forceinline__ void up_taps(int o, int L, int& i0, int& i1, float& w0, float& w1) {
+  // bilinear x2, align_corners=False: src = (o + .5)/2 - .5, clamped
+  const int h = o >> 1;
+  i0 = h;
+  i1 = (o & 1) ? min(h + 1, L - 1) : max(h - 1, 0);
+  w0 = 0.75f;
+  w1 = 0.25f;
+}
+// out = (1-alpha) * bilinear_up2(small) + alpha * large       (gan.py:213-220)
+__global__ void img_up2_lerp_kernel(const float* __restrict__ small, const float* __restrict__ large,
+                                    float* __restrict__ out, int P, int H, int W, float alpha) {
+  const int Ho = 2 * H, Wo = 2 * W;
+  const size_t total = (size_t)P * Ho * Wo;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int wo = (int)(i % Wo);
+    const int ho = (int)((i / Wo) % Ho);
+    const size_t pl = i / ((size_t)Wo * Ho);
+    int h0, h1, w0, w1;
+    float a0, a1, b0, b1;
+    up_taps(ho, H, h0, h1, a0, a1);
+    up_taps(wo, W, w0, w1, b0, b1);
+    const float* s = small + pl * H * W;
+    const float up = a0 * (b0 * s[h0 * W + w0] + b1 * s[h0 * W + w1]) + a1 * (b0 * s[h1 * W + w0] + b1 * s[h1 * W + w1]);
+    // torch.lerp(start, end, w) = start + w * (end - start)
+    out[i] = up + alpha * (large[i] - up);
+  }
+}
+// gsmall[h,w] = scale * sum over the hi-res pixels that read (h,w) of their tap weight * g
+__global__ void img_up2_bwd_kernel(const float* __restrict__ g, float* __restrict__ gsmall, int P, int H, int W,
+                                   float scale) {
+  const int Ho = 2 * H, Wo = 2 * W;
+  const size_t total = (size_t)P * H * W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    const int h = (int)((i / W) % H);
+    const size_t pl = i / ((size_t)W * H);
+    const float* gp = g + pl * Ho * Wo;
+    float acc = 0.f;
+    for (int r = 2 * h - 1; r <= 2 * h + 2; ++r) {
+      if (r < 0 || r >= Ho) continue;
+      int i0, i1;
+      float a0, a1;
+      up_taps(r, H, i0, i1, a0, a1);
+      const float wr = (i0 == h ? a0 : 0.f) + (i1 == h ? a1 : 0.f);
+      if (wr == 0.f) continue;
+      for (int s = 2 * w - 1; s <= 2 * w + 2; ++s) {
+        if (s < 0 || s >= Wo) continue;
+        int j0, j1;
+        float b0, b1;
+        up_taps(s, W, j0, j1, b0, b1);
+        const float ws = (j0 == w ? b0 : 0.f) + (j1 == w ? b1 : 0.f);
+        if (ws != 0.f) acc += wr * ws * gp[r * Wo + s];
+      }
+    }
+    gsmall[i] = scale * acc;
+  }
+}
+
+// sums[j] = sum over n, hw of g[n,j,hw]   (toRGB bias gradient);   planes laid out (B,3,HW)
+__global__ void plane_sums_kernel(const float* __restrict__ g, float* __restrict__ sums, int B, int HW) {
+  __shared__ float red[32];
+  const int j = blockIdx.y;
+  float s = 0.f;
+  const size_t total = (size_t)B * HW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = i / HW, hw = i % HW;
+    s += g[(n * 3 + j) * HW + hw];
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    s = warp_sum(s);
+    if (threadIdx.x == 0) atomicAdd(sums + j, s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// NHWC bf16 <-> NCHW fp32 for the critic head (nn.Flatten of a (B,512,1,1)/(B,512,4,4) map, gan.py:245-247)
+// ---------------------------------------------------------------------------------------------
+__global__ void nhwc_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int N, int HW,
+                                        int C) {
+  const size_t total = (size_t)N * HW * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int hw = (int)((i / C) % HW);
+    const size_t n = i / ((size_t)C * HW);
+    out[(n * C + c) * HW + hw] = __bfloat162float(x[i]);
+  }
+}
+// out[n,hw,c] = g[n,c,hw] * gate(gate_src[n,hw,c])
+__global__ void nchw_f32_to_nhwc_kernel(const float* __restrict__ g, const __nv_bfloat16* __restrict__ gate_src,
+                                        __nv_bfloat16* __restrict__ out, int N, int HW, int C, float slope) {
+  const size_t total = (size_t)N * HW * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int hw = (int)((i / C) % HW);
+    const size_t n = i / ((size_t)C * HW);
+    float v = g[(n * C + c) * HW + hw];
+    if (gate_src != nullptr) v *= gate_f(__bfloat162float(gate_src[i]), slope);
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// MiniBatchStdDev (gan.py:273-298).  x: (B,HW,C) bf16, J = HW*C positions, G groups, M = B/G slots.
+//   mu[j] = mean_n x[n][j];  d = x - mu;  var_m[j] = mean_g d[g*M+m][j]^2;  sig = sqrt(var + eps)
+//   s[m] = mean_j sig_m[j];  sample n gets plane value s[n mod M].
+// One thread per position j; each block reduces its partial sums per slot and adds them atomically.
+// Dynamic smem: M floats.
+// ---------------------------------------------------------------------------------------------
+// mode 0: s[m]    += sum_j sig_m[j] / J
+// mode 1: sdot[m] += sum_j (sum_g d_g * ddot_g) / (G * sig_m[j]) / J          (tangent; v = x-dot)
+__global__ void mbstd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ v,
+                                    float* __restrict__ out, int B, int G, int J, float eps, int mode) {
+  extern __shared__ float part[];
+  const int M = B / G;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) part[i] = 0.f;
+  __syncthreads();
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < J) {
+    float mu = 0.f, mud = 0.f;
+    for (int n = 0; n < B; ++n) {
+      mu += __bfloat162float(x[(size_t)n * J + j]);
+      if (mode == 1) mud += __bfloat162float(v[(size_t)n * J + j]);
+    }
+    mu /= B;
+    mud /= B;
+    for (int m = 0; m < M; ++m) {
+      float sq = 0.f, dd = 0.f;
+      for (int g = 0; g < G; ++g) {
+        const size_t off = (size_t)(g * M + m) * J + j;
+        const float d = __bfloat162float(x[off]) - mu;
+        sq += d * d;
+        if (mode == 1) dd += d * (__bfloat162float(v[off]) - mud);
+      }
+      const float sig = sqrtf(sq / G + eps);
+      const float val = mode == 0 ? sig : dd / (G * sig);
+      atomicAdd(&part[m], val);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < M; i += blockDim.x) atomicAdd(out + i, part[i] / J);
+}
+
+// xpad[n][hw][0..C) = x;  xpad[n][hw][C] = plane[n mod M];  xpad[n][hw][C+1..Cpad) = 0
+__global__ void mbstd_pad_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ plane,
+                                 __nv_bfloat16* __restrict__ xpad, int B, int HW, int C, int Cpad, int M) {
+  const size_t total = (size_t)B * HW * Cpad;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cpad);
+    const size_t p = i / Cpad;
+    const int n = (int)(p / HW);
+    __nv_bfloat16 v;
+    if (c < C) v = x[p * C + c];
+    else if (c == C) v = __float2bfloat16_rn(plane[n % M]);
+    else v = __float2bfloat16_rn(0.f);
+    xpad[i] = v;
+  }
+}
+
+// gs[m] = sum over n == m (mod M), hw of gpad[n][hw][C]      (gradient reaching the stddev plane)
+__global__ void mbstd_plane_grad_kernel(const __nv_bfloat16* __restrict__ gpad, float* __restrict__ gs, int B, int HW,
+                                        int C, int Cpad, int M) {
+  const int m = blockIdx.x;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < (B / M) * HW; i += blockDim.x) {
+    const int g = i / HW, hw = i % HW;
+    s += __bfloat162float(gpad[((size_t)(g * M + m) * HW + hw) * Cpad + C]);
+  }
+  s = warp_sum(s);
+  __shared__ float red[32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    gs[m] = t;
+  }
+}
+
+// gx[n][j] = gpad[n][j(:C)] + (1/(J*G)) * ( r[n][j] - mean_n' r[n'][j] ),
+//   r[n][j] = gs[m(n)] * d[n][j] / sig_m[j]                                       (first-order VJP)
+//           + gs2[m(n)] * ( ddot[n][j]/sig - A_m[j] * d[n][j] / (G * sig^3) )     (second-order term, optional)
+//   A_m[j] = sum_g d_g * ddot_g.   gs2/v null -> first-order only.  gpad null -> no pass-through term.
+__global__ void mbstd_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ v,
+                                 const __nv_bfloat16* __restrict__ gpad, const float* __restrict__ gs,
+                                 const float* __restrict__ gs2, __nv_bfloat16* __restrict__ gx, int B, int G, int HW,
+                                 int C, int Cpad, float eps) {
+  const int J = HW * C;
+  const int M = B / G;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= J) return;
+  const int c = j % C, hw = j / C;
+  float mu = 0.f, mud = 0.f;
+  for (int n = 0; n < B; ++n) {
+    mu += __bfloat162float(x[(size_t)n * J + j]);
+    if (v != nullptr) mud += __bfloat162float(v[(size_t)n * J + j]);
+  }
+  mu /= B;
+  mud /= B;
+  // pass 1: mean over n of r[n][j]
+  float rmean = 0.f;
+  for (int m = 0; m < M; ++m) {
+    float sq = 0.f, A = 0.f, sd = 0.f, sdd = 0.f;
+    for (int g = 0; g < G; ++g) {
+      const size_t off = (size_t)(g * M + m) * J + j;
+      const float d = __bfloat162float(x[off]) - mu;
+      sq += d * d;
+      sd += d;
+      if (v != nullptr) {
+        const float dd = __bfloat162float(v[off]) - mud;
+        A += d * dd;
+        sdd += dd;
+      }
+    }
+    const float sig = sqrtf(sq / G + eps);
+    float r = (gs ? gs[m] : 0.f) * sd / sig;
+    if (v != nullptr) r += gs2[m] * (sdd / sig - A * sd / (G * sig * sig * sig));
+    rmean += r;
+  }
+  rmean /= B;
+  // pass 2: per-sample values
+  const float scale = 1.f / ((float)J * G);
+  for (int m = 0; m < M; ++m) {
+    float sq = 0.f, A = 0.f;
+    for (int g = 0; g < G; ++g) {
+      const size_t off = (size_t)(g * M + m) * J + j;
+      const float d = __bfloat162float(x[off]) - mu;
+      sq += d * d;
+      if (v != nullptr) A += d * (__bfloat162float(v[off]) - mud);
+    }
+    const float sig = sqrtf(sq / G + eps);
+    for (int g = 0; g < G; ++g) {
+      const int n = g * M + m;
+      const size_t off = (size_t)n * J + j;
+      const float d = __bfloat162float(x[off]) - mu;
+      float r = (gs ? gs[m] : 0.f) * d / sig;
+      if (v != nullptr) {
+        const float dd = __bfloat162float(v[off]) - mud;
+        r += gs2[m] * (dd / sig - A * d / (G * sig * sig * sig));
+      }
+      float o = scale * (r - rmean);
+      if (gpad != nullptr) o += __bfloat162float(gpad[((size_t)n * HW + hw) * Cpad + c]);
+      gx[off] = __float2bfloat16_rn(o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// loss terms (gan.py:228, 396, 406):  loss = mean softplus(sign * pred);  seed = d loss / d pred * seed_scale
+// single block; n <= a few hundred
+// ---------------------------------------------------------------------------------------------
+__global__ void logistic_loss_kernel(const float* __restrict__ pred, int n, float sign, float* __restrict__ loss,
+                                     float* __restrict__ seed, float seed_scale) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float t = sign * pred[i];
+    // softplus with torch's threshold (beta=1, threshold=20)
+    s += t > 20.f ? t : log1pf(expf(t));
+    if (seed != nullptr) seed[i] = seed_scale * sign / (1.f + expf(-t)) / n;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    loss[0] = t / n;
+  }
+}
+
+// out[0] += scale * sum x^2
+__global__ void sumsq_kernel(const float* __restrict__ x, size_t n, float scale, float* __restrict__ out) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    s += x[i] * x[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    s = warp_sum(s);
+    if (threadIdx.x == 0) atomicAdd(out, s * scale);
+  }
+}
+
+inline int grid1d(size_t work, int block = 256, int cap_mult = 8) {
+  size_t blocks = (work + block - 1) / block;
+  const size_t cap = (size_t)num_sms() * cap_mult;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+int launch_linear_fwd(const float* x, const float* W, const float* bias, float* y, int M, int N, int K, float coef,
+                      int act, float slope, cudaStream_t s) {
+  BG_REQUIRE(M > 0 && N > 0 && K > 0, "linear_fwd: bad shape M %d N %d K %d", M, N, K);
+  const long warps = (long)N * ((M + kLinMT - 1) / kLinMT);
+  const int block = 256;
+  const long blocks = (warps * 32 + block - 1) / block;
+  linear_fwd_kernel<<<(unsigned)blocks, block, 0, s>>>(x, W, bias, y, M, N, K, coef, act, slope);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_linear_bwd_weight(const float* gy, const float* x, float* dW, float* db, int M, int N, int K, float coef,
+                             int accumulate, cudaStream_t s) {
+  BG_REQUIRE(M > 0 && N > 0 && K > 0 && K % 4 == 0, "linear_bwd_weight: bad shape M %d N %d K %d", M, N, K);
+  dim3 grid((K / 4 + 127) / 128, (N + kLbwNT - 1) / kLbwNT);
+  linear_bwd_weight_kernel<<<grid, 128, 0, s>>>(gy, x, dW, db, M, N, K, coef, accumulate);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_transpose_f32(const float* in, float* out, int R, int C, cudaStream_t s) {
+  dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
+  transpose_kernel<<<grid, block, 0, s>>>(in, out, R, C);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_act_gate_f32(const float* g, const float* y, float* out, size_t n, float slope, cudaStream_t s) {
+  act_gate_f32_kernel<<<grid1d(n), 256, 0, s>>>(g, y, out, n, slope);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_axpby_f32(const float* a, const float* b, float* out, size_t n, float ca, float cb, cudaStream_t s) {
+  axpby_f32_kernel<<<grid1d(n), 256, 0, s>>>(a, b, out, n, ca, cb);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_const_noise_act(const float* cst, const float* noise, const float* nw, void* a, int N, int HW, int C,
+                           float slope, cudaStream_t s) {
+  const_noise_act_kernel<<<grid1d((size_t)N * HW * C), 256, 0, s>>>(cst, noise, nw, (__nv_bfloat16*)a, N, HW, C, slope);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_const_bwd(const void* g, float* dconst, int N, int HW, int C, cudaStream_t s) {
+  const_bwd_kernel<<<(HW * C + 255) / 256, 256, 0, s>>>((const __nv_bfloat16*)g, dconst, N, HW, C);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_img_avgpool2(const float* img, float* out, int P, int Ho, int Wo, cudaStream_t s) {
+  img_avgpool2_kernel<<<grid1d((size_t)P * Ho * Wo), 256, 0, s>>>(img, out, P, Ho, Wo);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_img_avgpool2_bwd(const float* g, float* gimg, int P, int Ho, int Wo, float scale, int accumulate,
+                            cudaStream_t s) {
+  img_avgpool2_bwd_kernel<<<grid1d((size_t)P * Ho * Wo * 4), 256, 0, s>>>(g, gimg, P, Ho, Wo, scale, accumulate);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_img_up2_lerp(const float* small, const float* large, float* out, int P, int H, int W, float alpha,
+                        cudaStream_t s) {
+  img_up2_lerp_kernel<<<grid1d((size_t)P * H * W * 4), 256, 0, s>>>(small, large, out, P, H, W, alpha);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_img_up2_bwd(const float* g, float* gsmall, int P, int H, int W, float scale, cudaStream_t s) {
+  img_up2_bwd_kernel<<<grid1d((size_t)P * H * W), 256, 0, s>>>(g, gsmall, P, H, W, scale);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_plane_sums(const float* g, float* sums, int B, int HW, cudaStream_t s) {
+  BG_CHECK_CUDA(cudaMemsetAsync(sums, 0, 3 * sizeof(float), s));
+  int bx = grid1d((size_t)B * HW, 256, 2);
+  plane_sums_kernel<<<dim3(bx, 3), 256, 0, s>>>(g, sums, B, HW);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_nhwc_to_nchw_f32(const void* x, float* out, int N, int HW, int C, cudaStream_t s) {
+  nhwc_to_nchw_f32_kernel<<<grid1d((size_t)N * HW * C), 256, 0, s>>>((const __nv_bfloat16*)x, out, N, HW, C);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_nchw_f32_to_nhwc(const float* g, const void* gate_src, void* out, int N, int HW, int C, float slope,
+                            cudaStream_t s) {
+  nchw_f32_to_nhwc_kernel<<<grid1d((size_t)N * HW * C), 256, 0, s>>>(g, (const __nv_bfloat16*)gate_src,
+                                                                    (__nv_bfloat16*)out, N, HW, C, slope);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_mbstd_fwd(const void* x, const void* v, float* plane, void* xpad, int B, int G, int HW, int C, int Cpad,
+                     float eps, cudaStream_t s) {
+  BG_REQUIRE(G > 0 && B % G == 0, "mbstd: batch %d is not a multiple of the group size %d", B, G);
+  BG_REQUIRE(Cpad > C, "mbstd: Cpad %d must exceed C %d", Cpad, C);
+  const int M = B / G, J = HW * C;
+  BG_CHECK_CUDA(cudaMemsetAsync(plane, 0, M * sizeof(float), s));
+  const void* src = v ? v : x;
+  mbstd_reduce_kernel<<<(J + 127) / 128, 128, M * sizeof(float), s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)v,
+                                                                     plane, B, G, J, eps, v ? 1 : 0);
+  BG_CHECK_CUDA(cudaGetLastError());
+  if (xpad != nullptr) {
+    mbstd_pad_kernel<<<grid1d((size_t)B * HW * Cpad), 256, 0, s>>>((const __nv_bfloat16*)src, plane,
+                                                                  (__nv_bfloat16*)xpad, B, HW, C, Cpad, M);
+    BG_CHECK_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+int launch_mbstd_bwd(const void* x, const void* v, const void* gpad, const void* gpad2, float* gs_ws, void* gx, int B,
+                     int G, int HW, int C, int Cpad, float eps, cudaStream_t s) {
+  BG_REQUIRE(G > 0 && B % G == 0, "mbstd_bwd: batch %d is not a multiple of the group size %d", B, G);
+  BG_REQUIRE((v == nullptr) == (gpad2 == nullptr), "mbstd_bwd: tangent v and its plane gradient come together");
+  const int M = B / G, J = HW * C;
+  float* gs = nullptr;
+  float* gs2 = nullptr;
+  if (gpad != nullptr) {
+    gs = gs_ws;
+    mbstd_plane_grad_kernel<<<M, 128, 0, s>>>((const __nv_bfloat16*)gpad, gs, B, HW, C, Cpad, M);
+    BG_CHECK_CUDA(cudaGetLastError());
+  }
+  if (gpad2 != nullptr) {
+    gs2 = gs_ws + M;
+    mbstd_plane_grad_kernel<<<M, 128, 0, s>>>((const __nv_bfloat16*)gpad2, gs2, B, HW, C, Cpad, M);
+    BG_CHECK_CUDA(cudaGetLastError());
+  }
+  mbstd_bwd_kernel<<<(J + 127) / 128, 128, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)v,
+                                                  (const __nv_bfloat16*)gpad, gs, gs2, (__nv_bfloat16*)gx, B, G, HW, C,
+                                                  Cpad, eps);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_logistic_loss(const float* pred, int n, float sign, float* loss, float* seed, float seed_scale,
+                         cudaStream_t s) {
+  BG_REQUIRE(n > 0, "logistic_loss: empty prediction vector");
+  logistic_loss_kernel<<<1, 256, 0, s>>>(pred, n, sign, loss, seed, seed_scale);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_sumsq(const float* x, size_t n, float scale, float* out, cudaStream_t s) {
+  BG_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), s));
+  sumsq_kernel<<<grid1d(n, 256, 2), 256, 0, s>>>(x, n, scale, out);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace bg

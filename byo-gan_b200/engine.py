@@ -1,0 +1,709 @@
+"""Host-side schedule of the sm_100a kernels for the StyleGAN hot path.
+
+This module owns WHAT runs in which order for
+  * Generator.forward / its backward            (reference gan.py:183-222 + autograd),
+  * Critic.forward / its first-order backward    (reference gan.py:331-349 + autograd),
+  * the R1 critic loss with its double-backward  (reference gan.py:393-412),
+and nothing else: all arithmetic on feature maps happens inside libbg_b200.so (include/bg_b200.h).  torch is
+used for device memory (the caching allocator), the current stream, and a handful of reshapes/concats on
+(B, C)-sized tensors.  There is no CPU path and no eager fallback: every op goes through bg_native.call(),
+which raises if the library is missing or a kernel reports an error.
+
+Layout: feature maps NHWC bf16; images at the module boundary NCHW fp32; the mapping network, style
+vectors, instance-norm statistics, critic head and every parameter gradient are fp32.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+import bg_native as bgn
+
+SLOPE = 0.2          # nn.LeakyReLU(0.2) everywhere (gan.py:86,145,241,...)
+IN_EPS = 1e-8        # nn.InstanceNorm2d(eps=1e-8), gan.py:59
+MBSTD_EPS = 1e-8     # gan.py:287
+GEN_CHANNELS = [(512, 512), (512, 512), (512, 512), (512, 256), (256, 128), (128, 64), (64, 32), (32, 16)]
+CRITIC_CHANNELS = [(16, 32), (32, 64), (64, 128), (128, 256), (256, 512), (512, 512), (512, 512), (512, 512)]
+MBSTD_CPAD = 576     # 512 features + 1 stddev plane, padded to a multiple of 64 for the tensor-core conv
+
+call = bgn.call
+
+
+def _bf16(*shape, device):
+    return torch.empty(shape, dtype=torch.bfloat16, device=device)
+
+
+def _f32(*shape, device):
+    return torch.empty(shape, dtype=torch.float32, device=device)
+
+
+def coef_of(weight: torch.Tensor) -> float:
+    """Equalized-lr runtime scale sqrt(2 / fan_in) (gan.py:13-14, 26-27)."""
+    fan_in = weight.shape[1] * (weight[0][0].numel() if weight.dim() > 2 else 1)
+    return math.sqrt(2.0 / fan_in)
+
+
+# ------------------------------------------------------------------------------------------------------
+# packed-weight cache: bf16 [tap][Cout][Cin] (fprop) and [tap'][Cin][Cout] (dgrad) copies of the fp32
+# master weights with the equalized coefficient folded in; fp32 transposes of the linear weights.
+# Refreshed when the parameter's version counter or storage changes (optimizer steps and load_state_dict
+# are in-place, so they bump it).
+# ------------------------------------------------------------------------------------------------------
+class PackCache:
+    def __init__(self):
+        self._conv: Dict[int, tuple] = {}
+        self._lin: Dict[int, tuple] = {}
+
+    def conv(self, w: torch.Tensor, cin_pad: Optional[int] = None):
+        key = id(w)
+        tag = (w._version, w.data_ptr(), cin_pad)
+        hit = self._conv.get(key)
+        if hit is not None and hit[0] == tag:
+            return hit[1], hit[2]
+        cout, cin, ks, _ = w.shape
+        cp = cin_pad or cin
+        wf = _bf16(ks * ks, cout, cp, device=w.device)
+        wd = _bf16(ks * ks, cp, cout, device=w.device)
+        call("bg_pack_weight", w.detach(), wf, wd, cout, cin, cp, ks, coef_of(w))
+        self._conv[key] = (tag, wf, wd)
+        return wf, wd
+
+    def linear_t(self, w: torch.Tensor):
+        """fp32 transpose (K, N) of an (N, K) linear weight: the input-gradient pass is a forward on it."""
+        key = id(w)
+        tag = (w._version, w.data_ptr())
+        hit = self._lin.get(key)
+        if hit is not None and hit[0] == tag:
+            return hit[1]
+        w2 = w.detach().reshape(w.shape[0], -1)
+        n, k = w2.shape
+        wt = _f32(k, n, device=w.device)
+        call("bg_transpose_f32", w2, wt, n, k)
+        self._lin[key] = (tag, wt)
+        return wt
+
+
+# ------------------------------------------------------------------------------------------------------
+# thin op helpers
+# ------------------------------------------------------------------------------------------------------
+def linear_fwd(x, w, bias, act, coef=None):
+    w2 = w.detach().reshape(w.shape[0], -1)
+    m, k = x.shape
+    n = w2.shape[0]
+    y = _f32(m, n, device=x.device)
+    call("bg_linear_fwd", x, w2, None if bias is None else bias.detach(), y, m, n, k,
+         coef_of(w) if coef is None else coef, 1 if act else 0, SLOPE)
+    return y
+
+
+def linear_bwd_input(gy, w, packs: PackCache):
+    """gx = coef * gy @ W  via the forward kernel on the cached transpose."""
+    wt = packs.linear_t(w)                      # (K, N)
+    m, n = gy.shape
+    k = wt.shape[0]
+    gx = _f32(m, k, device=gy.device)
+    call("bg_linear_fwd", gy, wt, None, gx, m, k, n, coef_of(w), 0, SLOPE)
+    return gx
+
+
+def linear_bwd_weight(gy, x, w, want_bias=True, into=None, into_b=None):
+    """Returns (dW shaped like w, db) ; with `into` accumulates in place instead."""
+    m, n = gy.shape
+    k = x.shape[1]
+    acc = into is not None
+    dw = into if acc else _f32(*w.shape, device=gy.device)
+    db = into_b if acc else (_f32(n, device=gy.device) if want_bias else None)
+    call("bg_linear_bwd_weight", gy, x, dw, db, m, n, k, coef_of(w), 1 if acc else 0)
+    return dw, db
+
+
+def gate_f32(g, y):
+    out = torch.empty_like(g)
+    call("bg_act_gate_f32", g, y, out, g.numel(), SLOPE)
+    return out
+
+
+def conv3x3(x, wpack, cin, cout, bias=None, noise=None, noise_w=None, gate_src=None, act=False):
+    n, h, w_, _ = x.shape
+    out = _bf16(n, h, w_, cout, device=x.device)
+    call("bg_conv_fprop", x, wpack, out, n, h, w_, cin, cout, 3, bias, noise, noise_w, gate_src, 1 if act else 0, SLOPE)
+    return out
+
+
+def conv_wgrad(x, g, w_param, cin_pad=None, extra=None):
+    """dW for a 3x3 conv parameter `w_param` from input x and output-gradient g (both NHWC bf16).
+    `extra=(v, ghat)` adds the R1 second-order pair into the same accumulator (doubled-K contraction)."""
+    n, h, w_, cin_eff = x.shape
+    cout = g.shape[3]
+    dwp = _f32(9, cout, cin_eff, device=x.device)
+    call("bg_conv_wgrad", x, g, dwp, n, h, w_, cin_eff, cout, 0)
+    if extra is not None:
+        call("bg_conv_wgrad", extra[0], extra[1], dwp, n, h, w_, cin_eff, cout, 1)
+    dw = _f32(*w_param.shape, device=x.device)
+    call("bg_unpack_wgrad", dwp, dw, cout, w_param.shape[1], cin_eff, 3, coef_of(w_param), 0)
+    return dw
+
+
+def channel_wsum(g, planes, nplanes, hw, img_stride, plane_stride):
+    c = g.shape[-1]
+    p = g.numel() // c
+    out = _f32(1 + nplanes, c, device=g.device)
+    call("bg_channel_wsum", g, planes, out, p, c, hw, img_stride, plane_stride, nplanes)
+    return out
+
+
+def axpby(a, b, ca, cb):
+    out = torch.empty_like(a)
+    call("bg_axpby", a, b, out, a.numel(), float(ca), float(cb))
+    return out
+
+
+def clamp_alpha(alpha):
+    return min(1.0, max(0.0, float(alpha)))      # gan.py:211,344
+
+
+# ======================================================================================================
+# Generator
+# ======================================================================================================
+def generator_params(gen, steps: int, fade: bool) -> List[torch.nn.Parameter]:
+    """Parameters Generator.forward touches at (steps, fade), in a fixed order.  Everything else keeps
+    .grad = None exactly as in the reference (its autograd never reaches unused blocks)."""
+    ps = []
+    for i in range(8):
+        lin = gen.to_w_noise[0].layers[i][0]
+        ps += [lin.weight, lin.bias]
+    for k in range(steps):
+        blk = gen.gen_blocks[k]
+        for sc in (blk.conv_1, blk.conv_2):
+            if isinstance(sc.conv, torch.nn.Parameter):
+                ps.append(sc.conv)
+            else:
+                ps += [sc.conv.weight, sc.conv.bias]
+            ps += [sc.inject_noise.weights, sc.adain.style.weight, sc.adain.style.bias]
+    if fade:
+        ps += [gen.to_rgbs[steps - 2].weight, gen.to_rgbs[steps - 2].bias]
+    ps += [gen.to_rgbs[steps - 1].weight, gen.to_rgbs[steps - 1].bias]
+    return ps
+
+
+def generator_forward(gen, packs: PackCache, z, noise, steps, alpha, z2=None, crossover=None, keep_tape=True):
+    """Generator.forward (gan.py:183-222).  Returns (image (B,3,R,R) fp32, tape)."""
+    dev = z.device
+    B = z.shape[0]
+    fade = alpha is not None and steps > 1
+    a_mix = clamp_alpha(alpha) if fade else None
+
+    def mapping(zz):
+        hs = [zz.detach().float().contiguous()]
+        for i in range(8):                                   # MappingLayers, gan.py:130-148
+            lin = gen.to_w_noise[0].layers[i][0]
+            hs.append(linear_fwd(hs[-1], lin.weight, lin.bias, act=True))
+        return hs
+
+    maps = [mapping(z)]
+    if z2 is not None:
+        maps.append(mapping(z2))
+    layers = []
+    feats = []
+    feat = None
+    for k in range(steps):
+        blk = gen.gen_blocks[k]
+        cin, cout = GEN_CHANNELS[k]
+        R = 4 << k
+        which = 1 if (z2 is not None and crossover is not None and k >= crossover) else 0
+        wlat = maps[which][-1]
+        nz = noise[k].detach().float().contiguous()
+        for j, sc in enumerate((blk.conv_1, blk.conv_2)):
+            st = sc.adain.style
+            style = linear_fwd(wlat, st.weight, st.bias, act=False)              # gan.py:66
+            nw = sc.inject_noise.weights.detach().reshape(-1)
+            if k == 0 and j == 0:
+                a = _bf16(B, 4, 4, cout, device=dev)                             # gan.py:92,96-97
+                call("bg_const_noise_act", sc.conv.detach(), nz, nw, a, B, 16, cout, SLOPE)
+                xin = None
+            else:
+                ci = cin if j == 0 else cout
+                if j == 0:                                                       # gan.py:122-123
+                    xin = _bf16(B, R, R, ci, device=dev)
+                    call("bg_upsample2x_fwd", feat, xin, B, R // 2, R // 2, ci)
+                else:
+                    xin = feat
+                wf, _ = packs.conv(sc.conv.weight)
+                a = conv3x3(xin, wf, ci, cout, bias=sc.conv.bias.detach(), noise=nz, noise_w=nw, act=True)
+            stats = _f32(B, cout, 2, device=dev)
+            call("bg_in_stats", a, stats, B, R * R, cout)
+            xo = torch.empty_like(a)
+            call("bg_adain_apply", a, stats, style, xo, B, R * R, cout, IN_EPS)   # gan.py:69
+            layers.append(dict(k=k, j=j, sc=sc, xin=xin, a=a, stats=stats, style=style, R=R, C=cout, which=which,
+                               noise=nz))
+            feat = xo
+        feats.append(feat)
+    R = 4 << (steps - 1)
+    C = GEN_CHANNELS[steps - 1][1]
+    rgb = gen.to_rgbs[steps - 1]
+    img = _f32(B, 3, R, R, device=dev)
+    call("bg_nhwc_to_planes3", feat, rgb.weight.detach(), rgb.bias.detach(), img, B * R * R, R * R, C, 1, C,
+         coef_of(rgb.weight))
+    if fade:
+        Cp = GEN_CHANNELS[steps - 2][1]
+        rgb_p = gen.to_rgbs[steps - 2]
+        small = _f32(B, 3, R // 2, R // 2, device=dev)
+        call("bg_nhwc_to_planes3", feats[-2], rgb_p.weight.detach(), rgb_p.bias.detach(), small, B * R * R // 4,
+             R * R // 4, Cp, 1, Cp, coef_of(rgb_p.weight))
+        out = _f32(B, 3, R, R, device=dev)
+        call("bg_img_up2_lerp", small, img, out, B * 3, R // 2, R // 2, a_mix)   # gan.py:213-220
+        img = out
+    tape = None
+    if keep_tape:
+        tape = dict(maps=maps, layers=layers, feats=feats, steps=steps, fade=fade, a_mix=a_mix, B=B)
+    return img, tape
+
+
+def generator_backward(gen, packs: PackCache, tape, g_img, need: Dict[int, bool], need_z=True, need_z2=False):
+    """Backward of generator_forward.  `need[id(param)]` says which parameter gradients to produce.
+    Returns (grads {id(param): tensor}, dz, dz2)."""
+    dev = g_img.device
+    steps, fade, B = tape["steps"], tape["fade"], tape["B"]
+    layers, feats, maps = tape["layers"], tape["feats"], tape["maps"]
+    grads: Dict[int, torch.Tensor] = {}
+    g_img = g_img.detach().float().contiguous()
+    R = 4 << (steps - 1)
+    C = GEN_CHANNELS[steps - 1][1]
+    g_w = [None] * len(maps)
+
+    def want(p):
+        return need.get(id(p), False)
+
+    def rgb_backward(rgb, x_feat, g_planes, r, c):
+        """toRGB 1x1 conv (gan.py:172-179): returns grad wrt the NHWC feature map; fills weight/bias grads."""
+        if want(rgb.weight):
+            ws = channel_wsum(x_feat, g_planes, 3, r * r, 3 * r * r, r * r)
+            grads[id(rgb.weight)] = (ws[1:4] * coef_of(rgb.weight)).reshape(3, c, 1, 1)
+        if want(rgb.bias):
+            sums = _f32(3, device=dev)
+            call("bg_plane_sums", g_planes, sums, B, r * r)
+            grads[id(rgb.bias)] = sums
+        gx = _bf16(B, r, r, c, device=dev)
+        call("bg_planes3_to_nhwc", g_planes, rgb.weight.detach(), None, None, gx, B * r * r, r * r, c, 1, c,
+             coef_of(rgb.weight), 0, SLOPE)
+        return gx
+
+    g_prev_extra = None
+    if fade:
+        a_mix = tape["a_mix"]
+        g_large = _f32(B, 3, R, R, device=dev)
+        call("bg_axpby_f32", g_img, None, g_large, g_img.numel(), a_mix, 0.0)
+        g_small = _f32(B, 3, R // 2, R // 2, device=dev)
+        call("bg_img_up2_bwd", g_img, g_small, B * 3, R // 2, R // 2, 1.0 - a_mix)
+        g_prev_extra = rgb_backward(gen.to_rgbs[steps - 2], feats[-2], g_small, R // 2, GEN_CHANNELS[steps - 2][1])
+    else:
+        g_large = g_img
+    gx = rgb_backward(gen.to_rgbs[steps - 1], feats[-1], g_large, R, C)
+
+    for L in reversed(layers):
+        sc, k, j, r, c = L["sc"], L["k"], L["j"], L["R"], L["C"]
+        a, stats, style = L["a"], L["stats"], L["style"]
+        bs = _f32(B, c, 2, device=dev)
+        call("bg_adain_bwd_reduce", gx, a, stats, bs, B, r * r, c, IN_EPS)
+        gpre = torch.empty_like(a)
+        call("bg_adain_bwd_apply", gx, a, stats, style, bs, gpre, B, r * r, c, IN_EPS, SLOPE, 1)
+        # style FC (gan.py:60,66): dL/dgamma = sum g*ahat, dL/dbeta = sum g
+        dstyle = torch.cat([bs[..., 1], bs[..., 0]], dim=1).contiguous()
+        st = sc.adain.style
+        wlat = maps[L["which"]][-1]
+        if want(st.weight) or want(st.bias):
+            dw, db = linear_bwd_weight(dstyle, wlat, st.weight)
+            if want(st.weight):
+                grads[id(st.weight)] = dw
+            if want(st.bias):
+                grads[id(st.bias)] = db
+        gw_l = linear_bwd_input(dstyle, st.weight, packs)
+        if g_w[L["which"]] is None:
+            g_w[L["which"]] = gw_l
+        else:
+            call("bg_axpby_f32", g_w[L["which"]], gw_l, g_w[L["which"]], gw_l.numel(), 1.0, 1.0)
+        # bias / noise-weight gradients (gan.py:52): one pass over gpre
+        is_const = L["xin"] is None
+        need_b = (not is_const) and want(sc.conv.bias)
+        if need_b or want(sc.inject_noise.weights):
+            ws = channel_wsum(gpre, L["noise"], 1, r * r, r * r, 0)
+            if need_b:
+                grads[id(sc.conv.bias)] = ws[0].clone()
+            if want(sc.inject_noise.weights):
+                grads[id(sc.inject_noise.weights)] = ws[1].reshape(1, c, 1, 1).clone()
+        if is_const:
+            if want(sc.conv):
+                dc = _f32(1, c, 4, 4, device=dev)
+                call("bg_const_bwd", gpre, dc, B, 16, c)
+                grads[id(sc.conv)] = dc
+            gx = None
+            continue
+        ci = L["xin"].shape[3]
+        if want(sc.conv.weight):
+            grads[id(sc.conv.weight)] = conv_wgrad(L["xin"], gpre, sc.conv.weight)
+        _, wd = packs.conv(sc.conv.weight)
+        gxin = conv3x3(gpre, wd, c, ci)                       # data gradient: same kernel, flipped pack
+        if j == 0:
+            gfeat = _bf16(B, r // 2, r // 2, ci, device=dev)
+            call("bg_upsample2x_bwd", gxin, gfeat, B, r // 2, r // 2, ci)
+            if g_prev_extra is not None and k == steps - 1:
+                gfeat = axpby(gfeat, g_prev_extra, 1.0, 1.0)
+            gx = gfeat
+        else:
+            gx = gxin
+
+    # mapping network backward (gan.py:130-148)
+    dzs = [None, None]
+    for which, hs in enumerate(maps):
+        g = g_w[which]
+        if g is None:
+            g = torch.zeros(B, 512, device=dev)
+        need_in = need_z if which == 0 else need_z2
+        for i in reversed(range(8)):
+            lin = gen.to_w_noise[0].layers[i][0]
+            gp = gate_f32(g, hs[i + 1])
+            if want(lin.weight) or want(lin.bias):
+                acc = id(lin.weight) in grads
+                dw, db = linear_bwd_weight(gp, hs[i], lin.weight, into=grads.get(id(lin.weight)),
+                                           into_b=grads.get(id(lin.bias)))
+                if not acc:
+                    grads[id(lin.weight)] = dw
+                    grads[id(lin.bias)] = db
+            if i > 0 or need_in:
+                g = linear_bwd_input(gp, lin.weight, packs)
+        dzs[which] = g if need_in else None
+    return grads, dzs[0], dzs[1]
+
+
+# ======================================================================================================
+# Critic
+# ======================================================================================================
+def critic_params(critic, steps: int, fade: bool) -> List[torch.nn.Parameter]:
+    start = 8 - steps
+    ps = [critic.from_rgbs[start][0].weight, critic.from_rgbs[start][0].bias]
+    if fade:
+        ps += [critic.from_rgbs[start + 1][0].weight, critic.from_rgbs[start + 1][0].bias]
+    for k in range(start, 8):
+        blk = critic.conv_blocks[k]
+        if k < 7:
+            ps += [blk.conv_1[0].weight, blk.conv_1[0].bias, blk.conv_2[0].weight, blk.conv_2[0].bias]
+        else:
+            ps += [blk.conv_1[1].weight, blk.conv_1[1].bias, blk.conv_2[0].weight, blk.conv_2[0].bias,
+                   blk.conv_2[3].weight, blk.conv_2[3].bias, blk.conv_2[5].weight, blk.conv_2[5].bias]
+    return ps
+
+
+def critic_forward(critic, packs: PackCache, images, steps, alpha):
+    """Critic.forward (gan.py:331-349).  Returns (pred (B,1) fp32, tape)."""
+    dev = images.device
+    img = images.detach().float().contiguous()
+    B, _, R, _ = img.shape
+    start = 8 - steps
+    fade = alpha is not None and steps > 1
+    a_mix = clamp_alpha(alpha) if fade else None
+    fr = critic.from_rgbs[start][0]
+    c0 = CRITIC_CHANNELS[start][0]
+    x0 = _bf16(B, R, R, c0, device=dev)
+    call("bg_planes3_to_nhwc", img, fr.weight.detach(), fr.bias.detach(), None, x0, B * R * R, R * R, c0, 3, 1,
+         coef_of(fr.weight), 1, SLOPE)                                                        # gan.py:338,351-355
+    feat = x0
+    blocks = []
+    for idx, k in enumerate(range(start, 7)):
+        blk = critic.conv_blocks[k]
+        cin, cout = CRITIC_CHANNELS[k]
+        c1, c2 = blk.conv_1[0], blk.conv_2[0]
+        wf1, _ = packs.conv(c1.weight)
+        wf2, _ = packs.conv(c2.weight)
+        y1 = conv3x3(feat, wf1, cin, cout, bias=c1.bias.detach(), act=True)                   # gan.py:254-255
+        u = conv3x3(y1, wf2, cout, cout, bias=c2.bias.detach(), act=False)                    # gan.py:259
+        y2 = _bf16(B, R // 2, R // 2, cout, device=dev)
+        call("bg_pool_act_fwd", u, None, y2, B, R // 2, R // 2, cout, SLOPE, 0)               # gan.py:260-261
+        del u
+        e = dict(k=k, x=feat, y1=y1, y2=y2, R=R, cin=cin, cout=cout, c1=c1, c2=c2)
+        if idx == 0 and fade:
+            imgp = _f32(B, 3, R // 2, R // 2, device=dev)
+            call("bg_img_avgpool2", img, imgp, B * 3, R // 2, R // 2)                         # gan.py:345
+            fr2 = critic.from_rgbs[start + 1][0]
+            d = _bf16(B, R // 2, R // 2, cout, device=dev)
+            call("bg_planes3_to_nhwc", imgp, fr2.weight.detach(), fr2.bias.detach(), None, d, B * R * R // 4,
+                 R * R // 4, cout, 3, 1, coef_of(fr2.weight), 1, SLOPE)
+            feat = axpby(d, y2, 1.0 - a_mix, a_mix)                                           # gan.py:347
+            e.update(d=d, imgp=imgp, fr2=fr2)
+        else:
+            feat = y2
+        blocks.append(e)
+        R //= 2
+    # ---- final block (gan.py:237-251)
+    blk = critic.conv_blocks[7]
+    mb = blk.conv_1[0]
+    if B % mb.group_size != 0:                    # the reference mutates the module here (gan.py:277-278)
+        mb.group_size = B
+    G = mb.group_size
+    x7 = feat
+    plane = _f32(B // G, device=dev)
+    xpad = _bf16(B, 4, 4, MBSTD_CPAD, device=dev)
+    call("bg_mbstd_fwd", x7, None, plane, xpad, B, G, 16, 512, MBSTD_CPAD, MBSTD_EPS)
+    c1 = blk.conv_1[1]
+    wf, _ = packs.conv(c1.weight, cin_pad=MBSTD_CPAD)
+    y = conv3x3(xpad, wf, MBSTD_CPAD, 512, bias=c1.bias.detach(), act=True)
+    yf = _f32(B, 512 * 16, device=dev)
+    call("bg_nhwc_to_nchw_f32", y, yf, B, 16, 512)
+    c4, l3, l5 = blk.conv_2[0], blk.conv_2[3], blk.conv_2[5]
+    h1 = linear_fwd(yf, c4.weight, c4.bias, act=True)          # 4x4 valid conv == linear over (c,h,w), gan.py:245
+    h2 = linear_fwd(h1, l3.weight, l3.bias, act=True)          # gan.py:248-249
+    pred = linear_fwd(h2, l5.weight, l5.bias, act=False)       # gan.py:250
+    tape = dict(img=img, x0=x0, fr=fr, blocks=blocks, x7=x7, xpad=xpad, y=y, yf=yf, h1=h1, h2=h2, G=G, B=B,
+                steps=steps, fade=fade, a_mix=a_mix, c1=c1, c4=c4, l3=l3, l5=l5, R=img.shape[2])
+    return pred, tape
+
+
+def critic_tangent(critic, packs: PackCache, tape, v_img):
+    """Forward-mode pass of the critic along an image-space direction v (bias-free, LeakyReLU gates taken
+    from the saved activations).  Returns the tangents at the INPUT of every weight layer; they pair with
+    the gated ones-backprop (`ghat`) in the R1 weight gradient  dP/dW_l = wgrad(v_{l-1}, ghat_l)."""
+    dev = v_img.device
+    B, R = tape["B"], tape["R"]
+    T = dict(img=v_img, blocks=[])
+    fr = tape["fr"]
+    x0 = tape["x0"]
+    c0 = x0.shape[3]
+    v = _bf16(B, R, R, c0, device=dev)
+    call("bg_planes3_to_nhwc", v_img, fr.weight.detach(), None, x0, v, B * R * R, R * R, c0, 3, 1,
+         coef_of(fr.weight), 0, SLOPE)
+    for idx, e in enumerate(tape["blocks"]):
+        cin, cout, r = e["cin"], e["cout"], e["R"]
+        wf1, _ = packs.conv(e["c1"].weight)
+        wf2, _ = packs.conv(e["c2"].weight)
+        t = dict(x=v)
+        v1 = conv3x3(v, wf1, cin, cout, gate_src=e["y1"])
+        t["y1"] = v1
+        ud = conv3x3(v1, wf2, cout, cout)
+        v2 = _bf16(B, r // 2, r // 2, cout, device=dev)
+        call("bg_pool_act_fwd", ud, e["y2"], v2, B, r // 2, r // 2, cout, SLOPE, 1)
+        del ud
+        if "d" in e:
+            a_mix = tape["a_mix"]
+            vp = _f32(B, 3, r // 2, r // 2, device=dev)
+            call("bg_img_avgpool2", v_img, vp, B * 3, r // 2, r // 2)
+            fr2 = e["fr2"]
+            vd = _bf16(B, r // 2, r // 2, cout, device=dev)
+            call("bg_planes3_to_nhwc", vp, fr2.weight.detach(), None, e["d"], vd, B * r * r // 4, r * r // 4, cout, 3,
+                 1, coef_of(fr2.weight), 0, SLOPE)
+            t["imgp"] = vp
+            v = axpby(vd, v2, 1.0 - a_mix, a_mix)
+        else:
+            v = v2
+        T["blocks"].append(t)
+    T["x7"] = v
+    G = tape["G"]
+    sdot = _f32(B // G, device=dev)
+    vpad = _bf16(B, 4, 4, MBSTD_CPAD, device=dev)
+    call("bg_mbstd_fwd", tape["x7"], v, sdot, vpad, B, G, 16, 512, MBSTD_CPAD, MBSTD_EPS)
+    T["xpad"] = vpad
+    wf, _ = packs.conv(tape["c1"].weight, cin_pad=MBSTD_CPAD)
+    vy = conv3x3(vpad, wf, MBSTD_CPAD, 512, gate_src=tape["y"])
+    vyf = _f32(B, 512 * 16, device=dev)
+    call("bg_nhwc_to_nchw_f32", vy, vyf, B, 16, 512)
+    T["yf"] = vyf
+    vh1 = gate_f32(linear_fwd(vyf, tape["c4"].weight, None, act=False), tape["h1"])
+    T["h1"] = vh1
+    vh2 = gate_f32(linear_fwd(vh1, tape["l3"].weight, None, act=False), tape["h2"])
+    T["h2"] = vh2
+    return T
+
+
+def critic_backward(critic, packs: PackCache, tape, g_pred, need: Dict[int, bool], need_img: bool,
+                    keep: Optional[dict] = None, r1: Optional[tuple] = None):
+    """Reverse pass of critic_forward seeded with g_pred (B,1).
+
+    need[id(p)] -> produce that parameter gradient.  keep: dict that receives the gated gradient at every
+    weight layer's output (the `ghat` chain of the R1 penalty when seeded with ones).  r1=(T, ghat): adds
+    the second-order R1 terms — wgrad(v, ghat) into every weight gradient and the minibatch-stddev
+    curvature into the activation gradient (SURVEY.md §7 hard part 1).
+    Returns (grads {id(param): tensor}, g_img or None).
+    """
+    dev = g_pred.device
+    B, G = tape["B"], tape["G"]
+    grads: Dict[int, torch.Tensor] = {}
+    T, H = r1 if r1 is not None else (None, None)
+
+    def want(p):
+        return need.get(id(p), False)
+
+    def lin_grads(layer, gy, x, gy2=None, x2=None):
+        if want(layer.weight) or want(layer.bias):
+            dw, db = linear_bwd_weight(gy, x, layer.weight)
+            if gy2 is not None:                   # R1: + ghat^T v   (no bias term: the tangent pass is bias-free)
+                linear_bwd_weight(gy2, x2, layer.weight, into=dw, into_b=None)
+            if want(layer.weight):
+                grads[id(layer.weight)] = dw
+            if want(layer.bias):
+                grads[id(layer.bias)] = db
+
+    g_pred = g_pred.detach().float().contiguous()
+    c1, c4, l3, l5 = tape["c1"], tape["c4"], tape["l3"], tape["l5"]
+    # ---- head: Linear(512,1) <- LReLU <- Linear(512,512) <- LReLU <- conv4x4 (gan.py:244-251)
+    lin_grads(l5, g_pred, tape["h2"], H["pred"] if H else None, T["h2"] if T else None)
+    gh2 = gate_f32(linear_bwd_input(g_pred, l5.weight, packs), tape["h2"])
+    lin_grads(l3, gh2, tape["h1"], H["h2"] if H else None, T["h1"] if T else None)
+    gh1 = gate_f32(linear_bwd_input(gh2, l3.weight, packs), tape["h1"])
+    lin_grads(c4, gh1, tape["yf"], H["h1"] if H else None, T["yf"] if T else None)
+    gyf = linear_bwd_input(gh1, c4.weight, packs)                                   # (B, 8192) NCHW order
+    gy = _bf16(B, 4, 4, 512, device=dev)
+    call("bg_nchw_f32_to_nhwc", gyf, tape["y"], gy, B, 16, 512, SLOPE)             # + LReLU gate of conv_1
+    if keep is not None:
+        keep.update(pred=g_pred, h2=gh2, h1=gh1, y=gy)
+    # ---- conv_1 of the final block on the 513(->576)-channel input
+    if want(c1.weight):
+        grads[id(c1.weight)] = conv_wgrad(tape["xpad"], gy, c1.weight,
+                                          extra=(T["xpad"], H["y"]) if T else None)
+    if want(c1.bias):
+        grads[id(c1.bias)] = channel_wsum(gy, None, 0, 16, 0, 0)[0].clone()
+    _, wd = packs.conv(c1.weight, cin_pad=MBSTD_CPAD)
+    gxpad = conv3x3(gy, wd, 512, MBSTD_CPAD)
+    if keep is not None:
+        keep["xpad"] = gxpad
+    gs_ws = _f32(2 * (B // G), device=dev)
+    gx = _bf16(B, 4, 4, 512, device=dev)
+    call("bg_mbstd_bwd", tape["x7"], T["x7"] if T else None, gxpad, H["xpad"] if H else None, gs_ws, gx, B, G, 16,
+         512, MBSTD_CPAD, MBSTD_EPS)
+
+    g_img = None
+    if need_img:
+        g_img = torch.zeros_like(tape["img"])
+    blocks = tape["blocks"]
+    for idx in reversed(range(len(blocks))):
+        e = blocks[idx]
+        t = T["blocks"][idx] if T else None
+        h = H["blocks"][idx] if H else None
+        kk = dict() if keep is not None else None
+        cin, cout, r = e["cin"], e["cout"], e["R"]
+        c1b, c2b = e["c1"], e["c2"]
+        if "d" in e:                                             # fade-in lerp (gan.py:342-347)
+            a_mix = tape["a_mix"]
+            fr2 = e["fr2"]
+            gd = axpby(gx, None, 1.0 - a_mix, 0.0)
+            gdp = torch.empty_like(gd)
+            call("bg_act_gate", gd, e["d"], gdp, gd.numel(), SLOPE)
+            if kk is not None:
+                kk["d"] = gdp
+            hw = (r // 2) * (r // 2)
+            if want(fr2.weight) or want(fr2.bias):
+                ws = channel_wsum(gdp, e["imgp"], 3, hw, 3 * hw, hw)
+                dw = ws[1:4]
+                if t is not None:
+                    dw = dw + channel_wsum(h["d"], t["imgp"], 3, hw, 3 * hw, hw)[1:4]
+                if want(fr2.weight):
+                    grads[id(fr2.weight)] = (dw * coef_of(fr2.weight)).t().reshape(cout, 3, 1, 1).contiguous()
+                if want(fr2.bias):
+                    grads[id(fr2.bias)] = ws[0].clone()
+            if need_img:
+                gp_img = _f32(B, 3, r // 2, r // 2, device=dev)
+                call("bg_nhwc_to_planes3", gdp, fr2.weight.detach(), None, gp_img, B * hw, hw, cout, 3, 1,
+                     coef_of(fr2.weight))
+                call("bg_img_avgpool2_bwd", gp_img, g_img, B * 3, r // 2, r // 2, 1.0, 1)
+            gy2 = axpby(gx, None, a_mix, 0.0)
+        else:
+            gy2 = gx
+        gu = _bf16(B, r, r, cout, device=dev)
+        call("bg_pool_act_bwd", gy2, e["y2"], gu, B, r // 2, r // 2, cout, SLOPE)              # pool + LReLU adjoint
+        if kk is not None:
+            kk["u"] = gu
+        if want(c2b.weight):
+            grads[id(c2b.weight)] = conv_wgrad(e["y1"], gu, c2b.weight, extra=(t["y1"], h["u"]) if t else None)
+        if want(c2b.bias):
+            grads[id(c2b.bias)] = channel_wsum(gu, None, 0, r * r, 0, 0)[0].clone()
+        _, wd2 = packs.conv(c2b.weight)
+        g1 = conv3x3(gu, wd2, cout, cout, gate_src=e["y1"])                                    # dgrad + LReLU gate
+        del gu
+        if kk is not None:
+            kk["y1"] = g1
+        if want(c1b.weight):
+            grads[id(c1b.weight)] = conv_wgrad(e["x"], g1, c1b.weight, extra=(t["x"], h["y1"]) if t else None)
+        if want(c1b.bias):
+            grads[id(c1b.bias)] = channel_wsum(g1, None, 0, r * r, 0, 0)[0].clone()
+        _, wd1 = packs.conv(c1b.weight)
+        first = idx == 0
+        if first:
+            gx = conv3x3(g1, wd1, cout, cin, gate_src=tape["x0"])                              # gate of fromRGB's LReLU
+        else:
+            gx = conv3x3(g1, wd1, cout, cin)
+        del g1
+        if keep is not None:
+            keep.setdefault("blocks", [None] * len(blocks))[idx] = kk
+    # ---- fromRGB (gan.py:351-355); when steps == 1 gx is the (ungated) gradient at x7 = x0
+    fr = tape["fr"]
+    x0 = tape["x0"]
+    R = tape["R"]
+    c0 = x0.shape[3]
+    if not blocks:
+        g0 = torch.empty_like(gx)
+        call("bg_act_gate", gx, x0, g0, gx.numel(), SLOPE)
+    else:
+        g0 = gx
+    if keep is not None:
+        keep["x0"] = g0
+    if want(fr.weight) or want(fr.bias):
+        ws = channel_wsum(g0, tape["img"], 3, R * R, 3 * R * R, R * R)
+        dw = ws[1:4]
+        if T is not None:
+            dw = dw + channel_wsum(H["x0"], T["img"], 3, R * R, 3 * R * R, R * R)[1:4]
+        if want(fr.weight):
+            grads[id(fr.weight)] = (dw * coef_of(fr.weight)).t().reshape(c0, 3, 1, 1).contiguous()
+        if want(fr.bias):
+            grads[id(fr.bias)] = ws[0].clone()
+    if need_img:
+        gi = _f32(B, 3, R, R, device=dev)
+        call("bg_nhwc_to_planes3", g0, fr.weight.detach(), None, gi, B * R * R, R * R, c0, 3, 1, coef_of(fr.weight))
+        call("bg_axpby_f32", g_img, gi, g_img, gi.numel(), 1.0, 1.0)
+    return grads, g_img
+
+
+def critic_r1_step(critic, packs: PackCache, tape_fake, pred_fake, tape_real, pred_real, c_lambda):
+    """Critic.get_r1_loss (gan.py:393-412): loss value + gradients of every active critic parameter.
+
+    loss = mean softplus(-D(real)) + mean softplus(D(fake)) + lambda/2 * mean_n ||d sum D(real) / d real_n||^2
+    The double-backward autograd would run is scheduled by hand:
+      1. fake branch: ordinary backward seeded with sigmoid(D(fake))/B;
+      2. real branch: `ghat` = gated backprop of ones down to the image -> g_x, penalty, v0 = (lambda/B) g_x;
+      3. tangent forward of v0 through the critic (bias-free, saved gates);
+      4. one combined backward seeded with -sigmoid(-D(real))/B whose weight gradients contract over the
+         doubled K  [x ; v] . [ybar ; ghat]  and whose activation gradient picks up the minibatch-stddev
+         curvature term.
+    Returns (loss tensor (), grads {id(param): tensor}).
+    """
+    dev = pred_real.device
+    B = pred_real.shape[0]
+    steps, fade = tape_real["steps"], tape_real["fade"]
+    params = critic_params(critic, steps, fade)
+    need = {id(p): bool(p.requires_grad) for p in params}
+    terms = _f32(3, device=dev)
+    seed_f = _f32(B, 1, device=dev)
+    seed_r = _f32(B, 1, device=dev)
+    pf = pred_fake.detach().float().contiguous()
+    pr = pred_real.detach().float().contiguous()
+    call("bg_logistic_loss", pf, B, 1.0, terms[0:1], seed_f, 1.0)         # softplus(D(fake)).mean(), gan.py:406
+    call("bg_logistic_loss", pr, B, -1.0, terms[1:2], seed_r, 1.0)        # softplus(-D(real)).mean(), gan.py:396
+    grads_f, _ = critic_backward(critic, packs, tape_fake, seed_f, need, need_img=False)
+    ones = torch.ones(B, 1, device=dev)
+    ghat: dict = {}
+    _, g_x = critic_backward(critic, packs, tape_real, ones, {}, need_img=True, keep=ghat)   # gan.py:398-400
+    call("bg_sumsq", g_x, g_x.numel(), float(c_lambda) / 2.0 / B, terms[2:3])                # gan.py:401-404
+    v0 = torch.empty_like(g_x)
+    call("bg_axpby_f32", g_x, None, v0, g_x.numel(), float(c_lambda) / B, 0.0)
+    T = critic_tangent(critic, packs, tape_real, v0)
+    grads_r, _ = critic_backward(critic, packs, tape_real, seed_r, need, need_img=False, r1=(T, ghat))
+    grads = {}
+    for p in params:
+        k = id(p)
+        if not need[k]:
+            continue
+        gf, gr = grads_f.get(k), grads_r.get(k)
+        if gf is None or gr is None:
+            raise RuntimeError("internal: missing critic gradient")
+        call("bg_axpby_f32", gf, gr, gf, gf.numel(), 1.0, 1.0)
+        grads[k] = gf
+    loss = terms.sum()
+    return loss, grads, g_x

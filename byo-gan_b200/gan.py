@@ -1,0 +1,292 @@
+"""Drop-in replacement for the reference's ``gan.py`` (BYO-GAN), running on hand-written sm_100a kernels.
+
+Import it as ``gan`` (put ``byo-gan_b200/`` first on ``sys.path``): ``main.py`` / ``train.py`` /
+``generate_samples.py`` / ``interpolate.py`` of the reference then run unchanged, because this module keeps
+
+* the constructors ``Generator()`` / ``Critic()`` (no arguments; reference gan.py:151-181, 301-329),
+* the attribute tree and therefore the ``state_dict`` keys/shapes of a reference checkpoint
+  (``to_w_noise.0.layers.i.0.weight`` ... ``conv_blocks.7.conv_2.5.bias``; 111 + 52 fp32 tensors),
+* ``Generator.forward(z_noise, noise=None, steps=1, alpha=None)`` (gan.py:183-222),
+  ``Critic.forward(images, steps=1, alpha=None)`` (gan.py:331-349),
+* the loss methods ``get_r1_loss`` / ``get_wgan_loss`` with the reference's signatures; like the reference,
+  ``Critic.get_r1_loss`` runs its own backward and fills ``.grad`` (gan.py:393-412).
+
+Everything between those calls is different: feature maps live in NHWC bf16, every convolution is a
+tcgen05 implicit GEMM, and forward, backward and the R1 double-backward are scheduled by ``engine.py`` over
+the C ABI of ``libbg_b200.so`` (``include/bg_b200.h``).  The sub-modules below only HOLD parameters (so
+optimizers, ``requires_grad`` toggling, ``zero_grad`` and checkpoints work as in the reference); they have
+no forward of their own.  There is no CPU path: calling the model with CPU tensors raises.
+
+Opt-in extension (not in the reference, default off): style mixing — ``Generator.forward(..., z2=, crossover=)``
+feeds blocks ``>= crossover`` with the mapped second latent.
+"""
+from math import sqrt
+
+import torch
+from torch import nn
+
+import engine
+from engine import PackCache
+
+
+# --------------------------------------------------------------------------------------------------------
+# parameter holders (same construction order and initialisation as the reference, so a given
+# torch.manual_seed yields the same initial weights)
+# --------------------------------------------------------------------------------------------------------
+class _Holder(nn.Module):
+    def forward(self, *args, **kwargs):  # pragma: no cover - guard
+        raise RuntimeError(
+            f"{type(self).__name__} only holds parameters in the B200 build; call Generator/Critic.forward")
+
+
+class EqualizedLinear(nn.Linear):
+    """N(0,1) weight, zero bias, runtime scale sqrt(2/fan_in) applied inside the kernels (gan.py:7-17)."""
+
+    def __init__(self, in_features, out_features):
+        super().__init__(in_features, out_features)
+        with torch.no_grad():
+            self.weight.normal_()
+            self.bias.zero_()
+        self.equalized_coefficient = sqrt(2 / in_features)
+
+    forward = _Holder.forward
+
+
+class EqualizedConv2d(nn.Conv2d):
+    """N(0,1) weight, zero bias, runtime scale sqrt(2/(Cin*k*k)) applied at weight-pack time (gan.py:20-38)."""
+
+    def __init__(self, in_chan, out_chan, kernel_size, padding=0):
+        super().__init__(in_chan, out_chan, kernel_size=kernel_size, padding=padding)
+        with torch.no_grad():
+            self.weight.normal_()
+            self.bias.zero_()
+        self.equalized_coefficient = sqrt(2 / (in_chan * kernel_size * kernel_size))
+
+    forward = _Holder.forward
+
+
+class InjectSecondaryNoise(_Holder):
+    def __init__(self, channels):
+        super().__init__()
+        self.weights = nn.Parameter(torch.zeros((1, channels, 1, 1)))      # gan.py:44
+
+
+class AdaINBlock(_Holder):
+    def __init__(self, in_channel, style_dim=512):
+        super().__init__()
+        self.style = EqualizedLinear(style_dim, in_channel * 2)            # gan.py:60
+        with torch.no_grad():                                              # gan.py:62-63
+            self.style.bias[:in_channel] = 1
+            self.style.bias[in_channel:] = 0
+
+
+class StyleConvBlock(_Holder):
+    def __init__(self, in_chan, out_chan, is_initial=False):
+        super().__init__()
+        self.is_initial = is_initial
+        if is_initial:
+            self.conv = nn.Parameter(torch.randn(1, in_chan, 4, 4))        # gan.py:81
+        else:
+            self.conv = EqualizedConv2d(in_chan, out_chan, kernel_size=3, padding=1)
+        self.inject_noise = InjectSecondaryNoise(out_chan)
+        self.adain = AdaINBlock(out_chan)
+
+
+class StyleGanBlock(_Holder):
+    def __init__(self, in_chan, out_chan, is_initial=False, does_upsample=True):
+        super().__init__()
+        if is_initial and does_upsample:
+            raise ValueError("You cannot use the Starting Constant and Upsample.")   # gan.py:105-106
+        self.is_initial = is_initial
+        self.does_upsample = does_upsample
+        self.conv_1 = StyleConvBlock(in_chan, out_chan, is_initial=is_initial)
+        self.conv_2 = StyleConvBlock(out_chan, out_chan)
+
+
+class _Slot(_Holder):
+    """Parameter-free placeholder keeping nn.Sequential indices equal to the reference's
+    (LeakyReLU / AvgPool2d / Flatten positions, gan.py:145,238-262,353-355)."""
+
+
+class MappingLayers(_Holder):
+    def __init__(self, channels=512):
+        super().__init__()
+        self.layers = nn.Sequential(*[nn.Sequential(EqualizedLinear(channels, channels), _Slot()) for _ in range(8)])
+
+
+class MiniBatchStdDev(_Holder):
+    def __init__(self, group_size=4):
+        super().__init__()
+        self.group_size = group_size           # mutated like the reference when B % group_size != 0 (gan.py:277-278)
+
+
+class CriticBlock(_Holder):
+    def __init__(self, in_chan, out_chan, is_final_layer=False):
+        super().__init__()
+        self.is_final_layer = is_final_layer
+        if is_final_layer:
+            self.conv_1 = nn.Sequential(MiniBatchStdDev(), EqualizedConv2d(in_chan + 1, out_chan, 3, padding=1), _Slot())
+            self.conv_2 = nn.Sequential(EqualizedConv2d(out_chan, out_chan, 4), _Slot(), _Slot(),
+                                        EqualizedLinear(out_chan, out_chan), _Slot(), EqualizedLinear(out_chan, 1))
+        else:
+            self.conv_1 = nn.Sequential(EqualizedConv2d(in_chan, out_chan, 3, padding=1), _Slot())
+            self.conv_2 = nn.Sequential(EqualizedConv2d(out_chan, out_chan, 3, padding=1), _Slot(), _Slot())
+
+
+# --------------------------------------------------------------------------------------------------------
+# autograd glue: one node per network
+# --------------------------------------------------------------------------------------------------------
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(f"{what} must be a CUDA tensor: the B200 build has no CPU path")
+
+
+class _GeneratorFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gen, steps, alpha, crossover, n_noise, z, z2, *rest):
+        noise, params = rest[:n_noise], rest[n_noise:]
+        track = any(ctx.needs_input_grad)   # all False under torch.no_grad(): sampling keeps no tape
+        img, tape = engine.generator_forward(gen, gen._packs, z, noise, steps, alpha, z2=z2, crossover=crossover,
+                                             keep_tape=track)
+        ctx.gen, ctx.tape, ctx.params, ctx.n_noise = gen, tape, params, n_noise
+        ctx.set_materialize_grads(False)
+        return img
+
+    @staticmethod
+    def backward(ctx, g_img):
+        head = (None,) * 5
+        n_noise, params = ctx.n_noise, ctx.params
+        if g_img is None:
+            return head + (None, None) + (None,) * (n_noise + len(params))
+        need = {id(p): ctx.needs_input_grad[7 + n_noise + i] for i, p in enumerate(params)}
+        grads, dz, dz2 = engine.generator_backward(ctx.gen, ctx.gen._packs, ctx.tape, g_img, need,
+                                                   need_z=ctx.needs_input_grad[5], need_z2=ctx.needs_input_grad[6])
+        return head + (dz, dz2) + (None,) * n_noise + tuple(grads.get(id(p)) for p in params)
+
+
+class _CriticFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, critic, steps, alpha, images, *params):
+        pred, tape = engine.critic_forward(critic, critic._packs, images, steps, alpha)
+        ctx.critic, ctx.tape, ctx.params = critic, tape, params
+        critic._last_tape = tape
+        ctx.set_materialize_grads(False)
+        return pred
+
+    @staticmethod
+    def backward(ctx, g_pred):
+        params = ctx.params
+        if g_pred is None:
+            return (None,) * (4 + len(params))
+        need = {id(p): ctx.needs_input_grad[4 + i] for i, p in enumerate(params)}
+        grads, g_img = engine.critic_backward(ctx.critic, ctx.critic._packs, ctx.tape, g_pred, need,
+                                              need_img=ctx.needs_input_grad[3])
+        return (None, None, None, g_img) + tuple(grads.get(id(p)) for p in params)
+
+
+class _LogisticLossFn(torch.autograd.Function):
+    """mean softplus(sign * pred) with its gradient from the same kernel (gan.py:228)."""
+
+    @staticmethod
+    def forward(ctx, pred, sign):
+        p = pred.detach().float().contiguous()
+        n = p.numel()
+        loss = torch.empty(1, device=p.device)
+        seed = torch.empty_like(p)
+        engine.call("bg_logistic_loss", p, n, float(sign), loss, seed, 1.0)
+        ctx.save_for_backward(seed)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (seed,) = ctx.saved_tensors
+        return seed * g, None
+
+
+# --------------------------------------------------------------------------------------------------------
+# public modules
+# --------------------------------------------------------------------------------------------------------
+class Generator(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.to_w_noise = nn.Sequential(MappingLayers())
+        self.gen_blocks = nn.ModuleList(
+            [StyleGanBlock(512, 512, is_initial=True, does_upsample=False)]
+            + [StyleGanBlock(ci, co) for ci, co in engine.GEN_CHANNELS[1:]])
+        self.to_rgbs = nn.ModuleList([EqualizedConv2d(co, 3, kernel_size=1) for _, co in engine.GEN_CHANNELS])
+        self._packs = PackCache()
+
+    def forward(self, z_noise, noise=None, steps=1, alpha=None, z2=None, crossover=None):
+        _require_cuda(z_noise, "z_noise")
+        steps = int(steps)
+        if steps > len(self.gen_blocks):
+            return None                                   # the reference falls off its loop (gan.py:201-222)
+        batch = len(z_noise)
+        if noise is None:                                 # gan.py:189-197: torch global RNG, on z's device
+            noise = [torch.randn(batch, 1, 4 * 2 ** i, 4 * 2 ** i, device=z_noise.device) for i in range(steps)]
+        noise = tuple(noise[:steps])
+        fade = alpha is not None and steps > 1
+        params = engine.generator_params(self, steps, fade)
+        return _GeneratorFn.apply(self, steps, alpha, crossover, len(noise), z_noise, z2, *noise, *params)
+
+    def get_wgan_loss(self, crit_fake_pred):
+        return -crit_fake_pred.mean()                     # gan.py:224-225
+
+    def get_r1_loss(self, crit_fake_pred):
+        return _LogisticLossFn.apply(crit_fake_pred, -1.0)   # softplus(-pred).mean(), gan.py:227-228
+
+
+class Critic(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.from_rgbs = nn.ModuleList([self.gen_from_rgbs(ci) for ci, _ in engine.CRITIC_CHANNELS])
+        self.conv_blocks = nn.ModuleList(
+            [CriticBlock(ci, co) for ci, co in engine.CRITIC_CHANNELS[:7]] + [CriticBlock(512, 512, is_final_layer=True)])
+        self._packs = PackCache()
+        self._last_tape = None
+
+    def gen_from_rgbs(self, out_chan, image_chan=3):
+        return nn.Sequential(EqualizedConv2d(image_chan, out_chan, kernel_size=1), _Slot())
+
+    def forward(self, images, steps=1, alpha=None):
+        _require_cuda(images, "images")
+        steps = int(steps)
+        fade = alpha is not None and steps > 1
+        params = engine.critic_params(self, steps, fade)
+        pred = _CriticFn.apply(self, steps, alpha, images, *params)
+        pred._bg_tape = self._last_tape                   # lets get_r1_loss schedule the double-backward by hand
+        self._last_tape = None
+        return pred
+
+    def get_wgan_loss(self, crit_fake_pred, crit_real_pred, real_im, steps, alpha, c_lambda=1):
+        # The reference's implementation dereferences self.device and an undefined fake_im (gan.py:367-372)
+        # and therefore raises before doing any work; the WGAN-GP path is out of scope.
+        raise AttributeError("'Critic' object has no attribute 'device' (WGAN-GP is dead code in the reference, "
+                             "gan.py:357-391; train with use_r1=True)")
+
+    def get_r1_loss(self, crit_fake_pred, crit_real_pred, real_im, fake_im, steps, alpha, c_lambda=1):
+        """gan.py:393-412.  Runs the backward itself (like the reference's r1_loss.backward()) and accumulates
+        into .grad of every critic parameter that requires grad; returns the loss value."""
+        tape_f = getattr(crit_fake_pred, "_bg_tape", None)
+        tape_r = getattr(crit_real_pred, "_bg_tape", None)
+        if tape_f is None or tape_r is None:
+            raise RuntimeError(
+                "get_r1_loss needs the predictions returned by this Critic's forward (they carry the saved "
+                "activations).  Under multi-device nn.DataParallel the gather drops them: launch one process "
+                "per GPU instead (see INTEGRATION.md).")
+        loss, grads, g_x = engine.critic_r1_step(self, self._packs, tape_f, crit_fake_pred, tape_r, crit_real_pred,
+                                                 c_lambda)
+        hook = getattr(self, "_grad_ready_hook", None)
+        for p in engine.critic_params(self, tape_r["steps"], tape_r["fade"]):
+            g = grads.get(id(p))
+            if g is None:
+                continue
+            g = g.reshape(p.shape)
+            if p.grad is None:
+                p.grad = g
+            else:
+                p.grad.add_(g)
+            if hook is not None:
+                hook(p)
+        self.last_real_image_grad = g_x                   # d sum(D(real)) / d real, what autograd.grad returned
+        return loss

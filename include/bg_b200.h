@@ -47,9 +47,10 @@ int bg_conv_fprop(const void* x, const void* wpack, void* out, int N, int H, int
                   float slope, void* stream);
 
 /* ---- weight gradient of the 3x3 conv (autograd convolution_backward / _convolution_double_backward) ---
- * dw_packed: fp32 [9][Cout][Cin] (overwritten) = sum_pixels g[p,co] * x[p+tap,ci]. */
+ * dw_packed: fp32 [9][Cout][Cin] (overwritten, or += when accumulate) = sum_pixels g[p,co] * x[p+tap,ci].
+ * accumulate=1 is the second half of the R1 "doubled-K" weight gradient wgrad(x, ybar) + wgrad(v, ghat). */
 int bg_conv_wgrad(const void* x, const void* g, float* dw_packed, int N, int H, int W, int Cin, int Cout,
-                  void* stream);
+                  int accumulate, void* stream);
 
 /* ---- LeakyReLU backward gate (gan.py:86,145,241...): out = g * (y > 0 ? 1 : slope); n elements -------- */
 int bg_act_gate(const void* g, const void* y, void* out, size_t n, float slope, void* stream);
@@ -75,11 +76,12 @@ int bg_channel_wsum(const void* g, const float* planes, float* out, size_t P, in
                     size_t plane_stride, int nplanes, void* stream);
 
 /* ---- fromRGB / toRGB 1x1 convolutions (gan.py:172-179, 351-355) ----------------------------------------
- * planes3_to_nhwc: out[p,c] = act(coef * sum_j img[n,j,hw] * Wm[c*ws_c + j*ws_j] + bias[c])
+ * planes3_to_nhwc: out[p,c] = act(coef * sum_j img[n,j,hw] * Wm[c*ws_c + j*ws_j] + bias[c]) * gate(gate_src[p,c])
+ *   (gate_src may be NULL; with it and act=0/bias=NULL this is the R1 tangent pass through fromRGB)
  * nhwc_to_planes3: out[n,j,hw] = coef * sum_c x[p,c] * Wm[c*ws_c + j*ws_j] + bias[j]
  * (weight (C,3,1,1): ws_c=3, ws_j=1;  weight (3,C,1,1): ws_c=1, ws_j=C) */
-int bg_planes3_to_nhwc(const float* img, const float* Wm, const float* bias, void* out, size_t P, int HW, int C,
-                       int ws_c, int ws_j, float coef, int act, float slope, void* stream);
+int bg_planes3_to_nhwc(const float* img, const float* Wm, const float* bias, const void* gate_src, void* out, size_t P,
+                       int HW, int C, int ws_c, int ws_j, float coef, int act, float slope, void* stream);
 int bg_nhwc_to_planes3(const void* x, const float* Wm, const float* bias, float* out, size_t P, int HW, int C,
                        int ws_c, int ws_j, float coef, void* stream);
 
@@ -96,6 +98,53 @@ int bg_adain_bwd_reduce(const void* g, const void* a, const float* stats, float*
                         float eps, void* stream);
 int bg_adain_bwd_apply(const void* g, const void* a, const float* stats, const float* style, const float* bsums,
                        void* out, int N, int HW, int C, float eps, float slope, int gate, void* stream);
+
+/* ---- EqualizedLinear (gan.py:16-17): mapping network (gan.py:130-148), AdaIN style FCs (gan.py:60,66), critic
+ * head FCs and, on the NCHW-flattened 4x4 map, the critic's 4x4 valid conv (gan.py:245-250).  All fp32.
+ * fwd: y[M,N] = act(coef * x[M,K] W[N,K]^T + bias).  The input gradient is the same call on the transposed
+ * weight (bg_transpose_f32).  bwd_weight: dW[N,K] (+)= coef * gy^T x;  db[N] (+)= sum_m gy (db may be NULL). */
+int bg_linear_fwd(const float* x, const float* W, const float* bias, float* y, int M, int N, int K, float coef, int act,
+                  float slope, void* stream);
+int bg_linear_bwd_weight(const float* gy, const float* x, float* dW, float* db, int M, int N, int K, float coef,
+                         int accumulate, void* stream);
+int bg_transpose_f32(const float* in, float* out, int R, int C, void* stream);
+int bg_act_gate_f32(const float* g, const float* y, float* out, size_t n, float slope, void* stream);
+int bg_axpby_f32(const float* a, const float* b, float* out, size_t n, float ca, float cb, void* stream);
+
+/* ---- learned 4x4 constant + noise + LeakyReLU (StyleConvBlock is_initial, gan.py:81,92,96-97) and its gradient */
+int bg_const_noise_act(const float* cst, const float* noise, const float* nw, void* a, int N, int HW, int C,
+                       float slope, void* stream);
+int bg_const_bwd(const void* g, float* dconst, int N, int HW, int C, void* stream);
+
+/* ---- image-plane fade ops, NCHW fp32 viewed as P = B*3 planes ------------------------------------------
+ * avgpool2: F.avg_pool2d(images, 2) (gan.py:345) and its adjoint (gimg (+)= .25*scale*g).
+ * up2_lerp: torch.lerp(bilinear_up2(small), large, alpha) (gan.py:213-220); up2_bwd: gsmall = scale * up2^T(g). */
+int bg_img_avgpool2(const float* img, float* out, int P, int Ho, int Wo, void* stream);
+int bg_img_avgpool2_bwd(const float* g, float* gimg, int P, int Ho, int Wo, float scale, int accumulate, void* stream);
+int bg_img_up2_lerp(const float* small, const float* large, float* out, int P, int H, int W, float alpha,
+                    void* stream);
+int bg_img_up2_bwd(const float* g, float* gsmall, int P, int H, int W, float scale, void* stream);
+/* sums[3] = per-colour sum of g (B,3,HW): toRGB bias gradient */
+int bg_plane_sums(const float* g, float* sums, int B, int HW, void* stream);
+
+/* ---- nn.Flatten boundary of the critic head (gan.py:247): NHWC bf16 <-> NCHW fp32 (gate_src may be NULL) */
+int bg_nhwc_to_nchw_f32(const void* x, float* out, int N, int HW, int C, void* stream);
+int bg_nchw_f32_to_nhwc(const float* g, const void* gate_src, void* out, int N, int HW, int C, float slope,
+                        void* stream);
+
+/* ---- MiniBatchStdDev (gan.py:273-298), x: (B,HW,C) bf16, G = group size, M = B/G ------------------------
+ * fwd : plane[M] = s (v NULL) or the tangent s-dot along v (v given); xpad (B,HW,Cpad) = [x or v | plane | 0].
+ * bwd : gx (B,HW,C) = gpad[..., :C] + J^T gs  (+ second-order term with tangent v and gs2 when v/gpad2 given),
+ *       gs = per-slot sum of gpad[..., C], gs2 likewise from gpad2.  gs_ws: fp32 workspace of 2*M. */
+int bg_mbstd_fwd(const void* x, const void* v, float* plane, void* xpad, int B, int G, int HW, int C, int Cpad,
+                 float eps, void* stream);
+int bg_mbstd_bwd(const void* x, const void* v, const void* gpad, const void* gpad2, float* gs_ws, void* gx, int B, int G,
+                 int HW, int C, int Cpad, float eps, void* stream);
+
+/* ---- loss terms (gan.py:228,396,406): loss[0] = mean softplus(sign*pred); seed[i] = seed_scale * dloss/dpred_i
+ * (seed may be NULL).  sumsq: out[0] = scale * sum x^2 (the R1 penalty, gan.py:401-404). */
+int bg_logistic_loss(const float* pred, int n, float sign, float* loss, float* seed, float seed_scale, void* stream);
+int bg_sumsq(const float* x, size_t n, float scale, float* out, void* stream);
 
 #ifdef __cplusplus
 }

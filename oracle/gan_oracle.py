@@ -136,6 +136,33 @@ def make_images(batch: int, steps: int, seed: int) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------------------------------
+# optional bf16 emulation: with QUANT[0] = True the oracle rounds conv weights and every feature map that
+# the CUDA path stores in bf16 (forward value AND its gradient) to bf16.  This is the yardstick that separates
+# "bf16 storage noise" from "wrong arithmetic" in the GPU parity tests; the fp32 mode is the reference.
+# --------------------------------------------------------------------------------------------------------
+QUANT = [False]
+
+
+class _RoundBf16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+def q(x):
+    return _RoundBf16.apply(x) if QUANT[0] else x
+
+
+def qw(w):
+    """weights are rounded once (value only): the master copy and its gradient stay fp32"""
+    return (w.to(torch.bfloat16).to(w.dtype) - w).detach() + w if QUANT[0] else w
+
+
+# --------------------------------------------------------------------------------------------------------
 # layers
 # --------------------------------------------------------------------------------------------------------
 def eq_coef(weight: torch.Tensor) -> float:
@@ -151,7 +178,8 @@ def eq_linear(x, weight, bias):
 
 def eq_conv2d(x, weight, bias, padding=0):
     """EqualizedConv2d.forward, gan.py:29-38 (stride 1, no dilation/groups anywhere in the model)."""
-    return F.conv2d(x, weight * eq_coef(weight), bias, padding=padding)
+    return F.conv2d(x, qw(weight * eq_coef(weight)) if weight.shape[-1] == 3 else weight * eq_coef(weight), bias,
+                    padding=padding)
 
 
 def lrelu(x):
@@ -178,18 +206,18 @@ def style_conv(P, prefix, x, w_lat, noise, batch, initial=False):
     else:
         out = eq_conv2d(x, P[f"{prefix}.conv.weight"], P[f"{prefix}.conv.bias"], padding=1)  # gan.py:94
     out = out + P[f"{prefix}.inject_noise.weights"] * noise        # gan.py:52
-    out = lrelu(out)                                               # gan.py:97
+    out = q(lrelu(out))                                            # gan.py:97
     style = eq_linear(w_lat, P[f"{prefix}.adain.style.weight"], P[f"{prefix}.adain.style.bias"])  # gan.py:66
     c = out.shape[1]
     gamma = style[:, :c, None, None]
     beta = style[:, c:, None, None]
-    return gamma * instance_norm(out) + beta                       # gan.py:69
+    return q(gamma * instance_norm(out) + beta)                    # gan.py:69
 
 
 def synthesis_block(P, k, x, w_lat, noise, batch):
     """StyleGanBlock.forward, gan.py:118-127; both convs receive the same noise map."""
     if k > 0:
-        x = bilinear_up2(x)
+        x = q(bilinear_up2(x))
     out = style_conv(P, f"gen_blocks.{k}.conv_1", x, w_lat, noise, batch, initial=(k == 0))
     return style_conv(P, f"gen_blocks.{k}.conv_2", out, w_lat, noise, batch)
 
@@ -254,18 +282,18 @@ def minibatch_stddev(x, group_size: int = 4):
 
 def from_rgb(P, k, img):
     """gen_from_rgbs, gan.py:351-355: 1x1 EqualizedConv2d + LeakyReLU."""
-    return lrelu(eq_conv2d(img, P[f"from_rgbs.{k}.0.weight"], P[f"from_rgbs.{k}.0.bias"]))
+    return q(lrelu(eq_conv2d(img, P[f"from_rgbs.{k}.0.weight"], P[f"from_rgbs.{k}.0.bias"])))
 
 
 def critic_block(P, k, x, group_size: int = 4):
     """CriticBlock.forward, gan.py:264-265 with the layer lists of gan.py:237-262."""
     p = f"conv_blocks.{k}"
     if k < 7:
-        x = lrelu(eq_conv2d(x, P[f"{p}.conv_1.0.weight"], P[f"{p}.conv_1.0.bias"], padding=1))
-        x = eq_conv2d(x, P[f"{p}.conv_2.0.weight"], P[f"{p}.conv_2.0.bias"], padding=1)
-        return lrelu(F.avg_pool2d(x, 2)), group_size       # pool BEFORE the activation, gan.py:258-262
+        x = q(lrelu(eq_conv2d(x, P[f"{p}.conv_1.0.weight"], P[f"{p}.conv_1.0.bias"], padding=1)))
+        x = q(eq_conv2d(x, P[f"{p}.conv_2.0.weight"], P[f"{p}.conv_2.0.bias"], padding=1))
+        return q(lrelu(F.avg_pool2d(x, 2))), group_size    # pool BEFORE the activation, gan.py:258-262
     x, group_size = minibatch_stddev(x, group_size)
-    x = lrelu(eq_conv2d(x, P[f"{p}.conv_1.1.weight"], P[f"{p}.conv_1.1.bias"], padding=1))
+    x = q(lrelu(eq_conv2d(q(x), P[f"{p}.conv_1.1.weight"], P[f"{p}.conv_1.1.bias"], padding=1)))
     x = lrelu(eq_conv2d(x, P[f"{p}.conv_2.0.weight"], P[f"{p}.conv_2.0.bias"]))   # 4x4 valid -> (B,512,1,1)
     x = x.flatten(1)
     x = lrelu(eq_linear(x, P[f"{p}.conv_2.3.weight"], P[f"{p}.conv_2.3.bias"]))
@@ -284,7 +312,7 @@ def critic_forward(P, images, steps: int = 1, alpha: Optional[float] = None, gro
         if j == 0 and steps > 1 and alpha is not None:
             a = min(1.0, max(0.0, alpha))
             down = from_rgb(P, start + 1, F.avg_pool2d(images, 2))     # gan.py:345
-            out = torch.lerp(down, out, a)                              # gan.py:347
+            out = q(torch.lerp(down, out, a))                           # gan.py:347
     return (out, group_size) if return_group_size else out
 
 

@@ -1,0 +1,68 @@
+"""Shared helpers for the GPU parity tests: build the CUDA modules and the oracle from the same seeded
+state, run one G+D iteration through the public API exactly as train.py:135-217 drives it."""
+import torch
+
+import gan
+from oracle import gan_oracle as O
+
+# Stated tolerances (bf16 operands, fp32 accumulation, fp32 statistics; reference is fp32):
+TOL_IMG = 2.5e-2      # rel-L2 of generated images / critic feature-level outputs
+TOL_PRED = 5e-2       # critic scores: |diff| <= TOL_PRED * (rms(pred) + 1)
+TOL_LOSS = 3e-2       # relative, losses
+TOL_GRAD_REL = 8e-2   # per-tensor rel-L2 of gradients
+TOL_GRAD_COS = 0.995  # per-tensor cosine of gradients
+
+
+def no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def build_models(seed, device="cuda"):
+    g, c = gan.Generator(), gan.Critic()
+    g.load_state_dict(O.make_state("gen", seed))
+    c.load_state_dict(O.make_state("critic", seed))
+    return g.to(device), c.to(device)
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def cos(a, b):
+    a, b = a.detach().double().flatten().cpu(), b.detach().double().flatten().cpu()
+    return (a @ b / (a.norm() * b.norm() + 1e-30)).item()
+
+
+def cuda_iteration(g, c, z_d, z_g, real, n_d, n_g, steps, alpha, lam):
+    """train.py:135-217 with the optimizer steps removed (so the D and G gradients refer to the same weights)."""
+    dev = "cuda"
+    out = {}
+    for p in c.parameters():
+        p.requires_grad = True
+    for p in g.parameters():
+        p.requires_grad = False
+    z = z_d.to(dev).requires_grad_()
+    fake = g(z, noise=[n.to(dev) for n in n_d], steps=steps, alpha=alpha)
+    real_im = real.to(dev).requires_grad_()
+    pf = c(fake.detach(), steps, alpha)
+    pr = c(real_im, steps, alpha)
+    c.zero_grad()
+    c_loss = c.get_r1_loss(pf, pr, real_im, fake, steps, alpha, lam)
+    out.update(c_loss=c_loss.detach(), fake_d=fake.detach(), pred_fake=pf.detach(), pred_real=pr.detach(),
+               d_grads={k: (p.grad.detach().clone() if p.grad is not None else None) for k, p in c.named_parameters()},
+               real_grad=c.last_real_image_grad)
+    for p in c.parameters():
+        p.requires_grad = False
+    for p in g.parameters():
+        p.requires_grad = True
+    z2 = z_g.to(dev).requires_grad_()
+    fake2 = g(z2, noise=[n.to(dev) for n in n_g], steps=steps, alpha=alpha)
+    pred = c(fake2, steps, alpha)
+    g_loss = g.get_r1_loss(pred)
+    g.zero_grad()
+    g_loss.backward()
+    out.update(g_loss=g_loss.detach(), pred_g=pred.detach(), z_grad=z2.grad.detach(),
+               g_grads={k: (p.grad.detach().clone() if p.grad is not None else None) for k, p in g.named_parameters()})
+    return out

@@ -1,0 +1,176 @@
+"""Kernel-level parity (GPU) for the fp32 helper kernels: EqualizedLinear fwd/bwd (gan.py:16-17), learned
+constant (gan.py:92), image-plane fade ops (gan.py:213-220, 345), MiniBatchStdDev forward / tangent / backward /
+second-order (gan.py:273-298) against autograd over the oracle restatement, and the loss terms (gan.py:228,396-406)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+import bg_native as bgn  # noqa: E402
+from oracle import gan_oracle as O  # noqa: E402
+
+DEV = "cuda"
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / (b.double().norm() + 1e-30)).item()
+
+
+@pytest.mark.parametrize("m,n,k", [(16, 512, 512), (5, 1024, 512), (32, 512, 8192), (7, 1, 512), (9, 512, 1), (33, 32, 512)])
+def test_linear_fwd_and_bwd(m, n, k):
+    torch.manual_seed(0)
+    x = torch.randn(m, k, device=DEV)
+    w = torch.randn(n, k, device=DEV)
+    b = torch.randn(n, device=DEV)
+    coef = math.sqrt(2 / k)
+    y = torch.empty(m, n, device=DEV)
+    bgn.call("bg_linear_fwd", x, w, b, y, m, n, k, coef, 1, 0.2)
+    ref = F.leaky_relu(F.linear(x, w * coef, b), 0.2)
+    assert rel(y, ref) < 1e-5
+    gy = torch.randn(m, n, device=DEV)
+    wt = torch.empty(k, n, device=DEV)
+    bgn.call("bg_transpose_f32", w, wt, n, k)
+    assert torch.equal(wt, w.t().contiguous())
+    gx = torch.empty(m, k, device=DEV)
+    bgn.call("bg_linear_fwd", gy, wt, None, gx, m, k, n, coef, 0, 0.2)
+    assert rel(gx, gy @ (w * coef)) < 1e-5
+    if k % 4 == 0:
+        dw = torch.empty(n, k, device=DEV)
+        db = torch.empty(n, device=DEV)
+        bgn.call("bg_linear_bwd_weight", gy, x, dw, db, m, n, k, coef, 0)
+        assert rel(dw, coef * gy.t() @ x) < 1e-5 and rel(db, gy.sum(0)) < 1e-5
+        bgn.call("bg_linear_bwd_weight", gy, x, dw, db, m, n, k, coef, 1)
+        assert rel(dw, 2 * coef * gy.t() @ x) < 1e-5 and rel(db, 2 * gy.sum(0)) < 1e-5
+
+
+def test_const_noise_act_and_bwd():
+    torch.manual_seed(0)
+    n, c = 5, 512
+    cst = torch.randn(1, c, 4, 4, device=DEV)
+    noise = torch.randn(n, 1, 4, 4, device=DEV)
+    nw = torch.randn(c, device=DEV) * 0.1
+    a = torch.empty(n, 4, 4, c, dtype=torch.bfloat16, device=DEV)
+    bgn.call("bg_const_noise_act", cst, noise, nw, a, n, 16, c, 0.2)
+    ref = F.leaky_relu(cst.repeat(n, 1, 1, 1) + nw.view(1, c, 1, 1) * noise, 0.2)
+    assert rel(a.float().permute(0, 3, 1, 2), ref) < 4e-3
+    g = torch.randn(n, 4, 4, c, device=DEV).to(torch.bfloat16)
+    dc = torch.empty(1, c, 4, 4, device=DEV)
+    bgn.call("bg_const_bwd", g, dc, n, 16, c)
+    assert rel(dc, g.float().permute(0, 3, 1, 2).sum(0, keepdim=True)) < 1e-5
+
+
+@pytest.mark.parametrize("r", [2, 4, 16])
+def test_image_plane_fade_ops(r):
+    torch.manual_seed(0)
+    b, alpha = 3, 0.3
+    small = torch.randn(b, 3, r, r, device=DEV, requires_grad=True)
+    large = torch.randn(b, 3, 2 * r, 2 * r, device=DEV, requires_grad=True)
+    out = torch.empty(b, 3, 2 * r, 2 * r, device=DEV)
+    bgn.call("bg_img_up2_lerp", small.detach(), large.detach(), out, b * 3, r, r, alpha)
+    ref = torch.lerp(F.interpolate(small, scale_factor=2, mode="bilinear"), large, alpha)
+    assert rel(out, ref) < 1e-6
+    g = torch.randn_like(ref)
+    ref.backward(g)
+    gs = torch.empty(b, 3, r, r, device=DEV)
+    bgn.call("bg_img_up2_bwd", g, gs, b * 3, r, r, 1 - alpha)
+    assert rel(gs, small.grad) < 1e-5
+    img = torch.randn(b, 3, 2 * r, 2 * r, device=DEV, requires_grad=True)
+    p = torch.empty(b, 3, r, r, device=DEV)
+    bgn.call("bg_img_avgpool2", img.detach(), p, b * 3, r, r)
+    refp = F.avg_pool2d(img, 2)
+    assert rel(p, refp) < 1e-6
+    gp = torch.randn_like(refp)
+    refp.backward(gp)
+    gi = torch.ones(b, 3, 2 * r, 2 * r, device=DEV)
+    bgn.call("bg_img_avgpool2_bwd", gp, gi, b * 3, r, r, 1.0, 1)
+    assert rel(gi - 1, img.grad) < 1e-5
+    sums = torch.empty(3, device=DEV)
+    bgn.call("bg_plane_sums", g, sums, b, 4 * r * r)
+    assert rel(sums, g.sum((0, 2, 3))) < 1e-5
+
+
+@pytest.mark.parametrize("b,gsz", [(4, 4), (8, 4), (16, 4), (32, 4), (6, 6)])
+def test_minibatch_stddev_all_orders(b, gsz):
+    """forward value, tangent (JVP), VJP and the second-order term  d/dx [ ghat_s . J(x) v ]  vs autograd."""
+    torch.manual_seed(b)
+    C, HW, CP = 512, 16, 576
+    xb = (torch.randn(b, HW, C, device=DEV) * 1.5).to(torch.bfloat16)
+    vb = torch.randn(b, HW, C, device=DEV).to(torch.bfloat16)
+    M = b // gsz
+
+    def s_of(x_nhwc):                       # oracle on NCHW fp64
+        x = x_nhwc.permute(0, 2, 1).reshape(b, C, 4, 4)
+        y, _ = O.minibatch_stddev(x, gsz)
+        return y[:M, C, 0, 0]
+
+    x64 = xb.double().requires_grad_()
+    s_ref = s_of(x64)
+    plane = torch.empty(M, device=DEV)
+    xpad = torch.empty(b, HW, CP, dtype=torch.bfloat16, device=DEV)
+    bgn.call("bg_mbstd_fwd", xb, None, plane, xpad, b, gsz, HW, C, CP, 1e-8)
+    assert rel(plane, s_ref) < 1e-5
+    assert torch.equal(xpad[..., :C], xb) and xpad[..., C + 1:].abs().sum() == 0
+    assert rel(xpad[:, 0, C].float(), s_ref.repeat(gsz).float()) < 4e-3
+    # tangent
+    v64 = vb.double()
+    (sdot_ref,) = torch.autograd.functional.jvp(s_of, (xb.double(),), (v64,))[1:]
+    sdot = torch.empty(M, device=DEV)
+    vpad = torch.empty(b, HW, CP, dtype=torch.bfloat16, device=DEV)
+    bgn.call("bg_mbstd_fwd", xb, vb, sdot, vpad, b, gsz, HW, C, CP, 1e-8)
+    assert rel(sdot, sdot_ref) < 1e-4
+    assert torch.equal(vpad[..., :C], vb)
+    # VJP:  gpad carries the pass-through gradient (channels < C) and the plane gradient (channel C)
+    gpad = torch.randn(b, HW, CP, device=DEV).to(torch.bfloat16)
+    gs = gpad[..., C].double().sum(1).reshape(gsz, M).sum(0)              # per-slot plane gradient
+    (vjp_ref,) = torch.autograd.grad(s_ref, x64, gs, create_graph=False, retain_graph=True)
+    ws = torch.empty(2 * M, device=DEV)
+    gx = torch.empty(b, HW, C, dtype=torch.bfloat16, device=DEV)
+    bgn.call("bg_mbstd_bwd", xb, None, gpad, None, ws, gx, b, gsz, HW, C, CP, 1e-8)
+    ref_total = gpad[..., :C].double() + vjp_ref
+    assert rel(gx.double(), ref_total) < 5e-3
+    zero_pad = torch.zeros_like(gpad)                                     # isolate the (small) stddev term
+    zero_pad[..., C] = gpad[..., C]
+    bgn.call("bg_mbstd_bwd", xb, None, zero_pad, None, ws, gx, b, gsz, HW, C, CP, 1e-8)
+    assert rel(gx.double(), vjp_ref) < 5e-3
+    # second order: q = d/dx [ sum_m gs2[m] * sdot_m(x; v) ]
+    gpad2 = torch.randn(b, HW, CP, device=DEV).to(torch.bfloat16)
+    gs2 = gpad2[..., C].double().sum(1).reshape(gsz, M).sum(0)
+    x2 = xb.double().requires_grad_()
+    sd = torch.autograd.functional.jvp(s_of, (x2,), (v64,), create_graph=True)[1]
+    (q_ref,) = torch.autograd.grad((sd * gs2).sum(), x2)
+    bgn.call("bg_mbstd_bwd", xb, vb, zero_pad, gpad2, ws, gx, b, gsz, HW, C, CP, 1e-8)
+    assert rel(gx.double(), vjp_ref + q_ref) < 2e-2
+
+
+def test_loss_terms():
+    torch.manual_seed(0)
+    p = torch.randn(37, 1, device=DEV) * 3
+    p[0] = 25.0
+    loss = torch.empty(1, device=DEV)
+    seed = torch.empty(37, 1, device=DEV)
+    for sign in (1.0, -1.0):
+        pr = p.clone().requires_grad_()
+        ref = F.softplus(sign * pr).mean()
+        ref.backward()
+        bgn.call("bg_logistic_loss", p, 37, sign, loss, seed, 1.0)
+        assert abs(loss.item() - ref.item()) < 1e-6 * abs(ref.item()) + 1e-7
+        assert rel(seed, pr.grad) < 1e-5
+    x = torch.randn(100003, device=DEV)
+    out = torch.empty(1, device=DEV)
+    bgn.call("bg_sumsq", x, x.numel(), 0.5, out)
+    assert abs(out.item() - 0.5 * (x.double() ** 2).sum().item()) < 1e-3 * out.item()
+
+
+def test_flatten_boundary_roundtrip():
+    torch.manual_seed(0)
+    n = 6
+    x = torch.randn(n, 4, 4, 512, device=DEV).to(torch.bfloat16)
+    f = torch.empty(n, 8192, device=DEV)
+    bgn.call("bg_nhwc_to_nchw_f32", x, f, n, 16, 512)
+    assert torch.equal(f, x.float().permute(0, 3, 1, 2).reshape(n, -1))
+    back = torch.empty_like(x)
+    bgn.call("bg_nchw_f32_to_nhwc", f, x, back, n, 16, 512, 0.2)
+    assert torch.equal(back, (x.float() * torch.where(x.float() > 0, 1.0, 0.2)).to(torch.bfloat16))

@@ -115,7 +115,7 @@ def test_conv3x3_wgrad(shape):
     x = nhwc(torch.randn(n, ci, h, w_, device=DEV))
     g = nhwc(torch.randn(n, co, h, w_, device=DEV))
     dwp = torch.empty(9, co, ci, dtype=torch.float32, device=DEV)
-    bgn.call("bg_conv_wgrad", x, g, dwp, n, h, w_, ci, co)
+    bgn.call("bg_conv_wgrad", x, g, dwp, n, h, w_, ci, co, 0)
     torch.cuda.synchronize()
     ref = torch.nn.grad.conv2d_weight(nchw(x), (co, ci, 3, 3), nchw(g), padding=1)
     got = dwp.reshape(3, 3, co, ci).permute(2, 3, 0, 1)

@@ -1,0 +1,92 @@
+"""Model-level parity on the GPU: byo-gan_b200/gan.py (CUDA kernels through the C ABI) against
+ (a) the oracle restatement evaluated in fp32 on the same device with TF32 off, on the same seeded inputs, and
+ (b) the golden fingerprints recorded from the unmodified reference (tests/golden/*.json).
+Tolerances are the stated bf16-vs-fp32 ones in tests/parity_util.py."""
+import json
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import gan_oracle as O  # noqa: E402
+import parity_util as U  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def gold(name):
+    with open(os.path.join(GOLD, name)) as f:
+        return json.load(f)
+
+
+def fp_close(t, fp, tol, what):
+    got = O.fingerprint(t)
+    assert got["shape"] == fp["shape"], what
+    a, b = torch.tensor(got["samples"], dtype=torch.float64), torch.tensor(fp["samples"], dtype=torch.float64)
+    err = ((a - b).norm() / (b.norm() + 1e-30)).item()
+    assert err < tol, f"{what}: sampled rel-L2 {err:.3e} vs reference fingerprint"
+    assert abs(got["norm"] - fp["norm"]) < tol * fp["norm"] + 1e-6, f"{what}: norm {got['norm']} vs {fp['norm']}"
+
+
+@pytest.mark.parametrize("case", gold("forward.json"), ids=lambda c: f"s{c['steps']}-b{c['batch']}-a{c['alpha']}")
+def test_forward_vs_reference_golden_and_oracle(case):
+    U.no_tf32()
+    steps, batch, alpha = case["steps"], case["batch"], case["alpha"]
+    g, c = U.build_models(1)
+    z = O.make_latents(batch, steps).cuda()
+    noise = [n.cuda() for n in O.make_noise(batch, steps, steps)]
+    real = O.make_images(batch, steps, steps).cuda()
+    with torch.no_grad():
+        fake = g(z, noise=noise, steps=steps, alpha=alpha)
+        pr = c(real, steps, alpha)
+        Gs = {k: v.cuda() for k, v in O.make_state("gen", 1).items()}
+        Ds = {k: v.cuda() for k, v in O.make_state("critic", 1).items()}
+        fake_o = O.generator_forward(Gs, z, noise, steps, alpha)
+        pr_o = O.critic_forward(Ds, real, steps, alpha)
+        pf = c(fake_o, steps, alpha)
+        pf_o = O.critic_forward(Ds, fake_o, steps, alpha)
+    assert fake.shape == fake_o.shape and fake.dtype == torch.float32
+    assert U.rel(fake, fake_o) < U.TOL_IMG, f"image rel-L2 {U.rel(fake, fake_o):.3e}"
+    fp_close(fake, case["fake"], U.TOL_IMG, "image vs golden")
+    for got, ref, name in ((pr, pr_o, "D(real)"), (pf, pf_o, "D(fake)")):
+        scale = ref.pow(2).mean().sqrt().item() + 1.0
+        assert (got - ref).abs().max().item() < U.TOL_PRED * scale, f"{name}: {got.flatten()} vs {ref.flatten()}"
+    ref_pr = torch.tensor(case["pred_real"]["samples"])[: pr.numel()]
+    assert (pr.flatten().cpu()[: ref_pr.numel()] - ref_pr).abs().max() < U.TOL_PRED * (ref_pr.pow(2).mean().sqrt() + 1)
+
+
+@pytest.mark.parametrize("case", gold("train_iteration.json")[:6],
+                         ids=lambda c: f"s{c['steps']}-b{c['batch']}-a{c['alpha']}")
+def test_train_iteration_vs_reference(case):
+    """One G+D iteration (train.py:135-217): losses, every parameter gradient, which gradients are None."""
+    U.no_tf32()
+    steps, batch, alpha, lam = case["steps"], case["batch"], case["alpha"], case["lambda"]
+    g, c = U.build_models(2)
+    args = (O.make_latents(batch, 10 + steps), O.make_latents(batch, 20 + steps), O.make_images(batch, steps, 30 + steps),
+            O.make_noise(batch, steps, 10 + steps), O.make_noise(batch, steps, 20 + steps))
+    r = U.cuda_iteration(g, c, *args, steps, alpha, lam)
+    o = O.train_iteration(O.make_state("gen", 2), O.make_state("critic", 2), *args, steps, alpha, lam, device="cuda")
+    # losses vs the reference's recorded values and vs the oracle
+    assert abs(r["c_loss"].item() - case["c_loss"]) < U.TOL_LOSS * abs(case["c_loss"]), (r["c_loss"].item(), case["c_loss"])
+    assert abs(r["g_loss"].item() - case["g_loss"]) < U.TOL_LOSS * abs(case["g_loss"]), (r["g_loss"].item(), case["g_loss"])
+    assert abs(r["c_loss"].item() - o["c_loss"].item()) < U.TOL_LOSS * abs(o["c_loss"].item())
+    assert U.rel(r["fake_d"], o["fake_d"]) < U.TOL_IMG
+    bad = []
+    for kind in ("d_grads", "g_grads"):
+        for k, ref in o[kind].items():
+            got = r[kind][k]
+            assert (got is None) == (ref is None), f"{kind}[{k}]: None-ness differs from the reference"
+            assert (case[kind][k] is None) == (ref is None)
+            if ref is None:
+                continue
+            assert got.shape == ref.shape
+            if ref.norm().item() == 0.0:
+                assert got.abs().max().item() < 1e-6, k
+                continue
+            e, cs = U.rel(got, ref), U.cos(got, ref)
+            if e > U.TOL_GRAD_REL or cs < U.TOL_GRAD_COS:
+                bad.append((kind, k, round(e, 4), round(cs, 5)))
+    assert not bad, f"gradient parity failures (kind, key, rel-L2, cosine): {bad}"
+    assert U.cos(r["z_grad"], o["z_grad"]) > 0.98

@@ -1,0 +1,101 @@
+"""CPU checks of the drop-in boundary: attribute tree / state_dict layout of byo-gan_b200/gan.py against the
+reference's (tests/golden/state_layout.json), checkpoint round trips, C-ABI symbol export, error behaviour."""
+import ctypes
+import json
+import os
+import re
+
+import pytest
+import torch
+
+import gan  # byo-gan_b200/gan.py (conftest puts it first on sys.path)
+from oracle import gan_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def test_state_dict_layout_equals_reference():
+    layout = json.load(open(os.path.join(GOLD, "state_layout.json")))
+    g, c = gan.Generator(), gan.Critic()
+    assert {k: list(v.shape) for k, v in g.state_dict().items()} == layout["gen"]
+    assert {k: list(v.shape) for k, v in c.state_dict().items()} == layout["critic"]
+    assert list(g.state_dict().keys()) == list(layout["gen"].keys())          # same ORDER as the reference
+    assert list(c.state_dict().keys()) == list(layout["critic"].keys())
+    assert all(v.dtype == torch.float32 for v in g.state_dict().values())
+
+
+def test_reference_checkpoint_layout_loads_strict_with_dataparallel_prefix(tmp_path):
+    """train.py:250-251 saves DataParallel state_dicts (keys prefixed 'module.'); generate_samples.py:48-52
+    loads them back into a DataParallel-wrapped Generator."""
+    g = torch.nn.DataParallel(gan.Generator())
+    c = torch.nn.DataParallel(gan.Critic())
+    save = {"gen": {"module." + k: v for k, v in O.make_state("gen", 3).items()},
+            "critic": {"module." + k: v for k, v in O.make_state("critic", 3).items()},
+            "iter": 7, "im_count": 70, "step": 3, "epoch": 1, "alpha": 0.25}
+    path = tmp_path / "chk-7.pth"
+    torch.save(save, path)
+    back = torch.load(path)
+    g.load_state_dict(back["gen"])
+    c.load_state_dict(back["critic"])
+    for k, v in g.state_dict().items():
+        assert torch.equal(v, save["gen"][k])
+    assert hasattr(g.module, "get_r1_loss") and hasattr(c.module, "get_r1_loss") and hasattr(c.module, "get_wgan_loss")
+
+
+def test_optimizer_groups_and_requires_grad_toggle():
+    """train.py:59-70 builds three Adam groups from these attributes; helper.py:48-50 toggles requires_grad."""
+    g = gan.Generator()
+    n = sum(p.numel() for grp in (g.to_w_noise, g.gen_blocks, g.to_rgbs) for p in grp.parameters())
+    assert n == sum(p.numel() for p in g.parameters())
+    assert len(list(g.parameters())) == 111 and len(list(gan.Critic().parameters())) == 52
+    for p in g.parameters():
+        p.requires_grad = False
+    assert not any(p.requires_grad for p in g.parameters())
+
+
+def test_initialisation_follows_reference_rules():
+    torch.manual_seed(0)
+    g, c = gan.Generator(), gan.Critic()
+    sd = g.state_dict()
+    assert sd["gen_blocks.3.conv_1.inject_noise.weights"].abs().sum() == 0                 # gan.py:44
+    assert sd["gen_blocks.3.conv_1.conv.bias"].abs().sum() == 0                            # gan.py:24
+    b = sd["gen_blocks.3.conv_1.adain.style.bias"]
+    assert torch.equal(b[:256], torch.ones(256)) and torch.equal(b[256:], torch.zeros(256))  # gan.py:62-63
+    w = sd["gen_blocks.3.conv_1.conv.weight"]
+    assert abs(w.std().item() - 1.0) < 0.01 and abs(w.mean().item()) < 0.01                  # gan.py:23
+    assert c.conv_blocks[7].conv_1[0].group_size == 4                                        # gan.py:269
+    assert g.gen_blocks[3].conv_1.conv.equalized_coefficient == pytest.approx((2 / (512 * 9)) ** 0.5)
+
+
+def test_no_cpu_fallback_and_reference_error_behaviour():
+    g, c = gan.Generator(), gan.Critic()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        g(torch.zeros(2, 512))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        c(torch.zeros(2, 3, 4, 4))
+    with pytest.raises(AttributeError):                                # gan.py:367-368 raises AttributeError too
+        c.get_wgan_loss(None, None, None, 1, None)
+    with pytest.raises(ValueError):                                    # gan.py:105-106
+        gan.StyleGanBlock(4, 4, is_initial=True, does_upsample=True)
+    with pytest.raises(RuntimeError, match="forward"):
+        c.get_r1_loss(torch.zeros(2, 1), torch.zeros(2, 1), None, None, 1, None)
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    """include/bg_b200.h <-> libbg_b200.so <-> bg_native.SIGNATURES agree (no compute calls: no GPU here)."""
+    import bg_native
+
+    header = open(os.path.join(ROOT, "include", "bg_b200.h")).read()
+    declared = set(re.findall(r"\b(bg_[a-z0-9_]+)\s*\(", header))
+    lib = ctypes.CDLL(os.path.join(ROOT, "byo-gan_b200", "libbg_b200.so"))
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in bg_b200.h but not exported"
+    assert declared - {"bg_last_error", "bg_abi_version"} == set(bg_native.SIGNATURES)
+    lib.bg_abi_version.restype = ctypes.c_int
+    assert lib.bg_abi_version() >= 1
+    # argument counts in the binding match the header declarations
+    for name, args in bg_native.SIGNATURES.items():
+        m = re.search(r"int\s+" + name + r"\s*\(([^;]*?)\)\s*;", header, re.S)
+        assert m, name
+        assert len([a for a in m.group(1).split(",") if a.strip()]) == len(args), name
