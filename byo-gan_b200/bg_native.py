@@ -23,6 +23,8 @@ SIGNATURES = {
     "bg_pack_weight": [_P, _P, _P, _I, _I, _I, _I, _F, _P],
     "bg_unpack_wgrad": [_P, _P, _I, _I, _I, _I, _F, _I, _P],
     "bg_conv_fprop": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _F, _P],
+    "bg_conv_pool_fprop": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _F, _P],
+    "bg_conv_fprop_tapwise": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _F, _P],
     "bg_conv_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "bg_act_gate": [_P, _P, _P, _Z, _F, _P],
     "bg_axpby": [_P, _P, _P, _Z, _F, _F, _P],

@@ -5,6 +5,9 @@
 namespace bg {
 int launch_conv_fprop(const void*, const void*, void*, int, int, int, int, int, int, const float*, const float*,
                       const float*, const void*, int, float, cudaStream_t);
+int launch_conv_halo(const void*, const void*, void*, int, int, int, int, int, const float*, const float*, const float*,
+                     const void*, int, int, float, cudaStream_t);
+bool conv_halo_supported(int, int, int, int, int, int);
 int launch_conv_wgrad(const void*, const void*, float*, int, int, int, int, int, int, cudaStream_t);
 int launch_pack_weight(const float*, void*, void*, int, int, int, int, float, cudaStream_t);
 int launch_unpack_wgrad(const float*, float*, int, int, int, int, float, int, cudaStream_t);
@@ -60,6 +63,24 @@ int bg_unpack_wgrad(const float* dwp, float* dw, int Cout, int Cin, int Cin_pad,
 int bg_conv_fprop(const void* x, const void* wpack, void* out, int N, int H, int W, int Cin, int Cout, int ksize,
                   const float* bias, const float* noise, const float* noise_w, const void* gate_src, int act,
                   float slope, void* stream) {
+  if (bg::conv_halo_supported(N, H, W, Cin, Cout, ksize))
+    return bg::launch_conv_halo(x, wpack, out, N, H, W, Cin, Cout, bias, noise, noise_w, gate_src, act, 0, slope,
+                                S(stream));
+  return bg::launch_conv_fprop(x, wpack, out, N, H, W, Cin, Cout, ksize, bias, noise, noise_w, gate_src, act, slope,
+                               S(stream));
+}
+int bg_conv_pool_fprop(const void* x, const void* wpack, void* out, int N, int H, int W, int Cin, int Cout,
+                       const float* bias, const void* gate_src, int act, float slope, void* stream) {
+  if (!bg::conv_halo_supported(N, H, W, Cin, Cout, 3)) {
+    bg::set_error("conv_pool_fprop: needs a 3x3 layer at H,W >= 16 (got H %d W %d Cin %d Cout %d)", H, W, Cin, Cout);
+    return 2;
+  }
+  return bg::launch_conv_halo(x, wpack, out, N, H, W, Cin, Cout, bias, nullptr, nullptr, gate_src, act, 1, slope,
+                              S(stream));
+}
+int bg_conv_fprop_tapwise(const void* x, const void* wpack, void* out, int N, int H, int W, int Cin, int Cout, int ksize,
+                          const float* bias, const float* noise, const float* noise_w, const void* gate_src, int act,
+                          float slope, void* stream) {
   return bg::launch_conv_fprop(x, wpack, out, N, H, W, Cin, Cout, ksize, bias, noise, noise_w, gate_src, act, slope,
                                S(stream));
 }

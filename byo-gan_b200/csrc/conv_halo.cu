@@ -1,0 +1,522 @@
+// 3x3 pad-1 implicit-GEMM convolution with a HALO-RESIDENT input tile (resolutions >= 16x16).
+//
+// Same contract as conv_fprop.cu (EqualizedConv2d.forward, gan.py:29-38; its input-gradient on the flipped
+// pack; the R1 tangent pass) but a different operand feed.  The tap-wise TMA kernel re-reads every input
+// pixel 9 times from L2 and is bound by the per-SM L2->SMEM fill rate (~42 B/clk, see
+// profiles/r1_ncu_full_conv_fprop_256x256.csv).  Here a CTA owns a 16x16 output tile (two M=128 MMA halves)
+// and loads the 18x18 input halo of a channel chunk ONCE; the nine taps are nine shifted VIEWS of it:
+//
+//   smem A stage = kc/8 planes, plane c8 = [18*18 halo pixels][8 channels = 16 B]   (UMMA K-major, no swizzle:
+//   a core matrix is 8 consecutive pixels x 16 B, SBO = one halo row = 288 B, LBO = plane pitch), so the view
+//   of tap (ky,kx) for MMA half h is just  start address += ((ky*18 + kx + 8h) * 16 B)  — 16-byte granular,
+//   no swizzle phase to keep consistent.
+//
+// The halo is written by 4 producer warps with 16-byte cp.async (zero-fill for the padding), which is also the
+// hook where prologue transforms (AdaIN apply, bilinear upsample) fuse in later.  Weights stream by TMA
+// (128/64/32-byte swizzle) per (chunk, tap), or stay RESIDENT in shared memory for the whole kernel when the
+// layer's pack fits (all the high-resolution layers).  Accumulators: TMEM, 2 stages x 2 halves x 128 columns.
+//
+// Warp roles: 0 = weight TMA producer, 1 = MMA issuer + TMEM allocator, 2..9 = epilogue (one 32-row TMEM
+// quarter of one MMA half each), 10..13 = halo producers.
+#include "common.cuh"
+
+#include <stdlib.h>
+
+namespace bg {
+
+namespace {
+
+constexpr int kEpiWarps = 8;                     // warps 2..5 drain MMA half 0, warps 6..9 half 1
+constexpr int kProdWarps = 4;
+constexpr int kProdThreads = 32 * kProdWarps;
+constexpr int kThreads = 32 * (2 + kEpiWarps + kProdWarps);
+constexpr int kTile = 16;                       // output tile edge
+constexpr int kHalo = kTile + 2;                // 18
+constexpr int kHaloPix = kHalo * kHalo;         // 324
+constexpr uint32_t kPlaneBytes = 325 * 16;      // 324 pixels * 16 B, padded so the 8 planes hit distinct banks
+constexpr uint32_t kRowBytes = kHalo * 16;      // 288: SBO between 8-pixel groups (one image row down)
+constexpr int kMaxBStages = 8;
+constexpr int kAStages = 3;
+constexpr int kMaxN = 128;
+constexpr uint32_t kTmemCols = 512;
+
+struct HaloParams {
+  int N, H, W, Cin, Cout;
+  int tiles_w, tiles_h;
+  int block_n, n_blocks;
+  int kc, k_chunks, cpp_shift;
+  int b_stages, b_resident;
+  uint32_t a_stage_bytes, b_tile_bytes, b_tx_bytes;
+  uint32_t b_layout, b_sbo;
+  int num_tiles;
+  const __nv_bfloat16* x;
+  const float* bias;
+  const float* noise;
+  const float* noise_w;
+  const __nv_bfloat16* gate_src;
+  __nv_bfloat16* out;
+  int act;
+  int debug;      // bisecting aid (BG_HALO_DEBUG): 1 no global stores, 2 no MMAs, 4 no halo copies, 8 no epilogue math
+  int pool;       // 1: 2x2 average pool before the activation; out / gate_src are (N, H/2, W/2, Cout)
+  float slope;
+};
+
+struct TileCoord {
+  int w0, h0, n, co0;
+};
+
+__device__ __forceinline__ float4 lds128(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
+
+__device__ __forceinline__ TileCoord decode_tile(const HaloParams& p, int tile) {
+  TileCoord t;
+  const int nb = tile % p.n_blocks;
+  int pt = tile / p.n_blocks;
+  t.w0 = (pt % p.tiles_w) * kTile;
+  pt /= p.tiles_w;
+  t.h0 = (pt % p.tiles_h) * kTile;
+  t.n = pt / p.tiles_h;
+  t.co0 = nb * p.block_n;
+  return t;
+}
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Warp 1 issues every tcgen05.mma of the CTA.  For the narrow layers an M=128 x N<=64 MMA retires in 16-48 clk,
+// so the issue loop itself is the critical path: the whole warp runs it converged (all values warp-uniform, so
+// ptxas keeps descriptors in uniform registers instead of R2UR-ing them per instruction), one elected lane
+// executes the tcgen05 instructions, descriptors are 64-bit values advanced by compile-time constants, and the
+// k-steps / taps are unrolled.
+template <int KSTEPS>
+__device__ __forceinline__ void mma_issue_loop(const HaloParams& p, uint8_t* a_base, uint8_t* b_base, uint64_t* b_full,
+                                               uint64_t* b_empty, uint64_t* a_full, uint64_t* a_empty,
+                                               uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base) {
+  const uint32_t idesc = umma_idesc_bf16(128, p.block_n, 0, 0);
+  const uint64_t a_desc0 = umma_desc(smem_u32(a_base), kPlaneBytes, kRowBytes, 0u);
+  const uint64_t b_desc0 = umma_desc(smem_u32(b_base), 16u, p.b_sbo, p.b_layout);
+  const uint32_t a_stage_step = p.a_stage_bytes >> 4;
+  const uint32_t b_tile_step = p.b_tile_bytes >> 4;
+  const bool leader = elect_one();
+  int bstage = 0;
+  uint32_t bphase = 0;
+  int astage = 0;
+  uint32_t aphase = 0;
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  if (p.b_resident) {
+    mbar_wait(&b_full[0], 0);
+    tc_fence_after();
+  }
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+    tc_fence_after();
+    const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+    uint32_t accum = 0u;
+    for (int kcx = 0; kcx < p.k_chunks; ++kcx) {
+      mbar_wait(&a_full[astage], aphase);
+      tc_fence_after();
+      const uint64_t a_stage = a_desc0 + (uint64_t)((uint32_t)astage * a_stage_step);
+      if (p.b_resident) {
+        const uint64_t b_chunk = b_desc0 + (uint64_t)((uint32_t)(kcx * 9) * b_tile_step);
+        if (leader) {
+          if (!(p.debug & 2))
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint64_t a_tap = a_stage + (uint64_t)((tap / 3) * kHalo + (tap % 3));
+            const uint64_t b_tap = b_chunk + (uint64_t)((uint32_t)tap * b_tile_step);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k) {
+                tc_mma_bf16(d_tmem + (uint32_t)half * 128u,
+                            a_tap + (uint64_t)(half * 8 + k * (2 * (kPlaneBytes >> 4))), b_tap + (uint64_t)(k * 2),
+                            idesc, (k == 0 && tap == 0) ? accum : 1u);
+              }
+            }
+          }
+          tc_commit(&a_empty[astage]);
+        }
+        accum = 1u;
+      } else {
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&b_full[bstage], bphase);
+          tc_fence_after();
+          if (leader) {
+            const uint64_t a_tap = a_stage + (uint64_t)((tap / 3) * kHalo + (tap % 3));
+            const uint64_t b_tap = b_desc0 + (uint64_t)((uint32_t)bstage * b_tile_step);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k) {
+                tc_mma_bf16(d_tmem + (uint32_t)half * 128u,
+                            a_tap + (uint64_t)(half * 8 + k * (2 * (kPlaneBytes >> 4))), b_tap + (uint64_t)(k * 2),
+                            idesc, k == 0 ? accum : 1u);
+              }
+            }
+            tc_commit(&b_empty[bstage]);
+          }
+          accum = 1u;
+          if (++bstage == p.b_stages) {
+            bstage = 0;
+            bphase ^= 1u;
+          }
+        }
+        if (leader) tc_commit(&a_empty[astage]);
+      }
+      __syncwarp();
+      if (++astage == kAStages) {
+        astage = 0;
+        aphase ^= 1u;
+      }
+    }
+    if (leader) tc_commit(&tmem_full[acc]);
+    __syncwarp();
+    acc ^= 1;
+    if (acc == 0) acc_phase ^= 1u;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const HaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+
+  // carve: [B region (1024-aligned tiles)] [A stages] [aux]
+  const int b_tiles = p.b_resident ? p.k_chunks * 9 : p.b_stages;
+  uint8_t* b_base = smem;
+  uint8_t* a_base = b_base + (size_t)b_tiles * p.b_tile_bytes;
+  uint8_t* aux = a_base + (size_t)kAStages * p.a_stage_bytes;
+  aux = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(aux) + 15) & ~uintptr_t(15));
+  uint64_t* b_full = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* b_empty = b_full + kMaxBStages;
+  uint64_t* a_full = b_empty + kMaxBStages;
+  uint64_t* a_empty = a_full + kAStages;
+  uint64_t* tmem_full = a_empty + kAStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);
+  float* nw_s = bias_s + 512;
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform role index
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_w);
+    for (int s = 0; s < kMaxBStages; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int s = 0; s < kAStages; ++s) {
+      mbar_init(&a_full[s], kProdThreads);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  if (warp >= 2 && warp < 2 + kEpiWarps) {
+    for (int c = threadIdx.x - 64; c < p.Cout; c += 32 * kEpiWarps) {
+      bias_s[c] = p.bias ? p.bias[c] : 0.f;
+      nw_s[c] = p.noise_w ? p.noise_w[c] : 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ weight TMA producer ------------------------------
+    if (lane == 0) {
+      if (p.b_resident) {
+        // whole pack of this CTA's n-block range is loaded once per n-block change; with n_blocks == 1 (the
+        // only case the host selects residency for) that is once per kernel.
+        mbar_expect_tx(&b_full[0], (uint32_t)(p.k_chunks * 9) * p.b_tx_bytes);
+        for (int kcx = 0; kcx < p.k_chunks; ++kcx)
+          for (int tap = 0; tap < 9; ++tap)
+            tma_load_3d(&tmap_w, &b_full[0], b_base + (size_t)(kcx * 9 + tap) * p.b_tile_bytes, kcx * p.kc, 0, tap);
+      } else {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+          const TileCoord t = decode_tile(p, tile);
+          for (int kcx = 0; kcx < p.k_chunks; ++kcx) {
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&b_empty[stage], phase ^ 1u);
+              mbar_expect_tx(&b_full[stage], p.b_tx_bytes);
+              tma_load_3d(&tmap_w, &b_full[stage], b_base + (size_t)stage * p.b_tile_bytes, kcx * p.kc, t.co0, tap);
+              if (++stage == p.b_stages) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (p.kc == 64) mma_issue_loop<4>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+    else if (p.kc == 32) mma_issue_loop<2>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+    else mma_issue_loop<1>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+  } else if (warp < 2 + kEpiWarps) {
+    // ------------------------------ epilogue ------------------------------
+    // Warp e = warp - 2: TMEM lane quarter q = warp & 3 (hardware rule), MMA half = e / 4.  Lane i holds MMA row
+    // m = 32q + i = pixel (image row g = m / 8, column r = m % 8 of the half's 8-wide segment).
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int m = q * 32 + lane;
+    const int g = m >> 3, r = m & 7;
+    const bool pool_writer = ((lane & 1) == 0) && ((lane & 8) == 0);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const int h = t.h0 + g, w = t.w0 + half * 8 + r;
+      const size_t pix = ((size_t)t.n * p.H + h) * p.W + w;
+      const float nz = p.noise != nullptr ? p.noise[pix] : 0.f;
+      const size_t opix = p.pool ? ((size_t)t.n * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1) : pix;
+      __nv_bfloat16* orow = p.out + opix * p.Cout + t.co0;
+      const __nv_bfloat16* grow = p.gate_src ? p.gate_src + opix * p.Cout + t.co0 : nullptr;
+      const bool writer = p.pool ? pool_writer : true;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u + (uint32_t)half * 128u;
+      for (int c = 0; c < ((p.debug & 8) ? 0 : p.block_n); c += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(taddr + c, v);
+        float bn[16];
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 b4 = lds128(bias_s + t.co0 + c + 4 * j4);
+          bn[4 * j4 + 0] = b4.x; bn[4 * j4 + 1] = b4.y; bn[4 * j4 + 2] = b4.z; bn[4 * j4 + 3] = b4.w;
+        }
+        if (p.noise != nullptr) {
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 n4 = lds128(nw_s + t.co0 + c + 4 * j4);
+            bn[4 * j4 + 0] = fmaf(n4.x, nz, bn[4 * j4 + 0]);
+            bn[4 * j4 + 1] = fmaf(n4.y, nz, bn[4 * j4 + 1]);
+            bn[4 * j4 + 2] = fmaf(n4.z, nz, bn[4 * j4 + 2]);
+            bn[4 * j4 + 3] = fmaf(n4.w, nz, bn[4 * j4 + 3]);
+          }
+        }
+        uint4 ga = make_uint4(0, 0, 0, 0), gb = ga;
+        if (grow != nullptr && writer) {
+          const uint4* g4 = reinterpret_cast<const uint4*>(grow + c);
+          ga = g4[0];
+          gb = g4[1];
+        }
+        tmem_ld_wait();
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + bn[j];
+        if (p.pool) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float sum = f[j] + __shfl_xor_sync(0xffffffffu, f[j], 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+            f[j] = 0.25f * sum;
+          }
+        }
+        if (p.act) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], f[j] * p.slope);      // LeakyReLU, 0 < slope < 1
+        }
+        if (grow != nullptr) {
+          const uint32_t gw[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float2 gv = unpack_bf16x2(gw[j]);
+            f[2 * j] *= gv.x > 0.f ? 1.f : p.slope;
+            f[2 * j + 1] *= gv.y > 0.f ? 1.f : p.slope;
+          }
+        }
+        if (writer && !(p.debug & 1)) {
+          uint4 o0, o1;
+          o0.x = pack_bf16x2(f[0], f[1]);
+          o0.y = pack_bf16x2(f[2], f[3]);
+          o0.z = pack_bf16x2(f[4], f[5]);
+          o0.w = pack_bf16x2(f[6], f[7]);
+          o1.x = pack_bf16x2(f[8], f[9]);
+          o1.y = pack_bf16x2(f[10], f[11]);
+          o1.z = pack_bf16x2(f[12], f[13]);
+          o1.w = pack_bf16x2(f[14], f[15]);
+          uint4* o4 = reinterpret_cast<uint4*>(orow + c);
+          o4[0] = o0;
+          o4[1] = o1;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  } else {
+    // ------------------------------ halo producers (cp.async, zero-fill padding) ------------------------------
+    // Thread pt always copies the same 16-byte channel unit c8 of pixels px0, px0 + pstride, ... so the only
+    // per-copy work is an incremental (row, column) walk over the 18-wide halo, a bounds test and one address.
+    const int pt = threadIdx.x - 32 * (2 + kEpiWarps);       // 0..127
+    const int cpp_shift = p.cpp_shift;                        // log2(16-byte units per pixel in this chunk)
+    const int c8 = pt & ((1 << cpp_shift) - 1);
+    const int px0 = pt >> cpp_shift;
+    const int pstride = kProdThreads >> cpp_shift;            // pixels advanced per copy: 16 / 32 / 64
+    const int iters = (kHaloPix - px0 + pstride - 1) / pstride;
+    const int dq = pstride / kHalo, dr = pstride % kHalo;
+    const int hy0 = px0 / kHalo, hx0 = px0 % kHalo;
+    const uint32_t soff0 = (uint32_t)c8 * kPlaneBytes + (uint32_t)px0 * 16u;
+    const uint32_t sstep = (uint32_t)pstride * 16u;
+    int stage = 0;
+    uint32_t phase = 0;
+    int pending_stage = -1;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const __nv_bfloat16* xn = p.x + (size_t)t.n * p.H * p.W * p.Cin;
+      const int hb = t.h0 - 1, wb = t.w0 - 1;
+      for (int kcx = 0; kcx < p.k_chunks; ++kcx) {
+        mbar_wait(&a_empty[stage], phase ^ 1u);
+        uint32_t soff = smem_u32(a_base + (size_t)stage * p.a_stage_bytes) + soff0;
+        const __nv_bfloat16* cb = xn + kcx * p.kc + c8 * 8;
+        int hy = hy0, hx = hx0;
+#pragma unroll 4
+        for (int it = 0; it < iters; ++it) {
+          const int h = hb + hy, w = wb + hx;
+          const bool ok = ((unsigned)h < (unsigned)p.H) && ((unsigned)w < (unsigned)p.W);
+          const __nv_bfloat16* src = ok ? cb + ((int64_t)h * p.W + w) * p.Cin : p.x;
+          if (!(p.debug & 4)) cp_async_16(soff, src, ok ? 16u : 0u);
+          soff += sstep;
+          hx += dr;
+          hy += dq;
+          if (hx >= kHalo) {
+            hx -= kHalo;
+            ++hy;
+          }
+        }
+        cp_async_commit();
+        // publish the PREVIOUS stage: its copies have landed once at most one group (this one) is pending
+        if (pending_stage >= 0) {
+          cp_async_wait<1>();
+          fence_proxy_async();
+          mbar_arrive(&a_full[pending_stage]);
+        }
+        pending_stage = stage;
+        if (++stage == kAStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+    if (pending_stage >= 0) {
+      cp_async_wait<0>();
+      fence_proxy_async();
+      mbar_arrive(&a_full[pending_stage]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace
+
+bool conv_halo_supported(int N, int H, int W, int Cin, int Cout, int ksize) {
+  return ksize == 3 && H >= 16 && W >= 16 && H % 16 == 0 && W % 16 == 0 && Cin % 16 == 0 && Cout % 16 == 0 &&
+         Cout <= 512 && N > 0;
+}
+
+// Host launcher; same arguments as launch_conv_fprop (ksize must be 3).
+int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, int W, int Cin, int Cout,
+                     const float* bias, const float* noise, const float* noise_w, const void* gate_src, int act,
+                     int pool, float slope, cudaStream_t stream) {
+  BG_REQUIRE(conv_halo_supported(N, H, W, Cin, Cout, 3), "conv_halo: unsupported shape N %d H %d W %d Cin %d Cout %d", N,
+             H, W, Cin, Cout);
+  HaloParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  p.tiles_w = W / kTile;
+  p.tiles_h = H / kTile;
+  int bn_ch = 0;
+  for (int c = kMaxN; c >= 16; c -= 16) {
+    if (Cout % c == 0) { bn_ch = c; break; }
+  }
+  BG_REQUIRE(bn_ch > 0, "conv_halo: no valid N tile for Cout %d", Cout);
+  p.block_n = bn_ch;
+  p.n_blocks = Cout / bn_ch;
+  p.kc = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0 ? 32 : 16);
+  p.k_chunks = Cin / p.kc;
+  p.cpp_shift = p.kc == 64 ? 3 : (p.kc == 32 ? 2 : 1);
+  const uint32_t row_bytes = (uint32_t)p.kc * 2u;
+  p.b_layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+  p.b_sbo = 8u * row_bytes;
+  p.b_tx_bytes = (uint32_t)p.block_n * row_bytes;
+  p.b_tile_bytes = (p.b_tx_bytes + 1023u) & ~1023u;
+  p.a_stage_bytes = (uint32_t)(p.kc / 8) * kPlaneBytes;
+  const uint32_t aux_bytes = 8 * (2 * kMaxBStages + 2 * kAStages + 4) + 16 + 2 * 512 * 4 + 64;
+  const uint32_t budget = 227u * 1024u - 1024u - aux_bytes - kAStages * p.a_stage_bytes;
+  const uint32_t resident_bytes = (uint32_t)p.k_chunks * 9u * p.b_tile_bytes;
+  p.b_resident = (p.n_blocks == 1 && resident_bytes <= budget) ? 1 : 0;
+  if (p.b_resident) {
+    p.b_stages = 1;
+  } else {
+    int st = (int)(budget / p.b_tile_bytes);
+    if (st > kMaxBStages) st = kMaxBStages;
+    BG_REQUIRE(st >= 2, "conv_halo: weight tile does not fit shared memory");
+    p.b_stages = st;
+  }
+  p.num_tiles = p.tiles_w * p.tiles_h * N * p.n_blocks;
+  p.x = reinterpret_cast<const __nv_bfloat16*>(x);
+  p.bias = bias; p.noise = noise; p.noise_w = noise_w;
+  p.gate_src = reinterpret_cast<const __nv_bfloat16*>(gate_src);
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.act = act; p.pool = pool; p.slope = slope;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("BG_HALO_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.debug = dbg;
+  }
+
+  CUtensorMap tmw;
+  {
+    uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, 9ull};
+    uint64_t str[2] = {(uint64_t)Cin * 2, (uint64_t)Cout * Cin * 2};
+    uint32_t box[3] = {(uint32_t)p.kc, (uint32_t)p.block_n, 1u};
+    if (make_tmap_bf16(&tmw, wpack, 3, dims, str, box, (int)row_bytes) != 0) return 1;
+  }
+  const size_t b_tiles = p.b_resident ? (size_t)p.k_chunks * 9 : (size_t)p.b_stages;
+  const size_t smem_bytes = b_tiles * p.b_tile_bytes + (size_t)kAStages * p.a_stage_bytes + aux_bytes + 1024;
+  BG_REQUIRE(smem_bytes <= 227 * 1024, "conv_halo: shared memory budget exceeded (%zu)", smem_bytes);
+  static bool attr_set = false;
+  if (!attr_set) {
+    BG_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  conv_halo_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmw, p);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace bg

@@ -116,24 +116,28 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
     } else if (warp == 1) {
       if (lane == 0) {
         const uint32_t idesc = umma_idesc_bf16(128, p.ci_slab, 1, 1);
+        const uint32_t a_hi = umma_desc_hi(8u * p.a_row_bytes, p.a_layout);
+        const uint32_t b_hi = umma_desc_hi(8u * p.b_row_bytes, p.b_layout);
+        const uint32_t a_kstep = (16u * p.a_row_bytes) >> 4;   // 16 pixels per UMMA K step, in 16-byte units
+        const uint32_t b_kstep = (16u * p.b_row_bytes) >> 4;
         int stage = 0;
         uint32_t phase = 0;
+        uint32_t accum = 0u;
         for (int i = 0; i < my_kblocks; ++i) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * kStageBytes);
-          const uint32_t sb = sa + kARegion;
-#pragma unroll 1
-          for (int ks = 0; ks < 8; ++ks) {  // 16 pixels per UMMA K step
-            const uint64_t adesc =
-                umma_desc(sa + ks * 16 * p.a_row_bytes, p.a_slab_bytes, 8u * p.a_row_bytes, p.a_layout);
+          const uint32_t a_lo = umma_desc_lo(sa, p.a_slab_bytes);
+          const uint32_t b_lo = umma_desc_lo(sa + kARegion, kBSlab);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
-              const uint64_t bdesc = umma_desc(sb + kx * kBSlab + ks * 16 * p.b_row_bytes, kBSlab,
-                                               8u * p.b_row_bytes, p.b_layout);
-              tc_mma_bf16(tmem_base + kx * kTapStride, adesc, bdesc, idesc, (i > 0 || ks > 0) ? 1u : 0u);
+              tc_mma_bf16_lohi(tmem_base + kx * kTapStride, a_lo + ks * a_kstep, a_hi,
+                               b_lo + kx * (kBSlab >> 4) + ks * b_kstep, b_hi, idesc, ks == 0 ? accum : 1u);
             }
           }
+          accum = 1u;
           tc_commit(&empty_bar[stage]);
           if (i == my_kblocks - 1) tc_commit(done_bar);
           if (++stage == kStages) {

@@ -45,6 +45,16 @@ int bg_unpack_wgrad(const float* dw_packed, float* dw, int Cout, int Cin, int Ci
 int bg_conv_fprop(const void* x, const void* wpack, void* out, int N, int H, int W, int Cin, int Cout, int ksize,
                   const float* bias, const float* noise, const float* noise_w, const void* gate_src, int act,
                   float slope, void* stream);
+/* conv3x3 -> AvgPool2d(2) -> [LeakyReLU | gate] fused in the epilogue (CriticBlock.conv_2, gan.py:258-262; with
+ * act=0 and gate_src (pooled resolution) it is the R1 tangent pass through the same layers).  out: (N,H/2,W/2,Cout).
+ * Needs H,W >= 16. */
+int bg_conv_pool_fprop(const void* x, const void* wpack, void* out, int N, int H, int W, int Cin, int Cout,
+                       const float* bias, const void* gate_src, int act, float slope, void* stream);
+/* bg_conv_fprop picks the halo-resident kernel (conv_halo.cu) for 3x3 at H,W >= 16 and the tap-wise TMA kernel
+ * (conv_fprop.cu) otherwise; this entry forces the tap-wise kernel (A/B tests, small maps, 1x1). */
+int bg_conv_fprop_tapwise(const void* x, const void* wpack, void* out, int N, int H, int W, int Cin, int Cout,
+                          int ksize, const float* bias, const float* noise, const float* noise_w, const void* gate_src,
+                          int act, float slope, void* stream);
 
 /* ---- weight gradient of the 3x3 conv (autograd convolution_backward / _convolution_double_backward) ---
  * dw_packed: fp32 [9][Cout][Cin] (overwritten, or += when accumulate) = sum_pixels g[p,co] * x[p+tap,ci].

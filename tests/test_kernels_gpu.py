@@ -50,6 +50,10 @@ CONV_SHAPES = [
     (1, 128, 128, 16, 16),
     (2, 16, 16, 512, 256),
     (1, 32, 32, 64, 48),
+    (3, 16, 16, 128, 128),
+    (1, 32, 32, 128, 64),
+    (1, 64, 64, 64, 32),
+    (2, 32, 32, 16, 16),
 ]
 
 
@@ -67,7 +71,8 @@ def test_pack_weight(shape):
 
 @pytest.mark.parametrize("shape", CONV_SHAPES)
 @pytest.mark.parametrize("fused", [False, True])
-def test_conv3x3_fprop(shape, fused):
+@pytest.mark.parametrize("entry", ["bg_conv_fprop", "bg_conv_fprop_tapwise"])
+def test_conv3x3_fprop(shape, fused, entry):
     """EqualizedConv2d.forward (gan.py:29-38) [+ InjectSecondaryNoise gan.py:52 + LeakyReLU gan.py:86]."""
     n, h, w_, ci, co = shape
     torch.manual_seed(0)
@@ -79,14 +84,14 @@ def test_conv3x3_fprop(shape, fused):
     noise = torch.randn(n, 1, h, w_, device=DEV) if fused else None
     nw = torch.randn(co, device=DEV) * 0.1 if fused else None
     out = torch.empty(n, h, w_, co, dtype=torch.bfloat16, device=DEV)
-    bgn.call("bg_conv_fprop", x, wf, out, n, h, w_, ci, co, 3, bias, noise, nw, None, 1 if fused else 0, 0.2)
+    bgn.call(entry, x, wf, out, n, h, w_, ci, co, 3, bias, noise, nw, None, 1 if fused else 0, 0.2)
     torch.cuda.synchronize()
     ref = F.conv2d(nchw(x), (w * coef).to(torch.bfloat16).float(), None, padding=1)
     if fused:
         ref = ref + bias.view(1, -1, 1, 1) + nw.view(1, -1, 1, 1) * noise
         ref = F.leaky_relu(ref, 0.2)
     err = relerr(nchw(out), ref)
-    assert err < 6e-3, f"conv3x3 fprop {shape} fused={fused}: rel-L2 {err:.3e}"
+    assert err < 6e-3, f"conv3x3 fprop {entry} {shape} fused={fused}: rel-L2 {err:.3e}"
 
 
 @pytest.mark.parametrize("shape", [(2, 16, 16, 64, 64), (1, 64, 64, 16, 32), (4, 8, 8, 256, 128), (2, 32, 32, 32, 16)])
@@ -107,7 +112,7 @@ def test_conv3x3_dgrad_via_fprop(shape):
     assert err < 6e-3, f"dgrad {shape}: rel-L2 {err:.3e}"
 
 
-@pytest.mark.parametrize("shape", CONV_SHAPES[:-1])
+@pytest.mark.parametrize("shape", [s for s in CONV_SHAPES if s[4] != 48])
 def test_conv3x3_wgrad(shape):
     """autograd convolution_backward w.r.t. weight (and the weight half of the R1 double-backward)."""
     n, h, w_, ci, co = shape
@@ -158,3 +163,30 @@ def test_upsample_pool_adain_aux():
     bgn.call("bg_adain_apply", a, stats, style, xo, n, h * w_, c, 1e-8)
     ref = style[:, :c, None, None] * F.instance_norm(af, eps=1e-8) + style[:, c:, None, None]
     assert relerr(nchw(xo), ref) < 5e-3
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64, 64), (1, 64, 64, 32, 64), (3, 32, 32, 128, 128), (1, 32, 32, 256, 256),
+                                   (2, 16, 16, 512, 512)])
+@pytest.mark.parametrize("tangent", [False, True])
+def test_conv3x3_pool_fused(shape, tangent):
+    """CriticBlock.conv_2: conv3x3 -> AvgPool2d(2) -> LeakyReLU in one kernel (gan.py:258-262); with tangent=True the
+    bias-free R1 tangent form  avg_pool(conv(v)) * gate(saved y2)."""
+    n, h, w_, ci, co = shape
+    torch.manual_seed(0)
+    x = nhwc(torch.randn(n, ci, h, w_, device=DEV))
+    w = torch.randn(co, ci, 3, 3, device=DEV)
+    coef = math.sqrt(2 / (ci * 9))
+    wf, _ = pack(w, coef)
+    out = torch.empty(n, h // 2, w_ // 2, co, dtype=torch.bfloat16, device=DEV)
+    conv = F.conv2d(nchw(x), (w * coef).to(torch.bfloat16).float(), None, padding=1)
+    if tangent:
+        y2 = nhwc(torch.randn(n, co, h // 2, w_ // 2, device=DEV))
+        bgn.call("bg_conv_pool_fprop", x, wf, out, n, h, w_, ci, co, None, y2, 0, 0.2)
+        ref = F.avg_pool2d(conv, 2) * torch.where(nchw(y2) > 0, 1.0, 0.2)
+    else:
+        bias = torch.randn(co, device=DEV) * 0.1
+        bgn.call("bg_conv_pool_fprop", x, wf, out, n, h, w_, ci, co, bias, None, 1, 0.2)
+        ref = F.leaky_relu(F.avg_pool2d(conv + bias.view(1, -1, 1, 1), 2), 0.2)
+    torch.cuda.synchronize()
+    err = relerr(nchw(out), ref)
+    assert err < 6e-3, f"fused conv+pool {shape} tangent={tangent}: rel-L2 {err:.3e}"
