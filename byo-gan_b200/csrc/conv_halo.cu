@@ -11,13 +11,16 @@
 //   of tap (ky,kx) for MMA half h is just  start address += ((ky*18 + kx + 8h) * 16 B)  — 16-byte granular,
 //   no swizzle phase to keep consistent.
 //
-// The halo is written by 4 producer warps with 16-byte cp.async (zero-fill for the padding), which is also the
-// hook where prologue transforms (AdaIN apply, bilinear upsample) fuse in later.  Weights stream by TMA
+// The halo is written by 8 producer warps with 16-byte cp.async (zero-fill for the padding); per-thread copy
+// tables are built once per kernel and interior tiles skip every bounds test.  Weights stream by TMA
 // (128/64/32-byte swizzle) per (chunk, tap), or stay RESIDENT in shared memory for the whole kernel when the
 // layer's pack fits (all the high-resolution layers).  Accumulators: TMEM, 2 stages x 2 halves x 128 columns.
+// Epilogue: 8 warps; bias + noise + LeakyReLU (+ gate from a saved activation) in registers, then the bf16 tile
+// is transposed through a swizzled shared-memory stage so that every global store (and gate load) instruction
+// moves whole 128-byte lines; an optional 2x2 average pool (warp shuffles) runs before the activation.
 //
 // Warp roles: 0 = weight TMA producer, 1 = MMA issuer + TMEM allocator, 2..9 = epilogue (one 32-row TMEM
-// quarter of one MMA half each), 10..13 = halo producers.
+// quarter of one MMA half each), 10..17 = halo producers.
 #include "common.cuh"
 
 #include <stdlib.h>
@@ -27,7 +30,7 @@ namespace bg {
 namespace {
 
 constexpr int kEpiWarps = 8;                     // warps 2..5 drain MMA half 0, warps 6..9 half 1
-constexpr int kProdWarps = 4;
+constexpr int kProdWarps = 8;
 constexpr int kProdThreads = 32 * kProdWarps;
 constexpr int kThreads = 32 * (2 + kEpiWarps + kProdWarps);
 constexpr int kTile = 16;                       // output tile edge
@@ -36,18 +39,19 @@ constexpr int kHaloPix = kHalo * kHalo;         // 324
 constexpr uint32_t kPlaneBytes = 325 * 16;      // 324 pixels * 16 B, padded so the 8 planes hit distinct banks
 constexpr uint32_t kRowBytes = kHalo * 16;      // 288: SBO between 8-pixel groups (one image row down)
 constexpr int kMaxBStages = 8;
-constexpr int kAStages = 3;
+constexpr int kMaxAStages = 3;
 constexpr int kMaxN = 128;
 constexpr uint32_t kTmemCols = 512;
 
 struct HaloParams {
   int N, H, W, Cin, Cout;
-  int tiles_w, tiles_h;
-  int block_n, n_blocks;
+  int tw_shift, th_shift, nb_shift;     // log2 of tiles per row / per column / n-blocks (all powers of two)
+  int block_n;
   int kc, k_chunks, cpp_shift;
-  int b_stages, b_resident;
+  int a_stages, b_stages, b_resident;
   uint32_t a_stage_bytes, b_tile_bytes, b_tx_bytes;
   uint32_t b_layout, b_sbo;
+  uint32_t epi_row_bytes;               // bytes of one pixel row in the epilogue transpose stage (32 / 64 / 128)
   int num_tiles;
   const __nv_bfloat16* x;
   const float* bias;
@@ -65,26 +69,36 @@ struct TileCoord {
   int w0, h0, n, co0;
 };
 
-__device__ __forceinline__ float4 lds128(const float* p) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
-  return v;
-}
-
 __device__ __forceinline__ TileCoord decode_tile(const HaloParams& p, int tile) {
   TileCoord t;
-  const int nb = tile % p.n_blocks;
-  int pt = tile / p.n_blocks;
-  t.w0 = (pt % p.tiles_w) * kTile;
-  pt /= p.tiles_w;
-  t.h0 = (pt % p.tiles_h) * kTile;
-  t.n = pt / p.tiles_h;
+  const int nb = tile & ((1 << p.nb_shift) - 1);
+  int pt = tile >> p.nb_shift;
+  t.w0 = (pt & ((1 << p.tw_shift) - 1)) * kTile;
+  pt >>= p.tw_shift;
+  t.h0 = (pt & ((1 << p.th_shift) - 1)) * kTile;
+  t.n = pt >> p.th_shift;
   t.co0 = nb * p.block_n;
   return t;
 }
 
+__device__ __forceinline__ float4 lds128f(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_16_full(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -93,11 +107,12 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// Warp 1 issues every tcgen05.mma of the CTA.  For the narrow layers an M=128 x N<=64 MMA retires in 16-48 clk,
-// so the issue loop itself is the critical path: the whole warp runs it converged (all values warp-uniform, so
-// ptxas keeps descriptors in uniform registers instead of R2UR-ing them per instruction), one elected lane
-// executes the tcgen05 instructions, descriptors are 64-bit values advanced by compile-time constants, and the
-// k-steps / taps are unrolled.
+// ---------------------------------------------------------------------------------------------------------
+// MMA issue (warp 1).  For the narrow layers an M=128 x N<=64 MMA retires in 16-48 clk, so the issue loop itself
+// is the critical path: the whole warp runs it converged (all values warp-uniform, so ptxas keeps descriptors in
+// uniform registers), one elected lane executes the tcgen05 instructions, descriptors are 64-bit values advanced
+// by compile-time constants, and the k-steps / taps are unrolled.
+// ---------------------------------------------------------------------------------------------------------
 template <int KSTEPS>
 __device__ __forceinline__ void mma_issue_loop(const HaloParams& p, uint8_t* a_base, uint8_t* b_base, uint64_t* b_full,
                                                uint64_t* b_empty, uint64_t* a_full, uint64_t* a_empty,
@@ -130,18 +145,19 @@ __device__ __forceinline__ void mma_issue_loop(const HaloParams& p, uint8_t* a_b
       if (p.b_resident) {
         const uint64_t b_chunk = b_desc0 + (uint64_t)((uint32_t)(kcx * 9) * b_tile_step);
         if (leader) {
-          if (!(p.debug & 2))
+          if (!(p.debug & 2)) {
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const uint64_t a_tap = a_stage + (uint64_t)((tap / 3) * kHalo + (tap % 3));
-            const uint64_t b_tap = b_chunk + (uint64_t)((uint32_t)tap * b_tile_step);
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint64_t a_tap = a_stage + (uint64_t)((tap / 3) * kHalo + (tap % 3));
+              const uint64_t b_tap = b_chunk + (uint64_t)((uint32_t)tap * b_tile_step);
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
+              for (int half = 0; half < 2; ++half) {
 #pragma unroll
-              for (int k = 0; k < KSTEPS; ++k) {
-                tc_mma_bf16(d_tmem + (uint32_t)half * 128u,
-                            a_tap + (uint64_t)(half * 8 + k * (2 * (kPlaneBytes >> 4))), b_tap + (uint64_t)(k * 2),
-                            idesc, (k == 0 && tap == 0) ? accum : 1u);
+                for (int k = 0; k < KSTEPS; ++k) {
+                  tc_mma_bf16(d_tmem + (uint32_t)half * 128u,
+                              a_tap + (uint64_t)(half * 8 + k * (2 * (kPlaneBytes >> 4))), b_tap + (uint64_t)(k * 2),
+                              idesc, (k == 0 && tap == 0) ? accum : 1u);
+                }
               }
             }
           }
@@ -155,13 +171,15 @@ __device__ __forceinline__ void mma_issue_loop(const HaloParams& p, uint8_t* a_b
           if (leader) {
             const uint64_t a_tap = a_stage + (uint64_t)((tap / 3) * kHalo + (tap % 3));
             const uint64_t b_tap = b_desc0 + (uint64_t)((uint32_t)bstage * b_tile_step);
+            if (!(p.debug & 2)) {
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
+              for (int half = 0; half < 2; ++half) {
 #pragma unroll
-              for (int k = 0; k < KSTEPS; ++k) {
-                tc_mma_bf16(d_tmem + (uint32_t)half * 128u,
-                            a_tap + (uint64_t)(half * 8 + k * (2 * (kPlaneBytes >> 4))), b_tap + (uint64_t)(k * 2),
-                            idesc, k == 0 ? accum : 1u);
+                for (int k = 0; k < KSTEPS; ++k) {
+                  tc_mma_bf16(d_tmem + (uint32_t)half * 128u,
+                              a_tap + (uint64_t)(half * 8 + k * (2 * (kPlaneBytes >> 4))), b_tap + (uint64_t)(k * 2),
+                              idesc, k == 0 ? accum : 1u);
+                }
               }
             }
             tc_commit(&b_empty[bstage]);
@@ -175,7 +193,7 @@ __device__ __forceinline__ void mma_issue_loop(const HaloParams& p, uint8_t* a_b
         if (leader) tc_commit(&a_empty[astage]);
       }
       __syncwarp();
-      if (++astage == kAStages) {
+      if (++astage == p.a_stages) {
         astage = 0;
         aphase ^= 1u;
       }
@@ -187,23 +205,102 @@ __device__ __forceinline__ void mma_issue_loop(const HaloParams& p, uint8_t* a_b
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Halo producers (warps 10..17).  CPP_SHIFT = log2(16-byte channel units per pixel in a chunk) = 3 / 2 / 1 for
+// kc = 64 / 32 / 16.  Thread pt copies units u = pt + 256 i; for each it keeps, in registers, the element offset
+// relative to the halo origin and the packed (row, column), so an interior tile costs one 64-bit add and one
+// LDGSTS per 16 bytes.
+// ---------------------------------------------------------------------------------------------------------
+template <int CPP_SHIFT>
+__device__ __forceinline__ void halo_producer_loop(const HaloParams& p, uint8_t* a_base, uint64_t* a_full,
+                                                   uint64_t* a_empty, int pt) {
+  constexpr int kUnits = kHaloPix << CPP_SHIFT;
+  constexpr int kIters = (kUnits + kProdThreads - 1) / kProdThreads;     // 11 / 6 / 3
+  int rel[kIters];        // element offset of the unit relative to the halo origin pixel (h0-1, w0-1), channel 0
+  int hyx[kIters];        // (hy << 8) | hx, or -1 for the padding units past the end of the table
+  uint32_t soff[kIters];  // byte offset inside the A stage
+#pragma unroll
+  for (int i = 0; i < kIters; ++i) {
+    const int u = pt + i * kProdThreads;
+    const int px = u >> CPP_SHIFT;
+    const int c8 = u & ((1 << CPP_SHIFT) - 1);
+    const int hy = px / kHalo, hx = px - hy * kHalo;
+    const bool live = u < kUnits;
+    rel[i] = (hy * p.W + hx) * p.Cin + c8 * 8;
+    hyx[i] = live ? ((hy << 8) | hx) : -1;
+    soff[i] = (uint32_t)c8 * kPlaneBytes + (uint32_t)px * 16u;
+  }
+  int stage = 0;
+  uint32_t phase = 0;
+  int pending_stage = -1;
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    const TileCoord t = decode_tile(p, tile);
+    const int hb = t.h0 - 1, wb = t.w0 - 1;
+    // pointer to (n, h0-1, w0-1, 0); only dereferenced where in bounds
+    const __nv_bfloat16* org = p.x + ((int64_t)t.n * p.H * p.W + (int64_t)hb * p.W + wb) * p.Cin;
+    const bool interior = (hb >= 0) && (wb >= 0) && (t.h0 + kTile < p.H) && (t.w0 + kTile < p.W);
+    for (int kcx = 0; kcx < p.k_chunks; ++kcx) {
+      mbar_wait(&a_empty[stage], phase ^ 1u);
+      const uint32_t sdst = smem_u32(a_base + (size_t)stage * p.a_stage_bytes);
+      const __nv_bfloat16* cb = org + kcx * p.kc;
+      if (!(p.debug & 4)) {
+        if (interior) {
+#pragma unroll
+          for (int i = 0; i < kIters; ++i)
+            if (i < kIters - 1 || hyx[i] >= 0) cp_async_16_full(sdst + soff[i], cb + rel[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < kIters; ++i) {
+            if (i < kIters - 1 || hyx[i] >= 0) {
+              const int h = hb + (hyx[i] >> 8), w = wb + (hyx[i] & 255);
+              const bool ok = ((unsigned)h < (unsigned)p.H) && ((unsigned)w < (unsigned)p.W);
+              cp_async_16(sdst + soff[i], ok ? (const void*)(cb + rel[i]) : (const void*)p.x, ok ? 16u : 0u);
+            }
+          }
+        }
+      }
+      cp_async_commit();
+      // publish the PREVIOUS stage: its copies have landed once at most one group (this one) is pending
+      if (pending_stage >= 0) {
+        cp_async_wait<1>();
+        fence_proxy_async();
+        mbar_arrive(&a_full[pending_stage]);
+      }
+      pending_stage = stage;
+      if (++stage == p.a_stages) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  }
+  if (pending_stage >= 0) {
+    cp_async_wait<0>();
+    fence_proxy_async();
+    mbar_arrive(&a_full[pending_stage]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
-  // carve: [B region (1024-aligned tiles)] [A stages] [aux]
+  // carve: [B region (1024-aligned tiles)] [A stages] [epilogue transpose stages] [aux]
   const int b_tiles = p.b_resident ? p.k_chunks * 9 : p.b_stages;
   uint8_t* b_base = smem;
   uint8_t* a_base = b_base + (size_t)b_tiles * p.b_tile_bytes;
-  uint8_t* aux = a_base + (size_t)kAStages * p.a_stage_bytes;
-  aux = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(aux) + 15) & ~uintptr_t(15));
+  uint8_t* epi_base = a_base + (size_t)p.a_stages * p.a_stage_bytes;
+  epi_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(epi_base) + 127) & ~uintptr_t(127));
+  uint8_t* aux = epi_base + (size_t)kEpiWarps * 32 * p.epi_row_bytes;
   uint64_t* b_full = reinterpret_cast<uint64_t*>(aux);
   uint64_t* b_empty = b_full + kMaxBStages;
   uint64_t* a_full = b_empty + kMaxBStages;
-  uint64_t* a_empty = a_full + kAStages;
-  uint64_t* tmem_full = a_empty + kAStages;
+  uint64_t* a_empty = a_full + kMaxAStages;
+  uint64_t* tmem_full = a_empty + kMaxAStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);
@@ -218,7 +315,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const HaloParams p)
       mbar_init(&b_full[s], 1);
       mbar_init(&b_empty[s], 1);
     }
-    for (int s = 0; s < kAStages; ++s) {
+    for (int s = 0; s < kMaxAStages; ++s) {
       mbar_init(&a_full[s], kProdThreads);
       mbar_init(&a_empty[s], 1);
     }
@@ -247,8 +344,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const HaloParams p)
     // ------------------------------ weight TMA producer ------------------------------
     if (lane == 0) {
       if (p.b_resident) {
-        // whole pack of this CTA's n-block range is loaded once per n-block change; with n_blocks == 1 (the
-        // only case the host selects residency for) that is once per kernel.
+        // residency is only selected when there is a single n-block: the whole pack is loaded once per kernel
         mbar_expect_tx(&b_full[0], (uint32_t)(p.k_chunks * 9) * p.b_tx_bytes);
         for (int kcx = 0; kcx < p.k_chunks; ++kcx)
           for (int tap = 0; tap < 9; ++tap)
@@ -283,9 +379,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const HaloParams p)
     // m = 32q + i = pixel (image row g = m / 8, column r = m % 8 of the half's 8-wide segment).
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    const int m = q * 32 + lane;
-    const int g = m >> 3, r = m & 7;
+    const int g = (q * 32 + lane) >> 3, r = lane & 7;
     const bool pool_writer = ((lane & 1) == 0) && ((lane & 8) == 0);
+    // transpose stage of this warp: 32 pixel rows x epi_row_bytes, 16-byte chunks XOR-swizzled by row so that both
+    // the row-wise (lane = pixel) and the line-wise (8 lanes = 128 contiguous bytes) accesses are conflict-free
+    const uint32_t rb = p.epi_row_bytes;
+    const int cpr_shift = rb == 128 ? 3 : (rb == 64 ? 2 : 1);       // log2(chunks per row)
+    const int round_cols = (int)(rb >> 1);                          // output channels per transpose round
+    const uint32_t stg = smem_u32(epi_base) + (uint32_t)(warp - 2) * 32u * rb;
+    const uint32_t my_row = stg + (uint32_t)lane * rb;
+    const uint32_t my_swz = (uint32_t)(lane >> (3 - cpr_shift)) & ((1u << cpr_shift) - 1u);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -293,64 +396,86 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const HaloParams p)
       const int h = t.h0 + g, w = t.w0 + half * 8 + r;
       const size_t pix = ((size_t)t.n * p.H + h) * p.W + w;
       const float nz = p.noise != nullptr ? p.noise[pix] : 0.f;
-      const size_t opix = p.pool ? ((size_t)t.n * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1) : pix;
-      __nv_bfloat16* orow = p.out + opix * p.Cout + t.co0;
-      const __nv_bfloat16* grow = p.gate_src ? p.gate_src + opix * p.Cout + t.co0 : nullptr;
-      const bool writer = p.pool ? pool_writer : true;
+      // first pixel of this warp's 4 image rows x 8 columns block (row index 0 of the transpose stage)
+      const size_t pix_q0 = ((size_t)t.n * p.H + t.h0 + q * 4) * p.W + t.w0 + half * 8;
+      const size_t opix_pool = ((size_t)t.n * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u + (uint32_t)half * 128u;
-      for (int c = 0; c < ((p.debug & 8) ? 0 : p.block_n); c += 16) {
-        uint32_t v[16];
-        tmem_ld_x16(taddr + c, v);
-        float bn[16];
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 b4 = lds128(bias_s + t.co0 + c + 4 * j4);
-          bn[4 * j4 + 0] = b4.x; bn[4 * j4 + 1] = b4.y; bn[4 * j4 + 2] = b4.z; bn[4 * j4 + 3] = b4.w;
+      const int ncols = (p.debug & 8) ? 0 : p.block_n;
+      for (int c0 = 0; c0 < ncols; c0 += round_cols) {
+        const bool staged = !p.pool;
+        if (staged && p.gate_src != nullptr) {
+          // line-wise load of the gate tile into the stage: lane -> (row = lane / cpr + i * 32 / cpr, chunk = lane % cpr)
+          const int cpr = 1 << cpr_shift;
+          const int ch = lane & (cpr - 1);
+#pragma unroll 4
+          for (int row = lane >> cpr_shift; row < 32; row += 32 >> cpr_shift) {
+            const size_t gp = pix_q0 + (size_t)(row >> 3) * p.W + (row & 7);
+            const uint4 gv = *reinterpret_cast<const uint4*>(p.gate_src + gp * p.Cout + t.co0 + c0 + ch * 8);
+            const uint32_t swz = (uint32_t)(row >> (3 - cpr_shift)) & (uint32_t)(cpr - 1);
+            sts128(stg + (uint32_t)row * rb + (((uint32_t)ch ^ swz) << 4), gv);
+          }
+          __syncwarp();
         }
-        if (p.noise != nullptr) {
+        for (int c = c0; c < c0 + round_cols; c += 16) {
+          uint32_t v[16];
+          tmem_ld_x16(taddr + c, v);
+          float bn[16];
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 n4 = lds128(nw_s + t.co0 + c + 4 * j4);
-            bn[4 * j4 + 0] = fmaf(n4.x, nz, bn[4 * j4 + 0]);
-            bn[4 * j4 + 1] = fmaf(n4.y, nz, bn[4 * j4 + 1]);
-            bn[4 * j4 + 2] = fmaf(n4.z, nz, bn[4 * j4 + 2]);
-            bn[4 * j4 + 3] = fmaf(n4.w, nz, bn[4 * j4 + 3]);
+            const float4 b4 = lds128f(bias_s + t.co0 + c + 4 * j4);
+            bn[4 * j4 + 0] = b4.x; bn[4 * j4 + 1] = b4.y; bn[4 * j4 + 2] = b4.z; bn[4 * j4 + 3] = b4.w;
           }
-        }
-        uint4 ga = make_uint4(0, 0, 0, 0), gb = ga;
-        if (grow != nullptr && writer) {
-          const uint4* g4 = reinterpret_cast<const uint4*>(grow + c);
-          ga = g4[0];
-          gb = g4[1];
-        }
-        tmem_ld_wait();
-        float f[16];
+          if (p.noise != nullptr) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + bn[j];
-        if (p.pool) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float sum = f[j] + __shfl_xor_sync(0xffffffffu, f[j], 1);
-            sum += __shfl_xor_sync(0xffffffffu, sum, 8);
-            f[j] = 0.25f * sum;
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 n4 = lds128f(nw_s + t.co0 + c + 4 * j4);
+              bn[4 * j4 + 0] = fmaf(n4.x, nz, bn[4 * j4 + 0]);
+              bn[4 * j4 + 1] = fmaf(n4.y, nz, bn[4 * j4 + 1]);
+              bn[4 * j4 + 2] = fmaf(n4.z, nz, bn[4 * j4 + 2]);
+              bn[4 * j4 + 3] = fmaf(n4.w, nz, bn[4 * j4 + 3]);
+            }
           }
-        }
-        if (p.act) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], f[j] * p.slope);      // LeakyReLU, 0 < slope < 1
-        }
-        if (grow != nullptr) {
-          const uint32_t gw[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float2 gv = unpack_bf16x2(gw[j]);
-            f[2 * j] *= gv.x > 0.f ? 1.f : p.slope;
-            f[2 * j + 1] *= gv.y > 0.f ? 1.f : p.slope;
+          const uint32_t chunk0 = (uint32_t)((c - c0) >> 3);            // first of this thread's two 16-byte chunks
+          const uint32_t sa0 = my_row + (((chunk0) ^ my_swz) << 4);
+          const uint32_t sa1 = my_row + (((chunk0 + 1u) ^ my_swz) << 4);
+          uint4 ga = make_uint4(0, 0, 0, 0), gb = ga;
+          if (p.gate_src != nullptr) {
+            if (staged) {
+              ga = lds128(sa0);
+              gb = lds128(sa1);
+            } else if (pool_writer) {
+              const uint4* g4 = reinterpret_cast<const uint4*>(p.gate_src + opix_pool * p.Cout + t.co0 + c);
+              ga = g4[0];
+              gb = g4[1];
+            }
           }
-        }
-        if (writer && !(p.debug & 1)) {
+          tmem_ld_wait();
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + bn[j];
+          if (p.pool) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float sum = f[j] + __shfl_xor_sync(0xffffffffu, f[j], 1);
+              sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+              f[j] = 0.25f * sum;
+            }
+          }
+          if (p.act) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], f[j] * p.slope);      // LeakyReLU, 0 < slope < 1
+          }
+          if (p.gate_src != nullptr) {
+            const uint32_t gw[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 gv = unpack_bf16x2(gw[j]);
+              f[2 * j] *= gv.x > 0.f ? 1.f : p.slope;
+              f[2 * j + 1] *= gv.y > 0.f ? 1.f : p.slope;
+            }
+          }
           uint4 o0, o1;
           o0.x = pack_bf16x2(f[0], f[1]);
           o0.y = pack_bf16x2(f[2], f[3]);
@@ -360,9 +485,29 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const HaloParams p)
           o1.y = pack_bf16x2(f[10], f[11]);
           o1.z = pack_bf16x2(f[12], f[13]);
           o1.w = pack_bf16x2(f[14], f[15]);
-          uint4* o4 = reinterpret_cast<uint4*>(orow + c);
-          o4[0] = o0;
-          o4[1] = o1;
+          if (staged) {
+            sts128(sa0, o0);
+            sts128(sa1, o1);
+          } else if (pool_writer && !(p.debug & 1)) {
+            uint4* o4 = reinterpret_cast<uint4*>(p.out + opix_pool * p.Cout + t.co0 + c);
+            o4[0] = o0;
+            o4[1] = o1;
+          }
+        }
+        if (staged) {
+          __syncwarp();
+          if (!(p.debug & 1)) {
+            const int cpr = 1 << cpr_shift;
+            const int ch = lane & (cpr - 1);
+#pragma unroll 4
+            for (int row = lane >> cpr_shift; row < 32; row += 32 >> cpr_shift) {
+              const uint32_t swz = (uint32_t)(row >> (3 - cpr_shift)) & (uint32_t)(cpr - 1);
+              const uint4 ov = lds128(stg + (uint32_t)row * rb + (((uint32_t)ch ^ swz) << 4));
+              const size_t op = pix_q0 + (size_t)(row >> 3) * p.W + (row & 7);
+              *reinterpret_cast<uint4*>(p.out + op * p.Cout + t.co0 + c0 + ch * 8) = ov;
+            }
+          }
+          __syncwarp();
         }
       }
       tc_fence_before();
@@ -373,63 +518,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const HaloParams p)
     }
   } else {
     // ------------------------------ halo producers (cp.async, zero-fill padding) ------------------------------
-    // Thread pt always copies the same 16-byte channel unit c8 of pixels px0, px0 + pstride, ... so the only
-    // per-copy work is an incremental (row, column) walk over the 18-wide halo, a bounds test and one address.
-    const int pt = threadIdx.x - 32 * (2 + kEpiWarps);       // 0..127
-    const int cpp_shift = p.cpp_shift;                        // log2(16-byte units per pixel in this chunk)
-    const int c8 = pt & ((1 << cpp_shift) - 1);
-    const int px0 = pt >> cpp_shift;
-    const int pstride = kProdThreads >> cpp_shift;            // pixels advanced per copy: 16 / 32 / 64
-    const int iters = (kHaloPix - px0 + pstride - 1) / pstride;
-    const int dq = pstride / kHalo, dr = pstride % kHalo;
-    const int hy0 = px0 / kHalo, hx0 = px0 % kHalo;
-    const uint32_t soff0 = (uint32_t)c8 * kPlaneBytes + (uint32_t)px0 * 16u;
-    const uint32_t sstep = (uint32_t)pstride * 16u;
-    int stage = 0;
-    uint32_t phase = 0;
-    int pending_stage = -1;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
-      const __nv_bfloat16* xn = p.x + (size_t)t.n * p.H * p.W * p.Cin;
-      const int hb = t.h0 - 1, wb = t.w0 - 1;
-      for (int kcx = 0; kcx < p.k_chunks; ++kcx) {
-        mbar_wait(&a_empty[stage], phase ^ 1u);
-        uint32_t soff = smem_u32(a_base + (size_t)stage * p.a_stage_bytes) + soff0;
-        const __nv_bfloat16* cb = xn + kcx * p.kc + c8 * 8;
-        int hy = hy0, hx = hx0;
-#pragma unroll 4
-        for (int it = 0; it < iters; ++it) {
-          const int h = hb + hy, w = wb + hx;
-          const bool ok = ((unsigned)h < (unsigned)p.H) && ((unsigned)w < (unsigned)p.W);
-          const __nv_bfloat16* src = ok ? cb + ((int64_t)h * p.W + w) * p.Cin : p.x;
-          if (!(p.debug & 4)) cp_async_16(soff, src, ok ? 16u : 0u);
-          soff += sstep;
-          hx += dr;
-          hy += dq;
-          if (hx >= kHalo) {
-            hx -= kHalo;
-            ++hy;
-          }
-        }
-        cp_async_commit();
-        // publish the PREVIOUS stage: its copies have landed once at most one group (this one) is pending
-        if (pending_stage >= 0) {
-          cp_async_wait<1>();
-          fence_proxy_async();
-          mbar_arrive(&a_full[pending_stage]);
-        }
-        pending_stage = stage;
-        if (++stage == kAStages) {
-          stage = 0;
-          phase ^= 1u;
-        }
-      }
-    }
-    if (pending_stage >= 0) {
-      cp_async_wait<0>();
-      fence_proxy_async();
-      mbar_arrive(&a_full[pending_stage]);
-    }
+    const int pt = threadIdx.x - 32 * (2 + kEpiWarps);       // 0..255
+    if (p.cpp_shift == 3) halo_producer_loop<3>(p, a_base, a_full, a_empty, pt);
+    else if (p.cpp_shift == 2) halo_producer_loop<2>(p, a_base, a_full, a_empty, pt);
+    else halo_producer_loop<1>(p, a_base, a_full, a_empty, pt);
   }
 
   tc_fence_before();
@@ -440,14 +532,33 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const HaloParams p)
   }
 }
 
+int ilog2(int v) {
+  int s = 0;
+  while ((1 << s) < v) ++s;
+  return s;
+}
+
+int pick_block_n(int Cout) {
+  for (int c = kMaxN; c >= 16; c -= 16)
+    if (Cout % c == 0) return c;
+  return 0;
+}
+
 }  // namespace
 
 bool conv_halo_supported(int N, int H, int W, int Cin, int Cout, int ksize) {
-  return ksize == 3 && H >= 16 && W >= 16 && H % 16 == 0 && W % 16 == 0 && Cin % 16 == 0 && Cout % 16 == 0 &&
-         Cout <= 512 && N > 0;
+  if (!(ksize == 3 && H >= 16 && W >= 16 && (H & (H - 1)) == 0 && (W & (W - 1)) == 0 && Cin % 16 == 0 &&
+        Cout % 16 == 0 && Cout <= 512 && N > 0))
+    return false;
+  const int bn = pick_block_n(Cout);
+  if (bn == 0) return false;
+  const int nb = Cout / bn;
+  if ((nb & (nb - 1)) != 0) return false;                    // tile decode uses shifts
+  if (!(bn == 16 || bn == 32 || bn % 64 == 0)) return false; // epilogue transpose rounds are 16 / 32 / 64 columns
+  return true;
 }
 
-// Host launcher; same arguments as launch_conv_fprop (ksize must be 3).
+// Host launcher; same arguments as launch_conv_fprop (ksize must be 3) plus the fused-pool switch.
 int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, int W, int Cin, int Cout,
                      const float* bias, const float* noise, const float* noise_w, const void* gate_src, int act,
                      int pool, float slope, cudaStream_t stream) {
@@ -456,15 +567,12 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
   HaloParams p;
   memset(&p, 0, sizeof(p));
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
-  p.tiles_w = W / kTile;
-  p.tiles_h = H / kTile;
-  int bn_ch = 0;
-  for (int c = kMaxN; c >= 16; c -= 16) {
-    if (Cout % c == 0) { bn_ch = c; break; }
-  }
-  BG_REQUIRE(bn_ch > 0, "conv_halo: no valid N tile for Cout %d", Cout);
+  p.tw_shift = ilog2(W / kTile);
+  p.th_shift = ilog2(H / kTile);
+  const int bn_ch = pick_block_n(Cout);
   p.block_n = bn_ch;
-  p.n_blocks = Cout / bn_ch;
+  const int n_blocks = Cout / bn_ch;
+  p.nb_shift = ilog2(n_blocks);
   p.kc = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0 ? 32 : 16);
   p.k_chunks = Cin / p.kc;
   p.cpp_shift = p.kc == 64 ? 3 : (p.kc == 32 ? 2 : 1);
@@ -474,19 +582,31 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
   p.b_tx_bytes = (uint32_t)p.block_n * row_bytes;
   p.b_tile_bytes = (p.b_tx_bytes + 1023u) & ~1023u;
   p.a_stage_bytes = (uint32_t)(p.kc / 8) * kPlaneBytes;
-  const uint32_t aux_bytes = 8 * (2 * kMaxBStages + 2 * kAStages + 4) + 16 + 2 * 512 * 4 + 64;
-  const uint32_t budget = 227u * 1024u - 1024u - aux_bytes - kAStages * p.a_stage_bytes;
+  p.epi_row_bytes = (uint32_t)(bn_ch >= 64 ? 64 : bn_ch) * 2u;
+  const uint32_t epi_bytes = (uint32_t)kEpiWarps * 32u * p.epi_row_bytes + 128u;
+  const uint32_t aux_bytes = 8 * (2 * kMaxBStages + 2 * kMaxAStages + 4) + 16 + 2 * 512 * 4 + 64;
+  const uint32_t total = 227u * 1024u - 1024u - aux_bytes - epi_bytes;
   const uint32_t resident_bytes = (uint32_t)p.k_chunks * 9u * p.b_tile_bytes;
-  p.b_resident = (p.n_blocks == 1 && resident_bytes <= budget) ? 1 : 0;
+  // prefer resident weights (3 halo stages if they fit, else 2); otherwise stream the weights past 3 halo stages
+  p.a_stages = 3;
+  p.b_resident = 0;
+  if (n_blocks == 1) {
+    if (resident_bytes + 3u * p.a_stage_bytes <= total) {
+      p.b_resident = 1;
+    } else if (resident_bytes + 2u * p.a_stage_bytes <= total) {
+      p.b_resident = 1;
+      p.a_stages = 2;
+    }
+  }
   if (p.b_resident) {
     p.b_stages = 1;
   } else {
-    int st = (int)(budget / p.b_tile_bytes);
+    int st = (int)((total - 3u * p.a_stage_bytes) / p.b_tile_bytes);
     if (st > kMaxBStages) st = kMaxBStages;
     BG_REQUIRE(st >= 2, "conv_halo: weight tile does not fit shared memory");
     p.b_stages = st;
   }
-  p.num_tiles = p.tiles_w * p.tiles_h * N * p.n_blocks;
+  p.num_tiles = (W / kTile) * (H / kTile) * N * n_blocks;
   p.x = reinterpret_cast<const __nv_bfloat16*>(x);
   p.bias = bias; p.noise = noise; p.noise_w = noise_w;
   p.gate_src = reinterpret_cast<const __nv_bfloat16*>(gate_src);
@@ -506,7 +626,7 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
     if (make_tmap_bf16(&tmw, wpack, 3, dims, str, box, (int)row_bytes) != 0) return 1;
   }
   const size_t b_tiles = p.b_resident ? (size_t)p.k_chunks * 9 : (size_t)p.b_stages;
-  const size_t smem_bytes = b_tiles * p.b_tile_bytes + (size_t)kAStages * p.a_stage_bytes + aux_bytes + 1024;
+  const size_t smem_bytes = b_tiles * p.b_tile_bytes + (size_t)p.a_stages * p.a_stage_bytes + epi_bytes + aux_bytes + 1024;
   BG_REQUIRE(smem_bytes <= 227 * 1024, "conv_halo: shared memory budget exceeded (%zu)", smem_bytes);
   static bool attr_set = false;
   if (!attr_set) {

@@ -132,6 +132,19 @@ def conv3x3(x, wpack, cin, cout, bias=None, noise=None, noise_w=None, gate_src=N
     return out
 
 
+def conv3x3_pool(x, wpack, cin, cout, bias=None, gate_src=None, act=True):
+    """conv3x3 -> AvgPool2d(2) -> LeakyReLU (gan.py:258-262), or with act=False and gate_src the R1 tangent of it.
+    One fused kernel at H,W >= 16; conv + pool kernels below that."""
+    n, h, w_, _ = x.shape
+    out = _bf16(n, h // 2, w_ // 2, cout, device=x.device)
+    if h >= 16 and w_ >= 16:
+        call("bg_conv_pool_fprop", x, wpack, out, n, h, w_, cin, cout, bias, gate_src, 1 if act else 0, SLOPE)
+    else:
+        u = conv3x3(x, wpack, cin, cout, bias=bias, act=False)
+        call("bg_pool_act_fwd", u, gate_src, out, n, h // 2, w_ // 2, cout, SLOPE, 0 if act else 1)
+    return out
+
+
 def conv_wgrad(x, g, w_param, cin_pad=None, extra=None):
     """dW for a 3x3 conv parameter `w_param` from input x and output-gradient g (both NHWC bf16).
     `extra=(v, ghat)` adds the R1 second-order pair into the same accumulator (doubled-K contraction)."""
@@ -417,10 +430,7 @@ def critic_forward(critic, packs: PackCache, images, steps, alpha):
         wf1, _ = packs.conv(c1.weight)
         wf2, _ = packs.conv(c2.weight)
         y1 = conv3x3(feat, wf1, cin, cout, bias=c1.bias.detach(), act=True)                   # gan.py:254-255
-        u = conv3x3(y1, wf2, cout, cout, bias=c2.bias.detach(), act=False)                    # gan.py:259
-        y2 = _bf16(B, R // 2, R // 2, cout, device=dev)
-        call("bg_pool_act_fwd", u, None, y2, B, R // 2, R // 2, cout, SLOPE, 0)               # gan.py:260-261
-        del u
+        y2 = conv3x3_pool(y1, wf2, cout, cout, bias=c2.bias.detach(), act=True)               # gan.py:259-261
         e = dict(k=k, x=feat, y1=y1, y2=y2, R=R, cin=cin, cout=cout, c1=c1, c2=c2)
         if idx == 0 and fade:
             imgp = _f32(B, 3, R // 2, R // 2, device=dev)
@@ -479,10 +489,7 @@ def critic_tangent(critic, packs: PackCache, tape, v_img):
         t = dict(x=v)
         v1 = conv3x3(v, wf1, cin, cout, gate_src=e["y1"])
         t["y1"] = v1
-        ud = conv3x3(v1, wf2, cout, cout)
-        v2 = _bf16(B, r // 2, r // 2, cout, device=dev)
-        call("bg_pool_act_fwd", ud, e["y2"], v2, B, r // 2, r // 2, cout, SLOPE, 1)
-        del ud
+        v2 = conv3x3_pool(v1, wf2, cout, cout, gate_src=e["y2"], act=False)
         if "d" in e:
             a_mix = tape["a_mix"]
             vp = _f32(B, 3, r // 2, r // 2, device=dev)
