@@ -26,6 +26,7 @@ SIGNATURES = {
     "bg_conv_pool_fprop": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _F, _P],
     "bg_conv_fprop_tapwise": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _F, _P],
     "bg_conv_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "bg_conv_wgrad_tapwise": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "bg_act_gate": [_P, _P, _P, _Z, _F, _P],
     "bg_axpby": [_P, _P, _P, _Z, _F, _F, _P],
     "bg_pool_act_fwd": [_P, _P, _P, _I, _I, _I, _I, _F, _I, _P],

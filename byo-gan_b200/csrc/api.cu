@@ -9,6 +9,8 @@ int launch_conv_halo(const void*, const void*, void*, int, int, int, int, int, c
                      const void*, int, int, float, cudaStream_t);
 bool conv_halo_supported(int, int, int, int, int, int);
 int launch_conv_wgrad(const void*, const void*, float*, int, int, int, int, int, int, cudaStream_t);
+int launch_conv_wgrad_halo(const void*, const void*, float*, int, int, int, int, int, int, cudaStream_t);
+bool conv_wgrad_halo_supported(int, int, int, int, int);
 int launch_pack_weight(const float*, void*, void*, int, int, int, int, float, cudaStream_t);
 int launch_unpack_wgrad(const float*, float*, int, int, int, int, float, int, cudaStream_t);
 int launch_act_gate(const void*, const void*, void*, size_t, float, cudaStream_t);
@@ -86,6 +88,12 @@ int bg_conv_fprop_tapwise(const void* x, const void* wpack, void* out, int N, in
 }
 int bg_conv_wgrad(const void* x, const void* g, float* dwp, int N, int H, int W, int Cin, int Cout, int accumulate,
                   void* stream) {
+  if (bg::conv_wgrad_halo_supported(N, H, W, Cin, Cout))
+    return bg::launch_conv_wgrad_halo(x, g, dwp, N, H, W, Cin, Cout, accumulate, S(stream));
+  return bg::launch_conv_wgrad(x, g, dwp, N, H, W, Cin, Cout, accumulate, S(stream));
+}
+int bg_conv_wgrad_tapwise(const void* x, const void* g, float* dwp, int N, int H, int W, int Cin, int Cout,
+                          int accumulate, void* stream) {
   return bg::launch_conv_wgrad(x, g, dwp, N, H, W, Cin, Cout, accumulate, S(stream));
 }
 int bg_act_gate(const void* g, const void* y, void* out, size_t n, float slope, void* stream) {

@@ -1,0 +1,262 @@
+// Weight-gradient GEMM of the 3x3 pad-1 convolution for maps >= 16x16: shifted-view variant of conv_wgrad.cu.
+//
+//   dWp[tap][co][ci] = sum_{n,h,w} G[n,h,w,co] * X[n, h+ky-1, w+kx-1, ci]
+//
+// Same GEMM view as conv_wgrad.cu (M = co, N = ci, K = pixels, both operands MN-major straight from NHWC), but
+// the three kx taps of a kernel row no longer get three separately loaded X tiles.  A K block is a 16x8 pixel
+// tile; X is loaded ONCE per K block as an (16+2) x 8 halo box (TMA, zero fill = padding) and tap kx of image
+// row r is just the same shared-memory tile read from pixel row  r*18 + kx  on: UMMA's swizzle is a function of
+// the absolute shared-memory address, so a descriptor whose start is shifted by whole 128/64/32-byte pixel rows
+// stays consistent with what TMA wrote (verified on B200 against torch for all three swizzle widths).
+// That cuts the L2->SMEM fill per K block from G + 3 X tiles to G + 1.125 X tiles, which was the binding limit
+// (profiles/r1_ncu_full_conv_wgrad.csv).  The ci slab grows to 128 (two 64-wide sub-slabs, LBO apart) so the
+// N=128 MMAs run at full tensor rate; 3 tap accumulators x 128 columns live in TMEM; 3-stage TMA pipeline; the
+// issue loop is warp-uniform (descriptors in uniform registers); split-K partials are reduced with vector fp32
+// reductions (red.global.add.v4.f32).
+#include "common.cuh"
+
+namespace bg {
+
+namespace {
+
+constexpr int kEpiWarps = 4;
+constexpr int kThreads = 32 * (2 + kEpiWarps);
+constexpr int kStages = 3;
+constexpr int kBw = 16, kBh = 8;                 // K block = 16 x 8 pixels of one image
+constexpr int kHaloW = kBw + 2;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kTapStride = 128;             // TMEM columns reserved per tap accumulator
+constexpr uint32_t kARegion = 32768;             // 128 pixels x (2 x 64 co) x 2 B
+constexpr uint32_t kBSub = 18432;                // 18 x 8 pixels x 64 ci x 2 B (one 64-wide ci sub-slab)
+constexpr uint32_t kStageBytes = kARegion + 2 * kBSub;
+
+struct WgradHaloParams {
+  int N, H, W, Cin, Cout;
+  int tiles_w, tiles_h;
+  int total_kblocks, splits, kblocks_per_split;
+  int co_tiles, ci_slabs;
+  int co_slab, co_nslabs;          // G is loaded as co_nslabs boxes of co_slab channels (<= 64 each)
+  int ci_sub, ci_nsub, ci_slab;    // X slab = ci_nsub sub-slabs of ci_sub channels (<= 64 each)
+  uint32_t a_row_bytes, b_row_bytes;
+  uint32_t a_layout, b_layout;
+  uint32_t a_slab_bytes;
+  float* dw;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x,
+                       const WgradHaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+
+  uint8_t* aux = smem + (size_t)kStages * kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* done_bar = empty_bar + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+
+  // work decode: blockIdx -> (co tile, ci slab, kernel row, K split)
+  const int split = blockIdx.x % p.splits;
+  const int unit = blockIdx.x / p.splits;
+  const int tg = unit % 3;                       // ky
+  const int cis = (unit / 3) % p.ci_slabs;
+  const int cot = unit / (3 * p.ci_slabs);
+  const int co0 = cot * 128;
+  const int ci0 = cis * p.ci_slab;
+  const int kb_begin = split * p.kblocks_per_split;
+  int kb_end = kb_begin + p.kblocks_per_split;
+  if (kb_end > p.total_kblocks) kb_end = p.total_kblocks;
+  const int my_kblocks = kb_end > kb_begin ? kb_end - kb_begin : 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_g);
+    tma_prefetch_desc(&tmap_x);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (my_kblocks > 0) {
+    if (warp == 0) {
+      // ------------------------------ TMA producer ------------------------------
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t tx = (uint32_t)p.co_nslabs * p.a_slab_bytes +
+                            (uint32_t)p.ci_nsub * (uint32_t)(kHaloW * kBh) * p.b_row_bytes;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          const int tw = kb % p.tiles_w;
+          const int th = (kb / p.tiles_w) % p.tiles_h;
+          const int n = kb / (p.tiles_w * p.tiles_h);
+          const int w0 = tw * kBw, h0 = th * kBh;
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + (size_t)stage * kStageBytes;
+          uint8_t* sb = sa + kARegion;
+          mbar_expect_tx(&full_bar[stage], tx);
+          for (int s = 0; s < p.co_nslabs; ++s)
+            tma_load_4d(&tmap_g, &full_bar[stage], sa + (size_t)s * p.a_slab_bytes, co0 + s * p.co_slab, w0, h0, n);
+          for (int s = 0; s < p.ci_nsub; ++s)
+            tma_load_4d(&tmap_x, &full_bar[stage], sb + (size_t)s * kBSub, ci0 + s * p.ci_sub, w0 - 1, h0 + tg - 1, n);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ------------------------------ MMA issuer (whole warp converged, one elected lane issues) ----------------
+      const uint32_t idesc = umma_idesc_bf16(128, p.ci_slab, 1, 1);
+      const uint64_t a_desc0 = umma_desc(smem_u32(smem), p.a_slab_bytes, 8u * p.a_row_bytes, p.a_layout);
+      const uint64_t b_desc0 = umma_desc(smem_u32(smem) + kARegion, kBSub, 8u * p.b_row_bytes, p.b_layout);
+      const uint32_t a_kstep = (16u * p.a_row_bytes) >> 4;          // 16 pixels (one image row of the tile) per K step
+      const uint32_t b_kstep = ((uint32_t)kHaloW * p.b_row_bytes) >> 4;   // ... which is 18 halo pixels further in X
+      const uint32_t b_tap = p.b_row_bytes >> 4;                     // one pixel to the right = next tap
+      const bool leader = elect_one();
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t accum = 0u;
+      for (int i = 0; i < my_kblocks; ++i) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (leader) {
+          const uint64_t a_st = a_desc0 + (uint64_t)((uint32_t)stage * (kStageBytes >> 4));
+          const uint64_t b_st = b_desc0 + (uint64_t)((uint32_t)stage * (kStageBytes >> 4));
+#pragma unroll
+          for (int ks = 0; ks < kBh; ++ks) {
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              tc_mma_bf16(tmem_base + kx * kTapStride, a_st + (uint64_t)(ks * a_kstep),
+                          b_st + (uint64_t)(ks * b_kstep + kx * b_tap), idesc, ks == 0 ? accum : 1u);
+            }
+          }
+          tc_commit(&empty_bar[stage]);
+          if (i == my_kblocks - 1) tc_commit(done_bar);
+        }
+        accum = 1u;
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    } else {
+      // ------------------------------ epilogue: TMEM -> vector reductions into dWp ------------------------------
+      const int q = warp & 3;
+      const int row = q * 32 + lane;
+      const int co = co0 + row;
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+      const bool live = row < p.co_slab * p.co_nslabs && co < p.Cout;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int tap = tg * 3 + kx;
+        float* drow = p.dw + ((size_t)tap * p.Cout + co) * p.Cin + ci0;
+        for (int c = 0; c < p.ci_slab; c += 16) {
+          uint32_t v[16];
+          tmem_ld_x16(taddr + kx * kTapStride + c, v);
+          tmem_ld_wait();
+          if (live) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              red_add_v4(drow + c + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                         __uint_as_float(v[j + 3]));
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace
+
+bool conv_wgrad_halo_supported(int N, int H, int W, int Cin, int Cout) {
+  const bool cin_ok = Cin < 64 ? (Cin == 16 || Cin == 32) : Cin % 64 == 0;
+  const bool cout_ok = Cout < 64 ? (Cout == 16 || Cout == 32) : Cout % 64 == 0;
+  return N > 0 && W >= 16 && H >= 8 && W % kBw == 0 && H % kBh == 0 && cin_ok && cout_ok;
+}
+
+// x: (N,H,W,Cin) bf16, g: (N,H,W,Cout) bf16, dw: [9][Cout][Cin] fp32 (overwritten, or += if accumulate).
+int launch_conv_wgrad_halo(const void* x, const void* g, float* dw, int N, int H, int W, int Cin, int Cout,
+                           int accumulate, cudaStream_t stream) {
+  BG_REQUIRE(conv_wgrad_halo_supported(N, H, W, Cin, Cout), "conv_wgrad_halo: unsupported shape N %d H %d W %d Cin %d Cout %d",
+             N, H, W, Cin, Cout);
+  WgradHaloParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+  p.tiles_w = W / kBw;
+  p.tiles_h = H / kBh;
+  p.total_kblocks = p.tiles_w * p.tiles_h * N;
+  p.co_slab = Cout < 64 ? Cout : 64;
+  p.co_nslabs = Cout >= 128 ? 2 : 1;
+  p.co_tiles = (Cout + 127) / 128;
+  p.ci_sub = Cin < 64 ? Cin : 64;
+  p.ci_nsub = Cin >= 128 ? 2 : 1;
+  p.ci_slab = p.ci_sub * p.ci_nsub;
+  p.ci_slabs = Cin / p.ci_slab;
+  p.a_row_bytes = p.co_slab * 2;
+  p.b_row_bytes = p.ci_sub * 2;
+  p.a_layout = p.a_row_bytes == 128 ? 2u : (p.a_row_bytes == 64 ? 4u : 6u);
+  p.b_layout = p.b_row_bytes == 128 ? 2u : (p.b_row_bytes == 64 ? 4u : 6u);
+  p.a_slab_bytes = 128u * p.a_row_bytes;
+  p.dw = dw;
+  const int units = p.co_tiles * p.ci_slabs * 3;
+  int splits = (2 * num_sms() + units - 1) / units;
+  if (splits < 1) splits = 1;
+  if (splits > p.total_kblocks) splits = p.total_kblocks;
+  p.kblocks_per_split = (p.total_kblocks + splits - 1) / splits;
+  splits = (p.total_kblocks + p.kblocks_per_split - 1) / p.kblocks_per_split;
+  p.splits = splits;
+
+  CUtensorMap tmg, tmx;
+  {
+    uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t str[3] = {(uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
+    uint32_t box[4] = {(uint32_t)p.co_slab, (uint32_t)kBw, (uint32_t)kBh, 1u};
+    if (make_tmap_bf16(&tmg, g, 4, dims, str, box, (int)p.a_row_bytes) != 0) return 1;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+    uint32_t box[4] = {(uint32_t)p.ci_sub, (uint32_t)kHaloW, (uint32_t)kBh, 1u};
+    if (make_tmap_bf16(&tmx, x, 4, dims, str, box, (int)p.b_row_bytes) != 0) return 1;
+  }
+
+  if (!accumulate) BG_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)9 * Cout * Cin * sizeof(float), stream));
+  const size_t smem_bytes = (size_t)kStages * kStageBytes + 256 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    BG_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  conv_wgrad_halo_kernel<<<units * splits, kThreads, smem_bytes, stream>>>(tmg, tmx, p);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace bg

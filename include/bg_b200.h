@@ -61,6 +61,10 @@ int bg_conv_fprop_tapwise(const void* x, const void* wpack, void* out, int N, in
  * accumulate=1 is the second half of the R1 "doubled-K" weight gradient wgrad(x, ybar) + wgrad(v, ghat). */
 int bg_conv_wgrad(const void* x, const void* g, float* dw_packed, int N, int H, int W, int Cin, int Cout,
                   int accumulate, void* stream);
+/* bg_conv_wgrad picks the shifted-view kernel (conv_wgrad_halo.cu) at W >= 16 and the tap-wise one otherwise;
+ * this entry forces the tap-wise kernel (A/B tests, small maps). */
+int bg_conv_wgrad_tapwise(const void* x, const void* g, float* dw_packed, int N, int H, int W, int Cin, int Cout,
+                          int accumulate, void* stream);
 
 /* ---- LeakyReLU backward gate (gan.py:86,145,241...): out = g * (y > 0 ? 1 : slope); n elements -------- */
 int bg_act_gate(const void* g, const void* y, void* out, size_t n, float slope, void* stream);

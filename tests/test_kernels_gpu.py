@@ -113,14 +113,17 @@ def test_conv3x3_dgrad_via_fprop(shape):
 
 
 @pytest.mark.parametrize("shape", [s for s in CONV_SHAPES if s[4] != 48])
-def test_conv3x3_wgrad(shape):
+@pytest.mark.parametrize("entry", ["bg_conv_wgrad", "bg_conv_wgrad_tapwise"])
+def test_conv3x3_wgrad(shape, entry):
     """autograd convolution_backward w.r.t. weight (and the weight half of the R1 double-backward)."""
     n, h, w_, ci, co = shape
     torch.manual_seed(0)
     x = nhwc(torch.randn(n, ci, h, w_, device=DEV))
     g = nhwc(torch.randn(n, co, h, w_, device=DEV))
     dwp = torch.empty(9, co, ci, dtype=torch.float32, device=DEV)
-    bgn.call("bg_conv_wgrad", x, g, dwp, n, h, w_, ci, co, 0)
+    bgn.call(entry, x, g, dwp, n, h, w_, ci, co, 0)
+    bgn.call(entry, x, g, dwp, n, h, w_, ci, co, 1)          # accumulate=1: the R1 doubled-K form adds into dWp
+    dwp *= 0.5
     torch.cuda.synchronize()
     ref = torch.nn.grad.conv2d_weight(nchw(x), (co, ci, 3, 3), nchw(g), padding=1)
     got = dwp.reshape(3, 3, co, ci).permute(2, 3, 0, 1)
