@@ -221,21 +221,28 @@ def run_b200(args):
     tr.iteration(dev_real[0].clone(), dev_z[0][0].clone(), dev_z[0][1].clone(), read_losses=False)
     rec = bgn.stop_timing()
     fam = {}
+    FPROP = ("bg_conv_fprop", "bg_conv_fprop_stats", "bg_conv_pool_fprop")   # one kernel family (conv_halo / conv_fprop)
+    dom = [0, 0.0, 0.0]
     for name, a, t in rec:
         f = fam.setdefault(name, [0, 0.0, 0.0])
         f[0] += 1
         f[1] += t
-        if name in ("bg_conv_fprop", "bg_conv_wgrad"):
-            f[2] += conv_flops(a)
+        if name in FPROP or name == "bg_conv_wgrad":
+            fl = conv_flops(a if name != "bg_conv_pool_fprop" else a[:5] + (3, 0, 0.0))
+            f[2] += fl
+            if name in FPROP:
+                dom[0] += 1
+                dom[1] += t
+                dom[2] += fl
     tot_ms = sum(v[1] for v in fam.values())
-    dom = fam.get("bg_conv_fprop", [0, 1e-9, 0.0])
+    dom[1] = max(dom[1], 1e-9)
     achieved = dom[2] / (dom[1] / 1e3) / 1e12 if dom[0] else 0.0
     shares = {k: round(v[1] / tot_ms, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1][1])[:8]}
-    roofline = {"kernel": "conv_fprop_kernel (tcgen05 implicit GEMM: fprop, dgrad, R1 tangent pass)", "bound": "tensor",
+    roofline = {"kernel": "conv_halo_kernel / conv_fprop_kernel (tcgen05 implicit GEMM: fprop, dgrad, R1 tangent pass, fused pool / IN-stats / bias-grad epilogues)", "bound": "tensor",
                 "achieved": round(achieved, 1), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                 "frac": round(achieved / peaks["tf_sustained"], 4), "traffic": None,
                 "peak_source": peaks["src"] + ", sustained bf16 (kernel timed inside a long step)",
-                "launches_per_step": dom[0], "share_of_step": shares.get("bg_conv_fprop"),
+                "launches_per_step": dom[0], "share_of_step": round(dom[1] / tot_ms, 4),
                 "wgrad_tflops": round(fam["bg_conv_wgrad"][2] / (fam["bg_conv_wgrad"][1] / 1e3) / 1e12, 1)
                 if "bg_conv_wgrad" in fam else None,
                 "step_share_by_call": shares,
@@ -265,7 +272,7 @@ def run_b200(args):
             "cpu_baseline": cpu,
             "grad_allreduce_bytes_per_step": tr.sync.bytes_reduced // max(1, args.steps * 2 + args.warmup + 2) if world > 1 else 0,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
 
@@ -315,10 +322,29 @@ def run_reference(args):
                        "batch_per_gpu": batch},
             "cpu_baseline": cpu,
             "e2e": {"value": cpu["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
+
+
+def _protect_stdout():
+    """Libraries (NCCL's version banner, torchrun notices) write to fd 1; the contract is ONE JSON line on
+    stdout.  Point fd 1 at stderr for the whole run and keep the real stdout for the final line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    _protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

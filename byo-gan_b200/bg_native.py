@@ -23,6 +23,7 @@ SIGNATURES = {
     "bg_pack_weight": [_P, _P, _P, _I, _I, _I, _I, _F, _P],
     "bg_unpack_wgrad": [_P, _P, _I, _I, _I, _I, _F, _I, _P],
     "bg_conv_fprop": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _F, _P],
+    "bg_conv_fprop_stats": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _F, _P, _I, _P],
     "bg_conv_pool_fprop": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _F, _P],
     "bg_conv_fprop_tapwise": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _F, _P],
     "bg_conv_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
@@ -30,7 +31,7 @@ SIGNATURES = {
     "bg_act_gate": [_P, _P, _P, _Z, _F, _P],
     "bg_axpby": [_P, _P, _P, _Z, _F, _F, _P],
     "bg_pool_act_fwd": [_P, _P, _P, _I, _I, _I, _I, _F, _I, _P],
-    "bg_pool_act_bwd": [_P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "bg_pool_act_bwd": [_P, _P, _P, _I, _I, _I, _I, _F, _P, _P],
     "bg_upsample2x_fwd": [_P, _P, _I, _I, _I, _I, _P],
     "bg_upsample2x_bwd": [_P, _P, _I, _I, _I, _I, _P],
     "bg_channel_wsum": [_P, _P, _P, _Z, _I, _I, _Z, _Z, _I, _P],
@@ -39,7 +40,7 @@ SIGNATURES = {
     "bg_in_stats": [_P, _P, _I, _I, _I, _P],
     "bg_adain_apply": [_P, _P, _P, _P, _I, _I, _I, _F, _P],
     "bg_adain_bwd_reduce": [_P, _P, _P, _P, _I, _I, _I, _F, _P],
-    "bg_adain_bwd_apply": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _I, _P],
+    "bg_adain_bwd_apply": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _I, _P, _P, _P],
     "bg_linear_fwd": [_P, _P, _P, _P, _I, _I, _I, _F, _I, _F, _P],
     "bg_linear_bwd_weight": [_P, _P, _P, _P, _I, _I, _I, _F, _I, _P],
     "bg_transpose_f32": [_P, _P, _I, _I, _P],

@@ -6,7 +6,7 @@ namespace bg {
 int launch_conv_fprop(const void*, const void*, void*, int, int, int, int, int, int, const float*, const float*,
                       const float*, const void*, int, float, cudaStream_t);
 int launch_conv_halo(const void*, const void*, void*, int, int, int, int, int, const float*, const float*, const float*,
-                     const void*, int, int, float, cudaStream_t);
+                     const void*, int, int, float, float*, int, cudaStream_t);
 bool conv_halo_supported(int, int, int, int, int, int);
 int launch_conv_wgrad(const void*, const void*, float*, int, int, int, int, int, int, cudaStream_t);
 int launch_conv_wgrad_halo(const void*, const void*, float*, int, int, int, int, int, int, cudaStream_t);
@@ -16,7 +16,7 @@ int launch_unpack_wgrad(const float*, float*, int, int, int, int, float, int, cu
 int launch_act_gate(const void*, const void*, void*, size_t, float, cudaStream_t);
 int launch_axpby(const void*, const void*, void*, size_t, float, float, cudaStream_t);
 int launch_pool_act_fwd(const void*, const void*, void*, int, int, int, int, float, int, cudaStream_t);
-int launch_pool_act_bwd(const void*, const void*, void*, int, int, int, int, float, cudaStream_t);
+int launch_pool_act_bwd(const void*, const void*, void*, int, int, int, int, float, float*, cudaStream_t);
 int launch_upsample2x_fwd(const void*, void*, int, int, int, int, cudaStream_t);
 int launch_upsample2x_bwd(const void*, void*, int, int, int, int, cudaStream_t);
 int launch_channel_wsum(const void*, const float*, float*, size_t, int, int, size_t, size_t, int, cudaStream_t);
@@ -47,7 +47,7 @@ int launch_in_stats(const void*, float*, int, int, int, cudaStream_t);
 int launch_adain_apply(const void*, const float*, const float*, void*, int, int, int, float, cudaStream_t);
 int launch_adain_bwd_reduce(const void*, const void*, const float*, float*, int, int, int, float, cudaStream_t);
 int launch_adain_bwd_apply(const void*, const void*, const float*, const float*, const float*, void*, int, int, int,
-                           float, float, int, cudaStream_t);
+                           float, float, int, const float*, float*, cudaStream_t);
 }  // namespace bg
 
 #define S(stream) reinterpret_cast<cudaStream_t>(stream)
@@ -67,9 +67,26 @@ int bg_conv_fprop(const void* x, const void* wpack, void* out, int N, int H, int
                   float slope, void* stream) {
   if (bg::conv_halo_supported(N, H, W, Cin, Cout, ksize))
     return bg::launch_conv_halo(x, wpack, out, N, H, W, Cin, Cout, bias, noise, noise_w, gate_src, act, 0, slope,
-                                S(stream));
+                                nullptr, 0, S(stream));
   return bg::launch_conv_fprop(x, wpack, out, N, H, W, Cin, Cout, ksize, bias, noise, noise_w, gate_src, act, slope,
                                S(stream));
+}
+int bg_conv_fprop_stats(const void* x, const void* wpack, void* out, int N, int H, int W, int Cin, int Cout, int ksize,
+                        const float* bias, const float* noise, const float* noise_w, const void* gate_src, int act,
+                        float slope, float* stats, int stats_mode, void* stream) {
+  if (stats == nullptr || (stats_mode != 1 && stats_mode != 2)) {
+    bg::set_error("conv_fprop_stats: stats must be non-NULL and stats_mode 1 or 2 (got %d)", stats_mode);
+    return 2;
+  }
+  if (bg::conv_halo_supported(N, H, W, Cin, Cout, ksize))
+    return bg::launch_conv_halo(x, wpack, out, N, H, W, Cin, Cout, bias, noise, noise_w, gate_src, act, 0, slope, stats,
+                                stats_mode, S(stream));
+  // small maps (< 16x16): tap-wise kernel, then the stand-alone reduction over the (tiny) output
+  int rc = bg::launch_conv_fprop(x, wpack, out, N, H, W, Cin, Cout, ksize, bias, noise, noise_w, gate_src, act, slope,
+                                 S(stream));
+  if (rc != 0) return rc;
+  if (stats_mode == 1) return bg::launch_in_stats(out, stats, N, H * W, Cout, S(stream));
+  return bg::launch_channel_wsum(out, nullptr, stats, (size_t)N * H * W, Cout, H * W, 0, 0, 0, S(stream));
 }
 int bg_conv_pool_fprop(const void* x, const void* wpack, void* out, int N, int H, int W, int Cin, int Cout,
                        const float* bias, const void* gate_src, int act, float slope, void* stream) {
@@ -78,7 +95,7 @@ int bg_conv_pool_fprop(const void* x, const void* wpack, void* out, int N, int H
     return 2;
   }
   return bg::launch_conv_halo(x, wpack, out, N, H, W, Cin, Cout, bias, nullptr, nullptr, gate_src, act, 1, slope,
-                              S(stream));
+                              nullptr, 0, S(stream));
 }
 int bg_conv_fprop_tapwise(const void* x, const void* wpack, void* out, int N, int H, int W, int Cin, int Cout, int ksize,
                           const float* bias, const float* noise, const float* noise_w, const void* gate_src, int act,
@@ -106,9 +123,9 @@ int bg_pool_act_fwd(const void* u, const void* gate_src, void* y, int N, int Ho,
                     void* stream) {
   return bg::launch_pool_act_fwd(u, gate_src, y, N, Ho, Wo, C, slope, mode, S(stream));
 }
-int bg_pool_act_bwd(const void* gy, const void* y, void* gu, int N, int Ho, int Wo, int C, float slope,
+int bg_pool_act_bwd(const void* gy, const void* y, void* gu, int N, int Ho, int Wo, int C, float slope, float* csum,
                     void* stream) {
-  return bg::launch_pool_act_bwd(gy, y, gu, N, Ho, Wo, C, slope, S(stream));
+  return bg::launch_pool_act_bwd(gy, y, gu, N, Ho, Wo, C, slope, csum, S(stream));
 }
 int bg_upsample2x_fwd(const void* x, void* y, int N, int H, int W, int C, void* stream) {
   return bg::launch_upsample2x_fwd(x, y, N, H, W, C, S(stream));
@@ -140,8 +157,9 @@ int bg_adain_bwd_reduce(const void* g, const void* a, const float* stats, float*
   return bg::launch_adain_bwd_reduce(g, a, stats, bsums, N, HW, C, eps, S(stream));
 }
 int bg_adain_bwd_apply(const void* g, const void* a, const float* stats, const float* style, const float* bsums,
-                       void* out, int N, int HW, int C, float eps, float slope, int gate, void* stream) {
-  return bg::launch_adain_bwd_apply(g, a, stats, style, bsums, out, N, HW, C, eps, slope, gate, S(stream));
+                       void* out, int N, int HW, int C, float eps, float slope, int gate, const float* noise,
+                       float* wsum, void* stream) {
+  return bg::launch_adain_bwd_apply(g, a, stats, style, bsums, out, N, HW, C, eps, slope, gate, noise, wsum, S(stream));
 }
 
 int bg_linear_fwd(const float* x, const float* W, const float* bias, float* y, int M, int N, int K, float coef, int act,

@@ -36,6 +36,28 @@ inline int grid_for(size_t work, int cap_mult = 8) {
   return (int)blocks;
 }
 
+
+// Block-level tail of a fused per-channel reduction in a grid-stride kernel whose thread <-> channel-group mapping
+// is fixed (blockDim and gridDim * blockDim multiples of cv): thread t holds `nk` partial sums for the 8 channels of
+// group t % cv.  red: [blockDim][nk][8] floats of shared memory.  out[k * C + c] += block total.
+template <int NK>
+__device__ __forceinline__ void block_channel_reduce(float (&acc)[NK][8], float* red, float* __restrict__ out, int C) {
+  const int cv = C / 8;
+#pragma unroll
+  for (int k = 0; k < NK; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[((size_t)threadIdx.x * NK + k) * 8 + j] = acc[k][j];
+  __syncthreads();
+  const int rows = blockDim.x / cv;
+  for (int idx = threadIdx.x; idx < NK * C; idx += blockDim.x) {
+    const int k = idx / C, c = idx % C;
+    const int grp = c >> 3, j = c & 7;
+    float sum = 0.f;
+    for (int r = 0; r < rows; ++r) sum += red[((size_t)(r * cv + grp) * NK + k) * 8 + j];
+    atomicAdd(out + (size_t)k * C + c, sum);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // weight pack / unpack (equalized-lr coefficient folded in, gan.py:14,27,32)
 // ---------------------------------------------------------------------------------------------
@@ -140,12 +162,18 @@ __global__ void pool_act_fwd_kernel(const __nv_bfloat16* __restrict__ u, const _
   }
 }
 
-// gu[2h+dy, 2w+dx] = 0.25 * gy[h, w] * gate(y[h, w])
+// gu[2h+dy, 2w+dx] = 0.25 * gy[h, w] * gate(y[h, w]);  csum (optional, zeroed by the launcher): csum[c] += sum over
+// the full-resolution map of gu[.,c] = sum_{n,h,w} gy * gate — the bias gradient of the conv that feeds the pool.
 __global__ void pool_act_bwd_kernel(const __nv_bfloat16* __restrict__ gy, const __nv_bfloat16* __restrict__ y,
-                                    __nv_bfloat16* __restrict__ gu, int N, int Ho, int Wo, int C, float slope) {
+                                    __nv_bfloat16* __restrict__ gu, int N, int Ho, int Wo, int C, float slope,
+                                    float* __restrict__ csum) {
+  extern __shared__ float red[];
   const int cv = C / 8;
   const size_t total = (size_t)N * Ho * Wo * cv;
   const int W = Wo * 2;
+  float acc[1][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % cv) * 8;
     const size_t po = i / cv;
@@ -155,12 +183,20 @@ __global__ void pool_act_bwd_kernel(const __nv_bfloat16* __restrict__ gy, const 
     F8 g = ld8(gy + po * C + c);
     const F8 yy = ld8(y + po * C + c);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) g.v[j] *= 0.25f * (yy.v[j] > 0.f ? 1.f : slope);
+    for (int j = 0; j < 8; ++j) {
+      g.v[j] *= 0.25f * (yy.v[j] > 0.f ? 1.f : slope);
+      acc[0][j] += g.v[j];
+    }
     const size_t base = (((size_t)n * Ho * 2 + ho * 2) * W + wo * 2) * C + c;
     st8(gu + base, g);
     st8(gu + base + C, g);
     st8(gu + base + (size_t)W * C, g);
     st8(gu + base + (size_t)W * C + C, g);
+  }
+  if (csum != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[0][j] *= 4.f;
+    block_channel_reduce<1>(acc, red, csum, C);
   }
 }
 
@@ -473,19 +509,27 @@ __global__ void adain_apply_kernel(const __nv_bfloat16* __restrict__ a, const fl
 }
 
 // gpre = gate(a) * gamma * rstd * (g - S1/HW - ahat * S2/HW)   (instance-norm backward + LeakyReLU gate)
+// wsum (optional, zeroed by the launcher): wsum[0][c] += sum gpre (conv bias gradient, gan.py:30),
+// wsum[1][c] += sum gpre * noise[n,hw] (InjectSecondaryNoise weight gradient, gan.py:52).
 __global__ void adain_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ a,
                                        const float* __restrict__ stats, const float* __restrict__ style,
                                        const float* __restrict__ bsums, __nv_bfloat16* __restrict__ out, int N,
-                                       int HW, int C, float eps, float slope, int gate) {
+                                       int HW, int C, float eps, float slope, int gate,
+                                       const float* __restrict__ noise, float* __restrict__ wsum) {
+  extern __shared__ float red[];
   const int cv = C / 8;
   const size_t total = (size_t)N * HW * cv;
   const float inv = 1.f / HW;
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % cv) * 8;
     const size_t p = i / cv;
     const int n = (int)(p / HW);
     const F8 av = ld8(a + p * C + c);
     const F8 gv = ld8(g + p * C + c);
+    const float nz = (wsum != nullptr && noise != nullptr) ? noise[p] : 0.f;
     F8 r;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -498,9 +542,12 @@ __global__ void adain_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, cons
       float v = ga * rs * (gv.v[j] - bsums[sc] * inv - ah * bsums[sc + 1] * inv);
       if (gate) v *= av.v[j] > 0.f ? 1.f : slope;
       r.v[j] = v;
+      acc[0][j] += v;
+      acc[1][j] = fmaf(v, nz, acc[1][j]);
     }
     st8(out + p * C + c, r);
   }
+  if (wsum != nullptr) block_channel_reduce<2>(acc, red, wsum, C);
 }
 
 }  // namespace
@@ -555,11 +602,17 @@ int launch_pool_act_fwd(const void* u, const void* gate_src, void* y, int N, int
 }
 
 int launch_pool_act_bwd(const void* gy, const void* y, void* gu, int N, int Ho, int Wo, int C, float slope,
-                        cudaStream_t s) {
+                        float* csum, cudaStream_t s) {
   BG_REQUIRE(C % 8 == 0, "pool_act_bwd: C must be a multiple of 8");
   const size_t total = (size_t)N * Ho * Wo * (C / 8);
-  pool_act_bwd_kernel<<<grid_for(total), kBlock, 0, s>>>((const __nv_bfloat16*)gy, (const __nv_bfloat16*)y,
-                                                        (__nv_bfloat16*)gu, N, Ho, Wo, C, slope);
+  size_t smem = 0;
+  if (csum != nullptr) {
+    BG_REQUIRE(kBlock % (C / 8) == 0, "pool_act_bwd: fused bias-gradient sum needs C/8 to divide %d (C %d)", kBlock, C);
+    BG_CHECK_CUDA(cudaMemsetAsync(csum, 0, (size_t)C * sizeof(float), s));
+    smem = (size_t)kBlock * 8 * sizeof(float);
+  }
+  pool_act_bwd_kernel<<<grid_for(total), kBlock, smem, s>>>((const __nv_bfloat16*)gy, (const __nv_bfloat16*)y,
+                                                           (__nv_bfloat16*)gu, N, Ho, Wo, C, slope, csum);
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -664,12 +717,19 @@ int launch_adain_apply(const void* a, const float* stats, const float* style, vo
 }
 
 int launch_adain_bwd_apply(const void* g, const void* a, const float* stats, const float* style, const float* bsums,
-                           void* out, int N, int HW, int C, float eps, float slope, int gate, cudaStream_t s) {
+                           void* out, int N, int HW, int C, float eps, float slope, int gate, const float* noise,
+                           float* wsum, cudaStream_t s) {
   BG_REQUIRE(C % 8 == 0, "adain_bwd_apply: C must be a multiple of 8");
   const size_t total = (size_t)N * HW * (C / 8);
-  adain_bwd_apply_kernel<<<grid_for(total), kBlock, 0, s>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)a, stats,
-                                                           style, bsums, (__nv_bfloat16*)out, N, HW, C, eps, slope,
-                                                           gate);
+  size_t smem = 0;
+  if (wsum != nullptr) {
+    BG_REQUIRE(kBlock % (C / 8) == 0, "adain_bwd_apply: fused sums need C/8 to divide %d (C %d)", kBlock, C);
+    BG_CHECK_CUDA(cudaMemsetAsync(wsum, 0, (size_t)2 * C * sizeof(float), s));
+    smem = (size_t)kBlock * 16 * sizeof(float);
+  }
+  adain_bwd_apply_kernel<<<grid_for(total), kBlock, smem, s>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)a, stats,
+                                                              style, bsums, (__nv_bfloat16*)out, N, HW, C, eps, slope,
+                                                              gate, noise, wsum);
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

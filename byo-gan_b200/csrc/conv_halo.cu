@@ -63,6 +63,13 @@ struct HaloParams {
   int debug;      // bisecting aid (BG_HALO_DEBUG): 1 no global stores, 2 no MMAs, 4 no halo copies, 8 no epilogue math
   int pool;       // 1: 2x2 average pool before the activation; out / gate_src are (N, H/2, W/2, Cout)
   float slope;
+  // fused per-channel reductions of the (bf16-rounded) output, accumulated with fp32 atomics into a zeroed buffer:
+  //   stats_mode 1: stats[n][c][0] += sum_hw out, stats[n][c][1] += sum_hw out^2   (instance-norm statistics, gan.py:59)
+  //   stats_mode 2: stats[c] += sum_{n,hw} out                                      (bias gradient of the layer below)
+  float* stats;
+  int stats_mode;
+  int n_blocks;
+  int contig;     // tile order, see tile_range()
 };
 
 struct TileCoord {
@@ -79,6 +86,21 @@ __device__ __forceinline__ TileCoord decode_tile(const HaloParams& p, int tile) 
   t.n = pt >> p.th_shift;
   t.co0 = nb * p.block_n;
   return t;
+}
+
+// Tile order.  contig = 1: a CTA owns a CONTIGUOUS range of tiles, so consecutive tiles share the sample index and
+// the epilogue can keep per-sample reductions in registers across tiles.  contig = 0: tiles are dealt round-robin,
+// so that at any moment the 148 CTAs work on 148 neighbouring tiles (best L2 / DRAM-page locality).
+__device__ __forceinline__ void tile_range(const HaloParams& p, int& t0, int& t1, int& step) {
+  if (p.contig) {
+    t0 = (int)(((long long)p.num_tiles * (long long)blockIdx.x) / (long long)gridDim.x);
+    t1 = (int)(((long long)p.num_tiles * (long long)(blockIdx.x + 1)) / (long long)gridDim.x);
+    step = 1;
+  } else {
+    t0 = blockIdx.x;
+    t1 = p.num_tiles;
+    step = gridDim.x;
+  }
 }
 
 __device__ __forceinline__ float4 lds128f(const float* p) {
@@ -123,6 +145,8 @@ __device__ __forceinline__ void mma_issue_loop(const HaloParams& p, uint8_t* a_b
   const uint32_t a_stage_step = p.a_stage_bytes >> 4;
   const uint32_t b_tile_step = p.b_tile_bytes >> 4;
   const bool leader = elect_one();
+  int tile_lo, tile_hi, tile_step;
+  tile_range(p, tile_lo, tile_hi, tile_step);
   int bstage = 0;
   uint32_t bphase = 0;
   int astage = 0;
@@ -133,7 +157,7 @@ __device__ __forceinline__ void mma_issue_loop(const HaloParams& p, uint8_t* a_b
     mbar_wait(&b_full[0], 0);
     tc_fence_after();
   }
-  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+  for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
     mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
     tc_fence_after();
     const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
@@ -230,10 +254,12 @@ __device__ __forceinline__ void halo_producer_loop(const HaloParams& p, uint8_t*
     hyx[i] = live ? ((hy << 8) | hx) : -1;
     soff[i] = (uint32_t)c8 * kPlaneBytes + (uint32_t)px * 16u;
   }
+  int tile_lo, tile_hi, tile_step;
+  tile_range(p, tile_lo, tile_hi, tile_step);
   int stage = 0;
   uint32_t phase = 0;
   int pending_stage = -1;
-  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+  for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
     const TileCoord t = decode_tile(p, tile);
     const int hb = t.h0 - 1, wb = t.w0 - 1;
     // pointer to (n, h0-1, w0-1, 0); only dereferenced where in bounds
@@ -281,8 +307,60 @@ __device__ __forceinline__ void halo_producer_loop(const HaloParams& p, uint8_t*
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Fused reductions of the output tile (epilogue warps).  During the line-wise store phase lane l owns the 16-byte
+// channel chunk ch = l % cpr of rows l / cpr, l / cpr + 32 / cpr, ... and sums its 8 channels in registers; after the
+// round a butterfly over the lanes that share a chunk leaves the warp totals in lanes 0..cpr-1, which add them to
+// the warp's PRIVATE shared-memory slice [Cout][2] (plain load/add/store, no atomics).  The slices are combined and
+// sent to global memory (red.global.add.f32) only when the CTA's tile sequence moves to another sample, or ends:
+// a per-tile flush costs more than the convolution itself on the high-resolution layers.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stats_round(float* slice, float (&sa)[8], float (&sq)[8], int cpr_shift, int lane,
+                                            int cbase) {
+  const int cpr = 1 << cpr_shift;
+  for (int o = 16; o >= cpr; o >>= 1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sa[j] += __shfl_xor_sync(0xffffffffu, sa[j], o);
+      sq[j] += __shfl_xor_sync(0xffffffffu, sq[j], o);
+    }
+  }
+  if (lane < cpr) {
+    float4* d = reinterpret_cast<float4*>(slice + (size_t)(cbase + lane * 8) * 2);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float4 v = d[j];
+      v.x += sa[2 * j];
+      v.y += sq[2 * j];
+      v.z += sa[2 * j + 1];
+      v.w += sq[2 * j + 1];
+      d[j] = v;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sa[j] = sq[j] = 0.f;
+}
+
+// All 8 epilogue warps call this at the same point of their (identical) tile sequence.
+__device__ __forceinline__ void stats_flush(const HaloParams& p, float* slices, int et, int n) {
+  asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+  const int len = p.Cout * 2;
+  for (int i = et; i < len; i += 32 * kEpiWarps) {
+    float v = 0.f;
+#pragma unroll
+    for (int e = 0; e < kEpiWarps; ++e) {
+      v += slices[e * len + i];
+      slices[e * len + i] = 0.f;
+    }
+    if (p.stats_mode == 1) atomicAdd(p.stats + (size_t)n * len + i, v);
+    else if ((i & 1) == 0) atomicAdd(p.stats + (i >> 1), v);
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------------------
+template <bool kStats>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -305,6 +383,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const HaloParams p)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);
   float* nw_s = bias_s + 512;
+  float* stat_s = nw_s + 512;             // [kEpiWarps][Cout][2], only carved when stats_mode != 0
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform role index
   const int lane = threadIdx.x & 31;
@@ -334,11 +413,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const HaloParams p)
       bias_s[c] = p.bias ? p.bias[c] : 0.f;
       nw_s[c] = p.noise_w ? p.noise_w[c] : 0.f;
     }
+    if (kStats)
+      for (int i = threadIdx.x - 64; i < kEpiWarps * p.Cout * 2; i += 32 * kEpiWarps) stat_s[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  int tile_lo, tile_hi, tile_step;
+  tile_range(p, tile_lo, tile_hi, tile_step);
 
   if (warp == 0) {
     // ------------------------------ weight TMA producer ------------------------------
@@ -352,7 +435,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const HaloParams p)
       } else {
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
           const TileCoord t = decode_tile(p, tile);
           for (int kcx = 0; kcx < p.k_chunks; ++kcx) {
             for (int tap = 0; tap < 9; ++tap) {
@@ -391,8 +474,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const HaloParams p)
     const uint32_t my_swz = (uint32_t)(lane >> (3 - cpr_shift)) & ((1u << cpr_shift) - 1u);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    constexpr bool st_on = kStats;
+    // one transpose round per tile and a fixed channel range: the lane partials stay in registers across tiles
+    const bool st_regs = st_on && p.n_blocks == 1 && p.block_n <= round_cols;
+    float* st_slice = stat_s + (size_t)(warp - 2) * p.Cout * 2;
+    float sa[8], sq[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sa[j] = sq[j] = 0.f;
+    int st_n = -1;
+    for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
       const TileCoord t = decode_tile(p, tile);
+      if (st_on && p.stats_mode == 1 && st_n >= 0 && st_n != t.n) {
+        if (st_regs) stats_round(st_slice, sa, sq, cpr_shift, lane, 0);
+        stats_flush(p, stat_s, threadIdx.x - 64, st_n);
+      }
+      st_n = t.n;
       const int h = t.h0 + g, w = t.w0 + half * 8 + r;
       const size_t pix = ((size_t)t.n * p.H + h) * p.W + w;
       const float nz = p.noise != nullptr ? p.noise[pix] : 0.f;
@@ -505,8 +601,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const HaloParams p)
               const uint4 ov = lds128(stg + (uint32_t)row * rb + (((uint32_t)ch ^ swz) << 4));
               const size_t op = pix_q0 + (size_t)(row >> 3) * p.W + (row & 7);
               *reinterpret_cast<uint4*>(p.out + op * p.Cout + t.co0 + c0 + ch * 8) = ov;
+              if (st_on) {
+                const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f2 = unpack_bf16x2(ow[j]);
+                  sa[2 * j] += f2.x;
+                  sa[2 * j + 1] += f2.y;
+                  sq[2 * j] = fmaf(f2.x, f2.x, sq[2 * j]);
+                  sq[2 * j + 1] = fmaf(f2.y, f2.y, sq[2 * j + 1]);
+                }
+              }
             }
           }
+          if (st_on && !st_regs) stats_round(st_slice, sa, sq, cpr_shift, lane, t.co0 + c0);
           __syncwarp();
         }
       }
@@ -515,6 +623,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const HaloParams p)
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
+    }
+    if (st_on && st_n >= 0) {
+      if (st_regs) stats_round(st_slice, sa, sq, cpr_shift, lane, 0);
+      stats_flush(p, stat_s, threadIdx.x - 64, st_n);
     }
   } else {
     // ------------------------------ halo producers (cp.async, zero-fill padding) ------------------------------
@@ -561,7 +673,7 @@ bool conv_halo_supported(int N, int H, int W, int Cin, int Cout, int ksize) {
 // Host launcher; same arguments as launch_conv_fprop (ksize must be 3) plus the fused-pool switch.
 int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, int W, int Cin, int Cout,
                      const float* bias, const float* noise, const float* noise_w, const void* gate_src, int act,
-                     int pool, float slope, cudaStream_t stream) {
+                     int pool, float slope, float* stats, int stats_mode, cudaStream_t stream) {
   BG_REQUIRE(conv_halo_supported(N, H, W, Cin, Cout, 3), "conv_halo: unsupported shape N %d H %d W %d Cin %d Cout %d", N,
              H, W, Cin, Cout);
   HaloParams p;
@@ -584,7 +696,8 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
   p.a_stage_bytes = (uint32_t)(p.kc / 8) * kPlaneBytes;
   p.epi_row_bytes = (uint32_t)(bn_ch >= 64 ? 64 : bn_ch) * 2u;
   const uint32_t epi_bytes = (uint32_t)kEpiWarps * 32u * p.epi_row_bytes + 128u;
-  const uint32_t aux_bytes = 8 * (2 * kMaxBStages + 2 * kMaxAStages + 4) + 16 + 2 * 512 * 4 + 64;
+  const uint32_t stat_bytes = (stats != nullptr) ? (uint32_t)kEpiWarps * (uint32_t)Cout * 2u * 4u : 0u;
+  const uint32_t aux_bytes = 8 * (2 * kMaxBStages + 2 * kMaxAStages + 4) + 16 + 2 * 512 * 4 + 64 + stat_bytes;
   const uint32_t total = 227u * 1024u - 1024u - aux_bytes - epi_bytes;
   const uint32_t resident_bytes = (uint32_t)p.k_chunks * 9u * p.b_tile_bytes;
   // prefer resident weights (3 halo stages if they fit, else 2); otherwise stream the weights past 3 halo stages
@@ -612,11 +725,20 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
   p.gate_src = reinterpret_cast<const __nv_bfloat16*>(gate_src);
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.act = act; p.pool = pool; p.slope = slope;
+  p.n_blocks = n_blocks;
+  p.stats = stats;
+  p.stats_mode = stats != nullptr ? stats_mode : 0;
+  p.contig = p.stats_mode != 0 ? 1 : 0;
+  BG_REQUIRE(p.stats_mode == 0 || ((stats_mode == 1 || stats_mode == 2) && !pool),
+             "conv_halo: stats_mode must be 1 or 2 and cannot be combined with the fused pool");
+  if (p.stats_mode)
+    BG_CHECK_CUDA(cudaMemsetAsync(stats, 0, (stats_mode == 1 ? (size_t)N * Cout * 2 : (size_t)Cout) * sizeof(float), stream));
   {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("BG_HALO_DEBUG"); dbg = e ? atoi(e) : 0; }
     p.debug = dbg;
   }
+  if (p.debug & 16) p.contig ^= 1;       // A/B the tile order
 
   CUtensorMap tmw;
   {
@@ -630,11 +752,13 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
   BG_REQUIRE(smem_bytes <= 227 * 1024, "conv_halo: shared memory budget exceeded (%zu)", smem_bytes);
   static bool attr_set = false;
   if (!attr_set) {
-    BG_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BG_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BG_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  conv_halo_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmw, p);
+  if (p.stats_mode) conv_halo_kernel<true><<<grid, kThreads, smem_bytes, stream>>>(tmw, p);
+  else conv_halo_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(tmw, p);
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

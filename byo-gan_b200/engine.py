@@ -125,9 +125,16 @@ def gate_f32(g, y):
     return out
 
 
-def conv3x3(x, wpack, cin, cout, bias=None, noise=None, noise_w=None, gate_src=None, act=False):
+def conv3x3(x, wpack, cin, cout, bias=None, noise=None, noise_w=None, gate_src=None, act=False, stats=0):
+    """3x3 conv with the fused epilogue.  stats=1 also returns the instance-norm sums (N,Cout,2) of the output,
+    stats=2 its per-channel total (Cout) — both reduced inside the conv epilogue."""
     n, h, w_, _ = x.shape
     out = _bf16(n, h, w_, cout, device=x.device)
+    if stats:
+        st = _f32(n, cout, 2, device=x.device) if stats == 1 else _f32(cout, device=x.device)
+        call("bg_conv_fprop_stats", x, wpack, out, n, h, w_, cin, cout, 3, bias, noise, noise_w, gate_src,
+             1 if act else 0, SLOPE, st, stats)
+        return out, st
     call("bg_conv_fprop", x, wpack, out, n, h, w_, cin, cout, 3, bias, noise, noise_w, gate_src, 1 if act else 0, SLOPE)
     return out
 
@@ -244,9 +251,11 @@ def generator_forward(gen, packs: PackCache, z, noise, steps, alpha, z2=None, cr
                 else:
                     xin = feat
                 wf, _ = packs.conv(sc.conv.weight)
-                a = conv3x3(xin, wf, ci, cout, bias=sc.conv.bias.detach(), noise=nz, noise_w=nw, act=True)
-            stats = _f32(B, cout, 2, device=dev)
-            call("bg_in_stats", a, stats, B, R * R, cout)
+                a, stats = conv3x3(xin, wf, ci, cout, bias=sc.conv.bias.detach(), noise=nz, noise_w=nw, act=True,
+                                   stats=1)                                      # IN sums ride in the conv epilogue
+            if xin is None:
+                stats = _f32(B, cout, 2, device=dev)
+                call("bg_in_stats", a, stats, B, R * R, cout)
             xo = torch.empty_like(a)
             call("bg_adain_apply", a, stats, style, xo, B, R * R, cout, IN_EPS)   # gan.py:69
             layers.append(dict(k=k, j=j, sc=sc, xin=xin, a=a, stats=stats, style=style, R=R, C=cout, which=which,
@@ -321,7 +330,13 @@ def generator_backward(gen, packs: PackCache, tape, g_img, need: Dict[int, bool]
         bs = _f32(B, c, 2, device=dev)
         call("bg_adain_bwd_reduce", gx, a, stats, bs, B, r * r, c, IN_EPS)
         gpre = torch.empty_like(a)
-        call("bg_adain_bwd_apply", gx, a, stats, style, bs, gpre, B, r * r, c, IN_EPS, SLOPE, 1)
+        is_const = L["xin"] is None
+        need_b = (not is_const) and want(sc.conv.bias)
+        need_nw = want(sc.inject_noise.weights)
+        # bias / noise-weight gradients (gan.py:30,52) are reduced while gpre is written
+        ws = _f32(2, c, device=dev) if (need_b or need_nw) else None
+        call("bg_adain_bwd_apply", gx, a, stats, style, bs, gpre, B, r * r, c, IN_EPS, SLOPE, 1,
+             L["noise"] if ws is not None else None, ws)
         # style FC (gan.py:60,66): dL/dgamma = sum g*ahat, dL/dbeta = sum g
         dstyle = torch.cat([bs[..., 1], bs[..., 0]], dim=1).contiguous()
         st = sc.adain.style
@@ -337,15 +352,10 @@ def generator_backward(gen, packs: PackCache, tape, g_img, need: Dict[int, bool]
             g_w[L["which"]] = gw_l
         else:
             call("bg_axpby_f32", g_w[L["which"]], gw_l, g_w[L["which"]], gw_l.numel(), 1.0, 1.0)
-        # bias / noise-weight gradients (gan.py:52): one pass over gpre
-        is_const = L["xin"] is None
-        need_b = (not is_const) and want(sc.conv.bias)
-        if need_b or want(sc.inject_noise.weights):
-            ws = channel_wsum(gpre, L["noise"], 1, r * r, r * r, 0)
-            if need_b:
-                grads[id(sc.conv.bias)] = ws[0].clone()
-            if want(sc.inject_noise.weights):
-                grads[id(sc.inject_noise.weights)] = ws[1].reshape(1, c, 1, 1).clone()
+        if need_b:
+            grads[id(sc.conv.bias)] = ws[0]
+        if need_nw:
+            grads[id(sc.inject_noise.weights)] = ws[1].reshape(1, c, 1, 1)
         if is_const:
             if want(sc.conv):
                 dc = _f32(1, c, 4, 4, device=dev)
@@ -615,22 +625,25 @@ def critic_backward(critic, packs: PackCache, tape, g_pred, need: Dict[int, bool
         else:
             gy2 = gx
         gu = _bf16(B, r, r, cout, device=dev)
-        call("bg_pool_act_bwd", gy2, e["y2"], gu, B, r // 2, r // 2, cout, SLOPE)              # pool + LReLU adjoint
+        db2 = _f32(cout, device=dev) if want(c2b.bias) else None                               # bias grad of conv_2
+        call("bg_pool_act_bwd", gy2, e["y2"], gu, B, r // 2, r // 2, cout, SLOPE, db2)         # pool + LReLU adjoint
         if kk is not None:
             kk["u"] = gu
         if want(c2b.weight):
             grads[id(c2b.weight)] = conv_wgrad(e["y1"], gu, c2b.weight, extra=(t["y1"], h["u"]) if t else None)
-        if want(c2b.bias):
-            grads[id(c2b.bias)] = channel_wsum(gu, None, 0, r * r, 0, 0)[0].clone()
+        if db2 is not None:
+            grads[id(c2b.bias)] = db2
         _, wd2 = packs.conv(c2b.weight)
-        g1 = conv3x3(gu, wd2, cout, cout, gate_src=e["y1"])                                    # dgrad + LReLU gate
+        if want(c1b.bias):                                                                     # dgrad + LReLU gate,
+            g1, db1 = conv3x3(gu, wd2, cout, cout, gate_src=e["y1"], stats=2)                  # + bias grad of conv_1
+            grads[id(c1b.bias)] = db1
+        else:
+            g1 = conv3x3(gu, wd2, cout, cout, gate_src=e["y1"])
         del gu
         if kk is not None:
             kk["y1"] = g1
         if want(c1b.weight):
             grads[id(c1b.weight)] = conv_wgrad(e["x"], g1, c1b.weight, extra=(t["x"], h["y1"]) if t else None)
-        if want(c1b.bias):
-            grads[id(c1b.bias)] = channel_wsum(g1, None, 0, r * r, 0, 0)[0].clone()
         _, wd1 = packs.conv(c1b.weight)
         first = idx == 0
         if first:

@@ -45,6 +45,15 @@ int bg_unpack_wgrad(const float* dw_packed, float* dw, int Cout, int Cin, int Ci
 int bg_conv_fprop(const void* x, const void* wpack, void* out, int N, int H, int W, int Cin, int Cout, int ksize,
                   const float* bias, const float* noise, const float* noise_w, const void* gate_src, int act,
                   float slope, void* stream);
+/* bg_conv_fprop plus a per-channel reduction of the (bf16) output fused into the epilogue (no extra pass over
+ * the map).  The buffer is zeroed by the call.
+ *   stats_mode 1: stats fp32 (N,Cout,2) = [sum_hw out, sum_hw out^2] per sample — the nn.InstanceNorm2d statistics
+ *                 of AdaINBlock (gan.py:59,69) for the activation this conv produces;
+ *   stats_mode 2: stats fp32 (Cout)     = sum_{n,hw} out — when out is the gradient at a conv output (a dgrad pass),
+ *                 this is that conv's bias gradient (autograd convolution_backward, bias term). */
+int bg_conv_fprop_stats(const void* x, const void* wpack, void* out, int N, int H, int W, int Cin, int Cout, int ksize,
+                        const float* bias, const float* noise, const float* noise_w, const void* gate_src, int act,
+                        float slope, float* stats, int stats_mode, void* stream);
 /* conv3x3 -> AvgPool2d(2) -> [LeakyReLU | gate] fused in the epilogue (CriticBlock.conv_2, gan.py:258-262; with
  * act=0 and gate_src (pooled resolution) it is the R1 tangent pass through the same layers).  out: (N,H/2,W/2,Cout).
  * Needs H,W >= 16. */
@@ -76,7 +85,9 @@ int bg_axpby(const void* a, const void* b, void* out, size_t n, float ca, float 
  * bwd: gu = 0.25 * gate(y) * gy broadcast to the 2x2 window.  u,gu: (N,2Ho,2Wo,C); y,gy: (N,Ho,Wo,C). */
 int bg_pool_act_fwd(const void* u, const void* gate_src, void* y, int N, int Ho, int Wo, int C, float slope,
                     int mode, void* stream);
-int bg_pool_act_bwd(const void* gy, const void* y, void* gu, int N, int Ho, int Wo, int C, float slope,
+/* csum (optional fp32 (C), zeroed by the call) += sum_{n,h,w} gu[.,c]: the bias gradient of the conv feeding the pool
+ * (autograd convolution_backward, bias term), fused so the gradient map is not read again. */
+int bg_pool_act_bwd(const void* gy, const void* y, void* gu, int N, int Ho, int Wo, int C, float slope, float* csum,
                     void* stream);
 
 /* ---- nn.Upsample(scale_factor=2, bilinear) (gan.py:112,123) and its adjoint; x: (N,H,W,C) -------------- */
@@ -110,8 +121,11 @@ int bg_adain_apply(const void* a, const float* stats, const float* style, void* 
                    void* stream);
 int bg_adain_bwd_reduce(const void* g, const void* a, const float* stats, float* bsums, int N, int HW, int C,
                         float eps, void* stream);
+/* noise (fp32 (N,1,H,W)) / wsum (fp32 (2,C), zeroed by the call) optional: wsum[0] = sum out = conv bias gradient,
+ * wsum[1] = sum out * noise = InjectSecondaryNoise weight gradient (gan.py:52), reduced while out is written. */
 int bg_adain_bwd_apply(const void* g, const void* a, const float* stats, const float* style, const float* bsums,
-                       void* out, int N, int HW, int C, float eps, float slope, int gate, void* stream);
+                       void* out, int N, int HW, int C, float eps, float slope, int gate, const float* noise,
+                       float* wsum, void* stream);
 
 /* ---- EqualizedLinear (gan.py:16-17): mapping network (gan.py:130-148), AdaIN style FCs (gan.py:60,66), critic
  * head FCs and, on the NCHW-flattened 4x4 map, the critic's 4x4 valid conv (gan.py:245-250).  All fp32.

@@ -112,6 +112,40 @@ def test_conv3x3_dgrad_via_fprop(shape):
     assert err < 6e-3, f"dgrad {shape}: rel-L2 {err:.3e}"
 
 
+STATS_SHAPES = CONV_SHAPES + [(3, 64, 64, 64, 128), (5, 32, 32, 64, 64), (2, 64, 64, 32, 256)]
+
+
+@pytest.mark.parametrize("shape", STATS_SHAPES)
+@pytest.mark.parametrize("mode", [1, 2])
+def test_conv3x3_fprop_fused_stats(shape, mode):
+    """Epilogue-fused reductions: mode 1 = nn.InstanceNorm2d statistics of the produced activation (gan.py:59,69),
+    mode 2 = per-channel sum over batch and pixels (the bias gradient when the pass is a dgrad).  The map itself
+    must be bit-identical to the plain entry; the sums are compared with fp64 sums of that bf16 map."""
+    n, h, w_, ci, co = shape
+    torch.manual_seed(3)
+    x = nhwc(torch.randn(n, ci, h, w_, device=DEV))
+    w = torch.randn(co, ci, 3, 3, device=DEV)
+    wf, _ = pack(w, math.sqrt(2 / (ci * 9)))
+    bias = torch.randn(co, device=DEV) * 0.1
+    noise = torch.randn(n, 1, h, w_, device=DEV)
+    nw = torch.randn(co, device=DEV) * 0.1
+    ref = torch.empty(n, h, w_, co, dtype=torch.bfloat16, device=DEV)
+    bgn.call("bg_conv_fprop", x, wf, ref, n, h, w_, ci, co, 3, bias, noise, nw, None, 1, 0.2)
+    out = torch.empty_like(ref)
+    stats = torch.full((n, co, 2) if mode == 1 else (co,), 7.0, device=DEV)     # the call must zero it
+    bgn.call("bg_conv_fprop_stats", x, wf, out, n, h, w_, ci, co, 3, bias, noise, nw, None, 1, 0.2, stats, mode)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    o = out.double()
+    if mode == 1:
+        want = torch.stack([o.sum(dim=(1, 2)), (o * o).sum(dim=(1, 2))], dim=-1)
+    else:
+        want = o.sum(dim=(0, 1, 2))
+    err = (stats.double() - want).abs().max().item()
+    scale = want.abs().max().item() + 1.0
+    assert err < 2e-5 * scale * math.sqrt(h * w_), (err, scale)
+
+
 @pytest.mark.parametrize("shape", [s for s in CONV_SHAPES if s[4] != 48])
 @pytest.mark.parametrize("entry", ["bg_conv_wgrad", "bg_conv_wgrad_tapwise"])
 def test_conv3x3_wgrad(shape, entry):
@@ -166,6 +200,57 @@ def test_upsample_pool_adain_aux():
     bgn.call("bg_adain_apply", a, stats, style, xo, n, h * w_, c, 1e-8)
     ref = style[:, :c, None, None] * F.instance_norm(af, eps=1e-8) + style[:, c:, None, None]
     assert relerr(nchw(xo), ref) < 5e-3
+
+
+@pytest.mark.parametrize("dims", [(3, 16, 8, 8), (2, 64, 32, 32), (2, 512, 4, 4), (1, 128, 64, 64)])
+def test_pool_act_bwd_and_adain_bwd_with_fused_sums(dims):
+    """Adjoint of AvgPool2d(2)+LeakyReLU (gan.py:258-262) with the conv bias gradient reduced in the same pass, and the
+    instance-norm/AdaIN backward (gan.py:55-71, 94-98) with the conv-bias and noise-weight gradients (gan.py:30,52)."""
+    n, c, h, w_ = dims
+    torch.manual_seed(5)
+    # ---- pool + lrelu adjoint against autograd
+    u = nchw(nhwc(torch.randn(n, c, 2 * h, 2 * w_, device=DEV))).requires_grad_()
+    y = F.leaky_relu(F.avg_pool2d(u, 2), 0.2)
+    gy = nchw(nhwc(torch.randn(n, c, h, w_, device=DEV)))
+    y.backward(gy)
+    gu = torch.empty(n, 2 * h, 2 * w_, c, dtype=torch.bfloat16, device=DEV)
+    csum = torch.full((c,), 3.0, device=DEV)
+    bgn.call("bg_pool_act_bwd", nhwc(gy), nhwc(y.detach()), gu, n, h, w_, c, 0.2, csum)
+    gu2 = torch.empty_like(gu)
+    bgn.call("bg_pool_act_bwd", nhwc(gy), nhwc(y.detach()), gu2, n, h, w_, c, 0.2, None)
+    torch.cuda.synchronize()
+    assert torch.equal(gu, gu2)
+    assert relerr(nchw(gu), u.grad) < 6e-3
+    want = u.grad.sum((0, 2, 3))
+    assert (csum - want).abs().max().item() < 2e-3 * (want.abs().max().item() + 1.0) * math.sqrt(h * w_ * n)
+    # ---- AdaIN backward against autograd of: a -> lrelu -> instance_norm -> gamma * . + beta
+    pre = nchw(nhwc(torch.randn(n, c, h, w_, device=DEV) * 1.5 + 0.3)).requires_grad_()
+    a = F.leaky_relu(pre, 0.2)
+    a_q = nchw(nhwc(a.detach()))                       # the kernels see the bf16 activation
+    a_in = a_q.clone().requires_grad_()
+    style = torch.randn(n, 2 * c, device=DEV)
+    xo = style[:, :c, None, None] * F.instance_norm(a_in, eps=1e-8) + style[:, c:, None, None]
+    g = nchw(nhwc(torch.randn(n, c, h, w_, device=DEV)))
+    xo.backward(g)
+    gate = torch.where(a_q > 0, 1.0, 0.2)
+    gpre_ref = a_in.grad * gate
+    noise = torch.randn(n, 1, h, w_, device=DEV)
+    stats = torch.empty(n, c, 2, device=DEV)
+    bgn.call("bg_in_stats", nhwc(a_q), stats, n, h * w_, c)
+    bs = torch.empty(n, c, 2, device=DEV)
+    bgn.call("bg_adain_bwd_reduce", nhwc(g), nhwc(a_q), stats, bs, n, h * w_, c, 1e-8)
+    gpre = torch.empty(n, h, w_, c, dtype=torch.bfloat16, device=DEV)
+    ws = torch.full((2, c), -1.0, device=DEV)
+    bgn.call("bg_adain_bwd_apply", nhwc(g), nhwc(a_q), stats, style, bs, gpre, n, h * w_, c, 1e-8, 0.2, 1, noise, ws)
+    gpre2 = torch.empty_like(gpre)
+    bgn.call("bg_adain_bwd_apply", nhwc(g), nhwc(a_q), stats, style, bs, gpre2, n, h * w_, c, 1e-8, 0.2, 1, None, None)
+    torch.cuda.synchronize()
+    assert torch.equal(gpre, gpre2)
+    assert relerr(nchw(gpre), gpre_ref) < 1e-2
+    tol = 5e-3 * math.sqrt(h * w_ * n)
+    wb, wn = gpre_ref.sum((0, 2, 3)), (gpre_ref * noise).sum((0, 2, 3))
+    assert (ws[0] - wb).abs().max().item() < tol * (gpre_ref.abs().max().item())
+    assert (ws[1] - wn).abs().max().item() < tol * (gpre_ref.abs().max().item()) * 3
 
 
 @pytest.mark.parametrize("shape", [(2, 16, 16, 64, 64), (1, 64, 64, 32, 64), (3, 32, 32, 128, 128), (1, 32, 32, 256, 256),

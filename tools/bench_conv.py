@@ -35,7 +35,7 @@ def timeit(fn, reps=10):
 
 
 print(f"batch {B}")
-print(f"{'R':>4} {'Cin':>4} {'Cout':>4} | {'fprop ms':>9} {'TF/s':>7} {'GB/s':>7} | {'dgrad ms':>9} {'TF/s':>7} | {'wgrad ms':>9} {'TF/s':>7} | {'wg-tapw ms':>10} {'TF/s':>7}")
+print(f"{'R':>4} {'Cin':>4} {'Cout':>4} | {'fprop ms':>9} {'TF/s':>7} {'GB/s':>7} | {'dgrad ms':>9} {'TF/s':>7} | {'wgrad ms':>9} {'TF/s':>7} | {'fp+stats ms':>10} {'TF/s':>7}")
 for (R, ci, co) in LAYERS:
     if R > MAXR:
         continue
@@ -54,7 +54,8 @@ for (R, ci, co) in LAYERS:
     t_f = timeit(lambda: bgn.call("bg_conv_fprop", x, wf, out, n, R, R, ci, co, 3, bias, None, None, None, 1, 0.2))
     t_d = timeit(lambda: bgn.call("bg_conv_fprop", g, wd, gx, n, R, R, co, ci, 3, None, None, None, None, 0, 0.2))
     t_w = timeit(lambda: bgn.call("bg_conv_wgrad", x, g, dwp, n, R, R, ci, co, 0))
-    t_t = timeit(lambda: bgn.call("bg_conv_wgrad_tapwise", x, g, dwp, n, R, R, ci, co, 0))
+    stats = torch.empty(n, co, 2, device=DEV)
+    t_t = timeit(lambda: bgn.call("bg_conv_fprop_stats", x, wf, out, n, R, R, ci, co, 3, bias, None, None, None, 1, 0.2, stats, 1))
     byts = 2.0 * n * R * R * (ci + co)
     print(f"{R:>4} {ci:>4} {co:>4} | {t_f:9.3f} {flops / t_f / 1e9:7.1f} {byts / t_f / 1e6:7.0f} | {t_d:9.3f} {flops / t_d / 1e9:7.1f} | "
           f"{t_w:9.3f} {flops / t_w / 1e9:7.1f} | {t_t:10.3f} {flops / t_t / 1e9:7.1f}", flush=True)
