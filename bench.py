@@ -248,6 +248,11 @@ def run_b200(args):
                 "step_share_by_call": shares,
                 "step_model_flops_frac": round(value / world * gflop_img * 1e9 / (peaks["tf_sustained"] * 1e12), 4)}
 
+    sampling = None
+    if rank == 0 and world == 1 and not args.no_sampling:
+        del tr.critic
+        torch.cuda.empty_cache()
+        sampling = sampling_leg(device, gen=tr.gen)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_leg(args.workload, max_seconds=40.0, steps_cap=1)
@@ -270,11 +275,69 @@ def run_b200(args):
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "sampling_512": sampling,
             "grad_allreduce_bytes_per_step": tr.sync.bytes_reduced // max(1, args.steps * 2 + args.warmup + 2) if world > 1 else 0,
         }
         emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------------
+# sampling leg: generate_samples.py's hot call, Generator.forward(z, steps=8) under no_grad (BASELINE configs[4])
+# ------------------------------------------------------------------------------------------------------
+G_FWD_GFLOP_512 = 21.25      # per image, reference formulation
+
+
+def sampling_leg(device, batch=256, steps=8, iters=3, warmup=2, gen=None):
+    """512x512 sampling, batch 256, one GPU.  `value`: latents resident in HBM, images left in HBM.  `e2e`: latents
+    from pinned host memory and the finished images copied back to pinned host memory inside the timed region
+    (what generate_samples.py does before utils.save_image).  Per-layer noise is drawn on the device by the model
+    exactly like the reference (gan.py:189-197)."""
+    import gan
+
+    if gen is None:
+        torch.manual_seed(0)
+        gen = gan.Generator().to(device)
+        with torch.no_grad():
+            for n, p in gen.named_parameters():
+                if n.endswith("bias") or n.endswith("inject_noise.weights"):
+                    p.add_(0.05 * torch.randn_like(p))
+    gen.eval()
+    R = 4 * 2 ** (steps - 1)
+    g = torch.Generator(device="cpu").manual_seed(7)
+    host_z = [torch.randn(batch, 512, generator=g).clamp_(-0.75, 0.75).pin_memory() for _ in range(2)]
+    dev_z = [t.to(device) for t in host_z]
+    host_img = torch.empty(batch, 3, R, R).pin_memory()
+
+    def run(n, from_host):
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        with torch.no_grad():
+            for i in range(n):
+                if from_host:
+                    img = gen(host_z[i % 2].to(device, non_blocking=True), steps=steps, alpha=None)
+                    host_img.copy_(img, non_blocking=True)
+                else:
+                    img = gen(dev_z[i % 2], steps=steps, alpha=None)
+                del img
+        t1.record()
+        torch.cuda.synchronize()
+        return t0.elapsed_time(t1)
+
+    run(warmup, False)
+    ms = run(iters, False)
+    run(1, True)
+    ms_e2e = run(iters, True)
+    peaks = load_peaks()
+    v = batch * iters / (ms / 1e3)
+    return {"metric": "generate img/s at 512x512", "value": round(v, 1), "unit": "img/s", "batch": batch, "iters": iters,
+            "ms_per_batch": round(ms / iters, 2),
+            "e2e": {"value": round(batch * iters / (ms_e2e / 1e3), 1), "unit": "img/s",
+                    "h2d_bytes_per_step": batch * 512 * 4, "d2h_bytes_per_step": batch * 3 * R * R * 4},
+            "model_flops_frac": round(v * G_FWD_GFLOP_512 * 1e9 / (peaks["tf_sustained"] * 1e12), 4),
+            "config": f"Generator.forward(z, steps={steps}, alpha=None) under no_grad, batch {batch}, internal randn noise"}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -353,6 +416,7 @@ def main():
     ap.add_argument("--workload", default="train256", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (debugging only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sampling", action="store_true", help="skip the 512x512 sampling leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -24,6 +24,9 @@ SIGNATURES = {
     "bg_unpack_wgrad": [_P, _P, _I, _I, _I, _I, _F, _I, _P],
     "bg_conv_fprop": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _F, _P],
     "bg_conv_fprop_stats": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _F, _P, _I, _P],
+    "bg_style_modulate": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P],
+    "bg_conv_style_fprop": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _F, _P, _P],
+    "bg_to_rgb_adain": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _P],
     "bg_conv_pool_fprop": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _F, _P],
     "bg_conv_fprop_tapwise": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _F, _P],
     "bg_conv_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],

@@ -6,7 +6,7 @@ namespace bg {
 int launch_conv_fprop(const void*, const void*, void*, int, int, int, int, int, int, const float*, const float*,
                       const float*, const void*, int, float, cudaStream_t);
 int launch_conv_halo(const void*, const void*, void*, int, int, int, int, int, const float*, const float*, const float*,
-                     const void*, int, int, float, float*, int, cudaStream_t);
+                     const void*, int, int, float, float*, int, const float*, int, int, cudaStream_t);
 bool conv_halo_supported(int, int, int, int, int, int);
 int launch_conv_wgrad(const void*, const void*, float*, int, int, int, int, int, int, cudaStream_t);
 int launch_conv_wgrad_halo(const void*, const void*, float*, int, int, int, int, int, int, cudaStream_t);
@@ -48,6 +48,10 @@ int launch_adain_apply(const void*, const float*, const float*, void*, int, int,
 int launch_adain_bwd_reduce(const void*, const void*, const float*, float*, int, int, int, float, cudaStream_t);
 int launch_adain_bwd_apply(const void*, const void*, const float*, const float*, const float*, void*, int, int, int,
                            float, float, int, const float*, float*, cudaStream_t);
+int launch_style_modulate(const float*, const float*, const float*, const float*, void*, float*, int, int, int, int, float,
+                          float, cudaStream_t);
+int launch_to_rgb_adain(const void*, const float*, const float*, const float*, const float*, float*, int, int, int, float,
+                        float, cudaStream_t);
 }  // namespace bg
 
 #define S(stream) reinterpret_cast<cudaStream_t>(stream)
@@ -67,7 +71,7 @@ int bg_conv_fprop(const void* x, const void* wpack, void* out, int N, int H, int
                   float slope, void* stream) {
   if (bg::conv_halo_supported(N, H, W, Cin, Cout, ksize))
     return bg::launch_conv_halo(x, wpack, out, N, H, W, Cin, Cout, bias, noise, noise_w, gate_src, act, 0, slope,
-                                nullptr, 0, S(stream));
+                                nullptr, 0, nullptr, 0, 0, S(stream));
   return bg::launch_conv_fprop(x, wpack, out, N, H, W, Cin, Cout, ksize, bias, noise, noise_w, gate_src, act, slope,
                                S(stream));
 }
@@ -80,13 +84,35 @@ int bg_conv_fprop_stats(const void* x, const void* wpack, void* out, int N, int 
   }
   if (bg::conv_halo_supported(N, H, W, Cin, Cout, ksize))
     return bg::launch_conv_halo(x, wpack, out, N, H, W, Cin, Cout, bias, noise, noise_w, gate_src, act, 0, slope, stats,
-                                stats_mode, S(stream));
+                                stats_mode, nullptr, 0, 0, S(stream));
   // small maps (< 16x16): tap-wise kernel, then the stand-alone reduction over the (tiny) output
   int rc = bg::launch_conv_fprop(x, wpack, out, N, H, W, Cin, Cout, ksize, bias, noise, noise_w, gate_src, act, slope,
                                  S(stream));
   if (rc != 0) return rc;
   if (stats_mode == 1) return bg::launch_in_stats(out, stats, N, H * W, Cout, S(stream));
   return bg::launch_channel_wsum(out, nullptr, stats, (size_t)N * H * W, Cout, H * W, 0, 0, 0, S(stream));
+}
+int bg_conv_style_fprop(const void* x, const void* wmod, const float* btab, void* out, int N, int H, int W, int Cin,
+                        int Cout, int upsample, const float* noise, const float* noise_w, float slope, float* stats,
+                        void* stream) {
+  if (!bg::conv_halo_supported(N, H, W, Cin, Cout, 3)) {
+    bg::set_error("conv_style_fprop: needs a 3x3 layer at H,W >= 16 (got H %d W %d Cin %d Cout %d)", H, W, Cin, Cout);
+    return 2;
+  }
+  if (wmod == nullptr || btab == nullptr) {
+    bg::set_error("conv_style_fprop: wmod and btab (from bg_style_modulate) are required");
+    return 2;
+  }
+  return bg::launch_conv_halo(x, wmod, out, N, H, W, Cin, Cout, nullptr, noise, noise_w, nullptr, 1, 0, slope, stats, 1,
+                              btab, 1, upsample, S(stream));
+}
+int bg_style_modulate(const float* W, const float* bias, const float* stats, const float* style, void* wmod, float* btab,
+                      int N, int Cin, int Cout, int HW, float coef, float eps, void* stream) {
+  return bg::launch_style_modulate(W, bias, stats, style, wmod, btab, N, Cin, Cout, HW, coef, eps, S(stream));
+}
+int bg_to_rgb_adain(const void* a, const float* stats, const float* style, const float* Wm, const float* bias, float* out,
+                    int N, int HW, int C, float coef, float eps, void* stream) {
+  return bg::launch_to_rgb_adain(a, stats, style, Wm, bias, out, N, HW, C, coef, eps, S(stream));
 }
 int bg_conv_pool_fprop(const void* x, const void* wpack, void* out, int N, int H, int W, int Cin, int Cout,
                        const float* bias, const void* gate_src, int act, float slope, void* stream) {
@@ -95,7 +121,7 @@ int bg_conv_pool_fprop(const void* x, const void* wpack, void* out, int N, int H
     return 2;
   }
   return bg::launch_conv_halo(x, wpack, out, N, H, W, Cin, Cout, bias, nullptr, nullptr, gate_src, act, 1, slope,
-                              nullptr, 0, S(stream));
+                              nullptr, 0, nullptr, 0, 0, S(stream));
 }
 int bg_conv_fprop_tapwise(const void* x, const void* wpack, void* out, int N, int H, int W, int Cin, int Cout, int ksize,
                           const float* bias, const float* noise, const float* noise_w, const void* gate_src, int act,

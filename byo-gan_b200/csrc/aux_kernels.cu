@@ -550,6 +550,136 @@ __global__ void adain_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, cons
   if (wsum != nullptr) block_channel_reduce<2>(acc, red, wsum, C);
 }
 
+// ---------------------------------------------------------------------------------------------
+// AdaIN folded into the NEXT conv's operands (generator forward without materialising the normalised map):
+//   xo[n,p,ci] = s[n,ci] * a[n,p,ci] + t[n,ci],   s = gamma * rstd,  t = beta - s * mean      (gan.py:65-71)
+//   conv3x3(xo)[n,p,co] = sum_{tap,ci} (coef W[co,ci,tap] s[n,ci]) a[n,p+tap,ci]  +  sum_{tap in bounds} sum_ci coef W t
+// (the same holds through the bilinear upsample, whose taps sum to 1).  One block per (co, n):
+//   wmod[n][tap][co][ci] = bf16(coef * W[co][ci][tap] * s[n][ci])
+//   btab[n][cls][co]     = bias[co] + sum over the taps that are inside the image for border class cls = 3*rc + cc
+//                          (rc/cc: 0 first row/column, 1 interior, 2 last) of  sum_ci coef * W[co][ci][tap] * t[n][ci]
+// ---------------------------------------------------------------------------------------------
+__global__ void style_modulate_kernel(const float* __restrict__ W, const float* __restrict__ bias,
+                                      const float* __restrict__ stats, const float* __restrict__ style,
+                                      __nv_bfloat16* __restrict__ wmod, float* __restrict__ btab, int N, int Cin, int Cout,
+                                      int HW, float coef, float eps) {
+  __shared__ float red[9][32];
+  const int co = blockIdx.x, n = blockIdx.y;
+  const float inv = 1.f / HW;
+  float acc[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+  for (int ci = threadIdx.x; ci < Cin; ci += blockDim.x) {
+    const float* st = stats + ((size_t)n * Cin + ci) * 2;
+    const float m = st[0] * inv;
+    const float var = fmaxf(st[1] * inv - m * m, 0.f);
+    const float sc = style[(size_t)n * 2 * Cin + ci] * rsqrtf(var + eps);
+    const float sh = style[(size_t)n * 2 * Cin + Cin + ci] - sc * m;
+    const float* w = W + ((size_t)co * Cin + ci) * 9;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const float wk = w[k] * coef;
+      wmod[(((size_t)n * 9 + k) * Cout + co) * Cin + ci] = __float2bfloat16_rn(wk * sc);
+      acc[k] = fmaf(wk, sh, acc[k]);
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const float v = warp_sum(acc[k]);
+    if (lane == 0) red[k][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    const int cls = threadIdx.x, rc = cls / 3, cc = cls % 3;
+    const int nw = blockDim.x >> 5;
+    float tot = bias != nullptr ? bias[co] : 0.f;
+    for (int ky = 0; ky < 3; ++ky) {
+      if ((rc == 0 && ky == 0) || (rc == 2 && ky == 2)) continue;      // that tap row reads the zero padding
+      for (int kx = 0; kx < 3; ++kx) {
+        if ((cc == 0 && kx == 0) || (cc == 2 && kx == 2)) continue;
+        for (int wv = 0; wv < nw; ++wv) tot += red[ky * 3 + kx][wv];
+      }
+    }
+    btab[((size_t)n * 9 + cls) * Cout + co] = tot;
+  }
+}
+
+// toRGB (1x1 conv to 3 planes, gan.py:172-179) applied to AdaIN(a) without materialising it: per sample the AdaIN
+// scale is folded into the (3 x C) matrix and the shift into the bias.  grid = (blocks per sample, N).
+__global__ void to_rgb_adain_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ stats,
+                                    const float* __restrict__ style, const float* __restrict__ Wm,
+                                    const float* __restrict__ bias, float* __restrict__ out, int HW, int C, float coef,
+                                    float eps) {
+  extern __shared__ float sw[];  // [3][C] + [3]
+  const int n = blockIdx.y;
+  const float inv = 1.f / HW;
+  float part[3] = {0.f, 0.f, 0.f};
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float* st = stats + ((size_t)n * C + c) * 2;
+    const float m = st[0] * inv;
+    const float var = fmaxf(st[1] * inv - m * m, 0.f);
+    const float sc = style[(size_t)n * 2 * C + c] * rsqrtf(var + eps);
+    const float sh = style[(size_t)n * 2 * C + C + c] - sc * m;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float w = Wm[(size_t)j * C + c] * coef;
+      sw[j * C + c] = w * sc;
+      part[j] = fmaf(w, sh, part[j]);
+    }
+  }
+  __shared__ float redb[3][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const float v = warp_sum(part[j]);
+    if (lane == 0) redb[j][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float tot = bias != nullptr ? bias[threadIdx.x] : 0.f;
+    for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) tot += redb[threadIdx.x][wv];
+    sw[3 * C + threadIdx.x] = tot;
+  }
+  __syncthreads();
+  const float b0 = sw[3 * C], b1 = sw[3 * C + 1], b2 = sw[3 * C + 2];
+  const int cv = C / 8;
+  const int lanes_per_pix = cv < 32 ? cv : 32;
+  const int pix_per_warp = 32 / lanes_per_pix;
+  const int sub = lane % lanes_per_pix;
+  const int pw = lane / lanes_per_pix;
+  const int warps_per_block = blockDim.x >> 5;
+  const int groups = (HW + pix_per_warp - 1) / pix_per_warp;
+  const __nv_bfloat16* ab = a + (size_t)n * HW * C;
+  float* ob = out + (size_t)n * 3 * HW;
+  for (int gidx = blockIdx.x * warps_per_block + warp; gidx < groups; gidx += gridDim.x * warps_per_block) {
+    const int p = gidx * pix_per_warp + pw;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    if (p < HW) {
+      for (int v = sub; v < cv; v += lanes_per_pix) {
+        const F8 x = ld8(ab + (size_t)p * C + v * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = v * 8 + j;
+          s0 = fmaf(x.v[j], sw[c], s0);
+          s1 = fmaf(x.v[j], sw[C + c], s1);
+          s2 = fmaf(x.v[j], sw[2 * C + c], s2);
+        }
+      }
+    }
+    for (int o = lanes_per_pix >> 1; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (p < HW && sub == 0) {
+      ob[p] = s0 + b0;
+      ob[p + HW] = s1 + b1;
+      ob[p + 2 * (size_t)HW] = s2 + b2;
+    }
+  }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -730,6 +860,31 @@ int launch_adain_bwd_apply(const void* g, const void* a, const float* stats, con
   adain_bwd_apply_kernel<<<grid_for(total), kBlock, smem, s>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)a, stats,
                                                               style, bsums, (__nv_bfloat16*)out, N, HW, C, eps, slope,
                                                               gate, noise, wsum);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_style_modulate(const float* W, const float* bias, const float* stats, const float* style, void* wmod,
+                          float* btab, int N, int Cin, int Cout, int HW, float coef, float eps, cudaStream_t s) {
+  BG_REQUIRE(N > 0 && Cin > 0 && Cout > 0 && HW > 0, "style_modulate: bad shape N %d Cin %d Cout %d HW %d", N, Cin, Cout, HW);
+  const int threads = Cin >= 256 ? 256 : (Cin >= 64 ? 64 : 32);
+  style_modulate_kernel<<<dim3(Cout, N), threads, 0, s>>>(W, bias, stats, style, (__nv_bfloat16*)wmod, btab, N, Cin, Cout,
+                                                         HW, coef, eps);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_to_rgb_adain(const void* a, const float* stats, const float* style, const float* Wm, const float* bias,
+                        float* out, int N, int HW, int C, float coef, float eps, cudaStream_t s) {
+  BG_REQUIRE(C % 16 == 0 && C <= 1024, "to_rgb_adain: unsupported C %d", C);
+  int bps = (num_sms() * 8 + N - 1) / N;                    // blocks per sample
+  const int cv = C / 8;
+  const int ppw = 32 / (cv < 32 ? cv : 32);
+  const int max_bps = (HW / ppw + 63) / 64;                 // at least ~8 pixel groups per warp
+  if (bps > max_bps) bps = max_bps;
+  if (bps < 1) bps = 1;
+  to_rgb_adain_kernel<<<dim3(bps, N), kBlock, (size_t)(3 * C + 4) * sizeof(float), s>>>(
+      (const __nv_bfloat16*)a, stats, style, Wm, bias, out, HW, C, coef, eps);
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -70,6 +70,16 @@ struct HaloParams {
   int stats_mode;
   int n_blocks;
   int contig;     // tile order, see tile_range()
+  // StyleGAN generator forward (gan.py:89-98,118-127) with the layer's AdaIN folded into the operands:
+  //   per_sample_w: the weight pack is [N][9][Cout][Cin] (instance-norm scale * style gamma folded in per sample);
+  //   bias_tab:     fp32 [N][9][Cout] replaces bias: bias + the conv of the per-channel AdaIN shift, one row per border
+  //                 class (3 row classes x 3 column classes: which taps fall into the zero padding);
+  //   upsample:     x is (N, H/2, W/2, Cin); the bilinear x2 upsample (align_corners=False) is applied while the
+  //                 halo tile is built (patch -> shared memory -> 18x18 halo), so the 4x larger map never exists.
+  int per_sample_w;
+  const float* bias_tab;
+  int upsample;
+  uint32_t patch_bytes;   // one low-resolution 10x10 patch stage (upsample mode)
 };
 
 struct TileCoord {
@@ -153,11 +163,20 @@ __device__ __forceinline__ void mma_issue_loop(const HaloParams& p, uint8_t* a_b
   uint32_t aphase = 0;
   int acc = 0;
   uint32_t acc_phase = 0;
-  if (p.b_resident) {
-    mbar_wait(&b_full[0], 0);
-    tc_fence_after();
-  }
+  int w_cur = -1;
+  uint32_t w_loads = 0;
   for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
+    if (p.b_resident) {
+      const int wn = p.per_sample_w ? decode_tile(p, tile).n : 0;
+      if (wn != w_cur) {                      // first tile, or the tile range moved on to another sample's pack
+        if (w_loads > 0 && leader) tc_commit(&b_empty[0]);
+        __syncwarp();
+        mbar_wait(&b_full[0], w_loads & 1u);
+        tc_fence_after();
+        w_cur = wn;
+        ++w_loads;
+      }
+    }
     mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
     tc_fence_after();
     const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
@@ -307,6 +326,125 @@ __device__ __forceinline__ void halo_producer_loop(const HaloParams& p, uint8_t*
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Halo producers, upsample mode: the conv input is nn.Upsample(scale_factor=2, mode='bilinear') of x (gan.py:112,123;
+// align_corners=False: taps .75/.25, indices clamped at the edges).  Two phases per (tile, channel chunk):
+//   1. cp.async the 10x10 low-resolution patch that the 18x18 halo depends on into a 4-deep patch ring (issued two
+//      chunks ahead; indices are clamped at load time, so every copy is in bounds);
+//   2. after a producer-wide named barrier, each thread builds 2x2 output quads from 2x2 patch pixels (separable
+//      .75/.25 blends in fp32), writes them into the UMMA plane layout of the A stage (zeros outside the image: the
+//      conv's padding applies to the UPSAMPLED map) and arrives on a_full.
+// Thread -> (quad, 16-byte channel group): u = pt + 256 i, c8 = u % cpp, quad = u / cpp, quad = qk * 9 + ql covers
+// halo rows 2qk, 2qk+1 and columns 2ql, 2ql+1 from patch rows qk, qk+1 and columns ql, ql+1.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kPatch = 10;
+constexpr int kPatchStages = 4;
+
+template <int CPP_SHIFT>
+__device__ __forceinline__ void halo_producer_upsample(const HaloParams& p, uint8_t* a_base, uint8_t* patch_base,
+                                                       uint64_t* a_full, uint64_t* a_empty, int pt) {
+  constexpr int kCpp = 1 << CPP_SHIFT;
+  constexpr int kPatchUnits = kPatch * kPatch * kCpp;
+  constexpr int kLoadIters = (kPatchUnits + kProdThreads - 1) / kProdThreads;     // 4 / 2 / 1
+  constexpr int kQuadUnits = 81 * kCpp;
+  constexpr int kQuadIters = (kQuadUnits + kProdThreads - 1) / kProdThreads;      // 3 / 2 / 1
+  constexpr uint32_t kPixBytes = 16u * kCpp;                                        // one patch pixel (kc channels)
+  const int HL = p.H >> 1, WL = p.W >> 1;
+  int tile_lo, tile_hi, tile_step;
+  tile_range(p, tile_lo, tile_hi, tile_step);
+  const int total = ((tile_hi - tile_lo + tile_step - 1) / tile_step) * p.k_chunks;   // (tile, chunk) items of this CTA
+
+  // ---- patch loader state (runs two items ahead of the builder)
+  int l_item = 0, l_tile = tile_lo, l_kcx = 0;
+  auto issue_patch = [&]() {
+    if (l_item < total) {
+      const TileCoord t = decode_tile(p, l_tile);
+      const int k0 = (t.h0 >> 1) - 1, l0 = (t.w0 >> 1) - 1;
+      const uint32_t sdst = smem_u32(patch_base + (size_t)(l_item & (kPatchStages - 1)) * p.patch_bytes);
+      const __nv_bfloat16* src = p.x + (size_t)t.n * HL * WL * p.Cin + l_kcx * p.kc;
+#pragma unroll
+      for (int i = 0; i < kLoadIters; ++i) {
+        const int u = pt + i * kProdThreads;
+        if (i < kLoadIters - 1 || u < kPatchUnits) {
+          const int px = u >> CPP_SHIFT, c8 = u & (kCpp - 1);
+          const int pr = px / kPatch, pc = px - pr * kPatch;
+          const int r = min(max(k0 + pr, 0), HL - 1), c = min(max(l0 + pc, 0), WL - 1);
+          cp_async_16_full(sdst + (uint32_t)px * kPixBytes + (uint32_t)c8 * 16u, src + ((size_t)r * WL + c) * p.Cin + c8 * 8);
+        }
+      }
+      if (++l_kcx == p.k_chunks) {
+        l_kcx = 0;
+        l_tile += tile_step;
+      }
+    }
+    ++l_item;
+    cp_async_commit();          // always commit (possibly empty) so that wait_group<2> counts items uniformly
+  };
+  issue_patch();
+  issue_patch();
+
+  int stage = 0;
+  uint32_t phase = 0;
+  int item = 0;
+  for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
+    const TileCoord t = decode_tile(p, tile);
+    const int hb = t.h0 - 1, wb = t.w0 - 1;
+    for (int kcx = 0; kcx < p.k_chunks; ++kcx, ++item) {
+      issue_patch();                                        // item + 2
+      cp_async_wait<2>();                                   // this thread's copies of `item` have landed
+      asm volatile("bar.sync 2, %0;" ::"n"(kProdThreads) : "memory");   // ... and everybody else's
+      mbar_wait(&a_empty[stage], phase ^ 1u);
+      const uint32_t patch = smem_u32(patch_base + (size_t)(item & (kPatchStages - 1)) * p.patch_bytes);
+      const uint32_t sdst = smem_u32(a_base + (size_t)stage * p.a_stage_bytes);
+#pragma unroll
+      for (int i = 0; i < kQuadIters; ++i) {
+        const int u = pt + i * kProdThreads;
+        if (i < kQuadIters - 1 || u < kQuadUnits) {
+          const int q = u >> CPP_SHIFT, c8 = u & (kCpp - 1);
+          const int qk = q / 9, ql = q - qk * 9;
+          const uint32_t pa = patch + (uint32_t)(qk * kPatch + ql) * kPixBytes + (uint32_t)c8 * 16u;
+          const uint4 r00 = lds128(pa), r01 = lds128(pa + kPixBytes), r10 = lds128(pa + kPatch * kPixBytes),
+                      r11 = lds128(pa + (kPatch + 1) * kPixBytes);
+          const uint32_t w00[4] = {r00.x, r00.y, r00.z, r00.w}, w01[4] = {r01.x, r01.y, r01.z, r01.w};
+          const uint32_t w10[4] = {r10.x, r10.y, r10.z, r10.w}, w11[4] = {r11.x, r11.y, r11.z, r11.w};
+          uint32_t oAP[4], oAQ[4], oBP[4], oBQ[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 a = unpack_bf16x2(w00[j]), b = unpack_bf16x2(w01[j]);
+            const float2 c = unpack_bf16x2(w10[j]), d = unpack_bf16x2(w11[j]);
+            // columns: P = left output column (.75 left pixel), Q = right output column (.75 right pixel)
+            const float p0x = 0.75f * a.x + 0.25f * b.x, p0y = 0.75f * a.y + 0.25f * b.y;
+            const float q0x = 0.25f * a.x + 0.75f * b.x, q0y = 0.25f * a.y + 0.75f * b.y;
+            const float p1x = 0.75f * c.x + 0.25f * d.x, p1y = 0.75f * c.y + 0.25f * d.y;
+            const float q1x = 0.25f * c.x + 0.75f * d.x, q1y = 0.25f * c.y + 0.75f * d.y;
+            // rows: A = upper output row (.75 upper pixel), B = lower output row (.75 lower pixel)
+            oAP[j] = pack_bf16x2(0.75f * p0x + 0.25f * p1x, 0.75f * p0y + 0.25f * p1y);
+            oAQ[j] = pack_bf16x2(0.75f * q0x + 0.25f * q1x, 0.75f * q0y + 0.25f * q1y);
+            oBP[j] = pack_bf16x2(0.25f * p0x + 0.75f * p1x, 0.25f * p0y + 0.75f * p1y);
+            oBQ[j] = pack_bf16x2(0.25f * q0x + 0.75f * q1x, 0.25f * q0y + 0.75f * q1y);
+          }
+          const int hy = 2 * qk, hx = 2 * ql;
+          const bool rA = (unsigned)(hb + hy) < (unsigned)p.H, rB = (unsigned)(hb + hy + 1) < (unsigned)p.H;
+          const bool cP = (unsigned)(wb + hx) < (unsigned)p.W, cQ = (unsigned)(wb + hx + 1) < (unsigned)p.W;
+          const uint4 z = make_uint4(0, 0, 0, 0);
+          const uint32_t so = sdst + (uint32_t)c8 * kPlaneBytes + (uint32_t)(hy * kHalo + hx) * 16u;
+          sts128(so, (rA && cP) ? make_uint4(oAP[0], oAP[1], oAP[2], oAP[3]) : z);
+          sts128(so + 16u, (rA && cQ) ? make_uint4(oAQ[0], oAQ[1], oAQ[2], oAQ[3]) : z);
+          sts128(so + kRowBytes, (rB && cP) ? make_uint4(oBP[0], oBP[1], oBP[2], oBP[3]) : z);
+          sts128(so + kRowBytes + 16u, (rB && cQ) ? make_uint4(oBQ[0], oBQ[1], oBQ[2], oBQ[3]) : z);
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(&a_full[stage]);
+      if (++stage == p.a_stages) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  }
+  cp_async_wait<0>();
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Fused reductions of the output tile (epilogue warps).  During the line-wise store phase lane l owns the 16-byte
 // channel chunk ch = l % cpr of rows l / cpr, l / cpr + 32 / cpr, ... and sums its 8 channels in registers; after the
 // round a butterfly over the lanes that share a chunk leaves the warp totals in lanes 0..cpr-1, which add them to
@@ -360,7 +498,7 @@ __device__ __forceinline__ void stats_flush(const HaloParams& p, float* slices, 
 // ---------------------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------------------
-template <bool kStats>
+template <bool kStats, bool kUp>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -371,7 +509,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const HaloParams p)
   const int b_tiles = p.b_resident ? p.k_chunks * 9 : p.b_stages;
   uint8_t* b_base = smem;
   uint8_t* a_base = b_base + (size_t)b_tiles * p.b_tile_bytes;
-  uint8_t* epi_base = a_base + (size_t)p.a_stages * p.a_stage_bytes;
+  uint8_t* patch_base = a_base + (size_t)p.a_stages * p.a_stage_bytes;
+  patch_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(patch_base) + 127) & ~uintptr_t(127));
+  uint8_t* epi_base = patch_base + (p.upsample ? (size_t)kPatchStages * p.patch_bytes : 0);
   epi_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(epi_base) + 127) & ~uintptr_t(127));
   uint8_t* aux = epi_base + (size_t)kEpiWarps * 32 * p.epi_row_bytes;
   uint64_t* b_full = reinterpret_cast<uint64_t*>(aux);
@@ -427,11 +567,22 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const HaloParams p)
     // ------------------------------ weight TMA producer ------------------------------
     if (lane == 0) {
       if (p.b_resident) {
-        // residency is only selected when there is a single n-block: the whole pack is loaded once per kernel
-        mbar_expect_tx(&b_full[0], (uint32_t)(p.k_chunks * 9) * p.b_tx_bytes);
-        for (int kcx = 0; kcx < p.k_chunks; ++kcx)
-          for (int tap = 0; tap < 9; ++tap)
-            tma_load_3d(&tmap_w, &b_full[0], b_base + (size_t)(kcx * 9 + tap) * p.b_tile_bytes, kcx * p.kc, 0, tap);
+        // residency is only selected when there is a single n-block: the whole pack is loaded once per kernel, or,
+        // with per-sample weights, once per sample of this CTA's (contiguous) tile range — after the MMA warp has
+        // committed the last tile that used the previous sample's pack (b_empty[0]).
+        int cur = -1;
+        uint32_t loads = 0;
+        for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
+          const int wn = p.per_sample_w ? decode_tile(p, tile).n : 0;
+          if (wn == cur) continue;
+          if (loads > 0) mbar_wait(&b_empty[0], (loads - 1u) & 1u);
+          mbar_expect_tx(&b_full[0], (uint32_t)(p.k_chunks * 9) * p.b_tx_bytes);
+          for (int kcx = 0; kcx < p.k_chunks; ++kcx)
+            for (int tap = 0; tap < 9; ++tap)
+              tma_load_4d(&tmap_w, &b_full[0], b_base + (size_t)(kcx * 9 + tap) * p.b_tile_bytes, kcx * p.kc, 0, tap, wn);
+          cur = wn;
+          ++loads;
+        }
       } else {
         int stage = 0;
         uint32_t phase = 0;
@@ -441,7 +592,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const HaloParams p)
             for (int tap = 0; tap < 9; ++tap) {
               mbar_wait(&b_empty[stage], phase ^ 1u);
               mbar_expect_tx(&b_full[stage], p.b_tx_bytes);
-              tma_load_3d(&tmap_w, &b_full[stage], b_base + (size_t)stage * p.b_tile_bytes, kcx * p.kc, t.co0, tap);
+              tma_load_4d(&tmap_w, &b_full[stage], b_base + (size_t)stage * p.b_tile_bytes, kcx * p.kc, t.co0, tap,
+                          p.per_sample_w ? t.n : 0);
               if (++stage == p.b_stages) {
                 stage = 0;
                 phase ^= 1u;
@@ -495,6 +647,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const HaloParams p)
       // first pixel of this warp's 4 image rows x 8 columns block (row index 0 of the transpose stage)
       const size_t pix_q0 = ((size_t)t.n * p.H + t.h0 + q * 4) * p.W + t.w0 + half * 8;
       const size_t opix_pool = ((size_t)t.n * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
+      // per-sample, per-border-class bias row (AdaIN shift folded through the conv), else the plain bias in smem
+      const int cls = (h == 0 ? 0 : (h == p.H - 1 ? 2 : 1)) * 3 + (w == 0 ? 0 : (w == p.W - 1 ? 2 : 1));
+      const float* btab = p.bias_tab != nullptr ? p.bias_tab + ((size_t)t.n * 9 + cls) * p.Cout + t.co0 : nullptr;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u + (uint32_t)half * 128u;
@@ -520,7 +675,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const HaloParams p)
           float bn[16];
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 b4 = lds128f(bias_s + t.co0 + c + 4 * j4);
+            const float4 b4 = btab != nullptr ? __ldg(reinterpret_cast<const float4*>(btab + c + 4 * j4))
+                                              : lds128f(bias_s + t.co0 + c + 4 * j4);
             bn[4 * j4 + 0] = b4.x; bn[4 * j4 + 1] = b4.y; bn[4 * j4 + 2] = b4.z; bn[4 * j4 + 3] = b4.w;
           }
           if (p.noise != nullptr) {
@@ -631,7 +787,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const HaloParams p)
   } else {
     // ------------------------------ halo producers (cp.async, zero-fill padding) ------------------------------
     const int pt = threadIdx.x - 32 * (2 + kEpiWarps);       // 0..255
-    if (p.cpp_shift == 3) halo_producer_loop<3>(p, a_base, a_full, a_empty, pt);
+    if (kUp) {
+      if (p.cpp_shift == 3) halo_producer_upsample<3>(p, a_base, patch_base, a_full, a_empty, pt);
+      else if (p.cpp_shift == 2) halo_producer_upsample<2>(p, a_base, patch_base, a_full, a_empty, pt);
+      else halo_producer_upsample<1>(p, a_base, patch_base, a_full, a_empty, pt);
+    } else if (p.cpp_shift == 3) halo_producer_loop<3>(p, a_base, a_full, a_empty, pt);
     else if (p.cpp_shift == 2) halo_producer_loop<2>(p, a_base, a_full, a_empty, pt);
     else halo_producer_loop<1>(p, a_base, a_full, a_empty, pt);
   }
@@ -673,9 +833,11 @@ bool conv_halo_supported(int N, int H, int W, int Cin, int Cout, int ksize) {
 // Host launcher; same arguments as launch_conv_fprop (ksize must be 3) plus the fused-pool switch.
 int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, int W, int Cin, int Cout,
                      const float* bias, const float* noise, const float* noise_w, const void* gate_src, int act,
-                     int pool, float slope, float* stats, int stats_mode, cudaStream_t stream) {
+                     int pool, float slope, float* stats, int stats_mode, const float* bias_tab, int per_sample_w,
+                     int upsample, cudaStream_t stream) {
   BG_REQUIRE(conv_halo_supported(N, H, W, Cin, Cout, 3), "conv_halo: unsupported shape N %d H %d W %d Cin %d Cout %d", N,
              H, W, Cin, Cout);
+  BG_REQUIRE(!(upsample && pool), "conv_halo: upsample and pool cannot be combined");
   HaloParams p;
   memset(&p, 0, sizeof(p));
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
@@ -698,7 +860,10 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
   const uint32_t epi_bytes = (uint32_t)kEpiWarps * 32u * p.epi_row_bytes + 128u;
   const uint32_t stat_bytes = (stats != nullptr) ? (uint32_t)kEpiWarps * (uint32_t)Cout * 2u * 4u : 0u;
   const uint32_t aux_bytes = 8 * (2 * kMaxBStages + 2 * kMaxAStages + 4) + 16 + 2 * 512 * 4 + 64 + stat_bytes;
-  const uint32_t total = 227u * 1024u - 1024u - aux_bytes - epi_bytes;
+  p.upsample = upsample ? 1 : 0;
+  p.patch_bytes = (uint32_t)(kPatch * kPatch) * (uint32_t)p.kc * 2u;
+  const uint32_t patch_total = p.upsample ? (uint32_t)kPatchStages * p.patch_bytes + 128u : 0u;
+  const uint32_t total = 227u * 1024u - 1024u - aux_bytes - epi_bytes - patch_total;
   const uint32_t resident_bytes = (uint32_t)p.k_chunks * 9u * p.b_tile_bytes;
   // prefer resident weights (3 halo stages if they fit, else 2); otherwise stream the weights past 3 halo stages
   p.a_stages = 3;
@@ -714,7 +879,12 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
   if (p.b_resident) {
     p.b_stages = 1;
   } else {
-    int st = (int)((total - 3u * p.a_stage_bytes) / p.b_tile_bytes);
+    // streamed weights: 3 halo stages when at least 3 weight stages still fit, else 2 halo stages
+    int st = total > 3u * p.a_stage_bytes ? (int)((total - 3u * p.a_stage_bytes) / p.b_tile_bytes) : 0;
+    if (st < 3) {
+      p.a_stages = 2;
+      st = total > 2u * p.a_stage_bytes ? (int)((total - 2u * p.a_stage_bytes) / p.b_tile_bytes) : 0;
+    }
     if (st > kMaxBStages) st = kMaxBStages;
     BG_REQUIRE(st >= 2, "conv_halo: weight tile does not fit shared memory");
     p.b_stages = st;
@@ -728,7 +898,9 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
   p.n_blocks = n_blocks;
   p.stats = stats;
   p.stats_mode = stats != nullptr ? stats_mode : 0;
-  p.contig = p.stats_mode != 0 ? 1 : 0;
+  p.per_sample_w = per_sample_w ? 1 : 0;
+  p.bias_tab = bias_tab;
+  p.contig = (p.stats_mode != 0 || p.per_sample_w) ? 1 : 0;
   BG_REQUIRE(p.stats_mode == 0 || ((stats_mode == 1 || stats_mode == 2) && !pool),
              "conv_halo: stats_mode must be 1 or 2 and cannot be combined with the fused pool");
   if (p.stats_mode)
@@ -738,27 +910,33 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
     if (dbg < 0) { const char* e = getenv("BG_HALO_DEBUG"); dbg = e ? atoi(e) : 0; }
     p.debug = dbg;
   }
-  if (p.debug & 16) p.contig ^= 1;       // A/B the tile order
+  if ((p.debug & 16) && !p.per_sample_w) p.contig ^= 1;       // A/B the tile order
 
   CUtensorMap tmw;
   {
-    uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, 9ull};
-    uint64_t str[2] = {(uint64_t)Cin * 2, (uint64_t)Cout * Cin * 2};
-    uint32_t box[3] = {(uint32_t)p.kc, (uint32_t)p.block_n, 1u};
-    if (make_tmap_bf16(&tmw, wpack, 3, dims, str, box, (int)row_bytes) != 0) return 1;
+    // [sample][tap][Cout][Cin]; the sample dimension has extent 1 for the ordinary shared pack
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Cout, 9ull, (uint64_t)(p.per_sample_w ? N : 1)};
+    uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)Cout * Cin * 2, (uint64_t)9 * Cout * Cin * 2};
+    uint32_t box[4] = {(uint32_t)p.kc, (uint32_t)p.block_n, 1u, 1u};
+    if (make_tmap_bf16(&tmw, wpack, 4, dims, str, box, (int)row_bytes) != 0) return 1;
   }
   const size_t b_tiles = p.b_resident ? (size_t)p.k_chunks * 9 : (size_t)p.b_stages;
-  const size_t smem_bytes = b_tiles * p.b_tile_bytes + (size_t)p.a_stages * p.a_stage_bytes + epi_bytes + aux_bytes + 1024;
+  const size_t smem_bytes = b_tiles * p.b_tile_bytes + (size_t)p.a_stages * p.a_stage_bytes + patch_total + epi_bytes +
+                            aux_bytes + 1024;
   BG_REQUIRE(smem_bytes <= 227 * 1024, "conv_halo: shared memory budget exceeded (%zu)", smem_bytes);
   static bool attr_set = false;
   if (!attr_set) {
-    BG_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    BG_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BG_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BG_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BG_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BG_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  if (p.stats_mode) conv_halo_kernel<true><<<grid, kThreads, smem_bytes, stream>>>(tmw, p);
-  else conv_halo_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(tmw, p);
+  if (p.stats_mode && p.upsample) conv_halo_kernel<true, true><<<grid, kThreads, smem_bytes, stream>>>(tmw, p);
+  else if (p.stats_mode) conv_halo_kernel<true, false><<<grid, kThreads, smem_bytes, stream>>>(tmw, p);
+  else if (p.upsample) conv_halo_kernel<false, true><<<grid, kThreads, smem_bytes, stream>>>(tmw, p);
+  else conv_halo_kernel<false, false><<<grid, kThreads, smem_bytes, stream>>>(tmw, p);
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

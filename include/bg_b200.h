@@ -54,6 +54,23 @@ int bg_conv_fprop(const void* x, const void* wpack, void* out, int N, int H, int
 int bg_conv_fprop_stats(const void* x, const void* wpack, void* out, int N, int H, int W, int Cin, int Cout, int ksize,
                         const float* bias, const float* noise, const float* noise_w, const void* gate_src, int act,
                         float slope, float* stats, int stats_mode, void* stream);
+/* ---- StyleConvBlock.forward fused end to end (gan.py:89-98 inside StyleGanBlock.forward gan.py:118-127) -------
+ * The PREVIOUS layer's AdaIN (gan.py:65-71) never materialises: bg_style_modulate folds its per-sample scale
+ * gamma*rstd into a per-sample weight pack wmod bf16 [N][9][Cout][Cin] and its shift, pushed through the conv (with
+ * the zero padding accounted for per border class) and added to the conv bias, into btab fp32 [N][9][Cout].
+ *   stats: fp32 (N,Cin,2) sums of the previous activation over HW pixels; style: fp32 (N,2*Cin) = [gamma|beta].
+ * bg_conv_style_fprop then computes
+ *   out = LeakyReLU( conv3x3( [bilinear x2 upsample](x), wmod[n] ) + btab[n][class(h,w)] + noise_w[c]*noise[n,h,w] )
+ * with the upsample (gan.py:112,123) built inside the operand feed when upsample=1 (x is then (N,H/2,W/2,Cin)), and
+ * accumulates this layer's own instance-norm sums into stats fp32 (N,Cout,2) (zeroed by the call).  H,W >= 16. */
+int bg_style_modulate(const float* W, const float* bias, const float* stats, const float* style, void* wmod, float* btab,
+                      int N, int Cin, int Cout, int HW, float coef, float eps, void* stream);
+int bg_conv_style_fprop(const void* x, const void* wmod, const float* btab, void* out, int N, int H, int W, int Cin,
+                        int Cout, int upsample, const float* noise, const float* noise_w, float slope, float* stats,
+                        void* stream);
+/* toRGB 1x1 conv (gan.py:172-179,218,222) of AdaIN(a) without materialising it; out: fp32 (N,3,H,W). */
+int bg_to_rgb_adain(const void* a, const float* stats, const float* style, const float* Wm, const float* bias, float* out,
+                    int N, int HW, int C, float coef, float eps, void* stream);
 /* conv3x3 -> AvgPool2d(2) -> [LeakyReLU | gate] fused in the epilogue (CriticBlock.conv_2, gan.py:258-262; with
  * act=0 and gate_src (pooled resolution) it is the R1 tangent pass through the same layers).  out: (N,H/2,W/2,Cout).
  * Needs H,W >= 16. */

@@ -202,6 +202,78 @@ def test_upsample_pool_adain_aux():
     assert relerr(nchw(xo), ref) < 5e-3
 
 
+STYLE_SHAPES = [
+    # N, H, W (output), Cin, Cout, upsample
+    (2, 16, 16, 64, 64, 0), (2, 16, 16, 64, 64, 1), (3, 32, 32, 128, 64, 1), (3, 32, 32, 64, 64, 0),
+    (2, 64, 64, 32, 16, 1), (2, 64, 64, 16, 16, 0), (5, 32, 32, 256, 128, 1), (2, 64, 64, 64, 32, 1),
+    (2, 32, 32, 512, 256, 1), (1, 128, 128, 32, 32, 0), (4, 16, 16, 128, 256, 0),
+]
+
+
+@pytest.mark.parametrize("shape", STYLE_SHAPES)
+def test_style_conv_fused(shape):
+    """StyleGanBlock / StyleConvBlock forward (gan.py:89-98,118-127): AdaIN of the previous activation (gan.py:65-71)
+    -> [bilinear x2] -> conv3x3 -> + noise -> LeakyReLU, against torch fp32 on the same bf16 activation, and the
+    fused instance-norm sums of the result."""
+    n, h, w_, ci, co, up = shape
+    hi, wi = (h // 2, w_ // 2) if up else (h, w_)
+    torch.manual_seed(11)
+    a_prev = nhwc(F.leaky_relu(torch.randn(n, ci, hi, wi, device=DEV) * 1.3 + 0.2, 0.2))
+    style = torch.cat([1 + 0.3 * torch.randn(n, ci, device=DEV), 0.3 * torch.randn(n, ci, device=DEV)], dim=1).contiguous()
+    w = torch.randn(co, ci, 3, 3, device=DEV)
+    coef = math.sqrt(2 / (ci * 9))
+    bias = torch.randn(co, device=DEV) * 0.1
+    noise = torch.randn(n, 1, h, w_, device=DEV)
+    nw = torch.randn(co, device=DEV) * 0.1
+    # reference in fp32 from the bf16 activation the kernels see
+    af = nchw(a_prev)
+    xo = style[:, :ci, None, None] * F.instance_norm(af, eps=1e-8) + style[:, ci:, None, None]
+    if up:
+        xo = F.interpolate(xo, scale_factor=2, mode="bilinear")
+    ref = F.leaky_relu(F.conv2d(xo, w * coef, bias, padding=1) + nw.view(1, co, 1, 1) * noise, 0.2)
+    # fused path
+    stats_prev = torch.empty(n, ci, 2, device=DEV)
+    bgn.call("bg_in_stats", a_prev, stats_prev, n, hi * wi, ci)
+    wmod = torch.empty(n, 9, co, ci, dtype=torch.bfloat16, device=DEV)
+    btab = torch.empty(n, 9, co, device=DEV)
+    bgn.call("bg_style_modulate", w, bias, stats_prev, style, wmod, btab, n, ci, co, hi * wi, coef, 1e-8)
+    out = torch.empty(n, h, w_, co, dtype=torch.bfloat16, device=DEV)
+    stats = torch.full((n, co, 2), 5.0, device=DEV)
+    bgn.call("bg_conv_style_fprop", a_prev, wmod, btab, out, n, h, w_, ci, co, up, noise, nw, 0.2, stats)
+    torch.cuda.synchronize()
+    err = relerr(nchw(out), ref)
+    assert err < 1.2e-2, err
+    # border pixels exercise the per-class bias table: check them separately (they are few, so a wrong class would
+    # hide inside the global norm)
+    o, r = nchw(out), ref
+    for sl in [(slice(None), slice(None), 0), (slice(None), slice(None), -1), (slice(None), slice(None), slice(None), 0),
+               (slice(None), slice(None), slice(None), -1)]:
+        assert relerr(o[sl], r[sl]) < 1.5e-2, (sl, relerr(o[sl], r[sl]))
+    od = out.double()
+    want = torch.stack([od.sum(dim=(1, 2)), (od * od).sum(dim=(1, 2))], dim=-1)
+    assert (stats.double() - want).abs().max().item() < 2e-5 * (want.abs().max().item() + 1.0) * math.sqrt(h * w_)
+
+
+def test_to_rgb_adain():
+    """to_rgbs[k](AdaIN(a)) (gan.py:172-179 after gan.py:65-71) without the normalised map."""
+    torch.manual_seed(2)
+    for n, c, h in [(3, 32, 16), (2, 16, 64), (2, 512, 4), (1, 128, 32)]:
+        a = nhwc(F.leaky_relu(torch.randn(n, c, h, h, device=DEV) + 0.1, 0.2))
+        style = torch.cat([1 + 0.3 * torch.randn(n, c, device=DEV), 0.3 * torch.randn(n, c, device=DEV)], dim=1).contiguous()
+        wm = torch.randn(3, c, 1, 1, device=DEV)
+        b = torch.randn(3, device=DEV)
+        coef = math.sqrt(2 / c)
+        stats = torch.empty(n, c, 2, device=DEV)
+        bgn.call("bg_in_stats", a, stats, n, h * h, c)
+        out = torch.empty(n, 3, h, h, device=DEV)
+        bgn.call("bg_to_rgb_adain", a, stats, style, wm, b, out, n, h * h, c, coef, 1e-8)
+        torch.cuda.synchronize()
+        af = nchw(a)
+        xo = style[:, :c, None, None] * F.instance_norm(af, eps=1e-8) + style[:, c:, None, None]
+        ref = F.conv2d(xo, wm * coef, b)
+        assert relerr(out, ref) < 2e-3, (n, c, h, relerr(out, ref))
+
+
 @pytest.mark.parametrize("dims", [(3, 16, 8, 8), (2, 64, 32, 32), (2, 512, 4, 4), (1, 128, 64, 64)])
 def test_pool_act_bwd_and_adain_bwd_with_fused_sums(dims):
     """Adjoint of AvgPool2d(2)+LeakyReLU (gan.py:258-262) with the conv bias gradient reduced in the same pass, and the
