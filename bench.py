@@ -25,6 +25,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "byo-gan_b200"))
 sys.path.insert(0, ROOT)
 
+# the step allocates and frees GB-sized activations in a pattern that takes the caching allocator several iterations
+# to settle with fixed-size segments (cudaMalloc stalls inside the first timed steps); expandable segments settle at once
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
+
 import torch  # noqa: E402
 
 # step FLOPs per image in the reference's formulation: 4*G_fwd + 11*D_fwd
@@ -57,25 +61,32 @@ class ClockSampler:
         self.index, self.rows, self.proc = index, [], None
 
     def start(self):
+        """Started BEFORE the warm-up (nvidia-smi needs ~100 ms to produce its first row); only rows that arrive
+        inside the window() are reported."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "25", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def window(self, t0, t1):
+        self.t0, self.t1 = t0, t1
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        t0, t1 = getattr(self, "t0", 0.0), getattr(self, "t1", float("inf"))
+        rows = [r for (ts, r) in self.rows if t0 <= ts <= t1 + 0.05]
+        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "samples": len(sm)}
 
@@ -200,12 +211,14 @@ def run_b200(args):
             torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
         return ms.item()
 
-    timed(args.warmup, from_host=False)                      # warm-up (also builds the weight packs)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    timed(args.warmup, from_host=False)                      # warm-up (also builds the weight packs)
     n0 = bgn.launch_count
+    w0 = time.time()
     ms = timed(args.steps, from_host=False)
+    clocks.window(w0, time.time())
     launches = bgn.launch_count - n0
     clk = clocks.stop() if rank == 0 else None
     timed(1, from_host=True)

@@ -208,6 +208,36 @@ def generator_params(gen, steps: int, fade: bool) -> List[torch.nn.Parameter]:
     return ps
 
 
+def style_conv_fusable(R: int, cout: int) -> bool:
+    """Fold the previous AdaIN into per-sample weights (bg_style_modulate + bg_conv_style_fprop) when the halo kernel
+    runs the layer (R >= 16) and the per-sample packs (9*Cin*Cout per sample) are cheaper to write and read than the
+    normalised map (R*R*Cin per sample) the unfused path materialises."""
+    return R >= 16 and 18 * cout <= R * R
+
+
+def layer_output(layers, idx):
+    """AdaIN output gamma * IN(a) + beta (gan.py:69) of layer idx as a materialised NHWC bf16 map (cached)."""
+    L = layers[idx]
+    if L["xo"] is None:
+        a = L["a"]
+        xo = torch.empty_like(a)
+        call("bg_adain_apply", a, L["stats"], L["style"], xo, a.shape[0], L["R"] * L["R"], L["C"], IN_EPS)
+        L["xo"] = xo
+    return L["xo"]
+
+
+def layer_input(layers, idx, L):
+    """Materialised conv input of layer idx: AdaIN output of the layer before it, bilinearly upsampled for conv_1
+    (gan.py:122-123).  The fused forward never builds it; the unfused layers and the weight-gradient pass do."""
+    xo = layer_output(layers, idx - 1)
+    if not L["up"]:
+        return xo
+    B, r, _, c = xo.shape
+    xin = _bf16(B, 2 * r, 2 * r, c, device=xo.device)
+    call("bg_upsample2x_fwd", xo, xin, B, r, r, c)
+    return xin
+
+
 def generator_forward(gen, packs: PackCache, z, noise, steps, alpha, z2=None, crossover=None, keep_tape=True):
     """Generator.forward (gan.py:183-222).  Returns (image (B,3,R,R) fp32, tape)."""
     dev = z.device
@@ -226,8 +256,6 @@ def generator_forward(gen, packs: PackCache, z, noise, steps, alpha, z2=None, cr
     if z2 is not None:
         maps.append(mapping(z2))
     layers = []
-    feats = []
-    feat = None
     for k in range(steps):
         blk = gen.gen_blocks[k]
         cin, cout = GEN_CHANNELS[k]
@@ -239,47 +267,62 @@ def generator_forward(gen, packs: PackCache, z, noise, steps, alpha, z2=None, cr
             st = sc.adain.style
             style = linear_fwd(wlat, st.weight, st.bias, act=False)              # gan.py:66
             nw = sc.inject_noise.weights.detach().reshape(-1)
+            L = dict(k=k, j=j, sc=sc, xin=None, R=R, C=cout, which=which, noise=nz, style=style, xo=None,
+                     prev=len(layers) - 1, up=(j == 0 and k > 0))
             if k == 0 and j == 0:
                 a = _bf16(B, 4, 4, cout, device=dev)                             # gan.py:92,96-97
                 call("bg_const_noise_act", sc.conv.detach(), nz, nw, a, B, 16, cout, SLOPE)
-                xin = None
-            else:
-                ci = cin if j == 0 else cout
-                if j == 0:                                                       # gan.py:122-123
-                    xin = _bf16(B, R, R, ci, device=dev)
-                    call("bg_upsample2x_fwd", feat, xin, B, R // 2, R // 2, ci)
-                else:
-                    xin = feat
-                wf, _ = packs.conv(sc.conv.weight)
-                a, stats = conv3x3(xin, wf, ci, cout, bias=sc.conv.bias.detach(), noise=nz, noise_w=nw, act=True,
-                                   stats=1)                                      # IN sums ride in the conv epilogue
-            if xin is None:
                 stats = _f32(B, cout, 2, device=dev)
                 call("bg_in_stats", a, stats, B, R * R, cout)
-            xo = torch.empty_like(a)
-            call("bg_adain_apply", a, stats, style, xo, B, R * R, cout, IN_EPS)   # gan.py:69
-            layers.append(dict(k=k, j=j, sc=sc, xin=xin, a=a, stats=stats, style=style, R=R, C=cout, which=which,
-                               noise=nz))
-            feat = xo
-        feats.append(feat)
+                L["const"] = True
+            else:
+                ci = cin if j == 0 else cout
+                P = layers[-1]
+                if style_conv_fusable(R, cout):
+                    # gan.py:122-123 + 94-98 in ONE kernel: the previous layer's AdaIN is folded into per-sample
+                    # weights / bias rows, the upsample happens in the operand feed, IN sums come out of the epilogue
+                    wmod = _bf16(B, 9, cout, ci, device=dev)
+                    btab = _f32(B, 9, cout, device=dev)
+                    call("bg_style_modulate", sc.conv.weight.detach(), sc.conv.bias.detach(), P["stats"], P["style"],
+                         wmod, btab, B, ci, cout, P["R"] * P["R"], coef_of(sc.conv.weight), IN_EPS)
+                    a = _bf16(B, R, R, cout, device=dev)
+                    stats = _f32(B, cout, 2, device=dev)
+                    call("bg_conv_style_fprop", P["a"], wmod, btab, a, B, R, R, ci, cout, 1 if L["up"] else 0, nz, nw,
+                         SLOPE, stats)
+                    del wmod, btab
+                else:
+                    xin = layer_input(layers, len(layers), L)
+                    wf, _ = packs.conv(sc.conv.weight)
+                    a, stats = conv3x3(xin, wf, ci, cout, bias=sc.conv.bias.detach(), noise=nz, noise_w=nw, act=True,
+                                       stats=1)                                  # IN sums ride in the conv epilogue
+                    if keep_tape:
+                        L["xin"] = xin
+                L["const"] = False
+            L["a"], L["stats"] = a, stats
+            layers.append(L)
     R = 4 << (steps - 1)
     C = GEN_CHANNELS[steps - 1][1]
     rgb = gen.to_rgbs[steps - 1]
     img = _f32(B, 3, R, R, device=dev)
-    call("bg_nhwc_to_planes3", feat, rgb.weight.detach(), rgb.bias.detach(), img, B * R * R, R * R, C, 1, C,
-         coef_of(rgb.weight))
+    last = layers[-1]
+    call("bg_to_rgb_adain", last["a"], last["stats"], last["style"], rgb.weight.detach(), rgb.bias.detach(), img, B, R * R,
+         C, coef_of(rgb.weight), IN_EPS)                                         # gan.py:218,222 on AdaIN(a)
     if fade:
         Cp = GEN_CHANNELS[steps - 2][1]
         rgb_p = gen.to_rgbs[steps - 2]
         small = _f32(B, 3, R // 2, R // 2, device=dev)
-        call("bg_nhwc_to_planes3", feats[-2], rgb_p.weight.detach(), rgb_p.bias.detach(), small, B * R * R // 4,
-             R * R // 4, Cp, 1, Cp, coef_of(rgb_p.weight))
+        lp = layers[2 * (steps - 1) - 1]                                         # conv_2 of the previous block
+        call("bg_to_rgb_adain", lp["a"], lp["stats"], lp["style"], rgb_p.weight.detach(), rgb_p.bias.detach(), small, B,
+             R * R // 4, Cp, coef_of(rgb_p.weight), IN_EPS)
         out = _f32(B, 3, R, R, device=dev)
         call("bg_img_up2_lerp", small, img, out, B * 3, R // 2, R // 2, a_mix)   # gan.py:213-220
         img = out
+    if not keep_tape:
+        for L in layers:
+            L["xo"] = None
     tape = None
     if keep_tape:
-        tape = dict(maps=maps, layers=layers, feats=feats, steps=steps, fade=fade, a_mix=a_mix, B=B)
+        tape = dict(maps=maps, layers=layers, steps=steps, fade=fade, a_mix=a_mix, B=B)
     return img, tape
 
 
@@ -288,7 +331,7 @@ def generator_backward(gen, packs: PackCache, tape, g_img, need: Dict[int, bool]
     Returns (grads {id(param): tensor}, dz, dz2)."""
     dev = g_img.device
     steps, fade, B = tape["steps"], tape["fade"], tape["B"]
-    layers, feats, maps = tape["layers"], tape["feats"], tape["maps"]
+    layers, maps = tape["layers"], tape["maps"]
     grads: Dict[int, torch.Tensor] = {}
     g_img = g_img.detach().float().contiguous()
     R = 4 << (steps - 1)
@@ -319,18 +362,22 @@ def generator_backward(gen, packs: PackCache, tape, g_img, need: Dict[int, bool]
         call("bg_axpby_f32", g_img, None, g_large, g_img.numel(), a_mix, 0.0)
         g_small = _f32(B, 3, R // 2, R // 2, device=dev)
         call("bg_img_up2_bwd", g_img, g_small, B * 3, R // 2, R // 2, 1.0 - a_mix)
-        g_prev_extra = rgb_backward(gen.to_rgbs[steps - 2], feats[-2], g_small, R // 2, GEN_CHANNELS[steps - 2][1])
+        ip = 2 * (steps - 1) - 1                                   # conv_2 of the previous block feeds to_rgbs[steps-2]
+        g_prev_extra = rgb_backward(gen.to_rgbs[steps - 2], layer_output(layers, ip), g_small, R // 2,
+                                    GEN_CHANNELS[steps - 2][1])
     else:
         g_large = g_img
-    gx = rgb_backward(gen.to_rgbs[steps - 1], feats[-1], g_large, R, C)
+    gx = rgb_backward(gen.to_rgbs[steps - 1], layer_output(layers, len(layers) - 1), g_large, R, C)
+    layers[-1]["xo"] = None
 
-    for L in reversed(layers):
+    for idx in reversed(range(len(layers))):
+        L = layers[idx]
         sc, k, j, r, c = L["sc"], L["k"], L["j"], L["R"], L["C"]
         a, stats, style = L["a"], L["stats"], L["style"]
         bs = _f32(B, c, 2, device=dev)
         call("bg_adain_bwd_reduce", gx, a, stats, bs, B, r * r, c, IN_EPS)
         gpre = torch.empty_like(a)
-        is_const = L["xin"] is None
+        is_const = L["const"]
         need_b = (not is_const) and want(sc.conv.bias)
         need_nw = want(sc.inject_noise.weights)
         # bias / noise-weight gradients (gan.py:30,52) are reduced while gpre is written
@@ -363,9 +410,15 @@ def generator_backward(gen, packs: PackCache, tape, g_img, need: Dict[int, bool]
                 grads[id(sc.conv)] = dc
             gx = None
             continue
-        ci = L["xin"].shape[3]
+        ci = sc.conv.weight.shape[1]
         if want(sc.conv.weight):
-            grads[id(sc.conv.weight)] = conv_wgrad(L["xin"], gpre, sc.conv.weight)
+            # the fused forward never built this layer's input: the weight gradient is its only consumer, so it is
+            # rebuilt here (AdaIN apply [+ upsample] of the previous layer) and dropped right after
+            xin = L["xin"] if L["xin"] is not None else layer_input(layers, idx, L)
+            grads[id(sc.conv.weight)] = conv_wgrad(xin, gpre, sc.conv.weight)
+            del xin
+        L["xin"] = None
+        layers[idx - 1]["xo"] = None
         _, wd = packs.conv(sc.conv.weight)
         gxin = conv3x3(gpre, wd, c, ci)                       # data gradient: same kernel, flipped pack
         if j == 0:
