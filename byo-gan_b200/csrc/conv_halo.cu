@@ -39,7 +39,7 @@ constexpr int kHaloPix = kHalo * kHalo;         // 324
 constexpr uint32_t kPlaneBytes = 325 * 16;      // 324 pixels * 16 B, padded so the 8 planes hit distinct banks
 constexpr uint32_t kRowBytes = kHalo * 16;      // 288: SBO between 8-pixel groups (one image row down)
 constexpr int kMaxBStages = 8;
-constexpr int kMaxAStages = 3;
+constexpr int kMaxAStages = 8;
 constexpr int kMaxN = 128;
 constexpr uint32_t kTmemCols = 512;
 
@@ -136,6 +136,19 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// wait until at most n of this thread's cp.async groups are pending (n is warp-uniform, 0..7)
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {
+  switch (n) {
+    case 0: cp_async_wait<0>(); break;
+    case 1: cp_async_wait<1>(); break;
+    case 2: cp_async_wait<2>(); break;
+    case 3: cp_async_wait<3>(); break;
+    case 4: cp_async_wait<4>(); break;
+    case 5: cp_async_wait<5>(); break;
+    case 6: cp_async_wait<6>(); break;
+    default: cp_async_wait<7>(); break;
+  }
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -275,9 +288,15 @@ __device__ __forceinline__ void halo_producer_loop(const HaloParams& p, uint8_t*
   }
   int tile_lo, tile_hi, tile_step;
   tile_range(p, tile_lo, tile_hi, tile_step);
+  // Up to `depth` = a_stages - 1 stage fills are in flight as cp.async groups (one more stage is being read by the
+  // MMAs).  Fill g is published (a_full) right after fill g + depth - 1 has been issued: wait_group<depth-1> then
+  // guarantees it has landed.  Small stages (kc = 16 / 32) need this depth to keep enough bytes in flight to cover
+  // the HBM latency: 2 x 10 KB per SM sustains only ~1/3 of the HBM bandwidth.
+  const int depth = p.a_stages > 3 ? p.a_stages - 1 : 2;      // 2 or 3 stages: the original one-stage publish lag
   int stage = 0;
   uint32_t phase = 0;
-  int pending_stage = -1;
+  int issued = 0;         // fills issued so far
+  int pub_stage = 0;      // stage of the oldest unpublished fill
   for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
     const TileCoord t = decode_tile(p, tile);
     const int hb = t.h0 - 1, wb = t.w0 - 1;
@@ -305,23 +324,27 @@ __device__ __forceinline__ void halo_producer_loop(const HaloParams& p, uint8_t*
         }
       }
       cp_async_commit();
-      // publish the PREVIOUS stage: its copies have landed once at most one group (this one) is pending
-      if (pending_stage >= 0) {
-        cp_async_wait<1>();
+      ++issued;
+      if (issued >= depth) {
+        cp_async_wait_dyn(depth - 1);
         fence_proxy_async();
-        mbar_arrive(&a_full[pending_stage]);
+        mbar_arrive(&a_full[pub_stage]);
+        if (++pub_stage == p.a_stages) pub_stage = 0;
       }
-      pending_stage = stage;
       if (++stage == p.a_stages) {
         stage = 0;
         phase ^= 1u;
       }
     }
   }
-  if (pending_stage >= 0) {
-    cp_async_wait<0>();
+  // drain: the last min(issued, depth - 1) fills are still unpublished
+  int left = issued < depth - 1 ? issued : depth - 1;
+  while (left > 0) {
+    --left;
+    cp_async_wait_dyn(left);
     fence_proxy_async();
-    mbar_arrive(&a_full[pending_stage]);
+    mbar_arrive(&a_full[pub_stage]);
+    if (++pub_stage == p.a_stages) pub_stage = 0;
   }
 }
 
@@ -871,6 +894,13 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
   if (n_blocks == 1) {
     if (resident_bytes + 3u * p.a_stage_bytes <= total) {
       p.b_resident = 1;
+      // small stages (kc = 16 / 32): add stages until ~96 KB of halo fills can be in flight (HBM latency x per-SM
+      // bandwidth), as far as shared memory allows
+      if (!p.upsample) {
+        while (p.a_stages < kMaxAStages && (uint32_t)(p.a_stages - 1) * p.a_stage_bytes < 96u * 1024u &&
+               resident_bytes + (uint32_t)(p.a_stages + 1) * p.a_stage_bytes <= total)
+          ++p.a_stages;
+      }
     } else if (resident_bytes + 2u * p.a_stage_bytes <= total) {
       p.b_resident = 1;
       p.a_stages = 2;
