@@ -6,21 +6,23 @@
 // profiles/r1_ncu_full_conv_fprop_256x256.csv).  Here a CTA owns a 16x16 output tile (two M=128 MMA halves)
 // and loads the 18x18 input halo of a channel chunk ONCE; the nine taps are nine shifted VIEWS of it:
 //
-//   smem A stage = kc/8 planes, plane c8 = [18*18 halo pixels][8 channels = 16 B]   (UMMA K-major, no swizzle:
-//   a core matrix is 8 consecutive pixels x 16 B, SBO = one halo row = 288 B, LBO = plane pitch), so the view
-//   of tap (ky,kx) for MMA half h is just  start address += ((ky*18 + kx + 8h) * 16 B)  — 16-byte granular,
-//   no swizzle phase to keep consistent.
+//   smem A stage = [18*18 halo pixels][kc channels], one pixel = one 128/64/32-byte row, written by ONE TMA box load
+//   (kc x 18 x 18 x 1 of the NHWC input, out-of-bounds zero fill = the conv padding) with the matching 128/64/32-byte
+//   swizzle.  That is exactly UMMA's swizzled K-major layout with SBO = one halo row (18 pixels), and because the
+//   swizzle is a function of the absolute shared-memory address, the view of tap (ky,kx) for MMA half h is just
+//   start address += (ky*18 + kx + 8h) pixel rows.  Every operand row stays inside its own 128-byte line, so the
+//   shifted views cost no extra shared-memory wavefronts (an earlier no-swizzle plane layout needed cp.async
+//   producers and paid ~2x on the A reads: its 16-byte-shifted core matrices straddled two lines).
 //
-// The halo is written by 8 producer warps with 16-byte cp.async (zero-fill for the padding); per-thread copy
-// tables are built once per kernel and interior tiles skip every bounds test.  Weights stream by TMA
-// (128/64/32-byte swizzle) per (chunk, tap), or stay RESIDENT in shared memory for the whole kernel when the
-// layer's pack fits (all the high-resolution layers).  Accumulators: TMEM, 2 stages x 2 halves x 128 columns.
-// Epilogue: 8 warps; bias + noise + LeakyReLU (+ gate from a saved activation) in registers, then the bf16 tile
-// is transposed through a swizzled shared-memory stage so that every global store (and gate load) instruction
+// Weights stream by TMA (128/64/32-byte swizzle) per (chunk, tap), or stay RESIDENT in shared memory for the whole
+// kernel when the layer's pack fits (all the high-resolution layers).  Accumulators: TMEM, 2 stages x 2 halves x 128
+// columns.  Epilogue: 8 warps; bias + noise + LeakyReLU (+ gate from a saved activation) in registers, then the bf16
+// tile is transposed through a swizzled shared-memory stage so that every global store (and gate load) instruction
 // moves whole 128-byte lines; an optional 2x2 average pool (warp shuffles) runs before the activation.
 //
 // Warp roles: 0 = weight TMA producer, 1 = MMA issuer + TMEM allocator, 2..9 = epilogue (one 32-row TMEM
-// quarter of one MMA half each), 10..17 = halo producers.
+// quarter of one MMA half each), 10..17 = halo feed: one thread issuing the TMA box loads, or, in upsample mode,
+// all 256 threads building the bilinearly upsampled halo from a low-resolution patch.
 #include "common.cuh"
 
 #include <stdlib.h>
@@ -36,8 +38,6 @@ constexpr int kThreads = 32 * (2 + kEpiWarps + kProdWarps);
 constexpr int kTile = 16;                       // output tile edge
 constexpr int kHalo = kTile + 2;                // 18
 constexpr int kHaloPix = kHalo * kHalo;         // 324
-constexpr uint32_t kPlaneBytes = 325 * 16;      // 324 pixels * 16 B, padded so the 8 planes hit distinct banks
-constexpr uint32_t kRowBytes = kHalo * 16;      // 288: SBO between 8-pixel groups (one image row down)
 constexpr int kMaxBStages = 8;
 constexpr int kMaxAStages = 8;
 constexpr int kMaxN = 128;
@@ -49,8 +49,8 @@ struct HaloParams {
   int block_n;
   int kc, k_chunks, cpp_shift;
   int a_stages, b_stages, b_resident;
-  uint32_t a_stage_bytes, b_tile_bytes, b_tx_bytes;
-  uint32_t b_layout, b_sbo;
+  uint32_t a_stage_bytes, a_tx_bytes, b_tile_bytes, b_tx_bytes;
+  uint32_t a_layout, a_sbo, b_layout, b_sbo;
   uint32_t epi_row_bytes;               // bytes of one pixel row in the epilogue transpose stage (32 / 64 / 128)
   int num_tiles;
   const __nv_bfloat16* x;
@@ -150,6 +150,10 @@ __device__ __forceinline__ void cp_async_wait_dyn(int n) {
     default: cp_async_wait<7>(); break;
   }
 }
+// debug aid (BG_HALO_DEBUG & 4, "no halo copies"): complete the expected transaction bytes without loading anything
+__device__ __forceinline__ void mbar_arrive_tx_debug(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -163,7 +167,8 @@ __device__ __forceinline__ void mma_issue_loop(const HaloParams& p, uint8_t* a_b
                                                uint64_t* b_empty, uint64_t* a_full, uint64_t* a_empty,
                                                uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base) {
   const uint32_t idesc = umma_idesc_bf16(128, p.block_n, 0, 0);
-  const uint64_t a_desc0 = umma_desc(smem_u32(a_base), kPlaneBytes, kRowBytes, 0u);
+  constexpr uint32_t kRBU = 2u * KSTEPS;                       // one pixel row (kc bf16) in 16-byte units
+  const uint64_t a_desc0 = umma_desc(smem_u32(a_base), 16u, p.a_sbo, p.a_layout);
   const uint64_t b_desc0 = umma_desc(smem_u32(b_base), 16u, p.b_sbo, p.b_layout);
   const uint32_t a_stage_step = p.a_stage_bytes >> 4;
   const uint32_t b_tile_step = p.b_tile_bytes >> 4;
@@ -204,14 +209,14 @@ __device__ __forceinline__ void mma_issue_loop(const HaloParams& p, uint8_t* a_b
           if (!(p.debug & 2)) {
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
-              const uint64_t a_tap = a_stage + (uint64_t)((tap / 3) * kHalo + (tap % 3));
+              const uint64_t a_tap = a_stage + (uint64_t)(((tap / 3) * kHalo + (tap % 3)) * kRBU);
               const uint64_t b_tap = b_chunk + (uint64_t)((uint32_t)tap * b_tile_step);
 #pragma unroll
               for (int half = 0; half < 2; ++half) {
 #pragma unroll
                 for (int k = 0; k < KSTEPS; ++k) {
                   tc_mma_bf16(d_tmem + (uint32_t)half * 128u,
-                              a_tap + (uint64_t)(half * 8 + k * (2 * (kPlaneBytes >> 4))), b_tap + (uint64_t)(k * 2),
+                              a_tap + (uint64_t)(half * 8 * kRBU + k * 2), b_tap + (uint64_t)(k * 2),
                               idesc, (k == 0 && tap == 0) ? accum : 1u);
                 }
               }
@@ -225,7 +230,7 @@ __device__ __forceinline__ void mma_issue_loop(const HaloParams& p, uint8_t* a_b
           mbar_wait(&b_full[bstage], bphase);
           tc_fence_after();
           if (leader) {
-            const uint64_t a_tap = a_stage + (uint64_t)((tap / 3) * kHalo + (tap % 3));
+            const uint64_t a_tap = a_stage + (uint64_t)(((tap / 3) * kHalo + (tap % 3)) * kRBU);
             const uint64_t b_tap = b_desc0 + (uint64_t)((uint32_t)bstage * b_tile_step);
             if (!(p.debug & 2)) {
 #pragma unroll
@@ -233,7 +238,7 @@ __device__ __forceinline__ void mma_issue_loop(const HaloParams& p, uint8_t* a_b
 #pragma unroll
                 for (int k = 0; k < KSTEPS; ++k) {
                   tc_mma_bf16(d_tmem + (uint32_t)half * 128u,
-                              a_tap + (uint64_t)(half * 8 + k * (2 * (kPlaneBytes >> 4))), b_tap + (uint64_t)(k * 2),
+                              a_tap + (uint64_t)(half * 8 * kRBU + k * 2), b_tap + (uint64_t)(k * 2),
                               idesc, k == 0 ? accum : 1u);
                 }
               }
@@ -262,89 +267,30 @@ __device__ __forceinline__ void mma_issue_loop(const HaloParams& p, uint8_t* a_b
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Halo producers (warps 10..17).  CPP_SHIFT = log2(16-byte channel units per pixel in a chunk) = 3 / 2 / 1 for
-// kc = 64 / 32 / 16.  Thread pt copies units u = pt + 256 i; for each it keeps, in registers, the element offset
-// relative to the halo origin and the packed (row, column), so an interior tile costs one 64-bit add and one
-// LDGSTS per 16 bytes.
+// Halo feed, plain mode: one thread issues one TMA box load (kc channels x 18 x 18 pixels x 1 image) per (tile,
+// channel chunk); coordinates start at (w0-1, h0-1), the out-of-bounds part of the box is zero-filled by the TMA
+// unit — that IS the convolution's padding.
 // ---------------------------------------------------------------------------------------------------------
-template <int CPP_SHIFT>
-__device__ __forceinline__ void halo_producer_loop(const HaloParams& p, uint8_t* a_base, uint64_t* a_full,
-                                                   uint64_t* a_empty, int pt) {
-  constexpr int kUnits = kHaloPix << CPP_SHIFT;
-  constexpr int kIters = (kUnits + kProdThreads - 1) / kProdThreads;     // 11 / 6 / 3
-  int rel[kIters];        // element offset of the unit relative to the halo origin pixel (h0-1, w0-1), channel 0
-  int hyx[kIters];        // (hy << 8) | hx, or -1 for the padding units past the end of the table
-  uint32_t soff[kIters];  // byte offset inside the A stage
-#pragma unroll
-  for (int i = 0; i < kIters; ++i) {
-    const int u = pt + i * kProdThreads;
-    const int px = u >> CPP_SHIFT;
-    const int c8 = u & ((1 << CPP_SHIFT) - 1);
-    const int hy = px / kHalo, hx = px - hy * kHalo;
-    const bool live = u < kUnits;
-    rel[i] = (hy * p.W + hx) * p.Cin + c8 * 8;
-    hyx[i] = live ? ((hy << 8) | hx) : -1;
-    soff[i] = (uint32_t)c8 * kPlaneBytes + (uint32_t)px * 16u;
-  }
+__device__ __forceinline__ void halo_tma_loop(const HaloParams& p, const CUtensorMap* tmap_x, uint8_t* a_base,
+                                              uint64_t* a_full, uint64_t* a_empty) {
   int tile_lo, tile_hi, tile_step;
   tile_range(p, tile_lo, tile_hi, tile_step);
-  // Up to `depth` = a_stages - 1 stage fills are in flight as cp.async groups (one more stage is being read by the
-  // MMAs).  Fill g is published (a_full) right after fill g + depth - 1 has been issued: wait_group<depth-1> then
-  // guarantees it has landed.  Small stages (kc = 16 / 32) need this depth to keep enough bytes in flight to cover
-  // the HBM latency: 2 x 10 KB per SM sustains only ~1/3 of the HBM bandwidth.
-  const int depth = p.a_stages > 3 ? p.a_stages - 1 : 2;      // 2 or 3 stages: the original one-stage publish lag
   int stage = 0;
   uint32_t phase = 0;
-  int issued = 0;         // fills issued so far
-  int pub_stage = 0;      // stage of the oldest unpublished fill
   for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
     const TileCoord t = decode_tile(p, tile);
-    const int hb = t.h0 - 1, wb = t.w0 - 1;
-    // pointer to (n, h0-1, w0-1, 0); only dereferenced where in bounds
-    const __nv_bfloat16* org = p.x + ((int64_t)t.n * p.H * p.W + (int64_t)hb * p.W + wb) * p.Cin;
-    const bool interior = (hb >= 0) && (wb >= 0) && (t.h0 + kTile < p.H) && (t.w0 + kTile < p.W);
     for (int kcx = 0; kcx < p.k_chunks; ++kcx) {
       mbar_wait(&a_empty[stage], phase ^ 1u);
-      const uint32_t sdst = smem_u32(a_base + (size_t)stage * p.a_stage_bytes);
-      const __nv_bfloat16* cb = org + kcx * p.kc;
-      if (!(p.debug & 4)) {
-        if (interior) {
-#pragma unroll
-          for (int i = 0; i < kIters; ++i)
-            if (i < kIters - 1 || hyx[i] >= 0) cp_async_16_full(sdst + soff[i], cb + rel[i]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < kIters; ++i) {
-            if (i < kIters - 1 || hyx[i] >= 0) {
-              const int h = hb + (hyx[i] >> 8), w = wb + (hyx[i] & 255);
-              const bool ok = ((unsigned)h < (unsigned)p.H) && ((unsigned)w < (unsigned)p.W);
-              cp_async_16(sdst + soff[i], ok ? (const void*)(cb + rel[i]) : (const void*)p.x, ok ? 16u : 0u);
-            }
-          }
-        }
-      }
-      cp_async_commit();
-      ++issued;
-      if (issued >= depth) {
-        cp_async_wait_dyn(depth - 1);
-        fence_proxy_async();
-        mbar_arrive(&a_full[pub_stage]);
-        if (++pub_stage == p.a_stages) pub_stage = 0;
-      }
+      mbar_expect_tx(&a_full[stage], p.a_tx_bytes);
+      if (!(p.debug & 4))
+        tma_load_4d(tmap_x, &a_full[stage], a_base + (size_t)stage * p.a_stage_bytes, kcx * p.kc, t.w0 - 1, t.h0 - 1, t.n);
+      else
+        mbar_arrive_tx_debug(&a_full[stage], p.a_tx_bytes);
       if (++stage == p.a_stages) {
         stage = 0;
         phase ^= 1u;
       }
     }
-  }
-  // drain: the last min(issued, depth - 1) fills are still unpublished
-  int left = issued < depth - 1 ? issued : depth - 1;
-  while (left > 0) {
-    --left;
-    cp_async_wait_dyn(left);
-    fence_proxy_async();
-    mbar_arrive(&a_full[pub_stage]);
-    if (++pub_stage == p.a_stages) pub_stage = 0;
   }
 }
 
@@ -370,7 +316,8 @@ __device__ __forceinline__ void halo_producer_upsample(const HaloParams& p, uint
   constexpr int kLoadIters = (kPatchUnits + kProdThreads - 1) / kProdThreads;     // 4 / 2 / 1
   constexpr int kQuadUnits = 81 * kCpp;
   constexpr int kQuadIters = (kQuadUnits + kProdThreads - 1) / kProdThreads;      // 3 / 2 / 1
-  constexpr uint32_t kPixBytes = 16u * kCpp;                                        // one patch pixel (kc channels)
+  constexpr uint32_t kPixBytes = 16u * kCpp;                                        // one pixel row (kc channels)
+  constexpr uint32_t kSwzMask = kCpp - 1u;                                          // 7 / 3 / 1: SWIZZLE_128B / 64B / 32B
   const int HL = p.H >> 1, WL = p.W >> 1;
   int tile_lo, tile_hi, tile_step;
   tile_range(p, tile_lo, tile_hi, tile_step);
@@ -449,11 +396,14 @@ __device__ __forceinline__ void halo_producer_upsample(const HaloParams& p, uint
           const bool rA = (unsigned)(hb + hy) < (unsigned)p.H, rB = (unsigned)(hb + hy + 1) < (unsigned)p.H;
           const bool cP = (unsigned)(wb + hx) < (unsigned)p.W, cQ = (unsigned)(wb + hx + 1) < (unsigned)p.W;
           const uint4 z = make_uint4(0, 0, 0, 0);
-          const uint32_t so = sdst + (uint32_t)c8 * kPlaneBytes + (uint32_t)(hy * kHalo + hx) * 16u;
-          sts128(so, (rA && cP) ? make_uint4(oAP[0], oAP[1], oAP[2], oAP[3]) : z);
-          sts128(so + 16u, (rA && cQ) ? make_uint4(oAQ[0], oAQ[1], oAQ[2], oAQ[3]) : z);
-          sts128(so + kRowBytes, (rB && cP) ? make_uint4(oBP[0], oBP[1], oBP[2], oBP[3]) : z);
-          sts128(so + kRowBytes + 16u, (rB && cQ) ? make_uint4(oBQ[0], oBQ[1], oBQ[2], oBQ[3]) : z);
+          // A stage = [halo pixel][kc channels] with the 128/64/32-byte swizzle UMMA expects: the 16-byte chunk index
+          // is XORed with address bits 7.. (stage bases are 1024-byte aligned, so offsets can stand in for addresses)
+          const uint32_t l0 = (uint32_t)(hy * kHalo + hx) * kPixBytes + (uint32_t)c8 * 16u;
+          const uint32_t l1 = l0 + kPixBytes, l2 = l0 + kHalo * kPixBytes, l3 = l2 + kPixBytes;
+          sts128(sdst + (l0 ^ (((l0 >> 7) & kSwzMask) << 4)), (rA && cP) ? make_uint4(oAP[0], oAP[1], oAP[2], oAP[3]) : z);
+          sts128(sdst + (l1 ^ (((l1 >> 7) & kSwzMask) << 4)), (rA && cQ) ? make_uint4(oAQ[0], oAQ[1], oAQ[2], oAQ[3]) : z);
+          sts128(sdst + (l2 ^ (((l2 >> 7) & kSwzMask) << 4)), (rB && cP) ? make_uint4(oBP[0], oBP[1], oBP[2], oBP[3]) : z);
+          sts128(sdst + (l3 ^ (((l3 >> 7) & kSwzMask) << 4)), (rB && cQ) ? make_uint4(oBQ[0], oBQ[1], oBQ[2], oBQ[3]) : z);
         }
       }
       fence_proxy_async();
@@ -523,7 +473,8 @@ __device__ __forceinline__ void stats_flush(const HaloParams& p, float* slices, 
 // ---------------------------------------------------------------------------------------------------------
 template <bool kStats, bool kUp>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const HaloParams p) {
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
+                 const HaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -553,12 +504,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const HaloParams p)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_x);
     for (int s = 0; s < kMaxBStages; ++s) {
       mbar_init(&b_full[s], 1);
       mbar_init(&b_empty[s], 1);
     }
     for (int s = 0; s < kMaxAStages; ++s) {
-      mbar_init(&a_full[s], kProdThreads);
+      mbar_init(&a_full[s], kUp ? kProdThreads : 1);
       mbar_init(&a_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -814,9 +766,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const HaloParams p)
       if (p.cpp_shift == 3) halo_producer_upsample<3>(p, a_base, patch_base, a_full, a_empty, pt);
       else if (p.cpp_shift == 2) halo_producer_upsample<2>(p, a_base, patch_base, a_full, a_empty, pt);
       else halo_producer_upsample<1>(p, a_base, patch_base, a_full, a_empty, pt);
-    } else if (p.cpp_shift == 3) halo_producer_loop<3>(p, a_base, a_full, a_empty, pt);
-    else if (p.cpp_shift == 2) halo_producer_loop<2>(p, a_base, a_full, a_empty, pt);
-    else halo_producer_loop<1>(p, a_base, a_full, a_empty, pt);
+    } else if (pt == 0) {
+      halo_tma_loop(p, &tmap_x, a_base, a_full, a_empty);
+    }
   }
 
   tc_fence_before();
@@ -878,7 +830,10 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
   p.b_sbo = 8u * row_bytes;
   p.b_tx_bytes = (uint32_t)p.block_n * row_bytes;
   p.b_tile_bytes = (p.b_tx_bytes + 1023u) & ~1023u;
-  p.a_stage_bytes = (uint32_t)(p.kc / 8) * kPlaneBytes;
+  p.a_layout = p.b_layout;                                   // same row width (kc bf16) on both operands
+  p.a_sbo = (uint32_t)kHalo * row_bytes;                     // next 8-pixel group = one halo row down
+  p.a_tx_bytes = (uint32_t)kHaloPix * row_bytes;
+  p.a_stage_bytes = (p.a_tx_bytes + 1023u) & ~1023u;
   p.epi_row_bytes = (uint32_t)(bn_ch >= 64 ? 64 : bn_ch) * 2u;
   const uint32_t epi_bytes = (uint32_t)kEpiWarps * 32u * p.epi_row_bytes + 128u;
   const uint32_t stat_bytes = (stats != nullptr) ? (uint32_t)kEpiWarps * (uint32_t)Cout * 2u * 4u : 0u;
@@ -950,6 +905,16 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
     uint32_t box[4] = {(uint32_t)p.kc, (uint32_t)p.block_n, 1u, 1u};
     if (make_tmap_bf16(&tmw, wpack, 4, dims, str, box, (int)row_bytes) != 0) return 1;
   }
+  CUtensorMap tmx;
+  {
+    // plain mode: NHWC input as (Cin, W, H, N); the halo box starts at (w0-1, h0-1) and relies on OOB zero fill.
+    // (upsample mode builds the halo with the producer warps; the map is still encoded so the kernel signature is one)
+    const int Hx = upsample ? H / 2 : H, Wx = upsample ? W / 2 : W;
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Wx, (uint64_t)Hx, (uint64_t)N};
+    uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)Wx * Cin * 2, (uint64_t)Hx * Wx * Cin * 2};
+    uint32_t box[4] = {(uint32_t)p.kc, (uint32_t)(upsample ? 8 : kHalo), (uint32_t)(upsample ? 8 : kHalo), 1u};
+    if (make_tmap_bf16(&tmx, x, 4, dims, str, box, (int)row_bytes) != 0) return 1;
+  }
   const size_t b_tiles = p.b_resident ? (size_t)p.k_chunks * 9 : (size_t)p.b_stages;
   const size_t smem_bytes = b_tiles * p.b_tile_bytes + (size_t)p.a_stages * p.a_stage_bytes + patch_total + epi_bytes +
                             aux_bytes + 1024;
@@ -963,10 +928,10 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
     attr_set = true;
   }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  if (p.stats_mode && p.upsample) conv_halo_kernel<true, true><<<grid, kThreads, smem_bytes, stream>>>(tmw, p);
-  else if (p.stats_mode) conv_halo_kernel<true, false><<<grid, kThreads, smem_bytes, stream>>>(tmw, p);
-  else if (p.upsample) conv_halo_kernel<false, true><<<grid, kThreads, smem_bytes, stream>>>(tmw, p);
-  else conv_halo_kernel<false, false><<<grid, kThreads, smem_bytes, stream>>>(tmw, p);
+  if (p.stats_mode && p.upsample) conv_halo_kernel<true, true><<<grid, kThreads, smem_bytes, stream>>>(tmw, tmx, p);
+  else if (p.stats_mode) conv_halo_kernel<true, false><<<grid, kThreads, smem_bytes, stream>>>(tmw, tmx, p);
+  else if (p.upsample) conv_halo_kernel<false, true><<<grid, kThreads, smem_bytes, stream>>>(tmw, tmx, p);
+  else conv_halo_kernel<false, false><<<grid, kThreads, smem_bytes, stream>>>(tmw, tmx, p);
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
