@@ -20,9 +20,11 @@
 // tile is transposed through a swizzled shared-memory stage so that every global store (and gate load) instruction
 // moves whole 128-byte lines; an optional 2x2 average pool (warp shuffles) runs before the activation.
 //
-// Warp roles: 0 = weight TMA producer, 1 = MMA issuer + TMEM allocator, 2..9 = epilogue (one 32-row TMEM
-// quarter of one MMA half each), 10..17 = halo feed: one thread issuing the TMA box loads, or, in upsample mode,
-// all 256 threads building the bilinearly upsampled halo from a low-resolution patch.
+// Warp roles: 0 = weight TMA producer, 1 = MMA issuer + TMEM allocator, 2..9 = epilogue set 0 (one 32-row TMEM
+// quarter of one MMA half each), 10..17 = epilogue set 1 in plain mode (the epilogue of a tile is a latency chain
+// — TMEM load, math, transpose, stores — that is longer than the tile's MMAs on most layers, so two sets alternate
+// tiles, each owning one accumulator stage) or, in upsample mode, the 256 threads that build the bilinearly
+// upsampled halo from a low-resolution patch; 18 = halo TMA issuer (plain mode).
 #include "common.cuh"
 
 #include <stdlib.h>
@@ -31,10 +33,11 @@ namespace bg {
 
 namespace {
 
-constexpr int kEpiWarps = 8;                     // warps 2..5 drain MMA half 0, warps 6..9 half 1
-constexpr int kProdWarps = 8;
+constexpr int kEpiWarps = 8;                     // one epilogue SET: 4 TMEM lane quarters x 2 MMA halves
+constexpr int kEpiSets = 2;                      // plain mode: set s drains accumulator stage s (every other tile)
+constexpr int kProdWarps = 8;                    // upsample mode: these warps build the halo instead of being set 1
 constexpr int kProdThreads = 32 * kProdWarps;
-constexpr int kThreads = 32 * (2 + kEpiWarps + kProdWarps);
+constexpr int kThreads = 32 * (2 + kEpiWarps * kEpiSets + 1);   // + warp 18: halo TMA issuer (plain mode)
 constexpr int kTile = 16;                       // output tile edge
 constexpr int kHalo = kTile + 2;                // 18
 constexpr int kHaloPix = kHalo * kHalo;         // 324
@@ -70,6 +73,7 @@ struct HaloParams {
   int stats_mode;
   int n_blocks;
   int contig;     // tile order, see tile_range()
+  int epi_sets;   // 1 or 2 epilogue warp sets (2: set s drains accumulator stage s)
   // StyleGAN generator forward (gan.py:89-98,118-127) with the layer's AdaIN folded into the operands:
   //   per_sample_w: the weight pack is [N][9][Cout][Cin] (instance-norm scale * style gamma folded in per sample);
   //   bias_tab:     fp32 [N][9][Cout] replaces bias: bias + the conv of the per-channel AdaIN shift, one row per border
@@ -211,10 +215,12 @@ __device__ __forceinline__ void mma_issue_loop(const HaloParams& p, uint8_t* a_b
             for (int tap = 0; tap < 9; ++tap) {
               const uint64_t a_tap = a_stage + (uint64_t)(((tap / 3) * kHalo + (tap % 3)) * kRBU);
               const uint64_t b_tap = b_chunk + (uint64_t)((uint32_t)tap * b_tile_step);
+              // alternate the two accumulators (MMA halves): back-to-back MMAs into the SAME accumulator serialise
+              // on the tensor pipe's latency (~60 clk), which is longer than a small-N MMA itself
 #pragma unroll
-              for (int half = 0; half < 2; ++half) {
+              for (int k = 0; k < KSTEPS; ++k) {
 #pragma unroll
-                for (int k = 0; k < KSTEPS; ++k) {
+                for (int half = 0; half < 2; ++half) {
                   tc_mma_bf16(d_tmem + (uint32_t)half * 128u,
                               a_tap + (uint64_t)(half * 8 * kRBU + k * 2), b_tap + (uint64_t)(k * 2),
                               idesc, (k == 0 && tap == 0) ? accum : 1u);
@@ -234,9 +240,9 @@ __device__ __forceinline__ void mma_issue_loop(const HaloParams& p, uint8_t* a_b
             const uint64_t b_tap = b_desc0 + (uint64_t)((uint32_t)bstage * b_tile_step);
             if (!(p.debug & 2)) {
 #pragma unroll
-              for (int half = 0; half < 2; ++half) {
+              for (int k = 0; k < KSTEPS; ++k) {
 #pragma unroll
-                for (int k = 0; k < KSTEPS; ++k) {
+                for (int half = 0; half < 2; ++half) {
                   tc_mma_bf16(d_tmem + (uint32_t)half * 128u,
                               a_tap + (uint64_t)(half * 8 * kRBU + k * 2), b_tap + (uint64_t)(k * 2),
                               idesc, k == 0 ? accum : 1u);
@@ -451,9 +457,10 @@ __device__ __forceinline__ void stats_round(float* slice, float (&sa)[8], float 
   for (int j = 0; j < 8; ++j) sa[j] = sq[j] = 0.f;
 }
 
-// All 8 epilogue warps call this at the same point of their (identical) tile sequence.
-__device__ __forceinline__ void stats_flush(const HaloParams& p, float* slices, int et, int n) {
-  asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+// All 8 warps of an epilogue SET call this at the same point of their (identical) tile sequence; `slices` are the
+// set's own 8 slices, `bar_id` its named barrier.
+__device__ __forceinline__ void stats_flush(const HaloParams& p, float* slices, int et, int n, int bar_id) {
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * kEpiWarps) : "memory");
   const int len = p.Cout * 2;
   for (int i = et; i < len; i += 32 * kEpiWarps) {
     float v = 0.f;
@@ -465,12 +472,9 @@ __device__ __forceinline__ void stats_flush(const HaloParams& p, float* slices, 
     if (p.stats_mode == 1) atomicAdd(p.stats + (size_t)n * len + i, v);
     else if ((i & 1) == 0) atomicAdd(p.stats + (i >> 1), v);
   }
-  asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * kEpiWarps) : "memory");
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// kernel
-// ---------------------------------------------------------------------------------------------------------
 template <bool kStats, bool kUp>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
@@ -487,7 +491,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
   patch_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(patch_base) + 127) & ~uintptr_t(127));
   uint8_t* epi_base = patch_base + (p.upsample ? (size_t)kPatchStages * p.patch_bytes : 0);
   epi_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(epi_base) + 127) & ~uintptr_t(127));
-  uint8_t* aux = epi_base + (size_t)kEpiWarps * 32 * p.epi_row_bytes;
+  const int kEpiWarpsAll = kUp ? kEpiWarps : kEpiWarps * p.epi_sets;
+  uint8_t* aux = epi_base + (size_t)kEpiWarpsAll * 32 * p.epi_row_bytes;
   uint64_t* b_full = reinterpret_cast<uint64_t*>(aux);
   uint64_t* b_empty = b_full + kMaxBStages;
   uint64_t* a_full = b_empty + kMaxBStages;
@@ -523,13 +528,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
-  if (warp >= 2 && warp < 2 + kEpiWarps) {
-    for (int c = threadIdx.x - 64; c < p.Cout; c += 32 * kEpiWarps) {
+  if (warp >= 2 && warp < 2 + kEpiWarpsAll) {
+    for (int c = threadIdx.x - 64; c < p.Cout; c += 32 * kEpiWarpsAll) {
       bias_s[c] = p.bias ? p.bias[c] : 0.f;
       nw_s[c] = p.noise_w ? p.noise_w[c] : 0.f;
     }
     if (kStats)
-      for (int i = threadIdx.x - 64; i < kEpiWarps * p.Cout * 2; i += 32 * kEpiWarps) stat_s[i] = 0.f;
+      for (int i = threadIdx.x - 64; i < kEpiWarpsAll * p.Cout * 2; i += 32 * kEpiWarpsAll) stat_s[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -583,12 +588,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     if (p.kc == 64) mma_issue_loop<4>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
     else if (p.kc == 32) mma_issue_loop<2>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
     else mma_issue_loop<1>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
-  } else if (warp < 2 + kEpiWarps) {
+  } else if (warp < 2 + kEpiWarpsAll) {
     // ------------------------------ epilogue ------------------------------
     // Warp e = warp - 2: TMEM lane quarter q = warp & 3 (hardware rule), MMA half = e / 4.  Lane i holds MMA row
     // m = 32q + i = pixel (image row g = m / 8, column r = m % 8 of the half's 8-wide segment).
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int eset = (warp - 2) >> 3;                  // 0, or 1 for the second set (plain mode)
+    const int half = ((warp - 2) >> 2) & 1;
     const int g = (q * 32 + lane) >> 3, r = lane & 7;
     const bool pool_writer = ((lane & 1) == 0) && ((lane & 8) == 0);
     // transpose stage of this warp: 32 pixel rows x epi_row_bytes, 16-byte chunks XOR-swizzled by row so that both
@@ -605,15 +611,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     // one transpose round per tile and a fixed channel range: the lane partials stay in registers across tiles
     const bool st_regs = st_on && p.n_blocks == 1 && p.block_n <= round_cols;
     float* st_slice = stat_s + (size_t)(warp - 2) * p.Cout * 2;
+    float* st_set = stat_s + (size_t)eset * kEpiWarps * p.Cout * 2;
+    const int st_et = (int)threadIdx.x - 64 - eset * 32 * kEpiWarps;
     float sa[8], sq[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) sa[j] = sq[j] = 0.f;
     int st_n = -1;
-    for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
+    // plain mode: set `eset` takes every other tile of the CTA's sequence and always drains accumulator stage `eset`
+    // (the MMA warp alternates stages tile by tile); upsample mode: the single set alternates stages itself.
+    const int kSets = kUp ? 1 : p.epi_sets;
+    if (kSets == 2) acc = eset;
+    for (int tile = tile_lo + (kSets == 2 ? eset * tile_step : 0); tile < tile_hi; tile += tile_step * kSets) {
       const TileCoord t = decode_tile(p, tile);
       if (st_on && p.stats_mode == 1 && st_n >= 0 && st_n != t.n) {
         if (st_regs) stats_round(st_slice, sa, sq, cpr_shift, lane, 0);
-        stats_flush(p, stat_s, threadIdx.x - 64, st_n);
+        stats_flush(p, st_set, st_et, st_n, 1 + eset);
       }
       st_n = t.n;
       const int h = t.h0 + g, w = t.w0 + half * 8 + r;
@@ -752,22 +764,28 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
+      if (kSets == 2) {
+        acc_phase ^= 1u;
+      } else {
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
     }
     if (st_on && st_n >= 0) {
       if (st_regs) stats_round(st_slice, sa, sq, cpr_shift, lane, 0);
-      stats_flush(p, stat_s, threadIdx.x - 64, st_n);
+      stats_flush(p, st_set, st_et, st_n, 1 + eset);
     }
   } else {
     // ------------------------------ halo producers (cp.async, zero-fill padding) ------------------------------
-    const int pt = threadIdx.x - 32 * (2 + kEpiWarps);       // 0..255
     if (kUp) {
-      if (p.cpp_shift == 3) halo_producer_upsample<3>(p, a_base, patch_base, a_full, a_empty, pt);
-      else if (p.cpp_shift == 2) halo_producer_upsample<2>(p, a_base, patch_base, a_full, a_empty, pt);
-      else halo_producer_upsample<1>(p, a_base, patch_base, a_full, a_empty, pt);
-    } else if (pt == 0) {
-      halo_tma_loop(p, &tmap_x, a_base, a_full, a_empty);
+      if (warp < 2 + kEpiWarps + kProdWarps) {
+        const int pt = threadIdx.x - 32 * (2 + kEpiWarps);       // 0..255
+        if (p.cpp_shift == 3) halo_producer_upsample<3>(p, a_base, patch_base, a_full, a_empty, pt);
+        else if (p.cpp_shift == 2) halo_producer_upsample<2>(p, a_base, patch_base, a_full, a_empty, pt);
+        else halo_producer_upsample<1>(p, a_base, patch_base, a_full, a_empty, pt);
+      }
+    } else if (warp == 2 + kEpiWarps * kEpiSets && lane == 0) {
+      halo_tma_loop(p, &tmap_x, a_base, a_full, a_empty);        // warp 18
     }
   }
 
@@ -835,45 +853,73 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
   p.a_tx_bytes = (uint32_t)kHaloPix * row_bytes;
   p.a_stage_bytes = (p.a_tx_bytes + 1023u) & ~1023u;
   p.epi_row_bytes = (uint32_t)(bn_ch >= 64 ? 64 : bn_ch) * 2u;
-  const uint32_t epi_bytes = (uint32_t)kEpiWarps * 32u * p.epi_row_bytes + 128u;
-  const uint32_t stat_bytes = (stats != nullptr) ? (uint32_t)kEpiWarps * (uint32_t)Cout * 2u * 4u : 0u;
-  const uint32_t aux_bytes = 8 * (2 * kMaxBStages + 2 * kMaxAStages + 4) + 16 + 2 * 512 * 4 + 64 + stat_bytes;
   p.upsample = upsample ? 1 : 0;
   p.patch_bytes = (uint32_t)(kPatch * kPatch) * (uint32_t)p.kc * 2u;
   const uint32_t patch_total = p.upsample ? (uint32_t)kPatchStages * p.patch_bytes + 128u : 0u;
-  const uint32_t total = 227u * 1024u - 1024u - aux_bytes - epi_bytes - patch_total;
   const uint32_t resident_bytes = (uint32_t)p.k_chunks * 9u * p.b_tile_bytes;
-  // prefer resident weights (3 halo stages if they fit, else 2); otherwise stream the weights past 3 halo stages
-  p.a_stages = 3;
-  p.b_resident = 0;
-  if (n_blocks == 1) {
-    if (resident_bytes + 3u * p.a_stage_bytes <= total) {
-      p.b_resident = 1;
-      // small stages (kc = 16 / 32): add stages until ~96 KB of halo fills can be in flight (HBM latency x per-SM
-      // bandwidth), as far as shared memory allows
-      if (!p.upsample) {
-        while (p.a_stages < kMaxAStages && (uint32_t)(p.a_stages - 1) * p.a_stage_bytes < 96u * 1024u &&
-               resident_bytes + (uint32_t)(p.a_stages + 1) * p.a_stage_bytes <= total)
-          ++p.a_stages;
+  // Shared-memory plan.  Two epilogue sets (plain mode) double the transpose stages and the stats slices; fall back
+  // to one set when that would cost the weight residency or does not fit at all.
+  struct Plan {
+    bool ok;
+    int sets, a_stages, b_stages, resident;
+    uint32_t epi_bytes, aux_bytes;
+  };
+  auto make_plan = [&](int sets) {
+    Plan pl;
+    memset(&pl, 0, sizeof(pl));
+    pl.sets = sets;
+    const uint32_t epi_warps = (uint32_t)(kEpiWarps * sets);
+    pl.epi_bytes = epi_warps * 32u * p.epi_row_bytes + 128u;
+    const uint32_t stat_bytes = (stats != nullptr) ? epi_warps * (uint32_t)Cout * 2u * 4u : 0u;
+    pl.aux_bytes = 8 * (2 * kMaxBStages + 2 * kMaxAStages + 4) + 16 + 2 * 512 * 4 + 64 + stat_bytes;
+    const uint32_t fixed = 1024u + pl.aux_bytes + pl.epi_bytes + patch_total;
+    if (fixed + 2u * p.a_stage_bytes + 2u * p.b_tile_bytes > 227u * 1024u) return pl;
+    const uint32_t total = 227u * 1024u - fixed;
+    // prefer resident weights (3 halo stages if they fit, else 2); otherwise stream the weights past 3 halo stages
+    pl.a_stages = 3;
+    if (n_blocks == 1) {
+      if (resident_bytes + 3u * p.a_stage_bytes <= total) {
+        pl.resident = 1;
+        // small stages (kc = 16 / 32): more stages, until ~96 KB of halo loads can be in flight (HBM latency x per-SM
+        // bandwidth), as far as shared memory allows
+        if (!p.upsample) {
+          while (pl.a_stages < kMaxAStages && (uint32_t)(pl.a_stages - 1) * p.a_stage_bytes < 96u * 1024u &&
+                 resident_bytes + (uint32_t)(pl.a_stages + 1) * p.a_stage_bytes <= total)
+            ++pl.a_stages;
+        }
+      } else if (resident_bytes + 2u * p.a_stage_bytes <= total) {
+        pl.resident = 1;
+        pl.a_stages = 2;
       }
-    } else if (resident_bytes + 2u * p.a_stage_bytes <= total) {
-      p.b_resident = 1;
-      p.a_stages = 2;
     }
-  }
-  if (p.b_resident) {
-    p.b_stages = 1;
-  } else {
-    // streamed weights: 3 halo stages when at least 3 weight stages still fit, else 2 halo stages
-    int st = total > 3u * p.a_stage_bytes ? (int)((total - 3u * p.a_stage_bytes) / p.b_tile_bytes) : 0;
-    if (st < 3) {
-      p.a_stages = 2;
-      st = total > 2u * p.a_stage_bytes ? (int)((total - 2u * p.a_stage_bytes) / p.b_tile_bytes) : 0;
+    if (pl.resident) {
+      pl.b_stages = 1;
+      pl.ok = true;
+    } else {
+      // streamed weights: 3 halo stages when at least 3 weight stages still fit, else 2 halo stages
+      int st = total > 3u * p.a_stage_bytes ? (int)((total - 3u * p.a_stage_bytes) / p.b_tile_bytes) : 0;
+      if (st < 3) {
+        pl.a_stages = 2;
+        st = total > 2u * p.a_stage_bytes ? (int)((total - 2u * p.a_stage_bytes) / p.b_tile_bytes) : 0;
+      }
+      if (st > kMaxBStages) st = kMaxBStages;
+      pl.b_stages = st;
+      pl.ok = st >= 2;
     }
-    if (st > kMaxBStages) st = kMaxBStages;
-    BG_REQUIRE(st >= 2, "conv_halo: weight tile does not fit shared memory");
-    p.b_stages = st;
+    return pl;
+  };
+  Plan plan = make_plan(1);
+  if (!p.upsample) {
+    const Plan two = make_plan(kEpiSets);
+    if (two.ok && (two.resident || !plan.resident || !plan.ok)) plan = two;
   }
+  const bool planned = plan.ok;
+  const uint32_t epi_bytes = plan.epi_bytes, aux_bytes = plan.aux_bytes;
+  p.epi_sets = plan.sets;
+  p.a_stages = plan.a_stages;
+  p.b_stages = plan.b_stages;
+  p.b_resident = plan.resident;
+  BG_REQUIRE(planned, "conv_halo: weight tile does not fit shared memory");
   p.num_tiles = (W / kTile) * (H / kTile) * N * n_blocks;
   p.x = reinterpret_cast<const __nv_bfloat16*>(x);
   p.bias = bias; p.noise = noise; p.noise_w = noise_w;
