@@ -119,6 +119,36 @@ class Trainer:
         self.sync = sync_cls()
         self.critic._grad_ready_hook = self.sync.ready
 
+    def _read(self, loss, slot):
+        """Device->host read of a loss (train.py:191,219 do .item() for the progress bar).  The copy into pinned
+        memory is queued right behind the step's kernels and the VALUE is picked up one iteration later, when the
+        copy has long finished: the host never drains the launch queue, the losses still arrive every step."""
+        if not hasattr(self, "_pinned"):
+            self._pinned = [torch.zeros(2, 1).pin_memory() for _ in range(2)]     # [parity][slot]
+            self._events = [[None, None], [None, None]]
+            self._parity = 0
+        par = self._parity
+        self._pinned[par][slot].copy_(loss.detach().reshape(1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._events[par][slot] = ev
+        prev = self._events[par ^ 1][slot]
+        val = None
+        if prev is not None:
+            prev.synchronize()                              # completed an iteration ago
+            val = float(self._pinned[par ^ 1][slot])
+        if slot == 1:
+            self._parity ^= 1
+        return val
+
+    def flush_reads(self):
+        """Wait for the loss copies still in flight (end of a timed region)."""
+        for row in getattr(self, "_events", []):
+            for ev in row:
+                if ev is not None:
+                    ev.synchronize()
+        return [float(v) for buf in getattr(self, "_pinned", []) for v in buf]
+
     @staticmethod
     def _set_requires_grad(model, flag):                     # helper.py:48-50
         for p in model.parameters():
@@ -139,7 +169,7 @@ class Trainer:
         c_loss = critic.get_r1_loss(pf, pr, real_im, fake, steps, alpha, LAMBDA)
         self.sync.finish()
         self.critic_opt.step()
-        c_val = c_loss.item() if read_losses else None
+        c_val = self._read(c_loss, 0) if read_losses else None
         # ---- generator step (train.py:193-219)
         self._set_requires_grad(critic, False)
         self._set_requires_grad(gen, True)
@@ -153,8 +183,20 @@ class Trainer:
         self.sync.ready_all(p for p in gen.parameters() if p.grad is not None)
         self.sync.finish()
         self.gen_opt.step()
-        g_val = g_loss.item() if read_losses else None
+        g_val = self._read(g_loss, 1) if read_losses else None
         return c_val, g_val
+
+
+def conv_bytes(name, args):
+    """Algorithmic HBM bytes of one conv launch (bf16 maps read once and written once; weights excluded):
+    2 * N * (Cin * Hin * Win + Cout * Hout * Wout); + the gate map for a gated pass is not counted."""
+    n, h, w, ci, co = args[:5]
+    hin = win = None
+    if name == "bg_conv_style_fprop" and args[5]:          # upsample flag: the input is the quarter-size map
+        hin, win = h // 2, w // 2
+    hin, win = hin or h, win or w
+    ho, wo = (h // 2, w // 2) if name == "bg_conv_pool_fprop" else (h, w)
+    return 2.0 * n * (ci * hin * win + co * ho * wo)
 
 
 def conv_flops(args):
@@ -204,6 +246,8 @@ def run_b200(args):
                 tr.iteration(real, zz[0], zz[1], read_losses=True)
             else:
                 tr.iteration(dev_real[j].clone(), dev_z[j][0].clone(), dev_z[j][1].clone(), read_losses=False)
+        if from_host:
+            tr.flush_reads()                                 # the last iteration's losses, inside the timed region
         t1.record()
         barrier()
         ms = torch.tensor([t0.elapsed_time(t1)], device=device)
@@ -234,26 +278,40 @@ def run_b200(args):
     tr.iteration(dev_real[0].clone(), dev_z[0][0].clone(), dev_z[0][1].clone(), read_losses=False)
     rec = bgn.stop_timing()
     fam = {}
-    FPROP = ("bg_conv_fprop", "bg_conv_fprop_stats", "bg_conv_pool_fprop")   # one kernel family (conv_halo / conv_fprop)
-    dom = [0, 0.0, 0.0]
+    # one kernel family (conv_halo_kernel / conv_fprop_kernel)
+    FPROP = ("bg_conv_fprop", "bg_conv_fprop_stats", "bg_conv_pool_fprop", "bg_conv_style_fprop")
+    dom = [0, 0.0, 0.0, 0.0]
     for name, a, t in rec:
         f = fam.setdefault(name, [0, 0.0, 0.0])
         f[0] += 1
         f[1] += t
         if name in FPROP or name == "bg_conv_wgrad":
-            fl = conv_flops(a if name != "bg_conv_pool_fprop" else a[:5] + (3, 0, 0.0))
+            fl = conv_flops(a if name not in ("bg_conv_pool_fprop", "bg_conv_style_fprop") else a[:5] + (3, 0, 0.0))
             f[2] += fl
             if name in FPROP:
                 dom[0] += 1
                 dom[1] += t
                 dom[2] += fl
+                dom[3] += conv_bytes(name, a)
     tot_ms = sum(v[1] for v in fam.values())
     dom[1] = max(dom[1], 1e-9)
     achieved = dom[2] / (dom[1] / 1e3) / 1e12 if dom[0] else 0.0
     shares = {k: round(v[1] / tot_ms, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1][1])[:8]}
+    traffic = None
+    try:
+        if args.workload == "train256" and not args.batch:
+            with open(os.path.join(ROOT, "profiles", "r1_dram_traffic_fprop_family_train256.json")) as f:
+                tj = json.load(f)
+            traffic = tj["dram_read_bytes"] + tj["dram_write_bytes"]
+    except Exception:
+        traffic = None
     roofline = {"kernel": "conv_halo_kernel / conv_fprop_kernel (tcgen05 implicit GEMM: fprop, dgrad, R1 tangent pass, fused pool / IN-stats / bias-grad epilogues)", "bound": "tensor",
                 "achieved": round(achieved, 1), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                "frac": round(achieved / peaks["tf_sustained"], 4), "traffic": None,
+                "frac": round(achieved / peaks["tf_sustained"], 4), "traffic": traffic,
+                "traffic_note": "DRAM read+write bytes of ALL launches of this kernel family in one iteration (ncu, "
+                                "profiles/r1_dram_traffic_fprop_family_train256.json); algorithmic_bytes is the same sum "
+                                "of 2*N*(Cin*Hin*Win+Cout*Hout*Wout)",
+                "algorithmic_bytes": dom[3], "algorithmic_flops": dom[2],
                 "peak_source": peaks["src"] + ", sustained bf16 (kernel timed inside a long step)",
                 "launches_per_step": dom[0], "share_of_step": round(dom[1] / tot_ms, 4),
                 "wgrad_tflops": round(fam["bg_conv_wgrad"][2] / (fam["bg_conv_wgrad"][1] / 1e3) / 1e12, 1)
@@ -283,7 +341,7 @@ def run_b200(args):
                        "loss": "non-saturating logistic + R1 (lambda=10) with double-backward every step",
                        "l2_policy": "inputs rotate over 4 batches; per-step working set (GBs of activations) >> 126 MB L2"},
             "clocks": clk,
-            "e2e": {"value": round(e2e_value, 2), "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+            "e2e": {"value": round(e2e_value, 2), "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8, "loss_readback": "both losses copied to pinned host memory every step, consumed one step later (no queue drain)",
                     "ms_per_step": round(ms_e2e / args.steps, 3)},
             "gpu_launches": launches,
             "roofline": roofline,

@@ -584,8 +584,21 @@ def critic_tangent(critic, packs: PackCache, tape, v_img):
     return T
 
 
+class _EmitDict(dict):
+    """Gradient dict that reports every entry the moment it is stored (its kernels are already queued on the stream):
+    lets the caller finish and all-reduce a layer's gradient while the backward pass is still running."""
+
+    def __init__(self, emit):
+        super().__init__()
+        self._emit = emit
+
+    def __setitem__(self, key, value):
+        super().__setitem__(key, value)
+        self._emit(key, value)
+
+
 def critic_backward(critic, packs: PackCache, tape, g_pred, need: Dict[int, bool], need_img: bool,
-                    keep: Optional[dict] = None, r1: Optional[tuple] = None):
+                    keep: Optional[dict] = None, r1: Optional[tuple] = None, emit=None):
     """Reverse pass of critic_forward seeded with g_pred (B,1).
 
     need[id(p)] -> produce that parameter gradient.  keep: dict that receives the gated gradient at every
@@ -596,7 +609,7 @@ def critic_backward(critic, packs: PackCache, tape, g_pred, need: Dict[int, bool
     """
     dev = g_pred.device
     B, G = tape["B"], tape["G"]
-    grads: Dict[int, torch.Tensor] = {}
+    grads: Dict[int, torch.Tensor] = {} if emit is None else _EmitDict(emit)
     T, H = r1 if r1 is not None else (None, None)
 
     def want(p):
@@ -734,7 +747,7 @@ def critic_backward(critic, packs: PackCache, tape, g_pred, need: Dict[int, bool
     return grads, g_img
 
 
-def critic_r1_step(critic, packs: PackCache, tape_fake, pred_fake, tape_real, pred_real, c_lambda):
+def critic_r1_step(critic, packs: PackCache, tape_fake, pred_fake, tape_real, pred_real, c_lambda, emit=None):
     """Critic.get_r1_loss (gan.py:393-412): loss value + gradients of every active critic parameter.
 
     loss = mean softplus(-D(real)) + mean softplus(D(fake)) + lambda/2 * mean_n ||d sum D(real) / d real_n||^2
@@ -767,16 +780,26 @@ def critic_r1_step(critic, packs: PackCache, tape_fake, pred_fake, tape_real, pr
     v0 = torch.empty_like(g_x)
     call("bg_axpby_f32", g_x, None, v0, g_x.numel(), float(c_lambda) / B, 0.0)
     T = critic_tangent(critic, packs, tape_real, v0)
-    grads_r, _ = critic_backward(critic, packs, tape_real, seed_r, need, need_img=False, r1=(T, ghat))
     grads = {}
-    for p in params:
-        k = id(p)
-        if not need[k]:
-            continue
-        gf, gr = grads_f.get(k), grads_r.get(k)
-        if gf is None or gr is None:
+    by_id = {id(p): p for p in params}
+
+    def finish(k, gr):
+        """A real-branch gradient just became final: add the fake-branch part and hand the total out."""
+        if not need.get(k, False):
+            return
+        gf = grads_f.get(k)
+        if gf is None:
             raise RuntimeError("internal: missing critic gradient")
         call("bg_axpby_f32", gf, gr, gf, gf.numel(), 1.0, 1.0)
         grads[k] = gf
+        if emit is not None:
+            emit(by_id[k], gf)
+
+    # the last pass runs head -> high resolution: the big low-resolution weights finish first, so their all-reduce
+    # (emit) overlaps the expensive high-resolution layers still to come
+    grads_r, _ = critic_backward(critic, packs, tape_real, seed_r, need, need_img=False, r1=(T, ghat), emit=finish)
+    for p in params:
+        if need[id(p)] and id(p) not in grads:
+            raise RuntimeError("internal: missing critic gradient")
     loss = terms.sum()
     return loss, grads, g_x

@@ -274,19 +274,19 @@ class Critic(nn.Module):
                 "get_r1_loss needs the predictions returned by this Critic's forward (they carry the saved "
                 "activations).  Under multi-device nn.DataParallel the gather drops them: launch one process "
                 "per GPU instead (see INTEGRATION.md).")
-        loss, grads, g_x = engine.critic_r1_step(self, self._packs, tape_f, crit_fake_pred, tape_r, crit_real_pred,
-                                                 c_lambda)
         hook = getattr(self, "_grad_ready_hook", None)
-        for p in engine.critic_params(self, tape_r["steps"], tape_r["fade"]):
-            g = grads.get(id(p))
-            if g is None:
-                continue
+
+        def emit(p, g):
+            # called while the backward is still running, as each parameter's total gradient becomes final
             g = g.reshape(p.shape)
             if p.grad is None:
                 p.grad = g
             else:
                 p.grad.add_(g)
             if hook is not None:
-                hook(p)
+                hook(p)                                   # e.g. dist.GradSync.ready: bucketed all-reduce, overlapped
+
+        loss, grads, g_x = engine.critic_r1_step(self, self._packs, tape_f, crit_fake_pred, tape_r, crit_real_pred,
+                                                 c_lambda, emit=emit)
         self.last_real_image_grad = g_x                   # d sum(D(real)) / d real, what autograd.grad returned
         return loss
