@@ -101,33 +101,43 @@ def lib():
     return _lib
 
 
-def _ptr(t):
-    if t is None:
-        return None
-    if not t.is_cuda:
-        raise RuntimeError("bg_b200 kernels need CUDA tensors (no CPU fallback exists)")
-    if not t.is_contiguous():
-        raise RuntimeError("bg_b200 kernels need contiguous tensors")
-    return t.data_ptr()
-
-
-def _stream():
-    return torch.cuda.current_stream().cuda_stream
+_fns = {}
+_Tensor = torch.Tensor
+_raw_stream = torch._C._cuda_getCurrentRawStream      # (device index) -> cudaStream_t of torch's current stream
 
 
 def call(name, *args):
-    """Invoke a C-ABI entry point; tensors -> device pointers, stream appended."""
+    """Invoke a C-ABI entry point; tensors -> device pointers, torch's current stream appended.
+    This is the host-side hot loop (~700 calls per training iteration), so it does the minimum: one dict lookup, one
+    pass over the arguments (CUDA + contiguity checks stay: a wrong pointer would be silent corruption)."""
     global launch_count
-    l = lib()
-    conv = [(_ptr(a) if (a is None or isinstance(a, torch.Tensor)) else a) for a in args]
+    fn = _fns.get(name)
+    if fn is None:
+        fn = _fns[name] = getattr(lib(), name)
+    conv = []
+    dev = -1
+    for a in args:
+        if a is None:
+            conv.append(None)
+        elif isinstance(a, _Tensor):
+            if not a.is_cuda:
+                raise RuntimeError("bg_b200 kernels need CUDA tensors (no CPU fallback exists)")
+            if not a.is_contiguous():
+                raise RuntimeError("bg_b200 kernels need contiguous tensors")
+            if dev < 0:
+                dev = a.device.index
+            conv.append(a.data_ptr())
+        else:
+            conv.append(a)
+    stream = _raw_stream(dev if dev >= 0 else torch.cuda.current_device())
     if _timing is not None:
         s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s_ev.record()
-        rc = getattr(l, name)(*conv, _stream())
+        rc = fn(*conv, stream)
         e_ev.record()
-        _timing.append((name, tuple(a for a in args if not isinstance(a, torch.Tensor) and a is not None), s_ev, e_ev))
+        _timing.append((name, tuple(a for a in args if not isinstance(a, _Tensor) and a is not None), s_ev, e_ev))
     else:
-        rc = getattr(l, name)(*conv, _stream())
+        rc = fn(*conv, stream)
     launch_count += 1
     if rc != 0:
-        raise RuntimeError(f"{name} failed ({rc}): {l.bg_last_error().decode()}")
+        raise RuntimeError(f"{name} failed ({rc}): {lib().bg_last_error().decode()}")

@@ -15,6 +15,8 @@
 // reductions (red.global.add.v4.f32).
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace bg {
 
 namespace {
@@ -40,6 +42,7 @@ struct WgradHaloParams {
   uint32_t a_row_bytes, b_row_bytes;
   uint32_t a_layout, b_layout;
   uint32_t a_slab_bytes;
+  int stack_taps;                  // 1: the three kx taps are ONE MMA (N = 3 * ci_sub, N-atoms one pixel apart)
   float* dw;
 };
 
@@ -124,9 +127,13 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
       }
     } else if (warp == 1) {
       // ------------------------------ MMA issuer (whole warp converged, one elected lane issues) ----------------
-      const uint32_t idesc = umma_idesc_bf16(128, p.ci_slab, 1, 1);
+      // stack_taps (Cin <= 64): tap kx of X is the same tile one pixel row (b_row_bytes) further on, so the three
+      // taps are three N-atoms with LBO = one pixel row and run as ONE MMA with N = 3 * ci: a small-N tcgen05.mma
+      // costs ~60 clk no matter how narrow it is, so fewer, wider instructions are what speeds the narrow layers up.
+      const uint32_t idesc = umma_idesc_bf16(128, p.stack_taps ? 3 * p.ci_slab : p.ci_slab, 1, 1);
       const uint64_t a_desc0 = umma_desc(smem_u32(smem), p.a_slab_bytes, 8u * p.a_row_bytes, p.a_layout);
-      const uint64_t b_desc0 = umma_desc(smem_u32(smem) + kARegion, kBSub, 8u * p.b_row_bytes, p.b_layout);
+      const uint64_t b_desc0 = umma_desc(smem_u32(smem) + kARegion, p.stack_taps ? p.b_row_bytes : kBSub,
+                                         8u * p.b_row_bytes, p.b_layout);
       const uint32_t a_kstep = (16u * p.a_row_bytes) >> 4;          // 16 pixels (one image row of the tile) per K step
       const uint32_t b_kstep = ((uint32_t)kHaloW * p.b_row_bytes) >> 4;   // ... which is 18 halo pixels further in X
       const uint32_t b_tap = p.b_row_bytes >> 4;                     // one pixel to the right = next tap
@@ -140,12 +147,19 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
         if (leader) {
           const uint64_t a_st = a_desc0 + (uint64_t)((uint32_t)stage * (kStageBytes >> 4));
           const uint64_t b_st = b_desc0 + (uint64_t)((uint32_t)stage * (kStageBytes >> 4));
+          if (p.stack_taps) {
 #pragma unroll
-          for (int ks = 0; ks < kBh; ++ks) {
+            for (int ks = 0; ks < kBh; ++ks)
+              tc_mma_bf16(tmem_base, a_st + (uint64_t)(ks * a_kstep), b_st + (uint64_t)(ks * b_kstep), idesc,
+                          ks == 0 ? accum : 1u);
+          } else {
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-              tc_mma_bf16(tmem_base + kx * kTapStride, a_st + (uint64_t)(ks * a_kstep),
-                          b_st + (uint64_t)(ks * b_kstep + kx * b_tap), idesc, ks == 0 ? accum : 1u);
+            for (int ks = 0; ks < kBh; ++ks) {
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) {
+                tc_mma_bf16(tmem_base + kx * kTapStride, a_st + (uint64_t)(ks * a_kstep),
+                            b_st + (uint64_t)(ks * b_kstep + kx * b_tap), idesc, ks == 0 ? accum : 1u);
+              }
             }
           }
           tc_commit(&empty_bar[stage]);
@@ -172,7 +186,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
         float* drow = p.dw + ((size_t)tap * p.Cout + co) * p.Cin + ci0;
         for (int c = 0; c < p.ci_slab; c += 16) {
           uint32_t v[16];
-          tmem_ld_x16(taddr + kx * kTapStride + c, v);
+          tmem_ld_x16(taddr + kx * (p.stack_taps ? (uint32_t)p.ci_slab : kTapStride) + c, v);
           tmem_ld_wait();
           if (live) {
 #pragma unroll
@@ -225,6 +239,11 @@ int launch_conv_wgrad_halo(const void* x, const void* g, float* dw, int N, int H
   p.b_layout = p.b_row_bytes == 128 ? 2u : (p.b_row_bytes == 64 ? 4u : 6u);
   p.a_slab_bytes = 128u * p.a_row_bytes;
   p.dw = dw;
+  {
+    static int mode = -1;     // BG_WGRAD_STACK: 0 never, 1 Cin <= 32 only, 2 (default) whenever Cin <= 64
+    if (mode < 0) { const char* e = getenv("BG_WGRAD_STACK"); mode = e ? atoi(e) : 2; }
+    p.stack_taps = (p.ci_nsub == 1 && (mode == 2 || (mode == 1 && Cin <= 32))) ? 1 : 0;
+  }
   const int units = p.co_tiles * p.ci_slabs * 3;
   int splits = (2 * num_sms() + units - 1) / units;
   if (splits < 1) splits = 1;

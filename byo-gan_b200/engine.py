@@ -15,6 +15,7 @@ vectors, instance-norm statistics, critic head and every parameter gradient are 
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -212,6 +213,8 @@ def style_conv_fusable(R: int, cout: int) -> bool:
     """Fold the previous AdaIN into per-sample weights (bg_style_modulate + bg_conv_style_fprop) when the halo kernel
     runs the layer (R >= 16) and the per-sample packs (9*Cin*Cout per sample) are cheaper to write and read than the
     normalised map (R*R*Cin per sample) the unfused path materialises."""
+    if os.environ.get("BG_NO_STYLE_FUSION"):         # A/B switch (tools/flaky_probe.py); the default path is fused
+        return False
     return R >= 16 and 18 * cout <= R * R
 
 
