@@ -46,6 +46,9 @@ SIGNATURES = {
     "bg_adain_bwd_apply": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _I, _P, _P, _P],
     "bg_linear_fwd": [_P, _P, _P, _P, _I, _I, _I, _F, _I, _F, _P],
     "bg_linear_bwd_weight": [_P, _P, _P, _P, _I, _I, _I, _F, _I, _P],
+    "bg_linear_fwd_grouped": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "bg_linear_bwd_weight_grouped": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "bg_linear_bwd_input_grouped": [_P, _P, _P, _P, _I, _I, _I, _P, _P],
     "bg_transpose_f32": [_P, _P, _I, _I, _P],
     "bg_act_gate_f32": [_P, _P, _P, _Z, _F, _P],
     "bg_axpby_f32": [_P, _P, _P, _Z, _F, _F, _P],
@@ -119,6 +122,24 @@ def call(name, *args):
     for a in args:
         if a is None:
             conv.append(None)
+        elif isinstance(a, (list, tuple)):
+            # host array argument of a grouped entry point: device pointers, ints or floats
+            if a and isinstance(a[0], float):
+                conv.append((ctypes.c_float * len(a))(*a))
+            elif a and isinstance(a[0], int):
+                conv.append((ctypes.c_int * len(a))(*a))
+            else:
+                ptrs = []
+                for t in a:
+                    if t is None:
+                        ptrs.append(None)
+                    else:
+                        if not (t.is_cuda and t.is_contiguous()):
+                            raise RuntimeError("bg_b200 kernels need contiguous CUDA tensors")
+                        if dev < 0:
+                            dev = t.device.index
+                        ptrs.append(t.data_ptr())
+                conv.append((ctypes.c_void_p * len(a))(*ptrs))
         elif isinstance(a, _Tensor):
             if not a.is_cuda:
                 raise RuntimeError("bg_b200 kernels need CUDA tensors (no CPU fallback exists)")
@@ -135,7 +156,7 @@ def call(name, *args):
         s_ev.record()
         rc = fn(*conv, stream)
         e_ev.record()
-        _timing.append((name, tuple(a for a in args if not isinstance(a, _Tensor) and a is not None), s_ev, e_ev))
+        _timing.append((name, tuple(a for a in args if not isinstance(a, (_Tensor, list, tuple)) and a is not None), s_ev, e_ev))
     else:
         rc = fn(*conv, stream)
     launch_count += 1

@@ -272,10 +272,15 @@ int launch_conv_fprop(const void* x, const void* wpack, void* out, int N, int H,
   p.tiles_w = W / p.bw;
   p.tiles_h = H / p.bh;
   p.tiles_n = (N + p.bn - 1) / p.bn;
-  // Largest multiple of 16 that divides Cout and is <= 256.
+  // N tile: the largest multiple of 16 that divides Cout, is <= 256 and still yields ~one CTA per SM.  This kernel
+  // only runs the small maps (<= 8x8: 4..64 pixel tiles), where a CTA's time is the L2->SMEM fill of its K loop
+  // (~80 GB/s per SM): narrower N tiles spread that over more SMs (8x8, 512->512: 32 CTAs x 3.4 MB -> 128 x 1.7 MB).
   int bn_ch = 0;
+  const int pixel_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   for (int c = 256; c >= 16; c -= 16) {
-    if (Cout % c == 0) { bn_ch = c; break; }
+    if (Cout % c != 0) continue;
+    bn_ch = c;
+    if (pixel_tiles * (Cout / c) >= (num_sms() * 3) / 4) break;
   }
   BG_REQUIRE(bn_ch > 0, "conv_fprop: no valid N tile for Cout %d", Cout);
   p.block_n = bn_ch;

@@ -106,6 +106,143 @@ __global__ void linear_bwd_weight_kernel(const float* __restrict__ gy, const flo
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Grouped EqualizedLinear: the 2 x steps AdaIN style FCs of the generator (gan.py:60,66) all read the SAME latent
+// w (M x K), so forward, weight gradient and input gradient of all of them are one launch each instead of 14 (the
+// layers are tiny and each launch is latency-bound).  Groups are described by a by-value table of pointers.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxLinGroups = 16;
+struct LinGroups {
+  const float* W[kMaxLinGroups];     // fwd / bwd_weight: (N_g, K) weights;  bwd_input: (K, N_g) TRANSPOSED weights
+  const float* b[kMaxLinGroups];     // fwd: bias (may be null)
+  float* y[kMaxLinGroups];           // fwd: output (M, N_g);  bwd_*: gy (M, N_g) (read)
+  float* dW[kMaxLinGroups];          // bwd_weight: (N_g, K)
+  float* db[kMaxLinGroups];          // bwd_weight: (N_g) (may be null)
+  int N[kMaxLinGroups];
+  int blk0[kMaxLinGroups + 1];       // first block of each group (fwd / bwd_weight)
+  float coef[kMaxLinGroups];
+  int groups;
+};
+
+// fwd: one warp per (n, group of kLinMT rows) of one group; same inner loop as linear_fwd_kernel
+__global__ void linear_fwd_grouped_kernel(const float* __restrict__ x, const LinGroups G, int M, int K, int act,
+                                          float slope) {
+  int g = 0;
+  while (g + 1 < G.groups && (int)blockIdx.x >= G.blk0[g + 1]) ++g;
+  const int N = G.N[g];
+  const int warp = (((int)blockIdx.x - G.blk0[g]) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int mgroups = (M + kLinMT - 1) / kLinMT;
+  if (warp >= N * mgroups) return;
+  const int n = warp % N;
+  const int m0 = (warp / N) * kLinMT;
+  float acc[kLinMT];
+#pragma unroll
+  for (int i = 0; i < kLinMT; ++i) acc[i] = 0.f;
+  const float* wrow = G.W[g] + (size_t)n * K;
+  for (int k = lane * 4; k < K; k += 128) {
+    const float4 wv = *reinterpret_cast<const float4*>(wrow + k);
+#pragma unroll
+    for (int i = 0; i < kLinMT; ++i) {
+      if (m0 + i < M) {
+        const float4 xv = *reinterpret_cast<const float4*>(x + (size_t)(m0 + i) * K + k);
+        acc[i] += xv.x * wv.x + xv.y * wv.y + xv.z * wv.z + xv.w * wv.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kLinMT; ++i) acc[i] = warp_sum(acc[i]);
+  if (lane == 0) {
+    const float b = G.b[g] ? G.b[g][n] : 0.f;
+#pragma unroll
+    for (int i = 0; i < kLinMT; ++i) {
+      if (m0 + i < M) {
+        float v = acc[i] * G.coef[g] + b;
+        if (act) v = lrelu_f(v, slope);
+        G.y[g][(size_t)(m0 + i) * N + n] = v;
+      }
+    }
+  }
+}
+
+// bwd_weight: blocks of group g cover (K/4 threads) x (N_g / kLbwNT row groups); dW = coef * gy^T x, db = sum_m gy
+__global__ void linear_bwd_weight_grouped_kernel(const float* __restrict__ x, const LinGroups G, int M, int K) {
+  int g = 0;
+  while (g + 1 < G.groups && (int)blockIdx.x >= G.blk0[g + 1]) ++g;
+  const int N = G.N[g];
+  const float* __restrict__ gy = G.y[g];
+  const int kblocks = (K / 4 + 127) / 128;
+  const int local = (int)blockIdx.x - G.blk0[g];
+  const int k = ((local % kblocks) * blockDim.x + threadIdx.x) * 4;
+  const int n0 = (local / kblocks) * kLbwNT;
+  float acc[kLbwNT][4];
+#pragma unroll
+  for (int i = 0; i < kLbwNT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  if (k < K) {
+    for (int m = 0; m < M; ++m) {
+      const float4 xv = *reinterpret_cast<const float4*>(x + (size_t)m * K + k);
+#pragma unroll
+      for (int i = 0; i < kLbwNT; ++i) {
+        const float gg = (n0 + i < N) ? gy[(size_t)m * N + n0 + i] : 0.f;
+        acc[i][0] += gg * xv.x;
+        acc[i][1] += gg * xv.y;
+        acc[i][2] += gg * xv.z;
+        acc[i][3] += gg * xv.w;
+      }
+    }
+    const float coef = G.coef[g];
+#pragma unroll
+    for (int i = 0; i < kLbwNT; ++i) {
+      if (n0 + i < N)
+        *reinterpret_cast<float4*>(G.dW[g] + (size_t)(n0 + i) * K + k) =
+            make_float4(acc[i][0] * coef, acc[i][1] * coef, acc[i][2] * coef, acc[i][3] * coef);
+    }
+  }
+  if (G.db[g] != nullptr && (local % kblocks) == 0 && threadIdx.x < kLbwNT && n0 + threadIdx.x < N) {
+    float sacc = 0.f;
+    for (int m = 0; m < M; ++m) sacc += gy[(size_t)m * N + n0 + threadIdx.x];
+    G.db[g][n0 + threadIdx.x] = sacc;
+  }
+}
+
+// bwd_input: gx[m,k] = sum_g coef_g * sum_n gy_g[m,n] * Wt_g[k,n]   (Wt_g = transposed weight (K, N_g)); one warp per
+// (k, group of kLinMT rows), looping over the groups: the sum over layers needs no separate accumulation pass
+__global__ void linear_bwd_input_grouped_kernel(const LinGroups G, float* __restrict__ gx, int M, int K) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int mgroups = (M + kLinMT - 1) / kLinMT;
+  if (warp >= K * mgroups) return;
+  const int k = warp % K;
+  const int m0 = (warp / K) * kLinMT;
+  float acc[kLinMT];
+#pragma unroll
+  for (int i = 0; i < kLinMT; ++i) acc[i] = 0.f;
+  for (int g = 0; g < G.groups; ++g) {
+    const int N = G.N[g];
+    const float* wrow = G.W[g] + (size_t)k * N;
+    const float* gy = G.y[g];
+    const float coef = G.coef[g];
+    for (int n = lane * 4; n < N; n += 128) {
+      float4 wv = *reinterpret_cast<const float4*>(wrow + n);
+      wv.x *= coef; wv.y *= coef; wv.z *= coef; wv.w *= coef;
+#pragma unroll
+      for (int i = 0; i < kLinMT; ++i) {
+        if (m0 + i < M) {
+          const float4 gv = *reinterpret_cast<const float4*>(gy + (size_t)(m0 + i) * N + n);
+          acc[i] += gv.x * wv.x + gv.y * wv.y + gv.z * wv.z + gv.w * wv.w;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kLinMT; ++i) acc[i] = warp_sum(acc[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < kLinMT; ++i)
+      if (m0 + i < M) gx[(size_t)(m0 + i) * K + k] = acc[i];
+  }
+}
+
 // out[c][r] = in[r][c]  (fp32), 32x32 smem tiles
 __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int C) {
   __shared__ float tile[32][33];
@@ -646,6 +783,44 @@ int launch_logistic_loss(const float* pred, int n, float sign, float* loss, floa
 int launch_sumsq(const float* x, size_t n, float scale, float* out, cudaStream_t s) {
   BG_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), s));
   sumsq_kernel<<<grid1d(n, 256, 2), 256, 0, s>>>(x, n, scale, out);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// mode 0: forward, 1: weight gradient, 2: input gradient.  Pointer arrays are HOST arrays of device pointers.
+int launch_linear_grouped(int mode, const float* x, const float* const* W, const float* const* bias, float* const* y,
+                          float* const* dW, float* const* db, const int* N, const float* coef, int groups, int M, int K,
+                          int act, float slope, float* gx, cudaStream_t s) {
+  BG_REQUIRE(groups > 0 && groups <= kMaxLinGroups, "linear_grouped: 1..%d groups (got %d)", kMaxLinGroups, groups);
+  BG_REQUIRE(M > 0 && K > 0 && K % 4 == 0, "linear_grouped: bad shape M %d K %d", M, K);
+  LinGroups G;
+  memset(&G, 0, sizeof(G));
+  G.groups = groups;
+  const int mgroups = (M + kLinMT - 1) / kLinMT;
+  int blocks = 0;
+  for (int g = 0; g < groups; ++g) {
+    BG_REQUIRE(N[g] > 0 && N[g] % 4 == 0, "linear_grouped: N[%d] = %d must be a positive multiple of 4", g, N[g]);
+    G.W[g] = W[g];
+    G.b[g] = bias ? bias[g] : nullptr;
+    G.y[g] = y[g];
+    G.dW[g] = dW ? dW[g] : nullptr;
+    G.db[g] = db ? db[g] : nullptr;
+    G.N[g] = N[g];
+    G.coef[g] = coef[g];
+    G.blk0[g] = blocks;
+    if (mode == 0) blocks += (int)(((long)N[g] * mgroups * 32 + 255) / 256);
+    else if (mode == 1) blocks += ((K / 4 + 127) / 128) * ((N[g] + kLbwNT - 1) / kLbwNT);
+  }
+  G.blk0[groups] = blocks;
+  if (mode == 0) {
+    linear_fwd_grouped_kernel<<<blocks, 256, 0, s>>>(x, G, M, K, act, slope);
+  } else if (mode == 1) {
+    linear_bwd_weight_grouped_kernel<<<blocks, 128, 0, s>>>(x, G, M, K);
+  } else {
+    BG_REQUIRE(gx != nullptr, "linear_grouped: gx is required for the input gradient");
+    const long warps = (long)K * mgroups;
+    linear_bwd_input_grouped_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, s>>>(G, gx, M, K);
+  }
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

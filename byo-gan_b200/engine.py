@@ -259,16 +259,27 @@ def generator_forward(gen, packs: PackCache, z, noise, steps, alpha, z2=None, cr
     if z2 is not None:
         maps.append(mapping(z2))
     layers = []
+    # AdaIN style vectors [gamma | beta] = EqualizedLinear(512 -> 2C)(w) of every layer (gan.py:60,66): all layers fed
+    # by the same latent go in ONE grouped launch
+    which_of = [1 if (z2 is not None and crossover is not None and k >= crossover) else 0 for k in range(steps)]
+    styles = {}
+    for wsel in sorted(set(which_of)):
+        fcs = [(k, j, sc.adain.style) for k in range(steps) if which_of[k] == wsel
+               for j, sc in enumerate((gen.gen_blocks[k].conv_1, gen.gen_blocks[k].conv_2))]
+        outs = [_f32(B, fc.weight.shape[0], device=dev) for _, _, fc in fcs]
+        call("bg_linear_fwd_grouped", maps[wsel][-1], [fc.weight.detach() for _, _, fc in fcs],
+             [fc.bias.detach() for _, _, fc in fcs], outs, [fc.weight.shape[0] for _, _, fc in fcs],
+             [coef_of(fc.weight) for _, _, fc in fcs], len(fcs), B, 512, 0, SLOPE)
+        for (k, j, _), o in zip(fcs, outs):
+            styles[(k, j)] = o
     for k in range(steps):
         blk = gen.gen_blocks[k]
         cin, cout = GEN_CHANNELS[k]
         R = 4 << k
-        which = 1 if (z2 is not None and crossover is not None and k >= crossover) else 0
-        wlat = maps[which][-1]
+        which = which_of[k]
         nz = noise[k].detach().float().contiguous()
         for j, sc in enumerate((blk.conv_1, blk.conv_2)):
-            st = sc.adain.style
-            style = linear_fwd(wlat, st.weight, st.bias, act=False)              # gan.py:66
+            style = styles[(k, j)]
             nw = sc.inject_noise.weights.detach().reshape(-1)
             L = dict(k=k, j=j, sc=sc, xin=None, R=R, C=cout, which=which, noise=nz, style=style, xo=None,
                      prev=len(layers) - 1, up=(j == 0 and k > 0))
@@ -340,6 +351,7 @@ def generator_backward(gen, packs: PackCache, tape, g_img, need: Dict[int, bool]
     R = 4 << (steps - 1)
     C = GEN_CHANNELS[steps - 1][1]
     g_w = [None] * len(maps)
+    dstyles = []
 
     def want(p):
         return need.get(id(p), False)
@@ -387,21 +399,9 @@ def generator_backward(gen, packs: PackCache, tape, g_img, need: Dict[int, bool]
         ws = _f32(2, c, device=dev) if (need_b or need_nw) else None
         call("bg_adain_bwd_apply", gx, a, stats, style, bs, gpre, B, r * r, c, IN_EPS, SLOPE, 1,
              L["noise"] if ws is not None else None, ws)
-        # style FC (gan.py:60,66): dL/dgamma = sum g*ahat, dL/dbeta = sum g
-        dstyle = torch.cat([bs[..., 1], bs[..., 0]], dim=1).contiguous()
-        st = sc.adain.style
-        wlat = maps[L["which"]][-1]
-        if want(st.weight) or want(st.bias):
-            dw, db = linear_bwd_weight(dstyle, wlat, st.weight)
-            if want(st.weight):
-                grads[id(st.weight)] = dw
-            if want(st.bias):
-                grads[id(st.bias)] = db
-        gw_l = linear_bwd_input(dstyle, st.weight, packs)
-        if g_w[L["which"]] is None:
-            g_w[L["which"]] = gw_l
-        else:
-            call("bg_axpby_f32", g_w[L["which"]], gw_l, g_w[L["which"]], gw_l.numel(), 1.0, 1.0)
+        # style FC (gan.py:60,66): dL/dgamma = sum g*ahat, dL/dbeta = sum g; the FC gradients of all layers are taken in
+        # grouped launches after the loop
+        dstyles.append((L["which"], sc.adain.style, torch.cat([bs[..., 1], bs[..., 0]], dim=1).contiguous()))
         if need_b:
             grads[id(sc.conv.bias)] = ws[0]
         if need_nw:
@@ -432,6 +432,29 @@ def generator_backward(gen, packs: PackCache, tape, g_img, need: Dict[int, bool]
             gx = gfeat
         else:
             gx = gxin
+
+    # style FCs of all layers (gan.py:60,66), grouped per latent: weight / bias gradients and the latent gradient
+    for wsel in range(len(maps)):
+        grp = [(fc, d) for (w_, fc, d) in dstyles if w_ == wsel]
+        if not grp:
+            continue
+        fcs, gys = [fc for fc, _ in grp], [d for _, d in grp]
+        ns, cf = [fc.weight.shape[0] for fc in fcs], [coef_of(fc.weight) for fc in fcs]
+        wanted = [fc for fc in fcs if want(fc.weight) or want(fc.bias)]
+        if wanted:
+            sel = [i for i, fc in enumerate(fcs) if want(fc.weight) or want(fc.bias)]
+            dws = [_f32(*fcs[i].weight.shape, device=dev) for i in sel]
+            dbs = [_f32(ns[i], device=dev) for i in sel]
+            call("bg_linear_bwd_weight_grouped", maps[wsel][-1], [gys[i] for i in sel], dws, dbs, [ns[i] for i in sel],
+                 [cf[i] for i in sel], len(sel), B, 512)
+            for i, dw, db in zip(sel, dws, dbs):
+                if want(fcs[i].weight):
+                    grads[id(fcs[i].weight)] = dw
+                if want(fcs[i].bias):
+                    grads[id(fcs[i].bias)] = db
+        gw = _f32(B, 512, device=dev)
+        call("bg_linear_bwd_input_grouped", gys, [packs.linear_t(fc.weight) for fc in fcs], ns, cf, len(fcs), B, 512, gw)
+        g_w[wsel] = gw
 
     # mapping network backward (gan.py:130-148)
     dzs = [None, None]

@@ -174,3 +174,31 @@ def test_flatten_boundary_roundtrip():
     back = torch.empty_like(x)
     bgn.call("bg_nchw_f32_to_nhwc", f, x, back, n, 16, 512, 0.2)
     assert torch.equal(back, (x.float() * torch.where(x.float() > 0, 1.0, 0.2)).to(torch.bfloat16))
+
+
+def test_grouped_style_linears():
+    """The generator's AdaIN style FCs (gan.py:60,66) as grouped launches: forward, weight/bias gradient and the summed
+    input gradient against per-layer torch fp32."""
+    torch.manual_seed(4)
+    M, K = 12, 512
+    Ns = [1024, 512, 64, 32, 256]
+    x = torch.randn(M, K, device=DEV)
+    Ws = [torch.randn(n, K, device=DEV) for n in Ns]
+    bs = [torch.randn(n, device=DEV) for n in Ns]
+    coefs = [math.sqrt(2 / K) * (1 + 0.1 * i) for i in range(len(Ns))]
+    ys = [torch.empty(M, n, device=DEV) for n in Ns]
+    bgn.call("bg_linear_fwd_grouped", x, Ws, bs, ys, Ns, coefs, len(Ns), M, K, 0, 0.2)
+    for W, b, y, c in zip(Ws, bs, ys, coefs):
+        assert torch.allclose(y, x @ (W * c).t() + b, rtol=1e-4, atol=1e-4)
+    gys = [torch.randn(M, n, device=DEV) for n in Ns]
+    dWs = [torch.empty(n, K, device=DEV) for n in Ns]
+    dbs = [torch.empty(n, device=DEV) for n in Ns]
+    bgn.call("bg_linear_bwd_weight_grouped", x, gys, dWs, dbs, Ns, coefs, len(Ns), M, K)
+    for gy, dW, db, c in zip(gys, dWs, dbs, coefs):
+        assert torch.allclose(dW, c * gy.t() @ x, rtol=1e-4, atol=1e-4)
+        assert torch.allclose(db, gy.sum(0), rtol=1e-4, atol=1e-4)
+    Wts = [W.t().contiguous() for W in Ws]
+    gx = torch.empty(M, K, device=DEV)
+    bgn.call("bg_linear_bwd_input_grouped", gys, Wts, Ns, coefs, len(Ns), M, K, gx)
+    want = sum(c * gy @ W for gy, W, c in zip(gys, Ws, coefs))
+    assert torch.allclose(gx, want, rtol=1e-4, atol=2e-3)
