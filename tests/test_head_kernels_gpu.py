@@ -202,3 +202,21 @@ def test_grouped_style_linears():
     bgn.call("bg_linear_bwd_input_grouped", gys, Wts, Ns, coefs, len(Ns), M, K, gx)
     want = sum(c * gy @ W for gy, W, c in zip(gys, Ws, coefs))
     assert torch.allclose(gx, want, rtol=1e-4, atol=2e-3)
+
+
+def test_helper_truncated_noise_distribution():
+    """Drop-in helper.get_truncated_noise (helper.py:36-45): same distribution as scipy truncnorm.rvs(-t, t)."""
+    import helper
+    from scipy.stats import truncnorm
+
+    torch.manual_seed(0)
+    for t in (0.75, 2.0):
+        x = helper.get_truncated_noise(4096, 512, t)
+        assert x.is_cuda and x.dtype == torch.float32 and x.requires_grad and x.shape == (4096, 512)
+        v = x.detach()
+        assert v.abs().max().item() <= t + 1e-6
+        assert abs(v.mean().item()) < 3e-3
+        assert abs(v.std().item() - truncnorm.std(-t, t)) < 3e-3
+        # quartiles against the analytic inverse CDF
+        for q in (0.1, 0.25, 0.5, 0.9):
+            assert abs(torch.quantile(v.flatten()[:1000000], q).item() - truncnorm.ppf(q, -t, t)) < 5e-3
