@@ -21,6 +21,7 @@ _Z = ctypes.c_size_t
 # name -> argtypes, mirrors include/bg_b200.h one to one
 SIGNATURES = {
     "bg_pack_weight": [_P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "bg_pack_weight_grouped": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P],
     "bg_unpack_wgrad": [_P, _P, _I, _I, _I, _I, _F, _I, _P],
     "bg_conv_fprop": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _F, _P],
     "bg_conv_fprop_stats": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _F, _P, _I, _P],

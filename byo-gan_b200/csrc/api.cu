@@ -54,6 +54,8 @@ int launch_to_rgb_adain(const void*, const float*, const float*, const float*, c
                         float, cudaStream_t);
 int launch_linear_grouped(int, const float*, const float* const*, const float* const*, float* const*, float* const*,
                           float* const*, const int*, const float*, int, int, int, int, float, float*, cudaStream_t);
+int launch_pack_weight_grouped(const float* const*, void* const*, void* const*, const int*, const int*, const int*,
+                               const int*, const float*, int, cudaStream_t);
 }  // namespace bg
 
 #define S(stream) reinterpret_cast<cudaStream_t>(stream)
@@ -63,6 +65,10 @@ extern "C" {
 int bg_pack_weight(const float* w, void* wf, void* wd, int Cout, int Cin, int Cin_pad, int ks, float coef,
                    void* stream) {
   return bg::launch_pack_weight(w, wf, wd, Cout, Cin, Cin_pad, ks, coef, S(stream));
+}
+int bg_pack_weight_grouped(const float* const* w, void* const* wf, void* const* wd, const int* Cout, const int* Cin,
+                           const int* Cin_pad, const int* ks, const float* coef, int groups, void* stream) {
+  return bg::launch_pack_weight_grouped(w, wf, wd, Cout, Cin, Cin_pad, ks, coef, groups, S(stream));
 }
 int bg_unpack_wgrad(const float* dwp, float* dw, int Cout, int Cin, int Cin_pad, int ks, float coef, int accumulate,
                     void* stream) {

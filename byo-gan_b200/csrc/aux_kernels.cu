@@ -79,6 +79,40 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
   }
 }
 
+// All stale packs of a network in ONE launch (after an optimizer step every conv weight of the active stage is stale:
+// 13..26 layers).  Group g owns blocks [blk0[g], blk0[g+1]).
+constexpr int kMaxPackGroups = 32;
+struct PackGroups {
+  const float* w[kMaxPackGroups];
+  __nv_bfloat16* wf[kMaxPackGroups];
+  __nv_bfloat16* wd[kMaxPackGroups];
+  int Cout[kMaxPackGroups], Cin[kMaxPackGroups], Cin_pad[kMaxPackGroups], ks[kMaxPackGroups];
+  float coef[kMaxPackGroups];
+  int blk0[kMaxPackGroups + 1];
+  int groups;
+};
+__global__ void pack_weight_grouped_kernel(const PackGroups G) {
+  int g = 0;
+  while (g + 1 < G.groups && (int)blockIdx.x >= G.blk0[g + 1]) ++g;
+  const int Cout = G.Cout[g], Cin = G.Cin[g], Cin_pad = G.Cin_pad[g], taps = G.ks[g] * G.ks[g];
+  const float coef = G.coef[g];
+  const float* __restrict__ w = G.w[g];
+  __nv_bfloat16* __restrict__ wf = G.wf[g];
+  __nv_bfloat16* __restrict__ wd = G.wd[g];
+  const size_t total = (size_t)taps * Cout * Cin_pad;
+  const size_t nthreads = (size_t)(G.blk0[g + 1] - G.blk0[g]) * blockDim.x;
+  for (size_t i = ((size_t)blockIdx.x - G.blk0[g]) * blockDim.x + threadIdx.x; i < total; i += nthreads) {
+    const int ci = (int)(i % Cin_pad);
+    const int co = (int)((i / Cin_pad) % Cout);
+    const int tap = (int)(i / ((size_t)Cin_pad * Cout));
+    float v = 0.f;
+    if (ci < Cin) v = w[((size_t)co * Cin + ci) * taps + tap] * coef;
+    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+    wf[i] = b;
+    wd[((size_t)(taps - 1 - tap) * Cin_pad + ci) * Cout + co] = b;
+  }
+}
+
 // dwp: fp32 [tap][Cout][Cin_pad] -> dw: fp32 (Cout, Cin, ks, ks), scaled by coef; optionally accumulates.
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Cout, int Cin,
                                     int Cin_pad, int ks, float coef, int accumulate) {
@@ -885,6 +919,33 @@ int launch_to_rgb_adain(const void* a, const float* stats, const float* style, c
   if (bps < 1) bps = 1;
   to_rgb_adain_kernel<<<dim3(bps, N), kBlock, (size_t)(3 * C + 4) * sizeof(float), s>>>(
       (const __nv_bfloat16*)a, stats, style, Wm, bias, out, HW, C, coef, eps);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_pack_weight_grouped(const float* const* w, void* const* wf, void* const* wd, const int* Cout, const int* Cin,
+                               const int* Cin_pad, const int* ks, const float* coef, int groups, cudaStream_t s) {
+  BG_REQUIRE(groups > 0 && groups <= kMaxPackGroups, "pack_weight_grouped: 1..%d groups (got %d)", kMaxPackGroups, groups);
+  PackGroups G;
+  memset(&G, 0, sizeof(G));
+  G.groups = groups;
+  int blocks = 0;
+  for (int g = 0; g < groups; ++g) {
+    BG_REQUIRE((ks[g] == 1 || ks[g] == 3) && Cin_pad[g] >= Cin[g], "pack_weight_grouped: bad group %d", g);
+    G.w[g] = w[g];
+    G.wf[g] = (__nv_bfloat16*)wf[g];
+    G.wd[g] = (__nv_bfloat16*)wd[g];
+    G.Cout[g] = Cout[g]; G.Cin[g] = Cin[g]; G.Cin_pad[g] = Cin_pad[g]; G.ks[g] = ks[g];
+    G.coef[g] = coef[g];
+    G.blk0[g] = blocks;
+    const size_t total = (size_t)ks[g] * ks[g] * Cout[g] * Cin_pad[g];
+    size_t b = (total + (size_t)kBlock * 8 - 1) / ((size_t)kBlock * 8);      // ~8 elements per thread
+    if (b < 1) b = 1;
+    if (b > 1184) b = 1184;
+    blocks += (int)b;
+  }
+  G.blk0[groups] = blocks;
+  pack_weight_grouped_kernel<<<blocks, kBlock, 0, s>>>(G);
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

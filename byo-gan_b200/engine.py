@@ -71,6 +71,28 @@ class PackCache:
         self._conv[key] = (tag, wf, wd)
         return wf, wd
 
+    def refresh_convs(self, items):
+        """Re-pack every stale conv weight of `items` = [(weight, cin_pad or None)] in ONE grouped launch (after an
+        optimizer step all of a network's packs are stale); the per-layer conv() lookups that follow then hit."""
+        stale = []
+        for w, cin_pad in items:
+            hit = self._conv.get(id(w))
+            if hit is None or hit[0] != (w._version, w.data_ptr(), cin_pad):
+                stale.append((w, cin_pad))
+        for i in range(0, len(stale), 32):
+            grp = stale[i:i + 32]
+            wfs, wds, meta = [], [], []
+            for w, cin_pad in grp:
+                cout, cin, ks, _ = w.shape
+                cp = cin_pad or cin
+                wfs.append(_bf16(ks * ks, cout, cp, device=w.device))
+                wds.append(_bf16(ks * ks, cp, cout, device=w.device))
+                meta.append((cout, cin, cp, ks, coef_of(w)))
+            call("bg_pack_weight_grouped", [w.detach() for w, _ in grp], wfs, wds, [m[0] for m in meta],
+                 [m[1] for m in meta], [m[2] for m in meta], [m[3] for m in meta], [m[4] for m in meta], len(grp))
+            for (w, cin_pad), wf, wd in zip(grp, wfs, wds):
+                self._conv[id(w)] = ((w._version, w.data_ptr(), cin_pad), wf, wd)
+
     def linear_t(self, w: torch.Tensor):
         """fp32 transpose (K, N) of an (N, K) linear weight: the input-gradient pass is a forward on it."""
         key = id(w)
@@ -255,6 +277,8 @@ def generator_forward(gen, packs: PackCache, z, noise, steps, alpha, z2=None, cr
             hs.append(linear_fwd(hs[-1], lin.weight, lin.bias, act=True))
         return hs
 
+    packs.refresh_convs([(sc.conv.weight, None) for k in range(steps)
+                         for sc in (gen.gen_blocks[k].conv_1, gen.gen_blocks[k].conv_2) if not (k == 0 and sc.is_initial)])
     maps = [mapping(z)]
     if z2 is not None:
         maps.append(mapping(z2))
@@ -505,6 +529,9 @@ def critic_forward(critic, packs: PackCache, images, steps, alpha):
     start = 8 - steps
     fade = alpha is not None and steps > 1
     a_mix = clamp_alpha(alpha) if fade else None
+    packs.refresh_convs([(cv.weight, None) for k in range(start, 7)
+                         for cv in (critic.conv_blocks[k].conv_1[0], critic.conv_blocks[k].conv_2[0])]
+                        + [(critic.conv_blocks[7].conv_1[1].weight, MBSTD_CPAD)])
     fr = critic.from_rgbs[start][0]
     c0 = CRITIC_CHANNELS[start][0]
     x0 = _bf16(B, R, R, c0, device=dev)

@@ -32,6 +32,10 @@ int bg_abi_version(void);
  * w_dgrad: bf16 [ks*ks flipped][Cin_pad][Cout] or NULL (same forward kernel then computes dL/dx). */
 int bg_pack_weight(const float* w, void* w_fprop, void* w_dgrad, int Cout, int Cin, int Cin_pad, int ks, float coef,
                    void* stream);
+/* bg_pack_weight for up to 32 layers in one launch (every conv weight of a network is stale after an optimizer step).
+ * All arguments are HOST arrays with one entry per layer; both packs are written for every layer. */
+int bg_pack_weight_grouped(const float* const* w, void* const* w_fprop, void* const* w_dgrad, const int* Cout,
+                           const int* Cin, const int* Cin_pad, const int* ks, const float* coef, int groups, void* stream);
 /* dw_packed: fp32 [ks*ks][Cout][Cin_pad] -> dw: fp32 (Cout,Cin,ks,ks) * coef (+= if accumulate). */
 int bg_unpack_wgrad(const float* dw_packed, float* dw, int Cout, int Cin, int Cin_pad, int ks, float coef,
                     int accumulate, void* stream);
