@@ -119,6 +119,16 @@ class Trainer:
         self.sync = sync_cls()
         self.critic._grad_ready_hook = self.sync.ready
 
+    style_mixing = False
+
+    def _mix(self, z):
+        """--style-mixing (opt-in extension, not in the reference): second latent = the batch rolled by one sample,
+        crossover block drawn per call; costs one more mapping-network pass and a second group of style FCs."""
+        if not self.style_mixing:
+            return {}
+        self._mix_count = getattr(self, "_mix_count", 0) + 1
+        return {"z2": torch.roll(z.detach(), 1, 0).requires_grad_(), "crossover": 1 + self._mix_count % (self.steps - 1)}
+
     def _read(self, loss, slot):
         """Device->host read of a loss (train.py:191,219 do .item() for the progress bar).  The copy into pinned
         memory is queued right behind the step's kernels and the VALUE is picked up one iteration later, when the
@@ -160,7 +170,8 @@ class Trainer:
         self._set_requires_grad(critic, True)
         self._set_requires_grad(gen, False)
         z = z_d.requires_grad_()
-        fake = gen(z, steps=steps, alpha=alpha)
+        mix = self._mix(z_d)
+        fake = gen(z, steps=steps, alpha=alpha, **mix)
         real_im = real.requires_grad_()
         pf = critic(fake.detach(), steps, alpha)
         pr = critic(real_im, steps, alpha)
@@ -174,7 +185,7 @@ class Trainer:
         self._set_requires_grad(critic, False)
         self._set_requires_grad(gen, True)
         z2 = z_g.requires_grad_()
-        fake2 = gen(z2, steps=steps, alpha=alpha)
+        fake2 = gen(z2, steps=steps, alpha=alpha, **self._mix(z_g))
         pred = critic(fake2, steps, alpha)
         g_loss = gen.get_r1_loss(pred)
         gen.zero_grad()
@@ -221,6 +232,7 @@ def run_b200(args):
         batch = args.batch
     R = 4 * 2 ** (steps - 1)
     tr = Trainer(steps, alpha, batch, device, bdist.GradSync)
+    tr.style_mixing = bool(args.style_mixing)
     g = torch.Generator(device="cpu").manual_seed(1234 + rank)
     POOL = 4
     host_real = [torch.rand(batch, 3, R, R, generator=g).mul_(2).sub_(1).pin_memory() for _ in range(POOL)]
@@ -362,6 +374,7 @@ def run_b200(args):
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "resolution": R, "progressive_steps": steps, "alpha": alpha,
                        "batch_per_gpu": batch, "global_batch": batch * world, "parallelism": f"dp{world}",
+                       "style_mixing": bool(args.style_mixing),
                        "optimizer": "Adam(lr=0.002, betas=(0,0.99)), both updates inside the step",
                        "loss": "non-saturating logistic + R1 (lambda=10) with double-backward every step",
                        "l2_policy": "inputs rotate over 4 batches; per-step working set (GBs of activations) >> 126 MB L2"},
@@ -524,6 +537,8 @@ def main():
     ap.add_argument("--workload", default="train256", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (debugging only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--style-mixing", action="store_true",
+                    help="train with the opt-in style-mixing extension (two latents, per-step crossover)")
     ap.add_argument("--no-sampling", action="store_true", help="skip the 512x512 sampling leg")
     args = ap.parse_args()
     if args.impl == "reference":

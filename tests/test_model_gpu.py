@@ -138,3 +138,46 @@ def test_full_size_forward_and_batch_independence(steps, batch):
         rolled = torch.roll(fake_o, shifts=m, dims=0).contiguous()
         pf_r = c(rolled, steps, None)
         assert (torch.roll(pf, shifts=m, dims=0) - pf_r).abs().max().item() < 2e-2 * scale
+
+
+@pytest.mark.parametrize("steps,crossover", [(4, 2), (6, 3), (6, 0), (5, 5)])
+def test_style_mixing_extension(steps, crossover):
+    """Opt-in extension (not in the reference): blocks >= crossover are styled by a second latent.  Oracle =
+    the reference's own sub-blocks driven block by block with a per-block w (gan_oracle.generator_forward(w_override=)).
+    Checks the image and the gradients w.r.t. both latents and the parameters; crossover >= steps must equal the plain
+    forward."""
+    U.no_tf32()
+    batch = 4
+    g, _ = U.build_models(5)
+    Gs = {k: v.cuda().requires_grad_() for k, v in O.make_state("gen", 5).items()}
+    z1 = O.make_latents(batch, 61).cuda().requires_grad_()
+    z2 = O.make_latents(batch, 62).cuda().requires_grad_()
+    noise = [n.cuda() for n in O.make_noise(batch, steps, 63)]
+    probe = torch.randn(batch, 3, 4 << (steps - 1), 4 << (steps - 1), device="cuda")
+    img = g(z1, noise=noise, steps=steps, alpha=None, z2=z2, crossover=crossover)
+    (img * probe).sum().backward()
+    zo1, zo2 = z1.detach().clone().requires_grad_(), z2.detach().clone().requires_grad_()
+    w1, w2 = O.mapping(Gs, zo1), O.mapping(Gs, zo2)
+    img_o = O.generator_forward(Gs, zo1, noise, steps, None, w_override=[w1 if k < crossover else w2 for k in range(8)])
+    (img_o * probe).sum().backward()
+    assert U.rel(img, img_o) < U.TOL_IMG
+    if crossover > 0:
+        assert U.cos(z1.grad, zo1.grad) > 0.97, U.cos(z1.grad, zo1.grad)
+    else:                                        # no block is styled by the first latent
+        assert zo1.grad is None and (z1.grad is None or z1.grad.abs().max().item() == 0.0)
+    if crossover < steps:
+        assert U.cos(z2.grad, zo2.grad) > 0.97, U.cos(z2.grad, zo2.grad)
+    else:
+        assert z2.grad is None or z2.grad.abs().max().item() == 0.0
+        with torch.no_grad():
+            plain = g(z1.detach(), noise=noise, steps=steps, alpha=None)
+        assert U.rel(img, plain) < 1.5e-2
+    worst = 1.0
+    for name, p in g.named_parameters():
+        ref = Gs[name].grad
+        if p.grad is None:
+            assert ref is None or ref.abs().max().item() == 0.0, name
+            continue
+        if ref.norm().item() > 0:
+            worst = min(worst, U.cos(p.grad, ref))
+    assert worst > 0.93, worst
