@@ -56,6 +56,7 @@ int launch_linear_grouped(int, const float*, const float* const*, const float* c
                           float* const*, const int*, const float*, int, int, int, int, float, float*, cudaStream_t);
 int launch_pack_weight_grouped(const float* const*, void* const*, void* const*, const int*, const int*, const int*,
                                const int*, const float*, int, cudaStream_t);
+int launch_pack_weight_pool4(const float*, void*, int, int, float, cudaStream_t);
 }  // namespace bg
 
 #define S(stream) reinterpret_cast<cudaStream_t>(stream)
@@ -130,6 +131,22 @@ int bg_conv_pool_fprop(const void* x, const void* wpack, void* out, int N, int H
   }
   return bg::launch_conv_halo(x, wpack, out, N, H, W, Cin, Cout, bias, nullptr, nullptr, gate_src, act, 1, slope,
                               nullptr, 0, nullptr, 0, 0, S(stream));
+}
+int bg_pack_weight_pool4(const float* w, void* w16, int Cout, int Cin, float coef, void* stream) {
+  return bg::launch_pack_weight_pool4(w, w16, Cout, Cin, coef, S(stream));
+}
+int bg_conv_pool4_fprop(const void* x, const void* w16, void* out, int N, int H, int W, int Cin, int Cout, const float* bias,
+                        const void* gate_src, int act, float slope, void* stream) {
+  if (!bg_conv_pool4_supported(N, H, W, Cin, Cout)) {
+    bg::set_error("conv_pool4_fprop: needs H,W >= 32 (powers of two), Cin %% 32 == 0, Cout %% 16 == 0 (H %d W %d Cin %d Cout %d)",
+                  H, W, Cin, Cout);
+    return 2;
+  }
+  return bg::launch_conv_halo(x, w16, out, N, H, W, Cin, Cout, bias, nullptr, nullptr, gate_src, act, 2, slope, nullptr, 0,
+                              nullptr, 0, 0, S(stream));
+}
+int bg_conv_pool4_supported(int N, int H, int W, int Cin, int Cout) {
+  return (H >= 32 && W >= 32 && Cin % 32 == 0 && bg::conv_halo_supported(N, H / 2, W / 2, Cin, Cout, 3)) ? 1 : 0;
 }
 int bg_conv_fprop_tapwise(const void* x, const void* wpack, void* out, int N, int H, int W, int Cin, int Cout, int ksize,
                           const float* bias, const float* noise, const float* noise_w, const void* gate_src, int act,

@@ -79,6 +79,31 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
   }
 }
 
+// conv3x3 (pad 1) followed by AvgPool2d(2) (CriticBlock.conv_2, gan.py:258-260) is a 4x4 stride-2 convolution (pad 1)
+// whose kernel is the quarter sum of the four shifted copies of the 3x3 one:
+//   W4[a][b] = 1/4 * sum_{dy,dx in {0,1}} W3[a-dy][b-dx]        (terms with an index outside 0..2 drop out)
+// w: fp32 (Cout, Cin, 3, 3) -> w16: bf16 [a*4+b][Cout][Cin], equalized coefficient folded in; summed in fp32, rounded once.
+__global__ void pack_weight_pool4_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ w16, int Cout, int Cin,
+                                         float coef) {
+  const size_t total = (size_t)16 * Cout * Cin;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin);
+    const int co = (int)((i / Cin) % Cout);
+    const int tap = (int)(i / ((size_t)Cin * Cout));
+    const int a = tap >> 2, b = tap & 3;
+    const float* w3 = w + ((size_t)co * Cin + ci) * 9;
+    float acc = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int ky = a - dy, kx = b - dx;
+        if (ky >= 0 && ky <= 2 && kx >= 0 && kx <= 2) acc += w3[ky * 3 + kx];
+      }
+    w16[i] = __float2bfloat16_rn(0.25f * coef * acc);
+  }
+}
+
 // All stale packs of a network in ONE launch (after an optimizer step every conv weight of the active stage is stale:
 // 13..26 layers).  Group g owns blocks [blk0[g], blk0[g+1]).
 constexpr int kMaxPackGroups = 32;
@@ -946,6 +971,13 @@ int launch_pack_weight_grouped(const float* const* w, void* const* wf, void* con
   }
   G.blk0[groups] = blocks;
   pack_weight_grouped_kernel<<<blocks, kBlock, 0, s>>>(G);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_pack_weight_pool4(const float* w, void* w16, int Cout, int Cin, float coef, cudaStream_t s) {
+  BG_REQUIRE(Cout > 0 && Cin > 0, "pack_weight_pool4: bad shape");
+  pack_weight_pool4_kernel<<<grid_for((size_t)16 * Cout * Cin), kBlock, 0, s>>>(w, (__nv_bfloat16*)w16, Cout, Cin, coef);
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

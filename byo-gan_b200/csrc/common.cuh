@@ -38,6 +38,10 @@ int num_sms();
 // for dims 1..rank-1.  swizzle_bytes in {0,32,64,128}.  Returns 0 on success.
 int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
+// Same with a traversal stride per dimension (box = span in elements, tile = ceil(box / stride) elements).
+int make_tmap_bf16_strided(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides,
+                           int swizzle_bytes);
 
 #ifdef __CUDACC__
 

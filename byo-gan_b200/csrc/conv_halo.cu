@@ -84,6 +84,16 @@ struct HaloParams {
   const float* bias_tab;
   int upsample;
   uint32_t patch_bytes;   // one low-resolution 10x10 patch stage (upsample mode)
+  // pool4 mode: conv3x3 followed by AvgPool2d(2) (CriticBlock.conv_2, gan.py:258-260) computed as ONE 4x4 stride-2
+  // convolution (16 taps, weights = quarter sums of the shifted 3x3 kernel): N, H, W are the POOLED output's, the
+  // input is (N, 2H, 2W, Cin).  The 34x34 input region of a tile is loaded as four 17x17 parity-phase tiles (TMA boxes
+  // with element stride 2 along W and H, one pipeline stage each), so that tap (a, b) is phase (a&1, b&1) shifted by
+  // (a>>1, b>>1) pixel rows — 2.25x fewer MMAs than conv-then-pool.
+  int pool4;
+  int pool4_tma;  // == pool4: the four phase tiles are loaded by strided TMA boxes, one pipeline stage each
+  int taps;       // 9, or 16 in pool4 mode
+  int Hin, Win;
+  uint32_t phase_bytes;
 };
 
 struct TileCoord {
@@ -150,7 +160,85 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // uniform registers), one elected lane executes the tcgen05 instructions, descriptors are 64-bit values advanced
 // by compile-time constants, and the k-steps / taps are unrolled.
 // ---------------------------------------------------------------------------------------------------------
+// Descriptor offset (16-byte units) of the A view of one tap.  9 taps: the 18x18 halo shifted by (ky, kx) pixel rows.
+// 16 taps (pool4): parity-phase tile (a&1, b&1) of the 34x34 region, shifted by (a>>1, b>>1) inside its 17x17 pixels.
+template <int TAPS, uint32_t RBU>
+__device__ __forceinline__ uint64_t a_tap_offset(int tap, uint32_t phase_units) {
+  if (TAPS == 9) return (uint64_t)(((tap / 3) * kHalo + (tap % 3)) * RBU);
+  const int a = tap >> 2, b = tap & 3;
+  return (uint64_t)((uint32_t)((a & 1) * 2 + (b & 1)) * phase_units + (uint32_t)(((a >> 1) * 17 + (b >> 1)) * RBU));
+}
+
+// pool4 with TMA feed: the A pipeline unit is ONE parity-phase tile (17x17 pixels x kc channels); phase ph = 2*py + px
+// serves the four taps (a, b) = (py + 2i, px + 2j), i, j in {0, 1}, whose view is the tile shifted by (i, j) pixels.
+__device__ __forceinline__ int pool4_tap(int ph, int t4) { return ((ph >> 1) + 2 * (t4 >> 1)) * 4 + (ph & 1) + 2 * (t4 & 1); }
+
 template <int KSTEPS>
+__device__ __forceinline__ void mma_issue_loop_pool4(const HaloParams& p, uint8_t* a_base, uint8_t* b_base,
+                                                     uint64_t* b_full, uint64_t* b_empty, uint64_t* a_full,
+                                                     uint64_t* a_empty, uint64_t* tmem_full, uint64_t* tmem_empty,
+                                                     uint32_t tmem_base) {
+  constexpr uint32_t kRBU = 2u * KSTEPS;
+  const uint32_t idesc = umma_idesc_bf16(128, p.block_n, 0, 0);
+  const uint64_t a_desc0 = umma_desc(smem_u32(a_base), 16u, p.a_sbo, p.a_layout);
+  const uint64_t b_desc0 = umma_desc(smem_u32(b_base), 16u, p.b_sbo, p.b_layout);
+  const uint32_t a_stage_step = p.a_stage_bytes >> 4;
+  const uint32_t b_tile_step = p.b_tile_bytes >> 4;
+  const bool leader = elect_one();
+  int tile_lo, tile_hi, tile_step;
+  tile_range(p, tile_lo, tile_hi, tile_step);
+  int bstage = 0, astage = 0, acc = 0;
+  uint32_t bphase = 0, aphase = 0, acc_phase = 0;
+  for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
+    mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+    tc_fence_after();
+    const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+    uint32_t accum = 0u;
+    for (int kcx = 0; kcx < p.k_chunks; ++kcx) {
+      for (int ph = 0; ph < 4; ++ph) {
+        mbar_wait(&a_full[astage], aphase);
+        tc_fence_after();
+        const uint64_t a_stage = a_desc0 + (uint64_t)((uint32_t)astage * a_stage_step);
+#pragma unroll
+        for (int t4 = 0; t4 < 4; ++t4) {
+          mbar_wait(&b_full[bstage], bphase);
+          tc_fence_after();
+          if (leader) {
+            const uint64_t a_tap = a_stage + (uint64_t)(((t4 >> 1) * (kTile + 1) + (t4 & 1)) * kRBU);
+            const uint64_t b_tap = b_desc0 + (uint64_t)((uint32_t)bstage * b_tile_step);
+            if (!(p.debug & 2)) {
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k) {
+#pragma unroll
+                for (int half = 0; half < 2; ++half)
+                  tc_mma_bf16(d_tmem + (uint32_t)half * 128u, a_tap + (uint64_t)(half * 8 * kRBU + k * 2),
+                              b_tap + (uint64_t)(k * 2), idesc, k == 0 ? accum : 1u);
+              }
+            }
+            tc_commit(&b_empty[bstage]);
+          }
+          accum = 1u;
+          if (++bstage == p.b_stages) {
+            bstage = 0;
+            bphase ^= 1u;
+          }
+        }
+        if (leader) tc_commit(&a_empty[astage]);
+        __syncwarp();
+        if (++astage == p.a_stages) {
+          astage = 0;
+          aphase ^= 1u;
+        }
+      }
+    }
+    if (leader) tc_commit(&tmem_full[acc]);
+    __syncwarp();
+    acc ^= 1;
+    if (acc == 0) acc_phase ^= 1u;
+  }
+}
+
+template <int KSTEPS, int TAPS>
 __device__ __forceinline__ void mma_issue_loop(const HaloParams& p, uint8_t* a_base, uint8_t* b_base, uint64_t* b_full,
                                                uint64_t* b_empty, uint64_t* a_full, uint64_t* a_empty,
                                                uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base) {
@@ -159,6 +247,7 @@ __device__ __forceinline__ void mma_issue_loop(const HaloParams& p, uint8_t* a_b
   const uint64_t a_desc0 = umma_desc(smem_u32(a_base), 16u, p.a_sbo, p.a_layout);
   const uint64_t b_desc0 = umma_desc(smem_u32(b_base), 16u, p.b_sbo, p.b_layout);
   const uint32_t a_stage_step = p.a_stage_bytes >> 4;
+  const uint32_t phase_units = p.phase_bytes >> 4;
   const uint32_t b_tile_step = p.b_tile_bytes >> 4;
   const bool leader = elect_one();
   int tile_lo, tile_hi, tile_step;
@@ -192,12 +281,12 @@ __device__ __forceinline__ void mma_issue_loop(const HaloParams& p, uint8_t* a_b
       tc_fence_after();
       const uint64_t a_stage = a_desc0 + (uint64_t)((uint32_t)astage * a_stage_step);
       if (p.b_resident) {
-        const uint64_t b_chunk = b_desc0 + (uint64_t)((uint32_t)(kcx * 9) * b_tile_step);
+        const uint64_t b_chunk = b_desc0 + (uint64_t)((uint32_t)(kcx * TAPS) * b_tile_step);
         if (leader) {
           if (!(p.debug & 2)) {
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              const uint64_t a_tap = a_stage + (uint64_t)(((tap / 3) * kHalo + (tap % 3)) * kRBU);
+            for (int tap = 0; tap < TAPS; ++tap) {
+              const uint64_t a_tap = a_stage + a_tap_offset<TAPS, kRBU>(tap, phase_units);
               const uint64_t b_tap = b_chunk + (uint64_t)((uint32_t)tap * b_tile_step);
               // alternate the two accumulators (MMA halves): back-to-back MMAs into the SAME accumulator serialise
               // on the tensor pipe's latency (~60 clk), which is longer than a small-N MMA itself
@@ -216,11 +305,11 @@ __device__ __forceinline__ void mma_issue_loop(const HaloParams& p, uint8_t* a_b
         }
         accum = 1u;
       } else {
-        for (int tap = 0; tap < 9; ++tap) {
+        for (int tap = 0; tap < TAPS; ++tap) {
           mbar_wait(&b_full[bstage], bphase);
           tc_fence_after();
           if (leader) {
-            const uint64_t a_tap = a_stage + (uint64_t)(((tap / 3) * kHalo + (tap % 3)) * kRBU);
+            const uint64_t a_tap = a_stage + a_tap_offset<TAPS, kRBU>(tap, phase_units);
             const uint64_t b_tap = b_desc0 + (uint64_t)((uint32_t)bstage * b_tile_step);
             if (!(p.debug & 2)) {
 #pragma unroll
@@ -270,12 +359,31 @@ __device__ __forceinline__ void halo_tma_loop(const HaloParams& p, const CUtenso
   for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
     const TileCoord t = decode_tile(p, tile);
     for (int kcx = 0; kcx < p.k_chunks; ++kcx) {
+      if (p.pool4) {
+        // four pipeline units per chunk, one per parity-phase tile of the 34x34 input region: the tensor map walks W
+        // and H with element stride 2, so each unit is a dense 17x17-pixel tile
+        for (int ph = 0; ph < 4; ++ph) {
+          mbar_wait(&a_empty[stage], phase ^ 1u);
+          mbar_expect_tx(&a_full[stage], p.a_tx_bytes);
+          if (p.debug & 4)
+            mbar_arrive_tx_debug(&a_full[stage], p.a_tx_bytes);
+          else
+            tma_load_4d(tmap_x, &a_full[stage], a_base + (size_t)stage * p.a_stage_bytes, kcx * p.kc,
+                        2 * t.w0 - 1 + (ph & 1), 2 * t.h0 - 1 + (ph >> 1), t.n);
+          if (++stage == p.a_stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        continue;
+      }
       mbar_wait(&a_empty[stage], phase ^ 1u);
       mbar_expect_tx(&a_full[stage], p.a_tx_bytes);
-      if (!(p.debug & 4))
-        tma_load_4d(tmap_x, &a_full[stage], a_base + (size_t)stage * p.a_stage_bytes, kcx * p.kc, t.w0 - 1, t.h0 - 1, t.n);
-      else
+      if (p.debug & 4) {
         mbar_arrive_tx_debug(&a_full[stage], p.a_tx_bytes);
+      } else {
+        tma_load_4d(tmap_x, &a_full[stage], a_base + (size_t)stage * p.a_stage_bytes, kcx * p.kc, t.w0 - 1, t.h0 - 1, t.n);
+      }
       if (++stage == p.a_stages) {
         stage = 0;
         phase ^= 1u;
@@ -459,7 +567,7 @@ __device__ __forceinline__ void stats_flush(const HaloParams& p, float* slices, 
   asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * kEpiWarps) : "memory");
 }
 
-template <bool kStats, bool kUp>
+template <bool kStats, int kFeed>     // kFeed: 0 TMA halo (plain and pool4), 1 upsample producers
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                  const HaloParams p) {
@@ -468,13 +576,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
   // carve: [B region (1024-aligned tiles)] [A stages] [epilogue transpose stages] [aux]
-  const int b_tiles = p.b_resident ? p.k_chunks * 9 : p.b_stages;
+  const int b_tiles = p.b_resident ? p.k_chunks * p.taps : p.b_stages;
   uint8_t* b_base = smem;
   uint8_t* a_base = b_base + (size_t)b_tiles * p.b_tile_bytes;
   uint8_t* patch_base = a_base + (size_t)p.a_stages * p.a_stage_bytes;
   patch_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(patch_base) + 127) & ~uintptr_t(127));
   uint8_t* epi_base = patch_base + (p.upsample ? (size_t)kPatchStages * p.patch_bytes : 0);
   epi_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(epi_base) + 127) & ~uintptr_t(127));
+  constexpr bool kUp = kFeed != 0;        // warps 10..17 feed the halo instead of being the second epilogue set
   const int kEpiWarpsAll = kUp ? kEpiWarps : kEpiWarps * p.epi_sets;
   uint8_t* aux = epi_base + (size_t)kEpiWarpsAll * 32 * p.epi_row_bytes;
   uint64_t* b_full = reinterpret_cast<uint64_t*>(aux);
@@ -540,10 +649,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
           const int wn = p.per_sample_w ? decode_tile(p, tile).n : 0;
           if (wn == cur) continue;
           if (loads > 0) mbar_wait(&b_empty[0], (loads - 1u) & 1u);
-          mbar_expect_tx(&b_full[0], (uint32_t)(p.k_chunks * 9) * p.b_tx_bytes);
+          mbar_expect_tx(&b_full[0], (uint32_t)(p.k_chunks * p.taps) * p.b_tx_bytes);
           for (int kcx = 0; kcx < p.k_chunks; ++kcx)
-            for (int tap = 0; tap < 9; ++tap)
-              tma_load_4d(&tmap_w, &b_full[0], b_base + (size_t)(kcx * 9 + tap) * p.b_tile_bytes, kcx * p.kc, 0, tap, wn);
+            for (int tap = 0; tap < p.taps; ++tap)
+              tma_load_4d(&tmap_w, &b_full[0], b_base + (size_t)(kcx * p.taps + tap) * p.b_tile_bytes, kcx * p.kc, 0, tap,
+                          wn);
           cur = wn;
           ++loads;
         }
@@ -553,7 +663,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
           const TileCoord t = decode_tile(p, tile);
           for (int kcx = 0; kcx < p.k_chunks; ++kcx) {
-            for (int tap = 0; tap < 9; ++tap) {
+            for (int ti = 0; ti < p.taps; ++ti) {
+              const int tap = p.pool4_tma ? pool4_tap(ti >> 2, ti & 3) : ti;      // the order the MMA warp consumes them
               mbar_wait(&b_empty[stage], phase ^ 1u);
               mbar_expect_tx(&b_full[stage], p.b_tx_bytes);
               tma_load_4d(&tmap_w, &b_full[stage], b_base + (size_t)stage * p.b_tile_bytes, kcx * p.kc, t.co0, tap,
@@ -569,9 +680,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    if (p.kc == 64) mma_issue_loop<4>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
-    else if (p.kc == 32) mma_issue_loop<2>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
-    else mma_issue_loop<1>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+    if (kFeed == 0 && !kStats && p.pool4) {
+      if (p.kc == 64) mma_issue_loop_pool4<4>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+      else mma_issue_loop_pool4<2>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+    } else if (p.kc == 64) mma_issue_loop<4, 9>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+    else if (p.kc == 32) mma_issue_loop<2, 9>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+    else mma_issue_loop<1, 9>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
   } else if (warp < 2 + kEpiWarpsAll) {
     // ------------------------------ epilogue ------------------------------
     // Warp e = warp - 2: TMEM lane quarter q = warp & 3 (hardware rule), MMA half = e / 4.  Lane i holds MMA row
@@ -812,18 +926,31 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
                      const float* bias, const float* noise, const float* noise_w, const void* gate_src, int act,
                      int pool, float slope, float* stats, int stats_mode, const float* bias_tab, int per_sample_w,
                      int upsample, cudaStream_t stream) {
-  BG_REQUIRE(conv_halo_supported(N, H, W, Cin, Cout, 3), "conv_halo: unsupported shape N %d H %d W %d Cin %d Cout %d", N,
+  // pool: 0 none, 1 conv3x3 then 2x2 average in the epilogue, 2 "pool4": the same function as ONE 4x4 stride-2 conv
+  // (wpack is then the 16-tap pack of bg_pack_weight_pool4).  H, W are always the conv INPUT's.
+  const bool pool4 = pool == 2;
+  if (pool4) {
+    BG_REQUIRE(H >= 32 && W >= 32 && Cin % 32 == 0 && !upsample && stats == nullptr && !per_sample_w && noise == nullptr,
+               "conv_halo pool4: needs H,W >= 32, Cin %% 32 == 0 and no upsample / stats / noise (H %d W %d Cin %d)", H, W, Cin);
+    pool = 0;
+  }
+  const int Hc = pool4 ? H / 2 : H, Wc = pool4 ? W / 2 : W;      // the map the tiles and the epilogue work on
+  BG_REQUIRE(conv_halo_supported(N, Hc, Wc, Cin, Cout, 3), "conv_halo: unsupported shape N %d H %d W %d Cin %d Cout %d", N,
              H, W, Cin, Cout);
   BG_REQUIRE(!(upsample && pool), "conv_halo: upsample and pool cannot be combined");
   HaloParams p;
   memset(&p, 0, sizeof(p));
-  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
-  p.tw_shift = ilog2(W / kTile);
-  p.th_shift = ilog2(H / kTile);
+  p.N = N; p.H = Hc; p.W = Wc; p.Cin = Cin; p.Cout = Cout;
+  p.pool4 = pool4 ? 1 : 0;
+  p.taps = pool4 ? 16 : 9;
+  p.Hin = H; p.Win = W;
+  p.tw_shift = ilog2(Wc / kTile);
+  p.th_shift = ilog2(Hc / kTile);
   const int bn_ch = pick_block_n(Cout);
   p.block_n = bn_ch;
   const int n_blocks = Cout / bn_ch;
   p.nb_shift = ilog2(n_blocks);
+  p.pool4_tma = pool4 ? 1 : 0;
   p.kc = (Cin % 64 == 0) ? 64 : (Cin % 32 == 0 ? 32 : 16);
   p.k_chunks = Cin / p.kc;
   p.cpp_shift = p.kc == 64 ? 3 : (p.kc == 32 ? 2 : 1);
@@ -833,14 +960,22 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
   p.b_tx_bytes = (uint32_t)p.block_n * row_bytes;
   p.b_tile_bytes = (p.b_tx_bytes + 1023u) & ~1023u;
   p.a_layout = p.b_layout;                                   // same row width (kc bf16) on both operands
-  p.a_sbo = (uint32_t)kHalo * row_bytes;                     // next 8-pixel group = one halo row down
+  p.a_sbo = (uint32_t)(pool4 ? kTile + 1 : kHalo) * row_bytes;   // next 8-pixel group = one (phase-)tile row down
   p.a_tx_bytes = (uint32_t)kHaloPix * row_bytes;
-  p.a_stage_bytes = (p.a_tx_bytes + 1023u) & ~1023u;
+  p.phase_bytes = ((uint32_t)((kTile + 1) * (kTile + 1)) * row_bytes + 1023u) & ~1023u;
+  p.a_stage_bytes = pool4 ? 4u * p.phase_bytes : ((p.a_tx_bytes + 1023u) & ~1023u);
   p.epi_row_bytes = (uint32_t)(bn_ch >= 64 ? 64 : bn_ch) * 2u;
   p.upsample = upsample ? 1 : 0;
+  if (p.pool4_tma) {
+    // the pipeline unit is one phase tile (4 per chunk); two epilogue sets: keep the transpose stages at 32 KB
+    p.a_tx_bytes = (uint32_t)((kTile + 1) * (kTile + 1)) * row_bytes;
+    p.a_stage_bytes = p.phase_bytes;
+    if (p.epi_row_bytes > 64u) p.epi_row_bytes = 64u;
+  }
+  const bool feed_warps = p.upsample != 0;                   // warps 10..17 build the halo: one epilogue set
   p.patch_bytes = (uint32_t)(kPatch * kPatch) * (uint32_t)p.kc * 2u;
   const uint32_t patch_total = p.upsample ? (uint32_t)kPatchStages * p.patch_bytes + 128u : 0u;
-  const uint32_t resident_bytes = (uint32_t)p.k_chunks * 9u * p.b_tile_bytes;
+  const uint32_t resident_bytes = (uint32_t)(p.k_chunks * p.taps) * p.b_tile_bytes;
   // Shared-memory plan.  Two epilogue sets (plain mode) double the transpose stages and the stats slices; fall back
   // to one set when that would cost the weight residency or does not fit at all.
   struct Plan {
@@ -861,12 +996,12 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
     const uint32_t total = 227u * 1024u - fixed;
     // prefer resident weights (3 halo stages if they fit, else 2); otherwise stream the weights past 3 halo stages
     pl.a_stages = 3;
-    if (n_blocks == 1) {
+    if (n_blocks == 1 && !p.pool4_tma) {
       if (resident_bytes + 3u * p.a_stage_bytes <= total) {
         pl.resident = 1;
         // small stages (kc = 16 / 32): more stages, until ~96 KB of halo loads can be in flight (HBM latency x per-SM
         // bandwidth), as far as shared memory allows
-        if (!p.upsample) {
+        if (!feed_warps) {
           while (pl.a_stages < kMaxAStages && (uint32_t)(pl.a_stages - 1) * p.a_stage_bytes < 96u * 1024u &&
                  resident_bytes + (uint32_t)(pl.a_stages + 1) * p.a_stage_bytes <= total)
             ++pl.a_stages;
@@ -881,10 +1016,13 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
       pl.ok = true;
     } else {
       // streamed weights: 3 halo stages when at least 3 weight stages still fit, else 2 halo stages
-      int st = total > 3u * p.a_stage_bytes ? (int)((total - 3u * p.a_stage_bytes) / p.b_tile_bytes) : 0;
-      if (st < 3) {
-        pl.a_stages = 2;
-        st = total > 2u * p.a_stage_bytes ? (int)((total - 2u * p.a_stage_bytes) / p.b_tile_bytes) : 0;
+      if (p.pool4_tma) pl.a_stages = 4;                      // phase-sized stages: one whole chunk in flight
+      int st = total > (uint32_t)pl.a_stages * p.a_stage_bytes
+                   ? (int)((total - (uint32_t)pl.a_stages * p.a_stage_bytes) / p.b_tile_bytes) : 0;
+      while (st < 3 && pl.a_stages > 2) {
+        --pl.a_stages;
+        st = total > (uint32_t)pl.a_stages * p.a_stage_bytes
+                 ? (int)((total - (uint32_t)pl.a_stages * p.a_stage_bytes) / p.b_tile_bytes) : 0;
       }
       if (st > kMaxBStages) st = kMaxBStages;
       pl.b_stages = st;
@@ -893,7 +1031,7 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
     return pl;
   };
   Plan plan = make_plan(1);
-  if (!p.upsample) {
+  if (!feed_warps) {
     const Plan two = make_plan(kEpiSets);
     if (two.ok && (two.resident || !plan.resident || !plan.ok)) plan = two;
   }
@@ -904,7 +1042,7 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
   p.b_stages = plan.b_stages;
   p.b_resident = plan.resident;
   BG_REQUIRE(planned, "conv_halo: weight tile does not fit shared memory");
-  p.num_tiles = (W / kTile) * (H / kTile) * N * n_blocks;
+  p.num_tiles = (Wc / kTile) * (Hc / kTile) * N * n_blocks;
   p.x = reinterpret_cast<const __nv_bfloat16*>(x);
   p.bias = bias; p.noise = noise; p.noise_w = noise_w;
   p.gate_src = reinterpret_cast<const __nv_bfloat16*>(gate_src);
@@ -930,8 +1068,8 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
   CUtensorMap tmw;
   {
     // [sample][tap][Cout][Cin]; the sample dimension has extent 1 for the ordinary shared pack
-    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Cout, 9ull, (uint64_t)(p.per_sample_w ? N : 1)};
-    uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)Cout * Cin * 2, (uint64_t)9 * Cout * Cin * 2};
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)p.taps, (uint64_t)(p.per_sample_w ? N : 1)};
+    uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)Cout * Cin * 2, (uint64_t)p.taps * Cout * Cin * 2};
     uint32_t box[4] = {(uint32_t)p.kc, (uint32_t)p.block_n, 1u, 1u};
     if (make_tmap_bf16(&tmw, wpack, 4, dims, str, box, (int)row_bytes) != 0) return 1;
   }
@@ -942,26 +1080,31 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
     const int Hx = upsample ? H / 2 : H, Wx = upsample ? W / 2 : W;
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Wx, (uint64_t)Hx, (uint64_t)N};
     uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)Wx * Cin * 2, (uint64_t)Hx * Wx * Cin * 2};
-    uint32_t box[4] = {(uint32_t)p.kc, (uint32_t)(upsample ? 8 : kHalo), (uint32_t)(upsample ? 8 : kHalo), 1u};
-    if (make_tmap_bf16(&tmx, x, 4, dims, str, box, (int)row_bytes) != 0) return 1;
+    uint32_t box[4] = {(uint32_t)p.kc, (uint32_t)(feed_warps ? 8 : kHalo), (uint32_t)(feed_warps ? 8 : kHalo), 1u};
+    if (p.pool4_tma) {
+      // every other pixel of a 34-wide span -> 17 x 17 pixels per phase tile
+      uint32_t box2[4] = {(uint32_t)p.kc, 2u * (kTile + 1), 2u * (kTile + 1), 1u};
+      uint32_t est[4] = {1u, 2u, 2u, 1u};
+      if (make_tmap_bf16_strided(&tmx, x, 4, dims, str, box2, est, (int)row_bytes) != 0) return 1;
+    } else if (make_tmap_bf16(&tmx, x, 4, dims, str, box, (int)row_bytes) != 0) return 1;
   }
-  const size_t b_tiles = p.b_resident ? (size_t)p.k_chunks * 9 : (size_t)p.b_stages;
+  const size_t b_tiles = p.b_resident ? (size_t)p.k_chunks * p.taps : (size_t)p.b_stages;
   const size_t smem_bytes = b_tiles * p.b_tile_bytes + (size_t)p.a_stages * p.a_stage_bytes + patch_total + epi_bytes +
                             aux_bytes + 1024;
   BG_REQUIRE(smem_bytes <= 227 * 1024, "conv_halo: shared memory budget exceeded (%zu)", smem_bytes);
   static bool attr_set = false;
   if (!attr_set) {
-    BG_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    BG_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    BG_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    BG_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BG_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BG_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BG_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BG_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  if (p.stats_mode && p.upsample) conv_halo_kernel<true, true><<<grid, kThreads, smem_bytes, stream>>>(tmw, tmx, p);
-  else if (p.stats_mode) conv_halo_kernel<true, false><<<grid, kThreads, smem_bytes, stream>>>(tmw, tmx, p);
-  else if (p.upsample) conv_halo_kernel<false, true><<<grid, kThreads, smem_bytes, stream>>>(tmw, tmx, p);
-  else conv_halo_kernel<false, false><<<grid, kThreads, smem_bytes, stream>>>(tmw, tmx, p);
+  if (p.stats_mode && p.upsample) conv_halo_kernel<true, 1><<<grid, kThreads, smem_bytes, stream>>>(tmw, tmx, p);
+  else if (p.stats_mode) conv_halo_kernel<true, 0><<<grid, kThreads, smem_bytes, stream>>>(tmw, tmx, p);
+  else if (p.upsample) conv_halo_kernel<false, 1><<<grid, kThreads, smem_bytes, stream>>>(tmw, tmx, p);
+  else conv_halo_kernel<false, 0><<<grid, kThreads, smem_bytes, stream>>>(tmw, tmx, p);
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -56,6 +56,14 @@ static EncodeTiledFn encode_fn() {
 
 int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
+  return make_tmap_bf16_strided(map, base, rank, dims, strides_bytes, box, nullptr, swizzle_bytes);
+}
+
+// elem_strides (may be null = all 1): traversal stride per dimension; box[] is then the SPAN in elements and the tile
+// written to shared memory has ceil(box / stride) elements along that dimension.
+int make_tmap_bf16_strided(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides,
+                           int swizzle_bytes) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -68,7 +76,7 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t*
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bdim[i] = box[i];
-    estr[i] = 1;
+    estr[i] = elem_strides ? elem_strides[i] : 1;
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
   CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_NONE;

@@ -80,6 +80,13 @@ int bg_to_rgb_adain(const void* a, const float* stats, const float* style, const
  * Needs H,W >= 16. */
 int bg_conv_pool_fprop(const void* x, const void* wpack, void* out, int N, int H, int W, int Cin, int Cout,
                        const float* bias, const void* gate_src, int act, float slope, void* stream);
+/* The same function as bg_conv_pool_fprop computed as ONE 4x4 stride-2 convolution (2.25x fewer MACs): w16 is the
+ * 16-tap pack of bg_pack_weight_pool4 (quarter sums of the shifted 3x3 kernel, bf16 [16][Cout][Cin]).  x: (N,H,W,Cin),
+ * out / gate_src: (N,H/2,W/2,Cout).  Needs H,W >= 32 and Cin % 32 == 0 (bg_conv_pool4_supported). */
+int bg_pack_weight_pool4(const float* w, void* w16, int Cout, int Cin, float coef, void* stream);
+int bg_conv_pool4_fprop(const void* x, const void* w16, void* out, int N, int H, int W, int Cin, int Cout, const float* bias,
+                        const void* gate_src, int act, float slope, void* stream);
+int bg_conv_pool4_supported(int N, int H, int W, int Cin, int Cout);
 /* bg_conv_fprop picks the halo-resident kernel (conv_halo.cu) for 3x3 at H,W >= 16 and the tap-wise TMA kernel
  * (conv_fprop.cu) otherwise; this entry forces the tap-wise kernel (A/B tests, small maps, 1x1). */
 int bg_conv_fprop_tapwise(const void* x, const void* wpack, void* out, int N, int H, int W, int Cin, int Cout,

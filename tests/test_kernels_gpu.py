@@ -350,3 +350,37 @@ def test_conv3x3_pool_fused(shape, tangent):
     torch.cuda.synchronize()
     err = relerr(nchw(out), ref)
     assert err < 6e-3, f"fused conv+pool {shape} tangent={tangent}: rel-L2 {err:.3e}"
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 32, 64, 64), (1, 64, 64, 32, 64), (3, 32, 32, 128, 128), (1, 64, 64, 256, 256),
+                                   (2, 32, 32, 512, 512), (2, 64, 64, 64, 32), (1, 128, 128, 64, 64)])
+@pytest.mark.parametrize("tangent", [False, True])
+def test_conv_pool_as_4x4_stride2(shape, tangent):
+    """CriticBlock.conv_2 (gan.py:258-262): conv3x3 -> AvgPool2d(2) -> LeakyReLU computed as ONE 4x4 stride-2 conv
+    (bg_pack_weight_pool4 + bg_conv_pool4_fprop), against torch's conv2d + avg_pool2d in fp32; also the pack itself."""
+    n, h, w_, ci, co = shape
+    torch.manual_seed(0)
+    x = nhwc(torch.randn(n, ci, h, w_, device=DEV))
+    w = torch.randn(co, ci, 3, 3, device=DEV)
+    coef = math.sqrt(2 / (ci * 9))
+    w16 = torch.empty(16, co, ci, dtype=torch.bfloat16, device=DEV)
+    bgn.call("bg_pack_weight_pool4", w, w16, co, ci, coef)
+    w4 = torch.zeros(co, ci, 4, 4, device=DEV)
+    for dy in range(2):
+        for dx in range(2):
+            w4[:, :, dy:dy + 3, dx:dx + 3] += 0.25 * coef * w
+    # fp32 summation order may differ by an ulp before the single bf16 rounding: allow one bf16 ulp
+    assert (w16.float() - w4.permute(2, 3, 0, 1).reshape(16, co, ci)).abs().max().item() <= 2 ** -8 * w4.abs().max().item()
+    out = torch.empty(n, h // 2, w_ // 2, co, dtype=torch.bfloat16, device=DEV)
+    conv = F.conv2d(nchw(x), w * coef, None, padding=1)
+    if tangent:
+        y2 = nhwc(torch.randn(n, co, h // 2, w_ // 2, device=DEV))
+        bgn.call("bg_conv_pool4_fprop", x, w16, out, n, h, w_, ci, co, None, y2, 0, 0.2)
+        ref = F.avg_pool2d(conv, 2) * torch.where(nchw(y2) > 0, 1.0, 0.2)
+    else:
+        bias = torch.randn(co, device=DEV) * 0.1
+        bgn.call("bg_conv_pool4_fprop", x, w16, out, n, h, w_, ci, co, bias, None, 1, 0.2)
+        ref = F.leaky_relu(F.avg_pool2d(conv + bias.view(1, -1, 1, 1), 2), 0.2)
+    torch.cuda.synchronize()
+    err = relerr(nchw(out), ref)
+    assert err < 8e-3, f"conv+pool as 4x4s2 {shape} tangent={tangent}: rel-L2 {err:.3e}"
