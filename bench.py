@@ -202,6 +202,8 @@ def conv_bytes(name, args):
     """Algorithmic HBM bytes of one conv launch (bf16 maps read once and written once; weights excluded):
     2 * N * (Cin * Hin * Win + Cout * Hout * Wout); + the gate map for a gated pass is not counted."""
     n, h, w, ci, co = args[:5]
+    if name == "bg_conv_pool4_dgrad":                      # reads the pooled gradient, writes (and gates) the full map
+        return 2.0 * n * (ci * h * w + co * 4 * h * w)
     hin = win = None
     if name == "bg_conv_style_fprop" and args[5]:          # upsample flag: the input is the quarter-size map
         hin, win = h // 2, w // 2
@@ -314,7 +316,8 @@ def run_b200(args):
     rec = bgn.stop_timing()
     fam = {}
     # one kernel family (conv_halo_kernel / conv_fprop_kernel)
-    FPROP = ("bg_conv_fprop", "bg_conv_fprop_stats", "bg_conv_pool_fprop", "bg_conv_pool4_fprop", "bg_conv_style_fprop")
+    FPROP = ("bg_conv_fprop", "bg_conv_fprop_stats", "bg_conv_pool_fprop", "bg_conv_pool4_fprop", "bg_conv_pool4_dgrad",
+             "bg_conv_style_fprop")
     dom = [0, 0.0, 0.0, 0.0]
     for name, a, t in rec:
         f = fam.setdefault(name, [0, 0.0, 0.0])
@@ -323,8 +326,11 @@ def run_b200(args):
         if name in FPROP or name == "bg_conv_wgrad":
             # reference-formulation FLOPs: the pool4 kernel executes conv3x3+avgpool as a 4x4 stride-2 conv with 2.25x
             # fewer MACs, but is credited with the 3x3 count like every other launch
-            fl = conv_flops(a if name not in ("bg_conv_pool_fprop", "bg_conv_pool4_fprop", "bg_conv_style_fprop")
-                            else a[:5] + (3, 0, 0.0))
+            if name == "bg_conv_pool4_dgrad":        # args: N, Hp, Wp, Cout, Cin -> the 3x3 dgrad at full resolution
+                fl = conv_flops((a[0], 2 * a[1], 2 * a[2], a[3], a[4], 3, 0, 0.0))
+            else:
+                fl = conv_flops(a if name not in ("bg_conv_pool_fprop", "bg_conv_pool4_fprop", "bg_conv_style_fprop")
+                                else a[:5] + (3, 0, 0.0))
             f[2] += fl
             if name in FPROP:
                 dom[0] += 1

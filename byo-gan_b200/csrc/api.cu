@@ -57,6 +57,7 @@ int launch_linear_grouped(int, const float*, const float* const*, const float* c
 int launch_pack_weight_grouped(const float* const*, void* const*, void* const*, const int*, const int*, const int*,
                                const int*, const float*, int, cudaStream_t);
 int launch_pack_weight_pool4(const float*, void*, int, int, float, cudaStream_t);
+int launch_pack_weight_tconv4(const float*, void*, int, int, float, cudaStream_t);
 }  // namespace bg
 
 #define S(stream) reinterpret_cast<cudaStream_t>(stream)
@@ -144,6 +145,19 @@ int bg_conv_pool4_fprop(const void* x, const void* w16, void* out, int N, int H,
   }
   return bg::launch_conv_halo(x, w16, out, N, H, W, Cin, Cout, bias, nullptr, nullptr, gate_src, act, 2, slope, nullptr, 0,
                               nullptr, 0, 0, S(stream));
+}
+int bg_pack_weight_tconv4(const float* w, void* wt, int Cout, int Cin, float coef, void* stream) {
+  return bg::launch_pack_weight_tconv4(w, wt, Cout, Cin, coef, S(stream));
+}
+int bg_conv_pool4_dgrad(const void* gpool, const void* wt, void* gx, int N, int Hp, int Wp, int Cout, int Cin,
+                        const void* gate_src, float slope, float* bias_grad, void* stream) {
+  if (!bg::conv_halo_supported(N, Hp, Wp, Cout, Cin, 3)) {
+    bg::set_error("conv_pool4_dgrad: needs a pooled map >= 16x16 (powers of two), channels %% 16 == 0 (Hp %d Wp %d Cout %d Cin %d)",
+                  Hp, Wp, Cout, Cin);
+    return 2;
+  }
+  return bg::launch_conv_halo(gpool, wt, gx, N, Hp, Wp, Cout, Cin, nullptr, nullptr, nullptr, gate_src, 0, 3, slope,
+                              bias_grad, 2, nullptr, 0, 0, S(stream));
 }
 int bg_conv_pool4_supported(int N, int H, int W, int Cin, int Cout) {
   return (H >= 32 && W >= 32 && Cin % 32 == 0 && bg::conv_halo_supported(N, H / 2, W / 2, Cin, Cout, 3)) ? 1 : 0;

@@ -104,6 +104,31 @@ __global__ void pack_weight_pool4_kernel(const float* __restrict__ w, __nv_bfloa
   }
 }
 
+// Input-gradient (transposed conv) of that 4x4 stride-2 conv.  Output pixel (2i'+py, 2j'+px) receives the taps
+// a = ((py + 1) & 1) + 2 ta, b = ((px + 1) & 1) + 2 tb from pooled pixel (i' + (py + 1 - a) / 2, j' + (px + 1 - b) / 2).
+// wt: bf16 [(2 py + px) * 4 + 2 ta + tb][Cin][Cout] = W4[a][b][co][ci] transposed (GEMM N = ci, K = co).
+__global__ void pack_weight_tconv4_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wt, int Cout, int Cin,
+                                          float coef) {
+  const size_t total = (size_t)16 * Cin * Cout;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cout);
+    const int ci = (int)((i / Cout) % Cin);
+    const int idx = (int)(i / ((size_t)Cin * Cout));
+    const int ph = idx >> 2, t = idx & 3;
+    const int a = (((ph >> 1) + 1) & 1) + 2 * (t >> 1), b = (((ph & 1) + 1) & 1) + 2 * (t & 1);
+    const float* w3 = w + ((size_t)co * Cin + ci) * 9;
+    float acc = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int ky = a - dy, kx = b - dx;
+        if (ky >= 0 && ky <= 2 && kx >= 0 && kx <= 2) acc += w3[ky * 3 + kx];
+      }
+    wt[i] = __float2bfloat16_rn(0.25f * coef * acc);
+  }
+}
+
 // All stale packs of a network in ONE launch (after an optimizer step every conv weight of the active stage is stale:
 // 13..26 layers).  Group g owns blocks [blk0[g], blk0[g+1]).
 constexpr int kMaxPackGroups = 32;
@@ -978,6 +1003,13 @@ int launch_pack_weight_grouped(const float* const* w, void* const* wf, void* con
 int launch_pack_weight_pool4(const float* w, void* w16, int Cout, int Cin, float coef, cudaStream_t s) {
   BG_REQUIRE(Cout > 0 && Cin > 0, "pack_weight_pool4: bad shape");
   pack_weight_pool4_kernel<<<grid_for((size_t)16 * Cout * Cin), kBlock, 0, s>>>(w, (__nv_bfloat16*)w16, Cout, Cin, coef);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_pack_weight_tconv4(const float* w, void* wt, int Cout, int Cin, float coef, cudaStream_t s) {
+  BG_REQUIRE(Cout > 0 && Cin > 0, "pack_weight_tconv4: bad shape");
+  pack_weight_tconv4_kernel<<<grid_for((size_t)16 * Cout * Cin), kBlock, 0, s>>>(w, (__nv_bfloat16*)wt, Cout, Cin, coef);
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -89,6 +89,12 @@ struct HaloParams {
   // input is (N, 2H, 2W, Cin).  The 34x34 input region of a tile is loaded as four 17x17 parity-phase tiles (TMA boxes
   // with element stride 2 along W and H, one pipeline stage each), so that tap (a, b) is phase (a&1, b&1) shifted by
   // (a>>1, b>>1) pixel rows — 2.25x fewer MMAs than conv-then-pool.
+  // tconv4 mode: the input-gradient of that 4x4 stride-2 conv (a transposed conv): x is the POOLED gradient map
+  // (N, H, W, Cin), out the full-resolution map (N, 2H, 2W, Cout).  Output parity phase (py, px) is a 2x2-tap conv over
+  // the pooled map (4 of the 16 taps), so a work item is (16x16 pooled tile, phase): views of the ordinary 18x18 halo
+  // shifted by (py + 1 - ta, px + 1 - tb), results stored to pixels (2h + py, 2w + px).
+  int tconv4;
+  int ph_shift;   // 2 in tconv4 mode (phase = low bits of the tile index above the n-block), else 0
   int pool4;
   int pool4_tma;  // == pool4: the four phase tiles are loaded by strided TMA boxes, one pipeline stage each
   int taps;       // 9, or 16 in pool4 mode
@@ -97,13 +103,15 @@ struct HaloParams {
 };
 
 struct TileCoord {
-  int w0, h0, n, co0;
+  int w0, h0, n, co0, ph;
 };
 
 __device__ __forceinline__ TileCoord decode_tile(const HaloParams& p, int tile) {
   TileCoord t;
   const int nb = tile & ((1 << p.nb_shift) - 1);
   int pt = tile >> p.nb_shift;
+  t.ph = pt & ((1 << p.ph_shift) - 1);
+  pt >>= p.ph_shift;
   t.w0 = (pt & ((1 << p.tw_shift) - 1)) * kTile;
   pt >>= p.tw_shift;
   t.h0 = (pt & ((1 << p.th_shift) - 1)) * kTile;
@@ -162,11 +170,13 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // ---------------------------------------------------------------------------------------------------------
 // Descriptor offset (16-byte units) of the A view of one tap.  9 taps: the 18x18 halo shifted by (ky, kx) pixel rows.
 // 16 taps (pool4): parity-phase tile (a&1, b&1) of the 34x34 region, shifted by (a>>1, b>>1) inside its 17x17 pixels.
+// TAPS == 4 (tconv4): tap (ta, tb) of output phase ph = 2*py + px reads the halo shifted by (py + 1 - ta, px + 1 - tb);
+// `phase_units` carries ph in that mode.
 template <int TAPS, uint32_t RBU>
 __device__ __forceinline__ uint64_t a_tap_offset(int tap, uint32_t phase_units) {
   if (TAPS == 9) return (uint64_t)(((tap / 3) * kHalo + (tap % 3)) * RBU);
-  const int a = tap >> 2, b = tap & 3;
-  return (uint64_t)((uint32_t)((a & 1) * 2 + (b & 1)) * phase_units + (uint32_t)(((a >> 1) * 17 + (b >> 1)) * RBU));
+  const int py = (int)(phase_units >> 1), px = (int)(phase_units & 1u);
+  return (uint64_t)(((py + 1 - (tap >> 1)) * kHalo + (px + 1 - (tap & 1))) * RBU);
 }
 
 // pool4 with TMA feed: the A pipeline unit is ONE parity-phase tile (17x17 pixels x kc channels); phase ph = 2*py + px
@@ -276,17 +286,20 @@ __device__ __forceinline__ void mma_issue_loop(const HaloParams& p, uint8_t* a_b
     tc_fence_after();
     const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
     uint32_t accum = 0u;
+    // tconv4 (TAPS == 4): this work item's output phase selects the 4 taps (of the 16 resident ones) and their views
+    const uint32_t tap_sel = (TAPS == 4) ? (uint32_t)decode_tile(p, tile).ph : phase_units;
     for (int kcx = 0; kcx < p.k_chunks; ++kcx) {
       mbar_wait(&a_full[astage], aphase);
       tc_fence_after();
       const uint64_t a_stage = a_desc0 + (uint64_t)((uint32_t)astage * a_stage_step);
       if (p.b_resident) {
-        const uint64_t b_chunk = b_desc0 + (uint64_t)((uint32_t)(kcx * TAPS) * b_tile_step);
+        const uint64_t b_chunk =
+            b_desc0 + (uint64_t)((uint32_t)(TAPS == 4 ? kcx * 16 + (int)tap_sel * 4 : kcx * TAPS) * b_tile_step);
         if (leader) {
           if (!(p.debug & 2)) {
 #pragma unroll
             for (int tap = 0; tap < TAPS; ++tap) {
-              const uint64_t a_tap = a_stage + a_tap_offset<TAPS, kRBU>(tap, phase_units);
+              const uint64_t a_tap = a_stage + a_tap_offset<TAPS, kRBU>(tap, tap_sel);
               const uint64_t b_tap = b_chunk + (uint64_t)((uint32_t)tap * b_tile_step);
               // alternate the two accumulators (MMA halves): back-to-back MMAs into the SAME accumulator serialise
               // on the tensor pipe's latency (~60 clk), which is longer than a small-N MMA itself
@@ -309,7 +322,7 @@ __device__ __forceinline__ void mma_issue_loop(const HaloParams& p, uint8_t* a_b
           mbar_wait(&b_full[bstage], bphase);
           tc_fence_after();
           if (leader) {
-            const uint64_t a_tap = a_stage + a_tap_offset<TAPS, kRBU>(tap, phase_units);
+            const uint64_t a_tap = a_stage + a_tap_offset<TAPS, kRBU>(tap, tap_sel);
             const uint64_t b_tap = b_desc0 + (uint64_t)((uint32_t)bstage * b_tile_step);
             if (!(p.debug & 2)) {
 #pragma unroll
@@ -663,8 +676,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
           const TileCoord t = decode_tile(p, tile);
           for (int kcx = 0; kcx < p.k_chunks; ++kcx) {
-            for (int ti = 0; ti < p.taps; ++ti) {
-              const int tap = p.pool4_tma ? pool4_tap(ti >> 2, ti & 3) : ti;      // the order the MMA warp consumes them
+            const int ntap = p.tconv4 ? 4 : p.taps;
+            for (int ti = 0; ti < ntap; ++ti) {
+              // the order the MMA warp consumes them
+              const int tap = p.tconv4 ? t.ph * 4 + ti : (p.pool4_tma ? pool4_tap(ti >> 2, ti & 3) : ti);
               mbar_wait(&b_empty[stage], phase ^ 1u);
               mbar_expect_tx(&b_full[stage], p.b_tx_bytes);
               tma_load_4d(&tmap_w, &b_full[stage], b_base + (size_t)stage * p.b_tile_bytes, kcx * p.kc, t.co0, tap,
@@ -683,6 +698,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     if (kFeed == 0 && !kStats && p.pool4) {
       if (p.kc == 64) mma_issue_loop_pool4<4>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
       else mma_issue_loop_pool4<2>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+    } else if (p.tconv4) {
+      if (p.kc == 64) mma_issue_loop<4, 4>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+      else if (p.kc == 32) mma_issue_loop<2, 4>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+      else mma_issue_loop<1, 4>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
     } else if (p.kc == 64) mma_issue_loop<4, 9>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
     else if (p.kc == 32) mma_issue_loop<2, 9>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
     else mma_issue_loop<1, 9>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
@@ -729,8 +748,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
       const int h = t.h0 + g, w = t.w0 + half * 8 + r;
       const size_t pix = ((size_t)t.n * p.H + h) * p.W + w;
       const float nz = p.noise != nullptr ? p.noise[pix] : 0.f;
-      // first pixel of this warp's 4 image rows x 8 columns block (row index 0 of the transpose stage)
-      const size_t pix_q0 = ((size_t)t.n * p.H + t.h0 + q * 4) * p.W + t.w0 + half * 8;
+      // first pixel of this warp's 4 image rows x 8 columns block (row index 0 of the transpose stage); in tconv4 mode
+      // the tile's pixels are every other pixel (phase py, px) of the twice-as-large output map
+      const int os = p.tconv4 ? 2 : 1;
+      const size_t out_w = (size_t)p.W * os;
+      const size_t pix_q0 = ((size_t)t.n * p.H * os + (size_t)(t.h0 + q * 4) * os + (t.ph >> 1)) * out_w +
+                            (size_t)(t.w0 + half * 8) * os + (t.ph & 1);
       const size_t opix_pool = ((size_t)t.n * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
       // per-sample, per-border-class bias row (AdaIN shift folded through the conv), else the plain bias in smem
       const int cls = (h == 0 ? 0 : (h == p.H - 1 ? 2 : 1)) * 3 + (w == 0 ? 0 : (w == p.W - 1 ? 2 : 1));
@@ -747,7 +770,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
           const int ch = lane & (cpr - 1);
 #pragma unroll 4
           for (int row = lane >> cpr_shift; row < 32; row += 32 >> cpr_shift) {
-            const size_t gp = pix_q0 + (size_t)(row >> 3) * p.W + (row & 7);
+            const size_t gp = pix_q0 + (size_t)(row >> 3) * os * out_w + (size_t)(row & 7) * os;
             const uint4 gv = *reinterpret_cast<const uint4*>(p.gate_src + gp * p.Cout + t.co0 + c0 + ch * 8);
             const uint32_t swz = (uint32_t)(row >> (3 - cpr_shift)) & (uint32_t)(cpr - 1);
             sts128(stg + (uint32_t)row * rb + (((uint32_t)ch ^ swz) << 4), gv);
@@ -840,7 +863,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             for (int row = lane >> cpr_shift; row < 32; row += 32 >> cpr_shift) {
               const uint32_t swz = (uint32_t)(row >> (3 - cpr_shift)) & (uint32_t)(cpr - 1);
               const uint4 ov = lds128(stg + (uint32_t)row * rb + (((uint32_t)ch ^ swz) << 4));
-              const size_t op = pix_q0 + (size_t)(row >> 3) * p.W + (row & 7);
+              const size_t op = pix_q0 + (size_t)(row >> 3) * os * out_w + (size_t)(row & 7) * os;
               *reinterpret_cast<uint4*>(p.out + op * p.Cout + t.co0 + c0 + ch * 8) = ov;
               if (st_on) {
                 const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w};
@@ -928,7 +951,15 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
                      int upsample, cudaStream_t stream) {
   // pool: 0 none, 1 conv3x3 then 2x2 average in the epilogue, 2 "pool4": the same function as ONE 4x4 stride-2 conv
   // (wpack is then the 16-tap pack of bg_pack_weight_pool4).  H, W are always the conv INPUT's.
+  // 3 "tconv4": the input-gradient of pool4 (x = pooled gradient (N,H,W,Cin), out = (N,2H,2W,Cout), wpack = the
+  // 16-tile pack of bg_pack_weight_tconv4).
   const bool pool4 = pool == 2;
+  const bool tconv4 = pool == 3;
+  if (tconv4) {
+    BG_REQUIRE(!upsample && !per_sample_w && noise == nullptr && bias == nullptr && (stats == nullptr || stats_mode == 2),
+               "conv_halo tconv4: no upsample / per-sample weights / noise / bias; stats_mode 2 only");
+    pool = 0;
+  }
   if (pool4) {
     BG_REQUIRE(H >= 32 && W >= 32 && Cin % 32 == 0 && !upsample && stats == nullptr && !per_sample_w && noise == nullptr,
                "conv_halo pool4: needs H,W >= 32, Cin %% 32 == 0 and no upsample / stats / noise (H %d W %d Cin %d)", H, W, Cin);
@@ -942,7 +973,9 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
   memset(&p, 0, sizeof(p));
   p.N = N; p.H = Hc; p.W = Wc; p.Cin = Cin; p.Cout = Cout;
   p.pool4 = pool4 ? 1 : 0;
-  p.taps = pool4 ? 16 : 9;
+  p.tconv4 = tconv4 ? 1 : 0;
+  p.ph_shift = tconv4 ? 2 : 0;
+  p.taps = (pool4 || tconv4) ? 16 : 9;
   p.Hin = H; p.Win = W;
   p.tw_shift = ilog2(Wc / kTile);
   p.th_shift = ilog2(Hc / kTile);
@@ -1042,7 +1075,7 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
   p.b_stages = plan.b_stages;
   p.b_resident = plan.resident;
   BG_REQUIRE(planned, "conv_halo: weight tile does not fit shared memory");
-  p.num_tiles = (Wc / kTile) * (Hc / kTile) * N * n_blocks;
+  p.num_tiles = (Wc / kTile) * (Hc / kTile) * N * n_blocks * (tconv4 ? 4 : 1);
   p.x = reinterpret_cast<const __nv_bfloat16*>(x);
   p.bias = bias; p.noise = noise; p.noise_w = noise_w;
   p.gate_src = reinterpret_cast<const __nv_bfloat16*>(gate_src);

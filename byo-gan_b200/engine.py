@@ -84,6 +84,19 @@ class PackCache:
         self._conv[key] = (tag, w16, None)
         return w16
 
+    def conv_tconv4(self, w: torch.Tensor):
+        """16-tile pack of the input gradient of conv3x3 -> AvgPool2d(2) (transposed 4x4 stride-2 conv)."""
+        key = ("t4", id(w))
+        tag = (w._version, w.data_ptr())
+        hit = self._conv.get(key)
+        if hit is not None and hit[0] == tag:
+            return hit[1]
+        cout, cin = w.shape[0], w.shape[1]
+        wt = _bf16(16, cin, cout, device=w.device)
+        call("bg_pack_weight_tconv4", w.detach(), wt, cout, cin, coef_of(w))
+        self._conv[key] = (tag, wt, None)
+        return wt
+
     def refresh_convs(self, items):
         """Re-pack every stale conv weight of `items` = [(weight, cin_pad or None)] in ONE grouped launch (after an
         optimizer step all of a network's packs are stale); the per-layer conv() lookups that follow then hit."""
@@ -761,21 +774,38 @@ def critic_backward(critic, packs: PackCache, tape, g_pred, need: Dict[int, bool
             gy2 = axpby(gx, None, a_mix, 0.0)
         else:
             gy2 = gx
-        gu = _bf16(B, r, r, cout, device=dev)
-        db2 = _f32(cout, device=dev) if want(c2b.bias) else None                               # bias grad of conv_2
-        call("bg_pool_act_bwd", gy2, e["y2"], gu, B, r // 2, r // 2, cout, SLOPE, db2)         # pool + LReLU adjoint
-        if kk is not None:
-            kk["u"] = gu
-        if want(c2b.weight):
-            grads[id(c2b.weight)] = conv_wgrad(e["y1"], gu, c2b.weight, extra=(t["y1"], h["u"]) if t else None)
-        if db2 is not None:
-            grads[id(c2b.bias)] = db2
-        _, wd2 = packs.conv(c2b.weight)
-        if want(c1b.bias):                                                                     # dgrad + LReLU gate,
-            g1, db1 = conv3x3(gu, wd2, cout, cout, gate_src=e["y1"], stats=2)                  # + bias grad of conv_1
-            grads[id(c1b.bias)] = db1
+        # the full-resolution gradient gu at the conv_2 output (pool + LReLU adjoint) is only needed by the weight
+        # gradient (now, or later as the R1 "ghat" operand): the input gradient goes through the transposed 4x4 stride-2
+        # form of conv -> pool and reads the POOLED gated gradient instead
+        need_gu = want(c2b.weight) or want(c2b.bias) or kk is not None
+        fold = r >= 32                                                                          # pooled map >= 16x16
+        gu = None
+        if need_gu or not fold:
+            gu = _bf16(B, r, r, cout, device=dev)
+            db2 = _f32(cout, device=dev) if want(c2b.bias) else None                           # bias grad of conv_2
+            call("bg_pool_act_bwd", gy2, e["y2"], gu, B, r // 2, r // 2, cout, SLOPE, db2)     # pool + LReLU adjoint
+            if kk is not None:
+                kk["u"] = gu
+            if want(c2b.weight):
+                grads[id(c2b.weight)] = conv_wgrad(e["y1"], gu, c2b.weight, extra=(t["y1"], h["u"]) if t else None)
+            if db2 is not None:
+                grads[id(c2b.bias)] = db2
+        db1 = _f32(cout, device=dev) if want(c1b.bias) else None                               # bias grad of conv_1
+        if fold:
+            gpool = torch.empty_like(gy2)
+            call("bg_act_gate", gy2, e["y2"], gpool, gy2.numel(), SLOPE)
+            g1 = _bf16(B, r, r, cout, device=dev)
+            call("bg_conv_pool4_dgrad", gpool, packs.conv_tconv4(c2b.weight), g1, B, r // 2, r // 2, cout, cout, e["y1"],
+                 SLOPE, db1)                                                                    # dgrad + LReLU gate
+            del gpool
         else:
-            g1 = conv3x3(gu, wd2, cout, cout, gate_src=e["y1"])
+            _, wd2 = packs.conv(c2b.weight)
+            if db1 is not None:
+                g1, db1 = conv3x3(gu, wd2, cout, cout, gate_src=e["y1"], stats=2)
+            else:
+                g1 = conv3x3(gu, wd2, cout, cout, gate_src=e["y1"])
+        if db1 is not None:
+            grads[id(c1b.bias)] = db1
         del gu
         if kk is not None:
             kk["y1"] = g1

@@ -87,6 +87,13 @@ int bg_pack_weight_pool4(const float* w, void* w16, int Cout, int Cin, float coe
 int bg_conv_pool4_fprop(const void* x, const void* w16, void* out, int N, int H, int W, int Cin, int Cout, const float* bias,
                         const void* gate_src, int act, float slope, void* stream);
 int bg_conv_pool4_supported(int N, int H, int W, int Cin, int Cout);
+/* Input gradient of conv3x3 -> AvgPool2d(2) (autograd convolution_backward + avg_pool2d_backward) as the transposed
+ * 4x4 stride-2 conv: gpool = gradient at the POOLED map (N,Hp,Wp,Cout), gx = gradient at the conv input
+ * (N,2Hp,2Wp,Cin), optionally gated by gate_src (N,2Hp,2Wp,Cin) (LeakyReLU of the layer below) and with
+ * bias_grad fp32 (Cin) = sum over gx (that layer's bias gradient).  wt: 16-tile pack of bg_pack_weight_tconv4. */
+int bg_pack_weight_tconv4(const float* w, void* wt, int Cout, int Cin, float coef, void* stream);
+int bg_conv_pool4_dgrad(const void* gpool, const void* wt, void* gx, int N, int Hp, int Wp, int Cout, int Cin,
+                        const void* gate_src, float slope, float* bias_grad, void* stream);
 /* bg_conv_fprop picks the halo-resident kernel (conv_halo.cu) for 3x3 at H,W >= 16 and the tap-wise TMA kernel
  * (conv_fprop.cu) otherwise; this entry forces the tap-wise kernel (A/B tests, small maps, 1x1). */
 int bg_conv_fprop_tapwise(const void* x, const void* wpack, void* out, int N, int H, int W, int Cin, int Cout,

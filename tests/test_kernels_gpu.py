@@ -384,3 +384,35 @@ def test_conv_pool_as_4x4_stride2(shape, tangent):
     torch.cuda.synchronize()
     err = relerr(nchw(out), ref)
     assert err < 8e-3, f"conv+pool as 4x4s2 {shape} tangent={tangent}: rel-L2 {err:.3e}"
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 32, 64, 64), (1, 64, 64, 32, 64), (3, 32, 32, 128, 128), (1, 64, 64, 256, 256),
+                                   (2, 32, 32, 512, 512), (1, 128, 128, 64, 64), (2, 32, 32, 64, 32)])
+@pytest.mark.parametrize("gated", [False, True])
+def test_conv_pool_dgrad_as_transposed_4x4_stride2(shape, gated):
+    """autograd's input gradient of conv3x3 -> AvgPool2d(2) (gan.py:258-260) as the transposed 4x4 stride-2 conv
+    (bg_pack_weight_tconv4 + bg_conv_pool4_dgrad), optionally with the LeakyReLU gate of the layer below and that
+    layer's bias gradient (sum of the gated gradient) from the epilogue."""
+    n, h, w_, ci, co = shape                      # conv input (n, ci, h, w_), pooled output (n, co, h/2, w_/2)
+    torch.manual_seed(0)
+    y1 = nchw(nhwc(torch.randn(n, ci, h, w_, device=DEV))).requires_grad_()
+    w = torch.randn(co, ci, 3, 3, device=DEV)
+    coef = math.sqrt(2 / (ci * 9))
+    gpool = nhwc(torch.randn(n, co, h // 2, w_ // 2, device=DEV))
+    F.avg_pool2d(F.conv2d(y1, w * coef, None, padding=1), 2).backward(nchw(gpool))
+    ref = y1.grad
+    gate = None
+    if gated:
+        gate = nhwc(torch.randn(n, ci, h, w_, device=DEV))
+        ref = ref * torch.where(nchw(gate) > 0, 1.0, 0.2)
+    wt = torch.empty(16, ci, co, dtype=torch.bfloat16, device=DEV)
+    bgn.call("bg_pack_weight_tconv4", w, wt, co, ci, coef)
+    gx = torch.empty(n, h, w_, ci, dtype=torch.bfloat16, device=DEV)
+    db = torch.full((ci,), 9.0, device=DEV) if gated else None
+    bgn.call("bg_conv_pool4_dgrad", gpool, wt, gx, n, h // 2, w_ // 2, co, ci, gate, 0.2, db)
+    torch.cuda.synchronize()
+    err = relerr(nchw(gx), ref)
+    assert err < 8e-3, f"conv+pool dgrad as transposed 4x4s2 {shape} gated={gated}: rel-L2 {err:.3e}"
+    if gated:
+        want = gx.double().sum(dim=(0, 1, 2))
+        assert (db.double() - want).abs().max().item() < 2e-5 * (want.abs().max().item() + 1.0) * math.sqrt(h * w_)

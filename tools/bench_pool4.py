@@ -37,4 +37,23 @@ for (R, ci, co) in [(256, 64, 64), (128, 128, 128), (64, 256, 256), (32, 512, 51
     bias = torch.zeros(co, device=DEV)
     t1 = timeit(lambda: bgn.call("bg_conv_pool_fprop", x, wf, out, n, R, R, ci, co, bias, None, 1, 0.2))
     t2 = timeit(lambda: bgn.call("bg_conv_pool4_fprop", x, w16, out, n, R, R, ci, co, bias, None, 1, 0.2))
-    print(f"{R:4d} {ci:4d} {co:4d}  conv+pool epilogue {t1:.3f} ms   4x4 stride-2 {t2:.3f} ms")
+    # input gradient: pool adjoint materialised at full resolution + 3x3 dgrad, vs the transposed 4x4 stride-2 form
+    gpool = torch.randn(n, R // 2, R // 2, co, device=DEV).to(torch.bfloat16)
+    y2 = torch.randn(n, R // 2, R // 2, co, device=DEV).to(torch.bfloat16)
+    gate = torch.randn(n, R, R, ci, device=DEV).to(torch.bfloat16)
+    gu = torch.empty(n, R, R, co, dtype=torch.bfloat16, device=DEV)
+    gx = torch.empty(n, R, R, ci, dtype=torch.bfloat16, device=DEV)
+    wt = torch.empty(16, ci, co, dtype=torch.bfloat16, device=DEV)
+    bgn.call("bg_pack_weight_tconv4", w, wt, co, ci, 0.05)
+
+    def old_dgrad():
+        bgn.call("bg_pool_act_bwd", gpool, y2, gu, n, R // 2, R // 2, co, 0.2, None)
+        bgn.call("bg_conv_fprop", gu, wd, gx, n, R, R, co, ci, 3, None, None, None, gate, 0, 0.2)
+
+    def new_dgrad():
+        bgn.call("bg_act_gate", gpool, y2, gpool, gpool.numel(), 0.2)
+        bgn.call("bg_conv_pool4_dgrad", gpool, wt, gx, n, R // 2, R // 2, co, ci, gate, 0.2, None)
+
+    t3, t4 = timeit(old_dgrad), timeit(new_dgrad)
+    print(f"{R:4d} {ci:4d} {co:4d}  fprop: conv+pool epilogue {t1:.3f} ms, 4x4 stride-2 {t2:.3f} ms | "
+          f"dgrad: pool_bwd + 3x3 {t3:.3f} ms, gate + transposed 4x4s2 {t4:.3f} ms")
