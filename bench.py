@@ -323,6 +323,8 @@ def run_b200(args):
         f = fam.setdefault(name, [0, 0.0, 0.0])
         f[0] += 1
         f[1] += t
+        if name == "bg_conv_pool4_wgrad":          # args N, Hp, Wp, Cin, Cout: credited as the 3x3 wgrad at full resolution
+            f[2] += conv_flops((a[0], 2 * a[1], 2 * a[2], a[3], a[4], 0))
         if name in FPROP or name == "bg_conv_wgrad":
             # reference-formulation FLOPs: the pool4 kernel executes conv3x3+avgpool as a 4x4 stride-2 conv with 2.25x
             # fewer MACs, but is credited with the 3x3 count like every other launch
@@ -358,8 +360,9 @@ def run_b200(args):
                 "algorithmic_bytes": dom[3], "algorithmic_flops": dom[2],
                 "peak_source": peaks["src"] + ", sustained bf16 (kernel timed inside a long step)",
                 "launches_per_step": dom[0], "share_of_step": round(dom[1] / tot_ms, 4),
-                "wgrad_tflops": round(fam["bg_conv_wgrad"][2] / (fam["bg_conv_wgrad"][1] / 1e3) / 1e12, 1)
-                if "bg_conv_wgrad" in fam else None,
+                "wgrad_tflops": round(sum(fam[k][2] for k in ("bg_conv_wgrad", "bg_conv_pool4_wgrad") if k in fam) /
+                                      (sum(fam[k][1] for k in ("bg_conv_wgrad", "bg_conv_pool4_wgrad") if k in fam) / 1e3)
+                                      / 1e12, 1) if "bg_conv_wgrad" in fam else None,
                 "step_share_by_call": shares,
                 "step_model_flops_frac": round(value / world * gflop_img * 1e9 / (peaks["tf_sustained"] * 1e12), 4)}
 

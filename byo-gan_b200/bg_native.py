@@ -33,6 +33,8 @@ SIGNATURES = {
     "bg_conv_pool4_fprop": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _F, _P],
     "bg_pack_weight_tconv4": [_P, _P, _I, _I, _F, _P],
     "bg_conv_pool4_dgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _F, _P, _P],
+    "bg_conv_pool4_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "bg_unpack_wgrad_pool4": [_P, _P, _I, _I, _F, _I, _P],
     "bg_conv_pool4_supported": [_I, _I, _I, _I, _I],          # pure host-side predicate: no stream argument
     "bg_conv_fprop_tapwise": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _F, _P],
     "bg_conv_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],

@@ -9,7 +9,8 @@ int launch_conv_halo(const void*, const void*, void*, int, int, int, int, int, c
                      const void*, int, int, float, float*, int, const float*, int, int, cudaStream_t);
 bool conv_halo_supported(int, int, int, int, int, int);
 int launch_conv_wgrad(const void*, const void*, float*, int, int, int, int, int, int, cudaStream_t);
-int launch_conv_wgrad_halo(const void*, const void*, float*, int, int, int, int, int, int, cudaStream_t);
+int launch_conv_wgrad_halo(const void*, const void*, float*, int, int, int, int, int, int, int, cudaStream_t);
+int launch_unpack_wgrad_pool4(const float*, float*, int, int, float, int, cudaStream_t);
 bool conv_wgrad_halo_supported(int, int, int, int, int);
 int launch_pack_weight(const float*, void*, void*, int, int, int, int, float, cudaStream_t);
 int launch_unpack_wgrad(const float*, float*, int, int, int, int, float, int, cudaStream_t);
@@ -159,6 +160,17 @@ int bg_conv_pool4_dgrad(const void* gpool, const void* wt, void* gx, int N, int 
   return bg::launch_conv_halo(gpool, wt, gx, N, Hp, Wp, Cout, Cin, nullptr, nullptr, nullptr, gate_src, 0, 3, slope,
                               bias_grad, 2, nullptr, 0, 0, S(stream));
 }
+int bg_conv_pool4_wgrad(const void* x, const void* gpool, float* dw16, int N, int Hp, int Wp, int Cin, int Cout,
+                        int accumulate, void* stream) {
+  if (!bg::conv_wgrad_halo_supported(N, Hp, Wp, Cin, Cout) || Hp < 8 || Wp < 16) {
+    bg::set_error("conv_pool4_wgrad: unsupported shape (pooled %d x %d, Cin %d, Cout %d)", Hp, Wp, Cin, Cout);
+    return 2;
+  }
+  return bg::launch_conv_wgrad_halo(x, gpool, dw16, N, Hp, Wp, Cin, Cout, accumulate, 1, S(stream));
+}
+int bg_unpack_wgrad_pool4(const float* dw16, float* dw, int Cout, int Cin, float coef, int accumulate, void* stream) {
+  return bg::launch_unpack_wgrad_pool4(dw16, dw, Cout, Cin, coef, accumulate, S(stream));
+}
 int bg_conv_pool4_supported(int N, int H, int W, int Cin, int Cout) {
   return (H >= 32 && W >= 32 && Cin % 32 == 0 && bg::conv_halo_supported(N, H / 2, W / 2, Cin, Cout, 3)) ? 1 : 0;
 }
@@ -171,7 +183,7 @@ int bg_conv_fprop_tapwise(const void* x, const void* wpack, void* out, int N, in
 int bg_conv_wgrad(const void* x, const void* g, float* dwp, int N, int H, int W, int Cin, int Cout, int accumulate,
                   void* stream) {
   if (bg::conv_wgrad_halo_supported(N, H, W, Cin, Cout))
-    return bg::launch_conv_wgrad_halo(x, g, dwp, N, H, W, Cin, Cout, accumulate, S(stream));
+    return bg::launch_conv_wgrad_halo(x, g, dwp, N, H, W, Cin, Cout, accumulate, 0, S(stream));
   return bg::launch_conv_wgrad(x, g, dwp, N, H, W, Cin, Cout, accumulate, S(stream));
 }
 int bg_conv_wgrad_tapwise(const void* x, const void* g, float* dwp, int N, int H, int W, int Cin, int Cout,

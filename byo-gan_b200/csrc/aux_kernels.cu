@@ -177,6 +177,26 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __rest
   }
 }
 
+// dw4: fp32 [16][Cout][Cin] gradient of the 4x4 stride-2 kernel W4[a][b] = 1/4 sum_{dy,dx} W3[a-dy][b-dx]  ->
+// dw: fp32 (Cout, Cin, 3, 3):  dW3[ky][kx] = coef / 4 * sum_{dy,dx in {0,1}} dW4[ky+dy][kx+dx]   (adjoint of the pack)
+__global__ void unpack_wgrad_pool4_kernel(const float* __restrict__ dw4, float* __restrict__ dw, int Cout, int Cin,
+                                          float coef, int accumulate) {
+  const size_t total = (size_t)Cout * Cin * 9;
+  const size_t plane = (size_t)Cout * Cin;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % 9);
+    const size_t cc = i / 9;                      // co * Cin + ci
+    const int ky = tap / 3, kx = tap % 3;
+    float acc = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) acc += dw4[(size_t)((ky + dy) * 4 + kx + dx) * plane + cc];
+    const float v = 0.25f * coef * acc;
+    dw[i] = accumulate ? dw[i] + v : v;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // LeakyReLU gate:  out = g * (y > 0 ? 1 : slope)      (backward of nn.LeakyReLU(0.2), gan.py:86,241...)
 // ---------------------------------------------------------------------------------------------
@@ -1010,6 +1030,12 @@ int launch_pack_weight_pool4(const float* w, void* w16, int Cout, int Cin, float
 int launch_pack_weight_tconv4(const float* w, void* wt, int Cout, int Cin, float coef, cudaStream_t s) {
   BG_REQUIRE(Cout > 0 && Cin > 0, "pack_weight_tconv4: bad shape");
   pack_weight_tconv4_kernel<<<grid_for((size_t)16 * Cout * Cin), kBlock, 0, s>>>(w, (__nv_bfloat16*)wt, Cout, Cin, coef);
+  BG_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_unpack_wgrad_pool4(const float* dw4, float* dw, int Cout, int Cin, float coef, int accumulate, cudaStream_t s) {
+  unpack_wgrad_pool4_kernel<<<grid_for((size_t)Cout * Cin * 9), kBlock, 0, s>>>(dw4, dw, Cout, Cin, coef, accumulate);
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

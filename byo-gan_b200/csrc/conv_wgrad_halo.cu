@@ -43,6 +43,11 @@ struct WgradHaloParams {
   uint32_t a_layout, b_layout;
   uint32_t a_slab_bytes;
   int stack_taps;                  // 1: the three kx taps are ONE MMA (N = 3 * ci_sub, N-atoms one pixel apart)
+  // pool4: weight gradient of conv3x3 -> AvgPool2d(2) taken on the 4x4 stride-2 form: G is the POOLED gradient (H, W
+  // below are its dims), X the full-resolution conv input (2H x 2W).  A CTA owns one tap row a (0..3); per K block it
+  // loads two column-parity tiles of X (TMA boxes with element stride 2 along W and H): parity 1 serves taps b = 0, 2
+  // (pixel shifts 0, 1), parity 0 serves b = 1, 3 — each pair is one N-stacked MMA.  dw is then [16][Cout][Cin].
+  int pool4;
   float* dw;
 };
 
@@ -69,9 +74,10 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
   // work decode: blockIdx -> (co tile, ci slab, kernel row, K split)
   const int split = blockIdx.x % p.splits;
   const int unit = blockIdx.x / p.splits;
-  const int tg = unit % 3;                       // ky
-  const int cis = (unit / 3) % p.ci_slabs;
-  const int cot = unit / (3 * p.ci_slabs);
+  const int ntg = p.pool4 ? 4 : 3;
+  const int tg = unit % ntg;                     // ky (pool4: tap row a)
+  const int cis = (unit / ntg) % p.ci_slabs;
+  const int cot = unit / (ntg * p.ci_slabs);
   const int co0 = cot * 128;
   const int ci0 = cis * p.ci_slab;
   const int kb_begin = split * p.kblocks_per_split;
@@ -105,7 +111,8 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
         int stage = 0;
         uint32_t phase = 0;
         const uint32_t tx = (uint32_t)p.co_nslabs * p.a_slab_bytes +
-                            (uint32_t)p.ci_nsub * (uint32_t)(kHaloW * kBh) * p.b_row_bytes;
+                            (p.pool4 ? 2u * (uint32_t)((kBw + 1) * kBh) * p.b_row_bytes
+                                     : (uint32_t)p.ci_nsub * (uint32_t)(kHaloW * kBh) * p.b_row_bytes);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           const int tw = kb % p.tiles_w;
           const int th = (kb / p.tiles_w) % p.tiles_h;
@@ -117,8 +124,15 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
           mbar_expect_tx(&full_bar[stage], tx);
           for (int s = 0; s < p.co_nslabs; ++s)
             tma_load_4d(&tmap_g, &full_bar[stage], sa + (size_t)s * p.a_slab_bytes, co0 + s * p.co_slab, w0, h0, n);
-          for (int s = 0; s < p.ci_nsub; ++s)
-            tma_load_4d(&tmap_x, &full_bar[stage], sb + (size_t)s * kBSub, ci0 + s * p.ci_sub, w0 - 1, h0 + tg - 1, n);
+          if (p.pool4) {
+            // sub-region 0: odd full-resolution columns 2j-1 (j = w0..w0+16), sub-region 1: even columns 2j; rows
+            // 2i + a - 1 for the 8 pooled rows i of the block (both with element stride 2)
+            tma_load_4d(&tmap_x, &full_bar[stage], sb, ci0, 2 * w0 - 1, 2 * h0 + tg - 1, n);
+            tma_load_4d(&tmap_x, &full_bar[stage], sb + kBSub, ci0, 2 * w0, 2 * h0 + tg - 1, n);
+          } else {
+            for (int s = 0; s < p.ci_nsub; ++s)
+              tma_load_4d(&tmap_x, &full_bar[stage], sb + (size_t)s * kBSub, ci0 + s * p.ci_sub, w0 - 1, h0 + tg - 1, n);
+          }
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;
@@ -132,11 +146,13 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
       // costs ~60 clk no matter how narrow it is, so fewer, wider instructions are what speeds the narrow layers up.
       const uint32_t idesc = umma_idesc_bf16(128, p.stack_taps ? 3 * p.ci_slab : p.ci_slab, 1, 1);
       const uint64_t a_desc0 = umma_desc(smem_u32(smem), p.a_slab_bytes, 8u * p.a_row_bytes, p.a_layout);
-      const uint64_t b_desc0 = umma_desc(smem_u32(smem) + kARegion, p.stack_taps ? p.b_row_bytes : kBSub,
+      const uint64_t b_desc0 = umma_desc(smem_u32(smem) + kARegion, (p.stack_taps || p.pool4) ? p.b_row_bytes : kBSub,
                                          8u * p.b_row_bytes, p.b_layout);
       const uint32_t a_kstep = (16u * p.a_row_bytes) >> 4;          // 16 pixels (one image row of the tile) per K step
       const uint32_t b_kstep = ((uint32_t)kHaloW * p.b_row_bytes) >> 4;   // ... which is 18 halo pixels further in X
       const uint32_t b_tap = p.b_row_bytes >> 4;                     // one pixel to the right = next tap
+      const uint32_t idesc4 = umma_idesc_bf16(128, 2 * p.ci_slab, 1, 1);      // pool4: two taps per MMA
+      const uint32_t b_kstep4 = ((uint32_t)(kBw + 1) * p.b_row_bytes) >> 4;   // pool4: 17-pixel tile rows
       const bool leader = elect_one();
       int stage = 0;
       uint32_t phase = 0;
@@ -147,7 +163,16 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
         if (leader) {
           const uint64_t a_st = a_desc0 + (uint64_t)((uint32_t)stage * (kStageBytes >> 4));
           const uint64_t b_st = b_desc0 + (uint64_t)((uint32_t)stage * (kStageBytes >> 4));
-          if (p.stack_taps) {
+          if (p.pool4) {
+            // two N-stacked MMAs per K step: taps (b=0, b=2) from the odd-column tile, (b=1, b=3) from the even one
+#pragma unroll
+            for (int ks = 0; ks < kBh; ++ks) {
+#pragma unroll
+              for (int pc = 0; pc < 2; ++pc)
+                tc_mma_bf16(tmem_base + (uint32_t)pc * 2u * (uint32_t)p.ci_slab, a_st + (uint64_t)(ks * a_kstep),
+                            b_st + (uint64_t)(ks * b_kstep4 + pc * (kBSub >> 4)), idesc4, ks == 0 ? accum : 1u);
+            }
+          } else if (p.stack_taps) {
 #pragma unroll
             for (int ks = 0; ks < kBh; ++ks)
               tc_mma_bf16(tmem_base, a_st + (uint64_t)(ks * a_kstep), b_st + (uint64_t)(ks * b_kstep), idesc,
@@ -181,12 +206,14 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
       const bool live = row < p.co_slab * p.co_nslabs && co < p.Cout;
-      for (int kx = 0; kx < 3; ++kx) {
-        const int tap = tg * 3 + kx;
+      const int ntaps = p.pool4 ? 4 : 3;
+      for (int kx = 0; kx < ntaps; ++kx) {
+        // pool4: TMEM holds the taps in the order b = 0, 2, 1, 3 (ci_slab columns each)
+        const int tap = p.pool4 ? tg * 4 + ((kx & 1) * 2 + (kx >> 1)) : tg * 3 + kx;
         float* drow = p.dw + ((size_t)tap * p.Cout + co) * p.Cin + ci0;
         for (int c = 0; c < p.ci_slab; c += 16) {
           uint32_t v[16];
-          tmem_ld_x16(taddr + kx * (p.stack_taps ? (uint32_t)p.ci_slab : kTapStride) + c, v);
+          tmem_ld_x16(taddr + kx * ((p.stack_taps || p.pool4) ? (uint32_t)p.ci_slab : kTapStride) + c, v);
           tmem_ld_wait();
           if (live) {
 #pragma unroll
@@ -216,8 +243,10 @@ bool conv_wgrad_halo_supported(int N, int H, int W, int Cin, int Cout) {
 }
 
 // x: (N,H,W,Cin) bf16, g: (N,H,W,Cout) bf16, dw: [9][Cout][Cin] fp32 (overwritten, or += if accumulate).
+// pool4: g is the POOLED gradient (N,H,W,Cout) of conv3x3 -> AvgPool2d(2), x the conv input (N,2H,2W,Cin), dw the
+// 16-tap gradient [16][Cout][Cin] of the equivalent 4x4 stride-2 kernel (bg_unpack_wgrad_pool4 folds it back to 3x3).
 int launch_conv_wgrad_halo(const void* x, const void* g, float* dw, int N, int H, int W, int Cin, int Cout,
-                           int accumulate, cudaStream_t stream) {
+                           int accumulate, int pool4, cudaStream_t stream) {
   BG_REQUIRE(conv_wgrad_halo_supported(N, H, W, Cin, Cout), "conv_wgrad_halo: unsupported shape N %d H %d W %d Cin %d Cout %d",
              N, H, W, Cin, Cout);
   WgradHaloParams p;
@@ -230,7 +259,8 @@ int launch_conv_wgrad_halo(const void* x, const void* g, float* dw, int N, int H
   p.co_nslabs = Cout >= 128 ? 2 : 1;
   p.co_tiles = (Cout + 127) / 128;
   p.ci_sub = Cin < 64 ? Cin : 64;
-  p.ci_nsub = Cin >= 128 ? 2 : 1;
+  p.ci_nsub = (Cin >= 128 && !pool4) ? 2 : 1;      // pool4 uses the two sub-regions for the two column parities
+  p.pool4 = pool4 ? 1 : 0;
   p.ci_slab = p.ci_sub * p.ci_nsub;
   p.ci_slabs = Cin / p.ci_slab;
   p.a_row_bytes = p.co_slab * 2;
@@ -244,7 +274,8 @@ int launch_conv_wgrad_halo(const void* x, const void* g, float* dw, int N, int H
     if (mode < 0) { const char* e = getenv("BG_WGRAD_STACK"); mode = e ? atoi(e) : 2; }
     p.stack_taps = (p.ci_nsub == 1 && (mode == 2 || (mode == 1 && Cin <= 32))) ? 1 : 0;
   }
-  const int units = p.co_tiles * p.ci_slabs * 3;
+  if (p.pool4) p.stack_taps = 0;
+  const int units = p.co_tiles * p.ci_slabs * (p.pool4 ? 4 : 3);
   int splits = (2 * num_sms() + units - 1) / units;
   if (splits < 1) splits = 1;
   if (splits > p.total_kblocks) splits = p.total_kblocks;
@@ -260,13 +291,20 @@ int launch_conv_wgrad_halo(const void* x, const void* g, float* dw, int N, int H
     if (make_tmap_bf16(&tmg, g, 4, dims, str, box, (int)p.a_row_bytes) != 0) return 1;
   }
   {
-    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
-    uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+    const int Hx = pool4 ? 2 * H : H, Wx = pool4 ? 2 * W : W;
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Wx, (uint64_t)Hx, (uint64_t)N};
+    uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)Wx * Cin * 2, (uint64_t)Hx * Wx * Cin * 2};
     uint32_t box[4] = {(uint32_t)p.ci_sub, (uint32_t)kHaloW, (uint32_t)kBh, 1u};
-    if (make_tmap_bf16(&tmx, x, 4, dims, str, box, (int)p.b_row_bytes) != 0) return 1;
+    if (pool4) {
+      // every other pixel / row: a (16+1) x 8 pixel tile per column parity
+      uint32_t box2[4] = {(uint32_t)p.ci_sub, 2u * (kBw + 1), 2u * kBh, 1u};
+      uint32_t est[4] = {1u, 2u, 2u, 1u};
+      if (make_tmap_bf16_strided(&tmx, x, 4, dims, str, box2, est, (int)p.b_row_bytes) != 0) return 1;
+    } else if (make_tmap_bf16(&tmx, x, 4, dims, str, box, (int)p.b_row_bytes) != 0) return 1;
   }
 
-  if (!accumulate) BG_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)9 * Cout * Cin * sizeof(float), stream));
+  if (!accumulate)
+    BG_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)(pool4 ? 16 : 9) * Cout * Cin * sizeof(float), stream));
   const size_t smem_bytes = (size_t)kStages * kStageBytes + 256 + 1024;
   static bool attr_set = false;
   if (!attr_set) {

@@ -218,6 +218,21 @@ def conv_wgrad(x, g, w_param, cin_pad=None, extra=None):
     return dw
 
 
+def conv_pool_wgrad(x, gpool, w_param, extra=None):
+    """dW of a 3x3 conv that is followed by AvgPool2d(2), from the gradient gpool at the POOLED map (NHWC bf16) and the
+    conv input x: taken on the equivalent 4x4 stride-2 kernel (16 taps, a quarter of the pixels), folded back to 3x3.
+    `extra=(v, ghat_pooled)` adds the R1 second-order pair into the same accumulator."""
+    n, hp, wp, cout = gpool.shape
+    cin = x.shape[3]
+    dw16 = _f32(16, cout, cin, device=x.device)
+    call("bg_conv_pool4_wgrad", x, gpool, dw16, n, hp, wp, cin, cout, 0)
+    if extra is not None:
+        call("bg_conv_pool4_wgrad", extra[0], extra[1], dw16, n, hp, wp, cin, cout, 1)
+    dw = _f32(*w_param.shape, device=x.device)
+    call("bg_unpack_wgrad_pool4", dw16, dw, cout, cin, coef_of(w_param), 0)
+    return dw
+
+
 def channel_wsum(g, planes, nplanes, hw, img_stride, plane_stride):
     c = g.shape[-1]
     p = g.numel() // c
@@ -774,13 +789,25 @@ def critic_backward(critic, packs: PackCache, tape, g_pred, need: Dict[int, bool
             gy2 = axpby(gx, None, a_mix, 0.0)
         else:
             gy2 = gx
-        # the full-resolution gradient gu at the conv_2 output (pool + LReLU adjoint) is only needed by the weight
-        # gradient (now, or later as the R1 "ghat" operand): the input gradient goes through the transposed 4x4 stride-2
-        # form of conv -> pool and reads the POOLED gated gradient instead
-        need_gu = want(c2b.weight) or want(c2b.bias) or kk is not None
-        fold = r >= 32                                                                          # pooled map >= 16x16
+        db1 = _f32(cout, device=dev) if want(c1b.bias) else None                               # bias grad of conv_1
         gu = None
-        if need_gu or not fold:
+        if r >= 32:
+            # conv_2 -> pool is handled as ONE 4x4 stride-2 conv in all three directions: everything works from the
+            # gated gradient at the POOLED map, the full-resolution pool adjoint is never materialised
+            gpool = torch.empty_like(gy2)
+            call("bg_act_gate", gy2, e["y2"], gpool, gy2.numel(), SLOPE)                        # LReLU adjoint
+            if kk is not None:
+                kk["gp"] = gpool
+            if want(c2b.weight):
+                grads[id(c2b.weight)] = conv_pool_wgrad(e["y1"], gpool, c2b.weight,
+                                                        extra=(t["y1"], h["gp"]) if t else None)
+            if want(c2b.bias):
+                grads[id(c2b.bias)] = channel_wsum(gpool, None, 0, (r // 2) * (r // 2), 0, 0)[0]
+            g1 = _bf16(B, r, r, cout, device=dev)
+            call("bg_conv_pool4_dgrad", gpool, packs.conv_tconv4(c2b.weight), g1, B, r // 2, r // 2, cout, cout, e["y1"],
+                 SLOPE, db1)                                                                    # dgrad + LReLU gate
+            del gpool
+        else:
             gu = _bf16(B, r, r, cout, device=dev)
             db2 = _f32(cout, device=dev) if want(c2b.bias) else None                           # bias grad of conv_2
             call("bg_pool_act_bwd", gy2, e["y2"], gu, B, r // 2, r // 2, cout, SLOPE, db2)     # pool + LReLU adjoint
@@ -790,15 +817,6 @@ def critic_backward(critic, packs: PackCache, tape, g_pred, need: Dict[int, bool
                 grads[id(c2b.weight)] = conv_wgrad(e["y1"], gu, c2b.weight, extra=(t["y1"], h["u"]) if t else None)
             if db2 is not None:
                 grads[id(c2b.bias)] = db2
-        db1 = _f32(cout, device=dev) if want(c1b.bias) else None                               # bias grad of conv_1
-        if fold:
-            gpool = torch.empty_like(gy2)
-            call("bg_act_gate", gy2, e["y2"], gpool, gy2.numel(), SLOPE)
-            g1 = _bf16(B, r, r, cout, device=dev)
-            call("bg_conv_pool4_dgrad", gpool, packs.conv_tconv4(c2b.weight), g1, B, r // 2, r // 2, cout, cout, e["y1"],
-                 SLOPE, db1)                                                                    # dgrad + LReLU gate
-            del gpool
-        else:
             _, wd2 = packs.conv(c2b.weight)
             if db1 is not None:
                 g1, db1 = conv3x3(gu, wd2, cout, cout, gate_src=e["y1"], stats=2)

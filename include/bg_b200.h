@@ -94,6 +94,12 @@ int bg_conv_pool4_supported(int N, int H, int W, int Cin, int Cout);
 int bg_pack_weight_tconv4(const float* w, void* wt, int Cout, int Cin, float coef, void* stream);
 int bg_conv_pool4_dgrad(const void* gpool, const void* wt, void* gx, int N, int Hp, int Wp, int Cout, int Cin,
                         const void* gate_src, float slope, float* bias_grad, void* stream);
+/* Weight gradient of conv3x3 -> AvgPool2d(2) on the same 4x4 stride-2 form: dw16 fp32 [16][Cout][Cin] (overwritten, or
+ * += when accumulate) = sum over pooled pixels of gpool[i,j,co] * x[2i+a-1, 2j+b-1, ci]; bg_unpack_wgrad_pool4 applies the
+ * adjoint of the quarter-sum pack: dw (Cout,Cin,3,3) (+)= coef/4 * sum_{dy,dx} dw16[(ky+dy)*4 + kx+dx]. */
+int bg_conv_pool4_wgrad(const void* x, const void* gpool, float* dw16, int N, int Hp, int Wp, int Cin, int Cout,
+                        int accumulate, void* stream);
+int bg_unpack_wgrad_pool4(const float* dw16, float* dw, int Cout, int Cin, float coef, int accumulate, void* stream);
 /* bg_conv_fprop picks the halo-resident kernel (conv_halo.cu) for 3x3 at H,W >= 16 and the tap-wise TMA kernel
  * (conv_fprop.cu) otherwise; this entry forces the tap-wise kernel (A/B tests, small maps, 1x1). */
 int bg_conv_fprop_tapwise(const void* x, const void* wpack, void* out, int N, int H, int W, int Cin, int Cout,

@@ -416,3 +416,25 @@ def test_conv_pool_dgrad_as_transposed_4x4_stride2(shape, gated):
     if gated:
         want = gx.double().sum(dim=(0, 1, 2))
         assert (db.double() - want).abs().max().item() < 2e-5 * (want.abs().max().item() + 1.0) * math.sqrt(h * w_)
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 32, 64, 64), (1, 64, 64, 32, 64), (3, 32, 32, 128, 128), (1, 64, 64, 256, 256),
+                                   (2, 32, 32, 512, 512), (1, 128, 128, 64, 64), (2, 32, 32, 64, 32)])
+def test_conv_pool_wgrad_on_4x4_stride2_form(shape):
+    """autograd's weight gradient of conv3x3 -> AvgPool2d(2) (gan.py:258-260) from the POOLED output gradient
+    (bg_conv_pool4_wgrad + bg_unpack_wgrad_pool4), incl. the accumulate=1 form of the R1 doubled-K contraction."""
+    n, h, w_, ci, co = shape
+    torch.manual_seed(0)
+    y1 = nhwc(torch.randn(n, ci, h, w_, device=DEV))
+    gpool = nhwc(torch.randn(n, co, h // 2, w_ // 2, device=DEV))
+    coef = math.sqrt(2 / (ci * 9))
+    wparam = torch.randn(co, ci, 3, 3, device=DEV, requires_grad=True)
+    F.avg_pool2d(F.conv2d(nchw(y1), wparam * coef, None, padding=1), 2).backward(nchw(gpool))
+    dw16 = torch.empty(16, co, ci, device=DEV)
+    bgn.call("bg_conv_pool4_wgrad", y1, gpool, dw16, n, h // 2, w_ // 2, ci, co, 0)
+    bgn.call("bg_conv_pool4_wgrad", y1, gpool, dw16, n, h // 2, w_ // 2, ci, co, 1)
+    dw = torch.empty(co, ci, 3, 3, device=DEV)
+    bgn.call("bg_unpack_wgrad_pool4", dw16, dw, co, ci, 0.5 * coef, 0)
+    torch.cuda.synchronize()
+    err = relerr(dw, wparam.grad)
+    assert err < 6e-3, f"conv+pool wgrad {shape}: rel-L2 {err:.3e}"
