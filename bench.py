@@ -461,7 +461,7 @@ def sampling_leg(device, batch=256, steps=8, iters=3, warmup=2, gen=None):
 
     run(warmup, False)
     ms = run(iters, False)
-    run(1, True)
+    run(2, True)                  # touches BOTH pinned image buffers: the first copy into fresh pinned pages is ~10x slower
     ms_e2e = run(iters, True)
     peaks = load_peaks()
     v = batch * iters / (ms / 1e3)
