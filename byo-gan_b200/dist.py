@@ -19,6 +19,7 @@ import torch
 import torch.distributed as dist
 
 BUCKET_BYTES = 25 * 1024 * 1024
+LARGE_BYTES = 4 * 1024 * 1024
 
 
 def init_from_env():
@@ -61,13 +62,27 @@ class GradSync:
         self._pending: List[torch.nn.Parameter] = []
         self._pending_bytes = 0
         self._inflight = []
+        self._scale_later: List[torch.nn.Parameter] = []
         self.bytes_reduced = 0
+        # NCCL averages inside the collective; gloo (CPU tests) has no AVG: sum, then scale in finish()
+        self._avg_op = dist.ReduceOp.SUM
+        if self.enabled and dist.get_backend() == "nccl":
+            self._avg_op = dist.ReduceOp.AVG
 
     def begin(self):
-        self._pending, self._pending_bytes, self._inflight = [], 0, []
+        self._pending, self._pending_bytes, self._inflight, self._scale_later = [], 0, [], []
 
     def ready(self, p: torch.nn.Parameter):
         if not self.enabled or p.grad is None:
+            return
+        if p.grad.numel() * p.grad.element_size() >= LARGE_BYTES and p.grad.is_contiguous():
+            # big conv / FC gradients (>= 4 MB; they are ~90 % of the payload) are averaged IN PLACE, each as its own
+            # collective: no flatten copy, no scatter-back copy, no separate division pass
+            work = dist.all_reduce(p.grad, op=self._avg_op, async_op=True)
+            if self._avg_op is dist.ReduceOp.SUM:
+                self._scale_later.append(p)
+            self._inflight.append((work, None, [p]))
+            self.bytes_reduced += p.grad.numel() * 4
             return
         self._pending.append(p)
         self._pending_bytes += p.grad.numel() * p.grad.element_size()
@@ -83,8 +98,9 @@ class GradSync:
             return
         params, self._pending, self._pending_bytes = self._pending, [], 0
         flat = torch.cat([p.grad.reshape(-1) for p in params])
-        flat.div_(self.world)
-        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True)
+        if self._avg_op is dist.ReduceOp.SUM:
+            flat.div_(self.world)
+        work = dist.all_reduce(flat, op=self._avg_op, async_op=True)
         self._inflight.append((work, flat, params))
         self.bytes_reduced += flat.numel() * 4
 
@@ -94,9 +110,13 @@ class GradSync:
         self._flush()
         for work, flat, params in self._inflight:
             work.wait()
+            if flat is None:
+                continue
             off = 0
             for p in params:
                 n = p.grad.numel()
                 p.grad.copy_(flat[off:off + n].view_as(p.grad))
                 off += n
-        self._inflight = []
+        for p in self._scale_later:
+            p.grad.div_(self.world)
+        self._inflight, self._scale_later = [], []

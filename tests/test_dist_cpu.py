@@ -32,12 +32,14 @@ def _worker(rank, world, port, bucket_bytes, out):
     r, w, _ = bdist.init_from_env()
     assert (r, w) == (rank, world)
     torch.manual_seed(100 + rank)                      # different initial values per rank on purpose
-    model = torch.nn.ModuleList([torch.nn.Linear(37, 53), torch.nn.Linear(53, 11), torch.nn.Linear(11, 5)])
+    # the 1100 x 1000 weight (4.4 MB) takes the large-gradient path: averaged in place, outside the buckets
+    model = torch.nn.ModuleList([torch.nn.Linear(37, 53), torch.nn.Linear(53, 11), torch.nn.Linear(1100, 1000),
+                                 torch.nn.Linear(11, 5)])
     bdist.broadcast_parameters(model)
     params = list(model.parameters())
     flat0 = torch.cat([p.detach().reshape(-1) for p in params])
     # gradients: rank-dependent values; the LAST layer is "inactive" (grad None) like an unused progressive stage
-    for i, p in enumerate(params[:4]):
+    for i, p in enumerate(params[:6]):
         p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
     sync = bdist.GradSync(bucket_bytes=bucket_bytes)
     sync.begin()
@@ -62,11 +64,11 @@ def test_gradsync_world2_gloo(tmp_path, bucket_bytes):
     assert res["params_equal"], "broadcast_parameters must leave identical replicas"
     mean_scale = (1 + 2) / 2.0                          # average of rank+1 over the two ranks
     for i, g in enumerate(res["grads"]):
-        if i < 4:
+        if i < 6:
             assert torch.allclose(g, torch.full_like(g, mean_scale * (i + 1))), (i, g.flatten()[:4])
         else:
             assert g is None, "inactive parameter gradients stay None on every rank"
-    assert res["bytes"] == 4 * (37 * 53 + 53 + 53 * 11 + 11)
+    assert res["bytes"] == 4 * (37 * 53 + 53 + 53 * 11 + 11 + 1100 * 1000 + 1000)
 
 
 def test_single_process_is_a_noop():
