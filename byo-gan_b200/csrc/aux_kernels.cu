@@ -588,33 +588,40 @@ __global__ void in_reduce_kernel(const __nv_bfloat16* __restrict__ a, const __nv
 }
 
 // x = gamma * (a - mean) * rstd + beta;   style = [gamma (C) | beta (C)] per sample (gan.py:66-69)
+// grid = (blocks per sample, N): a thread keeps ONE (sample, 8-channel group) for its whole loop, so the per-(n,c)
+// scale / shift are computed once into registers and the inner loop is load - 8 FMA - store (HBM-bound).
 __global__ void adain_apply_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ stats,
                                    const float* __restrict__ style, __nv_bfloat16* __restrict__ x, int N, int HW,
                                    int C, float eps) {
   const int cv = C / 8;
-  const size_t total = (size_t)N * HW * cv;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cv) * 8;
-    const size_t p = i / cv;
-    const int n = (int)(p / HW);
-    F8 v = ld8(a + p * C + c);
+  const int n = blockIdx.y;
+  const int tc = threadIdx.x % cv;                   // channel group, fixed (blockDim.x and gridDim.x*blockDim.x % cv == 0)
+  const int c = tc * 8;
+  float sc[8], sh[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float* st = stats + ((size_t)n * C + c + j) * 2;
-      const float m = st[0] / HW;
-      const float var = fmaxf(st[1] / HW - m * m, 0.f);
-      const float r = rsqrtf(var + eps);
-      const float ga = style[(size_t)n * 2 * C + c + j];
-      const float be = style[(size_t)n * 2 * C + C + c + j];
-      v.v[j] = ga * (v.v[j] - m) * r + be;
-    }
-    st8(x + p * C + c, v);
+  for (int j = 0; j < 8; ++j) {
+    const float* st = stats + ((size_t)n * C + c + j) * 2;
+    const float m = st[0] / HW;
+    const float var = fmaxf(st[1] / HW - m * m, 0.f);
+    sc[j] = style[(size_t)n * 2 * C + c + j] * rsqrtf(var + eps);
+    sh[j] = style[(size_t)n * 2 * C + C + c + j] - sc[j] * m;
+  }
+  const __nv_bfloat16* ab = a + (size_t)n * HW * C + c;
+  __nv_bfloat16* xb = x + (size_t)n * HW * C + c;
+  const int rows = blockDim.x / cv;
+  for (int p = blockIdx.x * rows + threadIdx.x / cv; p < HW; p += gridDim.x * rows) {
+    F8 v = ld8(ab + (size_t)p * C);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v.v[j] = fmaf(v.v[j], sc[j], sh[j]);
+    st8(xb + (size_t)p * C, v);
   }
 }
 
 // gpre = gate(a) * gamma * rstd * (g - S1/HW - ahat * S2/HW)   (instance-norm backward + LeakyReLU gate)
 // wsum (optional, zeroed by the launcher): wsum[0][c] += sum gpre (conv bias gradient, gan.py:30),
 // wsum[1][c] += sum gpre * noise[n,hw] (InjectSecondaryNoise weight gradient, gan.py:52).
+// grid = (blocks per sample, N), fixed (sample, channel group) per thread: with k1 = gamma*rstd, k2 = S1/HW,
+// k3 = rstd*S2/HW the inner loop is  v = k1 * (g - k2 - (a - m) * k3)  on registers.
 __global__ void adain_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ a,
                                        const float* __restrict__ stats, const float* __restrict__ style,
                                        const float* __restrict__ bsums, __nv_bfloat16* __restrict__ out, int N,
@@ -622,34 +629,40 @@ __global__ void adain_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, cons
                                        const float* __restrict__ noise, float* __restrict__ wsum) {
   extern __shared__ float red[];
   const int cv = C / 8;
-  const size_t total = (size_t)N * HW * cv;
+  const int n = blockIdx.y;
+  const int c = (threadIdx.x % cv) * 8;
   const float inv = 1.f / HW;
+  float k1[8], k2[8], k3[8], mu[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const size_t sc = ((size_t)n * C + c + j) * 2;
+    const float m = stats[sc] * inv;
+    const float var = fmaxf(stats[sc + 1] * inv - m * m, 0.f);
+    const float rs = rsqrtf(var + eps);
+    mu[j] = m;
+    k1[j] = style[(size_t)n * 2 * C + c + j] * rs;
+    k2[j] = bsums[sc] * inv;
+    k3[j] = rs * bsums[sc + 1] * inv;
+  }
   float acc[2][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cv) * 8;
-    const size_t p = i / cv;
-    const int n = (int)(p / HW);
-    const F8 av = ld8(a + p * C + c);
-    const F8 gv = ld8(g + p * C + c);
-    const float nz = (wsum != nullptr && noise != nullptr) ? noise[p] : 0.f;
+  const size_t base = (size_t)n * HW * C + c;
+  const int rows = blockDim.x / cv;
+  for (int p = blockIdx.x * rows + threadIdx.x / cv; p < HW; p += gridDim.x * rows) {
+    const F8 av = ld8(a + base + (size_t)p * C);
+    const F8 gv = ld8(g + base + (size_t)p * C);
+    const float nz = (wsum != nullptr && noise != nullptr) ? noise[(size_t)n * HW + p] : 0.f;
     F8 r;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const size_t sc = ((size_t)n * C + c + j) * 2;
-      const float m = stats[sc] * inv;
-      const float var = fmaxf(stats[sc + 1] * inv - m * m, 0.f);
-      const float rs = rsqrtf(var + eps);
-      const float ga = style[(size_t)n * 2 * C + c + j];
-      const float ah = (av.v[j] - m) * rs;
-      float v = ga * rs * (gv.v[j] - bsums[sc] * inv - ah * bsums[sc + 1] * inv);
+      float v = k1[j] * (gv.v[j] - k2[j] - (av.v[j] - mu[j]) * k3[j]);
       if (gate) v *= av.v[j] > 0.f ? 1.f : slope;
       r.v[j] = v;
       acc[0][j] += v;
       acc[1][j] = fmaf(v, nz, acc[1][j]);
     }
-    st8(out + p * C + c, r);
+    st8(out + base + (size_t)p * C, r);
   }
   if (wsum != nullptr) block_channel_reduce<2>(acc, red, wsum, C);
 }
@@ -940,12 +953,20 @@ int launch_adain_bwd_reduce(const void* g, const void* a, const float* stats, fl
   return in_reduce_launch(a, g, stats, bsums, N, HW, C, eps, 1, s);
 }
 
+// blocks per sample for the sample-aligned elementwise kernels: ~8 blocks per SM overall, at least 8 pixel rows each
+static int blocks_per_sample(int N, int HW, int C) {
+  const int rows = kBlock / (C / 8);
+  int bps = (num_sms() * 8 + N - 1) / N;
+  const int max_bps = (HW + rows * 8 - 1) / (rows * 8);
+  if (bps > max_bps) bps = max_bps;
+  return bps < 1 ? 1 : bps;
+}
+
 int launch_adain_apply(const void* a, const float* stats, const float* style, void* x, int N, int HW, int C, float eps,
                        cudaStream_t s) {
-  BG_REQUIRE(C % 8 == 0, "adain_apply: C must be a multiple of 8");
-  const size_t total = (size_t)N * HW * (C / 8);
-  adain_apply_kernel<<<grid_for(total), kBlock, 0, s>>>((const __nv_bfloat16*)a, stats, style, (__nv_bfloat16*)x, N, HW,
-                                                       C, eps);
+  BG_REQUIRE(C % 8 == 0 && kBlock % (C / 8) == 0, "adain_apply: C/8 must divide %d (C %d)", kBlock, C);
+  adain_apply_kernel<<<dim3(blocks_per_sample(N, HW, C), N), kBlock, 0, s>>>((const __nv_bfloat16*)a, stats, style,
+                                                                           (__nv_bfloat16*)x, N, HW, C, eps);
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -953,17 +974,15 @@ int launch_adain_apply(const void* a, const float* stats, const float* style, vo
 int launch_adain_bwd_apply(const void* g, const void* a, const float* stats, const float* style, const float* bsums,
                            void* out, int N, int HW, int C, float eps, float slope, int gate, const float* noise,
                            float* wsum, cudaStream_t s) {
-  BG_REQUIRE(C % 8 == 0, "adain_bwd_apply: C must be a multiple of 8");
-  const size_t total = (size_t)N * HW * (C / 8);
+  BG_REQUIRE(C % 8 == 0 && kBlock % (C / 8) == 0, "adain_bwd_apply: C/8 must divide %d (C %d)", kBlock, C);
   size_t smem = 0;
   if (wsum != nullptr) {
-    BG_REQUIRE(kBlock % (C / 8) == 0, "adain_bwd_apply: fused sums need C/8 to divide %d (C %d)", kBlock, C);
     BG_CHECK_CUDA(cudaMemsetAsync(wsum, 0, (size_t)2 * C * sizeof(float), s));
     smem = (size_t)kBlock * 16 * sizeof(float);
   }
-  adain_bwd_apply_kernel<<<grid_for(total), kBlock, smem, s>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)a, stats,
-                                                              style, bsums, (__nv_bfloat16*)out, N, HW, C, eps, slope,
-                                                              gate, noise, wsum);
+  adain_bwd_apply_kernel<<<dim3(blocks_per_sample(N, HW, C), N), kBlock, smem, s>>>(
+      (const __nv_bfloat16*)g, (const __nv_bfloat16*)a, stats, style, bsums, (__nv_bfloat16*)out, N, HW, C, eps, slope, gate,
+      noise, wsum);
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
