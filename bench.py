@@ -460,9 +460,10 @@ def sampling_leg(device, batch=256, steps=8, iters=3, warmup=2, gen=None):
         return t0.elapsed_time(t1)
 
     run(warmup, False)
-    ms = run(iters, False)
+    ms = sorted(run(iters, False) for _ in range(3))[1]
     run(2, True)                  # touches BOTH pinned image buffers: the first copy into fresh pinned pages is ~10x slower
-    ms_e2e = run(iters, True)
+    # median of 3 regions: on the shared hosts the 805 MB device->host copies now and then run at a fraction of the PCIe rate
+    ms_e2e = sorted(run(iters, True) for _ in range(3))[1]
     peaks = load_peaks()
     v = batch * iters / (ms / 1e3)
     return {"metric": "generate img/s at 512x512", "value": round(v, 1), "unit": "img/s", "batch": batch, "iters": iters,

@@ -28,6 +28,32 @@ __device__ __forceinline__ void st8(__nv_bfloat16* p, const F8& r) {
   u.w = pack_bf16x2(r.v[6], r.v[7]);
   *reinterpret_cast<uint4*>(p) = u;
 }
+// Index decomposition for the grid-stride elementwise kernels: every divisor of the model's maps (C/8, W, H) is a power
+// of two, so quotient / remainder are a shift and a mask; 32-bit division is the fallback (element counts < 2^32).
+struct Div32 {
+  uint32_t d;
+  int shift;      // >= 0: d == 1 << shift
+};
+inline Div32 make_div(uint32_t d) {
+  Div32 k;
+  k.d = d;
+  k.shift = -1;
+  if (d != 0 && (d & (d - 1)) == 0) {
+    k.shift = 0;
+    while ((1u << k.shift) < d) ++k.shift;
+  }
+  return k;
+}
+__device__ __forceinline__ uint32_t divmod(uint32_t x, const Div32& k, uint32_t& rem) {
+  if (k.shift >= 0) {
+    rem = x & (k.d - 1u);
+    return x >> k.shift;
+  }
+  const uint32_t q = x / k.d;
+  rem = x - q * k.d;
+  return q;
+}
+
 inline int grid_for(size_t work, int cap_mult = 8) {
   size_t blocks = (work + kBlock - 1) / kBlock;
   size_t cap = (size_t)num_sms() * cap_mult;
@@ -234,16 +260,15 @@ __global__ void axpby_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfl
 // mode 0: y = lrelu(avg4(u));  mode 1: y = avg4(u) * gate(gate_src)   (tangent pass of the backward)
 __global__ void pool_act_fwd_kernel(const __nv_bfloat16* __restrict__ u, const __nv_bfloat16* __restrict__ gate_src,
                                     __nv_bfloat16* __restrict__ y, int N, int Ho, int Wo, int C, float slope,
-                                    int mode) {
+                                    int mode, Div32 dcv, Div32 dw, Div32 dh) {
   const int cv = C / 8;
   const size_t total = (size_t)N * Ho * Wo * cv;
   const int W = Wo * 2;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cv) * 8;
-    const size_t po = i / cv;
-    const int wo = (int)(po % Wo);
-    const int ho = (int)((po / Wo) % Ho);
-    const int n = (int)(po / ((size_t)Wo * Ho));
+    uint32_t cg, uw, uh;
+    const uint32_t po = divmod((uint32_t)i, dcv, cg);
+    const uint32_t n = divmod(divmod(po, dw, uw), dh, uh);
+    const int c = (int)cg * 8, wo = (int)uw, ho = (int)uh;
     const size_t base = (((size_t)n * Ho * 2 + ho * 2) * W + wo * 2) * C + c;
     const F8 a = ld8(u + base), b = ld8(u + base + C), d = ld8(u + base + (size_t)W * C),
              e = ld8(u + base + (size_t)W * C + C);
@@ -255,14 +280,14 @@ __global__ void pool_act_fwd_kernel(const __nv_bfloat16* __restrict__ u, const _
         r.v[j] = s > 0.f ? s : s * slope;
       }
     } else {
-      const F8 gt = ld8(gate_src + po * C + c);
+      const F8 gt = ld8(gate_src + (size_t)po * C + c);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float s = 0.25f * (a.v[j] + b.v[j] + d.v[j] + e.v[j]);
         r.v[j] = s * (gt.v[j] > 0.f ? 1.f : slope);
       }
     }
-    st8(y + po * C + c, r);
+    st8(y + (size_t)po * C + c, r);
   }
 }
 
@@ -270,7 +295,7 @@ __global__ void pool_act_fwd_kernel(const __nv_bfloat16* __restrict__ u, const _
 // the full-resolution map of gu[.,c] = sum_{n,h,w} gy * gate — the bias gradient of the conv that feeds the pool.
 __global__ void pool_act_bwd_kernel(const __nv_bfloat16* __restrict__ gy, const __nv_bfloat16* __restrict__ y,
                                     __nv_bfloat16* __restrict__ gu, int N, int Ho, int Wo, int C, float slope,
-                                    float* __restrict__ csum) {
+                                    float* __restrict__ csum, Div32 dcv, Div32 dw, Div32 dh) {
   extern __shared__ float red[];
   const int cv = C / 8;
   const size_t total = (size_t)N * Ho * Wo * cv;
@@ -279,13 +304,12 @@ __global__ void pool_act_bwd_kernel(const __nv_bfloat16* __restrict__ gy, const 
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cv) * 8;
-    const size_t po = i / cv;
-    const int wo = (int)(po % Wo);
-    const int ho = (int)((po / Wo) % Ho);
-    const int n = (int)(po / ((size_t)Wo * Ho));
-    F8 g = ld8(gy + po * C + c);
-    const F8 yy = ld8(y + po * C + c);
+    uint32_t cg, uw, uh;
+    const uint32_t po = divmod((uint32_t)i, dcv, cg);
+    const uint32_t n = divmod(divmod(po, dw, uw), dh, uh);
+    const int c = (int)cg * 8, wo = (int)uw, ho = (int)uh;
+    F8 g = ld8(gy + (size_t)po * C + c);
+    const F8 yy = ld8(y + (size_t)po * C + c);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       g.v[j] *= 0.25f * (yy.v[j] > 0.f ? 1.f : slope);
@@ -308,16 +332,15 @@ __global__ void pool_act_bwd_kernel(const __nv_bfloat16* __restrict__ gy, const 
 // bilinear x2 upsample, align_corners=False (nn.Upsample, gan.py:112,123): taps .75/.25, edge clamp
 // ---------------------------------------------------------------------------------------------
 __global__ void upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N,
-                                      int H, int W, int C) {
+                                      int H, int W, int C, Div32 dcv, Div32 dw, Div32 dh) {
   const int cv = C / 8;
   const int Ho = 2 * H, Wo = 2 * W;
   const size_t total = (size_t)N * Ho * Wo * cv;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cv) * 8;
-    const size_t po = i / cv;
-    const int wo = (int)(po % Wo);
-    const int ho = (int)((po / Wo) % Ho);
-    const int n = (int)(po / ((size_t)Wo * Ho));
+    uint32_t cg, uw, uh;
+    const uint32_t po = divmod((uint32_t)i, dcv, cg);
+    const uint32_t n = divmod(divmod(po, dw, uw), dh, uh);
+    const int c = (int)cg * 8, wo = (int)uw, ho = (int)uh;
     // source rows: ho even -> (h-1: .25, h: .75); ho odd -> (h: .75, h+1: .25)
     const int h = ho >> 1, w = wo >> 1;
     const int h2 = (ho & 1) ? min(h + 1, H - 1) : max(h - 1, 0);
@@ -329,7 +352,7 @@ __global__ void upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       r.v[j] = 0.5625f * a.v[j] + 0.1875f * (b.v[j] + d.v[j]) + 0.0625f * e.v[j];
-    st8(y + po * C + c, r);
+    st8(y + (size_t)po * C + c, r);
   }
 }
 
@@ -345,16 +368,15 @@ __device__ __forceinline__ float up_weight(int r, int l, int L) {
 
 // adjoint of the above: gx[h,w] = sum_{r,s} up_weight(r,h) up_weight(s,w) gy[r,s]
 __global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ gy, __nv_bfloat16* __restrict__ gx, int N,
-                                      int H, int W, int C) {
+                                      int H, int W, int C, Div32 dcv, Div32 dw, Div32 dh) {
   const int cv = C / 8;
   const int Ho = 2 * H, Wo = 2 * W;
   const size_t total = (size_t)N * H * W * cv;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cv) * 8;
-    const size_t p = i / cv;
-    const int w = (int)(p % W);
-    const int h = (int)((p / W) % H);
-    const int n = (int)(p / ((size_t)W * H));
+    uint32_t cg, uw, uh;
+    const uint32_t p = divmod((uint32_t)i, dcv, cg);
+    const uint32_t n = divmod(divmod(p, dw, uw), dh, uh);
+    const int c = (int)cg * 8, w = (int)uw, h = (int)uh;
     F8 acc;
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc.v[j] = 0.f;
@@ -372,7 +394,7 @@ __global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ gy, __nv
         for (int j = 0; j < 8; ++j) acc.v[j] += ws * g.v[j];
       }
     }
-    st8(gx + p * C + c, acc);
+    st8(gx + (size_t)p * C + c, acc);
   }
 }
 
@@ -384,7 +406,7 @@ __global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ gy, __nv
 // ---------------------------------------------------------------------------------------------
 __global__ void channel_wsum_kernel(const __nv_bfloat16* __restrict__ g, const float* __restrict__ planes,
                                     float* __restrict__ out, size_t P, int C, int HW, size_t img_stride,
-                                    size_t plane_stride, int nplanes, int pix_per_block) {
+                                    size_t plane_stride, int nplanes, int pix_per_block, int hw_shift) {
   extern __shared__ float red[];  // [rows][4][C]
   const int cv = C / 8;
   const int rows = blockDim.x / cv;  // pixel lanes per block
@@ -399,11 +421,15 @@ __global__ void channel_wsum_kernel(const __nv_bfloat16* __restrict__ g, const f
   size_t p1 = p0 + pix_per_block;
   if (p1 > P) p1 = P;
   if (tr < rows) {
+    // HW is a power of two for every map of the model: the plane index costs a shift and a mask instead of two 64-bit
+    // divisions per pixel (hw_shift < 0: general fallback)
+#pragma unroll 4
     for (size_t p = p0 + tr; p < p1; p += rows) {
       const F8 v = ld8(g + p * C + tc * 8);
       float s[3] = {0.f, 0.f, 0.f};
       if (nplanes > 0) {
-        const size_t b = (p / HW) * img_stride + (p % HW);
+        const size_t b = hw_shift >= 0 ? (p >> hw_shift) * img_stride + (p & (size_t)(HW - 1))
+                                       : (p / HW) * img_stride + (p % HW);
         for (int j = 0; j < nplanes; ++j) s[j] = planes[b + j * plane_stride];
       }
 #pragma unroll
@@ -439,7 +465,7 @@ __global__ void channel_wsum_kernel(const __nv_bfloat16* __restrict__ g, const f
 __global__ void planes3_to_nhwc_kernel(const float* __restrict__ img, const float* __restrict__ Wm,
                                        const float* __restrict__ bias, const __nv_bfloat16* __restrict__ gate_src,
                                        __nv_bfloat16* __restrict__ out, size_t P, int HW, int C, int ws_c, int ws_j,
-                                       float coef, int act, float slope) {
+                                       float coef, int act, float slope, Div32 dcv, Div32 dhw) {
   extern __shared__ float sw[];  // [C][3] + [C]
   for (int i = threadIdx.x; i < C * 3; i += blockDim.x) {
     const int c = i / 3, j = i % 3;
@@ -450,9 +476,11 @@ __global__ void planes3_to_nhwc_kernel(const float* __restrict__ img, const floa
   const int cv = C / 8;
   const size_t total = P * cv;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cv) * 8;
-    const size_t p = i / cv;
-    const size_t b = (p / HW) * (size_t)(3 * HW) + (p % HW);
+    uint32_t cg, hw;
+    const uint32_t p = divmod((uint32_t)i, dcv, cg);
+    const uint32_t n = divmod(p, dhw, hw);
+    const int c = (int)cg * 8;
+    const size_t b = (size_t)n * (size_t)(3 * HW) + hw;
     const float i0 = img[b], i1 = img[b + HW], i2 = img[b + 2 * (size_t)HW];
     F8 r;
 #pragma unroll
@@ -463,11 +491,11 @@ __global__ void planes3_to_nhwc_kernel(const float* __restrict__ img, const floa
       r.v[j] = v;
     }
     if (gate_src != nullptr) {
-      const F8 gt = ld8(gate_src + p * C + c);
+      const F8 gt = ld8(gate_src + (size_t)p * C + c);
 #pragma unroll
       for (int j = 0; j < 8; ++j) r.v[j] *= gt.v[j] > 0.f ? 1.f : slope;
     }
-    st8(out + p * C + c, r);
+    st8(out + (size_t)p * C + c, r);
   }
 }
 
@@ -842,8 +870,10 @@ int launch_pool_act_fwd(const void* u, const void* gate_src, void* y, int N, int
   BG_REQUIRE(C % 8 == 0, "pool_act_fwd: C must be a multiple of 8");
   BG_REQUIRE(mode == 0 || gate_src != nullptr, "pool_act_fwd: mode 1 needs gate_src");
   const size_t total = (size_t)N * Ho * Wo * (C / 8);
+  BG_REQUIRE(total < (1ull << 32), "pool_act_fwd: map too large");
   pool_act_fwd_kernel<<<grid_for(total), kBlock, 0, s>>>((const __nv_bfloat16*)u, (const __nv_bfloat16*)gate_src,
-                                                        (__nv_bfloat16*)y, N, Ho, Wo, C, slope, mode);
+                                                        (__nv_bfloat16*)y, N, Ho, Wo, C, slope, mode, make_div(C / 8),
+                                                        make_div(Wo), make_div(Ho));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -858,8 +888,10 @@ int launch_pool_act_bwd(const void* gy, const void* y, void* gu, int N, int Ho, 
     BG_CHECK_CUDA(cudaMemsetAsync(csum, 0, (size_t)C * sizeof(float), s));
     smem = (size_t)kBlock * 8 * sizeof(float);
   }
+  BG_REQUIRE(total < (1ull << 32), "pool_act_bwd: map too large");
   pool_act_bwd_kernel<<<grid_for(total), kBlock, smem, s>>>((const __nv_bfloat16*)gy, (const __nv_bfloat16*)y,
-                                                           (__nv_bfloat16*)gu, N, Ho, Wo, C, slope, csum);
+                                                           (__nv_bfloat16*)gu, N, Ho, Wo, C, slope, csum, make_div(C / 8),
+                                                           make_div(Wo), make_div(Ho));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -867,7 +899,9 @@ int launch_pool_act_bwd(const void* gy, const void* y, void* gu, int N, int Ho, 
 int launch_upsample2x_fwd(const void* x, void* y, int N, int H, int W, int C, cudaStream_t s) {
   BG_REQUIRE(C % 8 == 0, "upsample2x_fwd: C must be a multiple of 8");
   const size_t total = (size_t)N * H * W * 4 * (C / 8);
-  upsample2x_fwd_kernel<<<grid_for(total), kBlock, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C);
+  BG_REQUIRE(total < (1ull << 32), "upsample2x_fwd: map too large");
+  upsample2x_fwd_kernel<<<grid_for(total), kBlock, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C,
+                                                          make_div(C / 8), make_div(2 * W), make_div(2 * H));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -875,7 +909,9 @@ int launch_upsample2x_fwd(const void* x, void* y, int N, int H, int W, int C, cu
 int launch_upsample2x_bwd(const void* gy, void* gx, int N, int H, int W, int C, cudaStream_t s) {
   BG_REQUIRE(C % 8 == 0, "upsample2x_bwd: C must be a multiple of 8");
   const size_t total = (size_t)N * H * W * (C / 8);
-  upsample2x_bwd_kernel<<<grid_for(total), kBlock, 0, s>>>((const __nv_bfloat16*)gy, (__nv_bfloat16*)gx, N, H, W, C);
+  BG_REQUIRE(total < (1ull << 32), "upsample2x_bwd: map too large");
+  upsample2x_bwd_kernel<<<grid_for(total), kBlock, 0, s>>>((const __nv_bfloat16*)gy, (__nv_bfloat16*)gx, N, H, W, C,
+                                                          make_div(C / 8), make_div(W), make_div(H));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -894,8 +930,13 @@ int launch_channel_wsum(const void* g, const float* planes, float* out, size_t P
   const size_t blocks = (P + ppb - 1) / ppb;
   const size_t smem = (size_t)rows * 4 * C * sizeof(float);
   BG_REQUIRE(smem <= 48 * 1024, "channel_wsum: shared memory %zu too large", smem);
+  int hw_shift = -1;
+  if (HW > 0 && (HW & (HW - 1)) == 0) {
+    hw_shift = 0;
+    while ((1 << hw_shift) < HW) ++hw_shift;
+  }
   channel_wsum_kernel<<<(int)blocks, threads, smem, s>>>((const __nv_bfloat16*)g, planes, out, P, C, HW, img_stride,
-                                                        plane_stride, nplanes, (int)ppb);
+                                                        plane_stride, nplanes, (int)ppb, hw_shift);
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -906,7 +947,8 @@ int launch_planes3_to_nhwc(const float* img, const float* Wm, const float* bias,
   BG_REQUIRE(C % 8 == 0 && C <= 1024, "planes3_to_nhwc: unsupported C %d", C);
   const size_t total = P * (C / 8);
   planes3_to_nhwc_kernel<<<grid_for(total), kBlock, (size_t)C * 4 * sizeof(float), s>>>(
-      img, Wm, bias, (const __nv_bfloat16*)gate_src, (__nv_bfloat16*)out, P, HW, C, ws_c, ws_j, coef, act, slope);
+      img, Wm, bias, (const __nv_bfloat16*)gate_src, (__nv_bfloat16*)out, P, HW, C, ws_c, ws_j, coef, act, slope,
+      make_div(C / 8), make_div(HW));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
