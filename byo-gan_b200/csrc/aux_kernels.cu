@@ -381,15 +381,23 @@ __global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ gy, __nv
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc.v[j] = 0.f;
     const __nv_bfloat16* gb = gy + (size_t)n * Ho * Wo * C + c;
-    for (int r = 2 * h - 1; r <= 2 * h + 2; ++r) {
+    float wsv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int sx = 2 * w - 1 + q;
+      wsv[q] = (sx >= 0 && sx < Wo) ? up_weight(sx, w, W) : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = 2 * h - 1 + q;
       if (r < 0 || r >= Ho) continue;
       const float wr = up_weight(r, h, H);
       if (wr == 0.f) continue;
-      for (int s = 2 * w - 1; s <= 2 * w + 2; ++s) {
-        if (s < 0 || s >= Wo) continue;
-        const float ws = up_weight(s, w, W) * wr;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float ws = wsv[t] * wr;
         if (ws == 0.f) continue;
-        const F8 g = ld8(gb + ((size_t)r * Wo + s) * C);
+        const F8 g = ld8(gb + ((size_t)r * Wo + (2 * w - 1 + t)) * C);
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc.v[j] += ws * g.v[j];
       }
@@ -423,14 +431,15 @@ __global__ void channel_wsum_kernel(const __nv_bfloat16* __restrict__ g, const f
   if (tr < rows) {
     // HW is a power of two for every map of the model: the plane index costs a shift and a mask instead of two 64-bit
     // divisions per pixel (hw_shift < 0: general fallback)
-#pragma unroll 4
     for (size_t p = p0 + tr; p < p1; p += rows) {
       const F8 v = ld8(g + p * C + tc * 8);
       float s[3] = {0.f, 0.f, 0.f};
       if (nplanes > 0) {
         const size_t b = hw_shift >= 0 ? (p >> hw_shift) * img_stride + (p & (size_t)(HW - 1))
                                        : (p / HW) * img_stride + (p % HW);
-        for (int j = 0; j < nplanes; ++j) s[j] = planes[b + j * plane_stride];
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          if (j < nplanes) s[j] = planes[b + j * plane_stride];
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -443,9 +452,12 @@ __global__ void channel_wsum_kernel(const __nv_bfloat16* __restrict__ g, const f
   }
   const int nk = 1 + nplanes;
   if (tr < rows) {
-    for (int k = 0; k < nk; ++k)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) red[((size_t)tr * 4 + k) * C + tc * 8 + j] = acc[k][j];
+    for (int k = 0; k < 4; ++k)          // fully unrolled: a runtime index would push acc[][] into local memory
+      if (k < nk) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[((size_t)tr * 4 + k) * C + tc * 8 + j] = acc[k][j];
+      }
   }
   __syncthreads();
   for (int idx = threadIdx.x; idx < nk * C; idx += blockDim.x) {
