@@ -53,19 +53,56 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md recipe).  Sampled through NVML from a
+    thread of this process every 40 ms — the same counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*`
+    prints; a polling nvidia-smi PROCESS was observed to stall kernel launches for hundreds of milliseconds on these
+    hosts (timed regions 60 % long while it ran, never after it was stopped).  Falls back to nvidia-smi at a 500 ms
+    period if pynvml is unavailable."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self._stop, self._thread = index, [], None, False, None
+
+    def _nvml_loop(self, nv, h):
+        names = [("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap)]
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        while not self._stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                self.rows.append((time.time(), [str(sm), str(mx)] + ["Active" if mask & bit else "Not Active" for _, bit in names]))
+            except Exception:
+                pass
+            time.sleep(0.04)
 
     def start(self):
-        """Started BEFORE the warm-up (nvidia-smi needs ~100 ms to produce its first row); only rows that arrive
-        inside the window() are reported."""
+        """Started BEFORE the warm-up; only rows that arrive inside the window() are reported."""
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            # the process may see a subset of the GPUs (CUDA_VISIBLE_DEVICES): map through the PCI bus id
+            bus = torch.cuda.get_device_properties(self.index).pci_bus_id if hasattr(
+                torch.cuda.get_device_properties(self.index), "pci_bus_id") else None
+            h = None
+            if bus is not None:
+                for i in range(nv.nvmlDeviceGetCount()):
+                    hi = nv.nvmlDeviceGetHandleByIndex(i)
+                    if nv.nvmlDeviceGetPciInfo(hi).bus == bus:
+                        h = hi
+                        break
+            if h is None:
+                h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self._thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self._thread.start()
+            return
+        except Exception:
+            self._thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "500", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -78,9 +115,11 @@ class ClockSampler:
         self.t0, self.t1 = t0, t1
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        self._stop = True
+        if self._thread is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        if self.proc is not None:
+            self.proc.terminate()
         t0, t1 = getattr(self, "t0", 0.0), getattr(self, "t1", float("inf"))
         rows = [r for (ts, r) in self.rows if t0 <= ts <= t1 + 0.05]
         sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
@@ -88,7 +127,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvml" if self._thread is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -297,6 +336,8 @@ def run_b200(args):
     # cyclic GC sometimes need a few more iterations before the step time is stationary; keep warming up (untimed,
     # at most 8 more iterations) until two consecutive iterations are within 4 % of the fastest one seen
     import gc
+    gc.collect()
+    gc.disable()                                             # no collector pauses inside the timed regions
     extra, best, calm = 0, float("inf"), 0
     while extra < 8 and calm < 2:
         t = timed(1, from_host=False)
@@ -308,13 +349,11 @@ def run_b200(args):
             print(f"[settle] iteration {extra}: {t:.2f} ms  reserved {st['reserved_bytes.all.current'] / 2**30:.2f} GiB "
                   f"cudaMalloc retries {st.get('num_alloc_retries', 0)} segments {st.get('segment.all.current', 0)}",
                   file=sys.stderr)
-    gc.collect()
-    gc.disable()                                             # no collector pauses inside the timed regions
     # The GPU boxes are shared hosts: a neighbour's burst on the host cores now and then slows the Python thread that
-    # feeds ~680 launches per iteration, and one timed region in four or five comes out 10-40 % long with identical
-    # clocks and allocator state.  Each leg is therefore timed REPEATS times (each region = exactly K steps between
+    # feeds ~530 launches per iteration, and one timed region in four or five comes out 10-80 % long with identical
+    # clocks and allocator state.  Each leg is therefore timed REPEATS (5) times (each region = exactly K steps between
     # barrier + synchronize, max over ranks) and the MEDIAN region is reported; all regions are listed in the line.
-    REPEATS = 3
+    REPEATS = 5
     n0 = bgn.launch_count
     w0 = time.time()
     reps = [timed(args.steps, from_host=False) for _ in range(REPEATS)]

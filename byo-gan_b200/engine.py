@@ -756,6 +756,7 @@ def critic_backward(critic, packs: PackCache, tape, g_pred, need: Dict[int, bool
     if need_img:
         g_img = torch.zeros_like(tape["img"])
     blocks = tape["blocks"]
+    gx_gated = False          # the gradient entering the topmost block comes from the mbstd layer: not gated yet
     for idx in reversed(range(len(blocks))):
         e = blocks[idx]
         t = T["blocks"][idx] if T else None
@@ -794,8 +795,11 @@ def critic_backward(critic, packs: PackCache, tape, g_pred, need: Dict[int, bool
         if r >= 32:
             # conv_2 -> pool is handled as ONE 4x4 stride-2 conv in all three directions: everything works from the
             # gated gradient at the POOLED map, the full-resolution pool adjoint is never materialised
-            gpool = torch.empty_like(gy2)
-            call("bg_act_gate", gy2, e["y2"], gpool, gy2.numel(), SLOPE)                        # LReLU adjoint
+            if gx_gated:
+                gpool = gy2                                                                     # already gated above
+            else:
+                gpool = torch.empty_like(gy2)
+                call("bg_act_gate", gy2, e["y2"], gpool, gy2.numel(), SLOPE)                    # LReLU adjoint
             if kk is not None:
                 kk["gp"] = gpool
             if want(c2b.weight):
@@ -833,8 +837,13 @@ def critic_backward(critic, packs: PackCache, tape, g_pred, need: Dict[int, bool
         first = idx == 0
         if first:
             gx = conv3x3(g1, wd1, cout, cin, gate_src=tape["x0"])                              # gate of fromRGB's LReLU
+            gx_gated = False
         else:
-            gx = conv3x3(g1, wd1, cout, cin)
+            # this block's input IS the block below's pooled output y2: when that block takes the folded path (and there
+            # is no fade-in lerp in between) its LeakyReLU adjoint is applied right here, in this dgrad's epilogue
+            below = blocks[idx - 1]
+            gx_gated = ("d" not in below) and below["R"] >= 32
+            gx = conv3x3(g1, wd1, cout, cin, gate_src=e["x"] if gx_gated else None)
         del g1
         if keep is not None:
             keep.setdefault("blocks", [None] * len(blocks))[idx] = kk
