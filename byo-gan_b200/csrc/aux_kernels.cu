@@ -91,6 +91,7 @@ __device__ __forceinline__ void block_channel_reduce(float (&acc)[NK][8], float*
 // tap' = flipped tap, so that the dgrad pass is the same forward kernel run on the gradient.
 __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wf,
                                    __nv_bfloat16* __restrict__ wd, int Cout, int Cin, int Cin_pad, int ks, float coef) {
+  pdl_prologue();
   const int taps = ks * ks;
   const size_t total = (size_t)taps * Cout * Cin_pad;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -111,6 +112,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
 // w: fp32 (Cout, Cin, 3, 3) -> w16: bf16 [a*4+b][Cout][Cin], equalized coefficient folded in; summed in fp32, rounded once.
 __global__ void pack_weight_pool4_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ w16, int Cout, int Cin,
                                          float coef) {
+  pdl_prologue();
   const size_t total = (size_t)16 * Cout * Cin;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int ci = (int)(i % Cin);
@@ -135,6 +137,7 @@ __global__ void pack_weight_pool4_kernel(const float* __restrict__ w, __nv_bfloa
 // wt: bf16 [(2 py + px) * 4 + 2 ta + tb][Cin][Cout] = W4[a][b][co][ci] transposed (GEMM N = ci, K = co).
 __global__ void pack_weight_tconv4_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wt, int Cout, int Cin,
                                           float coef) {
+  pdl_prologue();
   const size_t total = (size_t)16 * Cin * Cout;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int co = (int)(i % Cout);
@@ -168,6 +171,7 @@ struct PackGroups {
   int groups;
 };
 __global__ void pack_weight_grouped_kernel(const PackGroups G) {
+  pdl_prologue();
   int g = 0;
   while (g + 1 < G.groups && (int)blockIdx.x >= G.blk0[g + 1]) ++g;
   const int Cout = G.Cout[g], Cin = G.Cin[g], Cin_pad = G.Cin_pad[g], taps = G.ks[g] * G.ks[g];
@@ -192,6 +196,7 @@ __global__ void pack_weight_grouped_kernel(const PackGroups G) {
 // dwp: fp32 [tap][Cout][Cin_pad] -> dw: fp32 (Cout, Cin, ks, ks), scaled by coef; optionally accumulates.
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Cout, int Cin,
                                     int Cin_pad, int ks, float coef, int accumulate) {
+  pdl_prologue();
   const int taps = ks * ks;
   const size_t total = (size_t)Cout * Cin * taps;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -207,6 +212,7 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __rest
 // dw: fp32 (Cout, Cin, 3, 3):  dW3[ky][kx] = coef / 4 * sum_{dy,dx in {0,1}} dW4[ky+dy][kx+dx]   (adjoint of the pack)
 __global__ void unpack_wgrad_pool4_kernel(const float* __restrict__ dw4, float* __restrict__ dw, int Cout, int Cin,
                                           float coef, int accumulate) {
+  pdl_prologue();
   const size_t total = (size_t)Cout * Cin * 9;
   const size_t plane = (size_t)Cout * Cin;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -228,6 +234,7 @@ __global__ void unpack_wgrad_pool4_kernel(const float* __restrict__ dw4, float* 
 // ---------------------------------------------------------------------------------------------
 __global__ void act_gate_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y,
                                 __nv_bfloat16* __restrict__ out, size_t nvec, float slope) {
+  pdl_prologue();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
     F8 a = ld8(g + i * 8);
     const F8 b = ld8(y + i * 8);
@@ -240,6 +247,7 @@ __global__ void act_gate_kernel(const __nv_bfloat16* __restrict__ g, const __nv_
 // out = ca * a + cb * b  (torch.lerp on feature maps, gan.py:347, and its gradient scalings)
 __global__ void axpby_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
                              __nv_bfloat16* __restrict__ out, size_t nvec, float ca, float cb) {
+  pdl_prologue();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
     F8 x = ld8(a + i * 8);
     if (b != nullptr) {
@@ -261,6 +269,7 @@ __global__ void axpby_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfl
 __global__ void pool_act_fwd_kernel(const __nv_bfloat16* __restrict__ u, const __nv_bfloat16* __restrict__ gate_src,
                                     __nv_bfloat16* __restrict__ y, int N, int Ho, int Wo, int C, float slope,
                                     int mode, Div32 dcv, Div32 dw, Div32 dh) {
+  pdl_prologue();
   const int cv = C / 8;
   const size_t total = (size_t)N * Ho * Wo * cv;
   const int W = Wo * 2;
@@ -296,6 +305,7 @@ __global__ void pool_act_fwd_kernel(const __nv_bfloat16* __restrict__ u, const _
 __global__ void pool_act_bwd_kernel(const __nv_bfloat16* __restrict__ gy, const __nv_bfloat16* __restrict__ y,
                                     __nv_bfloat16* __restrict__ gu, int N, int Ho, int Wo, int C, float slope,
                                     float* __restrict__ csum, Div32 dcv, Div32 dw, Div32 dh) {
+  pdl_prologue();
   extern __shared__ float red[];
   const int cv = C / 8;
   const size_t total = (size_t)N * Ho * Wo * cv;
@@ -333,6 +343,7 @@ __global__ void pool_act_bwd_kernel(const __nv_bfloat16* __restrict__ gy, const 
 // ---------------------------------------------------------------------------------------------
 __global__ void upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N,
                                       int H, int W, int C, Div32 dcv, Div32 dw, Div32 dh) {
+  pdl_prologue();
   const int cv = C / 8;
   const int Ho = 2 * H, Wo = 2 * W;
   const size_t total = (size_t)N * Ho * Wo * cv;
@@ -369,6 +380,7 @@ __device__ __forceinline__ float up_weight(int r, int l, int L) {
 // adjoint of the above: gx[h,w] = sum_{r,s} up_weight(r,h) up_weight(s,w) gy[r,s]
 __global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ gy, __nv_bfloat16* __restrict__ gx, int N,
                                       int H, int W, int C, Div32 dcv, Div32 dw, Div32 dh) {
+  pdl_prologue();
   const int cv = C / 8;
   const int Ho = 2 * H, Wo = 2 * W;
   const size_t total = (size_t)N * H * W * cv;
@@ -415,6 +427,7 @@ __global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ gy, __nv
 __global__ void channel_wsum_kernel(const __nv_bfloat16* __restrict__ g, const float* __restrict__ planes,
                                     float* __restrict__ out, size_t P, int C, int HW, size_t img_stride,
                                     size_t plane_stride, int nplanes, int pix_per_block, int hw_shift) {
+  pdl_prologue();
   extern __shared__ float red[];  // [rows][4][C]
   const int cv = C / 8;
   const int rows = blockDim.x / cv;  // pixel lanes per block
@@ -478,6 +491,7 @@ __global__ void planes3_to_nhwc_kernel(const float* __restrict__ img, const floa
                                        const float* __restrict__ bias, const __nv_bfloat16* __restrict__ gate_src,
                                        __nv_bfloat16* __restrict__ out, size_t P, int HW, int C, int ws_c, int ws_j,
                                        float coef, int act, float slope, Div32 dcv, Div32 dhw) {
+  pdl_prologue();
   extern __shared__ float sw[];  // [C][3] + [C]
   for (int i = threadIdx.x; i < C * 3; i += blockDim.x) {
     const int c = i / 3, j = i % 3;
@@ -518,6 +532,7 @@ __global__ void planes3_to_nhwc_kernel(const float* __restrict__ img, const floa
 __global__ void nhwc_to_planes3_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ Wm,
                                        const float* __restrict__ bias, float* __restrict__ out, size_t P, int HW,
                                        int C, int ws_c, int ws_j, float coef) {
+  pdl_prologue();
   extern __shared__ float sw[];  // [3][C]
   for (int i = threadIdx.x; i < C * 3; i += blockDim.x) {
     const int j = i / C, c = i % C;
@@ -571,6 +586,7 @@ __global__ void nhwc_to_planes3_kernel(const __nv_bfloat16* __restrict__ x, cons
 __global__ void in_reduce_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ g,
                                  const float* __restrict__ stats, float* __restrict__ sums, int HW, int C,
                                  int pix_per_block, int blocks_per_img, float eps, int mode) {
+  pdl_prologue();
   extern __shared__ float red[];  // [rows][2][C]
   const int n = blockIdx.x / blocks_per_img;
   const int chunk = blockIdx.x % blocks_per_img;
@@ -633,6 +649,7 @@ __global__ void in_reduce_kernel(const __nv_bfloat16* __restrict__ a, const __nv
 __global__ void adain_apply_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ stats,
                                    const float* __restrict__ style, __nv_bfloat16* __restrict__ x, int N, int HW,
                                    int C, float eps) {
+  pdl_prologue();
   const int cv = C / 8;
   const int n = blockIdx.y;
   const int tc = threadIdx.x % cv;                   // channel group, fixed (blockDim.x and gridDim.x*blockDim.x % cv == 0)
@@ -667,6 +684,7 @@ __global__ void adain_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, cons
                                        const float* __restrict__ bsums, __nv_bfloat16* __restrict__ out, int N,
                                        int HW, int C, float eps, float slope, int gate,
                                        const float* __restrict__ noise, float* __restrict__ wsum) {
+  pdl_prologue();
   extern __shared__ float red[];
   const int cv = C / 8;
   const int n = blockIdx.y;
@@ -720,6 +738,7 @@ __global__ void style_modulate_kernel(const float* __restrict__ W, const float* 
                                       const float* __restrict__ stats, const float* __restrict__ style,
                                       __nv_bfloat16* __restrict__ wmod, float* __restrict__ btab, int N, int Cin, int Cout,
                                       int HW, float coef, float eps) {
+  pdl_prologue();
   __shared__ float red[9][32];
   const int co = blockIdx.x, n = blockIdx.y;
   const float inv = 1.f / HW;
@@ -768,6 +787,7 @@ __global__ void to_rgb_adain_kernel(const __nv_bfloat16* __restrict__ a, const f
                                     const float* __restrict__ style, const float* __restrict__ Wm,
                                     const float* __restrict__ bias, float* __restrict__ out, int HW, int C, float coef,
                                     float eps) {
+  pdl_prologue();
   extern __shared__ float sw[];  // [3][C] + [3]
   const int n = blockIdx.y;
   const float inv = 1.f / HW;
@@ -847,8 +867,8 @@ int launch_pack_weight(const float* w, void* wf, void* wd, int Cout, int Cin, in
   BG_REQUIRE(ks == 1 || ks == 3, "pack_weight: ks must be 1 or 3");
   BG_REQUIRE(Cin_pad >= Cin, "pack_weight: Cin_pad < Cin");
   const size_t total = (size_t)ks * ks * Cout * Cin_pad;
-  pack_weight_kernel<<<grid_for(total), kBlock, 0, s>>>(w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wd, Cout, Cin, Cin_pad,
-                                                       ks, coef);
+  BG_CHECK_CUDA(launch_pdl(pack_weight_kernel, grid_for(total), kBlock, 0, s, w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wd, Cout, Cin, Cin_pad,
+                                                       ks, coef));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -856,23 +876,23 @@ int launch_pack_weight(const float* w, void* wf, void* wd, int Cout, int Cin, in
 int launch_unpack_wgrad(const float* dwp, float* dw, int Cout, int Cin, int Cin_pad, int ks, float coef,
                         int accumulate, cudaStream_t s) {
   const size_t total = (size_t)ks * ks * Cout * Cin;
-  unpack_wgrad_kernel<<<grid_for(total), kBlock, 0, s>>>(dwp, dw, Cout, Cin, Cin_pad, ks, coef, accumulate);
+  BG_CHECK_CUDA(launch_pdl(unpack_wgrad_kernel, grid_for(total), kBlock, 0, s, dwp, dw, Cout, Cin, Cin_pad, ks, coef, accumulate));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_act_gate(const void* g, const void* y, void* out, size_t n, float slope, cudaStream_t s) {
   BG_REQUIRE(n % 8 == 0, "act_gate: element count must be a multiple of 8");
-  act_gate_kernel<<<grid_for(n / 8), kBlock, 0, s>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)y,
-                                                    (__nv_bfloat16*)out, n / 8, slope);
+  BG_CHECK_CUDA(launch_pdl(act_gate_kernel, grid_for(n / 8), kBlock, 0, s, (const __nv_bfloat16*)g, (const __nv_bfloat16*)y,
+                                                    (__nv_bfloat16*)out, n / 8, slope));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_axpby(const void* a, const void* b, void* out, size_t n, float ca, float cb, cudaStream_t s) {
   BG_REQUIRE(n % 8 == 0, "axpby: element count must be a multiple of 8");
-  axpby_kernel<<<grid_for(n / 8), kBlock, 0, s>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b,
-                                                 (__nv_bfloat16*)out, n / 8, ca, cb);
+  BG_CHECK_CUDA(launch_pdl(axpby_kernel, grid_for(n / 8), kBlock, 0, s, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b,
+                                                 (__nv_bfloat16*)out, n / 8, ca, cb));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -883,9 +903,9 @@ int launch_pool_act_fwd(const void* u, const void* gate_src, void* y, int N, int
   BG_REQUIRE(mode == 0 || gate_src != nullptr, "pool_act_fwd: mode 1 needs gate_src");
   const size_t total = (size_t)N * Ho * Wo * (C / 8);
   BG_REQUIRE(total < (1ull << 32), "pool_act_fwd: map too large");
-  pool_act_fwd_kernel<<<grid_for(total), kBlock, 0, s>>>((const __nv_bfloat16*)u, (const __nv_bfloat16*)gate_src,
+  BG_CHECK_CUDA(launch_pdl(pool_act_fwd_kernel, grid_for(total), kBlock, 0, s, (const __nv_bfloat16*)u, (const __nv_bfloat16*)gate_src,
                                                         (__nv_bfloat16*)y, N, Ho, Wo, C, slope, mode, make_div(C / 8),
-                                                        make_div(Wo), make_div(Ho));
+                                                        make_div(Wo), make_div(Ho)));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -897,13 +917,13 @@ int launch_pool_act_bwd(const void* gy, const void* y, void* gu, int N, int Ho, 
   size_t smem = 0;
   if (csum != nullptr) {
     BG_REQUIRE(kBlock % (C / 8) == 0, "pool_act_bwd: fused bias-gradient sum needs C/8 to divide %d (C %d)", kBlock, C);
-    BG_CHECK_CUDA(cudaMemsetAsync(csum, 0, (size_t)C * sizeof(float), s));
+    if (launch_zero(csum, (size_t)C * sizeof(float), s) != 0) return 1;
     smem = (size_t)kBlock * 8 * sizeof(float);
   }
   BG_REQUIRE(total < (1ull << 32), "pool_act_bwd: map too large");
-  pool_act_bwd_kernel<<<grid_for(total), kBlock, smem, s>>>((const __nv_bfloat16*)gy, (const __nv_bfloat16*)y,
+  BG_CHECK_CUDA(launch_pdl(pool_act_bwd_kernel, grid_for(total), kBlock, smem, s, (const __nv_bfloat16*)gy, (const __nv_bfloat16*)y,
                                                            (__nv_bfloat16*)gu, N, Ho, Wo, C, slope, csum, make_div(C / 8),
-                                                           make_div(Wo), make_div(Ho));
+                                                           make_div(Wo), make_div(Ho)));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -912,8 +932,8 @@ int launch_upsample2x_fwd(const void* x, void* y, int N, int H, int W, int C, cu
   BG_REQUIRE(C % 8 == 0, "upsample2x_fwd: C must be a multiple of 8");
   const size_t total = (size_t)N * H * W * 4 * (C / 8);
   BG_REQUIRE(total < (1ull << 32), "upsample2x_fwd: map too large");
-  upsample2x_fwd_kernel<<<grid_for(total), kBlock, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C,
-                                                          make_div(C / 8), make_div(2 * W), make_div(2 * H));
+  BG_CHECK_CUDA(launch_pdl(upsample2x_fwd_kernel, grid_for(total), kBlock, 0, s, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C,
+                                                          make_div(C / 8), make_div(2 * W), make_div(2 * H)));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -922,8 +942,8 @@ int launch_upsample2x_bwd(const void* gy, void* gx, int N, int H, int W, int C, 
   BG_REQUIRE(C % 8 == 0, "upsample2x_bwd: C must be a multiple of 8");
   const size_t total = (size_t)N * H * W * (C / 8);
   BG_REQUIRE(total < (1ull << 32), "upsample2x_bwd: map too large");
-  upsample2x_bwd_kernel<<<grid_for(total), kBlock, 0, s>>>((const __nv_bfloat16*)gy, (__nv_bfloat16*)gx, N, H, W, C,
-                                                          make_div(C / 8), make_div(W), make_div(H));
+  BG_CHECK_CUDA(launch_pdl(upsample2x_bwd_kernel, grid_for(total), kBlock, 0, s, (const __nv_bfloat16*)gy, (__nv_bfloat16*)gx, N, H, W, C,
+                                                          make_div(C / 8), make_div(W), make_div(H)));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -935,7 +955,7 @@ int launch_channel_wsum(const void* g, const float* planes, float* out, size_t P
   const int cv = C / 8;
   const int threads = cv >= 256 ? cv : 256;
   const int rows = threads / cv;
-  BG_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)(1 + nplanes) * C * sizeof(float), s));
+  if (launch_zero(out, (size_t)(1 + nplanes) * C * sizeof(float), s) != 0) return 1;
   // enough blocks to fill the chip, but at least `rows * 8` pixels each
   size_t ppb = (P + (size_t)num_sms() * 4 - 1) / ((size_t)num_sms() * 4);
   if (ppb < (size_t)rows * 8) ppb = (size_t)rows * 8;
@@ -947,8 +967,8 @@ int launch_channel_wsum(const void* g, const float* planes, float* out, size_t P
     hw_shift = 0;
     while ((1 << hw_shift) < HW) ++hw_shift;
   }
-  channel_wsum_kernel<<<(int)blocks, threads, smem, s>>>((const __nv_bfloat16*)g, planes, out, P, C, HW, img_stride,
-                                                        plane_stride, nplanes, (int)ppb, hw_shift);
+  BG_CHECK_CUDA(launch_pdl(channel_wsum_kernel, (int)blocks, threads, smem, s, (const __nv_bfloat16*)g, planes, out, P, C, HW, img_stride,
+                                                        plane_stride, nplanes, (int)ppb, hw_shift));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -958,9 +978,9 @@ int launch_planes3_to_nhwc(const float* img, const float* Wm, const float* bias,
                            cudaStream_t s) {
   BG_REQUIRE(C % 8 == 0 && C <= 1024, "planes3_to_nhwc: unsupported C %d", C);
   const size_t total = P * (C / 8);
-  planes3_to_nhwc_kernel<<<grid_for(total), kBlock, (size_t)C * 4 * sizeof(float), s>>>(
+  BG_CHECK_CUDA(launch_pdl(planes3_to_nhwc_kernel, grid_for(total), kBlock, (size_t)C * 4 * sizeof(float), s, 
       img, Wm, bias, (const __nv_bfloat16*)gate_src, (__nv_bfloat16*)out, P, HW, C, ws_c, ws_j, coef, act, slope,
-      make_div(C / 8), make_div(HW));
+      make_div(C / 8), make_div(HW)));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -971,8 +991,8 @@ int launch_nhwc_to_planes3(const void* x, const float* Wm, const float* bias, fl
   const int cv = C / 8;
   const int lanes_per_pix = cv < 32 ? cv : 32;
   const size_t groups = (P + (32 / lanes_per_pix) - 1) / (32 / lanes_per_pix);
-  nhwc_to_planes3_kernel<<<grid_for(groups * 32), kBlock, (size_t)C * 3 * sizeof(float), s>>>(
-      (const __nv_bfloat16*)x, Wm, bias, out, P, HW, C, ws_c, ws_j, coef);
+  BG_CHECK_CUDA(launch_pdl(nhwc_to_planes3_kernel, grid_for(groups * 32), kBlock, (size_t)C * 3 * sizeof(float), s, 
+      (const __nv_bfloat16*)x, Wm, bias, out, P, HW, C, ws_c, ws_j, coef));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -983,7 +1003,7 @@ static int in_reduce_launch(const void* a, const void* g, const float* stats, fl
   const int cv = C / 8;
   const int threads = cv >= 256 ? cv : 256;
   const int rows = threads / cv;
-  BG_CHECK_CUDA(cudaMemsetAsync(sums, 0, (size_t)N * C * 2 * sizeof(float), s));
+  if (launch_zero(sums, (size_t)N * C * 2 * sizeof(float), s) != 0) return 1;
   int blocks_per_img = (num_sms() * 4 + N - 1) / N;
   int max_bpi = (HW + rows * 4 - 1) / (rows * 4);
   if (blocks_per_img > max_bpi) blocks_per_img = max_bpi;
@@ -992,8 +1012,8 @@ static int in_reduce_launch(const void* a, const void* g, const float* stats, fl
   blocks_per_img = (HW + ppb - 1) / ppb;
   const size_t smem = (size_t)rows * 2 * C * sizeof(float);
   BG_REQUIRE(smem <= 48 * 1024, "in_reduce: shared memory %zu too large", smem);
-  in_reduce_kernel<<<N * blocks_per_img, threads, smem, s>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)g, stats,
-                                                            sums, HW, C, ppb, blocks_per_img, eps, mode);
+  BG_CHECK_CUDA(launch_pdl(in_reduce_kernel, N * blocks_per_img, threads, smem, s, (const __nv_bfloat16*)a, (const __nv_bfloat16*)g, stats,
+                                                            sums, HW, C, ppb, blocks_per_img, eps, mode));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1019,8 +1039,8 @@ static int blocks_per_sample(int N, int HW, int C) {
 int launch_adain_apply(const void* a, const float* stats, const float* style, void* x, int N, int HW, int C, float eps,
                        cudaStream_t s) {
   BG_REQUIRE(C % 8 == 0 && kBlock % (C / 8) == 0, "adain_apply: C/8 must divide %d (C %d)", kBlock, C);
-  adain_apply_kernel<<<dim3(blocks_per_sample(N, HW, C), N), kBlock, 0, s>>>((const __nv_bfloat16*)a, stats, style,
-                                                                           (__nv_bfloat16*)x, N, HW, C, eps);
+  BG_CHECK_CUDA(launch_pdl(adain_apply_kernel, dim3(blocks_per_sample(N, HW, C), N), kBlock, 0, s, (const __nv_bfloat16*)a, stats, style,
+                                                                           (__nv_bfloat16*)x, N, HW, C, eps));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1031,12 +1051,12 @@ int launch_adain_bwd_apply(const void* g, const void* a, const float* stats, con
   BG_REQUIRE(C % 8 == 0 && kBlock % (C / 8) == 0, "adain_bwd_apply: C/8 must divide %d (C %d)", kBlock, C);
   size_t smem = 0;
   if (wsum != nullptr) {
-    BG_CHECK_CUDA(cudaMemsetAsync(wsum, 0, (size_t)2 * C * sizeof(float), s));
+    if (launch_zero(wsum, (size_t)2 * C * sizeof(float), s) != 0) return 1;
     smem = (size_t)kBlock * 16 * sizeof(float);
   }
-  adain_bwd_apply_kernel<<<dim3(blocks_per_sample(N, HW, C), N), kBlock, smem, s>>>(
+  BG_CHECK_CUDA(launch_pdl(adain_bwd_apply_kernel, dim3(blocks_per_sample(N, HW, C), N), kBlock, smem, s, 
       (const __nv_bfloat16*)g, (const __nv_bfloat16*)a, stats, style, bsums, (__nv_bfloat16*)out, N, HW, C, eps, slope, gate,
-      noise, wsum);
+      noise, wsum));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1045,8 +1065,8 @@ int launch_style_modulate(const float* W, const float* bias, const float* stats,
                           float* btab, int N, int Cin, int Cout, int HW, float coef, float eps, cudaStream_t s) {
   BG_REQUIRE(N > 0 && Cin > 0 && Cout > 0 && HW > 0, "style_modulate: bad shape N %d Cin %d Cout %d HW %d", N, Cin, Cout, HW);
   const int threads = Cin >= 256 ? 256 : (Cin >= 64 ? 64 : 32);
-  style_modulate_kernel<<<dim3(Cout, N), threads, 0, s>>>(W, bias, stats, style, (__nv_bfloat16*)wmod, btab, N, Cin, Cout,
-                                                         HW, coef, eps);
+  BG_CHECK_CUDA(launch_pdl(style_modulate_kernel, dim3(Cout, N), threads, 0, s, W, bias, stats, style, (__nv_bfloat16*)wmod, btab, N, Cin, Cout,
+                                                         HW, coef, eps));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1060,8 +1080,8 @@ int launch_to_rgb_adain(const void* a, const float* stats, const float* style, c
   const int max_bps = (HW / ppw + 63) / 64;                 // at least ~8 pixel groups per warp
   if (bps > max_bps) bps = max_bps;
   if (bps < 1) bps = 1;
-  to_rgb_adain_kernel<<<dim3(bps, N), kBlock, (size_t)(3 * C + 4) * sizeof(float), s>>>(
-      (const __nv_bfloat16*)a, stats, style, Wm, bias, out, HW, C, coef, eps);
+  BG_CHECK_CUDA(launch_pdl(to_rgb_adain_kernel, dim3(bps, N), kBlock, (size_t)(3 * C + 4) * sizeof(float), s, 
+      (const __nv_bfloat16*)a, stats, style, Wm, bias, out, HW, C, coef, eps));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1088,27 +1108,27 @@ int launch_pack_weight_grouped(const float* const* w, void* const* wf, void* con
     blocks += (int)b;
   }
   G.blk0[groups] = blocks;
-  pack_weight_grouped_kernel<<<blocks, kBlock, 0, s>>>(G);
+  BG_CHECK_CUDA(launch_pdl(pack_weight_grouped_kernel, blocks, kBlock, 0, s, G));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_pack_weight_pool4(const float* w, void* w16, int Cout, int Cin, float coef, cudaStream_t s) {
   BG_REQUIRE(Cout > 0 && Cin > 0, "pack_weight_pool4: bad shape");
-  pack_weight_pool4_kernel<<<grid_for((size_t)16 * Cout * Cin), kBlock, 0, s>>>(w, (__nv_bfloat16*)w16, Cout, Cin, coef);
+  BG_CHECK_CUDA(launch_pdl(pack_weight_pool4_kernel, grid_for((size_t)16 * Cout * Cin), kBlock, 0, s, w, (__nv_bfloat16*)w16, Cout, Cin, coef));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_pack_weight_tconv4(const float* w, void* wt, int Cout, int Cin, float coef, cudaStream_t s) {
   BG_REQUIRE(Cout > 0 && Cin > 0, "pack_weight_tconv4: bad shape");
-  pack_weight_tconv4_kernel<<<grid_for((size_t)16 * Cout * Cin), kBlock, 0, s>>>(w, (__nv_bfloat16*)wt, Cout, Cin, coef);
+  BG_CHECK_CUDA(launch_pdl(pack_weight_tconv4_kernel, grid_for((size_t)16 * Cout * Cin), kBlock, 0, s, w, (__nv_bfloat16*)wt, Cout, Cin, coef));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_unpack_wgrad_pool4(const float* dw4, float* dw, int Cout, int Cin, float coef, int accumulate, cudaStream_t s) {
-  unpack_wgrad_pool4_kernel<<<grid_for((size_t)Cout * Cin * 9), kBlock, 0, s>>>(dw4, dw, Cout, Cin, coef, accumulate);
+  BG_CHECK_CUDA(launch_pdl(unpack_wgrad_pool4_kernel, grid_for((size_t)Cout * Cin * 9), kBlock, 0, s, dw4, dw, Cout, Cin, coef, accumulate));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

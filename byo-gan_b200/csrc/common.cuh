@@ -252,6 +252,46 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+
+// ----------------------------------------------------------------------------------------
+// programmatic dependent launch: every kernel of this library is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization (launch_pdl below) so that the NEXT kernel of the stream can be
+// made resident while this one is still running; a kernel therefore (1) releases its dependents at its first
+// instruction and (2) executes pdl_wait() before its first global-memory access: everything ahead of the wait (smem
+// carve-up, mbarrier init, TMEM allocation, tensor-map prefetch) overlaps the tail of the kernel in front.
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+
+bool pdl_enabled();   // runtime.cu: BG_PDL=0 turns the launch attribute off (the device-side instructions become no-ops)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  return [&](KArgs... a) {
+    void* pargs[] = {(void*)&a...};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelExC(&cfg, (const void*)kernel, pargs);
+  }(static_cast<Args&&>(args)...);
+}
+
+// memset replacement that stays inside the programmatic launch chain (a cudaMemsetAsync node between two kernels
+// would serialise them fully); bytes % 4 == 0
+int launch_zero(void* ptr, size_t bytes, cudaStream_t stream);
+
 #endif  // __CUDACC__
 
 }  // namespace bg

@@ -70,6 +70,7 @@ __device__ __forceinline__ TileCoord decode_tile(const FpropParams& p, int tile)
 __global__ void __launch_bounds__(kThreads, 1)
 conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                   const FpropParams p) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -103,6 +104,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
+  pdl_wait();        // everything above overlaps the previous kernel's tail
   if (warp >= 2) {
     for (int c = threadIdx.x - 64; c < p.Cout; c += 32 * kEpiWarps) {
       bias_s[c] = p.bias ? p.bias[c] : 0.f;
@@ -326,7 +328,7 @@ int launch_conv_fprop(const void* x, const void* wpack, void* out, int N, int H,
     attr_set = true;
   }
   int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  conv_fprop_kernel<<<grid, kThreads, smem_bytes, stream>>>(tmx, tmw, p);
+  BG_CHECK_CUDA(launch_pdl(conv_fprop_kernel, grid, kThreads, smem_bytes, stream, tmx, tmw, p));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -584,6 +584,7 @@ template <bool kStats, int kFeed>     // kFeed: 0 TMA halo (plain and pool4), 1 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                  const HaloParams p) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -634,6 +635,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
+  pdl_wait();        // barrier init, TMEM allocation and descriptor prefetch above overlap the previous kernel's tail
   if (warp >= 2 && warp < 2 + kEpiWarpsAll) {
     for (int c = threadIdx.x - 64; c < p.Cout; c += 32 * kEpiWarpsAll) {
       bias_s[c] = p.bias ? p.bias[c] : 0.f;
@@ -1090,7 +1092,7 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
   BG_REQUIRE(p.stats_mode == 0 || ((stats_mode == 1 || stats_mode == 2) && !pool),
              "conv_halo: stats_mode must be 1 or 2 and cannot be combined with the fused pool");
   if (p.stats_mode)
-    BG_CHECK_CUDA(cudaMemsetAsync(stats, 0, (stats_mode == 1 ? (size_t)N * Cout * 2 : (size_t)Cout) * sizeof(float), stream));
+    if (launch_zero(stats, (stats_mode == 1 ? (size_t)N * Cout * 2 : (size_t)Cout) * sizeof(float), stream) != 0) return 1;
   {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("BG_HALO_DEBUG"); dbg = e ? atoi(e) : 0; }
@@ -1134,10 +1136,10 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
     attr_set = true;
   }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  if (p.stats_mode && p.upsample) conv_halo_kernel<true, 1><<<grid, kThreads, smem_bytes, stream>>>(tmw, tmx, p);
-  else if (p.stats_mode) conv_halo_kernel<true, 0><<<grid, kThreads, smem_bytes, stream>>>(tmw, tmx, p);
-  else if (p.upsample) conv_halo_kernel<false, 1><<<grid, kThreads, smem_bytes, stream>>>(tmw, tmx, p);
-  else conv_halo_kernel<false, 0><<<grid, kThreads, smem_bytes, stream>>>(tmw, tmx, p);
+  if (p.stats_mode && p.upsample) BG_CHECK_CUDA(launch_pdl(conv_halo_kernel<true, 1>, grid, kThreads, smem_bytes, stream, tmw, tmx, p));
+  else if (p.stats_mode) BG_CHECK_CUDA(launch_pdl(conv_halo_kernel<true, 0>, grid, kThreads, smem_bytes, stream, tmw, tmx, p));
+  else if (p.upsample) BG_CHECK_CUDA(launch_pdl(conv_halo_kernel<false, 1>, grid, kThreads, smem_bytes, stream, tmw, tmx, p));
+  else BG_CHECK_CUDA(launch_pdl(conv_halo_kernel<false, 0>, grid, kThreads, smem_bytes, stream, tmw, tmx, p));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

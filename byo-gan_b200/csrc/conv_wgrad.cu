@@ -43,6 +43,7 @@ struct WgradParams {
 __global__ void __launch_bounds__(kThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x,
                   const WgradParams p) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -83,6 +84,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_const
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
+  pdl_wait();        // everything above overlaps the previous kernel's tail
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -232,10 +234,10 @@ int launch_conv_wgrad(const void* x, const void* g, float* dw, int N, int H, int
     if (make_tmap_bf16(&tmx, x, 4, dims, str, box, (int)p.b_row_bytes) != 0) return 1;
   }
 
-  if (!accumulate) BG_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)9 * Cout * Cin * sizeof(float), stream));
+  if (!accumulate) if (launch_zero(dw, (size_t)9 * Cout * Cin * sizeof(float), stream) != 0) return 1;
   const size_t smem_bytes = (size_t)kStages * kStageBytes + 256 + 1024;
   BG_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  conv_wgrad_kernel<<<units * splits, kThreads, smem_bytes, stream>>>(tmg, tmx, p);
+  BG_CHECK_CUDA(launch_pdl(conv_wgrad_kernel, units * splits, kThreads, smem_bytes, stream, tmg, tmx, p));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -58,6 +58,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x,
                        const WgradHaloParams p) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -99,6 +100,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
+  pdl_wait();        // everything above overlaps the previous kernel's tail
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -304,14 +306,14 @@ int launch_conv_wgrad_halo(const void* x, const void* g, float* dw, int N, int H
   }
 
   if (!accumulate)
-    BG_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)(pool4 ? 16 : 9) * Cout * Cin * sizeof(float), stream));
+    if (launch_zero(dw, (size_t)(pool4 ? 16 : 9) * Cout * Cin * sizeof(float), stream) != 0) return 1;
   const size_t smem_bytes = (size_t)kStages * kStageBytes + 256 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     BG_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  conv_wgrad_halo_kernel<<<units * splits, kThreads, smem_bytes, stream>>>(tmg, tmx, p);
+  BG_CHECK_CUDA(launch_pdl(conv_wgrad_halo_kernel, units * splits, kThreads, smem_bytes, stream, tmg, tmx, p));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

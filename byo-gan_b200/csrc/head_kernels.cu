@@ -20,6 +20,7 @@ constexpr int kLinMT = 8;
 __global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                   const float* __restrict__ bias, float* __restrict__ y, int M, int N, int K,
                                   float coef, int act, float slope) {
+  pdl_prologue();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int mgroups = (M + kLinMT - 1) / kLinMT;
@@ -69,6 +70,7 @@ constexpr int kLbwNT = 8;
 __global__ void linear_bwd_weight_kernel(const float* __restrict__ gy, const float* __restrict__ x,
                                          float* __restrict__ dW, float* __restrict__ db, int M, int N, int K,
                                          float coef, int accumulate) {
+  pdl_prologue();
   const int k = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int n0 = blockIdx.y * kLbwNT;
   float acc[kLbwNT][4];
@@ -127,6 +129,7 @@ struct LinGroups {
 // fwd: one warp per (n, group of kLinMT rows) of one group; same inner loop as linear_fwd_kernel
 __global__ void linear_fwd_grouped_kernel(const float* __restrict__ x, const LinGroups G, int M, int K, int act,
                                           float slope) {
+  pdl_prologue();
   int g = 0;
   while (g + 1 < G.groups && (int)blockIdx.x >= G.blk0[g + 1]) ++g;
   const int N = G.N[g];
@@ -167,6 +170,7 @@ __global__ void linear_fwd_grouped_kernel(const float* __restrict__ x, const Lin
 
 // bwd_weight: blocks of group g cover (K/4 threads) x (N_g / kLbwNT row groups); dW = coef * gy^T x, db = sum_m gy
 __global__ void linear_bwd_weight_grouped_kernel(const float* __restrict__ x, const LinGroups G, int M, int K) {
+  pdl_prologue();
   int g = 0;
   while (g + 1 < G.groups && (int)blockIdx.x >= G.blk0[g + 1]) ++g;
   const int N = G.N[g];
@@ -208,6 +212,7 @@ __global__ void linear_bwd_weight_grouped_kernel(const float* __restrict__ x, co
 // bwd_input: gx[m,k] = sum_g coef_g * sum_n gy_g[m,n] * Wt_g[k,n]   (Wt_g = transposed weight (K, N_g)); one warp per
 // (k, group of kLinMT rows), looping over the groups: the sum over layers needs no separate accumulation pass
 __global__ void linear_bwd_input_grouped_kernel(const LinGroups G, float* __restrict__ gx, int M, int K) {
+  pdl_prologue();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int mgroups = (M + kLinMT - 1) / kLinMT;
@@ -245,6 +250,7 @@ __global__ void linear_bwd_input_grouped_kernel(const LinGroups G, float* __rest
 
 // out[c][r] = in[r][c]  (fp32), 32x32 smem tiles
 __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int C) {
+  pdl_prologue();
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -261,6 +267,7 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
 // out = g * gate(y) (+ add)   fp32 vectors (LeakyReLU backward on the small fp32 paths)
 __global__ void act_gate_f32_kernel(const float* __restrict__ g, const float* __restrict__ y,
                                     float* __restrict__ out, size_t n, float slope) {
+  pdl_prologue();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     out[i] = g[i] * gate_f(y[i], slope);
 }
@@ -268,6 +275,7 @@ __global__ void act_gate_f32_kernel(const float* __restrict__ g, const float* __
 // out = ca*a + cb*b  fp32 (b may be null)
 __global__ void axpby_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
                                  size_t n, float ca, float cb) {
+  pdl_prologue();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     out[i] = ca * a[i] + (b ? cb * b[i] : 0.f);
 }
@@ -279,6 +287,7 @@ __global__ void axpby_f32_kernel(const float* __restrict__ a, const float* __res
 __global__ void const_noise_act_kernel(const float* __restrict__ cst, const float* __restrict__ noise,
                                        const float* __restrict__ nw, __nv_bfloat16* __restrict__ a, int N, int HW,
                                        int C, float slope) {
+  pdl_prologue();
   const size_t total = (size_t)N * HW * C;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -291,6 +300,7 @@ __global__ void const_noise_act_kernel(const float* __restrict__ cst, const floa
 // dconst[c,hw] = sum_n g[n,hw,c]
 __global__ void const_bwd_kernel(const __nv_bfloat16* __restrict__ g, float* __restrict__ dconst, int N, int HW,
                                  int C) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= HW * C) return;
   const int c = i % C, hw = i / C;
@@ -304,6 +314,7 @@ __global__ void const_bwd_kernel(const __nv_bfloat16* __restrict__ g, float* __r
 // ---------------------------------------------------------------------------------------------
 // F.avg_pool2d(images, 2) (gan.py:345)
 __global__ void img_avgpool2_kernel(const float* __restrict__ img, float* __restrict__ out, int P, int Ho, int Wo) {
+  pdl_prologue();
   const size_t total = (size_t)P * Ho * Wo;
   const int W = 2 * Wo;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -317,6 +328,7 @@ __global__ void img_avgpool2_kernel(const float* __restrict__ img, float* __rest
 // gimg[2h+dy,2w+dx] (+)= 0.25 * scale * g[h,w]
 __global__ void img_avgpool2_bwd_kernel(const float* __restrict__ g, float* __restrict__ gimg, int P, int Ho, int Wo,
                                         float scale, int accumulate) {
+  pdl_prologue();
   const int W = 2 * Wo, H = 2 * Ho;
   const size_t total = (size_t)P * H * W;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -338,6 +350,7 @@ __device__ __forceinline__ void up_taps(int o, int L, int& i0, int& i1, float& w
 // out = (1-alpha) * bilinear_up2(small) + alpha * large       (gan.py:213-220)
 __global__ void img_up2_lerp_kernel(const float* __restrict__ small, const float* __restrict__ large,
                                     float* __restrict__ out, int P, int H, int W, float alpha) {
+  pdl_prologue();
   const int Ho = 2 * H, Wo = 2 * W;
   const size_t total = (size_t)P * Ho * Wo;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -357,6 +370,7 @@ __global__ void img_up2_lerp_kernel(const float* __restrict__ small, const float
 // gsmall[h,w] = scale * sum over the hi-res pixels that read (h,w) of their tap weight * g
 __global__ void img_up2_bwd_kernel(const float* __restrict__ g, float* __restrict__ gsmall, int P, int H, int W,
                                    float scale) {
+  pdl_prologue();
   const int Ho = 2 * H, Wo = 2 * W;
   const size_t total = (size_t)P * H * W;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -387,6 +401,7 @@ __global__ void img_up2_bwd_kernel(const float* __restrict__ g, float* __restric
 
 // sums[j] = sum over n, hw of g[n,j,hw]   (toRGB bias gradient);   planes laid out (B,3,HW)
 __global__ void plane_sums_kernel(const float* __restrict__ g, float* __restrict__ sums, int B, int HW) {
+  pdl_prologue();
   __shared__ float red[32];
   const int j = blockIdx.y;
   float s = 0.f;
@@ -410,6 +425,7 @@ __global__ void plane_sums_kernel(const float* __restrict__ g, float* __restrict
 // ---------------------------------------------------------------------------------------------
 __global__ void nhwc_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int N, int HW,
                                         int C) {
+  pdl_prologue();
   const size_t total = (size_t)N * HW * C;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -421,6 +437,7 @@ __global__ void nhwc_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x, flo
 // out[n,hw,c] = g[n,c,hw] * gate(gate_src[n,hw,c])
 __global__ void nchw_f32_to_nhwc_kernel(const float* __restrict__ g, const __nv_bfloat16* __restrict__ gate_src,
                                         __nv_bfloat16* __restrict__ out, int N, int HW, int C, float slope) {
+  pdl_prologue();
   const size_t total = (size_t)N * HW * C;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -443,6 +460,7 @@ __global__ void nchw_f32_to_nhwc_kernel(const float* __restrict__ g, const __nv_
 // mode 1: sdot[m] += sum_j (sum_g d_g * ddot_g) / (G * sig_m[j]) / J          (tangent; v = x-dot)
 __global__ void mbstd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ v,
                                     float* __restrict__ out, int B, int G, int J, float eps, int mode) {
+  pdl_prologue();
   extern __shared__ float part[];
   const int M = B / G;
   for (int i = threadIdx.x; i < M; i += blockDim.x) part[i] = 0.f;
@@ -476,6 +494,7 @@ __global__ void mbstd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const _
 // xpad[n][hw][0..C) = x;  xpad[n][hw][C] = plane[n mod M];  xpad[n][hw][C+1..Cpad) = 0
 __global__ void mbstd_pad_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ plane,
                                  __nv_bfloat16* __restrict__ xpad, int B, int HW, int C, int Cpad, int M) {
+  pdl_prologue();
   const size_t total = (size_t)B * HW * Cpad;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % Cpad);
@@ -492,6 +511,7 @@ __global__ void mbstd_pad_kernel(const __nv_bfloat16* __restrict__ x, const floa
 // gs[m] = sum over n == m (mod M), hw of gpad[n][hw][C]      (gradient reaching the stddev plane)
 __global__ void mbstd_plane_grad_kernel(const __nv_bfloat16* __restrict__ gpad, float* __restrict__ gs, int B, int HW,
                                         int C, int Cpad, int M) {
+  pdl_prologue();
   const int m = blockIdx.x;
   float s = 0.f;
   for (int i = threadIdx.x; i < (B / M) * HW; i += blockDim.x) {
@@ -517,6 +537,7 @@ __global__ void mbstd_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv
                                  const __nv_bfloat16* __restrict__ gpad, const float* __restrict__ gs,
                                  const float* __restrict__ gs2, __nv_bfloat16* __restrict__ gx, int B, int G, int HW,
                                  int C, int Cpad, float eps) {
+  pdl_prologue();
   const int J = HW * C;
   const int M = B / G;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -583,6 +604,7 @@ __global__ void mbstd_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv
 // ---------------------------------------------------------------------------------------------
 __global__ void logistic_loss_kernel(const float* __restrict__ pred, int n, float sign, float* __restrict__ loss,
                                      float* __restrict__ seed, float seed_scale) {
+  pdl_prologue();
   __shared__ float red[32];
   float s = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -603,6 +625,7 @@ __global__ void logistic_loss_kernel(const float* __restrict__ pred, int n, floa
 
 // out[0] += scale * sum x^2
 __global__ void sumsq_kernel(const float* __restrict__ x, size_t n, float scale, float* __restrict__ out) {
+  pdl_prologue();
   __shared__ float red[32];
   float s = 0.f;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -636,7 +659,7 @@ int launch_linear_fwd(const float* x, const float* W, const float* bias, float* 
   const long warps = (long)N * ((M + kLinMT - 1) / kLinMT);
   const int block = 256;
   const long blocks = (warps * 32 + block - 1) / block;
-  linear_fwd_kernel<<<(unsigned)blocks, block, 0, s>>>(x, W, bias, y, M, N, K, coef, act, slope);
+  BG_CHECK_CUDA(launch_pdl(linear_fwd_kernel, (unsigned)blocks, block, 0, s, x, W, bias, y, M, N, K, coef, act, slope));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -645,87 +668,87 @@ int launch_linear_bwd_weight(const float* gy, const float* x, float* dW, float* 
                              int accumulate, cudaStream_t s) {
   BG_REQUIRE(M > 0 && N > 0 && K > 0 && K % 4 == 0, "linear_bwd_weight: bad shape M %d N %d K %d", M, N, K);
   dim3 grid((K / 4 + 127) / 128, (N + kLbwNT - 1) / kLbwNT);
-  linear_bwd_weight_kernel<<<grid, 128, 0, s>>>(gy, x, dW, db, M, N, K, coef, accumulate);
+  BG_CHECK_CUDA(launch_pdl(linear_bwd_weight_kernel, grid, 128, 0, s, gy, x, dW, db, M, N, K, coef, accumulate));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_transpose_f32(const float* in, float* out, int R, int C, cudaStream_t s) {
   dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
-  transpose_kernel<<<grid, block, 0, s>>>(in, out, R, C);
+  BG_CHECK_CUDA(launch_pdl(transpose_kernel, grid, block, 0, s, in, out, R, C));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_act_gate_f32(const float* g, const float* y, float* out, size_t n, float slope, cudaStream_t s) {
-  act_gate_f32_kernel<<<grid1d(n), 256, 0, s>>>(g, y, out, n, slope);
+  BG_CHECK_CUDA(launch_pdl(act_gate_f32_kernel, grid1d(n), 256, 0, s, g, y, out, n, slope));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_axpby_f32(const float* a, const float* b, float* out, size_t n, float ca, float cb, cudaStream_t s) {
-  axpby_f32_kernel<<<grid1d(n), 256, 0, s>>>(a, b, out, n, ca, cb);
+  BG_CHECK_CUDA(launch_pdl(axpby_f32_kernel, grid1d(n), 256, 0, s, a, b, out, n, ca, cb));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_const_noise_act(const float* cst, const float* noise, const float* nw, void* a, int N, int HW, int C,
                            float slope, cudaStream_t s) {
-  const_noise_act_kernel<<<grid1d((size_t)N * HW * C), 256, 0, s>>>(cst, noise, nw, (__nv_bfloat16*)a, N, HW, C, slope);
+  BG_CHECK_CUDA(launch_pdl(const_noise_act_kernel, grid1d((size_t)N * HW * C), 256, 0, s, cst, noise, nw, (__nv_bfloat16*)a, N, HW, C, slope));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_const_bwd(const void* g, float* dconst, int N, int HW, int C, cudaStream_t s) {
-  const_bwd_kernel<<<(HW * C + 255) / 256, 256, 0, s>>>((const __nv_bfloat16*)g, dconst, N, HW, C);
+  BG_CHECK_CUDA(launch_pdl(const_bwd_kernel, (HW * C + 255) / 256, 256, 0, s, (const __nv_bfloat16*)g, dconst, N, HW, C));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_img_avgpool2(const float* img, float* out, int P, int Ho, int Wo, cudaStream_t s) {
-  img_avgpool2_kernel<<<grid1d((size_t)P * Ho * Wo), 256, 0, s>>>(img, out, P, Ho, Wo);
+  BG_CHECK_CUDA(launch_pdl(img_avgpool2_kernel, grid1d((size_t)P * Ho * Wo), 256, 0, s, img, out, P, Ho, Wo));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_img_avgpool2_bwd(const float* g, float* gimg, int P, int Ho, int Wo, float scale, int accumulate,
                             cudaStream_t s) {
-  img_avgpool2_bwd_kernel<<<grid1d((size_t)P * Ho * Wo * 4), 256, 0, s>>>(g, gimg, P, Ho, Wo, scale, accumulate);
+  BG_CHECK_CUDA(launch_pdl(img_avgpool2_bwd_kernel, grid1d((size_t)P * Ho * Wo * 4), 256, 0, s, g, gimg, P, Ho, Wo, scale, accumulate));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_img_up2_lerp(const float* small, const float* large, float* out, int P, int H, int W, float alpha,
                         cudaStream_t s) {
-  img_up2_lerp_kernel<<<grid1d((size_t)P * H * W * 4), 256, 0, s>>>(small, large, out, P, H, W, alpha);
+  BG_CHECK_CUDA(launch_pdl(img_up2_lerp_kernel, grid1d((size_t)P * H * W * 4), 256, 0, s, small, large, out, P, H, W, alpha));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_img_up2_bwd(const float* g, float* gsmall, int P, int H, int W, float scale, cudaStream_t s) {
-  img_up2_bwd_kernel<<<grid1d((size_t)P * H * W), 256, 0, s>>>(g, gsmall, P, H, W, scale);
+  BG_CHECK_CUDA(launch_pdl(img_up2_bwd_kernel, grid1d((size_t)P * H * W), 256, 0, s, g, gsmall, P, H, W, scale));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_plane_sums(const float* g, float* sums, int B, int HW, cudaStream_t s) {
-  BG_CHECK_CUDA(cudaMemsetAsync(sums, 0, 3 * sizeof(float), s));
+  if (launch_zero(sums, 3 * sizeof(float), s) != 0) return 1;
   int bx = grid1d((size_t)B * HW, 256, 2);
-  plane_sums_kernel<<<dim3(bx, 3), 256, 0, s>>>(g, sums, B, HW);
+  BG_CHECK_CUDA(launch_pdl(plane_sums_kernel, dim3(bx, 3), 256, 0, s, g, sums, B, HW));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_nhwc_to_nchw_f32(const void* x, float* out, int N, int HW, int C, cudaStream_t s) {
-  nhwc_to_nchw_f32_kernel<<<grid1d((size_t)N * HW * C), 256, 0, s>>>((const __nv_bfloat16*)x, out, N, HW, C);
+  BG_CHECK_CUDA(launch_pdl(nhwc_to_nchw_f32_kernel, grid1d((size_t)N * HW * C), 256, 0, s, (const __nv_bfloat16*)x, out, N, HW, C));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_nchw_f32_to_nhwc(const float* g, const void* gate_src, void* out, int N, int HW, int C, float slope,
                             cudaStream_t s) {
-  nchw_f32_to_nhwc_kernel<<<grid1d((size_t)N * HW * C), 256, 0, s>>>(g, (const __nv_bfloat16*)gate_src,
-                                                                    (__nv_bfloat16*)out, N, HW, C, slope);
+  BG_CHECK_CUDA(launch_pdl(nchw_f32_to_nhwc_kernel, grid1d((size_t)N * HW * C), 256, 0, s, g, (const __nv_bfloat16*)gate_src,
+                                                                    (__nv_bfloat16*)out, N, HW, C, slope));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -735,14 +758,14 @@ int launch_mbstd_fwd(const void* x, const void* v, float* plane, void* xpad, int
   BG_REQUIRE(G > 0 && B % G == 0, "mbstd: batch %d is not a multiple of the group size %d", B, G);
   BG_REQUIRE(Cpad > C, "mbstd: Cpad %d must exceed C %d", Cpad, C);
   const int M = B / G, J = HW * C;
-  BG_CHECK_CUDA(cudaMemsetAsync(plane, 0, M * sizeof(float), s));
+  if (launch_zero(plane, M * sizeof(float), s) != 0) return 1;
   const void* src = v ? v : x;
-  mbstd_reduce_kernel<<<(J + 127) / 128, 128, M * sizeof(float), s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)v,
-                                                                     plane, B, G, J, eps, v ? 1 : 0);
+  BG_CHECK_CUDA(launch_pdl(mbstd_reduce_kernel, (J + 127) / 128, 128, M * sizeof(float), s, (const __nv_bfloat16*)x, (const __nv_bfloat16*)v,
+                                                                     plane, B, G, J, eps, v ? 1 : 0));
   BG_CHECK_CUDA(cudaGetLastError());
   if (xpad != nullptr) {
-    mbstd_pad_kernel<<<grid1d((size_t)B * HW * Cpad), 256, 0, s>>>((const __nv_bfloat16*)src, plane,
-                                                                  (__nv_bfloat16*)xpad, B, HW, C, Cpad, M);
+    BG_CHECK_CUDA(launch_pdl(mbstd_pad_kernel, grid1d((size_t)B * HW * Cpad), 256, 0, s, (const __nv_bfloat16*)src, plane,
+                                                                  (__nv_bfloat16*)xpad, B, HW, C, Cpad, M));
     BG_CHECK_CUDA(cudaGetLastError());
   }
   return 0;
@@ -757,17 +780,17 @@ int launch_mbstd_bwd(const void* x, const void* v, const void* gpad, const void*
   float* gs2 = nullptr;
   if (gpad != nullptr) {
     gs = gs_ws;
-    mbstd_plane_grad_kernel<<<M, 128, 0, s>>>((const __nv_bfloat16*)gpad, gs, B, HW, C, Cpad, M);
+    BG_CHECK_CUDA(launch_pdl(mbstd_plane_grad_kernel, M, 128, 0, s, (const __nv_bfloat16*)gpad, gs, B, HW, C, Cpad, M));
     BG_CHECK_CUDA(cudaGetLastError());
   }
   if (gpad2 != nullptr) {
     gs2 = gs_ws + M;
-    mbstd_plane_grad_kernel<<<M, 128, 0, s>>>((const __nv_bfloat16*)gpad2, gs2, B, HW, C, Cpad, M);
+    BG_CHECK_CUDA(launch_pdl(mbstd_plane_grad_kernel, M, 128, 0, s, (const __nv_bfloat16*)gpad2, gs2, B, HW, C, Cpad, M));
     BG_CHECK_CUDA(cudaGetLastError());
   }
-  mbstd_bwd_kernel<<<(J + 127) / 128, 128, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)v,
+  BG_CHECK_CUDA(launch_pdl(mbstd_bwd_kernel, (J + 127) / 128, 128, 0, s, (const __nv_bfloat16*)x, (const __nv_bfloat16*)v,
                                                   (const __nv_bfloat16*)gpad, gs, gs2, (__nv_bfloat16*)gx, B, G, HW, C,
-                                                  Cpad, eps);
+                                                  Cpad, eps));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -775,14 +798,14 @@ int launch_mbstd_bwd(const void* x, const void* v, const void* gpad, const void*
 int launch_logistic_loss(const float* pred, int n, float sign, float* loss, float* seed, float seed_scale,
                          cudaStream_t s) {
   BG_REQUIRE(n > 0, "logistic_loss: empty prediction vector");
-  logistic_loss_kernel<<<1, 256, 0, s>>>(pred, n, sign, loss, seed, seed_scale);
+  BG_CHECK_CUDA(launch_pdl(logistic_loss_kernel, 1, 256, 0, s, pred, n, sign, loss, seed, seed_scale));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_sumsq(const float* x, size_t n, float scale, float* out, cudaStream_t s) {
-  BG_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), s));
-  sumsq_kernel<<<grid1d(n, 256, 2), 256, 0, s>>>(x, n, scale, out);
+  if (launch_zero(out, sizeof(float), s) != 0) return 1;
+  BG_CHECK_CUDA(launch_pdl(sumsq_kernel, grid1d(n, 256, 2), 256, 0, s, x, n, scale, out));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -813,13 +836,13 @@ int launch_linear_grouped(int mode, const float* x, const float* const* W, const
   }
   G.blk0[groups] = blocks;
   if (mode == 0) {
-    linear_fwd_grouped_kernel<<<blocks, 256, 0, s>>>(x, G, M, K, act, slope);
+    BG_CHECK_CUDA(launch_pdl(linear_fwd_grouped_kernel, blocks, 256, 0, s, x, G, M, K, act, slope));
   } else if (mode == 1) {
-    linear_bwd_weight_grouped_kernel<<<blocks, 128, 0, s>>>(x, G, M, K);
+    BG_CHECK_CUDA(launch_pdl(linear_bwd_weight_grouped_kernel, blocks, 128, 0, s, x, G, M, K));
   } else {
     BG_REQUIRE(gx != nullptr, "linear_grouped: gx is required for the input gradient");
     const long warps = (long)K * mgroups;
-    linear_bwd_input_grouped_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, s>>>(G, gx, M, K);
+    BG_CHECK_CUDA(launch_pdl(linear_bwd_input_grouped_kernel, (unsigned)((warps * 32 + 255) / 256), 256, 0, s, G, gx, M, K));
   }
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;

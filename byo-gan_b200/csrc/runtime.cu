@@ -4,6 +4,7 @@
 #include "common.cuh"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace bg {
@@ -35,6 +36,47 @@ int num_sms() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("BG_PDL");
+    on = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
+
+__global__ void zero_kernel(uint4* __restrict__ p16, size_t n16, uint32_t* __restrict__ tail, int ntail) {
+  pdl_prologue();
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) p16[i] = z;
+  if (blockIdx.x == 0 && (int)threadIdx.x < ntail) tail[threadIdx.x] = 0u;
+}
+
+int launch_zero(void* ptr, size_t bytes, cudaStream_t stream) {
+  if (bytes == 0) return 0;
+  if ((bytes & 3) != 0 || (reinterpret_cast<uintptr_t>(ptr) & 3) != 0) {      // not word sized: plain memset node
+    BG_CHECK_CUDA(cudaMemsetAsync(ptr, 0, bytes, stream));
+    return 0;
+  }
+  // head words up to 16-byte alignment go with the tail (at most 3 + 3 words)
+  uint8_t* b = static_cast<uint8_t*>(ptr);
+  const size_t head = (16 - (reinterpret_cast<uintptr_t>(b) & 15)) & 15;
+  if (head > 0 && head <= bytes) {
+    BG_CHECK_CUDA(cudaMemsetAsync(b, 0, head, stream));                         // never taken for torch allocations
+    b += head;
+    bytes -= head;
+  }
+  const size_t n16 = bytes / 16;
+  const int ntail = (int)((bytes - n16 * 16) / 4);
+  size_t blocks = (n16 + 255) / 256;
+  const size_t cap = (size_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks == 0) blocks = 1;
+  BG_CHECK_CUDA(launch_pdl(zero_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, reinterpret_cast<uint4*>(b), n16,
+                           reinterpret_cast<uint32_t*>(b + n16 * 16), ntail));
+  return 0;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
