@@ -12,14 +12,15 @@ constexpr int kBlock = 256;
 struct F8 {
   float v[8];
 };
-__device__ __forceinline__ F8 ld8(const __nv_bfloat16* p) {
-  const uint4 u = *reinterpret_cast<const uint4*>(p);
+__device__ __forceinline__ uint4 ld_raw8(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ F8 unpack8(const uint4 u) {
   F8 r;
   float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
   r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y;
   r.v[4] = c.x; r.v[5] = c.y; r.v[6] = d.x; r.v[7] = d.y;
   return r;
 }
+__device__ __forceinline__ F8 ld8(const __nv_bfloat16* p) { return unpack8(ld_raw8(p)); }
 __device__ __forceinline__ void st8(__nv_bfloat16* p, const F8& r) {
   uint4 u;
   u.x = pack_bf16x2(r.v[0], r.v[1]);
@@ -344,26 +345,40 @@ __global__ void pool_act_bwd_kernel(const __nv_bfloat16* __restrict__ gy, const 
 __global__ void upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N,
                                       int H, int W, int C, Div32 dcv, Div32 dw, Div32 dh) {
   pdl_prologue();
+  // one thread per (source pixel, 8 channels): the clamped 3 x 3 source window gives the 2 x 2 output quad, 9 loads
+  // for 4 stores (a thread per output pixel would load 16)
   const int cv = C / 8;
-  const int Ho = 2 * H, Wo = 2 * W;
-  const size_t total = (size_t)N * Ho * Wo * cv;
+  const int Wo = 2 * W;
+  const size_t total = (size_t)N * H * W * cv;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     uint32_t cg, uw, uh;
-    const uint32_t po = divmod((uint32_t)i, dcv, cg);
-    const uint32_t n = divmod(divmod(po, dw, uw), dh, uh);
-    const int c = (int)cg * 8, wo = (int)uw, ho = (int)uh;
-    // source rows: ho even -> (h-1: .25, h: .75); ho odd -> (h: .75, h+1: .25)
-    const int h = ho >> 1, w = wo >> 1;
-    const int h2 = (ho & 1) ? min(h + 1, H - 1) : max(h - 1, 0);
-    const int w2 = (wo & 1) ? min(w + 1, W - 1) : max(w - 1, 0);
+    const uint32_t p = divmod((uint32_t)i, dcv, cg);
+    const uint32_t n = divmod(divmod(p, dw, uw), dh, uh);
+    const int c = (int)cg * 8, w = (int)uw, h = (int)uh;
+    const int hs[3] = {max(h - 1, 0), h, min(h + 1, H - 1)};
+    const int ws[3] = {max(w - 1, 0), w, min(w + 1, W - 1)};
     const __nv_bfloat16* xb = x + (size_t)n * H * W * C + c;
-    const F8 a = ld8(xb + ((size_t)h * W + w) * C), b = ld8(xb + ((size_t)h * W + w2) * C),
-             d = ld8(xb + ((size_t)h2 * W + w) * C), e = ld8(xb + ((size_t)h2 * W + w2) * C);
-    F8 r;
+    uint4 raw[3][3];
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      r.v[j] = 0.5625f * a.v[j] + 0.1875f * (b.v[j] + d.v[j]) + 0.0625f * e.v[j];
-    st8(y + (size_t)po * C + c, r);
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) raw[r][q] = ld_raw8(xb + ((size_t)hs[r] * W + ws[q]) * C);
+    const F8 a = unpack8(raw[1][1]);
+    __nv_bfloat16* yb = y + (((size_t)n * 2 * H + 2 * h) * Wo + 2 * w) * C + c;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      // output row 2h + dy: even rows lean on h-1, odd rows on h+1 (taps .75 / .25, edge clamp)
+      const F8 d = unpack8(raw[2 * dy][1]);
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const F8 b = unpack8(raw[1][2 * dx]), e = unpack8(raw[2 * dy][2 * dx]);
+        F8 r;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          r.v[j] = 0.5625f * a.v[j] + 0.1875f * (b.v[j] + d.v[j]) + 0.0625f * e.v[j];
+        st8(yb + ((size_t)dy * Wo + dx) * C, r);
+      }
+    }
   }
 }
 
@@ -393,23 +408,29 @@ __global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ gy, __nv
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc.v[j] = 0.f;
     const __nv_bfloat16* gb = gy + (size_t)n * Ho * Wo * C + c;
-    float wsv[4];
+    // the 4 x 4 window of hi-res gradients that read (h, w); out-of-range rows / columns are clamped onto a window
+    // member and given weight 0, so all 16 loads are unconditional and in flight together
+    float wsv[4], wrv[4];
+    int cx[4], ry[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int sx = 2 * w - 1 + q;
+      const int sx = 2 * w - 1 + q, r = 2 * h - 1 + q;
       wsv[q] = (sx >= 0 && sx < Wo) ? up_weight(sx, w, W) : 0.f;
+      wrv[q] = (r >= 0 && r < Ho) ? up_weight(r, h, H) : 0.f;
+      cx[q] = min(max(sx, 0), Wo - 1);
+      ry[q] = min(max(r, 0), Ho - 1);
     }
+    uint4 raw[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) raw[q][t] = ld_raw8(gb + ((size_t)ry[q] * Wo + cx[t]) * C);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int r = 2 * h - 1 + q;
-      if (r < 0 || r >= Ho) continue;
-      const float wr = up_weight(r, h, H);
-      if (wr == 0.f) continue;
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        const float ws = wsv[t] * wr;
-        if (ws == 0.f) continue;
-        const F8 g = ld8(gb + ((size_t)r * Wo + (2 * w - 1 + t)) * C);
+        const float ws = wsv[t] * wrv[q];
+        const F8 g = unpack8(raw[q][t]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc.v[j] += ws * g.v[j];
       }
@@ -444,7 +465,38 @@ __global__ void channel_wsum_kernel(const __nv_bfloat16* __restrict__ g, const f
   if (tr < rows) {
     // HW is a power of two for every map of the model: the plane index costs a shift and a mask instead of two 64-bit
     // divisions per pixel (hw_shift < 0: general fallback)
-    for (size_t p = p0 + tr; p < p1; p += rows) {
+    constexpr int kU = 4;              // pixels per trip, loads issued ahead of the arithmetic
+    size_t p = p0 + tr;
+    for (; p + (size_t)(kU - 1) * rows < p1; p += (size_t)kU * rows) {
+      uint4 raw[kU];
+      float s[kU][3];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) raw[u] = ld_raw8(g + (p + (size_t)u * rows) * C + tc * 8);
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        s[u][0] = s[u][1] = s[u][2] = 0.f;
+        if (nplanes > 0) {
+          const size_t pu = p + (size_t)u * rows;
+          const size_t b = hw_shift >= 0 ? (pu >> hw_shift) * img_stride + (pu & (size_t)(HW - 1))
+                                         : (pu / HW) * img_stride + (pu % HW);
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+            if (j < nplanes) s[u][j] = planes[b + j * plane_stride];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const F8 v = unpack8(raw[u]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[0][j] += v.v[j];
+          acc[1][j] += v.v[j] * s[u][0];
+          acc[2][j] += v.v[j] * s[u][1];
+          acc[3][j] += v.v[j] * s[u][2];
+        }
+      }
+    }
+    for (; p < p1; p += rows) {
       const F8 v = ld8(g + p * C + tc * 8);
       float s[3] = {0.f, 0.f, 0.f};
       if (nplanes > 0) {
@@ -522,6 +574,65 @@ __global__ void planes3_to_nhwc_kernel(const float* __restrict__ img, const floa
       for (int j = 0; j < 8; ++j) r.v[j] *= gt.v[j] > 0.f ? 1.f : slope;
     }
     st8(out + (size_t)p * C + c, r);
+  }
+}
+
+// Same map, four consecutive pixels of one sample and 8 channels per thread: three 16-byte plane loads, the 24
+// weights + 8 biases of the channel group held in registers across the four pixels (HW % 4 == 0, img 16-byte aligned).
+__global__ void planes3_to_nhwc_quad_kernel(const float* __restrict__ img, const float* __restrict__ Wm,
+                                            const float* __restrict__ bias, const __nv_bfloat16* __restrict__ gate_src,
+                                            __nv_bfloat16* __restrict__ out, size_t P, int HW, int C, int ws_c, int ws_j,
+                                            float coef, int act, float slope, Div32 dcv, Div32 dq) {
+  pdl_prologue();
+  extern __shared__ float sw[];  // [C][3] + [C]
+  for (int i = threadIdx.x; i < C * 3; i += blockDim.x) {
+    const int c = i / 3, j = i % 3;
+    sw[i] = Wm[(size_t)c * ws_c + (size_t)j * ws_j] * coef;
+  }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sw[C * 3 + i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const int cv = C / 8;
+  const size_t total = (P / 4) * cv;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t cg, qi;
+    const uint32_t q = divmod((uint32_t)i, dcv, cg);          // pixel quad
+    const uint32_t n = divmod(q, dq, qi);                      // dq = HW / 4 quads per sample
+    const int c = (int)cg * 8;
+    const size_t b = (size_t)n * (size_t)(3 * HW) + (size_t)qi * 4;
+    const float4 p0 = *reinterpret_cast<const float4*>(img + b);
+    const float4 p1 = *reinterpret_cast<const float4*>(img + b + HW);
+    const float4 p2 = *reinterpret_cast<const float4*>(img + b + 2 * (size_t)HW);
+    const size_t pix = (size_t)q * 4;
+    uint4 graw[4];
+    if (gate_src != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) graw[k] = ld_raw8(gate_src + (pix + k) * C + c);
+    }
+    float w0[8], w1[8], w2[8], bb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      w0[j] = sw[(c + j) * 3];
+      w1[j] = sw[(c + j) * 3 + 1];
+      w2[j] = sw[(c + j) * 3 + 2];
+      bb[j] = sw[C * 3 + c + j];
+    }
+    const float i0[4] = {p0.x, p0.y, p0.z, p0.w}, i1[4] = {p1.x, p1.y, p1.z, p1.w}, i2[4] = {p2.x, p2.y, p2.z, p2.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      F8 r;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = i0[k] * w0[j] + i1[k] * w1[j] + i2[k] * w2[j] + bb[j];
+        if (act) v = v > 0.f ? v : v * slope;
+        r.v[j] = v;
+      }
+      if (gate_src != nullptr) {
+        const F8 gt = unpack8(graw[k]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r.v[j] *= gt.v[j] > 0.f ? 1.f : slope;
+      }
+      st8(out + (pix + k) * C + c, r);
+    }
   }
 }
 
@@ -610,9 +721,40 @@ __global__ void in_reduce_kernel(const __nv_bfloat16* __restrict__ a, const __nv
   const int p0 = chunk * pix_per_block;
   const int p1 = min(p0 + pix_per_block, HW);
   if (tr < rows) {
-    for (int p = p0 + tr; p < p1; p += rows) {
-      const size_t off = ((size_t)n * HW + p) * C + tc * 8;
-      const F8 av = ld8(a + off);
+    // four pixels per trip, all loads issued ahead of the arithmetic (the kernel is a pure HBM stream)
+    constexpr int kU = 4;
+    const __nv_bfloat16* ab = a + (size_t)n * HW * C + tc * 8;
+    const __nv_bfloat16* gb = mode == 0 ? ab : g + (size_t)n * HW * C + tc * 8;
+    int p = p0 + tr;
+    for (; p + (kU - 1) * rows < p1; p += kU * rows) {
+      uint4 ra[kU], rg[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) ra[u] = ld_raw8(ab + (size_t)(p + u * rows) * C);
+      if (mode != 0) {
+#pragma unroll
+        for (int u = 0; u < kU; ++u) rg[u] = ld_raw8(gb + (size_t)(p + u * rows) * C);
+      }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        const F8 av = unpack8(ra[u]);
+        if (mode == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            s1[j] += av.v[j];
+            s2[j] += av.v[j] * av.v[j];
+          }
+        } else {
+          const F8 gv = unpack8(rg[u]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            s1[j] += gv.v[j];
+            s2[j] += gv.v[j] * (av.v[j] - mean[j]) * rstd[j];
+          }
+        }
+      }
+    }
+    for (; p < p1; p += rows) {
+      const F8 av = ld8(ab + (size_t)p * C);
       if (mode == 0) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -620,7 +762,7 @@ __global__ void in_reduce_kernel(const __nv_bfloat16* __restrict__ a, const __nv
           s2[j] += av.v[j] * av.v[j];
         }
       } else {
-        const F8 gv = ld8(g + off);
+        const F8 gv = ld8(gb + (size_t)p * C);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           s1[j] += gv.v[j];
@@ -666,7 +808,21 @@ __global__ void adain_apply_kernel(const __nv_bfloat16* __restrict__ a, const fl
   const __nv_bfloat16* ab = a + (size_t)n * HW * C + c;
   __nv_bfloat16* xb = x + (size_t)n * HW * C + c;
   const int rows = blockDim.x / cv;
-  for (int p = blockIdx.x * rows + threadIdx.x / cv; p < HW; p += gridDim.x * rows) {
+  const int step = gridDim.x * rows;
+  int p = blockIdx.x * rows + threadIdx.x / cv;
+  for (; p + 3 * step < HW; p += 4 * step) {            // four independent 16-byte loads in flight per thread
+    uint4 raw[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) raw[u] = ld_raw8(ab + (size_t)(p + u * step) * C);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      F8 v = unpack8(raw[u]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v.v[j] = fmaf(v.v[j], sc[j], sh[j]);
+      st8(xb + (size_t)(p + u * step) * C, v);
+    }
+  }
+  for (; p < HW; p += step) {
     F8 v = ld8(ab + (size_t)p * C);
 #pragma unroll
     for (int j = 0; j < 8; ++j) v.v[j] = fmaf(v.v[j], sc[j], sh[j]);
@@ -707,10 +863,37 @@ __global__ void adain_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, cons
   for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
   const size_t base = (size_t)n * HW * C + c;
   const int rows = blockDim.x / cv;
-  for (int p = blockIdx.x * rows + threadIdx.x / cv; p < HW; p += gridDim.x * rows) {
+  const int step = gridDim.x * rows;
+  const bool want_nz = wsum != nullptr && noise != nullptr;
+  int p = blockIdx.x * rows + threadIdx.x / cv;
+  for (; p + step < HW; p += 2 * step) {                 // two pixels per trip: four 16-byte loads in flight
+    uint4 ra[2], rg[2];
+    float nz[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      ra[u] = ld_raw8(a + base + (size_t)(p + u * step) * C);
+      rg[u] = ld_raw8(g + base + (size_t)(p + u * step) * C);
+      nz[u] = want_nz ? noise[(size_t)n * HW + p + u * step] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const F8 av = unpack8(ra[u]), gv = unpack8(rg[u]);
+      F8 r;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = k1[j] * (gv.v[j] - k2[j] - (av.v[j] - mu[j]) * k3[j]);
+        if (gate) v *= av.v[j] > 0.f ? 1.f : slope;
+        r.v[j] = v;
+        acc[0][j] += v;
+        acc[1][j] = fmaf(v, nz[u], acc[1][j]);
+      }
+      st8(out + base + (size_t)(p + u * step) * C, r);
+    }
+  }
+  for (; p < HW; p += step) {
     const F8 av = ld8(a + base + (size_t)p * C);
     const F8 gv = ld8(g + base + (size_t)p * C);
-    const float nz = (wsum != nullptr && noise != nullptr) ? noise[(size_t)n * HW + p] : 0.f;
+    const float nz = want_nz ? noise[(size_t)n * HW + p] : 0.f;
     F8 r;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -930,10 +1113,10 @@ int launch_pool_act_bwd(const void* gy, const void* y, void* gu, int N, int Ho, 
 
 int launch_upsample2x_fwd(const void* x, void* y, int N, int H, int W, int C, cudaStream_t s) {
   BG_REQUIRE(C % 8 == 0, "upsample2x_fwd: C must be a multiple of 8");
-  const size_t total = (size_t)N * H * W * 4 * (C / 8);
+  const size_t total = (size_t)N * H * W * (C / 8);
   BG_REQUIRE(total < (1ull << 32), "upsample2x_fwd: map too large");
   BG_CHECK_CUDA(launch_pdl(upsample2x_fwd_kernel, grid_for(total), kBlock, 0, s, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C,
-                                                          make_div(C / 8), make_div(2 * W), make_div(2 * H)));
+                           make_div(C / 8), make_div(W), make_div(H)));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -977,6 +1160,12 @@ int launch_planes3_to_nhwc(const float* img, const float* Wm, const float* bias,
                            size_t P, int HW, int C, int ws_c, int ws_j, float coef, int act, float slope,
                            cudaStream_t s) {
   BG_REQUIRE(C % 8 == 0 && C <= 1024, "planes3_to_nhwc: unsupported C %d", C);
+  if (HW % 4 == 0 && P % 4 == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0 && P / 4 * (C / 8) < (1ull << 32)) {
+    BG_CHECK_CUDA(launch_pdl(planes3_to_nhwc_quad_kernel, grid_for(P / 4 * (C / 8)), kBlock, (size_t)C * 4 * sizeof(float), s,
+                             img, Wm, bias, (const __nv_bfloat16*)gate_src, (__nv_bfloat16*)out, P, HW, C, ws_c, ws_j, coef,
+                             act, slope, make_div(C / 8), make_div(HW / 4)));
+    return 0;
+  }
   const size_t total = P * (C / 8);
   BG_CHECK_CUDA(launch_pdl(planes3_to_nhwc_kernel, grid_for(total), kBlock, (size_t)C * 4 * sizeof(float), s, 
       img, Wm, bias, (const __nv_bfloat16*)gate_src, (__nv_bfloat16*)out, P, HW, C, ws_c, ws_j, coef, act, slope,

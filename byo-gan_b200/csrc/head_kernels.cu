@@ -450,6 +450,66 @@ __global__ void nchw_f32_to_nhwc_kernel(const float* __restrict__ g, const __nv_
 }
 
 // ---------------------------------------------------------------------------------------------
+// y = act(coef * x W^T + b) for the two skinny shapes of the critic's 4x4 -> 1x1 convolution (K = 8192 forward, N = 8192
+// input gradient), where one warp per output column re-reads the same 8 rows of x once per column (0.5 GB of L2 traffic
+// for a 17 MB weight).  Here a block owns kLinNT columns x kLinMT rows; its KS warps split K, every x vector loaded is
+// used for kLinNT columns, and the partial sums meet in shared memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int kLinNT = 4;
+
+template <int KS>
+__global__ void __launch_bounds__(32 * KS) linear_fwd_tile_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                                                  const float* __restrict__ bias, float* __restrict__ y,
+                                                                  int M, int N, int K, float coef, int act, float slope) {
+  pdl_prologue();
+  __shared__ float part[KS][kLinMT * kLinNT];
+  const int lane = threadIdx.x & 31, kw = threadIdx.x >> 5;
+  const int ntiles = (N + kLinNT - 1) / kLinNT;
+  const int n0 = ((int)blockIdx.x % ntiles) * kLinNT;
+  const int m0 = ((int)blockIdx.x / ntiles) * kLinMT;
+  float acc[kLinMT][kLinNT];
+#pragma unroll
+  for (int i = 0; i < kLinMT; ++i)
+#pragma unroll
+    for (int c = 0; c < kLinNT; ++c) acc[i][c] = 0.f;
+  const int kspan = ((K / 4 + KS - 1) / KS) * 4;          // K % 4 == 0 (launcher)
+  const int k_lo = kw * kspan, k_hi = min(K, k_lo + kspan);
+  for (int k = k_lo + lane * 4; k < k_hi; k += 128) {
+    float4 wv[kLinNT], xv[kLinMT];
+#pragma unroll
+    for (int c = 0; c < kLinNT; ++c)
+      wv[c] = *reinterpret_cast<const float4*>(W + (size_t)min(n0 + c, N - 1) * K + k);
+#pragma unroll
+    for (int i = 0; i < kLinMT; ++i)
+      xv[i] = *reinterpret_cast<const float4*>(x + (size_t)min(m0 + i, M - 1) * K + k);
+#pragma unroll
+    for (int i = 0; i < kLinMT; ++i)
+#pragma unroll
+      for (int c = 0; c < kLinNT; ++c)
+        acc[i][c] += xv[i].x * wv[c].x + xv[i].y * wv[c].y + xv[i].z * wv[c].z + xv[i].w * wv[c].w;
+  }
+#pragma unroll
+  for (int i = 0; i < kLinMT; ++i)
+#pragma unroll
+    for (int c = 0; c < kLinNT; ++c) {
+      const float v = warp_sum(acc[i][c]);
+      if (lane == 0) part[kw][i * kLinNT + c] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < kLinMT * kLinNT) {
+    const int i = threadIdx.x / kLinNT, c = threadIdx.x % kLinNT;
+    if (m0 + i < M && n0 + c < N) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < KS; ++w) v += part[w][threadIdx.x];
+      v = v * coef + (bias ? bias[n0 + c] : 0.f);
+      if (act) v = lrelu_f(v, slope);
+      y[(size_t)(m0 + i) * N + n0 + c] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // MiniBatchStdDev (gan.py:273-298).  x: (B,HW,C) bf16, J = HW*C positions, G groups, M = B/G slots.
 //   mu[j] = mean_n x[n][j];  d = x - mu;  var_m[j] = mean_g d[g*M+m][j]^2;  sig = sqrt(var + eps)
 //   s[m] = mean_j sig_m[j];  sample n gets plane value s[n mod M].
@@ -466,26 +526,29 @@ __global__ void mbstd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const _
   for (int i = threadIdx.x; i < M; i += blockDim.x) part[i] = 0.f;
   __syncthreads();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < J) {
-    float mu = 0.f, mud = 0.f;
-    for (int n = 0; n < B; ++n) {
-      mu += __bfloat162float(x[(size_t)n * J + j]);
-      if (mode == 1) mud += __bfloat162float(v[(size_t)n * J + j]);
+  const bool active = j < J;
+  const int jj = active ? j : J - 1;                      // idle lanes still take part in the warp sums
+  float mu = 0.f, mud = 0.f;
+#pragma unroll 8
+  for (int n = 0; n < B; ++n) {                            // batch loads are independent: keep 8 in flight
+    mu += __bfloat162float(x[(size_t)n * J + jj]);
+    if (mode == 1) mud += __bfloat162float(v[(size_t)n * J + jj]);
+  }
+  mu /= B;
+  mud /= B;
+  for (int m = 0; m < M; ++m) {
+    float sq = 0.f, dd = 0.f;
+#pragma unroll 4
+    for (int g = 0; g < G; ++g) {
+      const size_t off = (size_t)(g * M + m) * J + jj;
+      const float d = __bfloat162float(x[off]) - mu;
+      sq += d * d;
+      if (mode == 1) dd += d * (__bfloat162float(v[off]) - mud);
     }
-    mu /= B;
-    mud /= B;
-    for (int m = 0; m < M; ++m) {
-      float sq = 0.f, dd = 0.f;
-      for (int g = 0; g < G; ++g) {
-        const size_t off = (size_t)(g * M + m) * J + j;
-        const float d = __bfloat162float(x[off]) - mu;
-        sq += d * d;
-        if (mode == 1) dd += d * (__bfloat162float(v[off]) - mud);
-      }
-      const float sig = sqrtf(sq / G + eps);
-      const float val = mode == 0 ? sig : dd / (G * sig);
-      atomicAdd(&part[m], val);
-    }
+    const float sig = sqrtf(sq / G + eps);
+    float val = mode == 0 ? sig : dd / (G * sig);
+    val = warp_sum(active ? val : 0.f);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&part[m], val);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < M; i += blockDim.x) atomicAdd(out + i, part[i] / J);
@@ -544,6 +607,7 @@ __global__ void mbstd_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv
   if (j >= J) return;
   const int c = j % C, hw = j / C;
   float mu = 0.f, mud = 0.f;
+#pragma unroll 8
   for (int n = 0; n < B; ++n) {
     mu += __bfloat162float(x[(size_t)n * J + j]);
     if (v != nullptr) mud += __bfloat162float(v[(size_t)n * J + j]);
@@ -554,6 +618,7 @@ __global__ void mbstd_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv
   float rmean = 0.f;
   for (int m = 0; m < M; ++m) {
     float sq = 0.f, A = 0.f, sd = 0.f, sdd = 0.f;
+#pragma unroll 4
     for (int g = 0; g < G; ++g) {
       const size_t off = (size_t)(g * M + m) * J + j;
       const float d = __bfloat162float(x[off]) - mu;
@@ -575,6 +640,7 @@ __global__ void mbstd_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv
   const float scale = 1.f / ((float)J * G);
   for (int m = 0; m < M; ++m) {
     float sq = 0.f, A = 0.f;
+#pragma unroll 4
     for (int g = 0; g < G; ++g) {
       const size_t off = (size_t)(g * M + m) * J + j;
       const float d = __bfloat162float(x[off]) - mu;
@@ -656,7 +722,19 @@ inline int grid1d(size_t work, int block = 256, int cap_mult = 8) {
 int launch_linear_fwd(const float* x, const float* W, const float* bias, float* y, int M, int N, int K, float coef,
                       int act, float slope, cudaStream_t s) {
   BG_REQUIRE(M > 0 && N > 0 && K > 0, "linear_fwd: bad shape M %d N %d K %d", M, N, K);
-  const long warps = (long)N * ((M + kLinMT - 1) / kLinMT);
+  const int mgroups = (M + kLinMT - 1) / kLinMT;
+  if (K % 4 == 0 && (K >= 2048 || N >= 4096) && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(W) & 15) == 0) {
+    const unsigned tiles = (unsigned)(((N + kLinNT - 1) / kLinNT) * mgroups);
+    if (K >= 4096)
+      BG_CHECK_CUDA(launch_pdl(linear_fwd_tile_kernel<8>, tiles, 256, 0, s, x, W, bias, y, M, N, K, coef, act, slope));
+    else if (K >= 2048)
+      BG_CHECK_CUDA(launch_pdl(linear_fwd_tile_kernel<4>, tiles, 128, 0, s, x, W, bias, y, M, N, K, coef, act, slope));
+    else
+      BG_CHECK_CUDA(launch_pdl(linear_fwd_tile_kernel<1>, tiles, 32, 0, s, x, W, bias, y, M, N, K, coef, act, slope));
+    return 0;
+  }
+  const long warps = (long)N * mgroups;
   const int block = 256;
   const long blocks = (warps * 32 + block - 1) / block;
   BG_CHECK_CUDA(launch_pdl(linear_fwd_kernel, (unsigned)blocks, block, 0, s, x, W, bias, y, M, N, K, coef, act, slope));

@@ -19,7 +19,8 @@ def rel(a, b):
     return ((a.double() - b.double()).norm() / (b.double().norm() + 1e-30)).item()
 
 
-@pytest.mark.parametrize("m,n,k", [(16, 512, 512), (5, 1024, 512), (32, 512, 8192), (7, 1, 512), (9, 512, 1), (33, 32, 512)])
+@pytest.mark.parametrize("m,n,k", [(16, 512, 512), (5, 1024, 512), (32, 512, 8192), (7, 1, 512), (9, 512, 1), (33, 32, 512),
+                                   (32, 8192, 512), (5, 4098, 512), (3, 6, 2048), (11, 13, 4100)])
 def test_linear_fwd_and_bwd(m, n, k):
     torch.manual_seed(0)
     x = torch.randn(m, k, device=DEV)
