@@ -55,6 +55,16 @@ __device__ __forceinline__ uint32_t divmod(uint32_t x, const Div32& k, uint32_t&
   return q;
 }
 
+// Blocks of `kernel` that are resident on the whole device at once: the reductions below give every block an equal share
+// of the pixels, so a grid of exactly this many blocks is a single wave with no tail (a grid a few blocks larger costs a
+// whole extra wave: 608 blocks on 592 slots ran in twice the time of 592).
+template <typename K>
+inline int resident_blocks(K kernel, int threads, size_t smem) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem) != cudaSuccess || occ < 1) occ = 1;
+  return occ * num_sms();
+}
+
 inline int grid_for(size_t work, int cap_mult = 8) {
   size_t blocks = (work + kBlock - 1) / kBlock;
   size_t cap = (size_t)num_sms() * cap_mult;
@@ -445,7 +455,7 @@ __global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ gy, __nv
 // plane_j[p] = planes[(p / HW) * img_stride + j * plane_stride + (p % HW)]  (fp32)
 // Serves: bias grads, noise-weight grads (gan.py:52), fromRGB / toRGB weight grads.
 // ---------------------------------------------------------------------------------------------
-__global__ void channel_wsum_kernel(const __nv_bfloat16* __restrict__ g, const float* __restrict__ planes,
+__global__ void __launch_bounds__(256, 3) channel_wsum_kernel(const __nv_bfloat16* __restrict__ g, const float* __restrict__ planes,
                                     float* __restrict__ out, size_t P, int C, int HW, size_t img_stride,
                                     size_t plane_stride, int nplanes, int pix_per_block, int hw_shift) {
   pdl_prologue();
@@ -694,7 +704,7 @@ __global__ void nhwc_to_planes3_kernel(const __nv_bfloat16* __restrict__ x, cons
 // ---------------------------------------------------------------------------------------------
 // sums[n][c][0] += sum_hw a (* b if b given);  sums[n][c][1] += sum_hw a*a   (mode 0: statistics)
 // mode 1 (backward): sums[n][c][0] += sum g, sums[n][c][1] += sum g * ahat, ahat = (a - mean) * rstd
-__global__ void in_reduce_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ g,
+__global__ void __launch_bounds__(256, 3) in_reduce_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ g,
                                  const float* __restrict__ stats, float* __restrict__ sums, int HW, int C,
                                  int pix_per_block, int blocks_per_img, float eps, int mode) {
   pdl_prologue();
@@ -835,7 +845,7 @@ __global__ void adain_apply_kernel(const __nv_bfloat16* __restrict__ a, const fl
 // wsum[1][c] += sum gpre * noise[n,hw] (InjectSecondaryNoise weight gradient, gan.py:52).
 // grid = (blocks per sample, N), fixed (sample, channel group) per thread: with k1 = gamma*rstd, k2 = S1/HW,
 // k3 = rstd*S2/HW the inner loop is  v = k1 * (g - k2 - (a - m) * k3)  on registers.
-__global__ void adain_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ a,
+__global__ void __launch_bounds__(256, 3) adain_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ a,
                                        const float* __restrict__ stats, const float* __restrict__ style,
                                        const float* __restrict__ bsums, __nv_bfloat16* __restrict__ out, int N,
                                        int HW, int C, float eps, float slope, int gate,
@@ -1140,11 +1150,17 @@ int launch_channel_wsum(const void* g, const float* planes, float* out, size_t P
   const int rows = threads / cv;
   if (launch_zero(out, (size_t)(1 + nplanes) * C * sizeof(float), s) != 0) return 1;
   // enough blocks to fill the chip, but at least `rows * 8` pixels each
-  size_t ppb = (P + (size_t)num_sms() * 4 - 1) / ((size_t)num_sms() * 4);
-  if (ppb < (size_t)rows * 8) ppb = (size_t)rows * 8;
-  const size_t blocks = (P + ppb - 1) / ppb;
   const size_t smem = (size_t)rows * 4 * C * sizeof(float);
   BG_REQUIRE(smem <= 48 * 1024, "channel_wsum: shared memory %zu too large", smem);
+  static int cap_cache[2] = {0, 0};
+  if (cap_cache[1] == 0 || cap_cache[0] != (int)smem) {
+    cap_cache[1] = resident_blocks(channel_wsum_kernel, threads, smem);
+    cap_cache[0] = (int)smem;
+  }
+  const size_t cap = (size_t)cap_cache[1];                  // one resident wave, equal shares
+  size_t ppb = (P + cap - 1) / cap;
+  if (ppb < (size_t)rows * 8) ppb = (size_t)rows * 8;
+  const size_t blocks = (P + ppb - 1) / ppb;
   int hw_shift = -1;
   if (HW > 0 && (HW & (HW - 1)) == 0) {
     hw_shift = 0;
@@ -1193,14 +1209,19 @@ static int in_reduce_launch(const void* a, const void* g, const float* stats, fl
   const int threads = cv >= 256 ? cv : 256;
   const int rows = threads / cv;
   if (launch_zero(sums, (size_t)N * C * 2 * sizeof(float), s) != 0) return 1;
-  int blocks_per_img = (num_sms() * 4 + N - 1) / N;
+  const size_t smem = (size_t)rows * 2 * C * sizeof(float);
+  BG_REQUIRE(smem <= 48 * 1024, "in_reduce: shared memory %zu too large", smem);
+  static int cap_cache[2] = {0, 0};                         // [0] = smem bytes the capacity was computed for
+  if (cap_cache[1] == 0 || cap_cache[0] != (int)smem) {
+    cap_cache[1] = resident_blocks(in_reduce_kernel, threads, smem);
+    cap_cache[0] = (int)smem;
+  }
+  int blocks_per_img = cap_cache[1] / N;                    // floor: the grid never exceeds one resident wave
   int max_bpi = (HW + rows * 4 - 1) / (rows * 4);
   if (blocks_per_img > max_bpi) blocks_per_img = max_bpi;
   if (blocks_per_img < 1) blocks_per_img = 1;
   const int ppb = (HW + blocks_per_img - 1) / blocks_per_img;
   blocks_per_img = (HW + ppb - 1) / ppb;
-  const size_t smem = (size_t)rows * 2 * C * sizeof(float);
-  BG_REQUIRE(smem <= 48 * 1024, "in_reduce: shared memory %zu too large", smem);
   BG_CHECK_CUDA(launch_pdl(in_reduce_kernel, N * blocks_per_img, threads, smem, s, (const __nv_bfloat16*)a, (const __nv_bfloat16*)g, stats,
                                                             sums, HW, C, ppb, blocks_per_img, eps, mode));
   BG_CHECK_CUDA(cudaGetLastError());
