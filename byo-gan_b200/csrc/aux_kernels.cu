@@ -845,7 +845,7 @@ __global__ void adain_apply_kernel(const __nv_bfloat16* __restrict__ a, const fl
 // wsum[1][c] += sum gpre * noise[n,hw] (InjectSecondaryNoise weight gradient, gan.py:52).
 // grid = (blocks per sample, N), fixed (sample, channel group) per thread: with k1 = gamma*rstd, k2 = S1/HW,
 // k3 = rstd*S2/HW the inner loop is  v = k1 * (g - k2 - (a - m) * k3)  on registers.
-__global__ void __launch_bounds__(256, 3) adain_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ a,
+__global__ void adain_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ a,
                                        const float* __restrict__ stats, const float* __restrict__ style,
                                        const float* __restrict__ bsums, __nv_bfloat16* __restrict__ out, int N,
                                        int HW, int C, float eps, float slope, int gate,

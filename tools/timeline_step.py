@@ -48,6 +48,13 @@ for s, e, _ in ev:
         busy += e - cur_end
         cur_end = e
 span = t1 - t0
+# the long gaps, with the activities either side (where the device waited for the host)
+cur_end, prev_name = ev[0][0], ""
+for s, e, nme in ev:
+    if s - cur_end >= 20:
+        print(f"gap {s - cur_end:7.1f} us at +{(s - t0) / 1e3:8.3f} ms   after {prev_name[:70]!r}   before {nme[:70]!r}")
+    if e > cur_end:
+        cur_end, prev_name = e, nme
 print(f"{workload} batch {batch}: {iters} iterations, {len(ev)} device activities, span {span / iters / 1e3:.3f} ms/iter, "
       f"busy {busy / iters / 1e3:.3f} ms/iter, idle {(span - busy) / iters / 1e3:.3f} ms/iter in {len(gaps) // iters} gaps/iter")
 hist = collections.Counter()
