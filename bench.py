@@ -160,6 +160,8 @@ class Trainer:
         self.steps, self.alpha, self.batch, self.device = steps, alpha, batch, device
         self.sync = sync_cls()
         self.critic._grad_ready_hook = self.sync.ready
+        if self.sync.enabled:                                 # single process: plain autograd accumulation
+            self.gen._grad_ready_hook = self.sync.ready
 
     style_mixing = False
 
@@ -428,6 +430,18 @@ def run_b200(args):
                 "step_share_by_call": shares,
                 "step_model_flops_frac": round(value / world * gflop_img * 1e9 / (peaks["tf_sustained"] * 1e12), 4)}
 
+    # replicas must still hold identical parameters after all those averaged updates (outside every timed region)
+    replica_diff = None
+    if world > 1:
+        with torch.no_grad():
+            mine = torch.cat([p.detach().reshape(-1) for m in (tr.gen, tr.critic) for p in m.parameters()])
+            ref0 = mine.clone()
+            torch.distributed.broadcast(ref0, 0)
+            d = (mine - ref0).abs().max().reshape(1)
+            torch.distributed.all_reduce(d, op=torch.distributed.ReduceOp.MAX)
+            replica_diff = float(d)
+            del mine, ref0
+
     sampling = None
     if rank == 0 and world == 1 and not args.no_sampling:
         del tr.critic
@@ -461,6 +475,7 @@ def run_b200(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "sampling_512": sampling,
+            "replicas_max_abs_param_diff": replica_diff,
             "grad_allreduce_bytes_per_step": tr.sync.bytes_reduced // max(1, args.steps * 2 + args.warmup + 2) if world > 1 else 0,
         }
         emit(line)

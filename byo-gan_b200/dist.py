@@ -63,6 +63,7 @@ class GradSync:
         self._pending_bytes = 0
         self._inflight = []
         self._scale_later: List[torch.nn.Parameter] = []
+        self._seen = set()
         self.bytes_reduced = 0
         # NCCL averages inside the collective; gloo (CPU tests) has no AVG: sum, then scale in finish()
         self._avg_op = dist.ReduceOp.SUM
@@ -71,10 +72,14 @@ class GradSync:
 
     def begin(self):
         self._pending, self._pending_bytes, self._inflight, self._scale_later = [], 0, [], []
+        self._seen = set()
 
     def ready(self, p: torch.nn.Parameter):
         if not self.enabled or p.grad is None:
             return
+        if id(p) in self._seen:        # already queued in this step (layer hook first, ready_all() sweep afterwards)
+            return
+        self._seen.add(id(p))
         if p.grad.numel() * p.grad.element_size() >= LARGE_BYTES and p.grad.is_contiguous():
             # big conv / FC gradients (>= 4 MB; they are ~90 % of the payload) are averaged IN PLACE, each as its own
             # collective: no flatten copy, no scatter-back copy, no separate division pass

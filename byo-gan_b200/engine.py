@@ -408,13 +408,16 @@ def generator_forward(gen, packs: PackCache, z, noise, steps, alpha, z2=None, cr
     return img, tape
 
 
-def generator_backward(gen, packs: PackCache, tape, g_img, need: Dict[int, bool], need_z=True, need_z2=False):
+def generator_backward(gen, packs: PackCache, tape, g_img, need: Dict[int, bool], need_z=True, need_z2=False,
+                       emit=None):
     """Backward of generator_forward.  `need[id(param)]` says which parameter gradients to produce.
+    emit(id(param), grad): called the moment a parameter's TOTAL gradient has been queued (synthesis layers one by
+    one, the mapping network at the end because both latents of a style-mixing pass accumulate into it).
     Returns (grads {id(param): tensor}, dz, dz2)."""
     dev = g_img.device
     steps, fade, B = tape["steps"], tape["fade"], tape["B"]
     layers, maps = tape["layers"], tape["maps"]
-    grads: Dict[int, torch.Tensor] = {}
+    grads: Dict[int, torch.Tensor] = {} if emit is None else _EmitDict(emit)
     g_img = g_img.detach().float().contiguous()
     R = 4 << (steps - 1)
     C = GEN_CHANNELS[steps - 1][1]
@@ -526,6 +529,7 @@ def generator_backward(gen, packs: PackCache, tape, g_img, need: Dict[int, bool]
 
     # mapping network backward (gan.py:130-148)
     dzs = [None, None]
+    mgrads: Dict[int, torch.Tensor] = {}          # both latents accumulate here; handed over (emitted) when complete
     for which, hs in enumerate(maps):
         g = g_w[which]
         if g is None:
@@ -535,15 +539,17 @@ def generator_backward(gen, packs: PackCache, tape, g_img, need: Dict[int, bool]
             lin = gen.to_w_noise[0].layers[i][0]
             gp = gate_f32(g, hs[i + 1])
             if want(lin.weight) or want(lin.bias):
-                acc = id(lin.weight) in grads
-                dw, db = linear_bwd_weight(gp, hs[i], lin.weight, into=grads.get(id(lin.weight)),
-                                           into_b=grads.get(id(lin.bias)))
+                acc = id(lin.weight) in mgrads
+                dw, db = linear_bwd_weight(gp, hs[i], lin.weight, into=mgrads.get(id(lin.weight)),
+                                           into_b=mgrads.get(id(lin.bias)))
                 if not acc:
-                    grads[id(lin.weight)] = dw
-                    grads[id(lin.bias)] = db
+                    mgrads[id(lin.weight)] = dw
+                    mgrads[id(lin.bias)] = db
             if i > 0 or need_in:
                 g = linear_bwd_input(gp, lin.weight, packs)
         dzs[which] = g if need_in else None
+    for key, val in mgrads.items():
+        grads[key] = val
     return grads, dzs[0], dzs[1]
 
 

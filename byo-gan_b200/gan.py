@@ -159,9 +159,28 @@ class _GeneratorFn(torch.autograd.Function):
         if g_img is None:
             return head + (None, None) + (None,) * (n_noise + len(params))
         need = {id(p): ctx.needs_input_grad[7 + n_noise + i] for i, p in enumerate(params)}
-        grads, dz, dz2 = engine.generator_backward(ctx.gen, ctx.gen._packs, ctx.tape, g_img, need,
-                                                   need_z=ctx.needs_input_grad[5], need_z2=ctx.needs_input_grad[6])
-        return head + (dz, dz2) + (None,) * n_noise + tuple(grads.get(id(p)) for p in params)
+        hook = getattr(ctx.gen, "_grad_ready_hook", None)
+        if hook is None:
+            grads, dz, dz2 = engine.generator_backward(ctx.gen, ctx.gen._packs, ctx.tape, g_img, need,
+                                                       need_z=ctx.needs_input_grad[5], need_z2=ctx.needs_input_grad[6])
+            return head + (dz, dz2) + (None,) * n_noise + tuple(grads.get(id(p)) for p in params)
+        # overlapped data-parallel path (dist.GradSync.ready as the hook): every parameter gradient goes into .grad the
+        # moment its kernels are queued and is handed to the hook, so its all-reduce runs under the rest of the backward;
+        # autograd gets None for the parameters (nothing left to accumulate)
+        by_id = {id(p): p for p in params}
+
+        def emit(key, g):
+            p = by_id[key]
+            g = g.reshape(p.shape)
+            if p.grad is None:
+                p.grad = g
+            else:
+                p.grad.add_(g)
+            hook(p)
+
+        _, dz, dz2 = engine.generator_backward(ctx.gen, ctx.gen._packs, ctx.tape, g_img, need,
+                                               need_z=ctx.needs_input_grad[5], need_z2=ctx.needs_input_grad[6], emit=emit)
+        return head + (dz, dz2) + (None,) * (n_noise + len(params))
 
 
 class _CriticFn(torch.autograd.Function):

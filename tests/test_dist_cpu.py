@@ -45,6 +45,7 @@ def _worker(rank, world, port, bucket_bytes, out):
     sync.begin()
     for p in params:
         sync.ready(p)                                  # inactive ones (grad None) must be skipped, not waited on
+    sync.ready_all(params)                             # the end-of-backward sweep must not reduce anything twice
     sync.finish()
     got = [None if p.grad is None else p.grad.clone() for p in params]
     gathered = [torch.zeros_like(flat0) for _ in range(world)]

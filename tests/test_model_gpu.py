@@ -184,3 +184,48 @@ def test_style_mixing_extension(steps, crossover):
         if ref.norm().item() > 0:
             worst = min(worst, U.cos(p.grad, ref))
     assert worst > 0.93, worst
+
+
+@pytest.mark.parametrize("steps,alpha,mix", [(5, None, False), (4, 0.4, False), (5, None, True)])
+def test_generator_layerwise_gradient_emission(steps, alpha, mix):
+    """The overlapped data-parallel path (Generator._grad_ready_hook = dist.GradSync.ready): every parameter gradient is
+    put into .grad during the backward and reported exactly once, in an order that lets its all-reduce overlap the rest;
+    the values match the ones autograd accumulates without the hook to run-to-run noise, also on a second backward that
+    accumulates into existing .grad."""
+    U.no_tf32()
+    batch = 4
+    g, _ = U.build_models(7)
+    z1 = O.make_latents(batch, 71).cuda()
+    z2 = O.make_latents(batch, 72).cuda()
+    noise = [n.cuda() for n in O.make_noise(batch, steps, 73)]
+    probe = torch.randn(batch, 3, 4 << (steps - 1), 4 << (steps - 1), device="cuda")
+    kw = dict(z2=z2, crossover=2) if mix else {}
+
+    def run(times):
+        g.zero_grad()
+        for _ in range(times):
+            (g(z1, noise=noise, steps=steps, alpha=alpha, **kw) * probe).sum().backward()
+        return {n: p.grad.clone() for n, p in g.named_parameters() if p.grad is not None}
+
+    plain1, plain2 = run(1), run(2)
+    seen = []
+    g._grad_ready_hook = lambda p: seen.append(id(p))
+    try:
+        hooked1 = run(1)
+        first = list(seen)
+        hooked2 = run(2)
+    finally:
+        del g._grad_ready_hook
+    assert set(hooked1) == set(plain1) and len(first) == len(plain1) == len(set(first)), "each gradient reported once"
+    names = {id(p): n for n, p in g.named_parameters()}
+    order = [names[i] for i in first]
+    assert order[0].startswith("to_rgbs") and order[-1].startswith("to_w_noise"), order[:2] + order[-2:]
+    # two runs of the SAME path already differ by a few percent in the deepest layers (fp32 atomics reorder the IN
+    # statistics, a bf16 rounding flips, a LeakyReLU gate follows: tests/parity_util.py); a wrong parameter mapping or
+    # a lost accumulation would be an O(1) error
+    control = run(1)
+    for ref, got, what in ((plain1, control, "control"), (plain1, hooked1, "hooked"), (plain2, hooked2, "hooked x2")):
+        for n in ref:
+            assert U.rel(got[n], ref[n]) < 0.3, (what, n, U.rel(got[n], ref[n]))
+    for n in plain1:
+        assert U.rel(hooked2[n], 2 * hooked1[n]) < 0.3, n
