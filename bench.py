@@ -360,8 +360,10 @@ def run_b200(args):
     # barrier + synchronize, max over ranks) and the MEDIAN region is reported; all regions are listed in the line.
     REPEATS = 5
     n0 = bgn.launch_count
+    bytes0 = tr.sync.bytes_reduced
     w0 = time.time()
     reps = [timed(args.steps, from_host=False) for _ in range(REPEATS)]
+    allreduce_bytes_per_step = (tr.sync.bytes_reduced - bytes0) // (REPEATS * args.steps)
     clocks.window(w0, time.time())
     launches = (bgn.launch_count - n0) // REPEATS
     clk = clocks.stop() if rank == 0 else None
@@ -476,7 +478,7 @@ def run_b200(args):
             "cpu_baseline": cpu,
             "sampling_512": sampling,
             "replicas_max_abs_param_diff": replica_diff,
-            "grad_allreduce_bytes_per_step": tr.sync.bytes_reduced // max(1, args.steps * 2 + args.warmup + 2) if world > 1 else 0,
+            "grad_allreduce_bytes_per_step": allreduce_bytes_per_step if world > 1 else 0,
         }
         emit(line)
     if world > 1:

@@ -77,7 +77,8 @@ __global__ void linear_bwd_weight_kernel(const float* __restrict__ gy, const flo
 #pragma unroll
   for (int i = 0; i < kLbwNT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
   if (k < K) {
-    for (int m = 0; m < M; ++m) {
+#pragma unroll 8
+    for (int m = 0; m < M; ++m) {                    // rows are independent loads: keep 8 in flight (M is the batch)
       const float4 xv = *reinterpret_cast<const float4*>(x + (size_t)m * K + k);
 #pragma unroll
       for (int i = 0; i < kLbwNT; ++i) {
@@ -103,6 +104,7 @@ __global__ void linear_bwd_weight_kernel(const float* __restrict__ gy, const flo
   }
   if (db != nullptr && blockIdx.x == 0 && threadIdx.x < kLbwNT && n0 + threadIdx.x < N) {
     float s = 0.f;
+#pragma unroll 8
     for (int m = 0; m < M; ++m) s += gy[(size_t)m * N + n0 + threadIdx.x];
     db[n0 + threadIdx.x] = accumulate ? db[n0 + threadIdx.x] + s : s;
   }
@@ -183,6 +185,7 @@ __global__ void linear_bwd_weight_grouped_kernel(const float* __restrict__ x, co
 #pragma unroll
   for (int i = 0; i < kLbwNT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
   if (k < K) {
+#pragma unroll 8
     for (int m = 0; m < M; ++m) {
       const float4 xv = *reinterpret_cast<const float4*>(x + (size_t)m * K + k);
 #pragma unroll
@@ -204,6 +207,7 @@ __global__ void linear_bwd_weight_grouped_kernel(const float* __restrict__ x, co
   }
   if (G.db[g] != nullptr && (local % kblocks) == 0 && threadIdx.x < kLbwNT && n0 + threadIdx.x < N) {
     float sacc = 0.f;
+#pragma unroll 8
     for (int m = 0; m < M; ++m) sacc += gy[(size_t)m * N + n0 + threadIdx.x];
     G.db[g][n0 + threadIdx.x] = sacc;
   }
@@ -723,12 +727,12 @@ int launch_linear_fwd(const float* x, const float* W, const float* bias, float* 
                       int act, float slope, cudaStream_t s) {
   BG_REQUIRE(M > 0 && N > 0 && K > 0, "linear_fwd: bad shape M %d N %d K %d", M, N, K);
   const int mgroups = (M + kLinMT - 1) / kLinMT;
-  if (K % 4 == 0 && (K >= 2048 || N >= 4096) && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+  if (K % 4 == 0 && (K >= 512 || N >= 4096) && N >= 64 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(W) & 15) == 0) {
     const unsigned tiles = (unsigned)(((N + kLinNT - 1) / kLinNT) * mgroups);
     if (K >= 4096)
       BG_CHECK_CUDA(launch_pdl(linear_fwd_tile_kernel<8>, tiles, 256, 0, s, x, W, bias, y, M, N, K, coef, act, slope));
-    else if (K >= 2048)
+    else if (K >= 512 && N < 4096)   // e.g. the mapping network's 512 x 512 layers: one 128-float slice of K per warp
       BG_CHECK_CUDA(launch_pdl(linear_fwd_tile_kernel<4>, tiles, 128, 0, s, x, W, bias, y, M, N, K, coef, act, slope));
     else
       BG_CHECK_CUDA(launch_pdl(linear_fwd_tile_kernel<1>, tiles, 32, 0, s, x, W, bias, y, M, N, K, coef, act, slope));

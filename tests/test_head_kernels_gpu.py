@@ -20,7 +20,7 @@ def rel(a, b):
 
 
 @pytest.mark.parametrize("m,n,k", [(16, 512, 512), (5, 1024, 512), (32, 512, 8192), (7, 1, 512), (9, 512, 1), (33, 32, 512),
-                                   (32, 8192, 512), (5, 4098, 512), (3, 6, 2048), (11, 13, 4100)])
+                                   (32, 8192, 512), (5, 4098, 512), (3, 6, 2048), (11, 13, 4100), (3, 70, 2048), (11, 66, 4100), (32, 512, 516)])
 def test_linear_fwd_and_bwd(m, n, k):
     torch.manual_seed(0)
     x = torch.randn(m, k, device=DEV)
