@@ -455,7 +455,8 @@ __global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ gy, __nv
 // plane_j[p] = planes[(p / HW) * img_stride + j * plane_stride + (p % HW)]  (fp32)
 // Serves: bias grads, noise-weight grads (gan.py:52), fromRGB / toRGB weight grads.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 3) channel_wsum_kernel(const __nv_bfloat16* __restrict__ g, const float* __restrict__ planes,
+__global__ void __launch_bounds__(256, 3)
+channel_wsum_kernel(const __nv_bfloat16* __restrict__ g, const float* __restrict__ planes,
                                     float* __restrict__ out, size_t P, int C, int HW, size_t img_stride,
                                     size_t plane_stride, int nplanes, int pix_per_block, int hw_shift) {
   pdl_prologue();
@@ -704,7 +705,8 @@ __global__ void nhwc_to_planes3_kernel(const __nv_bfloat16* __restrict__ x, cons
 // ---------------------------------------------------------------------------------------------
 // sums[n][c][0] += sum_hw a (* b if b given);  sums[n][c][1] += sum_hw a*a   (mode 0: statistics)
 // mode 1 (backward): sums[n][c][0] += sum g, sums[n][c][1] += sum g * ahat, ahat = (a - mean) * rstd
-__global__ void __launch_bounds__(256, 3) in_reduce_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ g,
+__global__ void __launch_bounds__(256, 3)
+in_reduce_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ g,
                                  const float* __restrict__ stats, float* __restrict__ sums, int HW, int C,
                                  int pix_per_block, int blocks_per_img, float eps, int mode) {
   pdl_prologue();
@@ -1060,33 +1062,30 @@ int launch_pack_weight(const float* w, void* wf, void* wd, int Cout, int Cin, in
   BG_REQUIRE(ks == 1 || ks == 3, "pack_weight: ks must be 1 or 3");
   BG_REQUIRE(Cin_pad >= Cin, "pack_weight: Cin_pad < Cin");
   const size_t total = (size_t)ks * ks * Cout * Cin_pad;
-  BG_CHECK_CUDA(launch_pdl(pack_weight_kernel, grid_for(total), kBlock, 0, s, w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wd, Cout, Cin, Cin_pad,
-                                                       ks, coef));
-  BG_CHECK_CUDA(cudaGetLastError());
+  BG_CHECK_CUDA(launch_pdl(pack_weight_kernel, grid_for(total), kBlock, 0, s, w, (__nv_bfloat16*)wf, (__nv_bfloat16*)wd,
+                           Cout, Cin, Cin_pad, ks, coef));
   return 0;
 }
 
 int launch_unpack_wgrad(const float* dwp, float* dw, int Cout, int Cin, int Cin_pad, int ks, float coef,
                         int accumulate, cudaStream_t s) {
   const size_t total = (size_t)ks * ks * Cout * Cin;
-  BG_CHECK_CUDA(launch_pdl(unpack_wgrad_kernel, grid_for(total), kBlock, 0, s, dwp, dw, Cout, Cin, Cin_pad, ks, coef, accumulate));
-  BG_CHECK_CUDA(cudaGetLastError());
+  BG_CHECK_CUDA(launch_pdl(unpack_wgrad_kernel, grid_for(total), kBlock, 0, s, dwp, dw, Cout, Cin, Cin_pad, ks, coef,
+                           accumulate));
   return 0;
 }
 
 int launch_act_gate(const void* g, const void* y, void* out, size_t n, float slope, cudaStream_t s) {
   BG_REQUIRE(n % 8 == 0, "act_gate: element count must be a multiple of 8");
-  BG_CHECK_CUDA(launch_pdl(act_gate_kernel, grid_for(n / 8), kBlock, 0, s, (const __nv_bfloat16*)g, (const __nv_bfloat16*)y,
-                                                    (__nv_bfloat16*)out, n / 8, slope));
-  BG_CHECK_CUDA(cudaGetLastError());
+  BG_CHECK_CUDA(launch_pdl(act_gate_kernel, grid_for(n / 8), kBlock, 0, s, (const __nv_bfloat16*)g,
+                           (const __nv_bfloat16*)y, (__nv_bfloat16*)out, n / 8, slope));
   return 0;
 }
 
 int launch_axpby(const void* a, const void* b, void* out, size_t n, float ca, float cb, cudaStream_t s) {
   BG_REQUIRE(n % 8 == 0, "axpby: element count must be a multiple of 8");
   BG_CHECK_CUDA(launch_pdl(axpby_kernel, grid_for(n / 8), kBlock, 0, s, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b,
-                                                 (__nv_bfloat16*)out, n / 8, ca, cb));
-  BG_CHECK_CUDA(cudaGetLastError());
+                           (__nv_bfloat16*)out, n / 8, ca, cb));
   return 0;
 }
 
@@ -1096,10 +1095,9 @@ int launch_pool_act_fwd(const void* u, const void* gate_src, void* y, int N, int
   BG_REQUIRE(mode == 0 || gate_src != nullptr, "pool_act_fwd: mode 1 needs gate_src");
   const size_t total = (size_t)N * Ho * Wo * (C / 8);
   BG_REQUIRE(total < (1ull << 32), "pool_act_fwd: map too large");
-  BG_CHECK_CUDA(launch_pdl(pool_act_fwd_kernel, grid_for(total), kBlock, 0, s, (const __nv_bfloat16*)u, (const __nv_bfloat16*)gate_src,
-                                                        (__nv_bfloat16*)y, N, Ho, Wo, C, slope, mode, make_div(C / 8),
-                                                        make_div(Wo), make_div(Ho)));
-  BG_CHECK_CUDA(cudaGetLastError());
+  BG_CHECK_CUDA(launch_pdl(pool_act_fwd_kernel, grid_for(total), kBlock, 0, s, (const __nv_bfloat16*)u,
+                           (const __nv_bfloat16*)gate_src, (__nv_bfloat16*)y, N, Ho, Wo, C, slope, mode, make_div(C / 8),
+                           make_div(Wo), make_div(Ho)));
   return 0;
 }
 
@@ -1114,10 +1112,9 @@ int launch_pool_act_bwd(const void* gy, const void* y, void* gu, int N, int Ho, 
     smem = (size_t)kBlock * 8 * sizeof(float);
   }
   BG_REQUIRE(total < (1ull << 32), "pool_act_bwd: map too large");
-  BG_CHECK_CUDA(launch_pdl(pool_act_bwd_kernel, grid_for(total), kBlock, smem, s, (const __nv_bfloat16*)gy, (const __nv_bfloat16*)y,
-                                                           (__nv_bfloat16*)gu, N, Ho, Wo, C, slope, csum, make_div(C / 8),
-                                                           make_div(Wo), make_div(Ho)));
-  BG_CHECK_CUDA(cudaGetLastError());
+  BG_CHECK_CUDA(launch_pdl(pool_act_bwd_kernel, grid_for(total), kBlock, smem, s, (const __nv_bfloat16*)gy,
+                           (const __nv_bfloat16*)y, (__nv_bfloat16*)gu, N, Ho, Wo, C, slope, csum, make_div(C / 8),
+                           make_div(Wo), make_div(Ho)));
   return 0;
 }
 
@@ -1125,9 +1122,8 @@ int launch_upsample2x_fwd(const void* x, void* y, int N, int H, int W, int C, cu
   BG_REQUIRE(C % 8 == 0, "upsample2x_fwd: C must be a multiple of 8");
   const size_t total = (size_t)N * H * W * (C / 8);
   BG_REQUIRE(total < (1ull << 32), "upsample2x_fwd: map too large");
-  BG_CHECK_CUDA(launch_pdl(upsample2x_fwd_kernel, grid_for(total), kBlock, 0, s, (const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C,
-                           make_div(C / 8), make_div(W), make_div(H)));
-  BG_CHECK_CUDA(cudaGetLastError());
+  BG_CHECK_CUDA(launch_pdl(upsample2x_fwd_kernel, grid_for(total), kBlock, 0, s, (const __nv_bfloat16*)x,
+                           (__nv_bfloat16*)y, N, H, W, C, make_div(C / 8), make_div(W), make_div(H)));
   return 0;
 }
 
@@ -1135,9 +1131,8 @@ int launch_upsample2x_bwd(const void* gy, void* gx, int N, int H, int W, int C, 
   BG_REQUIRE(C % 8 == 0, "upsample2x_bwd: C must be a multiple of 8");
   const size_t total = (size_t)N * H * W * (C / 8);
   BG_REQUIRE(total < (1ull << 32), "upsample2x_bwd: map too large");
-  BG_CHECK_CUDA(launch_pdl(upsample2x_bwd_kernel, grid_for(total), kBlock, 0, s, (const __nv_bfloat16*)gy, (__nv_bfloat16*)gx, N, H, W, C,
-                                                          make_div(C / 8), make_div(W), make_div(H)));
-  BG_CHECK_CUDA(cudaGetLastError());
+  BG_CHECK_CUDA(launch_pdl(upsample2x_bwd_kernel, grid_for(total), kBlock, 0, s, (const __nv_bfloat16*)gy,
+                           (__nv_bfloat16*)gx, N, H, W, C, make_div(C / 8), make_div(W), make_div(H)));
   return 0;
 }
 
@@ -1166,9 +1161,8 @@ int launch_channel_wsum(const void* g, const float* planes, float* out, size_t P
     hw_shift = 0;
     while ((1 << hw_shift) < HW) ++hw_shift;
   }
-  BG_CHECK_CUDA(launch_pdl(channel_wsum_kernel, (int)blocks, threads, smem, s, (const __nv_bfloat16*)g, planes, out, P, C, HW, img_stride,
-                                                        plane_stride, nplanes, (int)ppb, hw_shift));
-  BG_CHECK_CUDA(cudaGetLastError());
+  BG_CHECK_CUDA(launch_pdl(channel_wsum_kernel, (int)blocks, threads, smem, s, (const __nv_bfloat16*)g, planes, out, P,
+                           C, HW, img_stride, plane_stride, nplanes, (int)ppb, hw_shift));
   return 0;
 }
 
@@ -1177,16 +1171,16 @@ int launch_planes3_to_nhwc(const float* img, const float* Wm, const float* bias,
                            cudaStream_t s) {
   BG_REQUIRE(C % 8 == 0 && C <= 1024, "planes3_to_nhwc: unsupported C %d", C);
   if (HW % 4 == 0 && P % 4 == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0 && P / 4 * (C / 8) < (1ull << 32)) {
-    BG_CHECK_CUDA(launch_pdl(planes3_to_nhwc_quad_kernel, grid_for(P / 4 * (C / 8)), kBlock, (size_t)C * 4 * sizeof(float), s,
-                             img, Wm, bias, (const __nv_bfloat16*)gate_src, (__nv_bfloat16*)out, P, HW, C, ws_c, ws_j, coef,
-                             act, slope, make_div(C / 8), make_div(HW / 4)));
+    BG_CHECK_CUDA(launch_pdl(planes3_to_nhwc_quad_kernel, grid_for(P / 4 * (C / 8)), kBlock,
+                             (size_t)C * 4 * sizeof(float), s, img, Wm, bias, (const __nv_bfloat16*)gate_src,
+                             (__nv_bfloat16*)out, P, HW, C, ws_c, ws_j, coef, act, slope, make_div(C / 8),
+                             make_div(HW / 4)));
     return 0;
   }
   const size_t total = P * (C / 8);
-  BG_CHECK_CUDA(launch_pdl(planes3_to_nhwc_kernel, grid_for(total), kBlock, (size_t)C * 4 * sizeof(float), s, 
-      img, Wm, bias, (const __nv_bfloat16*)gate_src, (__nv_bfloat16*)out, P, HW, C, ws_c, ws_j, coef, act, slope,
-      make_div(C / 8), make_div(HW)));
-  BG_CHECK_CUDA(cudaGetLastError());
+  BG_CHECK_CUDA(launch_pdl(planes3_to_nhwc_kernel, grid_for(total), kBlock, (size_t)C * 4 * sizeof(float), s, img, Wm,
+                           bias, (const __nv_bfloat16*)gate_src, (__nv_bfloat16*)out, P, HW, C, ws_c, ws_j, coef, act,
+                           slope, make_div(C / 8), make_div(HW)));
   return 0;
 }
 
@@ -1196,9 +1190,8 @@ int launch_nhwc_to_planes3(const void* x, const float* Wm, const float* bias, fl
   const int cv = C / 8;
   const int lanes_per_pix = cv < 32 ? cv : 32;
   const size_t groups = (P + (32 / lanes_per_pix) - 1) / (32 / lanes_per_pix);
-  BG_CHECK_CUDA(launch_pdl(nhwc_to_planes3_kernel, grid_for(groups * 32), kBlock, (size_t)C * 3 * sizeof(float), s, 
-      (const __nv_bfloat16*)x, Wm, bias, out, P, HW, C, ws_c, ws_j, coef));
-  BG_CHECK_CUDA(cudaGetLastError());
+  BG_CHECK_CUDA(launch_pdl(nhwc_to_planes3_kernel, grid_for(groups * 32), kBlock, (size_t)C * 3 * sizeof(float), s,
+                           (const __nv_bfloat16*)x, Wm, bias, out, P, HW, C, ws_c, ws_j, coef));
   return 0;
 }
 
@@ -1222,9 +1215,8 @@ static int in_reduce_launch(const void* a, const void* g, const float* stats, fl
   if (blocks_per_img < 1) blocks_per_img = 1;
   const int ppb = (HW + blocks_per_img - 1) / blocks_per_img;
   blocks_per_img = (HW + ppb - 1) / ppb;
-  BG_CHECK_CUDA(launch_pdl(in_reduce_kernel, N * blocks_per_img, threads, smem, s, (const __nv_bfloat16*)a, (const __nv_bfloat16*)g, stats,
-                                                            sums, HW, C, ppb, blocks_per_img, eps, mode));
-  BG_CHECK_CUDA(cudaGetLastError());
+  BG_CHECK_CUDA(launch_pdl(in_reduce_kernel, N * blocks_per_img, threads, smem, s, (const __nv_bfloat16*)a,
+                           (const __nv_bfloat16*)g, stats, sums, HW, C, ppb, blocks_per_img, eps, mode));
   return 0;
 }
 
@@ -1249,9 +1241,8 @@ static int blocks_per_sample(int N, int HW, int C) {
 int launch_adain_apply(const void* a, const float* stats, const float* style, void* x, int N, int HW, int C, float eps,
                        cudaStream_t s) {
   BG_REQUIRE(C % 8 == 0 && kBlock % (C / 8) == 0, "adain_apply: C/8 must divide %d (C %d)", kBlock, C);
-  BG_CHECK_CUDA(launch_pdl(adain_apply_kernel, dim3(blocks_per_sample(N, HW, C), N), kBlock, 0, s, (const __nv_bfloat16*)a, stats, style,
-                                                                           (__nv_bfloat16*)x, N, HW, C, eps));
-  BG_CHECK_CUDA(cudaGetLastError());
+  BG_CHECK_CUDA(launch_pdl(adain_apply_kernel, dim3(blocks_per_sample(N, HW, C), N), kBlock, 0, s,
+                           (const __nv_bfloat16*)a, stats, style, (__nv_bfloat16*)x, N, HW, C, eps));
   return 0;
 }
 
@@ -1264,10 +1255,9 @@ int launch_adain_bwd_apply(const void* g, const void* a, const float* stats, con
     if (launch_zero(wsum, (size_t)2 * C * sizeof(float), s) != 0) return 1;
     smem = (size_t)kBlock * 16 * sizeof(float);
   }
-  BG_CHECK_CUDA(launch_pdl(adain_bwd_apply_kernel, dim3(blocks_per_sample(N, HW, C), N), kBlock, smem, s, 
-      (const __nv_bfloat16*)g, (const __nv_bfloat16*)a, stats, style, bsums, (__nv_bfloat16*)out, N, HW, C, eps, slope, gate,
-      noise, wsum));
-  BG_CHECK_CUDA(cudaGetLastError());
+  BG_CHECK_CUDA(launch_pdl(adain_bwd_apply_kernel, dim3(blocks_per_sample(N, HW, C), N), kBlock, smem, s,
+                           (const __nv_bfloat16*)g, (const __nv_bfloat16*)a, stats, style, bsums, (__nv_bfloat16*)out, N,
+                           HW, C, eps, slope, gate, noise, wsum));
   return 0;
 }
 
@@ -1275,9 +1265,8 @@ int launch_style_modulate(const float* W, const float* bias, const float* stats,
                           float* btab, int N, int Cin, int Cout, int HW, float coef, float eps, cudaStream_t s) {
   BG_REQUIRE(N > 0 && Cin > 0 && Cout > 0 && HW > 0, "style_modulate: bad shape N %d Cin %d Cout %d HW %d", N, Cin, Cout, HW);
   const int threads = Cin >= 256 ? 256 : (Cin >= 64 ? 64 : 32);
-  BG_CHECK_CUDA(launch_pdl(style_modulate_kernel, dim3(Cout, N), threads, 0, s, W, bias, stats, style, (__nv_bfloat16*)wmod, btab, N, Cin, Cout,
-                                                         HW, coef, eps));
-  BG_CHECK_CUDA(cudaGetLastError());
+  BG_CHECK_CUDA(launch_pdl(style_modulate_kernel, dim3(Cout, N), threads, 0, s, W, bias, stats, style,
+                           (__nv_bfloat16*)wmod, btab, N, Cin, Cout, HW, coef, eps));
   return 0;
 }
 
@@ -1290,9 +1279,8 @@ int launch_to_rgb_adain(const void* a, const float* stats, const float* style, c
   const int max_bps = (HW / ppw + 63) / 64;                 // at least ~8 pixel groups per warp
   if (bps > max_bps) bps = max_bps;
   if (bps < 1) bps = 1;
-  BG_CHECK_CUDA(launch_pdl(to_rgb_adain_kernel, dim3(bps, N), kBlock, (size_t)(3 * C + 4) * sizeof(float), s, 
-      (const __nv_bfloat16*)a, stats, style, Wm, bias, out, HW, C, coef, eps));
-  BG_CHECK_CUDA(cudaGetLastError());
+  BG_CHECK_CUDA(launch_pdl(to_rgb_adain_kernel, dim3(bps, N), kBlock, (size_t)(3 * C + 4) * sizeof(float), s,
+                           (const __nv_bfloat16*)a, stats, style, Wm, bias, out, HW, C, coef, eps));
   return 0;
 }
 
@@ -1319,27 +1307,26 @@ int launch_pack_weight_grouped(const float* const* w, void* const* wf, void* con
   }
   G.blk0[groups] = blocks;
   BG_CHECK_CUDA(launch_pdl(pack_weight_grouped_kernel, blocks, kBlock, 0, s, G));
-  BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_pack_weight_pool4(const float* w, void* w16, int Cout, int Cin, float coef, cudaStream_t s) {
   BG_REQUIRE(Cout > 0 && Cin > 0, "pack_weight_pool4: bad shape");
-  BG_CHECK_CUDA(launch_pdl(pack_weight_pool4_kernel, grid_for((size_t)16 * Cout * Cin), kBlock, 0, s, w, (__nv_bfloat16*)w16, Cout, Cin, coef));
-  BG_CHECK_CUDA(cudaGetLastError());
+  BG_CHECK_CUDA(launch_pdl(pack_weight_pool4_kernel, grid_for((size_t)16 * Cout * Cin), kBlock, 0, s, w,
+                           (__nv_bfloat16*)w16, Cout, Cin, coef));
   return 0;
 }
 
 int launch_pack_weight_tconv4(const float* w, void* wt, int Cout, int Cin, float coef, cudaStream_t s) {
   BG_REQUIRE(Cout > 0 && Cin > 0, "pack_weight_tconv4: bad shape");
-  BG_CHECK_CUDA(launch_pdl(pack_weight_tconv4_kernel, grid_for((size_t)16 * Cout * Cin), kBlock, 0, s, w, (__nv_bfloat16*)wt, Cout, Cin, coef));
-  BG_CHECK_CUDA(cudaGetLastError());
+  BG_CHECK_CUDA(launch_pdl(pack_weight_tconv4_kernel, grid_for((size_t)16 * Cout * Cin), kBlock, 0, s, w,
+                           (__nv_bfloat16*)wt, Cout, Cin, coef));
   return 0;
 }
 
 int launch_unpack_wgrad_pool4(const float* dw4, float* dw, int Cout, int Cin, float coef, int accumulate, cudaStream_t s) {
-  BG_CHECK_CUDA(launch_pdl(unpack_wgrad_pool4_kernel, grid_for((size_t)Cout * Cin * 9), kBlock, 0, s, dw4, dw, Cout, Cin, coef, accumulate));
-  BG_CHECK_CUDA(cudaGetLastError());
+  BG_CHECK_CUDA(launch_pdl(unpack_wgrad_pool4_kernel, grid_for((size_t)Cout * Cin * 9), kBlock, 0, s, dw4, dw, Cout, Cin,
+                           coef, accumulate));
   return 0;
 }
 

@@ -329,7 +329,6 @@ int launch_conv_fprop(const void* x, const void* wpack, void* out, int N, int H,
   }
   int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   BG_CHECK_CUDA(launch_pdl(conv_fprop_kernel, grid, kThreads, smem_bytes, stream, tmx, tmw, p));
-  BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 

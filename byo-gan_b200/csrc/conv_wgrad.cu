@@ -238,7 +238,6 @@ int launch_conv_wgrad(const void* x, const void* g, float* dw, int N, int H, int
   const size_t smem_bytes = (size_t)kStages * kStageBytes + 256 + 1024;
   BG_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   BG_CHECK_CUDA(launch_pdl(conv_wgrad_kernel, units * splits, kThreads, smem_bytes, stream, tmg, tmx, p));
-  BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 

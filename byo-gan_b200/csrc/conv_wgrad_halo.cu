@@ -314,7 +314,6 @@ int launch_conv_wgrad_halo(const void* x, const void* g, float* dw, int N, int H
     attr_set = true;
   }
   BG_CHECK_CUDA(launch_pdl(conv_wgrad_halo_kernel, units * splits, kThreads, smem_bytes, stream, tmg, tmx, p));
-  BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 

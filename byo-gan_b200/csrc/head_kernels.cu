@@ -742,7 +742,6 @@ int launch_linear_fwd(const float* x, const float* W, const float* bias, float* 
   const int block = 256;
   const long blocks = (warps * 32 + block - 1) / block;
   BG_CHECK_CUDA(launch_pdl(linear_fwd_kernel, (unsigned)blocks, block, 0, s, x, W, bias, y, M, N, K, coef, act, slope));
-  BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -751,65 +750,59 @@ int launch_linear_bwd_weight(const float* gy, const float* x, float* dW, float* 
   BG_REQUIRE(M > 0 && N > 0 && K > 0 && K % 4 == 0, "linear_bwd_weight: bad shape M %d N %d K %d", M, N, K);
   dim3 grid((K / 4 + 127) / 128, (N + kLbwNT - 1) / kLbwNT);
   BG_CHECK_CUDA(launch_pdl(linear_bwd_weight_kernel, grid, 128, 0, s, gy, x, dW, db, M, N, K, coef, accumulate));
-  BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_transpose_f32(const float* in, float* out, int R, int C, cudaStream_t s) {
   dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
   BG_CHECK_CUDA(launch_pdl(transpose_kernel, grid, block, 0, s, in, out, R, C));
-  BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_act_gate_f32(const float* g, const float* y, float* out, size_t n, float slope, cudaStream_t s) {
   BG_CHECK_CUDA(launch_pdl(act_gate_f32_kernel, grid1d(n), 256, 0, s, g, y, out, n, slope));
-  BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_axpby_f32(const float* a, const float* b, float* out, size_t n, float ca, float cb, cudaStream_t s) {
   BG_CHECK_CUDA(launch_pdl(axpby_f32_kernel, grid1d(n), 256, 0, s, a, b, out, n, ca, cb));
-  BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_const_noise_act(const float* cst, const float* noise, const float* nw, void* a, int N, int HW, int C,
                            float slope, cudaStream_t s) {
-  BG_CHECK_CUDA(launch_pdl(const_noise_act_kernel, grid1d((size_t)N * HW * C), 256, 0, s, cst, noise, nw, (__nv_bfloat16*)a, N, HW, C, slope));
-  BG_CHECK_CUDA(cudaGetLastError());
+  BG_CHECK_CUDA(launch_pdl(const_noise_act_kernel, grid1d((size_t)N * HW * C), 256, 0, s, cst, noise, nw,
+                           (__nv_bfloat16*)a, N, HW, C, slope));
   return 0;
 }
 
 int launch_const_bwd(const void* g, float* dconst, int N, int HW, int C, cudaStream_t s) {
-  BG_CHECK_CUDA(launch_pdl(const_bwd_kernel, (HW * C + 255) / 256, 256, 0, s, (const __nv_bfloat16*)g, dconst, N, HW, C));
-  BG_CHECK_CUDA(cudaGetLastError());
+  BG_CHECK_CUDA(launch_pdl(const_bwd_kernel, (HW * C + 255) / 256, 256, 0, s, (const __nv_bfloat16*)g, dconst, N, HW,
+                           C));
   return 0;
 }
 
 int launch_img_avgpool2(const float* img, float* out, int P, int Ho, int Wo, cudaStream_t s) {
   BG_CHECK_CUDA(launch_pdl(img_avgpool2_kernel, grid1d((size_t)P * Ho * Wo), 256, 0, s, img, out, P, Ho, Wo));
-  BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_img_avgpool2_bwd(const float* g, float* gimg, int P, int Ho, int Wo, float scale, int accumulate,
                             cudaStream_t s) {
-  BG_CHECK_CUDA(launch_pdl(img_avgpool2_bwd_kernel, grid1d((size_t)P * Ho * Wo * 4), 256, 0, s, g, gimg, P, Ho, Wo, scale, accumulate));
-  BG_CHECK_CUDA(cudaGetLastError());
+  BG_CHECK_CUDA(launch_pdl(img_avgpool2_bwd_kernel, grid1d((size_t)P * Ho * Wo * 4), 256, 0, s, g, gimg, P, Ho, Wo,
+                           scale, accumulate));
   return 0;
 }
 
 int launch_img_up2_lerp(const float* small, const float* large, float* out, int P, int H, int W, float alpha,
                         cudaStream_t s) {
-  BG_CHECK_CUDA(launch_pdl(img_up2_lerp_kernel, grid1d((size_t)P * H * W * 4), 256, 0, s, small, large, out, P, H, W, alpha));
-  BG_CHECK_CUDA(cudaGetLastError());
+  BG_CHECK_CUDA(launch_pdl(img_up2_lerp_kernel, grid1d((size_t)P * H * W * 4), 256, 0, s, small, large, out, P, H, W,
+                           alpha));
   return 0;
 }
 
 int launch_img_up2_bwd(const float* g, float* gsmall, int P, int H, int W, float scale, cudaStream_t s) {
   BG_CHECK_CUDA(launch_pdl(img_up2_bwd_kernel, grid1d((size_t)P * H * W), 256, 0, s, g, gsmall, P, H, W, scale));
-  BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -817,21 +810,19 @@ int launch_plane_sums(const float* g, float* sums, int B, int HW, cudaStream_t s
   if (launch_zero(sums, 3 * sizeof(float), s) != 0) return 1;
   int bx = grid1d((size_t)B * HW, 256, 2);
   BG_CHECK_CUDA(launch_pdl(plane_sums_kernel, dim3(bx, 3), 256, 0, s, g, sums, B, HW));
-  BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_nhwc_to_nchw_f32(const void* x, float* out, int N, int HW, int C, cudaStream_t s) {
-  BG_CHECK_CUDA(launch_pdl(nhwc_to_nchw_f32_kernel, grid1d((size_t)N * HW * C), 256, 0, s, (const __nv_bfloat16*)x, out, N, HW, C));
-  BG_CHECK_CUDA(cudaGetLastError());
+  BG_CHECK_CUDA(launch_pdl(nhwc_to_nchw_f32_kernel, grid1d((size_t)N * HW * C), 256, 0, s, (const __nv_bfloat16*)x, out,
+                           N, HW, C));
   return 0;
 }
 
 int launch_nchw_f32_to_nhwc(const float* g, const void* gate_src, void* out, int N, int HW, int C, float slope,
                             cudaStream_t s) {
-  BG_CHECK_CUDA(launch_pdl(nchw_f32_to_nhwc_kernel, grid1d((size_t)N * HW * C), 256, 0, s, g, (const __nv_bfloat16*)gate_src,
-                                                                    (__nv_bfloat16*)out, N, HW, C, slope));
-  BG_CHECK_CUDA(cudaGetLastError());
+  BG_CHECK_CUDA(launch_pdl(nchw_f32_to_nhwc_kernel, grid1d((size_t)N * HW * C), 256, 0, s, g,
+                           (const __nv_bfloat16*)gate_src, (__nv_bfloat16*)out, N, HW, C, slope));
   return 0;
 }
 
@@ -842,13 +833,11 @@ int launch_mbstd_fwd(const void* x, const void* v, float* plane, void* xpad, int
   const int M = B / G, J = HW * C;
   if (launch_zero(plane, M * sizeof(float), s) != 0) return 1;
   const void* src = v ? v : x;
-  BG_CHECK_CUDA(launch_pdl(mbstd_reduce_kernel, (J + 127) / 128, 128, M * sizeof(float), s, (const __nv_bfloat16*)x, (const __nv_bfloat16*)v,
-                                                                     plane, B, G, J, eps, v ? 1 : 0));
-  BG_CHECK_CUDA(cudaGetLastError());
+  BG_CHECK_CUDA(launch_pdl(mbstd_reduce_kernel, (J + 127) / 128, 128, M * sizeof(float), s, (const __nv_bfloat16*)x,
+                           (const __nv_bfloat16*)v, plane, B, G, J, eps, v ? 1 : 0));
   if (xpad != nullptr) {
-    BG_CHECK_CUDA(launch_pdl(mbstd_pad_kernel, grid1d((size_t)B * HW * Cpad), 256, 0, s, (const __nv_bfloat16*)src, plane,
-                                                                  (__nv_bfloat16*)xpad, B, HW, C, Cpad, M));
-    BG_CHECK_CUDA(cudaGetLastError());
+    BG_CHECK_CUDA(launch_pdl(mbstd_pad_kernel, grid1d((size_t)B * HW * Cpad), 256, 0, s, (const __nv_bfloat16*)src,
+                             plane, (__nv_bfloat16*)xpad, B, HW, C, Cpad, M));
   }
   return 0;
 }
@@ -863,17 +852,15 @@ int launch_mbstd_bwd(const void* x, const void* v, const void* gpad, const void*
   if (gpad != nullptr) {
     gs = gs_ws;
     BG_CHECK_CUDA(launch_pdl(mbstd_plane_grad_kernel, M, 128, 0, s, (const __nv_bfloat16*)gpad, gs, B, HW, C, Cpad, M));
-    BG_CHECK_CUDA(cudaGetLastError());
   }
   if (gpad2 != nullptr) {
     gs2 = gs_ws + M;
-    BG_CHECK_CUDA(launch_pdl(mbstd_plane_grad_kernel, M, 128, 0, s, (const __nv_bfloat16*)gpad2, gs2, B, HW, C, Cpad, M));
-    BG_CHECK_CUDA(cudaGetLastError());
+    BG_CHECK_CUDA(launch_pdl(mbstd_plane_grad_kernel, M, 128, 0, s, (const __nv_bfloat16*)gpad2, gs2, B, HW, C, Cpad,
+                             M));
   }
-  BG_CHECK_CUDA(launch_pdl(mbstd_bwd_kernel, (J + 127) / 128, 128, 0, s, (const __nv_bfloat16*)x, (const __nv_bfloat16*)v,
-                                                  (const __nv_bfloat16*)gpad, gs, gs2, (__nv_bfloat16*)gx, B, G, HW, C,
-                                                  Cpad, eps));
-  BG_CHECK_CUDA(cudaGetLastError());
+  BG_CHECK_CUDA(launch_pdl(mbstd_bwd_kernel, (J + 127) / 128, 128, 0, s, (const __nv_bfloat16*)x,
+                           (const __nv_bfloat16*)v, (const __nv_bfloat16*)gpad, gs, gs2, (__nv_bfloat16*)gx, B, G, HW, C,
+                           Cpad, eps));
   return 0;
 }
 
@@ -881,14 +868,12 @@ int launch_logistic_loss(const float* pred, int n, float sign, float* loss, floa
                          cudaStream_t s) {
   BG_REQUIRE(n > 0, "logistic_loss: empty prediction vector");
   BG_CHECK_CUDA(launch_pdl(logistic_loss_kernel, 1, 256, 0, s, pred, n, sign, loss, seed, seed_scale));
-  BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_sumsq(const float* x, size_t n, float scale, float* out, cudaStream_t s) {
   if (launch_zero(out, sizeof(float), s) != 0) return 1;
   BG_CHECK_CUDA(launch_pdl(sumsq_kernel, grid1d(n, 256, 2), 256, 0, s, x, n, scale, out));
-  BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -924,7 +909,8 @@ int launch_linear_grouped(int mode, const float* x, const float* const* W, const
   } else {
     BG_REQUIRE(gx != nullptr, "linear_grouped: gx is required for the input gradient");
     const long warps = (long)K * mgroups;
-    BG_CHECK_CUDA(launch_pdl(linear_bwd_input_grouped_kernel, (unsigned)((warps * 32 + 255) / 256), 256, 0, s, G, gx, M, K));
+    BG_CHECK_CUDA(launch_pdl(linear_bwd_input_grouped_kernel, (unsigned)((warps * 32 + 255) / 256), 256, 0, s, G, gx, M,
+                             K));
   }
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
