@@ -20,7 +20,8 @@
 // tile is transposed through a swizzled shared-memory stage so that every global store (and gate load) instruction
 // moves whole 128-byte lines; an optional 2x2 average pool (warp shuffles) runs before the activation.
 //
-// Warp roles: 0 = weight TMA producer, 1 = MMA issuer + TMEM allocator, 2..9 = epilogue set 0 (one 32-row TMEM
+// Warp roles: 0 = weight TMA producer, 1 = MMA issuer (first M=128 half) + TMEM allocator, 19 = MMA issuer of the second
+// half (one thread tops out at one tcgen05.mma per ~53 clk; two reach the pipe's floor), 2..9 = epilogue set 0 (one 32-row TMEM
 // quarter of one MMA half each), 10..17 = epilogue set 1 in plain mode (the epilogue of a tile is a latency chain
 // — TMEM load, math, transpose, stores — that is longer than the tile's MMAs on most layers, so two sets alternate
 // tiles, each owning one accumulator stage) or, in upsample mode, the 256 threads that build the bilinearly
@@ -37,7 +38,8 @@ constexpr int kEpiWarps = 8;                     // one epilogue SET: 4 TMEM lan
 constexpr int kEpiSets = 2;                      // plain mode: set s drains accumulator stage s (every other tile)
 constexpr int kProdWarps = 8;                    // upsample mode: these warps build the halo instead of being set 1
 constexpr int kProdThreads = 32 * kProdWarps;
-constexpr int kThreads = 32 * (2 + kEpiWarps * kEpiSets + 1);   // + warp 18: halo TMA issuer (plain mode)
+constexpr int kIssuer2 = 2 + kEpiWarps * kEpiSets + 1;         // warp 19: second MMA issuer (see HaloParams::issuers)
+constexpr int kThreads = 32 * (kIssuer2 + 1);                  // warp 18: halo TMA issuer (plain mode)
 constexpr int kTile = 16;                       // output tile edge
 constexpr int kHalo = kTile + 2;                // 18
 constexpr int kHaloPix = kHalo * kHalo;         // 324
@@ -74,6 +76,10 @@ struct HaloParams {
   int n_blocks;
   int contig;     // tile order, see tile_range()
   int epi_sets;   // 1 or 2 epilogue warp sets (2: set s drains accumulator stage s)
+  // MMA-issuing threads.  One thread cannot issue tcgen05.mma faster than one per ~53 clk, two threads reach the tensor
+  // pipe's own floor (39 clk for N <= 32, 48 clk for N = 64: tools/mma2_probe.cu); with 2, warp 1 issues the MMAs of the
+  // tile's first M=128 half and warp 19 those of the second, and every barrier the issuers commit to expects 2 arrivals.
+  int issuers;
   // StyleGAN generator forward (gan.py:89-98,118-127) with the layer's AdaIN folded into the operands:
   //   per_sample_w: the weight pack is [N][9][Cout][Cin] (instance-norm scale * style gamma folded in per sample);
   //   bias_tab:     fp32 [N][9][Cout] replaces bias: bias + the conv of the per-channel AdaIN shift, one row per border
@@ -183,7 +189,8 @@ __device__ __forceinline__ uint64_t a_tap_offset(int tap, uint32_t phase_units) 
 // serves the four taps (a, b) = (py + 2i, px + 2j), i, j in {0, 1}, whose view is the tile shifted by (i, j) pixels.
 __device__ __forceinline__ int pool4_tap(int ph, int t4) { return ((ph >> 1) + 2 * (t4 >> 1)) * 4 + (ph & 1) + 2 * (t4 & 1); }
 
-template <int KSTEPS>
+// HSEL: -1 = this thread issues both M=128 halves of the tile, 0 / 1 = only that half (two issuing warps)
+template <int KSTEPS, int HSEL>
 __device__ __forceinline__ void mma_issue_loop_pool4(const HaloParams& p, uint8_t* a_base, uint8_t* b_base,
                                                      uint64_t* b_full, uint64_t* b_empty, uint64_t* a_full,
                                                      uint64_t* a_empty, uint64_t* tmem_full, uint64_t* tmem_empty,
@@ -220,7 +227,7 @@ __device__ __forceinline__ void mma_issue_loop_pool4(const HaloParams& p, uint8_
 #pragma unroll
               for (int k = 0; k < KSTEPS; ++k) {
 #pragma unroll
-                for (int half = 0; half < 2; ++half)
+                for (int half = (HSEL < 0 ? 0 : HSEL); half < (HSEL < 0 ? 2 : HSEL + 1); ++half)
                   tc_mma_bf16(d_tmem + (uint32_t)half * 128u, a_tap + (uint64_t)(half * 8 * kRBU + k * 2),
                               b_tap + (uint64_t)(k * 2), idesc, k == 0 ? accum : 1u);
               }
@@ -248,7 +255,7 @@ __device__ __forceinline__ void mma_issue_loop_pool4(const HaloParams& p, uint8_
   }
 }
 
-template <int KSTEPS, int TAPS>
+template <int KSTEPS, int TAPS, int HSEL>
 __device__ __forceinline__ void mma_issue_loop(const HaloParams& p, uint8_t* a_base, uint8_t* b_base, uint64_t* b_full,
                                                uint64_t* b_empty, uint64_t* a_full, uint64_t* a_empty,
                                                uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base) {
@@ -306,7 +313,7 @@ __device__ __forceinline__ void mma_issue_loop(const HaloParams& p, uint8_t* a_b
 #pragma unroll
               for (int k = 0; k < KSTEPS; ++k) {
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
+                for (int half = (HSEL < 0 ? 0 : HSEL); half < (HSEL < 0 ? 2 : HSEL + 1); ++half) {
                   tc_mma_bf16(d_tmem + (uint32_t)half * 128u,
                               a_tap + (uint64_t)(half * 8 * kRBU + k * 2), b_tap + (uint64_t)(k * 2),
                               idesc, (k == 0 && tap == 0) ? accum : 1u);
@@ -328,7 +335,7 @@ __device__ __forceinline__ void mma_issue_loop(const HaloParams& p, uint8_t* a_b
 #pragma unroll
               for (int k = 0; k < KSTEPS; ++k) {
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
+                for (int half = (HSEL < 0 ? 0 : HSEL); half < (HSEL < 0 ? 2 : HSEL + 1); ++half) {
                   tc_mma_bf16(d_tmem + (uint32_t)half * 128u,
                               a_tap + (uint64_t)(half * 8 * kRBU + k * 2), b_tap + (uint64_t)(k * 2),
                               idesc, k == 0 ? accum : 1u);
@@ -356,6 +363,23 @@ __device__ __forceinline__ void mma_issue_loop(const HaloParams& p, uint8_t* a_b
     acc ^= 1;
     if (acc == 0) acc_phase ^= 1u;
   }
+}
+
+// The issue loop specialised for the launch's chunk width / tap count, for the half (or both halves) this warp owns.
+template <bool kStats, int kFeed, int HSEL>
+__device__ __forceinline__ void issue_dispatch(const HaloParams& p, uint8_t* a_base, uint8_t* b_base, uint64_t* b_full,
+                                               uint64_t* b_empty, uint64_t* a_full, uint64_t* a_empty,
+                                               uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base) {
+  if (kFeed == 0 && !kStats && p.pool4) {
+    if (p.kc == 64) mma_issue_loop_pool4<4, HSEL>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+    else mma_issue_loop_pool4<2, HSEL>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+  } else if (p.tconv4) {
+    if (p.kc == 64) mma_issue_loop<4, 4, HSEL>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+    else if (p.kc == 32) mma_issue_loop<2, 4, HSEL>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+    else mma_issue_loop<1, 4, HSEL>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+  } else if (p.kc == 64) mma_issue_loop<4, 9, HSEL>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+  else if (p.kc == 32) mma_issue_loop<2, 9, HSEL>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+  else mma_issue_loop<1, 9, HSEL>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -619,14 +643,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     tma_prefetch_desc(&tmap_x);
     for (int s = 0; s < kMaxBStages; ++s) {
       mbar_init(&b_full[s], 1);
-      mbar_init(&b_empty[s], 1);
+      mbar_init(&b_empty[s], (uint32_t)p.issuers);
     }
     for (int s = 0; s < kMaxAStages; ++s) {
       mbar_init(&a_full[s], kUp ? kProdThreads : 1);
-      mbar_init(&a_empty[s], 1);
+      mbar_init(&a_empty[s], (uint32_t)p.issuers);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_full[s], (uint32_t)p.issuers);
       mbar_init(&tmem_empty[s], kEpiWarps);
     }
     fence_barrier_init();
@@ -695,18 +719,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------ MMA issuer ------------------------------
-    if (kFeed == 0 && !kStats && p.pool4) {
-      if (p.kc == 64) mma_issue_loop_pool4<4>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
-      else mma_issue_loop_pool4<2>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
-    } else if (p.tconv4) {
-      if (p.kc == 64) mma_issue_loop<4, 4>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
-      else if (p.kc == 32) mma_issue_loop<2, 4>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
-      else mma_issue_loop<1, 4>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
-    } else if (p.kc == 64) mma_issue_loop<4, 9>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
-    else if (p.kc == 32) mma_issue_loop<2, 9>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
-    else mma_issue_loop<1, 9>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+  } else if (warp == 1 || (warp == kIssuer2 && p.issuers == 2)) {
+    // ------------------------------ MMA issuer(s) ------------------------------
+    if (p.issuers == 2) {
+      if (warp == 1) issue_dispatch<kStats, kFeed, 0>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+      else issue_dispatch<kStats, kFeed, 1>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+    } else {
+      issue_dispatch<kStats, kFeed, -1>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+    }
   } else if (warp < 2 + kEpiWarpsAll) {
     // ------------------------------ epilogue ------------------------------
     // Warp e = warp - 2: TMEM lane quarter q = warp & 3 (hardware rule), MMA half = e / 4.  Lane i holds MMA row
@@ -1073,6 +1093,11 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
   const bool planned = plan.ok;
   const uint32_t epi_bytes = plan.epi_bytes, aux_bytes = plan.aux_bytes;
   p.epi_sets = plan.sets;
+  {
+    static int issuers = 0;                                     // BG_MMA_ISSUERS=1: the single-thread issue of round-1's first kernels
+    if (issuers == 0) { const char* e = getenv("BG_MMA_ISSUERS"); issuers = (e && e[0] == '1') ? 1 : 2; }
+    p.issuers = issuers;
+  }
   p.a_stages = plan.a_stages;
   p.b_stages = plan.b_stages;
   p.b_resident = plan.resident;
