@@ -355,7 +355,7 @@ def run_b200(args):
                   f"cudaMalloc retries {st.get('num_alloc_retries', 0)} segments {st.get('segment.all.current', 0)}",
                   file=sys.stderr)
     # The GPU boxes are shared hosts: a neighbour's burst on the host cores now and then slows the Python thread that
-    # feeds ~530 launches per iteration, and one timed region in four or five comes out 10-80 % long with identical
+    # feeds ~500 C-ABI calls (~700 launches) per iteration, and one timed region in four or five comes out 10-80 % long with identical
     # clocks and allocator state.  Each leg is therefore timed REPEATS (5) times (each region = exactly K steps between
     # barrier + synchronize, max over ranks) and the MEDIAN region is reported; all regions are listed in the line.
     REPEATS = 5
