@@ -257,8 +257,10 @@ __device__ __forceinline__ float warp_sum(float v) {
 // programmatic dependent launch: every kernel of this library is launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization (launch_pdl below) so that the NEXT kernel of the stream can be
 // made resident while this one is still running; a kernel therefore (1) releases its dependents at its first
-// instruction and (2) executes pdl_wait() before its first global-memory access: everything ahead of the wait (smem
-// carve-up, mbarrier init, TMEM allocation, tensor-map prefetch) overlaps the tail of the kernel in front.
+// instruction — the TMEM-using convolution kernels only once their own TMEM columns are allocated, or a dependent CTA
+// arriving on the same SM could take the columns and then wait for this grid — and (2) executes pdl_wait() before its
+// first global-memory access: everything ahead of the wait (smem carve-up, mbarrier init, TMEM allocation, tensor-map
+// prefetch) overlaps the tail of the kernel in front.
 // ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

@@ -70,7 +70,6 @@ __device__ __forceinline__ TileCoord decode_tile(const FpropParams& p, int tile)
 __global__ void __launch_bounds__(kThreads, 1)
 conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                   const FpropParams p) {
-  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -103,6 +102,9 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   if (warp == 1) {
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
+    // only now may the next kernel of the stream become resident: released at kernel entry, a dependent CTA that landed
+    // on this SM could take the TMEM columns first and then wait for this grid, which would be waiting for the columns
+    pdl_launch_dependents();
   }
   pdl_wait();        // everything above overlaps the previous kernel's tail
   if (warp >= 2) {

@@ -608,7 +608,6 @@ template <bool kStats, int kFeed>     // kFeed: 0 TMA halo (plain and pool4), 1 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                  const HaloParams p) {
-  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -658,6 +657,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
   if (warp == 1) {
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
+    // only now may the next kernel of the stream become resident: released at kernel entry, a dependent CTA that landed
+    // on this SM could take the TMEM columns first and then wait for this grid, which would be waiting for the columns
+    pdl_launch_dependents();
   }
   pdl_wait();        // barrier init, TMEM allocation and descriptor prefetch above overlap the previous kernel's tail
   if (warp >= 2 && warp < 2 + kEpiWarpsAll) {

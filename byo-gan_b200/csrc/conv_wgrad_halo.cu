@@ -58,7 +58,6 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x,
                        const WgradHaloParams p) {
-  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -99,6 +98,9 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
   if (warp == 1) {
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
+    // only now may the next kernel of the stream become resident: released at kernel entry, a dependent CTA that landed
+    // on this SM could take the TMEM columns first and then wait for this grid, which would be waiting for the columns
+    pdl_launch_dependents();
   }
   pdl_wait();        // everything above overlaps the previous kernel's tail
   tc_fence_before();
