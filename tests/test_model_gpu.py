@@ -223,9 +223,14 @@ def test_generator_layerwise_gradient_emission(steps, alpha, mix):
     # two runs of the SAME path already differ by a few percent in the deepest layers (fp32 atomics reorder the IN
     # statistics, a bf16 rounding flips, a LeakyReLU gate follows: tests/parity_util.py); a wrong parameter mapping or
     # a lost accumulation would be an O(1) error
+    # (a lost or misrouted gradient has rel >= 1); small tensors - per-channel sums over all pixels - are the noisiest
     control = run(1)
+
+    def tol(t):
+        return 0.3 if t.numel() >= 4096 else 0.6
+
     for ref, got, what in ((plain1, control, "control"), (plain1, hooked1, "hooked"), (plain2, hooked2, "hooked x2")):
         for n in ref:
-            assert U.rel(got[n], ref[n]) < 0.3, (what, n, U.rel(got[n], ref[n]))
+            assert U.rel(got[n], ref[n]) < tol(ref[n]), (what, n, U.rel(got[n], ref[n]))
     for n in plain1:
-        assert U.rel(hooked2[n], 2 * hooked1[n]) < 0.3, n
+        assert U.rel(hooked2[n], 2 * hooked1[n]) < tol(plain1[n]), n
