@@ -12,7 +12,12 @@
  *   - feature maps are NHWC bf16 (C multiple of 16 for convolutions, 8 elsewhere);
  *     images at the module boundary are NCHW fp32 as the reference passes them;
  *   - return 0 on success, non-zero on error; bg_last_error() returns a thread-local message;
- *   - re-entrant: no global mutable state besides per-device attribute caches.
+ *   - re-entrant: no global mutable state besides per-device attribute caches;
+ *   - kernels are launched with programmatic stream serialisation: the next kernel of the stream may become
+ *     resident while this one is still running, and every kernel of the library waits (griddepcontrol.wait) for
+ *     its predecessor's completion and memory visibility before its first global access, so results are exactly
+ *     those of plain stream order.  Kernels of other libraries on the same stream are ordered as usual.
+ *     BG_PDL=0 in the environment turns the attribute off.
  */
 #ifndef BG_B200_H_
 #define BG_B200_H_
