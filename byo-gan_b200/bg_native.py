@@ -73,7 +73,11 @@ SIGNATURES = {
     "bg_mbstd_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "bg_logistic_loss": [_P, _I, _F, _P, _P, _F, _P],
     "bg_sumsq": [_P, _Z, _F, _P, _P],
+    "bg_gp_rows": [_P, _I, _Z, _F, _F, _P, _P, _P],
 }
+
+# host-side switches / predicates called directly (no stream argument, no launch)
+HOST_FUNCS = {"bg_set_deterministic": [_I], "bg_get_deterministic": []}
 
 launch_count = 0  # C-ABI calls made through this binding; each launches >= 1 kernel (bench.py: gpu_launches)
 _timing = None    # when a list: (name, args, start_event, end_event) per call, for bench.py's roofline leg
@@ -104,12 +108,19 @@ def lib():
         l = ctypes.CDLL(_LIB_PATH)
         l.bg_last_error.restype = ctypes.c_char_p
         l.bg_abi_version.restype = _I
-        for name, argtypes in SIGNATURES.items():
+        for name, argtypes in list(SIGNATURES.items()) + list(HOST_FUNCS.items()):
             fn = getattr(l, name)
             fn.argtypes = argtypes
             fn.restype = _I
         _lib = l
     return _lib
+
+
+def set_deterministic(on: bool) -> bool:
+    """Chain-deterministic reductions on/off (include/bg_b200.h: bg_set_deterministic).  Returns the previous setting."""
+    prev = bool(lib().bg_get_deterministic())
+    lib().bg_set_deterministic(1 if on else 0)
+    return prev
 
 
 _fns = {}

@@ -42,6 +42,7 @@ int launch_mbstd_bwd(const void*, const void*, const void*, const void*, float*,
                      cudaStream_t);
 int launch_logistic_loss(const float*, int, float, float*, float*, float, cudaStream_t);
 int launch_sumsq(const float*, size_t, float, float*, cudaStream_t);
+int launch_gp_rows(const float*, int, size_t, float, float, float*, float*, cudaStream_t);
 int launch_nhwc_to_planes3(const void*, const float*, const float*, float*, size_t, int, int, int, int, float,
                            cudaStream_t);
 int launch_in_stats(const void*, float*, int, int, int, cudaStream_t);
@@ -93,9 +94,17 @@ int bg_conv_fprop_stats(const void* x, const void* wpack, void* out, int N, int 
     bg::set_error("conv_fprop_stats: stats must be non-NULL and stats_mode 1 or 2 (got %d)", stats_mode);
     return 2;
   }
-  if (bg::conv_halo_supported(N, H, W, Cin, Cout, ksize))
+  if (bg::conv_halo_supported(N, H, W, Cin, Cout, ksize)) {
+    if (stats_mode == 1 && bg::deterministic()) {
+      // chain-deterministic mode: the statistics feed the next layer, so they are summed in a fixed order by the
+      // stand-alone reduction (one block per sample) instead of the epilogue's cross-CTA fp32 atomics
+      const int rc = bg::launch_conv_halo(x, wpack, out, N, H, W, Cin, Cout, bias, noise, noise_w, gate_src, act, 0,
+                                          slope, nullptr, 0, nullptr, 0, 0, S(stream));
+      return rc != 0 ? rc : bg::launch_in_stats(out, stats, N, H * W, Cout, S(stream));
+    }
     return bg::launch_conv_halo(x, wpack, out, N, H, W, Cin, Cout, bias, noise, noise_w, gate_src, act, 0, slope, stats,
                                 stats_mode, nullptr, 0, 0, S(stream));
+  }
   // small maps (< 16x16): tap-wise kernel, then the stand-alone reduction over the (tiny) output
   int rc = bg::launch_conv_fprop(x, wpack, out, N, H, W, Cin, Cout, ksize, bias, noise, noise_w, gate_src, act, slope,
                                  S(stream));
@@ -113,6 +122,11 @@ int bg_conv_style_fprop(const void* x, const void* wmod, const float* btab, void
   if (wmod == nullptr || btab == nullptr) {
     bg::set_error("conv_style_fprop: wmod and btab (from bg_style_modulate) are required");
     return 2;
+  }
+  if (stats != nullptr && bg::deterministic()) {
+    const int rc = bg::launch_conv_halo(x, wmod, out, N, H, W, Cin, Cout, nullptr, noise, noise_w, nullptr, 1, 0, slope,
+                                        nullptr, 0, btab, 1, upsample, S(stream));
+    return rc != 0 ? rc : bg::launch_in_stats(out, stats, N, H * W, Cout, S(stream));
   }
   return bg::launch_conv_halo(x, wmod, out, N, H, W, Cin, Cout, nullptr, noise, noise_w, nullptr, 1, 0, slope, stats, 1,
                               btab, 1, upsample, S(stream));
@@ -315,6 +329,9 @@ int bg_logistic_loss(const float* pred, int n, float sign, float* loss, float* s
 }
 int bg_sumsq(const float* x, size_t n, float scale, float* out, void* stream) {
   return bg::launch_sumsq(x, n, scale, out, S(stream));
+}
+int bg_gp_rows(const float* g, int B, size_t D, float pen_scale, float v_scale, float* pen, float* v, void* stream) {
+  return bg::launch_gp_rows(g, B, D, pen_scale, v_scale, pen, v, S(stream));
 }
 
 }  // extern "C"

@@ -1213,6 +1213,7 @@ static int in_reduce_launch(const void* a, const void* g, const float* stats, fl
   int max_bpi = (HW + rows * 4 - 1) / (rows * 4);
   if (blocks_per_img > max_bpi) blocks_per_img = max_bpi;
   if (blocks_per_img < 1) blocks_per_img = 1;
+  if (deterministic()) blocks_per_img = 1;                  // one contributor per (sample, channel): ordered sums only
   const int ppb = (HW + blocks_per_img - 1) / blocks_per_img;
   blocks_per_img = (HW + ppb - 1) / ppb;
   BG_CHECK_CUDA(launch_pdl(in_reduce_kernel, N * blocks_per_img, threads, smem, s, (const __nv_bfloat16*)a,

@@ -20,6 +20,7 @@ namespace bg {
 void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 int num_sms();
+bool deterministic();   // runtime.cu: chain-deterministic reductions (bg_set_deterministic)
 
 #define BG_CHECK_CUDA(expr)                                   \
   do {                                                        \

@@ -558,6 +558,43 @@ __global__ void mbstd_reduce_kernel(const __nv_bfloat16* __restrict__ x, const _
   for (int i = threadIdx.x; i < M; i += blockDim.x) atomicAdd(out + i, part[i] / J);
 }
 
+// Deterministic variant (bg_set_deterministic): block m owns slot m alone; threads stride over the positions, the block
+// total is an ordered two-stage sum (xor-butterfly inside a warp, warps in index order).
+__global__ void mbstd_reduce_det_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ v,
+                                        float* __restrict__ out, int B, int G, int J, float eps, int mode) {
+  pdl_prologue();
+  __shared__ float red[32];
+  const int M = B / G;
+  const int m = blockIdx.x;
+  float acc = 0.f;
+  for (int j = threadIdx.x; j < J; j += blockDim.x) {
+    float mu = 0.f, mud = 0.f;
+    for (int n = 0; n < B; ++n) {
+      mu += __bfloat162float(x[(size_t)n * J + j]);
+      if (mode == 1) mud += __bfloat162float(v[(size_t)n * J + j]);
+    }
+    mu /= B;
+    mud /= B;
+    float sq = 0.f, dd = 0.f;
+    for (int g = 0; g < G; ++g) {
+      const size_t off = (size_t)(g * M + m) * J + j;
+      const float d = __bfloat162float(x[off]) - mu;
+      sq += d * d;
+      if (mode == 1) dd += d * (__bfloat162float(v[off]) - mud);
+    }
+    const float sig = sqrtf(sq / G + eps);
+    acc += mode == 0 ? sig : dd / (G * sig);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    out[m] = t / J;
+  }
+}
+
 // xpad[n][hw][0..C) = x;  xpad[n][hw][C] = plane[n mod M];  xpad[n][hw][C+1..Cpad) = 0
 __global__ void mbstd_pad_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ plane,
                                  __nv_bfloat16* __restrict__ xpad, int B, int HW, int C, int Cpad, int M) {
@@ -831,10 +868,15 @@ int launch_mbstd_fwd(const void* x, const void* v, float* plane, void* xpad, int
   BG_REQUIRE(G > 0 && B % G == 0, "mbstd: batch %d is not a multiple of the group size %d", B, G);
   BG_REQUIRE(Cpad > C, "mbstd: Cpad %d must exceed C %d", Cpad, C);
   const int M = B / G, J = HW * C;
-  if (launch_zero(plane, M * sizeof(float), s) != 0) return 1;
   const void* src = v ? v : x;
-  BG_CHECK_CUDA(launch_pdl(mbstd_reduce_kernel, (J + 127) / 128, 128, M * sizeof(float), s, (const __nv_bfloat16*)x,
-                           (const __nv_bfloat16*)v, plane, B, G, J, eps, v ? 1 : 0));
+  if (deterministic()) {
+    BG_CHECK_CUDA(launch_pdl(mbstd_reduce_det_kernel, M, 256, 0, s, (const __nv_bfloat16*)x, (const __nv_bfloat16*)v, plane,
+                             B, G, J, eps, v ? 1 : 0));
+  } else {
+    if (launch_zero(plane, M * sizeof(float), s) != 0) return 1;
+    BG_CHECK_CUDA(launch_pdl(mbstd_reduce_kernel, (J + 127) / 128, 128, M * sizeof(float), s, (const __nv_bfloat16*)x,
+                             (const __nv_bfloat16*)v, plane, B, G, J, eps, v ? 1 : 0));
+  }
   if (xpad != nullptr) {
     BG_CHECK_CUDA(launch_pdl(mbstd_pad_kernel, grid1d((size_t)B * HW * Cpad), 256, 0, s, (const __nv_bfloat16*)src,
                              plane, (__nv_bfloat16*)xpad, B, HW, C, Cpad, M));
@@ -868,6 +910,40 @@ int launch_logistic_loss(const float* pred, int n, float sign, float* loss, floa
                          cudaStream_t s) {
   BG_REQUIRE(n > 0, "logistic_loss: empty prediction vector");
   BG_CHECK_CUDA(launch_pdl(logistic_loss_kernel, 1, 256, 0, s, pred, n, sign, loss, seed, seed_scale));
+  return 0;
+}
+
+// WGAN-GP rows (gan.py:385): block n owns sample n.  r = ||g_n||_2 (ordered two-stage sum: the result feeds the tangent pass);
+// pen[0] += pen_scale * (r - 1)^2;  v[n] = v_scale * 2 (r - 1) / r * g_n  (d penalty / d g_n).
+__global__ void gp_rows_kernel(const float* __restrict__ g, size_t D, float pen_scale, float v_scale,
+                               float* __restrict__ pen, float* __restrict__ v) {
+  pdl_prologue();
+  __shared__ float red[32];
+  __shared__ float coef_s;
+  const float* gn = g + (size_t)blockIdx.x * D;
+  float* vn = v + (size_t)blockIdx.x * D;
+  float s = 0.f;
+  for (size_t i = threadIdx.x; i < D; i += blockDim.x) s += gn[i] * gn[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    const float r = sqrtf(t);
+    atomicAdd(pen, pen_scale * (r - 1.f) * (r - 1.f));
+    coef_s = v_scale * 2.f * (r - 1.f) / fmaxf(r, 1e-30f);
+  }
+  __syncthreads();
+  const float coef = coef_s;
+  for (size_t i = threadIdx.x; i < D; i += blockDim.x) vn[i] = coef * gn[i];
+}
+
+int launch_gp_rows(const float* g, int B, size_t D, float pen_scale, float v_scale, float* pen, float* v,
+                   cudaStream_t s) {
+  BG_REQUIRE(B > 0 && D > 0, "gp_rows: empty input");
+  if (launch_zero(pen, sizeof(float), s) != 0) return 1;
+  BG_CHECK_CUDA(launch_pdl(gp_rows_kernel, B, 1024, 0, s, g, D, pen_scale, v_scale, pen, v));
   return 0;
 }
 

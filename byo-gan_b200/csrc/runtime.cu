@@ -47,6 +47,21 @@ bool pdl_enabled() {
   return on != 0;
 }
 
+// Chain-deterministic mode (bg_set_deterministic / BG_DETERMINISTIC=1): every reduction whose result feeds later layers
+// (instance-norm statistics, the AdaIN backward sums, the minibatch-stddev plane) is summed in a fixed order — one
+// contributing block per output, ordered two-stage sums inside it — so images, critic scores and activation gradients are
+// bit-reproducible from run to run.  Leaf sums (weight-gradient split-K partials, bias / noise-weight gradients, loss
+// terms) keep their fp32 atomics: their order noise (~1e-6 relative) ends in that tensor and is never amplified.
+static int g_deterministic = -1;
+bool deterministic() {
+  if (g_deterministic < 0) {
+    const char* e = getenv("BG_DETERMINISTIC");
+    g_deterministic = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return g_deterministic != 0;
+}
+void set_deterministic(int on) { g_deterministic = on ? 1 : 0; }
+
 __global__ void zero_kernel(uint4* __restrict__ p16, size_t n16, uint32_t* __restrict__ tail, int ntail) {
   pdl_prologue();
   const uint4 z = make_uint4(0u, 0u, 0u, 0u);
@@ -141,4 +156,9 @@ int make_tmap_bf16_strided(CUtensorMap* map, const void* base, int rank, const u
 }  // namespace bg
 
 extern "C" const char* bg_last_error(void) { return bg::last_error(); }
-extern "C" int bg_abi_version(void) { return 1; }
+extern "C" int bg_abi_version(void) { return 2; }
+extern "C" int bg_set_deterministic(int on) {
+  bg::set_deterministic(on);
+  return 0;
+}
+extern "C" int bg_get_deterministic(void) { return bg::deterministic() ? 1 : 0; }

@@ -97,6 +97,12 @@ class PackCache:
         self._conv[key] = (tag, wt, None)
         return wt
 
+    def invalidate(self):
+        """Forget every pack: the next forward re-packs from the fp32 masters.  Needed after writes that bypass the
+        version counter (p.data.mul_(...), p.data.copy_(...)); optimizer steps and load_state_dict do not need it."""
+        self._conv.clear()
+        self._lin.clear()
+
     def refresh_convs(self, items):
         """Re-pack every stale conv weight of `items` = [(weight, cin_pad or None)] in ONE grouped launch (after an
         optimizer step all of a network's packs are stale); the per-layer conv() lookups that follow then hit."""
@@ -881,59 +887,109 @@ def critic_backward(critic, packs: PackCache, tape, g_pred, need: Dict[int, bool
     return grads, g_img
 
 
-def critic_r1_step(critic, packs: PackCache, tape_fake, pred_fake, tape_real, pred_real, c_lambda, emit=None):
-    """Critic.get_r1_loss (gan.py:393-412): loss value + gradients of every active critic parameter.
+def _penalised_critic_step(critic, packs: PackCache, first_order, pen_tape, pen_seed, make_v0, emit=None):
+    """Shared schedule of the two gradient-penalty critic losses (R1: gan.py:393-412, WGAN-GP: gan.py:357-391).
 
-    loss = mean softplus(-D(real)) + mean softplus(D(fake)) + lambda/2 * mean_n ||d sum D(real) / d real_n||^2
+    first_order: [(tape, seed (B,1))] — ordinary backward passes whose parameter gradients are summed in.
+    pen_tape:    the forward whose input-gradient g_x = d sum D(x) / d x is penalised; pen_seed (B,1) is ITS first-order
+                 seed (zeros when the loss has no first-order term on that forward).
+    make_v0(g_x) -> v0: the image-space direction (d penalty / d g_x) the second-order pass is taken along.
     The double-backward autograd would run is scheduled by hand:
-      1. fake branch: ordinary backward seeded with sigmoid(D(fake))/B;
-      2. real branch: `ghat` = gated backprop of ones down to the image -> g_x, penalty, v0 = (lambda/B) g_x;
-      3. tangent forward of v0 through the critic (bias-free, saved gates);
-      4. one combined backward seeded with -sigmoid(-D(real))/B whose weight gradients contract over the
-         doubled K  [x ; v] . [ybar ; ghat]  and whose activation gradient picks up the minibatch-stddev
-         curvature term.
-    Returns (loss tensor (), grads {id(param): tensor}).
-    """
-    dev = pred_real.device
-    B = pred_real.shape[0]
-    steps, fade = tape_real["steps"], tape_real["fade"]
+      1. `ghat` = gated backprop of ones down to the image -> g_x;  v0 = make_v0(g_x);
+      2. tangent forward of v0 through the critic (bias-free, saved LeakyReLU gates);
+      3. ONE combined backward seeded with pen_seed whose weight gradients contract over the doubled K
+         [x ; v] . [ybar ; ghat]  and whose activation gradient picks up the minibatch-stddev curvature term.
+    Returns (grads {id(param): tensor}, g_x)."""
+    steps, fade = pen_tape["steps"], pen_tape["fade"]
     params = critic_params(critic, steps, fade)
     need = {id(p): bool(p.requires_grad) for p in params}
-    terms = _f32(3, device=dev)
-    seed_f = _f32(B, 1, device=dev)
-    seed_r = _f32(B, 1, device=dev)
-    pf = pred_fake.detach().float().contiguous()
-    pr = pred_real.detach().float().contiguous()
-    call("bg_logistic_loss", pf, B, 1.0, terms[0:1], seed_f, 1.0)         # softplus(D(fake)).mean(), gan.py:406
-    call("bg_logistic_loss", pr, B, -1.0, terms[1:2], seed_r, 1.0)        # softplus(-D(real)).mean(), gan.py:396
-    grads_f, _ = critic_backward(critic, packs, tape_fake, seed_f, need, need_img=False)
+    firsts = [critic_backward(critic, packs, tape, seed, need, need_img=False)[0] for tape, seed in first_order]
+    B = pen_tape["B"]
+    dev = pen_tape["img"].device
     ones = torch.ones(B, 1, device=dev)
     ghat: dict = {}
-    _, g_x = critic_backward(critic, packs, tape_real, ones, {}, need_img=True, keep=ghat)   # gan.py:398-400
-    call("bg_sumsq", g_x, g_x.numel(), float(c_lambda) / 2.0 / B, terms[2:3])                # gan.py:401-404
-    v0 = torch.empty_like(g_x)
-    call("bg_axpby_f32", g_x, None, v0, g_x.numel(), float(c_lambda) / B, 0.0)
-    T = critic_tangent(critic, packs, tape_real, v0)
+    _, g_x = critic_backward(critic, packs, pen_tape, ones, {}, need_img=True, keep=ghat)    # gan.py:398-400 / 375-381
+    v0 = make_v0(g_x)
+    T = critic_tangent(critic, packs, pen_tape, v0)
     grads = {}
     by_id = {id(p): p for p in params}
 
     def finish(k, gr):
-        """A real-branch gradient just became final: add the fake-branch part and hand the total out."""
+        """A penalised-branch gradient just became final: add the first-order parts and hand the total out."""
         if not need.get(k, False):
             return
-        gf = grads_f.get(k)
-        if gf is None:
-            raise RuntimeError("internal: missing critic gradient")
-        call("bg_axpby_f32", gf, gr, gf, gf.numel(), 1.0, 1.0)
-        grads[k] = gf
+        for gf in firsts:
+            part = gf.get(k)
+            if part is None:
+                raise RuntimeError("internal: missing critic gradient")
+            call("bg_axpby_f32", part, gr, part, part.numel(), 1.0, 1.0)
+            gr = part
+        grads[k] = gr
         if emit is not None:
-            emit(by_id[k], gf)
+            emit(by_id[k], gr)
 
     # the last pass runs head -> high resolution: the big low-resolution weights finish first, so their all-reduce
     # (emit) overlaps the expensive high-resolution layers still to come
-    grads_r, _ = critic_backward(critic, packs, tape_real, seed_r, need, need_img=False, r1=(T, ghat), emit=finish)
+    critic_backward(critic, packs, pen_tape, pen_seed, need, need_img=False, r1=(T, ghat), emit=finish)
     for p in params:
         if need[id(p)] and id(p) not in grads:
             raise RuntimeError("internal: missing critic gradient")
-    loss = terms.sum()
+    return grads, g_x
+
+
+def critic_r1_step(critic, packs: PackCache, tape_fake, pred_fake, tape_real, pred_real, c_lambda, emit=None,
+                   first_order=True):
+    """Critic.get_r1_loss (gan.py:393-412): loss value + gradients of every active critic parameter.
+
+    loss = mean softplus(-D(real)) + mean softplus(D(fake)) + lambda/2 * mean_n ||d sum D(real) / d real_n||^2
+    fake branch: ordinary backward seeded with sigmoid(D(fake))/B; real branch: _penalised_critic_step with
+    v0 = (lambda/B) g_x and the first-order seed -sigmoid(-D(real))/B.  first_order=False keeps ONLY the penalty term
+    (loss and gradients): the purely second-order part, checked in isolation by the parity tests.
+    Returns (loss tensor (), grads {id(param): tensor}, g_x).
+    """
+    dev = pred_real.device
+    B = pred_real.shape[0]
+    terms = _f32(3, device=dev) if first_order else torch.zeros(3, device=dev)
+    seed_f = _f32(B, 1, device=dev)
+    seed_r = _f32(B, 1, device=dev)
+    if first_order:
+        pf = pred_fake.detach().float().contiguous()
+        pr = pred_real.detach().float().contiguous()
+        call("bg_logistic_loss", pf, B, 1.0, terms[0:1], seed_f, 1.0)         # softplus(D(fake)).mean(), gan.py:406
+        call("bg_logistic_loss", pr, B, -1.0, terms[1:2], seed_r, 1.0)        # softplus(-D(real)).mean(), gan.py:396
+    else:
+        seed_r.zero_()
+
+    def make_v0(g_x):
+        call("bg_sumsq", g_x, g_x.numel(), float(c_lambda) / 2.0 / B, terms[2:3])            # gan.py:401-404
+        v0 = torch.empty_like(g_x)
+        call("bg_axpby_f32", g_x, None, v0, g_x.numel(), float(c_lambda) / B, 0.0)
+        return v0
+
+    grads, g_x = _penalised_critic_step(critic, packs, [(tape_fake, seed_f)] if first_order else [], tape_real, seed_r,
+                                        make_v0, emit=emit)
+    return terms.sum(), grads, g_x
+
+
+def critic_wgan_gp_step(critic, packs: PackCache, tape_fake, pred_fake, tape_real, pred_real, tape_mixed, c_lambda,
+                        emit=None):
+    """Critic.get_wgan_loss as gan.py:357-391 intends it (the reference's body cannot run, see gan.Critic.get_wgan_loss):
+    loss = -mean D(real) + mean D(fake) + lambda * mean_n (||d sum D(mixed) / d mixed_n||_2 - 1)^2.
+    fake / real branches: ordinary backward passes seeded with +1/B, -1/B; mixed branch: _penalised_critic_step with
+    v0_n = (lambda/B) * 2 (r_n - 1) / r_n * g_n, r_n = ||g_n||  and no first-order seed.
+    Returns (loss tensor (), grads {id(param): tensor}, g_mixed)."""
+    dev = pred_real.device
+    B = pred_real.shape[0]
+    pen = _f32(1, device=dev)
+    seed_f = torch.full((B, 1), 1.0 / B, device=dev)
+    seed_r = torch.full((B, 1), -1.0 / B, device=dev)
+
+    def make_v0(g_x):
+        v0 = torch.empty_like(g_x)
+        call("bg_gp_rows", g_x, B, g_x.numel() // B, float(c_lambda) / B, float(c_lambda) / B, pen, v0)   # gan.py:385
+        return v0
+
+    grads, g_x = _penalised_critic_step(critic, packs, [(tape_fake, seed_f), (tape_real, seed_r)], tape_mixed,
+                                        torch.zeros(B, 1, device=dev), make_v0, emit=emit)
+    loss = pred_fake.detach().float().mean() - pred_real.detach().float().mean() + pen[0]    # gan.py:387
     return loss, grads, g_x

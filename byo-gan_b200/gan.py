@@ -141,6 +141,26 @@ def _require_cuda(t, what):
         raise RuntimeError(f"{what} must be a CUDA tensor: the B200 build has no CPU path")
 
 
+_REPLICA_MSG = (
+    "this {} is an nn.DataParallel replica: the B200 build runs one process per GPU (torchrun + dist.py, see "
+    "INTEGRATION.md); single-process multi-device nn.DataParallel (train.py:71,79 with several visible GPUs) is not "
+    "supported — launch with CUDA_VISIBLE_DEVICES set to one device per process, where the unchanged wrapper takes "
+    "torch's single-device path")
+
+
+def _reject_replica(module):
+    # torch.nn.parallel.replicate() marks its shallow copies with _is_replica; their parameters are plain tensors, so
+    # the parameter walk below would fail with an opaque AttributeError long before get_r1_loss could explain
+    if getattr(module, "_is_replica", False):
+        raise RuntimeError(_REPLICA_MSG.format(type(module).__name__))
+
+
+def _install_pack_invalidation(module):
+    """load_state_dict copies into the parameters in place (version counters move, so the packed bf16 copies refresh
+    by themselves), but a checkpoint load is also the natural point to drop every cached pack and transpose."""
+    module.register_load_state_dict_post_hook(lambda mod, incompatible: mod._packs.invalidate())
+
+
 class _GeneratorFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, gen, steps, alpha, crossover, n_noise, z, z2, *rest):
@@ -234,8 +254,16 @@ class Generator(nn.Module):
             + [StyleGanBlock(ci, co) for ci, co in engine.GEN_CHANNELS[1:]])
         self.to_rgbs = nn.ModuleList([EqualizedConv2d(co, 3, kernel_size=1) for _, co in engine.GEN_CHANNELS])
         self._packs = PackCache()
+        _install_pack_invalidation(self)
+
+    def invalidate_packs(self):
+        """Drop the cached bf16 weight packs.  They refresh automatically when a parameter's version counter or storage
+        changes (optimizer steps, load_state_dict, copy_/mul_ on the parameter); writes through `.data`
+        (p.data.mul_(...), EMA / weight-clipping code) do NOT bump the counter and must be followed by this call."""
+        self._packs.invalidate()
 
     def forward(self, z_noise, noise=None, steps=1, alpha=None, z2=None, crossover=None):
+        _reject_replica(self)
         _require_cuda(z_noise, "z_noise")
         steps = int(steps)
         if steps > len(self.gen_blocks):
@@ -263,11 +291,15 @@ class Critic(nn.Module):
             [CriticBlock(ci, co) for ci, co in engine.CRITIC_CHANNELS[:7]] + [CriticBlock(512, 512, is_final_layer=True)])
         self._packs = PackCache()
         self._last_tape = None
+        _install_pack_invalidation(self)
+
+    invalidate_packs = Generator.invalidate_packs
 
     def gen_from_rgbs(self, out_chan, image_chan=3):
         return nn.Sequential(EqualizedConv2d(image_chan, out_chan, kernel_size=1), _Slot())
 
     def forward(self, images, steps=1, alpha=None):
+        _reject_replica(self)
         _require_cuda(images, "images")
         steps = int(steps)
         fade = alpha is not None and steps > 1
@@ -277,22 +309,7 @@ class Critic(nn.Module):
         self._last_tape = None
         return pred
 
-    def get_wgan_loss(self, crit_fake_pred, crit_real_pred, real_im, steps, alpha, c_lambda=1):
-        # The reference's implementation dereferences self.device and an undefined fake_im (gan.py:367-372)
-        # and therefore raises before doing any work; the WGAN-GP path is out of scope.
-        raise AttributeError("'Critic' object has no attribute 'device' (WGAN-GP is dead code in the reference, "
-                             "gan.py:357-391; train with use_r1=True)")
-
-    def get_r1_loss(self, crit_fake_pred, crit_real_pred, real_im, fake_im, steps, alpha, c_lambda=1):
-        """gan.py:393-412.  Runs the backward itself (like the reference's r1_loss.backward()) and accumulates
-        into .grad of every critic parameter that requires grad; returns the loss value."""
-        tape_f = getattr(crit_fake_pred, "_bg_tape", None)
-        tape_r = getattr(crit_real_pred, "_bg_tape", None)
-        if tape_f is None or tape_r is None:
-            raise RuntimeError(
-                "get_r1_loss needs the predictions returned by this Critic's forward (they carry the saved "
-                "activations).  Under multi-device nn.DataParallel the gather drops them: launch one process "
-                "per GPU instead (see INTEGRATION.md).")
+    def _emit_into_grad(self):
         hook = getattr(self, "_grad_ready_hook", None)
 
         def emit(p, g):
@@ -305,7 +322,44 @@ class Critic(nn.Module):
             if hook is not None:
                 hook(p)                                   # e.g. dist.GradSync.ready: bucketed all-reduce, overlapped
 
-        loss, grads, g_x = engine.critic_r1_step(self, self._packs, tape_f, crit_fake_pred, tape_r, crit_real_pred,
-                                                 c_lambda, emit=emit)
+        return emit
+
+    @staticmethod
+    def _tapes(*preds):
+        tapes = [getattr(p, "_bg_tape", None) for p in preds]
+        if any(t is None for t in tapes):
+            raise RuntimeError(
+                "the critic losses need the predictions returned by this Critic's forward (they carry the saved "
+                "activations).  Under multi-device nn.DataParallel the gather drops them: launch one process "
+                "per GPU instead (see INTEGRATION.md).")
+        return tapes
+
+    def get_wgan_loss(self, crit_fake_pred, crit_real_pred, real_im, steps, alpha, c_lambda=1, fake_im=None,
+                      epsilon=None):
+        """WGAN-GP critic loss as gan.py:357-391 intends it; runs its own backward like the reference (gan.py:389).
+
+        The reference's body cannot execute: it reads `self.device` (gan.py:368; nn.Module has none) and an undefined
+        `fake_im` (gan.py:372; train.py:178-185 does not pass one).  The signature train.py uses is kept; the fake images
+        are the ones `crit_fake_pred` was computed from (saved with its activations), or `fake_im=` when given;
+        `epsilon=` (B,1,1,1) overrides the torch.rand draw of gan.py:367-369 (parity tests)."""
+        tape_f, tape_r = self._tapes(crit_fake_pred, crit_real_pred)
+        _require_cuda(real_im, "real_im")
+        fake = tape_f["img"] if fake_im is None else fake_im.detach().float()
+        if epsilon is None:
+            epsilon = torch.rand(real_im.shape[0], 1, 1, 1, device=real_im.device)
+        mixed = torch.lerp(fake, real_im.detach().float(), epsilon.to(real_im.device))      # gan.py:372
+        _, tape_m = engine.critic_forward(self, self._packs, mixed, int(steps), alpha)      # gan.py:373
+        loss, _, g_m = engine.critic_wgan_gp_step(self, self._packs, tape_f, crit_fake_pred, tape_r, crit_real_pred,
+                                                  tape_m, c_lambda, emit=self._emit_into_grad())
+        self.last_mixed_image_grad = g_m                  # d sum(D(mixed)) / d mixed, what autograd.grad returned
+        return loss
+
+    def get_r1_loss(self, crit_fake_pred, crit_real_pred, real_im, fake_im, steps, alpha, c_lambda=1):
+        """gan.py:393-412.  Runs the backward itself (like the reference's r1_loss.backward()) and accumulates
+        into .grad of every critic parameter that requires grad; returns the loss value."""
+        tape_f, tape_r = self._tapes(crit_fake_pred, crit_real_pred)
+        loss, _, g_x = engine.critic_r1_step(self, self._packs, tape_f, crit_fake_pred, tape_r, crit_real_pred,
+                                             c_lambda, emit=self._emit_into_grad(),
+                                             first_order=not getattr(self, "_r1_penalty_only", False))
         self.last_real_image_grad = g_x                   # d sum(D(real)) / d real, what autograd.grad returned
         return loss

@@ -12,7 +12,7 @@
  *   - feature maps are NHWC bf16 (C multiple of 16 for convolutions, 8 elsewhere);
  *     images at the module boundary are NCHW fp32 as the reference passes them;
  *   - return 0 on success, non-zero on error; bg_last_error() returns a thread-local message;
- *   - re-entrant: no global mutable state besides per-device attribute caches;
+ *   - re-entrant: no global mutable state besides per-device attribute caches and the bg_set_deterministic switch;
  *   - kernels are launched with programmatic stream serialisation: the next kernel of the stream may become
  *     resident while this one is still running, and every kernel of the library waits (griddepcontrol.wait) for
  *     its predecessor's completion and memory visibility before its first global access, so results are exactly
@@ -31,6 +31,17 @@ extern "C" {
 
 const char* bg_last_error(void);
 int bg_abi_version(void);
+/* Chain-deterministic reductions (process-wide switch; default off, or BG_DETERMINISTIC=1 in the environment).
+ * The reference's results are deterministic on one device (gan.py uses no atomics of its own); the fast path of this
+ * library is not: instance-norm statistics (gan.py:59), the AdaIN backward sums and the minibatch-stddev plane
+ * (gan.py:283-291) are combined across CTAs with fp32 atomics, and a last-bit difference there is amplified by the bf16
+ * roundings and LeakyReLU gates of the ~50 layers behind it.  With the switch on, every reduction whose result FEEDS
+ * LATER LAYERS is an ordered sum with one contributing block per output (the fused conv-epilogue statistics run as the
+ * stand-alone bg_in_stats pass), so images, critic scores, activation gradients and the R1 image gradient are
+ * bit-reproducible.  Leaf sums (weight-gradient split-K partials, bias / noise-weight gradients, loss terms) keep
+ * their atomics: ~1e-6 relative order noise that ends in that tensor.  Used by the parity tests; costs a few percent. */
+int bg_set_deterministic(int on);
+int bg_get_deterministic(void);
 
 /* ---- equalized-lr weight staging (gan.py:14,27,32: weight * sqrt(2/fan_in) every forward) -------------
  * w: fp32 (Cout,Cin,ks,ks).  w_fprop: bf16 [ks*ks][Cout][Cin_pad] or NULL.
@@ -231,6 +242,10 @@ int bg_mbstd_bwd(const void* x, const void* v, const void* gpad, const void* gpa
  * (seed may be NULL).  sumsq: out[0] = scale * sum x^2 (the R1 penalty, gan.py:401-404). */
 int bg_logistic_loss(const float* pred, int n, float sign, float* loss, float* seed, float seed_scale, void* stream);
 int bg_sumsq(const float* x, size_t n, float scale, float* out, void* stream);
+/* WGAN-GP penalty rows (gan.py:383-385: gp = mean_n (||gradient_n||_2 - 1)^2), g: fp32 (B, D):
+ * pen[0] = pen_scale * sum_n (r_n - 1)^2, r_n = ||g_n||_2;  v[n] = v_scale * 2 (r_n - 1) / r_n * g_n, i.e. the
+ * derivative of the penalty w.r.t. g_n — the direction the second-order pass is taken along. */
+int bg_gp_rows(const float* g, int B, size_t D, float pen_scale, float v_scale, float* pen, float* v, void* stream);
 
 #ifdef __cplusplus
 }

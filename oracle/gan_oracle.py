@@ -334,17 +334,57 @@ def critic_r1_loss(pred_fake, pred_real, real_im, c_lambda=1.0):
     return real_term + fake_term + c_lambda / 2 * penalty
 
 
+def critic_r1_penalty(pred_real, real_im, c_lambda=1.0):
+    """Only the gradient-penalty term of Critic.get_r1_loss (gan.py:398-404): lambda/2 * mean_n ||d sum D(real) / d real_n||^2.
+    Its parameter gradient is PURELY second order, so checking it alone isolates the double-backward of every layer."""
+    (grad_real,) = torch.autograd.grad(outputs=pred_real.sum(), inputs=real_im, create_graph=True)
+    return c_lambda / 2 * (grad_real.reshape(grad_real.size(0), -1).norm(2, dim=1) ** 2).mean()
+
+
+def make_epsilon(batch: int, seed: int) -> torch.Tensor:
+    """The per-sample interpolation factor of WGAN-GP, U(0,1) of shape (B,1,1,1) (gan.py:367-369), from a seeded
+    CPU generator so the reference restatement, the oracle and the CUDA path mix the same images."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(32452843 * seed + 7)
+    return torch.rand(batch, 1, 1, 1, generator=g)
+
+
+def generator_wgan_loss(pred_fake):
+    """Generator.get_wgan_loss, gan.py:224-225."""
+    return -pred_fake.mean()
+
+
+def critic_wgan_gp_loss(D, pred_fake, pred_real, real_im, fake_im, epsilon, steps, alpha, c_lambda=1.0, group_size=4):
+    """Critic.get_wgan_loss as gan.py:357-391 INTENDS it, WITHOUT the internal .backward().  The reference's body cannot
+    run: it reads `self.device` (nn.Module has none, gan.py:368) and an undefined `fake_im` (gan.py:372; train.py:178-185
+    does not pass it).  Repaired here and in oracle/make_golden.py the same way: device taken from real_im, fake_im
+    passed in, epsilon supplied (the reference draws torch.rand).  Everything else follows the lines:
+      mixed = real * eps + (1 - eps) * fake                      gan.py:372
+      g = d sum D(mixed) / d mixed  (create_graph)               gan.py:373-381
+      gp = mean_n (||g_n||_2 - 1)^2                              gan.py:385
+      loss = -mean D(real) + mean D(fake) + lambda * gp          gan.py:387"""
+    mixed = real_im * epsilon + (1 - epsilon) * fake_im
+    scores = critic_forward(D, mixed, steps, alpha, group_size)
+    (gradient,) = torch.autograd.grad(inputs=mixed, outputs=scores, grad_outputs=torch.ones_like(scores),
+                                      create_graph=True, retain_graph=True)
+    gp = ((gradient.reshape(gradient.size(0), -1).norm(2, dim=1) - 1) ** 2).mean()
+    return -pred_real.mean() + pred_fake.mean() + c_lambda * gp
+
+
 def _as_params(state, requires_grad, device=None, dtype=torch.float32):
     return {k: v.detach().to(device=device, dtype=dtype).clone().requires_grad_(requires_grad)
             for k, v in state.items()}
 
 
 def train_iteration(gen_state, critic_state, z_d, z_g, real, noise_d, noise_g, steps, alpha, c_lambda=10.0,
-                    device=None, dtype=torch.float32):
+                    device=None, dtype=torch.float32, loss="r1", epsilon=None):
     """One reference iteration (train.py:135-217) without the optimizer steps: the critic step
     (train.py:135-191: G frozen, fake detached, R1 loss, backward into D) then the generator step
     (train.py:193-217: D frozen, non-saturating loss, backward into G).  Both steps see the SAME weights
     (no Adam update in between) so gradients are comparable tensor by tensor.
+
+    loss: "r1" (use_r1=True, the reference's working path), "r1_penalty" (critic step = the penalty term alone: second-order
+    gradients in isolation) or "wgan" (train.py:177-185,213 with the repaired gan.py:357-391; needs `epsilon` (B,1,1,1)).
 
     Returns dict(c_loss, g_loss, fake_d, pred_fake, pred_real, d_grads{key: tensor|None}, g_grads{...}).
     """
@@ -357,8 +397,14 @@ def train_iteration(gen_state, critic_state, z_d, z_g, real, noise_d, noise_g, s
     real_im = real.detach().to(device=device, dtype=dtype).requires_grad_()   # train.py:150-158
     pred_fake = critic_forward(D, fake.detach(), steps, alpha)
     pred_real = critic_forward(D, real_im, steps, alpha)
-    c_loss = critic_r1_loss(pred_fake, pred_real, real_im, c_lambda)
-    c_loss.backward()                                                          # gan.py:410
+    if loss == "r1":
+        c_loss = critic_r1_loss(pred_fake, pred_real, real_im, c_lambda)
+    elif loss == "r1_penalty":
+        c_loss = critic_r1_penalty(pred_real, real_im, c_lambda)
+    else:
+        c_loss = critic_wgan_gp_loss(D, pred_fake, pred_real, real_im, fake.detach(),
+                                     epsilon.detach().to(device=device, dtype=dtype), steps, alpha, c_lambda)
+    c_loss.backward()                                                          # gan.py:410 / gan.py:389
     out.update(c_loss=c_loss.detach(), fake_d=fake.detach(), pred_fake=pred_fake.detach(),
                pred_real=pred_real.detach(),
                d_grads={k: (v.grad.detach() if v.grad is not None else None) for k, v in D.items()})
@@ -368,7 +414,7 @@ def train_iteration(gen_state, critic_state, z_d, z_g, real, noise_d, noise_g, s
     z = z_g.detach().to(device=device, dtype=dtype).requires_grad_()
     fake = generator_forward(G, z, [n.to(device=device, dtype=dtype) for n in noise_g], steps, alpha)
     pred = critic_forward(D, fake, steps, alpha)
-    g_loss = generator_r1_loss(pred)
+    g_loss = generator_wgan_loss(pred) if loss == "wgan" else generator_r1_loss(pred)   # train.py:207-213
     g_loss.backward()                                                          # train.py:216
     out.update(g_loss=g_loss.detach(), fake_g=fake.detach(), pred_g=pred.detach(),
                g_grads={k: (v.grad.detach() if v.grad is not None else None) for k, v in G.items()},

@@ -41,7 +41,13 @@ TRAIN_CASES = [
     (5, 4, 0.5, 10.0),     # BASELINE config 2 shape at reduced batch
     (6, 4, None, 10.0),
     (7, 4, None, 10.0),    # BASELINE config 3 shape at reduced batch
+    (8, 4, None, 10.0),    # BASELINE config 4 shape (512x512) at reduced batch
+    (8, 4, 0.5, 10.0),     # ... with the fade-in branches
 ]
+# critic step with ONLY the R1 penalty term (gan.py:398-404): purely second-order parameter gradients
+PENALTY_CASES = [(2, 8, 0.4, 10.0), (4, 4, None, 10.0), (5, 4, 0.5, 10.0), (6, 4, None, 10.0)]
+# WGAN-GP (train.py:177-185 -> gan.py:357-391), dead code in the reference: run here with its two defects repaired
+WGAN_CASES = [(1, 8, None, 10.0), (2, 8, 0.4, 10.0), (4, 4, None, 10.0), (6, 4, 0.5, 10.0)]
 MBSTD_BATCHES = [4, 8, 16, 32, 6, 12, 8]   # the tail reproduces the group_size mutation 6 -> 6 -> 8... (gan.py:277-278)
 
 
@@ -144,6 +150,62 @@ def main():
         print(f"train steps={steps} B={batch} alpha={alpha}: c_loss={c_loss.item():.6f} g_loss={g_loss.item():.6f} "
               f"{time.time() - t0:.1f}s", flush=True)
     json.dump(train, open(os.path.join(OUT, "train_iteration.json"), "w"))
+
+    # ---- R1 penalty alone: gan.py:398-404 on the real modules, then backward of just that term
+    pen = []
+    for steps, batch, alpha, lam in PENALTY_CASES:
+        gen, critic = load_ref(seed=2)
+        real_im = O.make_images(batch, steps, seed=30 + steps).requires_grad_()
+        pr = critic(real_im, steps, alpha)
+        critic.zero_grad()
+        grad_real = torch.autograd.grad(outputs=pr.sum(), inputs=real_im, create_graph=True)[0]
+        penalty = lam / 2 * (grad_real.view(grad_real.size(0), -1).norm(2, dim=1) ** 2).mean()
+        penalty.backward()
+        pen.append({"steps": steps, "batch": batch, "alpha": alpha, "lambda": lam, "penalty": penalty.item(),
+                    "grad_real": O.fingerprint(grad_real),
+                    "d_grads": {k: O.fingerprint(p.grad) for k, p in critic.named_parameters()}})
+        print(f"penalty steps={steps} B={batch} alpha={alpha}: {penalty.item():.6f}", flush=True)
+    json.dump(pen, open(os.path.join(OUT, "r1_penalty.json"), "w"))
+
+    # ---- WGAN-GP: the body of Critic.get_wgan_loss (gan.py:357-391) executed on the real modules with the two
+    # defects that keep it from running repaired (self.device -> real_im.device; the undefined fake_im passed in) and
+    # epsilon supplied instead of torch.rand; generator step with Generator.get_wgan_loss (gan.py:224-225)
+    wg = []
+    for steps, batch, alpha, lam in WGAN_CASES:
+        gen, critic = load_ref(seed=2)
+        z_d, z_g = O.make_latents(batch, seed=10 + steps), O.make_latents(batch, seed=20 + steps)
+        n_d, n_g = O.make_noise(batch, steps, seed=10 + steps), O.make_noise(batch, steps, seed=20 + steps)
+        real = O.make_images(batch, steps, seed=30 + steps)
+        eps = O.make_epsilon(batch, seed=40 + steps)
+        for p in gen.parameters():
+            p.requires_grad = False
+        fake = gen(z_d, noise=n_d, steps=steps, alpha=alpha)
+        real_im = real.clone().requires_grad_()
+        pf = critic(fake.detach(), steps, alpha)
+        pr = critic(real_im, steps, alpha)
+        critic.zero_grad()
+        mixed_images = real_im * eps + (1 - eps) * fake                                    # gan.py:372
+        mixed_image_scores = critic.forward(mixed_images, steps=steps, alpha=alpha)        # gan.py:373
+        gradient = torch.autograd.grad(inputs=mixed_images, outputs=mixed_image_scores,
+                                       grad_outputs=torch.ones_like(mixed_image_scores),
+                                       create_graph=True, retain_graph=True)[0]            # gan.py:375-381
+        gp = ((gradient.view(gradient.size(0), -1).norm(2, dim=1) - 1) ** 2).mean()        # gan.py:385
+        wgan_loss = -pr.mean() + pf.mean() + (lam * gp)                                    # gan.py:387
+        wgan_loss.backward()                                                               # gan.py:389
+        d_grads = {k: O.fingerprint(p.grad) for k, p in critic.named_parameters()}
+        for p in critic.parameters():
+            p.requires_grad = False
+        for p in gen.parameters():
+            p.requires_grad = True
+        fake2 = gen(z_g, noise=n_g, steps=steps, alpha=alpha)
+        g_loss = gen.get_wgan_loss(critic(fake2, steps, alpha))
+        gen.zero_grad()
+        g_loss.backward()
+        wg.append({"steps": steps, "batch": batch, "alpha": alpha, "lambda": lam, "c_loss": wgan_loss.item(),
+                   "g_loss": g_loss.item(), "gp": gp.item(), "d_grads": d_grads,
+                   "g_grads": {k: O.fingerprint(p.grad) for k, p in gen.named_parameters()}})
+        print(f"wgan steps={steps} B={batch} alpha={alpha}: c_loss={wgan_loss.item():.6f} gp={gp.item():.6f}", flush=True)
+    json.dump(wg, open(os.path.join(OUT, "wgan_gp.json"), "w"))
     print("wrote", sorted(os.listdir(OUT)))
 
 

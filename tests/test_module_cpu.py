@@ -74,12 +74,88 @@ def test_no_cpu_fallback_and_reference_error_behaviour():
         g(torch.zeros(2, 512))
     with pytest.raises(RuntimeError, match="CUDA"):
         c(torch.zeros(2, 3, 4, 4))
-    with pytest.raises(AttributeError):                                # gan.py:367-368 raises AttributeError too
-        c.get_wgan_loss(None, None, None, 1, None)
+    with pytest.raises(RuntimeError, match="forward"):                 # WGAN-GP is implemented: same contract
+        c.get_wgan_loss(torch.zeros(2, 1), torch.zeros(2, 1), torch.zeros(2, 3, 4, 4), 1, None)
     with pytest.raises(ValueError):                                    # gan.py:105-106
         gan.StyleGanBlock(4, 4, is_initial=True, does_upsample=True)
     with pytest.raises(RuntimeError, match="forward"):
         c.get_r1_loss(torch.zeros(2, 1), torch.zeros(2, 1), None, None, 1, None)
+
+
+def test_dataparallel_replicas_are_rejected_with_an_explanation():
+    """Unmodified train.py on a multi-GPU box would wrap the modules in a multi-device nn.DataParallel (train.py:71,79),
+    whose replicas hold plain tensors instead of Parameters; forward must say 'one process per GPU' instead of failing
+    with an opaque AttributeError deep inside the parameter walk."""
+    for m, x in ((gan.Generator(), torch.zeros(2, 512)), (gan.Critic(), torch.zeros(2, 3, 4, 4))):
+        m._is_replica = True                       # what torch.nn.parallel.replicate() sets on its copies
+        with pytest.raises(RuntimeError, match="one process per GPU"):
+            m(x)
+
+
+def test_load_state_dict_drops_cached_weight_packs():
+    g = gan.Generator()
+    g._packs._conv["sentinel"] = ("tag", None, None)
+    g._packs._lin["sentinel"] = ("tag", None)
+    g.load_state_dict(O.make_state("gen", 4))
+    assert not g._packs._conv and not g._packs._lin
+    g._packs._conv["sentinel"] = ("tag", None, None)
+    g.invalidate_packs()
+    assert not g._packs._conv
+    c = gan.Critic()
+    c._packs._conv["sentinel"] = ("tag", None, None)
+    torch.nn.DataParallel(c).load_state_dict({"module." + k: v for k, v in O.make_state("critic", 4).items()})
+    assert not c._packs._conv
+
+
+REF = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "gan.py")), reason="the reference checkout only exists in the build container")
+def test_checkpoints_cross_load_with_the_real_reference_classes(tmp_path):
+    """SURVEY §8c KAT 10 with the REAL reference modules: a checkpoint written by train.py's save call (train.py:247-259)
+    from reference modules loads strictly into the drop-in, and one written from the drop-in loads strictly into the
+    reference's Generator / Critic (generate_samples.py:48-52), with and without the DataParallel 'module.' prefix —
+    same keys, same order, same shapes, same values."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("ref_gan_for_kat10", os.path.join(REF, "gan.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    torch.manual_seed(3)
+    rg, rc = ref.Generator(), ref.Critic()
+    torch.manual_seed(3)
+    ng, nc = gan.Generator(), gan.Critic()
+    # same construction order and init rules: identical initial weights from the same seed
+    for (ka, va), (kb, vb) in zip(rg.state_dict().items(), ng.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb), ka
+    for (ka, va), (kb, vb) in zip(rc.state_dict().items(), nc.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb), ka
+    # reference -> drop-in (DataParallel-wrapped on both sides, as train.py saves and generate_samples.py loads)
+    for p in list(rg.parameters()) + list(rc.parameters()):
+        p.data.normal_()
+    path = tmp_path / "chk-ref.pth"
+    torch.save({"gen": torch.nn.DataParallel(rg).state_dict(), "critic": torch.nn.DataParallel(rc).state_dict(),
+                "iter": 11, "im_count": 352, "step": 2, "epoch": 0, "alpha": 0.4}, path)
+    save = torch.load(path)
+    wg, wc = torch.nn.DataParallel(ng), torch.nn.DataParallel(nc)
+    wg.load_state_dict(save["gen"], strict=True)
+    wc.load_state_dict(save["critic"], strict=True)
+    for k, v in rg.state_dict().items():
+        assert torch.equal(ng.state_dict()[k], v), k
+    # drop-in -> reference
+    for p in list(ng.parameters()) + list(nc.parameters()):
+        p.data.mul_(0.5)
+    path2 = tmp_path / "chk-new.pth"
+    torch.save({"gen": wg.state_dict(), "critic": wc.state_dict(), "iter": 12, "im_count": 384, "step": 2, "epoch": 0,
+                "alpha": None}, path2)
+    back = torch.load(path2)
+    torch.nn.DataParallel(rg).load_state_dict(back["gen"], strict=True)
+    torch.nn.DataParallel(rc).load_state_dict(back["critic"], strict=True)
+    for k, v in nc.state_dict().items():
+        assert torch.equal(rc.state_dict()[k], v), k
+    # the three optimizer groups train.py:59-70 builds see the same parameter sets in both implementations
+    for attr in ("to_w_noise", "gen_blocks", "to_rgbs"):
+        assert [tuple(p.shape) for p in getattr(rg, attr).parameters()] == [tuple(p.shape) for p in getattr(ng, attr).parameters()]
 
 
 def test_c_abi_library_exports_every_declared_symbol():
@@ -91,11 +167,13 @@ def test_c_abi_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(os.path.join(ROOT, "byo-gan_b200", "libbg_b200.so"))
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in bg_b200.h but not exported"
-    assert declared - {"bg_last_error", "bg_abi_version"} == set(bg_native.SIGNATURES)
+    assert declared - {"bg_last_error", "bg_abi_version"} == set(bg_native.SIGNATURES) | set(bg_native.HOST_FUNCS)
     lib.bg_abi_version.restype = ctypes.c_int
-    assert lib.bg_abi_version() >= 1
+    assert lib.bg_abi_version() >= 2
+    # the deterministic-reduction switch is plain host state: it can be exercised without a GPU
+    assert bg_native.set_deterministic(True) is False and bg_native.set_deterministic(False) is True
     # argument counts in the binding match the header declarations
-    for name, args in bg_native.SIGNATURES.items():
+    for name, args in list(bg_native.SIGNATURES.items()) + list(bg_native.HOST_FUNCS.items()):
         m = re.search(r"int\s+" + name + r"\s*\(([^;]*?)\)\s*;", header, re.S)
         assert m, name
-        assert len([a for a in m.group(1).split(",") if a.strip()]) == len(args), name
+        assert len([a for a in m.group(1).split(",") if a.strip() and a.strip() != "void"]) == len(args), name

@@ -94,3 +94,33 @@ def test_train_iteration_matches_reference(case):
         check_fp(r["d_grads"][k], fp, f"D grad {k}", tol=2e-4)
     for k, fp in case["g_grads"].items():
         check_fp(r["g_grads"][k], fp, f"G grad {k}", tol=2e-4)
+
+
+def _iteration_inputs(steps, batch):
+    return (O.make_latents(batch, 10 + steps), O.make_latents(batch, 20 + steps), O.make_images(batch, steps, 30 + steps),
+            O.make_noise(batch, steps, 10 + steps), O.make_noise(batch, steps, 20 + steps))
+
+
+@pytest.mark.parametrize("case", load("r1_penalty.json"), ids=lambda c: f"s{c['steps']}-b{c['batch']}-a{c['alpha']}")
+def test_r1_penalty_alone_matches_reference(case):
+    """The penalty term of gan.py:398-404 by itself: purely second-order parameter gradients."""
+    steps, batch, alpha, lam = case["steps"], case["batch"], case["alpha"], case["lambda"]
+    r = O.train_iteration(O.make_state("gen", 2), O.make_state("critic", 2), *_iteration_inputs(steps, batch), steps, alpha,
+                          lam, loss="r1_penalty")
+    assert abs(r["c_loss"].item() - case["penalty"]) <= 1e-4 * abs(case["penalty"])
+    for k, fp in case["d_grads"].items():
+        check_fp(r["d_grads"][k], fp, f"D grad {k}", tol=2e-4)
+
+
+@pytest.mark.parametrize("case", load("wgan_gp.json"), ids=lambda c: f"s{c['steps']}-b{c['batch']}-a{c['alpha']}")
+def test_wgan_gp_iteration_matches_repaired_reference(case):
+    """gan.py:357-391 executed on the reference's modules with its two defects repaired (oracle/make_golden.py)."""
+    steps, batch, alpha, lam = case["steps"], case["batch"], case["alpha"], case["lambda"]
+    r = O.train_iteration(O.make_state("gen", 2), O.make_state("critic", 2), *_iteration_inputs(steps, batch), steps, alpha,
+                          lam, loss="wgan", epsilon=O.make_epsilon(batch, 40 + steps))
+    assert abs(r["c_loss"].item() - case["c_loss"]) <= 1e-4 * abs(case["c_loss"])
+    assert abs(r["g_loss"].item() - case["g_loss"]) <= 1e-4 * (abs(case["g_loss"]) + 1e-2)
+    for k, fp in case["d_grads"].items():
+        check_fp(r["d_grads"][k], fp, f"D grad {k}", tol=2e-4)
+    for k, fp in case["g_grads"].items():
+        check_fp(r["g_grads"][k], fp, f"G grad {k}", tol=2e-4)

@@ -1,0 +1,235 @@
+"""The drop-in driven by the reference's OWN call sequence (VERDICT r1 'boundary proof'): the loop body of
+train.py:58-80,135-259 and generate_samples.py:48-57, restated line by line around byo-gan_b200/gan.py + helper.py
+(/root/reference does not exist on the GPU box, so the callers cannot be imported there; tests/test_module_cpu.py
+cross-loads checkpoints with the real reference classes in the build container).
+
+What the callers do that the kernel-level tests do not: nn.DataParallel wrapping and `.module.` access, three Adam
+parameter groups stepping the fp32 masters in place (so every cached bf16 weight pack must refresh), internally drawn
+per-layer noise from torch's global RNG, fade-in alpha from the running image count, the 25-latent preview forward
+under no_grad, checkpoint save / load and the sampling call with the saved (step, alpha)."""
+import os
+
+import pytest
+import torch
+from torch import nn
+
+pytestmark = pytest.mark.gpu
+
+from oracle import gan_oracle as O  # noqa: E402
+import parity_util as U  # noqa: E402
+
+
+def _adam_groups(gen_like, lr, betas, params_of):
+    """train.py:59-70: mapping network at lr * 0.01, synthesis blocks and toRGBs at lr."""
+    return torch.optim.Adam(
+        [{"params": params_of(gen_like, "to_w_noise"), "lr": lr * 0.01},
+         {"params": params_of(gen_like, "gen_blocks")},
+         {"params": params_of(gen_like, "to_rgbs")}], lr=lr, betas=betas)
+
+
+def test_reference_training_loop_runs_on_the_drop_in_and_tracks_the_oracle(tmp_path):
+    import gan
+    import helper
+
+    U.no_tf32()
+    dev = "cuda"
+    lr, betas, c_lambda = 0.002, (0.0, 0.99), 10
+    steps, batch, iters_n, fade_in = 3, 8, 3, 40.0
+    # ---- train.py:58-80
+    gen = gan.Generator().to(dev)
+    critic = gan.Critic().to(dev)
+    gen.load_state_dict(O.make_state("gen", 6))
+    critic.load_state_dict(O.make_state("critic", 6))
+    gen_opt = _adam_groups(gen, lr, betas, lambda m, a: getattr(m, a).parameters())
+    critic_opt = torch.optim.Adam(critic.parameters(), lr=lr, betas=betas)
+    gen = nn.DataParallel(gen, device_ids=[0])         # one visible device per process: torch's single-device path
+    critic = nn.DataParallel(critic, device_ids=[0])
+    gen.train()
+    critic.train()
+    # ---- the oracle twin: same initial weights as plain fp32 tensors, its own Adam instances with the same groups
+    Gs = {k: v.to(dev).requires_grad_() for k, v in O.make_state("gen", 6).items()}
+    Ds = {k: v.to(dev).requires_grad_() for k, v in O.make_state("critic", 6).items()}
+    g_opt_o = torch.optim.Adam(
+        [{"params": [v for k, v in Gs.items() if k.startswith("to_w_noise")], "lr": lr * 0.01},
+         {"params": [v for k, v in Gs.items() if k.startswith("gen_blocks")]},
+         {"params": [v for k, v in Gs.items() if k.startswith("to_rgbs")]}], lr=lr, betas=betas)
+    d_opt_o = torch.optim.Adam(list(Ds.values()), lr=lr, betas=betas)
+
+    show_noise = O.make_latents(25, 99).to(dev)                       # train.py:84 (25 preview latents)
+    reals = [O.make_images(batch, steps + 1, 50 + i) for i in range(iters_n)]      # loader yields a larger size
+    zs = [(O.make_latents(batch, 60 + i).to(dev), O.make_latents(batch, 70 + i).to(dev)) for i in range(iters_n)]
+    im_count, iters = 0, 0
+    c_hist, g_hist, c_hist_o, g_hist_o = [], [], [], []
+    with U.deterministic():
+        for it in range(iters_n):
+            real_cpu = reals[it]
+            cur_batch_size = len(real_cpu)
+            # ---------------- critic step, train.py:135-191 ----------------
+            helper.set_requires_grad(critic, True)
+            helper.set_requires_grad(gen, False)
+            z_noise = zs[it][0].clone().requires_grad_()                 # get_truncated_noise(...).to(device)
+            alpha = im_count / fade_in
+            if alpha > 1.0:
+                alpha = None
+            torch.manual_seed(1000 + it)
+            fake_im = gen(z_noise, steps=steps, alpha=alpha)
+            real_im = torch.nn.functional.interpolate(real_cpu, size=(fake_im.shape[2], fake_im.shape[3]),
+                                                      mode="bilinear").to(dev, dtype=torch.float).requires_grad_()
+            critic_fake_pred = critic(fake_im.detach(), steps, alpha)
+            critic_real_pred = critic(real_im, steps, alpha)
+            critic.zero_grad()
+            c_loss = critic.module.get_r1_loss(critic_fake_pred, critic_real_pred, real_im, fake_im, steps, alpha, c_lambda)
+            critic_opt.step()
+            im_count += cur_batch_size
+            c_hist.append(c_loss.item())
+            # ---------------- generator step, train.py:193-219 ----------------
+            helper.set_requires_grad(critic, False)
+            helper.set_requires_grad(gen, True)
+            noise = zs[it][1].clone().requires_grad_()
+            alpha_g = im_count / fade_in
+            if alpha_g > 1.0:
+                alpha_g = None
+            torch.manual_seed(2000 + it)
+            fake_images = gen(noise, steps=steps, alpha=alpha_g)
+            critic_fake_pred = critic(fake_images, steps, alpha_g)
+            g_loss = gen.module.get_r1_loss(critic_fake_pred)
+            gen.zero_grad()
+            g_loss.backward()
+            gen_opt.step()
+            g_hist.append(g_loss.item())
+            iters += 1
+            with torch.no_grad():                                        # train.py:236-237, every iteration
+                torch.manual_seed(3000 + it)
+                examples = gen(show_noise, alpha=alpha_g, steps=steps)
+                shown = torch.clamp(examples, 0, 1)
+            assert shown.shape == (25, 3, 16, 16)
+
+            # ---------------- the same iteration on the oracle (fp32 autograd, same RNG seeds => same noise) ---------
+            for v in Gs.values():
+                v.requires_grad_(False)
+            for v in Ds.values():
+                v.requires_grad_(True)
+            torch.manual_seed(1000 + it)
+            fake_o = O.generator_forward(Gs, zs[it][0], None, steps, alpha)
+            real_o = real_im.detach().clone().requires_grad_()
+            d_opt_o.zero_grad()
+            c_loss_o = O.critic_r1_loss(O.critic_forward(Ds, fake_o.detach(), steps, alpha),
+                                        O.critic_forward(Ds, real_o, steps, alpha), real_o, c_lambda)
+            c_loss_o.backward()
+            d_opt_o.step()
+            c_hist_o.append(c_loss_o.item())
+            for v in Ds.values():
+                v.requires_grad_(False)
+            for v in Gs.values():
+                v.requires_grad_(True)
+            torch.manual_seed(2000 + it)
+            g_opt_o.zero_grad()
+            g_loss_o = O.generator_r1_loss(O.critic_forward(Ds, O.generator_forward(Gs, zs[it][1], None, steps, alpha_g),
+                                                            steps, alpha_g))
+            g_loss_o.backward()
+            g_opt_o.step()
+            g_hist_o.append(g_loss_o.item())
+            with torch.no_grad():
+                torch.manual_seed(3000 + it)
+                examples_o = O.generator_forward(Gs, show_noise, None, steps, alpha_g)
+            assert U.rel(examples, examples_o) < U.TOL_IMG, (it, U.rel(examples, examples_o))
+
+        for a, b in zip(c_hist + g_hist, c_hist_o + g_hist_o):
+            assert abs(a - b) < U.TOL_LOSS * abs(b), (c_hist, c_hist_o, g_hist, g_hist_o)
+        # three Adam updates later the fp32 masters moved the same way: per-tensor cosine of the weight DELTAS
+        init_g, init_d = O.make_state("gen", 6), O.make_state("critic", 6)
+        worst = 1.0
+        for module, ref_state, init in ((gen.module, Gs, init_g), (critic.module, Ds, init_d)):
+            for name, p in module.named_parameters():
+                d_new = p.detach().cpu() - init[name]
+                d_ref = ref_state[name].detach().cpu() - init[name]
+                if d_ref.norm() == 0:
+                    assert d_new.norm() == 0, f"{name} moved but the reference's did not (inactive stage)"
+                    continue
+                assert d_new.norm() > 0, f"{name} did not move but the reference's did"
+                if d_ref.numel() >= 4096:
+                    worst = min(worst, U.cos(d_new, d_ref))
+        assert worst > 0.8, f"worst cosine between parameter updates after {iters_n} Adam steps: {worst}"
+
+        # ---------------- checkpoint, train.py:247-259, then generate_samples.py:48-57 ----------------
+        path = os.path.join(tmp_path, f"chk-{iters}.pth")
+        torch.save({"gen": gen.state_dict(), "critic": critic.state_dict(), "iter": iters, "im_count": im_count,
+                    "step": steps, "epoch": 0, "alpha": alpha_g}, path)
+        gen2 = nn.DataParallel(gan.Generator().to(dev), device_ids=[0])
+        save = torch.load(path)
+        gen2.load_state_dict(save["gen"])
+        assert all(k.startswith("module.") for k in save["gen"])
+        z1 = O.make_latents(1, 5).to(dev).requires_grad_()           # helper.get_truncated_noise returns requires_grad
+        torch.manual_seed(7)
+        img = gen2.forward(z1, steps=save["step"], alpha=save["alpha"])
+        torch.manual_seed(7)
+        img_trained = gen.forward(z1, steps=save["step"], alpha=save["alpha"])
+        assert torch.equal(img, img_trained), "a reloaded checkpoint must reproduce the trained generator bit for bit"
+        torch.manual_seed(7)
+        with torch.no_grad():
+            img_o = O.generator_forward(Gs, z1.detach(), None, steps, save["alpha"])
+        assert U.rel(img, img_o) < U.TOL_IMG
+
+
+@pytest.mark.parametrize("fused", [False, True], ids=["foreach-adam", "fused-adam"])
+def test_weight_packs_follow_the_fp32_masters(fused):
+    """the bf16 weight packs are cached per parameter (version counter, storage pointer).  After
+    optimizer.step() (for-each and fused multi-tensor Adam), load_state_dict, and a `.data` write followed by
+    invalidate_packs(), a forward must equal the forward of a FRESHLY built model holding the same weights."""
+    import gan
+
+    U.no_tf32()
+    dev = "cuda"
+    steps, batch = 4, 4
+    z = O.make_latents(batch, 81).to(dev)
+    noise = [n.to(dev) for n in O.make_noise(batch, steps, 82)]
+    real = O.make_images(batch, steps, 83).to(dev)
+
+    def fresh_like(g, c):
+        g2, c2 = gan.Generator().to(dev), gan.Critic().to(dev)
+        g2.load_state_dict(g.state_dict())
+        c2.load_state_dict(c.state_dict())
+        return g2, c2
+
+    def outputs(g, c):
+        with torch.no_grad():
+            img = g(z, noise=noise, steps=steps, alpha=0.6)
+            return img, c(real, steps, 0.6), c(img, steps, 0.6)
+
+    def same(g, c, what):
+        got, want = outputs(g, c), outputs(*fresh_like(g, c))
+        for a, b in zip(got, want):
+            assert torch.equal(a, b), f"stale weight pack after {what}"
+
+    with U.deterministic():
+        g, c = U.build_models(8)
+        before = outputs(g, c)
+        # 1. optimizer steps (in place on the masters; large lr so a stale pack cannot hide in the tolerance)
+        opt_g = torch.optim.Adam(g.parameters(), lr=0.05, betas=(0.0, 0.99), fused=fused)
+        opt_c = torch.optim.Adam(c.parameters(), lr=0.05, betas=(0.0, 0.99), fused=fused)
+        for _ in range(2):
+            img = g(z.clone().requires_grad_(), noise=noise, steps=steps, alpha=0.6)
+            loss = g.get_r1_loss(c(img, steps, 0.6))
+            g.zero_grad()
+            c.zero_grad()
+            loss.backward()
+            opt_g.step()
+            opt_c.step()
+            same(g, c, "optimizer.step()")
+        after = outputs(g, c)
+        assert U.rel(after[0], before[0]) > 1e-2, "the optimizer steps must have changed the images"
+        # 2. load_state_dict into a model that already holds packs
+        g.load_state_dict(O.make_state("gen", 9))
+        c.load_state_dict(O.make_state("critic", 9))
+        same(g, c, "load_state_dict")
+        # 3. in-place op on the parameter itself bumps the version counter
+        with torch.no_grad():
+            for p in list(g.parameters()) + list(c.parameters()):
+                p.mul_(0.9)
+        same(g, c, "p.mul_()")
+        # 4. writes through .data bypass the counter: documented to need invalidate_packs()
+        for p in list(g.parameters()) + list(c.parameters()):
+            p.data.mul_(1.1)
+        g.invalidate_packs()
+        c.invalidate_packs()
+        same(g, c, "p.data.mul_() + invalidate_packs()")
