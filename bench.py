@@ -34,10 +34,13 @@ import torch  # noqa: E402
 # step FLOPs per image in the reference's formulation: 4*G_fwd + 11*D_fwd
 WORKLOADS = {
     # name: (steps, alpha, per-GPU batch, GFLOP/img/iteration, description)
+    "train4": (1, None, 16, 1.258, "4x4 stage, batch 16 (BASELINE configs[0], the reference's CPU-runnable case)"),
     "train64": (5, 0.5, 64, 235.09, "64x64 stage with fade-in alpha=0.5, batch 64 (BASELINE configs[1])"),
-    "train256": (7, None, 32, 423.65, "256x256 stage, batch 32 per GPU, R1 every step (BASELINE configs[2])"),
+    "train256": (7, None, 32, 423.65, "256x256 stage with style mixing, batch 32 per GPU, R1 every step (BASELINE configs[2])"),
     "train512": (8, None, 16, 518.06, "512x512 stage, batch 16 per GPU, R1 every step (BASELINE configs[3])"),
 }
+BOUND = {"train4": "tensor", "train64": "tensor", "train256": "tensor", "train512": "hbm"}
+STYLE_MIXING_DEFAULT = {"train256"}     # BASELINE configs[2] is "256x256 stage WITH style mixing"
 LAMBDA = 10.0          # config.txt gradient_lambda
 LR, BETAS = 0.002, (0.0, 0.99)   # config.txt lr / beta_1 / beta_2
 # train.py:76-80 builds plain torch.optim.Adam; fused=True is the same update in one multi-tensor kernel per optimizer
@@ -136,110 +139,12 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------
 # the B200 arm
 # ------------------------------------------------------------------------------------------------------
-class Trainer:
-    """train.py:58-80 (models + the two Adam optimizers) and one iteration of train.py:135-219."""
+def make_trainer(steps, alpha, batch, device, style_mixing):
+    """The package's Trainer (byo-gan_b200/trainer.py): train.py:58-80 + one iteration of train.py:135-219."""
+    import trainer
 
-    def __init__(self, steps, alpha, batch, device, sync_cls):
-        import gan
-        import dist as bdist
-
-        torch.manual_seed(0)
-        self.gen, self.critic = gan.Generator().to(device), gan.Critic().to(device)
-        # reference init leaves biases / noise weights at zero; give them small values so no path is dead
-        with torch.no_grad():
-            for n, p in list(self.gen.named_parameters()) + list(self.critic.named_parameters()):
-                if n.endswith("bias") or n.endswith("inject_noise.weights"):
-                    p.add_(0.05 * torch.randn_like(p))
-        bdist.broadcast_parameters(self.gen)
-        bdist.broadcast_parameters(self.critic)
-        g = self.gen
-        self.gen_opt = torch.optim.Adam([{"params": g.to_w_noise.parameters(), "lr": LR * 0.01},
-                                         {"params": g.gen_blocks.parameters()}, {"params": g.to_rgbs.parameters()}],
-                                        lr=LR, betas=BETAS, fused=FUSED_ADAM)
-        self.critic_opt = torch.optim.Adam(self.critic.parameters(), lr=LR, betas=BETAS, fused=FUSED_ADAM)
-        self.steps, self.alpha, self.batch, self.device = steps, alpha, batch, device
-        self.sync = sync_cls()
-        self.critic._grad_ready_hook = self.sync.ready
-        if self.sync.enabled:                                 # single process: plain autograd accumulation
-            self.gen._grad_ready_hook = self.sync.ready
-
-    style_mixing = False
-
-    def _mix(self, z):
-        """--style-mixing (opt-in extension, not in the reference): second latent = the batch rolled by one sample,
-        crossover block drawn per call; costs one more mapping-network pass and a second group of style FCs."""
-        if not self.style_mixing:
-            return {}
-        self._mix_count = getattr(self, "_mix_count", 0) + 1
-        return {"z2": torch.roll(z.detach(), 1, 0).requires_grad_(), "crossover": 1 + self._mix_count % (self.steps - 1)}
-
-    def _read(self, loss, slot):
-        """Device->host read of a loss (train.py:191,219 do .item() for the progress bar).  The copy into pinned
-        memory is queued right behind the step's kernels and the VALUE is picked up one iteration later, when the
-        copy has long finished: the host never drains the launch queue, the losses still arrive every step."""
-        if not hasattr(self, "_pinned"):
-            self._pinned = [torch.zeros(2, 1).pin_memory() for _ in range(2)]     # [parity][slot]
-            self._events = [[None, None], [None, None]]
-            self._parity = 0
-        par = self._parity
-        self._pinned[par][slot].copy_(loss.detach().reshape(1), non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
-        self._events[par][slot] = ev
-        prev = self._events[par ^ 1][slot]
-        val = None
-        if prev is not None:
-            prev.synchronize()                              # completed an iteration ago
-            val = float(self._pinned[par ^ 1][slot])
-        if slot == 1:
-            self._parity ^= 1
-        return val
-
-    def flush_reads(self):
-        """Wait for the loss copies still in flight (end of a timed region)."""
-        for row in getattr(self, "_events", []):
-            for ev in row:
-                if ev is not None:
-                    ev.synchronize()
-        return [float(v) for buf in getattr(self, "_pinned", []) for v in buf]
-
-    @staticmethod
-    def _set_requires_grad(model, flag):                     # helper.py:48-50
-        for p in model.parameters():
-            p.requires_grad = flag
-
-    def iteration(self, real, z_d, z_g, read_losses):
-        gen, critic, steps, alpha = self.gen, self.critic, self.steps, self.alpha
-        # ---- critic step (train.py:135-191)
-        self._set_requires_grad(critic, True)
-        self._set_requires_grad(gen, False)
-        z = z_d.requires_grad_()
-        mix = self._mix(z_d)
-        fake = gen(z, steps=steps, alpha=alpha, **mix)
-        real_im = real.requires_grad_()
-        pf = critic(fake.detach(), steps, alpha)
-        pr = critic(real_im, steps, alpha)
-        critic.zero_grad()
-        self.sync.begin()
-        c_loss = critic.get_r1_loss(pf, pr, real_im, fake, steps, alpha, LAMBDA)
-        self.sync.finish()
-        self.critic_opt.step()
-        c_val = self._read(c_loss, 0) if read_losses else None
-        # ---- generator step (train.py:193-219)
-        self._set_requires_grad(critic, False)
-        self._set_requires_grad(gen, True)
-        z2 = z_g.requires_grad_()
-        fake2 = gen(z2, steps=steps, alpha=alpha, **self._mix(z_g))
-        pred = critic(fake2, steps, alpha)
-        g_loss = gen.get_r1_loss(pred)
-        gen.zero_grad()
-        self.sync.begin()
-        g_loss.backward()
-        self.sync.ready_all(p for p in gen.parameters() if p.grad is not None)
-        self.sync.finish()
-        self.gen_opt.step()
-        g_val = self._read(g_loss, 1) if read_losses else None
-        return c_val, g_val
+    return trainer.Trainer(steps, alpha, batch, device, lr=LR, betas=BETAS, c_lambda=LAMBDA, fused_adam=FUSED_ADAM,
+                           style_mixing=style_mixing, perturb_init=True)
 
 
 def conv_bytes(name, args):

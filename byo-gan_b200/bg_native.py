@@ -74,6 +74,7 @@ SIGNATURES = {
     "bg_logistic_loss": [_P, _I, _F, _P, _P, _F, _P],
     "bg_sumsq": [_P, _Z, _F, _P, _P],
     "bg_gp_rows": [_P, _I, _Z, _F, _F, _P, _P, _P],
+    "bg_image_feed_u8": [_P, _P, _P, _I, _I, _I, _P],
 }
 
 # host-side switches / predicates called directly (no stream argument, no launch)

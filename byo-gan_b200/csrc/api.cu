@@ -42,6 +42,7 @@ int launch_mbstd_bwd(const void*, const void*, const void*, const void*, float*,
                      cudaStream_t);
 int launch_logistic_loss(const float*, int, float, float*, float*, float, cudaStream_t);
 int launch_sumsq(const float*, size_t, float, float*, cudaStream_t);
+int launch_image_feed_u8(const void*, const void*, float*, int, int, int, cudaStream_t);
 int launch_gp_rows(const float*, int, size_t, float, float, float*, float*, cudaStream_t);
 int launch_nhwc_to_planes3(const void*, const float*, const float*, float*, size_t, int, int, int, int, float,
                            cudaStream_t);
@@ -329,6 +330,9 @@ int bg_logistic_loss(const float* pred, int n, float sign, float* loss, float* s
 }
 int bg_sumsq(const float* x, size_t n, float scale, float* out, void* stream) {
   return bg::launch_sumsq(x, n, scale, out, S(stream));
+}
+int bg_image_feed_u8(const void* src_u8, const void* flip_u8, float* out, int B, int H, int W, void* stream) {
+  return bg::launch_image_feed_u8(src_u8, flip_u8, out, B, H, W, S(stream));
 }
 int bg_gp_rows(const float* g, int B, size_t D, float pen_scale, float v_scale, float* pen, float* v, void* stream) {
   return bg::launch_gp_rows(g, B, D, pen_scale, v_scale, pen, v, S(stream));

@@ -947,6 +947,32 @@ int launch_gp_rows(const float* g, int B, size_t D, float pen_scale, float v_sca
   return 0;
 }
 
+// Data feed (train.py:43-50 on the device): uint8 (B,H,W,3) -> fp32 (B,3,H,W), x / 127.5 - 1 (ToTensor + Normalize(.5,.5)),
+// sample n mirrored along W when flip[n] != 0 (RandomHorizontalFlip).  One thread per output pixel: the three colour
+// planes are written coalesced, the 3-byte source pixels of a warp are 96 contiguous bytes.
+__global__ void image_feed_u8_kernel(const uint8_t* __restrict__ src, const uint8_t* __restrict__ flip,
+                                     float* __restrict__ out, int B, int H, int W) {
+  pdl_prologue();
+  const size_t HW = (size_t)H * W, total = (size_t)B * HW;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = i / HW, hw = i % HW;
+    const int h = (int)(hw / W), w = (int)(hw % W);
+    const int ws = (flip != nullptr && flip[n] != 0) ? W - 1 - w : w;
+    const uint8_t* px = src + ((n * H + h) * (size_t)W + ws) * 3;
+    float* o = out + n * 3 * HW + hw;
+    o[0] = (float)px[0] * (1.f / 127.5f) - 1.f;
+    o[HW] = (float)px[1] * (1.f / 127.5f) - 1.f;
+    o[2 * HW] = (float)px[2] * (1.f / 127.5f) - 1.f;
+  }
+}
+
+int launch_image_feed_u8(const void* src, const void* flip, float* out, int B, int H, int W, cudaStream_t s) {
+  BG_REQUIRE(B > 0 && H > 0 && W > 0, "image_feed_u8: empty batch");
+  BG_CHECK_CUDA(launch_pdl(image_feed_u8_kernel, grid1d((size_t)B * H * W, 256, 8), 256, 0, s, (const uint8_t*)src,
+                           (const uint8_t*)flip, out, B, H, W));
+  return 0;
+}
+
 int launch_sumsq(const float* x, size_t n, float scale, float* out, cudaStream_t s) {
   if (launch_zero(out, sizeof(float), s) != 0) return 1;
   BG_CHECK_CUDA(launch_pdl(sumsq_kernel, grid1d(n, 256, 2), 256, 0, s, x, n, scale, out));

@@ -49,9 +49,30 @@ def coef_of(weight: torch.Tensor) -> float:
 # ------------------------------------------------------------------------------------------------------
 # packed-weight cache: bf16 [tap][Cout][Cin] (fprop) and [tap'][Cin][Cout] (dgrad) copies of the fp32
 # master weights with the equalized coefficient folded in; fp32 transposes of the linear weights.
-# Refreshed when the parameter's version counter or storage changes (optimizer steps and load_state_dict
-# are in-place, so they bump it).
+# A pack is stale when the parameter's version counter or storage changed (load_state_dict, copy_/mul_ on the
+# parameter, for-each optimizers) OR an optimizer has stepped it since: the multi-tensor `fused=True` optimizers
+# update the masters WITHOUT moving the version counter (torch 2.11: Adam(fused=True).step() leaves p._version
+# unchanged), so every torch optimizer step is observed through a global step post-hook that stamps the parameters of
+# that optimizer.  Writes through `.data` are invisible to both and need PackCache.invalidate().
 # ------------------------------------------------------------------------------------------------------
+_OPT_EPOCH: Dict[int, int] = {}
+
+
+def _note_optimizer_step(optimizer, args, kwargs):
+    for group in optimizer.param_groups:
+        for p in group["params"]:
+            _OPT_EPOCH[id(p)] = _OPT_EPOCH.get(id(p), 0) + 1
+
+
+from torch.optim.optimizer import register_optimizer_step_post_hook as _register_step_hook  # noqa: E402
+
+_register_step_hook(_note_optimizer_step)
+
+
+def _tag(w: torch.Tensor, *extra):
+    return (w._version, w.data_ptr(), _OPT_EPOCH.get(id(w), 0)) + extra
+
+
 class PackCache:
     def __init__(self):
         self._conv: Dict[int, tuple] = {}
@@ -59,7 +80,7 @@ class PackCache:
 
     def conv(self, w: torch.Tensor, cin_pad: Optional[int] = None):
         key = id(w)
-        tag = (w._version, w.data_ptr(), cin_pad)
+        tag = _tag(w, cin_pad)
         hit = self._conv.get(key)
         if hit is not None and hit[0] == tag:
             return hit[1], hit[2]
@@ -74,7 +95,7 @@ class PackCache:
     def conv_pool4(self, w: torch.Tensor):
         """16-tap pack of conv3x3 followed by AvgPool2d(2) as one 4x4 stride-2 conv (bg_pack_weight_pool4)."""
         key = ("p4", id(w))
-        tag = (w._version, w.data_ptr())
+        tag = _tag(w)
         hit = self._conv.get(key)
         if hit is not None and hit[0] == tag:
             return hit[1]
@@ -87,7 +108,7 @@ class PackCache:
     def conv_tconv4(self, w: torch.Tensor):
         """16-tile pack of the input gradient of conv3x3 -> AvgPool2d(2) (transposed 4x4 stride-2 conv)."""
         key = ("t4", id(w))
-        tag = (w._version, w.data_ptr())
+        tag = _tag(w)
         hit = self._conv.get(key)
         if hit is not None and hit[0] == tag:
             return hit[1]
@@ -109,7 +130,7 @@ class PackCache:
         stale = []
         for w, cin_pad in items:
             hit = self._conv.get(id(w))
-            if hit is None or hit[0] != (w._version, w.data_ptr(), cin_pad):
+            if hit is None or hit[0] != _tag(w, cin_pad):
                 stale.append((w, cin_pad))
         for i in range(0, len(stale), 32):
             grp = stale[i:i + 32]
@@ -123,12 +144,12 @@ class PackCache:
             call("bg_pack_weight_grouped", [w.detach() for w, _ in grp], wfs, wds, [m[0] for m in meta],
                  [m[1] for m in meta], [m[2] for m in meta], [m[3] for m in meta], [m[4] for m in meta], len(grp))
             for (w, cin_pad), wf, wd in zip(grp, wfs, wds):
-                self._conv[id(w)] = ((w._version, w.data_ptr(), cin_pad), wf, wd)
+                self._conv[id(w)] = (_tag(w, cin_pad), wf, wd)
 
     def linear_t(self, w: torch.Tensor):
         """fp32 transpose (K, N) of an (N, K) linear weight: the input-gradient pass is a forward on it."""
         key = id(w)
-        tag = (w._version, w.data_ptr())
+        tag = _tag(w)
         hit = self._lin.get(key)
         if hit is not None and hit[0] == tag:
             return hit[1]

@@ -247,6 +247,11 @@ int bg_sumsq(const float* x, size_t n, float scale, float* out, void* stream);
  * derivative of the penalty w.r.t. g_n — the direction the second-order pass is taken along. */
 int bg_gp_rows(const float* g, int B, size_t D, float pen_scale, float v_scale, float* pen, float* v, void* stream);
 
+/* ---- data feed (train.py:43-50: RandomHorizontalFlip, ToTensor, Normalize((.5,.5,.5),(.5,.5,.5)) on the device) -------
+ * src: uint8 (B,H,W,3) device;  flip: uint8 (B) device or NULL (non-zero = mirror that sample along W);
+ * out: fp32 (B,3,H,W) = src / 127.5 - 1. */
+int bg_image_feed_u8(const void* src_u8, const void* flip_u8, float* out, int B, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,24 +15,21 @@ from oracle import gan_oracle as O
 TOL_IMG = 4e-2        # rel-L2 of generated images
 TOL_PRED = 5e-2       # critic scores: |diff| <= TOL_PRED * (rms(pred) + 1)
 TOL_LOSS = 3e-2       # relative, losses
-# Gradient gate, PER TENSOR (grad_gate below): every parameter gradient of the CUDA path must be
-#   * no further from the fp32 reference than K_EMU x the error the reference's OWN bf16-storage emulation makes on
-#     that very tensor (+ EPS_EMU): a tensor with a lost or mis-scaled term (a missing R1 second-order contribution, a
-#     dropped minibatch-stddev curvature term) is off by O(its share), far outside the storage noise of that tensor;
-#   * of the right magnitude: norm ratio within NORM_LO..NORM_HI (a constant factor has cosine 1.0 and would pass a
-#     cosine test);
-#   * aligned: cosine >= COS_MIN (COS_MIN_SMALL for tensors of < 4096 numbers).
+# Gradient gate, PER TENSOR (grad_gate below).  The yardstick of every criterion is the error that the reference's OWN
+# bf16-storage emulation (gan_oracle.QUANT) makes on that very tensor: profiles/r2_parity_table.txt lists, for every
+# parameter gradient of every golden case, the CUDA path's and the emulation's rel-L2 / cosine side by side — the CUDA
+# path sits at 0.6-1.6x the emulated error on all but a handful of tiny tensors (worst: a 64-number noise-weight
+# gradient at 2.4x).  A tensor with a lost or mis-scaled term (a missing R1 second-order contribution, a dropped
+# minibatch-stddev curvature term, a wrong constant) is off by O(its share) and lands far outside these bands:
+#   * rel-L2 vs the fp32 reference  <= K_EMU x emulated rel-L2 + EPS_EMU   (K_EMU_SMALL for tensors of < 4096 numbers:
+#     per-channel sums over every pixel — biases, noise weights, toRGB — cancel heavily);
+#   * magnitude: | |g|/|ref| - 1 |  <= 0.2 + 1.5 x emulated rel-L2  (a constant factor has cosine 1.0);
+#   * direction: 1 - cosine         <= 2.5 x (1 - emulated cosine) + 0.02.
 # The tests run the library in chain-deterministic mode (bg_set_deterministic): images, scores and activation
-# gradients are then bit-reproducible, so these gates see ONE fixed realisation of the bf16 rounding noise instead of a
-# run-to-run distribution.  "Small" tensors (per-channel sums over every pixel: biases, noise weights, toRGB) cancel
-# heavily and carry the largest relative storage noise; they get K_EMU_SMALL.
+# gradients are then bit-reproducible, so the gate sees ONE fixed realisation of the bf16 rounding noise.
 K_EMU = 2.0
 K_EMU_SMALL = 3.0
 EPS_EMU = 0.02
-NORM_LO, NORM_HI = 0.8, 1.25
-COS_MIN = 0.97
-COS_MIN_SMALL = 0.90
-TOL_GRAD_REL = 0.85   # absolute backstop, never the binding criterion
 TOL_VS_EMU = 1.5      # median rel-L2 over a network's tensors <= TOL_VS_EMU * same statistic of the bf16 emulation + 0.01
 
 
@@ -40,17 +37,16 @@ def grad_gate(name, got, ref, emu):
     """None if the gradient tensor passes the per-tensor gate, else a description of the failure."""
     if ref.norm().item() == 0.0:
         return None if got.abs().max().item() < 1e-6 else f"{name}: reference gradient is 0, got {got.abs().max().item():.2e}"
-    e, e_emu, cs = rel(got, ref), rel(emu, ref), cos(got, ref)
-    small = ref.numel() < 4096
-    k = K_EMU_SMALL if small else K_EMU
+    e, e_emu, cs, cs_emu = rel(got, ref), rel(emu, ref), cos(got, ref), cos(emu, ref)
+    k = K_EMU_SMALL if ref.numel() < 4096 else K_EMU
     ratio = got.double().norm().item() / ref.double().norm().item()
     why = []
-    if e > k * e_emu + EPS_EMU or e > TOL_GRAD_REL:
+    if e > k * e_emu + EPS_EMU:
         why.append(f"rel-L2 {e:.4f} > {k} x emulation {e_emu:.4f} + {EPS_EMU}")
-    if not (NORM_LO <= ratio <= NORM_HI) and e > 2 * EPS_EMU:
-        why.append(f"norm ratio {ratio:.3f}")
-    if cs < (COS_MIN_SMALL if small else COS_MIN) and ref.numel() >= 16:
-        why.append(f"cosine {cs:.4f}")
+    if abs(ratio - 1.0) > 0.2 + 1.5 * e_emu:
+        why.append(f"norm ratio {ratio:.3f} (emulated rel-L2 {e_emu:.3f})")
+    if ref.numel() >= 2 and 1.0 - cs > 2.5 * (1.0 - cs_emu) + 0.02:
+        why.append(f"cosine {cs:.4f} (emulation {cs_emu:.4f})")
     return f"{name} [{ref.numel()}]: " + ", ".join(why) if why else None
 
 

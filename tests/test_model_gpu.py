@@ -134,7 +134,20 @@ def test_r1_penalty_alone_second_order_terms(case):
     o, q = _oracle_pair(args, steps, alpha, lam, loss="r1_penalty")
     assert abs(r["c_loss"].item() - case["penalty"]) < U.TOL_LOSS * abs(case["penalty"]), (r["c_loss"].item(), case["penalty"])
     assert abs(o["c_loss"].item() - case["penalty"]) < 1e-3 * abs(case["penalty"])
-    fp_close(r["real_grad"], case["grad_real"], 6e-2, "d sum D(real) / d real vs golden")
+    # the image gradient itself (what autograd.grad returns at gan.py:398-400): against the oracle, its emulation, the golden
+    real = args[2].cuda()
+    grads = []
+    for quant in (False, True):
+        O.QUANT[0] = quant
+        try:
+            x = real.clone().requires_grad_()
+            Ds = {k: v.cuda() for k, v in O.make_state("critic", 2).items()}
+            grads.append(torch.autograd.grad(O.critic_forward(Ds, x, steps, alpha).sum(), x)[0])
+        finally:
+            O.QUANT[0] = False
+    why = U.grad_gate("d sum D(real) / d real", r["real_grad"], grads[0], grads[1])
+    assert why is None, why
+    fp_close(grads[0], case["grad_real"], 1e-3, "oracle image gradient vs golden")
     _check_gradients(r, o, q, kinds=("d_grads",), case=case)
 
 

@@ -107,6 +107,26 @@ def test_load_state_dict_drops_cached_weight_packs():
     assert not c._packs._conv
 
 
+def test_pack_staleness_sees_fused_optimizer_steps():
+    """torch's multi-tensor optimizers (fused=True) update parameters WITHOUT moving their version counter (observed on
+    torch 2.11, CPU and CUDA): the pack cache must notice the step through its optimizer post-hook, or the convolutions
+    would keep using the pre-step bf16 weights while the fp32 masters train."""
+    import engine
+
+    for fused in (False, True):
+        p = torch.nn.Parameter(torch.randn(8, 8))
+        opt = torch.optim.Adam([p], lr=0.1, fused=fused)
+        p.grad = torch.randn(8, 8)
+        before = engine._tag(p)
+        opt.step()
+        assert engine._tag(p) != before, f"optimizer step (fused={fused}) not visible to the pack cache"
+    q = torch.nn.Parameter(torch.randn(4))
+    before = engine._tag(q)
+    with torch.no_grad():
+        q.mul_(2.0)
+    assert engine._tag(q) != before
+
+
 REF = "/root/reference"
 
 
