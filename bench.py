@@ -168,6 +168,191 @@ def conv_flops(args):
     return 2.0 * n * h * w * ks * ks * ci * co
 
 
+FPROP_CALLS = ("bg_conv_fprop", "bg_conv_fprop_stats", "bg_conv_pool_fprop", "bg_conv_pool4_fprop", "bg_conv_pool4_dgrad",
+               "bg_conv_style_fprop")
+WGRAD_CALLS = ("bg_conv_wgrad", "bg_conv_pool4_wgrad")
+
+
+def conv_call_work(name, a):
+    """(credited flops, executed flops, algorithmic bytes) of one conv C-ABI call from its scalar arguments.
+    Credited = the reference formulation (a 3x3 conv at full resolution); executed = what the kernel
+    really multiplies: the folded conv+pool calls run 16 taps per POOLED pixel = 16/36 of the credited MACs."""
+    if name == "bg_conv_pool4_wgrad":          # N, Hp, Wp, Cin, Cout, accumulate
+        fl = conv_flops((a[0], 2 * a[1], 2 * a[2], a[3], a[4], 0))
+        return fl, fl * 16.0 / 36.0, 2.0 * a[0] * (a[3] * 4 * a[1] * a[2] + a[4] * a[1] * a[2])
+    if name == "bg_conv_pool4_dgrad":          # N, Hp, Wp, Cout, Cin -> the 3x3 dgrad at full resolution
+        fl = conv_flops((a[0], 2 * a[1], 2 * a[2], a[3], a[4], 3, 0, 0.0))
+        return fl, fl * 16.0 / 36.0, conv_bytes(name, a)
+    if name == "bg_conv_wgrad":
+        fl = conv_flops(a)
+        return fl, fl, 2.0 * a[0] * a[1] * a[2] * (a[3] + a[4])
+    fl = conv_flops(a if name not in ("bg_conv_pool_fprop", "bg_conv_pool4_fprop", "bg_conv_style_fprop") else a[:5] + (3, 0, 0.0))
+    return fl, (fl * 16.0 / 36.0 if name == "bg_conv_pool4_fprop" else fl), conv_bytes(name, a)
+
+
+def aux_call_bytes(name, a):
+    """Algorithmic HBM bytes of the fused norm / noise / resample / 1x1 helpers (one read of every input map, one write of
+    every output map; bf16 feature maps, fp32 image planes), or None for calls that are not map-sized streams."""
+    try:
+        if name in ("bg_adain_apply",):                       # N, HW, C, eps: read a, write x
+            return 2.0 * 2 * a[0] * a[1] * a[2]
+        if name == "bg_adain_bwd_reduce":                     # N, HW, C: read g, a
+            return 2.0 * 2 * a[0] * a[1] * a[2]
+        if name == "bg_adain_bwd_apply":                      # read g, a; write gpre
+            return 2.0 * 3 * a[0] * a[1] * a[2]
+        if name == "bg_in_stats":
+            return 2.0 * a[0] * a[1] * a[2]
+        if name in ("bg_upsample2x_fwd", "bg_upsample2x_bwd"):   # N, H, W, C of the SMALL map: small + 4x large
+            return 2.0 * 5 * a[0] * a[1] * a[2] * a[3]
+        if name == "bg_planes3_to_nhwc":                      # P, HW, C, ...: 3 fp32 planes in (or C planes), C bf16 out
+            return a[0] * (12.0 + 2.0 * a[2])
+        if name == "bg_nhwc_to_planes3":
+            return a[0] * (12.0 + 2.0 * a[2])
+        if name == "bg_to_rgb_adain":                         # N, HW, C
+            return a[0] * a[1] * (12.0 + 2.0 * a[2])
+        if name == "bg_channel_wsum":                         # P, C, HW, img_stride, plane_stride, nplanes
+            return a[0] * (2.0 * a[1] + 4.0 * a[5])
+        if name in ("bg_act_gate", "bg_axpby"):               # n elements: two maps in (gate: g, y), one out
+            return 2.0 * 3 * a[0]
+        if name == "bg_axpby_f32":
+            return 4.0 * 3 * a[0]
+        if name == "bg_pool_act_bwd":                         # N, Ho, Wo, C: read gy, y (pooled), write gu (4x)
+            return 2.0 * 6 * a[0] * a[1] * a[2] * a[3]
+        if name == "bg_pool_act_fwd":
+            return 2.0 * 5 * a[0] * a[1] * a[2] * a[3]
+        if name == "bg_style_modulate":                       # N, Cin, Cout, HW: fp32 W in, N bf16 packs out
+            return 9.0 * a[1] * a[2] * (4.0 + 2.0 * a[0])
+    except Exception:
+        return None
+    return None
+
+
+def roofline_from_calls(rec, workload, peaks, img_per_s_per_gpu, gflop_img, use_traffic_file):
+    """rec: [(C-ABI call, scalar args, ms)] of ONE iteration, each timed with a CUDA-event pair on the launching stream."""
+    fam = {}
+    dom = {"n": 0, "ms": 0.0, "flops": 0.0, "exec": 0.0, "bytes": 0.0}
+    wg = {"ms": 0.0, "flops": 0.0, "exec": 0.0}
+    aux = {}
+    for name, a, t in rec:
+        f = fam.setdefault(name, [0, 0.0])
+        f[0] += 1
+        f[1] += t
+        if name in FPROP_CALLS or name in WGRAD_CALLS:
+            fl, ex, by = conv_call_work(name, a)
+            tgt = dom if name in FPROP_CALLS else wg
+            tgt["ms"] += t
+            tgt["flops"] += fl
+            tgt["exec"] += ex
+            if name in FPROP_CALLS:
+                dom["n"] += 1
+                dom["bytes"] += by
+        else:
+            by = aux_call_bytes(name, a)
+            if by is not None and t >= 0.015:                 # below ~15 us an event pair mostly times the launch itself
+                e = aux.setdefault((name, a), [0, 0.0, by])
+                e[0] += 1
+                e[1] += t
+    tot_ms = sum(v[1] for v in fam.values())
+    dom["ms"] = max(dom["ms"], 1e-9)
+    tf = dom["flops"] / (dom["ms"] / 1e3) / 1e12 if dom["n"] else 0.0
+    tf_exec = dom["exec"] / (dom["ms"] / 1e3) / 1e12 if dom["n"] else 0.0
+    gbs = dom["bytes"] / (dom["ms"] / 1e3) / 1e9 if dom["n"] else 0.0
+    shares = {k: round(v[1] / tot_ms, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1][1])[:8]}
+    traffic = None
+    if use_traffic_file:
+        for fn in ("r2_dram_traffic_fprop_family_train256.json", "r1_dram_traffic_fprop_family_train256.json"):
+            try:
+                with open(os.path.join(ROOT, "profiles", fn)) as f:
+                    tj = json.load(f)
+                traffic = tj["dram_read_bytes"] + tj["dram_write_bytes"]
+                break
+            except Exception:
+                continue
+    bound = BOUND.get(workload, "tensor")
+    kernel = ("conv_halo_kernel / conv_fprop_kernel (tcgen05 implicit GEMM: fprop, dgrad, R1 tangent pass, fused pool / "
+              "IN-stats / bias-grad epilogues)")
+    common = {"kernel": kernel, "bound": bound, "traffic": traffic,
+              "traffic_note": "DRAM read+write bytes of ALL launches of this kernel family in one iteration (ncu capture under "
+                              "profiles/); algorithmic_bytes is the same sum of 2*N*(Cin*Hin*Win+Cout*Hout*Wout)",
+              "algorithmic_bytes": dom["bytes"], "algorithmic_flops": dom["flops"], "executed_flops": dom["exec"],
+              "launches_per_step": dom["n"], "share_of_step": round(dom["ms"] / tot_ms, 4)}
+    if bound == "hbm":
+        # the dominant layers of this workload have <= 32 channels: below the 216 flop/B ridge (SURVEY.md §8a)
+        roofline = dict(common, achieved=round(gbs, 1), peak=peaks["hbm"], unit="GB/s", frac=round(gbs / peaks["hbm"], 4),
+                        peak_source=peaks["src"] + ", copy bandwidth",
+                        tensor_tflops=round(tf, 1), tensor_frac=round(tf / peaks["tf_sustained"], 4))
+    else:
+        roofline = dict(common, achieved=round(tf, 1), peak=peaks["tf_sustained"], unit="TFLOP/s",
+                        frac=round(tf / peaks["tf_sustained"], 4),
+                        frac_note="reference-formulation FLOPs (the folded conv+pool launches are credited with the 3x3 "
+                                  "count they replace, SURVEY.md §8d); executed_frac counts the MACs really issued",
+                        executed_tflops=round(tf_exec, 1), executed_frac=round(tf_exec / peaks["tf_sustained"], 4),
+                        hbm_gbs=round(gbs, 1),
+                        peak_source=peaks["src"] + ", sustained bf16 (kernel timed inside a long step)")
+    roofline["wgrad_tflops"] = round(wg["flops"] / (wg["ms"] / 1e3) / 1e12, 1) if wg["ms"] > 0 else None
+    roofline["wgrad_executed_tflops"] = round(wg["exec"] / (wg["ms"] / 1e3) / 1e12, 1) if wg["ms"] > 0 else None
+    roofline["wgrad_share_of_step"] = round(wg["ms"] / tot_ms, 4)
+    roofline["step_share_by_call"] = shares
+    roofline["step_model_flops_frac"] = round(img_per_s_per_gpu * gflop_img * 1e9 / (peaks["tf_sustained"] * 1e12), 4)
+    # achieved GB/s of the HBM-bound helpers (the fused norm / noise / resample / 1x1 paths), worst first by lost time
+    rows = []
+    for (name, a), (cnt, ms_sum, by) in aux.items():
+        g = by * cnt / (ms_sum / 1e3) / 1e9
+        rows.append({"call": name, "args": list(a[:6]), "launches": cnt, "us": round(ms_sum / cnt * 1e3, 1),
+                     "GB/s": round(g, 1), "frac_of_hbm": round(g / peaks["hbm"], 3),
+                     "lost_us": round(max(0.0, ms_sum * 1e3 - by * cnt / (peaks["hbm"] * 1e9) * 1e6), 1)})
+    rows.sort(key=lambda r: -r["lost_us"])
+    aux_table = {"peak_GB/s": peaks["hbm"], "share_of_step": round(sum(v[1] for v in aux.values()) / tot_ms, 4),
+                 "worst": rows[0] if rows else None, "top": rows[:10],
+                 "note": "per C-ABI call, CUDA events on the launching stream inside the step; bytes = one read of each "
+                         "input map + one write of each output map"}
+    return roofline, aux_table
+
+
+def workload_config(workload, world, style_mixing, batch=None):
+    """The `config` object of the JSON line — built by ONE function so both arms print the same one."""
+    steps, alpha, b, _, desc = WORKLOADS[workload]
+    b = batch or b
+    return {"workload": f"{workload}: {desc}", "resolution": 4 * 2 ** (steps - 1), "progressive_steps": steps, "alpha": alpha,
+            "batch_per_gpu": b, "global_batch": b * world, "parallelism": f"dp{world}",
+            "style_mixing": bool(style_mixing),
+            "optimizer": "Adam(lr=0.002, betas=(0,0.99)), both updates inside the step",
+            "loss": "non-saturating logistic + R1 (lambda=10) with double-backward every step",
+            "l2_policy": "inputs rotate over 4 batches; per-step working set (GBs of activations) >> 126 MB L2"}
+
+
+def metric_name(workload):
+    return "G+D train img/s at 256x256" if workload == "train256" else f"G+D train img/s ({workload})"
+
+
+def torch_gpu_leg(workload, batch, device, iters=3):
+    """The reference's arithmetic on THIS GPU: the oracle (plain torch ops, i.e. cuDNN / cuBLAS kernels, fp32 with torch's
+    default TF32 convolution setting, autograd incl. create_graph double-backward) running the same iteration at the
+    workload's real batch.  The checker timed as a side note: it answers 'what would unmodified PyTorch code
+    reach on the same device', which the CPU arm cannot."""
+    from oracle import gan_oracle as O
+
+    steps, alpha, _, gflop_img, _ = WORKLOADS[workload]
+    try:
+        G, D = O.make_state("gen", 0), O.make_state("critic", 0)
+        args = (O.make_latents(batch, 1), O.make_latents(batch, 2), O.make_images(batch, steps, 3),
+                O.make_noise(batch, steps, 4), O.make_noise(batch, steps, 5))
+        O.train_iteration(G, D, *args, steps, alpha, LAMBDA, device=device)           # warm-up (cuDNN autotune)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            O.train_iteration(G, D, *args, steps, alpha, LAMBDA, device=device)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / iters
+        out = {"value": round(batch / dt, 1), "unit": "img/s", "ms_per_step": round(dt * 1e3, 1), "batch": batch,
+               "kind": "oracle port on the GPU (torch/cuDNN fp32, TF32 convolutions at torch's default, Adam excluded, "
+                       "state re-uploaded every iteration)"}
+    except Exception as e:  # noqa: BLE001 - a side note must never fail the bench
+        out = {"unavailable": f"{type(e).__name__}: {str(e)[:120]}"}
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_b200(args):
     import bg_native as bgn
     import dist as bdist
@@ -182,8 +367,8 @@ def run_b200(args):
     if args.batch:
         batch = args.batch
     R = 4 * 2 ** (steps - 1)
-    tr = Trainer(steps, alpha, batch, device, bdist.GradSync)
-    tr.style_mixing = bool(args.style_mixing)
+    style_mixing = (args.workload in STYLE_MIXING_DEFAULT) if args.style_mixing is None else bool(args.style_mixing)
+    tr = make_trainer(steps, alpha, batch, device, style_mixing)
     g = torch.Generator(device="cpu").manual_seed(1234 + rank)
     POOL = 4
     host_real = [torch.rand(batch, 3, R, R, generator=g).mul_(2).sub_(1).pin_memory() for _ in range(POOL)]
@@ -272,6 +457,16 @@ def run_b200(args):
     clocks.window(w0, time.time())
     launches = (bgn.launch_count - n0) // REPEATS
     clk = clocks.stop() if rank == 0 else None
+    parity_variant = None
+    if style_mixing:
+        tr.style_mixing = False
+        timed(2, from_host=False)
+        pv = sorted(timed(args.steps, from_host=False) for _ in range(3))[1]
+        parity_variant = {"style_mixing": False, "value": round(batch * world * args.steps / (pv / 1e3), 2), "unit": "img/s",
+                          "ms_per_step": round(pv / args.steps, 3),
+                          "note": "same workload exactly as the reference's Generator.forward runs it (one latent); this is "
+                                  "the variant the parity tests and the reference arm cover"}
+        tr.style_mixing = True
     timed(1, from_host=True)
     reps_e2e = [timed(args.steps, from_host=True) for _ in range(REPEATS)]
     ms, ms_e2e = sorted(reps)[REPEATS // 2], sorted(reps_e2e)[REPEATS // 2]
@@ -285,57 +480,8 @@ def run_b200(args):
     bgn.start_timing()
     tr.iteration(dev_real[0].clone(), dev_z[0][0].clone(), dev_z[0][1].clone(), read_losses=False)
     rec = bgn.stop_timing()
-    fam = {}
-    # one kernel family (conv_halo_kernel / conv_fprop_kernel)
-    FPROP = ("bg_conv_fprop", "bg_conv_fprop_stats", "bg_conv_pool_fprop", "bg_conv_pool4_fprop", "bg_conv_pool4_dgrad",
-             "bg_conv_style_fprop")
-    dom = [0, 0.0, 0.0, 0.0]
-    for name, a, t in rec:
-        f = fam.setdefault(name, [0, 0.0, 0.0])
-        f[0] += 1
-        f[1] += t
-        if name == "bg_conv_pool4_wgrad":          # args N, Hp, Wp, Cin, Cout: credited as the 3x3 wgrad at full resolution
-            f[2] += conv_flops((a[0], 2 * a[1], 2 * a[2], a[3], a[4], 0))
-        if name in FPROP or name == "bg_conv_wgrad":
-            # reference-formulation FLOPs: the pool4 kernel executes conv3x3+avgpool as a 4x4 stride-2 conv with 2.25x
-            # fewer MACs, but is credited with the 3x3 count like every other launch
-            if name == "bg_conv_pool4_dgrad":        # args: N, Hp, Wp, Cout, Cin -> the 3x3 dgrad at full resolution
-                fl = conv_flops((a[0], 2 * a[1], 2 * a[2], a[3], a[4], 3, 0, 0.0))
-            else:
-                fl = conv_flops(a if name not in ("bg_conv_pool_fprop", "bg_conv_pool4_fprop", "bg_conv_style_fprop")
-                                else a[:5] + (3, 0, 0.0))
-            f[2] += fl
-            if name in FPROP:
-                dom[0] += 1
-                dom[1] += t
-                dom[2] += fl
-                dom[3] += conv_bytes(name, a)
-    tot_ms = sum(v[1] for v in fam.values())
-    dom[1] = max(dom[1], 1e-9)
-    achieved = dom[2] / (dom[1] / 1e3) / 1e12 if dom[0] else 0.0
-    shares = {k: round(v[1] / tot_ms, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1][1])[:8]}
-    traffic = None
-    try:
-        if args.workload == "train256" and not args.batch:
-            with open(os.path.join(ROOT, "profiles", "r1_dram_traffic_fprop_family_train256.json")) as f:
-                tj = json.load(f)
-            traffic = tj["dram_read_bytes"] + tj["dram_write_bytes"]
-    except Exception:
-        traffic = None
-    roofline = {"kernel": "conv_halo_kernel / conv_fprop_kernel (tcgen05 implicit GEMM: fprop, dgrad, R1 tangent pass, fused pool / IN-stats / bias-grad epilogues)", "bound": "tensor",
-                "achieved": round(achieved, 1), "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                "frac": round(achieved / peaks["tf_sustained"], 4), "traffic": traffic,
-                "traffic_note": "DRAM read+write bytes of ALL launches of this kernel family in one iteration (ncu, "
-                                "profiles/r1_dram_traffic_fprop_family_train256.json); algorithmic_bytes is the same sum "
-                                "of 2*N*(Cin*Hin*Win+Cout*Hout*Wout)",
-                "algorithmic_bytes": dom[3], "algorithmic_flops": dom[2],
-                "peak_source": peaks["src"] + ", sustained bf16 (kernel timed inside a long step)",
-                "launches_per_step": dom[0], "share_of_step": round(dom[1] / tot_ms, 4),
-                "wgrad_tflops": round(sum(fam[k][2] for k in ("bg_conv_wgrad", "bg_conv_pool4_wgrad") if k in fam) /
-                                      (sum(fam[k][1] for k in ("bg_conv_wgrad", "bg_conv_pool4_wgrad") if k in fam) / 1e3)
-                                      / 1e12, 1) if "bg_conv_wgrad" in fam else None,
-                "step_share_by_call": shares,
-                "step_model_flops_frac": round(value / world * gflop_img * 1e9 / (peaks["tf_sustained"] * 1e12), 4)}
+    roofline, aux_table = roofline_from_calls(rec, args.workload, peaks, value / world, gflop_img,
+                                              use_traffic_file=(args.workload == "train256" and not args.batch))
 
     # replicas must still hold identical parameters after all those averaged updates (outside every timed region)
     replica_diff = None
@@ -354,25 +500,24 @@ def run_b200(args):
         del tr.critic
         torch.cuda.empty_cache()
         sampling = sampling_leg(device, gen=tr.gen)
-    cpu = None
+    cpu = torch_gpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_leg(args.workload, max_seconds=40.0, steps_cap=1)
+        del tr
+        torch.cuda.empty_cache()
+        torch_gpu = torch_gpu_leg(args.workload, batch, device)
+        cpu = cpu_leg(args.workload, max_seconds=40.0, steps_cap=3, warmup=1)
 
     if rank == 0:
         h2d = host_real[0].numel() * 4 + host_z[0].numel() * 4
         line = {
-            "metric": "G+D train img/s at 256x256" if args.workload == "train256" else f"G+D train img/s ({args.workload})",
+            "metric": metric_name(args.workload),
             "value": round(value, 2), "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "warmup_extra_settle_steps": extra,
             "timed_regions_ms_per_step": {"value": [round(t / args.steps, 3) for t in reps],
                                           "e2e": [round(t / args.steps, 3) for t in reps_e2e], "reported": "median"},
             "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {desc}", "resolution": R, "progressive_steps": steps, "alpha": alpha,
-                       "batch_per_gpu": batch, "global_batch": batch * world, "parallelism": f"dp{world}",
-                       "style_mixing": bool(args.style_mixing),
-                       "optimizer": "Adam(lr=0.002, betas=(0,0.99)), both updates inside the step",
-                       "loss": "non-saturating logistic + R1 (lambda=10) with double-backward every step",
-                       "l2_policy": "inputs rotate over 4 batches; per-step working set (GBs of activations) >> 126 MB L2"},
+            "config": workload_config(args.workload, world, style_mixing, args.batch or None),
+            "parity_variant": parity_variant,
             "clocks": clk,
             "e2e": {"value": round(e2e_value, 2), "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8, "loss_readback": "both losses copied to pinned host memory every step, consumed one step later (no queue drain)",
                     "input_feed": "each step's images + latents copied from pinned host memory inside the timed region, "
@@ -380,7 +525,9 @@ def run_b200(args):
                     "ms_per_step": round(ms_e2e / args.steps, 3)},
             "gpu_launches": launches,
             "roofline": roofline,
+            "aux_kernels": aux_table,
             "cpu_baseline": cpu,
+            "torch_gpu_baseline": torch_gpu,
             "sampling_512": sampling,
             "replicas_max_abs_param_diff": replica_diff,
             "grad_allreduce_bytes_per_step": allreduce_bytes_per_step if world > 1 else 0,
@@ -452,7 +599,31 @@ def sampling_leg(device, batch=256, steps=8, iters=3, warmup=2, gen=None):
     ms_e2e = sorted(run(iters, True) for _ in range(3))[1]
     peaks = load_peaks()
     v = batch * iters / (ms / 1e3)
-    return {"metric": "generate img/s at 512x512", "value": round(v, 1), "unit": "img/s", "batch": batch, "iters": iters,
+    # roofline of the sampling batch: every C-ABI call of one more batch timed with CUDA events on the launching stream
+    import bg_native as bgn
+
+    torch.cuda.synchronize()
+    bgn.start_timing()
+    with torch.no_grad():
+        gen(dev_z[0], steps=steps, alpha=None)
+    rec = bgn.stop_timing()
+    conv_ms = sum(t for n, a, t in rec if n in FPROP_CALLS)
+    conv_by = sum(conv_call_work(n, a)[2] for n, a, t in rec if n in FPROP_CALLS)
+    conv_fl = sum(conv_call_work(n, a)[0] for n, a, t in rec if n in FPROP_CALLS)
+    tot = sum(t for _, _, t in rec)
+    gbs = conv_by / (max(conv_ms, 1e-9) / 1e3) / 1e9
+    s_roof = {"kernel": "conv_halo_kernel fused style / upsample forms (bg_conv_style_fprop) + small-map convs",
+              "bound": "hbm", "achieved": round(gbs, 1), "peak": peaks["hbm"], "unit": "GB/s",
+              "frac": round(gbs / peaks["hbm"], 4), "traffic": None,
+              "algorithmic_bytes": conv_by, "share_of_batch": round(conv_ms / max(tot, 1e-9), 4),
+              "tensor_tflops": round(conv_fl / (max(conv_ms, 1e-9) / 1e3) / 1e12, 1),
+              "note": "the 256x256 / 512x512 layers (16-64 channels) that dominate the batch are below the 216 flop/B ridge "
+                      "(SURVEY.md §8a); bytes = 2*N*(Cin*Hin*Win + Cout*H*W) per conv, upsampled inputs counted at low "
+                      "resolution",
+              "step_share_by_call": {k: round(sum(t for n, _, t in rec if n == k) / max(tot, 1e-9), 4)
+                                     for k in sorted({n for n, _, _ in rec},
+                                                     key=lambda k: -sum(t for n, _, t in rec if n == k))[:6]}}
+    return {"metric": "generate img/s at 512x512", "roofline": s_roof, "value": round(v, 1), "unit": "img/s", "batch": batch, "iters": iters,
             "ms_per_batch": round(ms / iters, 2),
             "e2e": {"value": round(batch * iters / (ms_e2e / 1e3), 1), "unit": "img/s",
                     "h2d_bytes_per_step": batch * 512 * 4, "d2h_bytes_per_step": batch * 3 * R * R * 4},
@@ -469,7 +640,9 @@ def cpu_leg(workload, max_seconds, steps_cap, warmup=0):
     steps, alpha, _, gflop_img, _ = WORKLOADS[workload]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    batch = 4                                   # smallest batch the minibatch-stddev groups allow (gan.py:269)
+    # config 1 (4x4) runs in full on the CPU; the others at the smallest batch the minibatch-stddev groups allow
+    # (gan.py:269; img/s is batch-insensitive on the CPU)
+    batch = WORKLOADS[workload][2] if workload == "train4" else 4
     G, D = O.make_state("gen", 0), O.make_state("critic", 0)
     done, t_total = 0, 0.0
     for i in range(warmup + steps_cap):
@@ -484,8 +657,9 @@ def cpu_leg(workload, max_seconds, steps_cap, warmup=0):
         if t_total > max_seconds:
             break
     return {"value": round(batch * done / t_total, 3), "unit": "img/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{done} iteration(s) of the same workload at batch {batch} (fp32, torch CPU, {cores} host threads; "
-                      f"forward+R1 double-backward+G backward, Adam excluded)",
+            "batch": batch, "iterations": done, "warmup_iterations": warmup, "ms_per_iteration": round(t_total / done * 1e3, 1),
+            "sample": f"{done} timed iteration(s) after {warmup} warm-up of the same workload at batch {batch} (fp32, torch "
+                      f"CPU, {cores} host threads; forward+R1 double-backward+G backward, Adam excluded)",
             "gflops": round(batch * done * gflop_img / t_total, 1)}
 
 
@@ -493,16 +667,18 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, alpha, batch, gflop_img, desc = WORKLOADS[args.workload]
-    cpu = cpu_leg(args.workload, max_seconds=240.0, steps_cap=max(1, args.steps), warmup=min(args.warmup, 1))
-    R = 4 * 2 ** (steps - 1)
-    line = {"impl": "reference",
-            "metric": "G+D train img/s at 256x256" if args.workload == "train256" else f"G+D train img/s ({args.workload})",
+    cpu = cpu_leg(args.workload, max_seconds=240.0, steps_cap=max(1, args.steps), warmup=max(1, min(args.warmup, 1)))
+    style_mixing = (args.workload in STYLE_MIXING_DEFAULT) if args.style_mixing is None else bool(args.style_mixing)
+    line = {"impl": "reference", "metric": metric_name(args.workload),
             "value": cpu["value"], "unit": "img/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(4 / cpu["value"] * 1e3, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {desc}", "resolution": R, "progressive_steps": steps, "alpha": alpha,
-                       "batch_per_gpu": batch},
+            # one "step" of this arm is one iteration of the bounded sample: the SAME workload at batch `sample_batch`
+            "ms_per_step": cpu["ms_per_iteration"], "sample_batch": cpu["batch"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.workload, max(1, args.gpus), style_mixing, args.batch or None),
+            "note": "the reference's CPU path (oracle port of gan.py / train.py:135-217, pinned to the real gan.py by "
+                    "tests/golden) on this box's host cores, one process whatever --gpus says; a bounded sample of the "
+                    "configured workload at batch `sample_batch` (img/s is batch-insensitive on the CPU); the reference "
+                    "has no style mixing, so the sample runs Generator.forward as the reference defines it",
             "cpu_baseline": cpu,
             "e2e": {"value": cpu["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -536,8 +712,10 @@ def main():
     ap.add_argument("--workload", default="train256", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (debugging only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--style-mixing", action="store_true",
-                    help="train with the opt-in style-mixing extension (two latents, per-step crossover)")
+    ap.add_argument("--style-mixing", dest="style_mixing", action="store_true", default=None,
+                    help="train with the style-mixing extension (two latents, per-step crossover); default: on for train256 "
+                         "(BASELINE configs[2] names it), off elsewhere")
+    ap.add_argument("--no-style-mixing", dest="style_mixing", action="store_false")
     ap.add_argument("--no-sampling", action="store_true", help="skip the 512x512 sampling leg")
     args = ap.parse_args()
     if args.impl == "reference":
