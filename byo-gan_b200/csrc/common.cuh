@@ -223,6 +223,77 @@ __device__ __forceinline__ void tc_mma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo,
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ----------------------------------------------------------------------------------------
+// CTA pair (cta_group::2): two CTAs of a 2-CTA cluster run ONE M=256 tcgen05.mma — each supplies its own 128 rows of A
+// and HALF of the B tile from its shared memory, the accumulator rows of each CTA land in its own TMEM.  Only the
+// leader (cluster rank 0) issues; TMA loads of both CTAs complete on the LEADER's mbarriers, tcgen05.commit multicasts
+// its arrive to the same barrier offset in both CTAs.
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the object at shared::cta address `local_addr` in CTA `cta` of this cluster
+__device__ __forceinline__ uint32_t mapa_cta(uint32_t local_addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are counted on a barrier given by its shared::cluster address (the leader's)
+__device__ __forceinline__ void tma_load_4d_2sm(const CUtensorMap* m, uint32_t bar_cluster_addr, void* dst, int c0, int c1,
+                                                int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+// arrives (once every tcgen05.mma issued so far by this thread has retired) on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void tc_commit2(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <bool CTA2>
+__device__ __forceinline__ void tc_mma_g(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (CTA2) tc_mma_bf16_2(d_tmem, adesc, bdesc, idesc, accumulate);
+  else tc_mma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
+}
+template <bool CTA2>
+__device__ __forceinline__ void tc_commit_g(uint64_t* bar) {
+  if (CTA2) tc_commit2(bar);
+  else tc_commit(bar);
+}
+
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 D.
 __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
   uint32_t d = 0;
@@ -273,22 +344,32 @@ __device__ __forceinline__ void pdl_prologue() {
 bool pdl_enabled();   // runtime.cu: BG_PDL=0 turns the launch attribute off (the device-side instructions become no-ops)
 
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                              Args&&... args) {
+inline cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                      int cluster_x, Args&&... args) {
   return [&](KArgs... a) {
     void* pargs[] = {(void*)&a...};
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = (unsigned)cluster_x;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = cluster_x > 1 ? 2 : 1;
     return cudaLaunchKernelExC(&cfg, (const void*)kernel, pargs);
   }(static_cast<Args&&>(args)...);
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  return launch_pdl_cluster(kernel, grid, block, smem, stream, 1, static_cast<Args&&>(args)...);
 }
 
 // memset replacement that stays inside the programmatic launch chain (a cudaMemsetAsync node between two kernels

@@ -106,20 +106,34 @@ struct HaloParams {
   int taps;       // 9, or 16 in pool4 mode
   int Hin, Win;
   uint32_t phase_bytes;
+  // CTA pair mode (wide layers, block_n = 128): the two CTAs of a 2-CTA cluster work on two horizontally adjacent
+  // tiles with the same weights; every tcgen05.mma is ONE M=256 cta_group::2 instruction issued by the leader CTA
+  // (rows 0..127 = this half of the leader's tile, rows 128..255 = the same half of the peer's), and each CTA keeps only
+  // HALF of the weight tile (block_n / 2 rows) in shared memory: per instruction an SM reads A 4 KB + B 2 KB instead of
+  // 4 + 4 KB, which takes the operand fetch off the 128 B/clk shared-memory limit that N = 128 sits on.
+  // b_tx_bytes / b_tile_bytes describe the per-CTA half tile.  Tile indices handed to decode_tile are PAIR indices.
+  int cta2;
 };
 
 struct TileCoord {
   int w0, h0, n, co0, ph;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const HaloParams& p, int tile) {
+__device__ __forceinline__ TileCoord decode_tile(const HaloParams& p, int tile, uint32_t crank = 0) {
   TileCoord t;
   const int nb = tile & ((1 << p.nb_shift) - 1);
   int pt = tile >> p.nb_shift;
   t.ph = pt & ((1 << p.ph_shift) - 1);
   pt >>= p.ph_shift;
-  t.w0 = (pt & ((1 << p.tw_shift) - 1)) * kTile;
-  pt >>= p.tw_shift;
+  if (p.cta2) {
+    // pair index: the pair covers tile columns 2j (leader) and 2j + 1 (peer) of the same tile row, n-block and sample
+    const int tws = p.tw_shift - 1;
+    t.w0 = (((pt & ((1 << tws) - 1)) << 1) + (int)crank) * kTile;
+    pt >>= tws;
+  } else {
+    t.w0 = (pt & ((1 << p.tw_shift) - 1)) * kTile;
+    pt >>= p.tw_shift;
+  }
   t.h0 = (pt & ((1 << p.th_shift) - 1)) * kTile;
   t.n = pt >> p.th_shift;
   t.co0 = nb * p.block_n;
@@ -130,14 +144,18 @@ __device__ __forceinline__ TileCoord decode_tile(const HaloParams& p, int tile) 
 // the epilogue can keep per-sample reductions in registers across tiles.  contig = 0: tiles are dealt round-robin,
 // so that at any moment the 148 CTAs work on 148 neighbouring tiles (best L2 / DRAM-page locality).
 __device__ __forceinline__ void tile_range(const HaloParams& p, int& t0, int& t1, int& step) {
+  // pair mode: the unit of work is a tile PAIR and the unit of the grid a CTA pair (both CTAs walk the same sequence)
+  const int bid = p.cta2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int nblk = p.cta2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int ntiles = p.cta2 ? p.num_tiles >> 1 : p.num_tiles;
   if (p.contig) {
-    t0 = (int)(((long long)p.num_tiles * (long long)blockIdx.x) / (long long)gridDim.x);
-    t1 = (int)(((long long)p.num_tiles * (long long)(blockIdx.x + 1)) / (long long)gridDim.x);
+    t0 = (int)(((long long)ntiles * (long long)bid) / (long long)nblk);
+    t1 = (int)(((long long)ntiles * (long long)(bid + 1)) / (long long)nblk);
     step = 1;
   } else {
-    t0 = blockIdx.x;
-    t1 = p.num_tiles;
-    step = gridDim.x;
+    t0 = bid;
+    t1 = ntiles;
+    step = nblk;
   }
 }
 
@@ -190,13 +208,13 @@ __device__ __forceinline__ uint64_t a_tap_offset(int tap, uint32_t phase_units) 
 __device__ __forceinline__ int pool4_tap(int ph, int t4) { return ((ph >> 1) + 2 * (t4 >> 1)) * 4 + (ph & 1) + 2 * (t4 & 1); }
 
 // HSEL: -1 = this thread issues both M=128 halves of the tile, 0 / 1 = only that half (two issuing warps)
-template <int KSTEPS, int HSEL>
+template <int KSTEPS, int HSEL, bool CTA2>
 __device__ __forceinline__ void mma_issue_loop_pool4(const HaloParams& p, uint8_t* a_base, uint8_t* b_base,
                                                      uint64_t* b_full, uint64_t* b_empty, uint64_t* a_full,
                                                      uint64_t* a_empty, uint64_t* tmem_full, uint64_t* tmem_empty,
                                                      uint32_t tmem_base) {
   constexpr uint32_t kRBU = 2u * KSTEPS;
-  const uint32_t idesc = umma_idesc_bf16(128, p.block_n, 0, 0);
+  const uint32_t idesc = umma_idesc_bf16(CTA2 ? 256 : 128, p.block_n, 0, 0);
   const uint64_t a_desc0 = umma_desc(smem_u32(a_base), 16u, p.a_sbo, p.a_layout);
   const uint64_t b_desc0 = umma_desc(smem_u32(b_base), 16u, p.b_sbo, p.b_layout);
   const uint32_t a_stage_step = p.a_stage_bytes >> 4;
@@ -228,11 +246,11 @@ __device__ __forceinline__ void mma_issue_loop_pool4(const HaloParams& p, uint8_
               for (int k = 0; k < KSTEPS; ++k) {
 #pragma unroll
                 for (int half = (HSEL < 0 ? 0 : HSEL); half < (HSEL < 0 ? 2 : HSEL + 1); ++half)
-                  tc_mma_bf16(d_tmem + (uint32_t)half * 128u, a_tap + (uint64_t)(half * 8 * kRBU + k * 2),
+                  tc_mma_g<CTA2>(d_tmem + (uint32_t)half * 128u, a_tap + (uint64_t)(half * 8 * kRBU + k * 2),
                               b_tap + (uint64_t)(k * 2), idesc, k == 0 ? accum : 1u);
               }
             }
-            tc_commit(&b_empty[bstage]);
+            tc_commit_g<CTA2>(&b_empty[bstage]);
           }
           accum = 1u;
           if (++bstage == p.b_stages) {
@@ -240,7 +258,7 @@ __device__ __forceinline__ void mma_issue_loop_pool4(const HaloParams& p, uint8_
             bphase ^= 1u;
           }
         }
-        if (leader) tc_commit(&a_empty[astage]);
+        if (leader) tc_commit_g<CTA2>(&a_empty[astage]);
         __syncwarp();
         if (++astage == p.a_stages) {
           astage = 0;
@@ -248,18 +266,18 @@ __device__ __forceinline__ void mma_issue_loop_pool4(const HaloParams& p, uint8_
         }
       }
     }
-    if (leader) tc_commit(&tmem_full[acc]);
+    if (leader) tc_commit_g<CTA2>(&tmem_full[acc]);
     __syncwarp();
     acc ^= 1;
     if (acc == 0) acc_phase ^= 1u;
   }
 }
 
-template <int KSTEPS, int TAPS, int HSEL>
+template <int KSTEPS, int TAPS, int HSEL, bool CTA2>
 __device__ __forceinline__ void mma_issue_loop(const HaloParams& p, uint8_t* a_base, uint8_t* b_base, uint64_t* b_full,
                                                uint64_t* b_empty, uint64_t* a_full, uint64_t* a_empty,
                                                uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base) {
-  const uint32_t idesc = umma_idesc_bf16(128, p.block_n, 0, 0);
+  const uint32_t idesc = umma_idesc_bf16(CTA2 ? 256 : 128, p.block_n, 0, 0);
   constexpr uint32_t kRBU = 2u * KSTEPS;                       // one pixel row (kc bf16) in 16-byte units
   const uint64_t a_desc0 = umma_desc(smem_u32(a_base), 16u, p.a_sbo, p.a_layout);
   const uint64_t b_desc0 = umma_desc(smem_u32(b_base), 16u, p.b_sbo, p.b_layout);
@@ -281,7 +299,7 @@ __device__ __forceinline__ void mma_issue_loop(const HaloParams& p, uint8_t* a_b
     if (p.b_resident) {
       const int wn = p.per_sample_w ? decode_tile(p, tile).n : 0;
       if (wn != w_cur) {                      // first tile, or the tile range moved on to another sample's pack
-        if (w_loads > 0 && leader) tc_commit(&b_empty[0]);
+        if (w_loads > 0 && leader) tc_commit_g<CTA2>(&b_empty[0]);
         __syncwarp();
         mbar_wait(&b_full[0], w_loads & 1u);
         tc_fence_after();
@@ -314,14 +332,14 @@ __device__ __forceinline__ void mma_issue_loop(const HaloParams& p, uint8_t* a_b
               for (int k = 0; k < KSTEPS; ++k) {
 #pragma unroll
                 for (int half = (HSEL < 0 ? 0 : HSEL); half < (HSEL < 0 ? 2 : HSEL + 1); ++half) {
-                  tc_mma_bf16(d_tmem + (uint32_t)half * 128u,
+                  tc_mma_g<CTA2>(d_tmem + (uint32_t)half * 128u,
                               a_tap + (uint64_t)(half * 8 * kRBU + k * 2), b_tap + (uint64_t)(k * 2),
                               idesc, (k == 0 && tap == 0) ? accum : 1u);
                 }
               }
             }
           }
-          tc_commit(&a_empty[astage]);
+          tc_commit_g<CTA2>(&a_empty[astage]);
         }
         accum = 1u;
       } else {
@@ -336,13 +354,13 @@ __device__ __forceinline__ void mma_issue_loop(const HaloParams& p, uint8_t* a_b
               for (int k = 0; k < KSTEPS; ++k) {
 #pragma unroll
                 for (int half = (HSEL < 0 ? 0 : HSEL); half < (HSEL < 0 ? 2 : HSEL + 1); ++half) {
-                  tc_mma_bf16(d_tmem + (uint32_t)half * 128u,
+                  tc_mma_g<CTA2>(d_tmem + (uint32_t)half * 128u,
                               a_tap + (uint64_t)(half * 8 * kRBU + k * 2), b_tap + (uint64_t)(k * 2),
                               idesc, k == 0 ? accum : 1u);
                 }
               }
             }
-            tc_commit(&b_empty[bstage]);
+            tc_commit_g<CTA2>(&b_empty[bstage]);
           }
           accum = 1u;
           if (++bstage == p.b_stages) {
@@ -350,7 +368,7 @@ __device__ __forceinline__ void mma_issue_loop(const HaloParams& p, uint8_t* a_b
             bphase ^= 1u;
           }
         }
-        if (leader) tc_commit(&a_empty[astage]);
+        if (leader) tc_commit_g<CTA2>(&a_empty[astage]);
       }
       __syncwarp();
       if (++astage == p.a_stages) {
@@ -358,7 +376,7 @@ __device__ __forceinline__ void mma_issue_loop(const HaloParams& p, uint8_t* a_b
         aphase ^= 1u;
       }
     }
-    if (leader) tc_commit(&tmem_full[acc]);
+    if (leader) tc_commit_g<CTA2>(&tmem_full[acc]);
     __syncwarp();
     acc ^= 1;
     if (acc == 0) acc_phase ^= 1u;
@@ -366,20 +384,20 @@ __device__ __forceinline__ void mma_issue_loop(const HaloParams& p, uint8_t* a_b
 }
 
 // The issue loop specialised for the launch's chunk width / tap count, for the half (or both halves) this warp owns.
-template <bool kStats, int kFeed, int HSEL>
+template <bool kStats, int kFeed, int HSEL, bool CTA2>
 __device__ __forceinline__ void issue_dispatch(const HaloParams& p, uint8_t* a_base, uint8_t* b_base, uint64_t* b_full,
                                                uint64_t* b_empty, uint64_t* a_full, uint64_t* a_empty,
                                                uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base) {
   if (kFeed == 0 && !kStats && p.pool4) {
-    if (p.kc == 64) mma_issue_loop_pool4<4, HSEL>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
-    else mma_issue_loop_pool4<2, HSEL>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+    if (p.kc == 64) mma_issue_loop_pool4<4, HSEL, CTA2>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+    else mma_issue_loop_pool4<2, HSEL, CTA2>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
   } else if (p.tconv4) {
-    if (p.kc == 64) mma_issue_loop<4, 4, HSEL>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
-    else if (p.kc == 32) mma_issue_loop<2, 4, HSEL>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
-    else mma_issue_loop<1, 4, HSEL>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
-  } else if (p.kc == 64) mma_issue_loop<4, 9, HSEL>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
-  else if (p.kc == 32) mma_issue_loop<2, 9, HSEL>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
-  else mma_issue_loop<1, 9, HSEL>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+    if (p.kc == 64) mma_issue_loop<4, 4, HSEL, CTA2>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+    else if (p.kc == 32) mma_issue_loop<2, 4, HSEL, CTA2>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+    else mma_issue_loop<1, 4, HSEL, CTA2>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+  } else if (p.kc == 64) mma_issue_loop<4, 9, HSEL, CTA2>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+  else if (p.kc == 32) mma_issue_loop<2, 9, HSEL, CTA2>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+  else mma_issue_loop<1, 9, HSEL, CTA2>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -387,26 +405,36 @@ __device__ __forceinline__ void issue_dispatch(const HaloParams& p, uint8_t* a_b
 // channel chunk); coordinates start at (w0-1, h0-1), the out-of-bounds part of the box is zero-filled by the TMA
 // unit — that IS the convolution's padding.
 // ---------------------------------------------------------------------------------------------------------
+// Pair mode: both CTAs load their own tile's halo into their own shared memory; the bytes of BOTH loads are counted on
+// the LEADER's a_full barrier (the leader's thread posts the expected total), because only the leader's MMA warps wait.
+__device__ __forceinline__ void halo_load(const HaloParams& p, const CUtensorMap* tmap_x, uint64_t* full, void* dst, int c0,
+                                          int c1, int c2, int c3, uint32_t crank) {
+  if (p.cta2) {
+    if (crank == 0) mbar_expect_tx(full, 2u * p.a_tx_bytes);
+    tma_load_4d_2sm(tmap_x, mapa_cta(smem_u32(full), 0u), dst, c0, c1, c2, c3);
+  } else {
+    mbar_expect_tx(full, p.a_tx_bytes);
+    if (p.debug & 4) mbar_arrive_tx_debug(full, p.a_tx_bytes);
+    else tma_load_4d(tmap_x, full, dst, c0, c1, c2, c3);
+  }
+}
+
 __device__ __forceinline__ void halo_tma_loop(const HaloParams& p, const CUtensorMap* tmap_x, uint8_t* a_base,
-                                              uint64_t* a_full, uint64_t* a_empty) {
+                                              uint64_t* a_full, uint64_t* a_empty, uint32_t crank) {
   int tile_lo, tile_hi, tile_step;
   tile_range(p, tile_lo, tile_hi, tile_step);
   int stage = 0;
   uint32_t phase = 0;
   for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
-    const TileCoord t = decode_tile(p, tile);
+    const TileCoord t = decode_tile(p, tile, crank);
     for (int kcx = 0; kcx < p.k_chunks; ++kcx) {
       if (p.pool4) {
         // four pipeline units per chunk, one per parity-phase tile of the 34x34 input region: the tensor map walks W
         // and H with element stride 2, so each unit is a dense 17x17-pixel tile
         for (int ph = 0; ph < 4; ++ph) {
           mbar_wait(&a_empty[stage], phase ^ 1u);
-          mbar_expect_tx(&a_full[stage], p.a_tx_bytes);
-          if (p.debug & 4)
-            mbar_arrive_tx_debug(&a_full[stage], p.a_tx_bytes);
-          else
-            tma_load_4d(tmap_x, &a_full[stage], a_base + (size_t)stage * p.a_stage_bytes, kcx * p.kc,
-                        2 * t.w0 - 1 + (ph & 1), 2 * t.h0 - 1 + (ph >> 1), t.n);
+          halo_load(p, tmap_x, &a_full[stage], a_base + (size_t)stage * p.a_stage_bytes, kcx * p.kc,
+                    2 * t.w0 - 1 + (ph & 1), 2 * t.h0 - 1 + (ph >> 1), t.n, crank);
           if (++stage == p.a_stages) {
             stage = 0;
             phase ^= 1u;
@@ -415,12 +443,8 @@ __device__ __forceinline__ void halo_tma_loop(const HaloParams& p, const CUtenso
         continue;
       }
       mbar_wait(&a_empty[stage], phase ^ 1u);
-      mbar_expect_tx(&a_full[stage], p.a_tx_bytes);
-      if (p.debug & 4) {
-        mbar_arrive_tx_debug(&a_full[stage], p.a_tx_bytes);
-      } else {
-        tma_load_4d(tmap_x, &a_full[stage], a_base + (size_t)stage * p.a_stage_bytes, kcx * p.kc, t.w0 - 1, t.h0 - 1, t.n);
-      }
+      halo_load(p, tmap_x, &a_full[stage], a_base + (size_t)stage * p.a_stage_bytes, kcx * p.kc, t.w0 - 1, t.h0 - 1, t.n,
+                crank);
       if (++stage == p.a_stages) {
         stage = 0;
         phase ^= 1u;
@@ -604,7 +628,7 @@ __device__ __forceinline__ void stats_flush(const HaloParams& p, float* slices, 
   asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * kEpiWarps) : "memory");
 }
 
-template <bool kStats, int kFeed>     // kFeed: 0 TMA halo (plain and pool4), 1 upsample producers
+template <bool kStats, int kFeed, bool kCta2>     // kFeed: 0 TMA halo (plain and pool4), 1 upsample producers
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                  const HaloParams p) {
@@ -636,6 +660,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform role index
   const int lane = threadIdx.x & 31;
+  const uint32_t crank = kCta2 ? cluster_ctarank() : 0u;                   // 0 = leader of the CTA pair
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_w);
@@ -650,13 +675,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], (uint32_t)p.issuers);
-      mbar_init(&tmem_empty[s], kEpiWarps);
+      mbar_init(&tmem_empty[s], kCta2 ? 2 * kEpiWarps : kEpiWarps);   // pair mode: the leader's copy counts both CTAs
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if (kCta2) {
+      tmem_alloc2(tmem_slot, kTmemCols);        // one warp of EACH CTA of the pair takes part
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_slot, kTmemCols);
+      tmem_relinquish();
+    }
     // only now may the next kernel of the stream become resident: released at kernel entry, a dependent CTA that landed
     // on this SM could take the TMEM columns first and then wait for this grid, which would be waiting for the columns
     pdl_launch_dependents();
@@ -672,6 +702,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (kCta2) cluster_sync_all();     // the peer's barriers are initialised and its TMEM allocated before anything remote
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   int tile_lo, tile_hi, tile_step;
@@ -690,11 +721,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
           const int wn = p.per_sample_w ? decode_tile(p, tile).n : 0;
           if (wn == cur) continue;
           if (loads > 0) mbar_wait(&b_empty[0], (loads - 1u) & 1u);
-          mbar_expect_tx(&b_full[0], (uint32_t)(p.k_chunks * p.taps) * p.b_tx_bytes);
+          // pair mode: this CTA keeps rows [crank * block_n / 2, ...) of every tile; all bytes count on the leader's barrier
+          if (!kCta2 || crank == 0)
+            mbar_expect_tx(&b_full[0], (uint32_t)(p.k_chunks * p.taps) * p.b_tx_bytes * (kCta2 ? 2u : 1u));
+          const uint32_t full_addr = kCta2 ? mapa_cta(smem_u32(&b_full[0]), 0u) : 0u;
           for (int kcx = 0; kcx < p.k_chunks; ++kcx)
-            for (int tap = 0; tap < p.taps; ++tap)
-              tma_load_4d(&tmap_w, &b_full[0], b_base + (size_t)(kcx * p.taps + tap) * p.b_tile_bytes, kcx * p.kc, 0, tap,
-                          wn);
+            for (int tap = 0; tap < p.taps; ++tap) {
+              uint8_t* dst = b_base + (size_t)(kcx * p.taps + tap) * p.b_tile_bytes;
+              if (kCta2) tma_load_4d_2sm(&tmap_w, full_addr, dst, kcx * p.kc, (int)crank * (p.block_n >> 1), tap, wn);
+              else tma_load_4d(&tmap_w, &b_full[0], dst, kcx * p.kc, 0, tap, wn);
+            }
           cur = wn;
           ++loads;
         }
@@ -709,9 +745,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
               // the order the MMA warp consumes them
               const int tap = p.tconv4 ? t.ph * 4 + ti : (p.pool4_tma ? pool4_tap(ti >> 2, ti & 3) : ti);
               mbar_wait(&b_empty[stage], phase ^ 1u);
-              mbar_expect_tx(&b_full[stage], p.b_tx_bytes);
-              tma_load_4d(&tmap_w, &b_full[stage], b_base + (size_t)stage * p.b_tile_bytes, kcx * p.kc, t.co0, tap,
-                          p.per_sample_w ? t.n : 0);
+              if (kCta2) {
+                if (crank == 0) mbar_expect_tx(&b_full[stage], 2u * p.b_tx_bytes);
+                tma_load_4d_2sm(&tmap_w, mapa_cta(smem_u32(&b_full[stage]), 0u), b_base + (size_t)stage * p.b_tile_bytes,
+                                kcx * p.kc, t.co0 + (int)crank * (p.block_n >> 1), tap, p.per_sample_w ? t.n : 0);
+              } else {
+                mbar_expect_tx(&b_full[stage], p.b_tx_bytes);
+                tma_load_4d(&tmap_w, &b_full[stage], b_base + (size_t)stage * p.b_tile_bytes, kcx * p.kc, t.co0, tap,
+                            p.per_sample_w ? t.n : 0);
+              }
               if (++stage == p.b_stages) {
                 stage = 0;
                 phase ^= 1u;
@@ -723,11 +765,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     }
   } else if (warp == 1 || (warp == kIssuer2 && p.issuers == 2)) {
     // ------------------------------ MMA issuer(s) ------------------------------
-    if (p.issuers == 2) {
-      if (warp == 1) issue_dispatch<kStats, kFeed, 0>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
-      else issue_dispatch<kStats, kFeed, 1>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+    if (kCta2 && crank != 0) {
+      // the leader CTA issues the pair's instructions; this CTA's MMA warps have nothing to do
+    } else if (p.issuers == 2) {
+      if (warp == 1) issue_dispatch<kStats, kFeed, 0, kCta2>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+      else issue_dispatch<kStats, kFeed, 1, kCta2>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
     } else {
-      issue_dispatch<kStats, kFeed, -1>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+      issue_dispatch<kStats, kFeed, -1, kCta2>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
     }
   } else if (warp < 2 + kEpiWarpsAll) {
     // ------------------------------ epilogue ------------------------------
@@ -763,7 +807,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     const int kSets = kUp ? 1 : p.epi_sets;
     if (kSets == 2) acc = eset;
     for (int tile = tile_lo + (kSets == 2 ? eset * tile_step : 0); tile < tile_hi; tile += tile_step * kSets) {
-      const TileCoord t = decode_tile(p, tile);
+      const TileCoord t = decode_tile(p, tile, crank);
       if (st_on && p.stats_mode == 1 && st_n >= 0 && st_n != t.n) {
         if (st_regs) stats_round(st_slice, sa, sq, cpr_shift, lane, 0);
         stats_flush(p, st_set, st_et, st_n, 1 + eset);
@@ -908,7 +952,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if (kCta2 && crank != 0) mbar_arrive_cluster(mapa_cta(smem_u32(&tmem_empty[acc]), 0u));   // the leader's MMA warps wait
+        else mbar_arrive(&tmem_empty[acc]);
+      }
       if (kSets == 2) {
         acc_phase ^= 1u;
       } else {
@@ -930,15 +977,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         else halo_producer_upsample<1>(p, a_base, patch_base, a_full, a_empty, pt);
       }
     } else if (warp == 2 + kEpiWarps * kEpiSets && lane == 0) {
-      halo_tma_loop(p, &tmap_x, a_base, a_full, a_empty);        // warp 18
+      halo_tma_loop(p, &tmap_x, a_base, a_full, a_empty, crank);        // warp 18
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (kCta2) cluster_sync_all();     // the peer's shared memory / barriers stay valid until both CTAs are done with them
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (kCta2) tmem_dealloc2(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -1014,7 +1063,13 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
   const uint32_t row_bytes = (uint32_t)p.kc * 2u;
   p.b_layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
   p.b_sbo = 8u * row_bytes;
-  p.b_tx_bytes = (uint32_t)p.block_n * row_bytes;
+  {
+    static int cta2_on = -1;                                  // BG_CTA2=0: every layer with one CTA per tile (A/B switch)
+    if (cta2_on < 0) { const char* e = getenv("BG_CTA2"); cta2_on = (e && e[0] == '0') ? 0 : 1; }
+    // pair mode for the wide layers: N = 128 per instruction, at least two tile columns, TMA halo feed
+    p.cta2 = (cta2_on && bn_ch == 128 && !upsample && (Wc / kTile) >= 2) ? 1 : 0;
+  }
+  p.b_tx_bytes = (uint32_t)(p.block_n >> p.cta2) * row_bytes;     // pair mode: each CTA holds half of the weight tile
   p.b_tile_bytes = (p.b_tx_bytes + 1023u) & ~1023u;
   p.a_layout = p.b_layout;                                   // same row width (kc bf16) on both operands
   p.a_sbo = (uint32_t)(pool4 ? kTile + 1 : kHalo) * row_bytes;   // next 8-pixel group = one (phase-)tile row down
@@ -1132,7 +1187,7 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
     // [sample][tap][Cout][Cin]; the sample dimension has extent 1 for the ordinary shared pack
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)p.taps, (uint64_t)(p.per_sample_w ? N : 1)};
     uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)Cout * Cin * 2, (uint64_t)p.taps * Cout * Cin * 2};
-    uint32_t box[4] = {(uint32_t)p.kc, (uint32_t)p.block_n, 1u, 1u};
+    uint32_t box[4] = {(uint32_t)p.kc, (uint32_t)(p.block_n >> p.cta2), 1u, 1u};
     if (make_tmap_bf16(&tmw, wpack, 4, dims, str, box, (int)row_bytes) != 0) return 1;
   }
   CUtensorMap tmx;
@@ -1156,17 +1211,28 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
   BG_REQUIRE(smem_bytes <= 227 * 1024, "conv_halo: shared memory budget exceeded (%zu)", smem_bytes);
   static bool attr_set = false;
   if (!attr_set) {
-    BG_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    BG_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    BG_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    BG_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BG_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BG_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<true, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BG_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BG_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<true, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BG_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<false, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BG_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_kernel<true, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
+  if (p.cta2) {
+    // one CTA pair (2-CTA cluster) per tile pair; persistent over at most one pair per two SMs
+    const int pairs_total = p.num_tiles / 2;
+    const int pairs = pairs_total < num_sms() / 2 ? pairs_total : num_sms() / 2;
+    if (p.stats_mode) BG_CHECK_CUDA(launch_pdl_cluster(conv_halo_kernel<true, 0, true>, 2 * pairs, kThreads, smem_bytes, stream, 2, tmw, tmx, p));
+    else BG_CHECK_CUDA(launch_pdl_cluster(conv_halo_kernel<false, 0, true>, 2 * pairs, kThreads, smem_bytes, stream, 2, tmw, tmx, p));
+    BG_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  if (p.stats_mode && p.upsample) BG_CHECK_CUDA(launch_pdl(conv_halo_kernel<true, 1>, grid, kThreads, smem_bytes, stream, tmw, tmx, p));
-  else if (p.stats_mode) BG_CHECK_CUDA(launch_pdl(conv_halo_kernel<true, 0>, grid, kThreads, smem_bytes, stream, tmw, tmx, p));
-  else if (p.upsample) BG_CHECK_CUDA(launch_pdl(conv_halo_kernel<false, 1>, grid, kThreads, smem_bytes, stream, tmw, tmx, p));
-  else BG_CHECK_CUDA(launch_pdl(conv_halo_kernel<false, 0>, grid, kThreads, smem_bytes, stream, tmw, tmx, p));
+  if (p.stats_mode && p.upsample) BG_CHECK_CUDA(launch_pdl(conv_halo_kernel<true, 1, false>, grid, kThreads, smem_bytes, stream, tmw, tmx, p));
+  else if (p.stats_mode) BG_CHECK_CUDA(launch_pdl(conv_halo_kernel<true, 0, false>, grid, kThreads, smem_bytes, stream, tmw, tmx, p));
+  else if (p.upsample) BG_CHECK_CUDA(launch_pdl(conv_halo_kernel<false, 1, false>, grid, kThreads, smem_bytes, stream, tmw, tmx, p));
+  else BG_CHECK_CUDA(launch_pdl(conv_halo_kernel<false, 0, false>, grid, kThreads, smem_bytes, stream, tmw, tmx, p));
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -73,13 +73,18 @@ def _oracle_pair(args, steps, alpha, lam, **kw):
     return o, q
 
 
-def _check_gradients(r, o, q, kinds=("d_grads", "g_grads"), case=None):
-    """Per-tensor gate (parity_util.grad_gate) on every parameter gradient + None-ness + the network-median criterion."""
+def _check_gradients(r, o, q, kinds=("d_grads", "g_grads"), case=None, zero_for_none=False):
+    """Per-tensor gate (parity_util.grad_gate) on every parameter gradient + None-ness + the network-median criterion.
+    zero_for_none: a parameter the reference's autograd never reaches (.grad None) may carry an all-zero gradient here
+    (the penalty-only critic step: the last bias cannot influence d D / d x, the hand-scheduled pass still visits it)."""
     bad = []
     for kind in kinds:
         errs, errs_emu = [], []
         for k, ref in o[kind].items():
             got = r[kind][k]
+            if zero_for_none and ref is None and got is not None:
+                assert got.abs().max().item() == 0.0, f"{kind}[{k}]: the reference has no gradient, got a non-zero one"
+                continue
             assert (got is None) == (ref is None), f"{kind}[{k}]: None-ness differs from the reference"
             if case is not None:
                 assert (case[kind][k] is None) == (ref is None), f"{kind}[{k}]: oracle None-ness differs from the golden"
@@ -147,8 +152,8 @@ def test_r1_penalty_alone_second_order_terms(case):
             O.QUANT[0] = False
     why = U.grad_gate("d sum D(real) / d real", r["real_grad"], grads[0], grads[1])
     assert why is None, why
-    fp_close(grads[0], case["grad_real"], 1e-3, "oracle image gradient vs golden")
-    _check_gradients(r, o, q, kinds=("d_grads",), case=case)
+    fp_close(grads[0], case["grad_real"], 5e-3, "oracle image gradient (GPU fp32) vs golden (CPU fp32)")
+    _check_gradients(r, o, q, kinds=("d_grads",), case=case, zero_for_none=True)
 
 
 @pytest.mark.parametrize("case", gold("wgan_gp.json"), ids=lambda c: f"s{c['steps']}-b{c['batch']}-a{c['alpha']}")

@@ -136,8 +136,13 @@ def test_reference_training_loop_runs_on_the_drop_in_and_tracks_the_oracle(tmp_p
             # +-lr differences per element), hence twice the single-forward image tolerance
             assert U.rel(examples, examples_o) < 2 * U.TOL_IMG, (it, U.rel(examples, examples_o))
 
-        for a, b in zip(c_hist + g_hist, c_hist_o + g_hist_o):
-            assert abs(a - b) < U.TOL_LOSS * abs(b), (c_hist, c_hist_o, g_hist, g_hist_o)
+        # iteration 0 runs on identical weights: the single-iteration loss tolerance; afterwards both sides carry their own
+        # Adam-updated weights (a sign-like update of +-lr per element turns gradient noise into weight differences) and
+        # the trajectories separate slowly: 10 % on the losses of iterations 1 and 2
+        for hist, hist_o in ((c_hist, c_hist_o), (g_hist, g_hist_o)):
+            for it, (a, b) in enumerate(zip(hist, hist_o)):
+                tol = U.TOL_LOSS if it == 0 else 0.10
+                assert abs(a - b) < tol * abs(b), (it, c_hist, c_hist_o, g_hist, g_hist_o)
         # three Adam updates later the fp32 masters moved the same way: per-tensor cosine of the weight DELTAS
         init_g, init_d = O.make_state("gen", 6), O.make_state("critic", 6)
         worst = 1.0
