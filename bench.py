@@ -139,12 +139,16 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------
 # the B200 arm
 # ------------------------------------------------------------------------------------------------------
-def make_trainer(steps, alpha, batch, device, style_mixing):
-    """The package's Trainer (byo-gan_b200/trainer.py): train.py:58-80 + one iteration of train.py:135-219."""
+def make_trainer(steps, alpha, batch, device, style_mixing, graph=False):
+    """The package's Trainer (byo-gan_b200/trainer.py): train.py:58-80 + one iteration of train.py:135-219.
+    graph: replay the iteration from CUDA graphs (single process only; Adam with device-side step counters)."""
     import trainer
 
-    return trainer.Trainer(steps, alpha, batch, device, lr=LR, betas=BETAS, c_lambda=LAMBDA, fused_adam=FUSED_ADAM,
-                           style_mixing=style_mixing, perturb_init=True)
+    tr = trainer.Trainer(steps, alpha, batch, device, lr=LR, betas=BETAS, c_lambda=LAMBDA, fused_adam=FUSED_ADAM,
+                         style_mixing=style_mixing, perturb_init=True, capturable=graph)
+    if graph:
+        tr.enable_graphs()
+    return tr
 
 
 def conv_bytes(name, args):
@@ -368,7 +372,8 @@ def run_b200(args):
         batch = args.batch
     R = 4 * 2 ** (steps - 1)
     style_mixing = (args.workload in STYLE_MIXING_DEFAULT) if args.style_mixing is None else bool(args.style_mixing)
-    tr = make_trainer(steps, alpha, batch, device, style_mixing)
+    use_graph = bool(args.graph) and world == 1
+    tr = make_trainer(steps, alpha, batch, device, style_mixing, graph=use_graph)
     g = torch.Generator(device="cpu").manual_seed(1234 + rank)
     POOL = 4
     host_real = [torch.rand(batch, 3, R, R, generator=g).mul_(2).sub_(1).pin_memory() for _ in range(POOL)]
@@ -477,9 +482,11 @@ def run_b200(args):
     # ---- roofline leg: CUDA-event pair around every C-ABI call of one more iteration (rank 0's numbers)
     peaks = load_peaks()
     barrier()
+    saved_graphs, tr.graphs = tr.graphs, None                # per-call timing needs the eager call sequence
     bgn.start_timing()
     tr.iteration(dev_real[0].clone(), dev_z[0][0].clone(), dev_z[0][1].clone(), read_losses=False)
     rec = bgn.stop_timing()
+    tr.graphs = saved_graphs
     roofline, aux_table = roofline_from_calls(rec, args.workload, peaks, value / world, gflop_img,
                                               use_traffic_file=(args.workload == "train256" and not args.batch))
 
@@ -524,6 +531,7 @@ def run_b200(args):
                                   "step i+1 on a copy stream while step i computes",
                     "ms_per_step": round(ms_e2e / args.steps, 3)},
             "gpu_launches": launches,
+            "cuda_graph": use_graph,
             "roofline": roofline,
             "aux_kernels": aux_table,
             "cpu_baseline": cpu,
@@ -717,6 +725,8 @@ def main():
                          "(BASELINE configs[2] names it), off elsewhere")
     ap.add_argument("--no-style-mixing", dest="style_mixing", action="store_false")
     ap.add_argument("--no-sampling", action="store_true", help="skip the 512x512 sampling leg")
+    ap.add_argument("--graph", dest="graph", action="store_true", default=False,
+                    help="replay each iteration from a CUDA graph (Trainer.enable_graphs; single GPU only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -407,9 +407,11 @@ __device__ __forceinline__ void issue_dispatch(const HaloParams& p, uint8_t* a_b
 // ---------------------------------------------------------------------------------------------------------
 // Pair mode: both CTAs load their own tile's halo into their own shared memory; the bytes of BOTH loads are counted on
 // the LEADER's a_full barrier (the leader's thread posts the expected total), because only the leader's MMA warps wait.
+// (compile-time switch: a kernel that merely CONTAINS cta_group::2 instructions cannot be launched without a cluster)
+template <bool CTA2>
 __device__ __forceinline__ void halo_load(const HaloParams& p, const CUtensorMap* tmap_x, uint64_t* full, void* dst, int c0,
                                           int c1, int c2, int c3, uint32_t crank) {
-  if (p.cta2) {
+  if (CTA2) {
     if (crank == 0) mbar_expect_tx(full, 2u * p.a_tx_bytes);
     tma_load_4d_2sm(tmap_x, mapa_cta(smem_u32(full), 0u), dst, c0, c1, c2, c3);
   } else {
@@ -419,6 +421,7 @@ __device__ __forceinline__ void halo_load(const HaloParams& p, const CUtensorMap
   }
 }
 
+template <bool CTA2>
 __device__ __forceinline__ void halo_tma_loop(const HaloParams& p, const CUtensorMap* tmap_x, uint8_t* a_base,
                                               uint64_t* a_full, uint64_t* a_empty, uint32_t crank) {
   int tile_lo, tile_hi, tile_step;
@@ -433,7 +436,7 @@ __device__ __forceinline__ void halo_tma_loop(const HaloParams& p, const CUtenso
         // and H with element stride 2, so each unit is a dense 17x17-pixel tile
         for (int ph = 0; ph < 4; ++ph) {
           mbar_wait(&a_empty[stage], phase ^ 1u);
-          halo_load(p, tmap_x, &a_full[stage], a_base + (size_t)stage * p.a_stage_bytes, kcx * p.kc,
+          halo_load<CTA2>(p, tmap_x, &a_full[stage], a_base + (size_t)stage * p.a_stage_bytes, kcx * p.kc,
                     2 * t.w0 - 1 + (ph & 1), 2 * t.h0 - 1 + (ph >> 1), t.n, crank);
           if (++stage == p.a_stages) {
             stage = 0;
@@ -443,7 +446,7 @@ __device__ __forceinline__ void halo_tma_loop(const HaloParams& p, const CUtenso
         continue;
       }
       mbar_wait(&a_empty[stage], phase ^ 1u);
-      halo_load(p, tmap_x, &a_full[stage], a_base + (size_t)stage * p.a_stage_bytes, kcx * p.kc, t.w0 - 1, t.h0 - 1, t.n,
+      halo_load<CTA2>(p, tmap_x, &a_full[stage], a_base + (size_t)stage * p.a_stage_bytes, kcx * p.kc, t.w0 - 1, t.h0 - 1, t.n,
                 crank);
       if (++stage == p.a_stages) {
         stage = 0;
@@ -977,7 +980,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         else halo_producer_upsample<1>(p, a_base, patch_base, a_full, a_empty, pt);
       }
     } else if (warp == 2 + kEpiWarps * kEpiSets && lane == 0) {
-      halo_tma_loop(p, &tmap_x, a_base, a_full, a_empty, crank);        // warp 18
+      halo_tma_loop<kCta2>(p, &tmap_x, a_base, a_full, a_empty, crank);        // warp 18
     }
   }
 

@@ -20,6 +20,7 @@ from typing import Optional
 
 import torch
 
+import bg_native as bgn
 import dist as bdist
 import gan
 
@@ -70,7 +71,7 @@ class Trainer:
     """train.py:58-80 (models + the two Adam optimizers) and one iteration of train.py:135-219."""
 
     def __init__(self, steps, alpha, batch, device, lr=0.002, betas=(0.0, 0.99), c_lambda=10.0, use_r1=True,
-                 fused_adam=True, style_mixing=False, perturb_init=False, seed=0):
+                 fused_adam=True, style_mixing=False, perturb_init=False, seed=0, capturable=False):
         torch.manual_seed(seed)
         self.gen, self.critic = gan.Generator().to(device), gan.Critic().to(device)
         if perturb_init:
@@ -84,8 +85,9 @@ class Trainer:
         g = self.gen
         self.gen_opt = torch.optim.Adam([{"params": g.to_w_noise.parameters(), "lr": lr * 0.01},      # train.py:59-70
                                          {"params": g.gen_blocks.parameters()}, {"params": g.to_rgbs.parameters()}],
-                                        lr=lr, betas=betas, fused=fused_adam)
-        self.critic_opt = torch.optim.Adam(self.critic.parameters(), lr=lr, betas=betas, fused=fused_adam)  # train.py:76-78
+                                        lr=lr, betas=betas, fused=fused_adam, capturable=capturable)
+        self.critic_opt = torch.optim.Adam(self.critic.parameters(), lr=lr, betas=betas, fused=fused_adam,   # train.py:76-78
+                                           capturable=capturable)
         self.steps, self.alpha, self.batch, self.device = steps, alpha, batch, device
         self.c_lambda, self.use_r1, self.style_mixing = c_lambda, use_r1, style_mixing
         self.sync = bdist.GradSync()
@@ -111,12 +113,9 @@ class Trainer:
         for p in model.parameters():
             p.requires_grad = flag
 
-    def iteration(self, real, z_d, z_g, read_losses=True, alpha_g="same"):
-        """alpha_g: the generator step's fade-in alpha when it differs from the critic step's (train.py:198-202
-        re-evaluates it after im_count has moved); default: the same value."""
+    def _step(self, real, z_d, z_g, alpha_g):
+        """One iteration of train.py:135-219 on device tensors; returns the two loss tensors (no host interaction)."""
         gen, critic, steps, alpha = self.gen, self.critic, self.steps, self.alpha
-        if isinstance(alpha_g, str):
-            alpha_g = alpha
         # ---- critic step (train.py:135-191)
         self._set_requires_grad(critic, True)
         self._set_requires_grad(gen, False)
@@ -133,7 +132,6 @@ class Trainer:
             c_loss = critic.get_wgan_loss(pf, pr, real_im, steps, alpha, self.c_lambda)
         self.sync.finish()
         self.critic_opt.step()
-        c_val = self.reader.push(c_loss, 0) if read_losses else None
         # ---- generator step (train.py:193-219)
         self._set_requires_grad(critic, False)
         self._set_requires_grad(gen, True)
@@ -147,8 +145,79 @@ class Trainer:
         self.sync.ready_all(p for p in gen.parameters() if p.grad is not None)
         self.sync.finish()
         self.gen_opt.step()
+        return c_loss.detach(), g_loss.detach()
+
+    def iteration(self, real, z_d, z_g, read_losses=True, alpha_g="same"):
+        """alpha_g: the generator step's fade-in alpha when it differs from the critic step's (train.py:198-202
+        re-evaluates it after im_count has moved); default: the same value."""
+        if isinstance(alpha_g, str):
+            alpha_g = self.alpha
+        if self.graphs is not None:
+            c_loss, g_loss = self._replay(real, z_d, z_g, alpha_g)
+        else:
+            c_loss, g_loss = self._step(real, z_d, z_g, alpha_g)
+        c_val = self.reader.push(c_loss, 0) if read_losses else None
         g_val = self.reader.push(g_loss, 1) if read_losses else None
         return c_val, g_val
+
+    # ---- CUDA-graph mode: the whole iteration (~500 C-ABI calls, ~700 kernels incl. both Adam updates) is captured once
+    # per (stage, alpha, batch, style-mixing phase) and replayed, so the host issues one launch per iteration; the
+    # programmatic-dependent-launch edges between the library's kernels are part of the captured graph.  Valid while
+    # alpha is constant (a stage after its fade-in, or a benchmark); a changed key captures a new graph in the same pool.
+    graphs = None
+
+    def enable_graphs(self):
+        if self.sync.enabled:
+            raise RuntimeError("CUDA-graph mode is single-process only (the NCCL all-reduce is launched from the host)")
+        for opt in (self.gen_opt, self.critic_opt):
+            if not opt.defaults.get("capturable", False):
+                raise RuntimeError("build the Trainer with capturable=True to use CUDA graphs")
+        self.graphs, self._pool, self._static = {}, None, None
+
+    def _replay(self, real, z_d, z_g, alpha_g):
+        st = self._static
+        if st is None or st["real"].shape != real.shape:
+            self._static = st = {"real": torch.empty_like(real), "z_d": torch.empty_like(z_d), "z_g": torch.empty_like(z_g)}
+            self.graphs.clear()
+        st["real"].copy_(real.detach())
+        st["z_d"].copy_(z_d.detach())
+        st["z_g"].copy_(z_g.detach())
+        period = max(1, self.steps - 1) if self.style_mixing else 1
+        key = (self.steps, self.alpha, alpha_g, self._mix_count % period)
+        entry = self.graphs.get(key)
+        if entry is None:
+            count0 = self._mix_count
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                      # allocator warm-up outside the capture: ONE REAL iteration
+                self._mix_count = count0
+                trained = self._step(st["real"].clone(), st["z_d"].clone(), st["z_g"].clone(), alpha_g)
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            self._mix_count = count0
+            calls0 = bgn.launch_count
+            with torch.cuda.graph(g, pool=self._pool):
+                out = self._step(st["real"], st["z_d"], st["z_g"], alpha_g)
+            calls = bgn.launch_count - calls0
+            bgn.launch_count = calls0                          # recorded, not executed
+            if self._pool is None:
+                self._pool = g.pool()
+            self.graphs[key] = (g, out, self._mix_count - count0, calls)
+            self._forget_packs()
+            return trained                                     # the capture itself executed nothing: this batch was
+                                                               # trained on by the eager iteration above
+        g, out, advance, calls = entry
+        g.replay()
+        bgn.launch_count += calls                              # the C-ABI calls this replay stands for
+        self._mix_count += advance
+        self._forget_packs()
+        return out
+
+    def _forget_packs(self):
+        """A replay moves the fp32 masters without running any Python (no optimizer hook, no version counter): eager
+        forwards between replays (previews, checkpoints, evaluation) must not reuse the weight packs they cached."""
+        self.gen.invalidate_packs()
+        self.critic.invalidate_packs()
 
 
 def run(config: dict, feed_for_stage, checkpoint_path: Optional[str] = None, on_preview=None, on_checkpoint=None,
