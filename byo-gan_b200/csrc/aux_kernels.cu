@@ -219,6 +219,39 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __rest
   }
 }
 
+// Tiled form of the two unpack kernels for 3x3 layers: a block owns (one co, 128 ci); it reads the 9 (or 16) tap planes
+// coalesced along ci into shared memory and writes the (ci, ky, kx)-ordered run of 128 * 9 floats coalesced.  The
+// element-wise kernels above read 9 tap planes with 16 useful bytes per 128-byte line (17 us for a 512 x 512 layer whose
+// 19 MB move in 3 us).  MODE 0: plain transpose; MODE 1: the pool4 fold dW3[ky][kx] = 1/4 sum dW4[ky+dy][kx+dx].
+template <int MODE>
+__global__ void __launch_bounds__(128)
+unpack_wgrad_tiled_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Cout, int Cin, int Cin_pad, float coef,
+                          int accumulate) {
+  pdl_prologue();
+  constexpr int kTapsIn = MODE == 0 ? 9 : 16;
+  __shared__ float tile[kTapsIn][129];
+  const int co = blockIdx.y, ci0 = blockIdx.x * 128, t = threadIdx.x;
+#pragma unroll
+  for (int tap = 0; tap < kTapsIn; ++tap)
+    tile[tap][t] = (ci0 + t < Cin) ? dwp[((size_t)tap * Cout + co) * Cin_pad + ci0 + t] : 0.f;
+  __syncthreads();
+  const int nci = min(128, Cin - ci0);
+  float* out = dw + ((size_t)co * Cin + ci0) * 9;
+  for (int j = t; j < nci * 9; j += 128) {
+    const int cil = j / 9, tap = j - cil * 9;
+    float v;
+    if (MODE == 0) {
+      v = tile[tap][cil];
+    } else {
+      const int ky = tap / 3, kx = tap - ky * 3;
+      v = 0.25f * (tile[ky * 4 + kx][cil] + tile[ky * 4 + kx + 1][cil] + tile[(ky + 1) * 4 + kx][cil] +
+                   tile[(ky + 1) * 4 + kx + 1][cil]);
+    }
+    v *= coef;
+    out[j] = accumulate ? out[j] + v : v;
+  }
+}
+
 // dw4: fp32 [16][Cout][Cin] gradient of the 4x4 stride-2 kernel W4[a][b] = 1/4 sum_{dy,dx} W3[a-dy][b-dx]  ->
 // dw: fp32 (Cout, Cin, 3, 3):  dW3[ky][kx] = coef / 4 * sum_{dy,dx in {0,1}} dW4[ky+dy][kx+dx]   (adjoint of the pack)
 __global__ void unpack_wgrad_pool4_kernel(const float* __restrict__ dw4, float* __restrict__ dw, int Cout, int Cin,
@@ -1070,6 +1103,11 @@ int launch_pack_weight(const float* w, void* wf, void* wd, int Cout, int Cin, in
 int launch_unpack_wgrad(const float* dwp, float* dw, int Cout, int Cin, int Cin_pad, int ks, float coef,
                         int accumulate, cudaStream_t s) {
   const size_t total = (size_t)ks * ks * Cout * Cin;
+  if (ks == 3 && Cout <= 65535) {
+    BG_CHECK_CUDA(launch_pdl(unpack_wgrad_tiled_kernel<0>, dim3((Cin + 127) / 128, Cout), 128, 0, s, dwp, dw, Cout, Cin,
+                             Cin_pad, coef, accumulate));
+    return 0;
+  }
   BG_CHECK_CUDA(launch_pdl(unpack_wgrad_kernel, grid_for(total), kBlock, 0, s, dwp, dw, Cout, Cin, Cin_pad, ks, coef,
                            accumulate));
   return 0;
@@ -1326,6 +1364,11 @@ int launch_pack_weight_tconv4(const float* w, void* wt, int Cout, int Cin, float
 }
 
 int launch_unpack_wgrad_pool4(const float* dw4, float* dw, int Cout, int Cin, float coef, int accumulate, cudaStream_t s) {
+  if (Cout <= 65535) {
+    BG_CHECK_CUDA(launch_pdl(unpack_wgrad_tiled_kernel<1>, dim3((Cin + 127) / 128, Cout), 128, 0, s, dw4, dw, Cout, Cin, Cin,
+                             coef, accumulate));
+    return 0;
+  }
   BG_CHECK_CUDA(launch_pdl(unpack_wgrad_pool4_kernel, grid_for((size_t)Cout * Cin * 9), kBlock, 0, s, dw4, dw, Cout, Cin,
                            coef, accumulate));
   return 0;

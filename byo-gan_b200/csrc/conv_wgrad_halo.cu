@@ -35,7 +35,7 @@ constexpr uint32_t kStageBytes = kARegion + 2 * kBSub;
 struct WgradHaloParams {
   int N, H, W, Cin, Cout;
   int tiles_w, tiles_h;
-  int total_kblocks, splits, kblocks_per_split;
+  int total_kblocks, splits, kblocks_per_split, units;
   int co_tiles, ci_slabs;
   int co_slab, co_nslabs;          // G is loaded as co_nslabs boxes of co_slab channels (<= 64 each)
   int ci_sub, ci_nsub, ci_slab;    // X slab = ci_nsub sub-slabs of ci_sub channels (<= 64 each)
@@ -71,9 +71,13 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
-  // work decode: blockIdx -> (co tile, ci slab, kernel row, K split)
-  const int split = blockIdx.x % p.splits;
-  const int unit = blockIdx.x / p.splits;
+  // work decode: blockIdx -> (K split, co tile, ci slab, kernel row), UNIT FASTEST: the CTAs that share a K range (the
+  // three kernel rows and all co / ci tiles of it) are neighbours in the launch order and run at the same time, so G
+  // and the X halos they all need come out of L2 after the first of them has touched them.  (With the split index
+  // fastest — round 1 — kernel row 0 streamed the whole map in the first wave and row 2 in the last: every operand was
+  // read from DRAM three times on the 256x256 layers, 1.83x over the whole family, profiles/r1_ncu_dram_*.)
+  const int unit = blockIdx.x % p.units;
+  const int split = blockIdx.x / p.units;
   const int ntg = p.pool4 ? 4 : 3;
   const int tg = unit % ntg;                     // ky (pool4: tap row a)
   const int cis = (unit / ntg) % p.ci_slabs;
@@ -280,7 +284,12 @@ int launch_conv_wgrad_halo(const void* x, const void* g, float* dw, int N, int H
   }
   if (p.pool4) p.stack_taps = 0;
   const int units = p.co_tiles * p.ci_slabs * (p.pool4 ? 4 : 3);
-  int splits = (2 * num_sms() + units - 1) / units;
+  p.units = units;
+  // one resident wave (1 CTA per SM: 3 x 68 KB stages): splits = floor(SMs / units), so that every CTA of the grid runs
+  // concurrently with the others that read the same K range.  BG_WGRAD_WAVES=2 restores round 1's two waves.
+  static int waves = 0;
+  if (waves == 0) { const char* e = getenv("BG_WGRAD_WAVES"); waves = (e && atoi(e) > 0) ? atoi(e) : 1; }
+  int splits = waves * num_sms() / units;
   if (splits < 1) splits = 1;
   if (splits > p.total_kblocks) splits = p.total_kblocks;
   p.kblocks_per_split = (p.total_kblocks + splits - 1) / splits;

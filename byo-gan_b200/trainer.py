@@ -177,11 +177,13 @@ class Trainer:
     def _replay(self, real, z_d, z_g, alpha_g):
         st = self._static
         if st is None or st["real"].shape != real.shape:
-            self._static = st = {"real": torch.empty_like(real), "z_d": torch.empty_like(z_d), "z_g": torch.empty_like(z_g)}
+            self._static = st = {"real": torch.empty_like(real.detach()), "z_d": torch.empty_like(z_d.detach()),
+                                 "z_g": torch.empty_like(z_g.detach())}
             self.graphs.clear()
-        st["real"].copy_(real.detach())
-        st["z_d"].copy_(z_d.detach())
-        st["z_g"].copy_(z_g.detach())
+        with torch.no_grad():                     # the static inputs are autograd leaves (requires_grad_ inside the step)
+            st["real"].copy_(real.detach())
+            st["z_d"].copy_(z_d.detach())
+            st["z_g"].copy_(z_g.detach())
         period = max(1, self.steps - 1) if self.style_mixing else 1
         key = (self.steps, self.alpha, alpha_g, self._mix_count % period)
         entry = self.graphs.get(key)

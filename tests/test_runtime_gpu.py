@@ -166,7 +166,9 @@ def test_loop_driver_runs_the_progressive_schedule(tmp_path):
     assert save["step"] == 2 and save["iter"] == 8 and save["im_count"] == 16 and "critic_opt" in save
     assert save["alpha"] is None or 0.0 < save["alpha"] <= 1.0
     iters2, _ = trainer.run(config, feed_for_stage, checkpoint_path=saved[-1], on_checkpoint=lambda *a: None)
-    assert iters2 == 9                                                     # one batch of stage 2 was left
+    # like train.py:125-128 the resume is at EPOCH granularity: the epoch the checkpoint was taken in runs again in full
+    # (3 batches), now with the restored optimizer state and fade-in position
+    assert iters2 == 8 + 3
 
 
 def test_wgan_gp_training_iteration_through_the_trainer():
