@@ -294,6 +294,24 @@ __device__ __forceinline__ void tc_commit_g(uint64_t* bar) {
   else tc_commit(bar);
 }
 
+// TMA multicast: ONE load whose box lands at the same shared-memory offset in every CTA of `cta_mask` (and completes
+// bytes on the barrier at the same offset in each of them)
+__device__ __forceinline__ void tma_load_4d_mc(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, "
+      "%6}], [%2], %7;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(cta_mask)
+      : "memory");
+}
+// tcgen05.commit (one-CTA MMAs) arriving on the barrier at this offset in every CTA of `cta_mask`
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 D.
 __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
   uint32_t d = 0;

@@ -18,6 +18,8 @@
 // warps 2..5 = epilogue (TMEM -> registers -> fused bias / noise / LeakyReLU / gate -> global).
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace bg {
 
 namespace {
@@ -47,6 +49,11 @@ struct FpropParams {
   __nv_bfloat16* out;
   int act;
   float slope;
+  // A-operand multicast (the small maps this kernel serves are bound by the L2 -> shared-memory fill, and 2/3 of that
+  // fill is the pixel tile that every n-block of a layer re-reads): the `csize` CTAs of a cluster work on the SAME pixel
+  // tile and consecutive n-blocks; each loads 1/csize of the tile (slice_rows pixel rows) and multicasts it to all.
+  int csize, slice_rows, slice_n0_div, slice_h_rows;
+  uint32_t slice_bytes;
 };
 
 struct TileCoord {
@@ -67,6 +74,7 @@ __device__ __forceinline__ TileCoord decode_tile(const FpropParams& p, int tile)
   return t;
 }
 
+template <bool kMc>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                   const FpropParams p) {
@@ -85,13 +93,15 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t crank = kMc ? cluster_ctarank() : 0u;
+  const uint16_t cmask = (uint16_t)((1u << p.csize) - 1u);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], kMc ? (uint32_t)p.csize : 1u);   // multicast: every CTA of the cluster must have consumed it
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -115,6 +125,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
+  if (kMc) cluster_sync_all();       // every CTA's barriers exist before a peer multicasts into it
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -134,7 +145,15 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             uint8_t* sb = sa + p.a_bytes;
             mbar_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
             const int ky = tap / p.ksize, kx = tap % p.ksize;
-            tma_load_4d(&tmap_x, &full_bar[stage], sa, kcx * p.kc, t.w0 + kx - p.pad, t.h0 + ky - p.pad, t.n0);
+            if (kMc) {
+              // this CTA's slice of the pixel tile: rows [crank * slice_rows, ...) in (w, h, n) order, to every CTA
+              const int first = (int)crank * p.slice_rows;
+              const int ni0 = first / (p.bw * p.bh), hi0 = (first / p.bw) % p.bh;
+              tma_load_4d_mc(&tmap_x, &full_bar[stage], sa + (size_t)crank * p.slice_bytes, kcx * p.kc, t.w0 + kx - p.pad,
+                             t.h0 + hi0 + ky - p.pad, t.n0 + ni0, cmask);
+            } else {
+              tma_load_4d(&tmap_x, &full_bar[stage], sa, kcx * p.kc, t.w0 + kx - p.pad, t.h0 + ky - p.pad, t.n0);
+            }
             tma_load_3d(&tmap_w, &full_bar[stage], sb, kcx * p.kc, t.co0, tap);
             if (++stage == p.stages) {
               stage = 0;
@@ -167,7 +186,8 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             const uint64_t bdesc = umma_desc(sb + k * 32, 16, p.sbo_bytes, p.layout_type);
             tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
-          tc_commit(&empty_bar[stage]);
+          if (kMc) tc_commit_mc(&empty_bar[stage], cmask);
+          else tc_commit(&empty_bar[stage]);
           if (kb == k_blocks - 1) tc_commit(&tmem_full[acc]);
           if (++stage == p.stages) {
             stage = 0;
@@ -247,6 +267,7 @@ conv_fprop_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  if (kMc) cluster_sync_all();       // no CTA leaves while a peer may still multicast into it or arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -309,11 +330,31 @@ int launch_conv_fprop(const void* x, const void* wpack, void* out, int N, int H,
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.act = act; p.slope = slope;
 
+  // cluster size for the A multicast: the largest of 8 / 4 / 2 that divides the number of n-blocks (128-byte rows and
+  // whole 8-row swizzle atoms per slice only); BG_FPROP_MC=0 switches it off
+  p.csize = 1;
+  {
+    static int mc_on = -1;
+    if (mc_on < 0) { const char* e = getenv("BG_FPROP_MC"); mc_on = (e && e[0] == '0') ? 0 : 1; }
+    if (mc_on && row_bytes == 128 && p.n_blocks >= 2 && p.bw * p.bh * p.bn == 128)
+      for (int c = 8; c >= 2; c >>= 1)
+        if (p.n_blocks % c == 0) { p.csize = c; break; }
+  }
+  p.slice_rows = 128 / p.csize;
+  p.slice_bytes = (uint32_t)p.slice_rows * (uint32_t)row_bytes;
   CUtensorMap tmx, tmw;
   {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
     uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
     uint32_t box[4] = {(uint32_t)p.kc, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+    if (p.csize > 1) {
+      // one slice: slice_rows consecutive rows of the (w, h, n)-ordered tile = whole image rows, or whole images
+      const int per_img = p.bw * p.bh;
+      if (p.slice_rows >= per_img) { box[3] = (uint32_t)(p.slice_rows / per_img); }
+      else { box[2] = (uint32_t)(p.slice_rows / p.bw); box[3] = 1u; }
+      BG_REQUIRE(p.slice_rows % p.bw == 0 && (p.slice_rows >= per_img ? p.slice_rows % per_img == 0 : per_img % p.slice_rows == 0),
+                 "conv_fprop: multicast slice does not tile the pixel box");
+    }
     if (make_tmap_bf16(&tmx, x, 4, dims, str, box, row_bytes) != 0) return 1;
   }
   {
@@ -326,11 +367,18 @@ int launch_conv_fprop(const void* x, const void* wpack, void* out, int N, int H,
   const size_t smem_bytes = (size_t)p.stages * p.stage_bytes + aux_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    BG_CHECK_CUDA(cudaFuncSetAttribute(conv_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BG_CHECK_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BG_CHECK_CUDA(cudaFuncSetAttribute(conv_fprop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  BG_CHECK_CUDA(launch_pdl(conv_fprop_kernel, grid, kThreads, smem_bytes, stream, tmx, tmw, p));
+  if (p.csize > 1) {
+    // whole clusters only: the CTAs of a cluster walk the tile list in lock step (same pixel tile, consecutive n-blocks)
+    grid = (grid / p.csize) * p.csize;
+    BG_CHECK_CUDA(launch_pdl_cluster(conv_fprop_kernel<true>, grid, kThreads, smem_bytes, stream, p.csize, tmx, tmw, p));
+    return 0;
+  }
+  BG_CHECK_CUDA(launch_pdl(conv_fprop_kernel<false>, grid, kThreads, smem_bytes, stream, tmx, tmw, p));
   return 0;
 }
 
