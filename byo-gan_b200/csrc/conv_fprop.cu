@@ -331,11 +331,14 @@ int launch_conv_fprop(const void* x, const void* wpack, void* out, int N, int H,
   p.act = act; p.slope = slope;
 
   // cluster size for the A multicast: the largest of 8 / 4 / 2 that divides the number of n-blocks (128-byte rows and
-  // whole 8-row swizzle atoms per slice only); BG_FPROP_MC=0 switches it off
+  // whole 8-row swizzle atoms per slice only).  OFF by default (BG_FPROP_MC=1 enables it): measured on B200 it HALVES
+  // the speed of the 4x4 / 8x8 layers (512 -> 512, batch 32: 37 -> 73 us, profiles/r2_conv_fprop_multicast.txt) — eight
+  // CTAs advancing in lock step through 2 KB multicast slices lose more to the cluster-wide stage hand-shake than the
+  // 2.4x lower L2 -> shared-memory traffic gains.  Kept as a measured negative result.
   p.csize = 1;
   {
     static int mc_on = -1;
-    if (mc_on < 0) { const char* e = getenv("BG_FPROP_MC"); mc_on = (e && e[0] == '0') ? 0 : 1; }
+    if (mc_on < 0) { const char* e = getenv("BG_FPROP_MC"); mc_on = (e && e[0] == '1') ? 1 : 0; }
     if (mc_on && row_bytes == 128 && p.n_blocks >= 2 && p.bw * p.bh * p.bn == 128)
       for (int c = 8; c >= 2; c >>= 1)
         if (p.n_blocks % c == 0) { p.csize = c; break; }

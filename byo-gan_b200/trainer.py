@@ -197,6 +197,9 @@ class Trainer:
             torch.cuda.current_stream().wait_stream(side)
             g = torch.cuda.CUDAGraph()
             self._mix_count = count0
+            # every weight pack must be (re)built INSIDE the graph: a pack cached by the eager iteration above would be
+            # read by every replay without ever being refreshed (and its memory is recycled once the cache drops it)
+            self._forget_packs()
             calls0 = bgn.launch_count
             with torch.cuda.graph(g, pool=self._pool):
                 out = self._step(st["real"], st["z_d"], st["z_g"], alpha_g)
