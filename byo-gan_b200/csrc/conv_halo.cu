@@ -829,34 +829,43 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
       // per-sample, per-border-class bias row (AdaIN shift folded through the conv), else the plain bias in smem
       const int cls = (h == 0 ? 0 : (h == p.H - 1 ? 2 : 1)) * 3 + (w == 0 ? 0 : (w == p.W - 1 ? 2 : 1));
       const float* btab = p.bias_tab != nullptr ? p.bias_tab + ((size_t)t.n * 9 + cls) * p.Cout + t.co0 : nullptr;
+      const bool staged = !p.pool;
+      // line-wise load of the gate tile of round c0 into the (warp-private) stage: lane -> (row = lane / cpr + i * 32 / cpr,
+      // chunk = lane % cpr)
+      auto stage_gate = [&](int c0) {
+        const int cpr = 1 << cpr_shift;
+        const int ch = lane & (cpr - 1);
+#pragma unroll 4
+        for (int row = lane >> cpr_shift; row < 32; row += 32 >> cpr_shift) {
+          const size_t gp = pix_q0 + (size_t)(row >> 3) * os * out_w + (size_t)(row & 7) * os;
+          const uint4 gv = *reinterpret_cast<const uint4*>(p.gate_src + gp * p.Cout + t.co0 + c0 + ch * 8);
+          const uint32_t swz = (uint32_t)(row >> (3 - cpr_shift)) & (uint32_t)(cpr - 1);
+          sts128(stg + (uint32_t)row * rb + (((uint32_t)ch ^ swz) << 4), gv);
+        }
+        __syncwarp();
+      };
+      // the first round's gate tile is fetched BEFORE waiting for the accumulator: its DRAM latency (14 % of the
+      // epilogue warps' time in profiles/r2_ncu_pool4_dgrad_stalls.txt) then overlaps the tile's MMAs
+      if (staged && p.gate_src != nullptr && !(p.debug & 8)) stage_gate(0);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u + (uint32_t)half * 128u;
       const int ncols = (p.debug & 8) ? 0 : p.block_n;
+      // dgrad / tangent passes have neither bias nor noise: skip the 16 shared-memory loads and 64 adds per 64 channels
+      const bool has_add = btab != nullptr || p.bias != nullptr || p.noise != nullptr;
       for (int c0 = 0; c0 < ncols; c0 += round_cols) {
-        const bool staged = !p.pool;
-        if (staged && p.gate_src != nullptr) {
-          // line-wise load of the gate tile into the stage: lane -> (row = lane / cpr + i * 32 / cpr, chunk = lane % cpr)
-          const int cpr = 1 << cpr_shift;
-          const int ch = lane & (cpr - 1);
-#pragma unroll 4
-          for (int row = lane >> cpr_shift; row < 32; row += 32 >> cpr_shift) {
-            const size_t gp = pix_q0 + (size_t)(row >> 3) * os * out_w + (size_t)(row & 7) * os;
-            const uint4 gv = *reinterpret_cast<const uint4*>(p.gate_src + gp * p.Cout + t.co0 + c0 + ch * 8);
-            const uint32_t swz = (uint32_t)(row >> (3 - cpr_shift)) & (uint32_t)(cpr - 1);
-            sts128(stg + (uint32_t)row * rb + (((uint32_t)ch ^ swz) << 4), gv);
-          }
-          __syncwarp();
-        }
+        if (c0 > 0 && staged && p.gate_src != nullptr) stage_gate(c0);
         for (int c = c0; c < c0 + round_cols; c += 16) {
           uint32_t v[16];
           tmem_ld_x16(taddr + c, v);
           float bn[16];
+          if (has_add) {
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 b4 = btab != nullptr ? __ldg(reinterpret_cast<const float4*>(btab + c + 4 * j4))
-                                              : lds128f(bias_s + t.co0 + c + 4 * j4);
-            bn[4 * j4 + 0] = b4.x; bn[4 * j4 + 1] = b4.y; bn[4 * j4 + 2] = b4.z; bn[4 * j4 + 3] = b4.w;
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 b4 = btab != nullptr ? __ldg(reinterpret_cast<const float4*>(btab + c + 4 * j4))
+                                                : lds128f(bias_s + t.co0 + c + 4 * j4);
+              bn[4 * j4 + 0] = b4.x; bn[4 * j4 + 1] = b4.y; bn[4 * j4 + 2] = b4.z; bn[4 * j4 + 3] = b4.w;
+            }
           }
           if (p.noise != nullptr) {
 #pragma unroll
@@ -884,8 +893,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
           }
           tmem_ld_wait();
           float f[16];
+          if (has_add) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + bn[j];
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + bn[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+          }
           if (p.pool) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -938,13 +952,22 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
               *reinterpret_cast<uint4*>(p.out + op * p.Cout + t.co0 + c0 + ch * 8) = ov;
               if (st_on) {
                 const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w};
+                if (p.stats_mode == 1) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 f2 = unpack_bf16x2(ow[j]);
-                  sa[2 * j] += f2.x;
-                  sa[2 * j + 1] += f2.y;
-                  sq[2 * j] = fmaf(f2.x, f2.x, sq[2 * j]);
-                  sq[2 * j + 1] = fmaf(f2.y, f2.y, sq[2 * j + 1]);
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 f2 = unpack_bf16x2(ow[j]);
+                    sa[2 * j] += f2.x;
+                    sa[2 * j + 1] += f2.y;
+                    sq[2 * j] = fmaf(f2.x, f2.x, sq[2 * j]);
+                    sq[2 * j + 1] = fmaf(f2.y, f2.y, sq[2 * j + 1]);
+                  }
+                } else {                         // stats_mode 2 (bias gradient): plain sums only
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 f2 = unpack_bf16x2(ow[j]);
+                    sa[2 * j] += f2.x;
+                    sa[2 * j + 1] += f2.y;
+                  }
                 }
               }
             }

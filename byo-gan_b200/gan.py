@@ -25,8 +25,15 @@ from math import sqrt
 import torch
 from torch import nn
 
+import os
+
 import engine
+import lazy
 from engine import PackCache
+
+# Opt-in host-overhead shims for an unmodified train.py (lazy.py); both default off
+DEFER_LOSS_ITEMS = os.environ.get("BG_DEFER_ITEMS", "0") == "1"        # loss.item() returns a float-like that syncs on use
+LAZY_NO_GRAD_FORWARD = os.environ.get("BG_LAZY_PREVIEW", "0") == "1"   # no_grad forwards run when their result is first used
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -274,13 +281,25 @@ class Generator(nn.Module):
         noise = tuple(noise[:steps])
         fade = alpha is not None and steps > 1
         params = engine.generator_params(self, steps, fade)
+        if LAZY_NO_GRAD_FORWARD and not torch.is_grad_enabled():
+            # the noise above is already drawn (same RNG consumption as the reference); the kernels run on first use
+            z_now, z2_now = z_noise.detach().clone(), None if z2 is None else z2.detach().clone()
+
+            def thunk():
+                with torch.no_grad():
+                    return _GeneratorFn.apply(self, steps, alpha, crossover, len(noise), z_now, z2_now, *noise, *params)
+
+            r = 4 * 2 ** (steps - 1)
+            return lazy.LazyImages(thunk, (batch, 3, r, r), z_noise.device)
         return _GeneratorFn.apply(self, steps, alpha, crossover, len(noise), z_noise, z2, *noise, *params)
 
     def get_wgan_loss(self, crit_fake_pred):
-        return -crit_fake_pred.mean()                     # gan.py:224-225
+        loss = -crit_fake_pred.mean()                     # gan.py:224-225
+        return lazy.defer_item(loss) if DEFER_LOSS_ITEMS else loss
 
     def get_r1_loss(self, crit_fake_pred):
-        return _LogisticLossFn.apply(crit_fake_pred, -1.0)   # softplus(-pred).mean(), gan.py:227-228
+        loss = _LogisticLossFn.apply(crit_fake_pred, -1.0)   # softplus(-pred).mean(), gan.py:227-228
+        return lazy.defer_item(loss) if DEFER_LOSS_ITEMS else loss
 
 
 class Critic(nn.Module):
@@ -352,7 +371,7 @@ class Critic(nn.Module):
         loss, _, g_m = engine.critic_wgan_gp_step(self, self._packs, tape_f, crit_fake_pred, tape_r, crit_real_pred,
                                                   tape_m, c_lambda, emit=self._emit_into_grad())
         self.last_mixed_image_grad = g_m                  # d sum(D(mixed)) / d mixed, what autograd.grad returned
-        return loss
+        return lazy.defer_item(loss) if DEFER_LOSS_ITEMS else loss
 
     def get_r1_loss(self, crit_fake_pred, crit_real_pred, real_im, fake_im, steps, alpha, c_lambda=1):
         """gan.py:393-412.  Runs the backward itself (like the reference's r1_loss.backward()) and accumulates
@@ -362,4 +381,4 @@ class Critic(nn.Module):
                                              c_lambda, emit=self._emit_into_grad(),
                                              first_order=not getattr(self, "_r1_penalty_only", False))
         self.last_real_image_grad = g_x                   # d sum(D(real)) / d real, what autograd.grad returned
-        return loss
+        return lazy.defer_item(loss) if DEFER_LOSS_ITEMS else loss

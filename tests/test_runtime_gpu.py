@@ -236,3 +236,54 @@ def test_cuda_graph_iterations_equal_eager_iterations(mix):
     for pa, pb in zip(probes_a, probes_b):
         assert U.rel(pb, pa) < 0.2, U.rel(pb, pa)
     assert U.rel(probes_b[1], probes_b[0]) > 1e-3          # the eager preview after more replays sees newer weights
+
+
+def test_deferred_item_and_lazy_preview_shims():
+    """lazy.py (opt-in, for an unmodified train.py): `.item()` on the losses returns a float-like that synchronises only
+    when used; no_grad forwards run when their result is first touched, with the SAME images as the eager forward (the
+    noise is drawn up front from torch's generator exactly as the reference does)."""
+    import gan
+    import lazy
+
+    U.no_tf32()
+    g, c = U.build_models(4)
+    steps, batch = 3, 8
+    z = O.make_latents(25, 7).cuda()
+    try:
+        gan.LAZY_NO_GRAD_FORWARD = True
+        gan.DEFER_LOSS_ITEMS = True
+        with U.deterministic():
+            torch.manual_seed(11)
+            with torch.no_grad():
+                lazy_img = g(z, alpha=0.3, steps=steps)                   # train.py:237
+            assert isinstance(lazy_img, lazy.LazyImages) and not lazy_img.computed
+            assert lazy_img.shape == (25, 3, 16, 16) and lazy_img.is_cuda and len(lazy_img) == 25
+            after = torch.randn(4, device="cuda")                          # the RNG stream has moved past the noise draws
+            shown = torch.clamp(lazy_img, 0, 1)                            # train.py:239: first use runs the kernels
+            assert lazy_img.computed and type(shown) is torch.Tensor
+            gan.LAZY_NO_GRAD_FORWARD = False
+            torch.manual_seed(11)
+            with torch.no_grad():
+                eager = g(z, alpha=0.3, steps=steps)
+            assert torch.equal(torch.randn(4, device="cuda"), after)
+            assert torch.equal(shown, torch.clamp(eager, 0, 1))
+            # with grad enabled nothing is deferred (training forwards)
+            gan.LAZY_NO_GRAD_FORWARD = True
+            assert type(g(z.clone().requires_grad_(), steps=steps)) is torch.Tensor
+        # losses: .item() is a LazyScalar that behaves like the float train.py expects
+        real = O.make_images(batch, steps, 3).cuda().requires_grad_()
+        fake = g(O.make_latents(batch, 8).cuda().requires_grad_(), steps=steps)
+        c.zero_grad()
+        c_loss = c.get_r1_loss(c(fake.detach(), steps, None), c(real, steps, None), real, fake, steps, None, 10)
+        g_loss = g.get_r1_loss(c(fake, steps, None))
+        g_loss.backward()                                                  # still an ordinary differentiable tensor
+        hist = [c_loss.item(), g_loss.item()]
+        assert all(isinstance(h, lazy.LazyScalar) for h in hist)
+        avg = sum(hist[-2:]) / 2                                           # train.py:222-227
+        assert isinstance(avg, float) and abs(avg - (float(c_loss) + float(g_loss)) / 2) < 1e-6
+        assert f"{hist[0]:.3}" == f"{float(c_loss):.3}"
+        gan.DEFER_LOSS_ITEMS = False
+        assert isinstance(g.get_r1_loss(c(fake.detach(), steps, None)).item(), float)
+    finally:
+        gan.LAZY_NO_GRAD_FORWARD = False
+        gan.DEFER_LOSS_ITEMS = False
