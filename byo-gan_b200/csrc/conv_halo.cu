@@ -912,24 +912,33 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], f[j] * p.slope);      // LeakyReLU, 0 < slope < 1
           }
+          uint4 o0, o1;
           if (p.gate_src != nullptr) {
+            // LeakyReLU backward gate (1 where the saved activation is > 0, slope elsewhere) on PACKED pairs: both
+            // candidates f and slope * f are rounded to bf16x2 and one bf16x2 compare mask (set.gt.bf16x2) picks per
+            // half — 2.5 instructions per element instead of 4.5 (unpack, FSETP, FSEL, FMUL), same values bit for bit
             const uint32_t gw[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+            uint32_t ow[8];
+            const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float2 gv = unpack_bf16x2(gw[j]);
-              f[2 * j] *= gv.x > 0.f ? 1.f : p.slope;
-              f[2 * j + 1] *= gv.y > 0.f ? 1.f : p.slope;
+              const uint32_t m = __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&gw[j]), zero2);
+              const uint32_t keep = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+              const uint32_t scaled = pack_bf16x2(f[2 * j] * p.slope, f[2 * j + 1] * p.slope);
+              ow[j] = (keep & m) | (scaled & ~m);
             }
+            o0 = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            o1 = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+          } else {
+            o0.x = pack_bf16x2(f[0], f[1]);
+            o0.y = pack_bf16x2(f[2], f[3]);
+            o0.z = pack_bf16x2(f[4], f[5]);
+            o0.w = pack_bf16x2(f[6], f[7]);
+            o1.x = pack_bf16x2(f[8], f[9]);
+            o1.y = pack_bf16x2(f[10], f[11]);
+            o1.z = pack_bf16x2(f[12], f[13]);
+            o1.w = pack_bf16x2(f[14], f[15]);
           }
-          uint4 o0, o1;
-          o0.x = pack_bf16x2(f[0], f[1]);
-          o0.y = pack_bf16x2(f[2], f[3]);
-          o0.z = pack_bf16x2(f[4], f[5]);
-          o0.w = pack_bf16x2(f[6], f[7]);
-          o1.x = pack_bf16x2(f[8], f[9]);
-          o1.y = pack_bf16x2(f[10], f[11]);
-          o1.z = pack_bf16x2(f[12], f[13]);
-          o1.w = pack_bf16x2(f[14], f[15]);
           if (staged) {
             sts128(sa0, o0);
             sts128(sa1, o1);
@@ -952,22 +961,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
               *reinterpret_cast<uint4*>(p.out + op * p.Cout + t.co0 + c0 + ch * 8) = ov;
               if (st_on) {
                 const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w};
-                if (p.stats_mode == 1) {
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const float2 f2 = unpack_bf16x2(ow[j]);
-                    sa[2 * j] += f2.x;
-                    sa[2 * j + 1] += f2.y;
-                    sq[2 * j] = fmaf(f2.x, f2.x, sq[2 * j]);
-                    sq[2 * j + 1] = fmaf(f2.y, f2.y, sq[2 * j + 1]);
-                  }
-                } else {                         // stats_mode 2 (bias gradient): plain sums only
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const float2 f2 = unpack_bf16x2(ow[j]);
-                    sa[2 * j] += f2.x;
-                    sa[2 * j + 1] += f2.y;
-                  }
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f2 = unpack_bf16x2(ow[j]);
+                  sa[2 * j] += f2.x;
+                  sa[2 * j + 1] += f2.y;
+                  sq[2 * j] = fmaf(f2.x, f2.x, sq[2 * j]);
+                  sq[2 * j + 1] = fmaf(f2.y, f2.y, sq[2 * j + 1]);
                 }
               }
             }
