@@ -113,6 +113,7 @@ struct HaloParams {
   // 4 + 4 KB, which takes the operand fetch off the 128 B/clk shared-memory limit that N = 128 sits on.
   // b_tx_bytes / b_tile_bytes describe the per-CTA half tile.  Tile indices handed to decode_tile are PAIR indices.
   int cta2;
+  int epi_templated;   // 1: epilogue specialised for the stage row width (default); BG_EPI_TEMPLATED=0: run-time widths
 };
 
 struct TileCoord {
@@ -631,152 +632,17 @@ __device__ __forceinline__ void stats_flush(const HaloParams& p, float* slices, 
   asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * kEpiWarps) : "memory");
 }
 
-template <bool kStats, int kFeed, bool kCta2>     // kFeed: 0 TMA halo (plain and pool4), 1 upsample producers
-__global__ void __launch_bounds__(kThreads, 1)
-conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
-                 const HaloParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-
-  // carve: [B region (1024-aligned tiles)] [A stages] [epilogue transpose stages] [aux]
-  const int b_tiles = p.b_resident ? p.k_chunks * p.taps : p.b_stages;
-  uint8_t* b_base = smem;
-  uint8_t* a_base = b_base + (size_t)b_tiles * p.b_tile_bytes;
-  uint8_t* patch_base = a_base + (size_t)p.a_stages * p.a_stage_bytes;
-  patch_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(patch_base) + 127) & ~uintptr_t(127));
-  uint8_t* epi_base = patch_base + (p.upsample ? (size_t)kPatchStages * p.patch_bytes : 0);
-  epi_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(epi_base) + 127) & ~uintptr_t(127));
-  constexpr bool kUp = kFeed != 0;        // warps 10..17 feed the halo instead of being the second epilogue set
-  const int kEpiWarpsAll = kUp ? kEpiWarps : kEpiWarps * p.epi_sets;
-  uint8_t* aux = epi_base + (size_t)kEpiWarpsAll * 32 * p.epi_row_bytes;
-  uint64_t* b_full = reinterpret_cast<uint64_t*>(aux);
-  uint64_t* b_empty = b_full + kMaxBStages;
-  uint64_t* a_full = b_empty + kMaxBStages;
-  uint64_t* a_empty = a_full + kMaxAStages;
-  uint64_t* tmem_full = a_empty + kMaxAStages;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);
-  float* nw_s = bias_s + 512;
-  float* stat_s = nw_s + 512;             // [kEpiWarps][Cout][2], only carved when stats_mode != 0
-
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform role index
-  const int lane = threadIdx.x & 31;
-  const uint32_t crank = kCta2 ? cluster_ctarank() : 0u;                   // 0 = leader of the CTA pair
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_w);
-    tma_prefetch_desc(&tmap_x);
-    for (int s = 0; s < kMaxBStages; ++s) {
-      mbar_init(&b_full[s], 1);
-      mbar_init(&b_empty[s], (uint32_t)p.issuers);
-    }
-    for (int s = 0; s < kMaxAStages; ++s) {
-      mbar_init(&a_full[s], kUp ? kProdThreads : 1);
-      mbar_init(&a_empty[s], (uint32_t)p.issuers);
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&tmem_full[s], (uint32_t)p.issuers);
-      mbar_init(&tmem_empty[s], kCta2 ? 2 * kEpiWarps : kEpiWarps);   // pair mode: the leader's copy counts both CTAs
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    if (kCta2) {
-      tmem_alloc2(tmem_slot, kTmemCols);        // one warp of EACH CTA of the pair takes part
-      tmem_relinquish2();
-    } else {
-      tmem_alloc(tmem_slot, kTmemCols);
-      tmem_relinquish();
-    }
-    // only now may the next kernel of the stream become resident: released at kernel entry, a dependent CTA that landed
-    // on this SM could take the TMEM columns first and then wait for this grid, which would be waiting for the columns
-    pdl_launch_dependents();
-  }
-  pdl_wait();        // barrier init, TMEM allocation and descriptor prefetch above overlap the previous kernel's tail
-  if (warp >= 2 && warp < 2 + kEpiWarpsAll) {
-    for (int c = threadIdx.x - 64; c < p.Cout; c += 32 * kEpiWarpsAll) {
-      bias_s[c] = p.bias ? p.bias[c] : 0.f;
-      nw_s[c] = p.noise_w ? p.noise_w[c] : 0.f;
-    }
-    if (kStats)
-      for (int i = threadIdx.x - 64; i < kEpiWarpsAll * p.Cout * 2; i += 32 * kEpiWarpsAll) stat_s[i] = 0.f;
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (kCta2) cluster_sync_all();     // the peer's barriers are initialised and its TMEM allocated before anything remote
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  int tile_lo, tile_hi, tile_step;
-  tile_range(p, tile_lo, tile_hi, tile_step);
-
-  if (warp == 0) {
-    // ------------------------------ weight TMA producer ------------------------------
-    if (lane == 0) {
-      if (p.b_resident) {
-        // residency is only selected when there is a single n-block: the whole pack is loaded once per kernel, or,
-        // with per-sample weights, once per sample of this CTA's (contiguous) tile range — after the MMA warp has
-        // committed the last tile that used the previous sample's pack (b_empty[0]).
-        int cur = -1;
-        uint32_t loads = 0;
-        for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
-          const int wn = p.per_sample_w ? decode_tile(p, tile).n : 0;
-          if (wn == cur) continue;
-          if (loads > 0) mbar_wait(&b_empty[0], (loads - 1u) & 1u);
-          // pair mode: this CTA keeps rows [crank * block_n / 2, ...) of every tile; all bytes count on the leader's barrier
-          if (!kCta2 || crank == 0)
-            mbar_expect_tx(&b_full[0], (uint32_t)(p.k_chunks * p.taps) * p.b_tx_bytes * (kCta2 ? 2u : 1u));
-          const uint32_t full_addr = kCta2 ? mapa_cta(smem_u32(&b_full[0]), 0u) : 0u;
-          for (int kcx = 0; kcx < p.k_chunks; ++kcx)
-            for (int tap = 0; tap < p.taps; ++tap) {
-              uint8_t* dst = b_base + (size_t)(kcx * p.taps + tap) * p.b_tile_bytes;
-              if (kCta2) tma_load_4d_2sm(&tmap_w, full_addr, dst, kcx * p.kc, (int)crank * (p.block_n >> 1), tap, wn);
-              else tma_load_4d(&tmap_w, &b_full[0], dst, kcx * p.kc, 0, tap, wn);
-            }
-          cur = wn;
-          ++loads;
-        }
-      } else {
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
-          const TileCoord t = decode_tile(p, tile);
-          for (int kcx = 0; kcx < p.k_chunks; ++kcx) {
-            const int ntap = p.tconv4 ? 4 : p.taps;
-            for (int ti = 0; ti < ntap; ++ti) {
-              // the order the MMA warp consumes them
-              const int tap = p.tconv4 ? t.ph * 4 + ti : (p.pool4_tma ? pool4_tap(ti >> 2, ti & 3) : ti);
-              mbar_wait(&b_empty[stage], phase ^ 1u);
-              if (kCta2) {
-                if (crank == 0) mbar_expect_tx(&b_full[stage], 2u * p.b_tx_bytes);
-                tma_load_4d_2sm(&tmap_w, mapa_cta(smem_u32(&b_full[stage]), 0u), b_base + (size_t)stage * p.b_tile_bytes,
-                                kcx * p.kc, t.co0 + (int)crank * (p.block_n >> 1), tap, p.per_sample_w ? t.n : 0);
-              } else {
-                mbar_expect_tx(&b_full[stage], p.b_tx_bytes);
-                tma_load_4d(&tmap_w, &b_full[stage], b_base + (size_t)stage * p.b_tile_bytes, kcx * p.kc, t.co0, tap,
-                            p.per_sample_w ? t.n : 0);
-              }
-              if (++stage == p.b_stages) {
-                stage = 0;
-                phase ^= 1u;
-              }
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1 || (warp == kIssuer2 && p.issuers == 2)) {
-    // ------------------------------ MMA issuer(s) ------------------------------
-    if (kCta2 && crank != 0) {
-      // the leader CTA issues the pair's instructions; this CTA's MMA warps have nothing to do
-    } else if (p.issuers == 2) {
-      if (warp == 1) issue_dispatch<kStats, kFeed, 0, kCta2>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
-      else issue_dispatch<kStats, kFeed, 1, kCta2>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
-    } else {
-      issue_dispatch<kStats, kFeed, -1, kCta2>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
-    }
-  } else if (warp < 2 + kEpiWarpsAll) {
+// ---------------------------------------------------------------------------------------------------------
+// Epilogue (one warp): TMEM -> registers -> bias / noise / activation / gate -> bf16 -> swizzled transpose stage ->
+// 128-byte-line global stores (+ fused reductions).  Templated on the stage row width: an ncu capture of the narrow
+// layers (profiles/r2_ncu_pool4_dgrad_stalls.txt) shows the SM issuing instructions 55 % of the time, ~30 thread
+// instructions per output element, most of them the run-time swizzle / address arithmetic of these loops.
+// ---------------------------------------------------------------------------------------------------------
+template <bool kStats, bool kUp, bool kCta2, int CPRS>
+__device__ __forceinline__ void epilogue_warp(const HaloParams& p, const int warp, const int lane, const uint32_t crank,
+                                              const uint32_t tmem_base, uint64_t* tmem_full, uint64_t* tmem_empty,
+                                              uint8_t* epi_base, float* bias_s, float* nw_s, float* stat_s, const int tile_lo,
+                                              const int tile_hi, const int tile_step) {
     // ------------------------------ epilogue ------------------------------
     // Warp e = warp - 2: TMEM lane quarter q = warp & 3 (hardware rule), MMA half = e / 4.  Lane i holds MMA row
     // m = 32q + i = pixel (image row g = m / 8, column r = m % 8 of the half's 8-wide segment).
@@ -787,8 +653,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     const bool pool_writer = ((lane & 1) == 0) && ((lane & 8) == 0);
     // transpose stage of this warp: 32 pixel rows x epi_row_bytes, 16-byte chunks XOR-swizzled by row so that both
     // the row-wise (lane = pixel) and the line-wise (8 lanes = 128 contiguous bytes) accesses are conflict-free
-    const uint32_t rb = p.epi_row_bytes;
-    const int cpr_shift = rb == 128 ? 3 : (rb == 64 ? 2 : 1);       // log2(chunks per row)
+    // CPRS >= 0: the row width is a compile-time constant (16 << CPRS bytes), so the swizzle / address arithmetic of the
+    // transpose loops folds and the loops unroll; CPRS < 0: taken from the launch parameters (BG_EPI_TEMPLATED=0)
+    const uint32_t rb = CPRS >= 0 ? (16u << (CPRS >= 0 ? CPRS : 0)) : p.epi_row_bytes;
+    const int cpr_shift = CPRS >= 0 ? CPRS : (rb == 128 ? 3 : (rb == 64 ? 2 : 1));       // log2(chunks per row)
     const int round_cols = (int)(rb >> 1);                          // output channels per transpose round
     const uint32_t stg = smem_u32(epi_base) + (uint32_t)(warp - 2) * 32u * rb;
     const uint32_t my_row = stg + (uint32_t)lane * rb;
@@ -993,6 +861,163 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
       if (st_regs) stats_round(st_slice, sa, sq, cpr_shift, lane, 0);
       stats_flush(p, st_set, st_et, st_n, 1 + eset);
     }
+}
+
+template <bool kStats, int kFeed, bool kCta2>     // kFeed: 0 TMA halo (plain and pool4), 1 upsample producers
+__global__ void __launch_bounds__(kThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
+                 const HaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+
+  // carve: [B region (1024-aligned tiles)] [A stages] [epilogue transpose stages] [aux]
+  const int b_tiles = p.b_resident ? p.k_chunks * p.taps : p.b_stages;
+  uint8_t* b_base = smem;
+  uint8_t* a_base = b_base + (size_t)b_tiles * p.b_tile_bytes;
+  uint8_t* patch_base = a_base + (size_t)p.a_stages * p.a_stage_bytes;
+  patch_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(patch_base) + 127) & ~uintptr_t(127));
+  uint8_t* epi_base = patch_base + (p.upsample ? (size_t)kPatchStages * p.patch_bytes : 0);
+  epi_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(epi_base) + 127) & ~uintptr_t(127));
+  constexpr bool kUp = kFeed != 0;        // warps 10..17 feed the halo instead of being the second epilogue set
+  const int kEpiWarpsAll = kUp ? kEpiWarps : kEpiWarps * p.epi_sets;
+  uint8_t* aux = epi_base + (size_t)kEpiWarpsAll * 32 * p.epi_row_bytes;
+  uint64_t* b_full = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* b_empty = b_full + kMaxBStages;
+  uint64_t* a_full = b_empty + kMaxBStages;
+  uint64_t* a_empty = a_full + kMaxAStages;
+  uint64_t* tmem_full = a_empty + kMaxAStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);
+  float* nw_s = bias_s + 512;
+  float* stat_s = nw_s + 512;             // [kEpiWarps][Cout][2], only carved when stats_mode != 0
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform role index
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = kCta2 ? cluster_ctarank() : 0u;                   // 0 = leader of the CTA pair
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_x);
+    for (int s = 0; s < kMaxBStages; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], (uint32_t)p.issuers);
+    }
+    for (int s = 0; s < kMaxAStages; ++s) {
+      mbar_init(&a_full[s], kUp ? kProdThreads : 1);
+      mbar_init(&a_empty[s], (uint32_t)p.issuers);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], (uint32_t)p.issuers);
+      mbar_init(&tmem_empty[s], kCta2 ? 2 * kEpiWarps : kEpiWarps);   // pair mode: the leader's copy counts both CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    if (kCta2) {
+      tmem_alloc2(tmem_slot, kTmemCols);        // one warp of EACH CTA of the pair takes part
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_slot, kTmemCols);
+      tmem_relinquish();
+    }
+    // only now may the next kernel of the stream become resident: released at kernel entry, a dependent CTA that landed
+    // on this SM could take the TMEM columns first and then wait for this grid, which would be waiting for the columns
+    pdl_launch_dependents();
+  }
+  pdl_wait();        // barrier init, TMEM allocation and descriptor prefetch above overlap the previous kernel's tail
+  if (warp >= 2 && warp < 2 + kEpiWarpsAll) {
+    for (int c = threadIdx.x - 64; c < p.Cout; c += 32 * kEpiWarpsAll) {
+      bias_s[c] = p.bias ? p.bias[c] : 0.f;
+      nw_s[c] = p.noise_w ? p.noise_w[c] : 0.f;
+    }
+    if (kStats)
+      for (int i = threadIdx.x - 64; i < kEpiWarpsAll * p.Cout * 2; i += 32 * kEpiWarpsAll) stat_s[i] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (kCta2) cluster_sync_all();     // the peer's barriers are initialised and its TMEM allocated before anything remote
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  int tile_lo, tile_hi, tile_step;
+  tile_range(p, tile_lo, tile_hi, tile_step);
+
+  if (warp == 0) {
+    // ------------------------------ weight TMA producer ------------------------------
+    if (lane == 0) {
+      if (p.b_resident) {
+        // residency is only selected when there is a single n-block: the whole pack is loaded once per kernel, or,
+        // with per-sample weights, once per sample of this CTA's (contiguous) tile range — after the MMA warp has
+        // committed the last tile that used the previous sample's pack (b_empty[0]).
+        int cur = -1;
+        uint32_t loads = 0;
+        for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
+          const int wn = p.per_sample_w ? decode_tile(p, tile).n : 0;
+          if (wn == cur) continue;
+          if (loads > 0) mbar_wait(&b_empty[0], (loads - 1u) & 1u);
+          // pair mode: this CTA keeps rows [crank * block_n / 2, ...) of every tile; all bytes count on the leader's barrier
+          if (!kCta2 || crank == 0)
+            mbar_expect_tx(&b_full[0], (uint32_t)(p.k_chunks * p.taps) * p.b_tx_bytes * (kCta2 ? 2u : 1u));
+          const uint32_t full_addr = kCta2 ? mapa_cta(smem_u32(&b_full[0]), 0u) : 0u;
+          for (int kcx = 0; kcx < p.k_chunks; ++kcx)
+            for (int tap = 0; tap < p.taps; ++tap) {
+              uint8_t* dst = b_base + (size_t)(kcx * p.taps + tap) * p.b_tile_bytes;
+              if (kCta2) tma_load_4d_2sm(&tmap_w, full_addr, dst, kcx * p.kc, (int)crank * (p.block_n >> 1), tap, wn);
+              else tma_load_4d(&tmap_w, &b_full[0], dst, kcx * p.kc, 0, tap, wn);
+            }
+          cur = wn;
+          ++loads;
+        }
+      } else {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = tile_lo; tile < tile_hi; tile += tile_step) {
+          const TileCoord t = decode_tile(p, tile);
+          for (int kcx = 0; kcx < p.k_chunks; ++kcx) {
+            const int ntap = p.tconv4 ? 4 : p.taps;
+            for (int ti = 0; ti < ntap; ++ti) {
+              // the order the MMA warp consumes them
+              const int tap = p.tconv4 ? t.ph * 4 + ti : (p.pool4_tma ? pool4_tap(ti >> 2, ti & 3) : ti);
+              mbar_wait(&b_empty[stage], phase ^ 1u);
+              if (kCta2) {
+                if (crank == 0) mbar_expect_tx(&b_full[stage], 2u * p.b_tx_bytes);
+                tma_load_4d_2sm(&tmap_w, mapa_cta(smem_u32(&b_full[stage]), 0u), b_base + (size_t)stage * p.b_tile_bytes,
+                                kcx * p.kc, t.co0 + (int)crank * (p.block_n >> 1), tap, p.per_sample_w ? t.n : 0);
+              } else {
+                mbar_expect_tx(&b_full[stage], p.b_tx_bytes);
+                tma_load_4d(&tmap_w, &b_full[stage], b_base + (size_t)stage * p.b_tile_bytes, kcx * p.kc, t.co0, tap,
+                            p.per_sample_w ? t.n : 0);
+              }
+              if (++stage == p.b_stages) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 || (warp == kIssuer2 && p.issuers == 2)) {
+    // ------------------------------ MMA issuer(s) ------------------------------
+    if (kCta2 && crank != 0) {
+      // the leader CTA issues the pair's instructions; this CTA's MMA warps have nothing to do
+    } else if (p.issuers == 2) {
+      if (warp == 1) issue_dispatch<kStats, kFeed, 0, kCta2>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+      else issue_dispatch<kStats, kFeed, 1, kCta2>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+    } else {
+      issue_dispatch<kStats, kFeed, -1, kCta2>(p, a_base, b_base, b_full, b_empty, a_full, a_empty, tmem_full, tmem_empty, tmem_base);
+    }
+  } else if (warp < 2 + kEpiWarpsAll) {
+    // ------------------------------ epilogue (epilogue_warp above) ------------------------------
+    if (p.epi_templated && p.epi_row_bytes == 128u)
+      epilogue_warp<kStats, kUp, kCta2, 3>(p, warp, lane, crank, tmem_base, tmem_full, tmem_empty, epi_base, bias_s, nw_s, stat_s, tile_lo, tile_hi, tile_step);
+    else if (p.epi_templated && p.epi_row_bytes == 64u)
+      epilogue_warp<kStats, kUp, kCta2, 2>(p, warp, lane, crank, tmem_base, tmem_full, tmem_empty, epi_base, bias_s, nw_s, stat_s, tile_lo, tile_hi, tile_step);
+    else if (p.epi_templated && p.epi_row_bytes == 32u)
+      epilogue_warp<kStats, kUp, kCta2, 1>(p, warp, lane, crank, tmem_base, tmem_full, tmem_empty, epi_base, bias_s, nw_s, stat_s, tile_lo, tile_hi, tile_step);
+    else
+      epilogue_warp<kStats, kUp, kCta2, -1>(p, warp, lane, crank, tmem_base, tmem_full, tmem_empty, epi_base, bias_s, nw_s, stat_s, tile_lo, tile_hi, tile_step);
   } else {
     // ------------------------------ halo producers (cp.async, zero-fill padding) ------------------------------
     if (kUp) {
@@ -1180,6 +1205,11 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
     static int issuers = 0;                                     // BG_MMA_ISSUERS=1: the single-thread issue of round-1's first kernels
     if (issuers == 0) { const char* e = getenv("BG_MMA_ISSUERS"); issuers = (e && e[0] == '1') ? 1 : 2; }
     p.issuers = issuers;
+  }
+  {
+    static int epi_t = -1;
+    if (epi_t < 0) { const char* e = getenv("BG_EPI_TEMPLATED"); epi_t = (e && e[0] == '0') ? 0 : 1; }
+    p.epi_templated = epi_t;
   }
   p.a_stages = plan.a_stages;
   p.b_stages = plan.b_stages;
