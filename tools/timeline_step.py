@@ -20,7 +20,7 @@ if len(sys.argv) > 2:
     batch = int(sys.argv[2])
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 dev = torch.device("cuda", 0)
-tr = bench.Trainer(steps, alpha, batch, dev, bdist.GradSync)
+tr = bench.make_trainer(steps, alpha, batch, dev, style_mixing=workload in bench.STYLE_MIXING_DEFAULT)
 R = 4 * 2 ** (steps - 1)
 real = torch.rand(batch, 3, R, R, device=dev) * 2 - 1
 z = torch.randn(2, batch, 512, device=dev).clamp_(-0.75, 0.75)
