@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libbg_b200.so")
 STAMP = os.path.join(HERE, "build", "stamp.txt")
-SOURCES = ["runtime.cu", "conv_fprop.cu", "conv_halo.cu", "conv_wgrad.cu", "conv_wgrad_halo.cu", "aux_kernels.cu", "head_kernels.cu", "api.cu"]
+SOURCES = ["runtime.cu", "conv_fprop.cu", "conv_splitk.cu", "conv_halo.cu", "conv_wgrad.cu", "conv_wgrad_halo.cu", "aux_kernels.cu", "head_kernels.cu", "api.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

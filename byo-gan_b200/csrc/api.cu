@@ -8,6 +8,9 @@ int launch_conv_fprop(const void*, const void*, void*, int, int, int, int, int, 
 int launch_conv_halo(const void*, const void*, void*, int, int, int, int, int, const float*, const float*, const float*,
                      const void*, int, int, float, float*, int, const float*, int, int, cudaStream_t);
 bool conv_halo_supported(int, int, int, int, int, int);
+bool conv_splitk_supported(int, int, int, int, int, int);
+int launch_conv_splitk(const void*, const void*, void*, int, int, int, int, int, const float*, const float*, const float*,
+                       const void*, int, float, cudaStream_t);
 int launch_conv_wgrad(const void*, const void*, float*, int, int, int, int, int, int, cudaStream_t);
 int launch_conv_wgrad_halo(const void*, const void*, float*, int, int, int, int, int, int, int, cudaStream_t);
 int launch_unpack_wgrad_pool4(const float*, float*, int, int, float, int, cudaStream_t);
@@ -85,6 +88,9 @@ int bg_conv_fprop(const void* x, const void* wpack, void* out, int N, int H, int
   if (bg::conv_halo_supported(N, H, W, Cin, Cout, ksize))
     return bg::launch_conv_halo(x, wpack, out, N, H, W, Cin, Cout, bias, noise, noise_w, gate_src, act, 0, slope,
                                 nullptr, 0, nullptr, 0, 0, S(stream));
+  // 4x4 / 8x8 maps: split-K over a thread-block cluster with a distributed-shared-memory reduction (conv_splitk.cu)
+  if (bg::conv_splitk_supported(N, H, W, Cin, Cout, ksize))
+    return bg::launch_conv_splitk(x, wpack, out, N, H, W, Cin, Cout, bias, noise, noise_w, gate_src, act, slope, S(stream));
   return bg::launch_conv_fprop(x, wpack, out, N, H, W, Cin, Cout, ksize, bias, noise, noise_w, gate_src, act, slope,
                                S(stream));
 }
@@ -106,9 +112,11 @@ int bg_conv_fprop_stats(const void* x, const void* wpack, void* out, int N, int 
     return bg::launch_conv_halo(x, wpack, out, N, H, W, Cin, Cout, bias, noise, noise_w, gate_src, act, 0, slope, stats,
                                 stats_mode, nullptr, 0, 0, S(stream));
   }
-  // small maps (< 16x16): tap-wise kernel, then the stand-alone reduction over the (tiny) output
-  int rc = bg::launch_conv_fprop(x, wpack, out, N, H, W, Cin, Cout, ksize, bias, noise, noise_w, gate_src, act, slope,
-                                 S(stream));
+  // small maps (< 16x16): split-K cluster kernel (or the tap-wise one), then the stand-alone reduction over the (tiny) output
+  int rc = bg::conv_splitk_supported(N, H, W, Cin, Cout, ksize)
+               ? bg::launch_conv_splitk(x, wpack, out, N, H, W, Cin, Cout, bias, noise, noise_w, gate_src, act, slope, S(stream))
+               : bg::launch_conv_fprop(x, wpack, out, N, H, W, Cin, Cout, ksize, bias, noise, noise_w, gate_src, act, slope,
+                                       S(stream));
   if (rc != 0) return rc;
   if (stats_mode == 1) return bg::launch_in_stats(out, stats, N, H * W, Cout, S(stream));
   return bg::launch_channel_wsum(out, nullptr, stats, (size_t)N * H * W, Cout, H * W, 0, 0, 0, S(stream));

@@ -438,3 +438,37 @@ def test_conv_pool_wgrad_on_4x4_stride2_form(shape):
     torch.cuda.synchronize()
     err = relerr(dw, wparam.grad)
     assert err < 6e-3, f"conv+pool wgrad {shape}: rel-L2 {err:.3e}"
+
+
+@pytest.mark.parametrize("shape", [(32, 8, 8, 512, 512), (32, 4, 4, 512, 576), (32, 4, 4, 576, 512), (16, 4, 4, 512, 512),
+                                   (6, 8, 8, 512, 512), (3, 4, 4, 512, 512), (5, 8, 8, 128, 256), (4, 8, 8, 256, 128)])
+@pytest.mark.parametrize("variant", ["plain", "fused", "gated"])
+def test_small_map_conv_split_k_cluster(shape, variant):
+    """conv_splitk.cu: the K loop of a small-map layer split over the CTAs of a cluster, partials reduced through
+    distributed shared memory.  Against F.conv2d (the reference op, gan.py:29-38), against the tap-wise kernel, and
+    bit-reproducible from run to run (ordered reduction, no atomics: these are forward activations)."""
+    n, h, w_, ci, co = shape
+    torch.manual_seed(3)
+    x = nhwc(torch.randn(n, ci, h, w_, device=DEV))
+    w = torch.randn(co, ci, 3, 3, device=DEV)
+    coef = math.sqrt(2 / (ci * 9))
+    wf, _ = pack(w, coef)
+    fused, gated = variant == "fused", variant == "gated"
+    bias = torch.randn(co, device=DEV) * 0.1 if fused else None
+    noise = torch.randn(n, 1, h, w_, device=DEV) if fused else None
+    nw = torch.randn(co, device=DEV) * 0.1 if fused else None
+    gate = nhwc(torch.randn(n, co, h, w_, device=DEV)) if gated else None
+    outs = []
+    for entry in ("bg_conv_fprop", "bg_conv_fprop", "bg_conv_fprop_tapwise"):
+        out = torch.empty(n, h, w_, co, dtype=torch.bfloat16, device=DEV)
+        bgn.call(entry, x, wf, out, n, h, w_, ci, co, 3, bias, noise, nw, gate, 1 if fused else 0, 0.2)
+        outs.append(out)
+    torch.cuda.synchronize()
+    ref = F.conv2d(nchw(x), (w * coef).to(torch.bfloat16).float(), None, padding=1)
+    if fused:
+        ref = F.leaky_relu(ref + bias.view(1, -1, 1, 1) + nw.view(1, -1, 1, 1) * noise, 0.2)
+    if gated:
+        ref = ref * torch.where(nchw(gate) > 0, 1.0, 0.2)
+    assert relerr(nchw(outs[0]), ref) < 6e-3, relerr(nchw(outs[0]), ref)
+    assert torch.equal(outs[0], outs[1]), "split-K result differs between two runs"
+    assert relerr(outs[0].float(), outs[2].float()) < 4e-3        # other summation order than the tap-wise kernel
