@@ -204,6 +204,51 @@ __global__ void pack_weight_grouped_kernel(const PackGroups G) {
   }
 }
 
+// Tiled form for 3x3 layers (every group ks == 3): a block owns a (64 co x 64 ci) tile of one layer; it reads the 9-tap runs
+// w[co][ci0..ci0+63][0..8] (576 contiguous floats per co) coalesced, keeps the bf16 tile in shared memory and writes 128-byte
+// runs on both sides: wf[tap][co][ci0..] and wd[8 - tap][ci][co0..].  The element-wise kernel above wrote wd with one
+// 2-byte store per 128-byte line (154 us for a network's packs that move in ~40 us); since the pack cache was fixed to
+// notice fused optimizer steps this runs twice per iteration.
+constexpr int kPackTile = 64;
+__global__ void __launch_bounds__(256)
+pack_weight_grouped_tiled_kernel(const PackGroups G) {
+  pdl_prologue();
+  extern __shared__ __nv_bfloat16 ptile[];                  // [9][64 co][66 ci], tap planes padded against bank conflicts
+  constexpr int kStride = kPackTile + 2;
+  constexpr int kTapStride = kPackTile * kStride + 2;       // odd number of 4-byte words
+  int g = 0;
+  while (g + 1 < G.groups && (int)blockIdx.x >= G.blk0[g + 1]) ++g;
+  const int Cout = G.Cout[g], Cin = G.Cin[g], Cin_pad = G.Cin_pad[g];
+  const float coef = G.coef[g];
+  const float* __restrict__ w = G.w[g];
+  __nv_bfloat16* __restrict__ wf = G.wf[g];
+  __nv_bfloat16* __restrict__ wd = G.wd[g];
+  const int tiles_ci = (Cin_pad + kPackTile - 1) / kPackTile;
+  const int tile = (int)blockIdx.x - G.blk0[g];
+  const int co0 = (tile / tiles_ci) * kPackTile, ci0 = (tile % tiles_ci) * kPackTile;
+  const int nco = min(kPackTile, Cout - co0), nci = min(kPackTile, Cin_pad - ci0);
+  // read: for each co a run of nci * 9 floats (zero beyond Cin)
+  for (int col = 0; col < nco; ++col) {
+    const float* src = w + ((size_t)(co0 + col) * Cin + ci0) * 9;
+    for (int j = threadIdx.x; j < nci * 9; j += blockDim.x) {
+      const int cil = j / 9, tap = j - cil * 9;
+      const float v = (ci0 + cil < Cin) ? src[j] * coef : 0.f;
+      ptile[tap * kTapStride + col * kStride + cil] = __float2bfloat16_rn(v);
+    }
+  }
+  __syncthreads();
+  // wf[tap][co][ci]: runs of nci along ci
+  for (int idx = threadIdx.x; idx < 9 * nco * nci; idx += blockDim.x) {
+    const int cil = idx % nci, col = (idx / nci) % nco, tap = idx / (nci * nco);
+    wf[((size_t)tap * Cout + co0 + col) * Cin_pad + ci0 + cil] = ptile[tap * kTapStride + col * kStride + cil];
+  }
+  // wd[8 - tap][ci][co]: runs of nco along co
+  for (int idx = threadIdx.x; idx < 9 * nco * nci; idx += blockDim.x) {
+    const int col = idx % nco, cil = (idx / nco) % nci, tap = idx / (nci * nco);
+    wd[((size_t)(8 - tap) * Cin_pad + ci0 + cil) * Cout + co0 + col] = ptile[tap * kTapStride + col * kStride + cil];
+  }
+}
+
 // dwp: fp32 [tap][Cout][Cin_pad] -> dw: fp32 (Cout, Cin, ks, ks), scaled by coef; optionally accumulates.
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Cout, int Cin,
                                     int Cin_pad, int ks, float coef, int accumulate) {
@@ -1345,6 +1390,24 @@ int launch_pack_weight_grouped(const float* const* w, void* const* wf, void* con
     blocks += (int)b;
   }
   G.blk0[groups] = blocks;
+  bool all3 = true;
+  for (int g = 0; g < groups; ++g) all3 = all3 && ks[g] == 3;
+  if (all3) {
+    int tiles = 0;
+    for (int g = 0; g < groups; ++g) {
+      G.blk0[g] = tiles;
+      tiles += ((Cout[g] + kPackTile - 1) / kPackTile) * ((Cin_pad[g] + kPackTile - 1) / kPackTile);
+    }
+    G.blk0[groups] = tiles;
+    const size_t smem = (size_t)9 * (kPackTile * (kPackTile + 2) + 2) * sizeof(__nv_bfloat16);
+    static bool attr_set = false;
+    if (!attr_set) {
+      BG_CHECK_CUDA(cudaFuncSetAttribute(pack_weight_grouped_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = true;
+    }
+    BG_CHECK_CUDA(launch_pdl(pack_weight_grouped_tiled_kernel, tiles, 256, smem, s, G));
+    return 0;
+  }
   BG_CHECK_CUDA(launch_pdl(pack_weight_grouped_kernel, blocks, kBlock, 0, s, G));
   return 0;
 }

@@ -472,3 +472,24 @@ def test_small_map_conv_split_k_cluster(shape, variant):
     assert relerr(nchw(outs[0]), ref) < 6e-3, relerr(nchw(outs[0]), ref)
     assert torch.equal(outs[0], outs[1]), "split-K result differs between two runs"
     assert relerr(outs[0].float(), outs[2].float()) < 4e-3        # other summation order than the tap-wise kernel
+
+
+def test_pack_weight_grouped_equals_single_packs():
+    """bg_pack_weight_grouped (all stale packs of a network in one launch, tiled kernel) == bg_pack_weight layer by layer,
+    including the padded 513 -> 576 input channels of the critic's minibatch-stddev layer and ragged tile edges."""
+    torch.manual_seed(2)
+    layers = [(512, 513, 576), (32, 16, 16), (16, 32, 32), (256, 512, 512), (48, 64, 64), (64, 96, 96), (128, 128, 128)]
+    ws, wfs, wds, meta = [], [], [], []
+    for co, ci, cp in layers:
+        w = torch.randn(co, ci, 3, 3, device=DEV)
+        ws.append(w)
+        wfs.append(torch.full((9, co, cp), 7.0, dtype=torch.bfloat16, device=DEV))
+        wds.append(torch.full((9, cp, co), 7.0, dtype=torch.bfloat16, device=DEV))
+        meta.append((co, ci, cp, 3, math.sqrt(2 / (ci * 9))))
+    bgn.call("bg_pack_weight_grouped", ws, wfs, wds, [m[0] for m in meta], [m[1] for m in meta], [m[2] for m in meta],
+             [m[3] for m in meta], [m[4] for m in meta], len(layers))
+    for w, wf, wd, (co, ci, cp, _, coef) in zip(ws, wfs, wds, meta):
+        rf = torch.empty(9, co, cp, dtype=torch.bfloat16, device=DEV)
+        rd = torch.empty(9, cp, co, dtype=torch.bfloat16, device=DEV)
+        bgn.call("bg_pack_weight", w, rf, rd, co, ci, cp, 3, coef)
+        assert torch.equal(wf, rf) and torch.equal(wd, rd), (co, ci, cp)
