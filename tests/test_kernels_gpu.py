@@ -493,3 +493,25 @@ def test_pack_weight_grouped_equals_single_packs():
         rd = torch.empty(9, cp, co, dtype=torch.bfloat16, device=DEV)
         bgn.call("bg_pack_weight", w, rf, rd, co, ci, cp, 3, coef)
         assert torch.equal(wf, rf) and torch.equal(wd, rd), (co, ci, cp)
+
+
+@pytest.mark.parametrize("shape", [(32, 8, 8, 512, 512), (32, 4, 4, 512, 512), (16, 8, 8, 256, 128), (6, 4, 4, 128, 384)])
+def test_small_map_wgrad_single_tap_output_stationary(shape):
+    """conv_wgrad.cu single-tap mode (one CTA per (tap, 128 co, 128 ci), whole pixel range, no split-K): overwrite and
+    accumulate forms against autograd's conv2d_weight and the split-K decomposition; bit-reproducible (no atomics)."""
+    n, h, w_, ci, co = shape
+    torch.manual_seed(4)
+    x = nhwc(torch.randn(n, ci, h, w_, device=DEV))
+    g = nhwc(torch.randn(n, co, h, w_, device=DEV))
+    ref = torch.nn.grad.conv2d_weight(nchw(x), (co, ci, 3, 3), nchw(g), padding=1)
+    outs = []
+    for _ in range(2):
+        dwp = torch.full((9, co, ci), 3.0, dtype=torch.float32, device=DEV)          # must be overwritten, not added to
+        bgn.call("bg_conv_wgrad", x, g, dwp, n, h, w_, ci, co, 0)
+        outs.append(dwp.clone())
+        bgn.call("bg_conv_wgrad", x, g, dwp, n, h, w_, ci, co, 1)
+        assert relerr(dwp, 2 * outs[-1]) < 1e-6
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
+    got = outs[0].reshape(3, 3, co, ci).permute(2, 3, 0, 1)
+    assert relerr(got, ref) < 2e-3, relerr(got, ref)
