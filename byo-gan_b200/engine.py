@@ -231,21 +231,22 @@ def conv3x3_pool(x, wpack, cin, cout, bias=None, gate_src=None, act=True, w16=No
     return out
 
 
-def conv_wgrad(x, g, w_param, cin_pad=None, extra=None):
+def conv_wgrad(x, g, w_param, cin_pad=None, extra=None, into=None):
     """dW for a 3x3 conv parameter `w_param` from input x and output-gradient g (both NHWC bf16).
-    `extra=(v, ghat)` adds the R1 second-order pair into the same accumulator (doubled-K contraction)."""
+    `extra=(v, ghat)` adds the R1 second-order pair into the same accumulator (doubled-K contraction).
+    `into`: an existing gradient of w_param's shape that the result is ADDED to by the unpack pass (returned)."""
     n, h, w_, cin_eff = x.shape
     cout = g.shape[3]
     dwp = _f32(9, cout, cin_eff, device=x.device)
     call("bg_conv_wgrad", x, g, dwp, n, h, w_, cin_eff, cout, 0)
     if extra is not None:
         call("bg_conv_wgrad", extra[0], extra[1], dwp, n, h, w_, cin_eff, cout, 1)
-    dw = _f32(*w_param.shape, device=x.device)
-    call("bg_unpack_wgrad", dwp, dw, cout, w_param.shape[1], cin_eff, 3, coef_of(w_param), 0)
+    dw = into if into is not None else _f32(*w_param.shape, device=x.device)
+    call("bg_unpack_wgrad", dwp, dw, cout, w_param.shape[1], cin_eff, 3, coef_of(w_param), 0 if into is None else 1)
     return dw
 
 
-def conv_pool_wgrad(x, gpool, w_param, extra=None):
+def conv_pool_wgrad(x, gpool, w_param, extra=None, into=None):
     """dW of a 3x3 conv that is followed by AvgPool2d(2), from the gradient gpool at the POOLED map (NHWC bf16) and the
     conv input x: taken on the equivalent 4x4 stride-2 kernel (16 taps, a quarter of the pixels), folded back to 3x3.
     `extra=(v, ghat_pooled)` adds the R1 second-order pair into the same accumulator."""
@@ -255,8 +256,8 @@ def conv_pool_wgrad(x, gpool, w_param, extra=None):
     call("bg_conv_pool4_wgrad", x, gpool, dw16, n, hp, wp, cin, cout, 0)
     if extra is not None:
         call("bg_conv_pool4_wgrad", extra[0], extra[1], dw16, n, hp, wp, cin, cout, 1)
-    dw = _f32(*w_param.shape, device=x.device)
-    call("bg_unpack_wgrad_pool4", dw16, dw, cout, cin, coef_of(w_param), 0)
+    dw = into if into is not None else _f32(*w_param.shape, device=x.device)
+    call("bg_unpack_wgrad_pool4", dw16, dw, cout, cin, coef_of(w_param), 0 if into is None else 1)
     return dw
 
 
@@ -743,7 +744,7 @@ class _EmitDict(dict):
 
 
 def critic_backward(critic, packs: PackCache, tape, g_pred, need: Dict[int, bool], need_img: bool,
-                    keep: Optional[dict] = None, r1: Optional[tuple] = None, emit=None):
+                    keep: Optional[dict] = None, r1: Optional[tuple] = None, emit=None, acc: Optional[dict] = None):
     """Reverse pass of critic_forward seeded with g_pred (B,1).
 
     need[id(p)] -> produce that parameter gradient.  keep: dict that receives the gated gradient at every
@@ -756,6 +757,8 @@ def critic_backward(critic, packs: PackCache, tape, g_pred, need: Dict[int, bool
     B, G = tape["B"], tape["G"]
     grads: Dict[int, torch.Tensor] = {} if emit is None else _EmitDict(emit)
     T, H = r1 if r1 is not None else (None, None)
+    acc = acc or {}            # {id(conv weight): gradient of another branch}: this pass's result is added INTO it by the
+                               # weight-gradient unpack kernel (no separate add pass over the 9.4 MB tensors)
 
     def want(p):
         return need.get(id(p), False)
@@ -786,7 +789,7 @@ def critic_backward(critic, packs: PackCache, tape, g_pred, need: Dict[int, bool
     # ---- conv_1 of the final block on the 513(->576)-channel input
     if want(c1.weight):
         grads[id(c1.weight)] = conv_wgrad(tape["xpad"], gy, c1.weight,
-                                          extra=(T["xpad"], H["y"]) if T else None)
+                                          extra=(T["xpad"], H["y"]) if T else None, into=acc.get(id(c1.weight)))
     if want(c1.bias):
         grads[id(c1.bias)] = channel_wsum(gy, None, 0, 16, 0, 0)[0].clone()
     _, wd = packs.conv(c1.weight, cin_pad=MBSTD_CPAD)
@@ -850,7 +853,7 @@ def critic_backward(critic, packs: PackCache, tape, g_pred, need: Dict[int, bool
                 kk["gp"] = gpool
             if want(c2b.weight):
                 grads[id(c2b.weight)] = conv_pool_wgrad(e["y1"], gpool, c2b.weight,
-                                                        extra=(t["y1"], h["gp"]) if t else None)
+                                                        extra=(t["y1"], h["gp"]) if t else None, into=acc.get(id(c2b.weight)))
             if want(c2b.bias):
                 grads[id(c2b.bias)] = channel_wsum(gpool, None, 0, (r // 2) * (r // 2), 0, 0)[0]
             g1 = _bf16(B, r, r, cout, device=dev)
@@ -864,7 +867,8 @@ def critic_backward(critic, packs: PackCache, tape, g_pred, need: Dict[int, bool
             if kk is not None:
                 kk["u"] = gu
             if want(c2b.weight):
-                grads[id(c2b.weight)] = conv_wgrad(e["y1"], gu, c2b.weight, extra=(t["y1"], h["u"]) if t else None)
+                grads[id(c2b.weight)] = conv_wgrad(e["y1"], gu, c2b.weight, extra=(t["y1"], h["u"]) if t else None,
+                                                   into=acc.get(id(c2b.weight)))
             if db2 is not None:
                 grads[id(c2b.bias)] = db2
             _, wd2 = packs.conv(c2b.weight)
@@ -878,7 +882,8 @@ def critic_backward(critic, packs: PackCache, tape, g_pred, need: Dict[int, bool
         if kk is not None:
             kk["y1"] = g1
         if want(c1b.weight):
-            grads[id(c1b.weight)] = conv_wgrad(e["x"], g1, c1b.weight, extra=(t["x"], h["y1"]) if t else None)
+            grads[id(c1b.weight)] = conv_wgrad(e["x"], g1, c1b.weight, extra=(t["x"], h["y1"]) if t else None,
+                                               into=acc.get(id(c1b.weight)))
         _, wd1 = packs.conv(c1b.weight)
         first = idx == 0
         if first:
@@ -956,7 +961,8 @@ def _penalised_critic_step(critic, packs: PackCache, first_order, pen_tape, pen_
             part = gf.get(k)
             if part is None:
                 raise RuntimeError("internal: missing critic gradient")
-            call("bg_axpby_f32", part, gr, part, part.numel(), 1.0, 1.0)
+            if part.data_ptr() != gr.data_ptr():         # conv weights were accumulated in place by the unpack kernel
+                call("bg_axpby_f32", part, gr, part, part.numel(), 1.0, 1.0)
             gr = part
         grads[k] = gr
         if emit is not None:
@@ -964,7 +970,10 @@ def _penalised_critic_step(critic, packs: PackCache, first_order, pen_tape, pen_
 
     # the last pass runs head -> high resolution: the big low-resolution weights finish first, so their all-reduce
     # (emit) overlaps the expensive high-resolution layers still to come
-    critic_backward(critic, packs, pen_tape, pen_seed, need, need_img=False, r1=(T, ghat), emit=finish)
+    conv_acc = None
+    if len(firsts) == 1:
+        conv_acc = {k: v for k, v in firsts[0].items() if v.dim() == 4 and v.shape[-1] == 3}
+    critic_backward(critic, packs, pen_tape, pen_seed, need, need_img=False, r1=(T, ghat), emit=finish, acc=conv_acc)
     for p in params:
         if need[id(p)] and id(p) not in grads:
             raise RuntimeError("internal: missing critic gradient")
