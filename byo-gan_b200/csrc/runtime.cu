@@ -26,6 +26,11 @@ int check_cuda(cudaError_t e, const char* what) {
   return 1;
 }
 
+// SMs the persistent / one-wave grids are sized for = SMs of the device minus a reserve (bg_set_sm_reserve, BG_SM_RESERVE):
+// in a data-parallel run NCCL's all-reduce CTAs occupy a few SMs while the backward is still running; a 148-CTA
+// persistent grid (one CTA per SM, 200+ KB of shared memory each) then cannot be fully resident and its last CTAs run as
+// a second wave.  Sizing the grids for 148 - reserve keeps them one wave next to the collective.
+static int g_sm_reserve = -1;
 int num_sms() {
   static int cached[64] = {0};
   int dev = 0;
@@ -35,8 +40,16 @@ int num_sms() {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
     cached[dev] = n;
   }
-  return cached[dev];
+  if (g_sm_reserve < 0) {
+    const char* e = getenv("BG_SM_RESERVE");
+    g_sm_reserve = e ? atoi(e) : 0;
+    if (g_sm_reserve < 0) g_sm_reserve = 0;
+  }
+  int n = cached[dev] - g_sm_reserve;
+  n &= ~1;                                       // CTA pairs need an even count
+  return n < 16 ? 16 : n;
 }
+void set_sm_reserve(int n) { g_sm_reserve = n < 0 ? 0 : n; }
 
 bool pdl_enabled() {
   static int on = -1;
@@ -162,3 +175,7 @@ extern "C" int bg_set_deterministic(int on) {
   return 0;
 }
 extern "C" int bg_get_deterministic(void) { return bg::deterministic() ? 1 : 0; }
+extern "C" int bg_set_sm_reserve(int sms) {
+  bg::set_sm_reserve(sms);
+  return 0;
+}

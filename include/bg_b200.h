@@ -42,6 +42,10 @@ int bg_abi_version(void);
  * their atomics: ~1e-6 relative order noise that ends in that tensor.  Used by the parity tests; costs a few percent. */
 int bg_set_deterministic(int on);
 int bg_get_deterministic(void);
+/* SMs left free by the persistent / one-wave grids of this library (default 0, or BG_SM_RESERVE in the environment): in a
+ * data-parallel run the gradient all-reduce (train.py:71,79's nn.DataParallel reduce, here NCCL) runs UNDER the backward
+ * and its CTAs occupy a few SMs; grids sized for all 148 SMs would then spill into a second wave. */
+int bg_set_sm_reserve(int sms);
 
 /* ---- equalized-lr weight staging (gan.py:14,27,32: weight * sqrt(2/fan_in) every forward) -------------
  * w: fp32 (Cout,Cin,ks,ks).  w_fprop: bf16 [ks*ks][Cout][Cin_pad] or NULL.
