@@ -700,22 +700,50 @@ __device__ __forceinline__ void epilogue_warp(const HaloParams& p, const int war
       const bool staged = !p.pool;
       // line-wise load of the gate tile of round c0 into the (warp-private) stage: lane -> (row = lane / cpr + i * 32 / cpr,
       // chunk = lane % cpr)
+      // Line-wise walks over the warp's 32 pixel rows (gate staging below, global stores further down): lane -> rows
+      // r0 + i * step.  The byte offset of row r in the global map is (r >> 3) * row_bytes + (r & 7) * col_bytes; with the
+      // stage width known at compile time the walk is a chain of ADDS of two precomputed strides (the 64-bit index
+      // arithmetic of these two loops was ~13 % of all instructions, profiles/r2_ncu_pool4_dgrad_lines.txt).
+      const size_t row_bytes = (size_t)os * out_w * p.Cout * 2, col_bytes = (size_t)os * p.Cout * 2;
+      const int line_r0 = lane >> cpr_shift;
+      const size_t line_off0 = ((pix_q0 * p.Cout + t.co0 + (lane & ((1 << cpr_shift) - 1)) * 8) * 2) +
+                               (size_t)(line_r0 >> 3) * row_bytes + (size_t)(line_r0 & 7) * col_bytes;
+      auto line_step = [&](int i) -> size_t {     // offset of row i + 1 minus offset of row i
+        if (CPRS == 3) return (i & 1) ? row_bytes - 4 * col_bytes : 4 * col_bytes;
+        if (CPRS == 2) return row_bytes;
+        return 2 * row_bytes;
+      };
       auto stage_gate = [&](int c0) {
         const int cpr = 1 << cpr_shift;
         const int ch = lane & (cpr - 1);
+        if (CPRS >= 0) {
+          const char* gptr = reinterpret_cast<const char*>(p.gate_src) + line_off0 + (size_t)c0 * 2;
+#pragma unroll
+          for (int i = 0; i < (1 << (CPRS >= 0 ? CPRS : 0)); ++i) {
+            const int row = line_r0 + i * (32 >> cpr_shift);
+            const uint4 gv = *reinterpret_cast<const uint4*>(gptr);
+            const uint32_t swz = (uint32_t)(row >> (3 - cpr_shift)) & (uint32_t)(cpr - 1);
+            sts128(stg + (uint32_t)row * rb + (((uint32_t)ch ^ swz) << 4), gv);
+            gptr += line_step(i);
+          }
+        } else {
 #pragma unroll 4
-        for (int row = lane >> cpr_shift; row < 32; row += 32 >> cpr_shift) {
-          const size_t gp = pix_q0 + (size_t)(row >> 3) * os * out_w + (size_t)(row & 7) * os;
-          const uint4 gv = *reinterpret_cast<const uint4*>(p.gate_src + gp * p.Cout + t.co0 + c0 + ch * 8);
-          const uint32_t swz = (uint32_t)(row >> (3 - cpr_shift)) & (uint32_t)(cpr - 1);
-          sts128(stg + (uint32_t)row * rb + (((uint32_t)ch ^ swz) << 4), gv);
+          for (int row = lane >> cpr_shift; row < 32; row += 32 >> cpr_shift) {
+            const size_t gp = pix_q0 + (size_t)(row >> 3) * os * out_w + (size_t)(row & 7) * os;
+            const uint4 gv = *reinterpret_cast<const uint4*>(p.gate_src + gp * p.Cout + t.co0 + c0 + ch * 8);
+            const uint32_t swz = (uint32_t)(row >> (3 - cpr_shift)) & (uint32_t)(cpr - 1);
+            sts128(stg + (uint32_t)row * rb + (((uint32_t)ch ^ swz) << 4), gv);
+          }
         }
         __syncwarp();
       };
       // the first round's gate tile is fetched BEFORE waiting for the accumulator: its DRAM latency (14 % of the
       // epilogue warps' time in profiles/r2_ncu_pool4_dgrad_stalls.txt) then overlaps the tile's MMAs
       if (staged && p.gate_src != nullptr && !(p.debug & 8)) stage_gate(0);
-      mbar_wait(&tmem_full[acc], acc_phase);
+      // one warp of the set polls the accumulator barrier, the other seven block in a named barrier: eight warps
+      // retrying try_wait cost 15 % of all issued instructions (profiles/r2_ncu_pool4_dgrad_lines.txt)
+      if (((warp - 2) & 7) == 0) mbar_wait(&tmem_full[acc], acc_phase);
+      asm volatile("bar.sync %0, %1;" ::"r"(3 + eset), "n"(32 * kEpiWarps) : "memory");
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u + (uint32_t)half * 128u;
       const int ncols = (p.debug & 8) ? 0 : p.block_n;
@@ -821,12 +849,19 @@ __device__ __forceinline__ void epilogue_warp(const HaloParams& p, const int war
           if (!(p.debug & 1)) {
             const int cpr = 1 << cpr_shift;
             const int ch = lane & (cpr - 1);
+            char* optr = reinterpret_cast<char*>(p.out) + line_off0 + (size_t)c0 * 2;
 #pragma unroll 4
-            for (int row = lane >> cpr_shift; row < 32; row += 32 >> cpr_shift) {
+            for (int i = 0; i < cpr; ++i) {
+              const int row = line_r0 + i * (32 >> cpr_shift);
               const uint32_t swz = (uint32_t)(row >> (3 - cpr_shift)) & (uint32_t)(cpr - 1);
               const uint4 ov = lds128(stg + (uint32_t)row * rb + (((uint32_t)ch ^ swz) << 4));
-              const size_t op = pix_q0 + (size_t)(row >> 3) * os * out_w + (size_t)(row & 7) * os;
-              *reinterpret_cast<uint4*>(p.out + op * p.Cout + t.co0 + c0 + ch * 8) = ov;
+              if (CPRS >= 0) {
+                *reinterpret_cast<uint4*>(optr) = ov;
+                optr += line_step(i);
+              } else {
+                const size_t op = pix_q0 + (size_t)(row >> 3) * os * out_w + (size_t)(row & 7) * os;
+                *reinterpret_cast<uint4*>(p.out + op * p.Cout + t.co0 + c0 + ch * 8) = ov;
+              }
               if (st_on) {
                 const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w};
 #pragma unroll
