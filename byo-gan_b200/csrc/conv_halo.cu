@@ -524,8 +524,8 @@ __device__ __forceinline__ void halo_producer_upsample(const HaloParams& p, uint
     for (int kcx = 0; kcx < p.k_chunks; ++kcx, ++item) {
       issue_patch();                                        // item + 2
       cp_async_wait<2>();                                   // this thread's copies of `item` have landed
-      asm volatile("bar.sync 2, %0;" ::"n"(kProdThreads) : "memory");   // ... and everybody else's
-      mbar_wait(&a_empty[stage], phase ^ 1u);
+      if (pt < 32) mbar_wait(&a_empty[stage], phase ^ 1u);  // ONE warp polls for the free stage (8 polling warps only burn issue slots)
+      asm volatile("bar.sync 2, %0;" ::"n"(kProdThreads) : "memory");   // ... everybody's copies have landed, the stage is free
       const uint32_t patch = smem_u32(patch_base + (size_t)(item & (kPatchStages - 1)) * p.patch_bytes);
       const uint32_t sdst = smem_u32(a_base + (size_t)stage * p.a_stage_bytes);
 #pragma unroll
