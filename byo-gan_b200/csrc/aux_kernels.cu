@@ -227,14 +227,15 @@ pack_weight_grouped_tiled_kernel(const PackGroups G) {
   const int tile = (int)blockIdx.x - G.blk0[g];
   const int co0 = (tile / tiles_ci) * kPackTile, ci0 = (tile % tiles_ci) * kPackTile;
   const int nco = min(kPackTile, Cout - co0), nci = min(kPackTile, Cin_pad - ci0);
-  // read: for each co a run of nci * 9 floats (zero beyond Cin)
-  for (int col = 0; col < nco; ++col) {
-    const float* src = w + ((size_t)(co0 + col) * Cin + ci0) * 9;
-    for (int j = threadIdx.x; j < nci * 9; j += blockDim.x) {
-      const int cil = j / 9, tap = j - cil * 9;
-      const float v = (ci0 + cil < Cin) ? src[j] * coef : 0.f;
-      ptile[tap * kTapStride + col * kStride + cil] = __float2bfloat16_rn(v);
-    }
+  // read: for each co a run of nci * 9 floats (zero beyond Cin); ONE flat loop over (co, run position) so that every
+  // thread has many independent loads in flight (a per-co loop serialised 64 memory round trips per block)
+  const int per_col = nci * 9;
+#pragma unroll 4
+  for (int idx = threadIdx.x; idx < nco * per_col; idx += blockDim.x) {
+    const int col = idx / per_col, j = idx - col * per_col;
+    const int cil = j / 9, tap = j - cil * 9;
+    const float v = (ci0 + cil < Cin) ? w[((size_t)(co0 + col) * Cin + ci0) * 9 + j] * coef : 0.f;
+    ptile[tap * kTapStride + col * kStride + cil] = __float2bfloat16_rn(v);
   }
   __syncthreads();
   // wf[tap][co][ci]: runs of nci along ci
