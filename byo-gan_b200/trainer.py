@@ -113,9 +113,18 @@ class Trainer:
         for p in model.parameters():
             p.requires_grad = flag
 
+    _marks = None        # BG_TRAINER_TIMING=1: CUDA events at the phase boundaries of every iteration (tools/phase_times.py)
+
+    def _mark(self, name):
+        if self._marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._marks.append((name, ev))
+
     def _step(self, real, z_d, z_g, alpha_g):
         """One iteration of train.py:135-219 on device tensors; returns the two loss tensors (no host interaction)."""
         gen, critic, steps, alpha = self.gen, self.critic, self.steps, self.alpha
+        self._mark("start")
         # ---- critic step (train.py:135-191)
         self._set_requires_grad(critic, True)
         self._set_requires_grad(gen, False)
@@ -125,13 +134,17 @@ class Trainer:
         pf = critic(fake.detach(), steps, alpha)
         pr = critic(real_im, steps, alpha)
         critic.zero_grad()
+        self._mark("d_forward_done")
         self.sync.begin()
         if self.use_r1:
             c_loss = critic.get_r1_loss(pf, pr, real_im, fake, steps, alpha, self.c_lambda)
         else:
             c_loss = critic.get_wgan_loss(pf, pr, real_im, steps, alpha, self.c_lambda)
+        self._mark("d_backward_queued")
         self.sync.finish()
+        self._mark("d_allreduce_joined")
         self.critic_opt.step()
+        self._mark("d_adam_done")
         # ---- generator step (train.py:193-219)
         self._set_requires_grad(critic, False)
         self._set_requires_grad(gen, True)
@@ -140,11 +153,15 @@ class Trainer:
         pred = critic(fake2, steps, alpha_g)
         g_loss = gen.get_r1_loss(pred) if self.use_r1 else gen.get_wgan_loss(pred)
         gen.zero_grad()
+        self._mark("g_forward_done")
         self.sync.begin()
         g_loss.backward()
         self.sync.ready_all(p for p in gen.parameters() if p.grad is not None)
+        self._mark("g_backward_queued")
         self.sync.finish()
+        self._mark("g_allreduce_joined")
         self.gen_opt.step()
+        self._mark("g_adam_done")
         return c_loss.detach(), g_loss.detach()
 
     def iteration(self, real, z_d, z_g, read_losses=True, alpha_g="same"):
