@@ -78,7 +78,8 @@ SIGNATURES = {
 }
 
 # host-side switches / predicates called directly (no stream argument, no launch)
-HOST_FUNCS = {"bg_set_deterministic": [_I], "bg_get_deterministic": [], "bg_set_sm_reserve": [_I]}
+HOST_FUNCS = {"bg_set_deterministic": [_I], "bg_get_deterministic": [], "bg_set_sm_reserve": [_I],
+              "bg_set_prezeroed_range": [_P, _Z]}
 
 launch_count = 0  # C-ABI calls made through this binding; each launches >= 1 kernel (bench.py: gpu_launches)
 _timing = None    # when a list: (name, args, start_event, end_event) per call, for bench.py's roofline leg

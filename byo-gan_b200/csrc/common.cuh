@@ -21,6 +21,7 @@ void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 int num_sms();           // SMs the grids are sized for (device SMs minus the bg_set_sm_reserve reserve)
 void set_sm_reserve(int n);
+void set_prezeroed_range(const void* base, size_t bytes);
 bool deterministic();   // runtime.cu: chain-deterministic reductions (bg_set_deterministic)
 
 #define BG_CHECK_CUDA(expr)                                   \

@@ -40,6 +40,56 @@ def _f32(*shape, device):
     return torch.empty(shape, dtype=torch.float32, device=device)
 
 
+class ZeroSlab:
+    """One zero-filled fp32 slab per pass that every accumulation target of the pass (fused statistics, split-K weight-
+    gradient scratch, channel sums) is carved from: ONE memset instead of one zero-fill launch per accumulator (~120 per
+    iteration).  While active the slab is registered with the library (bg_set_prezeroed_range), which then skips its
+    own zero fill for targets inside it.  Buffers that do not fit fall back to ordinary allocations (zeroed by the call)."""
+
+    current: "Optional[ZeroSlab]" = None
+
+    def __init__(self, device, nfloats: int):
+        self.device = device
+        self.buf = torch.zeros(max(int(nfloats), 4), dtype=torch.float32, device=device)
+        self.off = 0
+        self.prev = None
+
+    def __enter__(self):
+        self.prev = ZeroSlab.current
+        ZeroSlab.current = self
+        bgn.lib().bg_set_prezeroed_range(self.buf.data_ptr(), self.buf.numel() * 4)
+        return self
+
+    def __exit__(self, *exc):
+        ZeroSlab.current = self.prev
+        if self.prev is not None:
+            bgn.lib().bg_set_prezeroed_range(self.prev.buf.data_ptr(), self.prev.buf.numel() * 4)
+        else:
+            bgn.lib().bg_set_prezeroed_range(None, 0)
+
+    def take(self, shape):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        n_pad = (n + 3) & ~3                       # keep every buffer 16-byte aligned (vector reductions)
+        if self.off + n_pad > self.buf.numel():
+            return None
+        v = self.buf[self.off:self.off + n].view(*shape)
+        self.off += n_pad
+        return v
+
+
+def _acc(*shape, device):
+    """fp32 accumulation target: a carved piece of the active ZeroSlab (already zero), else a plain allocation that the
+    library zeroes itself."""
+    slab = ZeroSlab.current
+    if slab is not None and slab.device == device:
+        v = slab.take(shape)
+        if v is not None:
+            return v
+    return torch.empty(shape, dtype=torch.float32, device=device)
+
+
 def coef_of(weight: torch.Tensor) -> float:
     """Equalized-lr runtime scale sqrt(2 / fan_in) (gan.py:13-14, 26-27)."""
     fan_in = weight.shape[1] * (weight[0][0].numel() if weight.dim() > 2 else 1)
@@ -207,7 +257,7 @@ def conv3x3(x, wpack, cin, cout, bias=None, noise=None, noise_w=None, gate_src=N
     n, h, w_, _ = x.shape
     out = _bf16(n, h, w_, cout, device=x.device)
     if stats:
-        st = _f32(n, cout, 2, device=x.device) if stats == 1 else _f32(cout, device=x.device)
+        st = _acc(n, cout, 2, device=x.device) if stats == 1 else _acc(cout, device=x.device)
         call("bg_conv_fprop_stats", x, wpack, out, n, h, w_, cin, cout, 3, bias, noise, noise_w, gate_src,
              1 if act else 0, SLOPE, st, stats)
         return out, st
@@ -237,7 +287,7 @@ def conv_wgrad(x, g, w_param, cin_pad=None, extra=None, into=None):
     `into`: an existing gradient of w_param's shape that the result is ADDED to by the unpack pass (returned)."""
     n, h, w_, cin_eff = x.shape
     cout = g.shape[3]
-    dwp = _f32(9, cout, cin_eff, device=x.device)
+    dwp = _acc(9, cout, cin_eff, device=x.device)
     call("bg_conv_wgrad", x, g, dwp, n, h, w_, cin_eff, cout, 0)
     if extra is not None:
         call("bg_conv_wgrad", extra[0], extra[1], dwp, n, h, w_, cin_eff, cout, 1)
@@ -252,7 +302,7 @@ def conv_pool_wgrad(x, gpool, w_param, extra=None, into=None):
     `extra=(v, ghat_pooled)` adds the R1 second-order pair into the same accumulator."""
     n, hp, wp, cout = gpool.shape
     cin = x.shape[3]
-    dw16 = _f32(16, cout, cin, device=x.device)
+    dw16 = _acc(16, cout, cin, device=x.device)
     call("bg_conv_pool4_wgrad", x, gpool, dw16, n, hp, wp, cin, cout, 0)
     if extra is not None:
         call("bg_conv_pool4_wgrad", extra[0], extra[1], dw16, n, hp, wp, cin, cout, 1)
@@ -264,7 +314,7 @@ def conv_pool_wgrad(x, gpool, w_param, extra=None, into=None):
 def channel_wsum(g, planes, nplanes, hw, img_stride, plane_stride):
     c = g.shape[-1]
     p = g.numel() // c
-    out = _f32(1 + nplanes, c, device=g.device)
+    out = _acc(1 + nplanes, c, device=g.device)
     call("bg_channel_wsum", g, planes, out, p, c, hw, img_stride, plane_stride, nplanes)
     return out
 
@@ -335,8 +385,24 @@ def layer_input(layers, idx, L):
     return xin
 
 
+def _wgrad_scratch_floats(params, need) -> int:
+    """Upper bound of the split-K weight-gradient scratch of a backward pass: 16/9 of every wanted 3x3 conv weight (the
+    pooled 4x4-stride-2 form has 16 taps; the padded 513 -> 576 layer stays below that factor)."""
+    n = 0
+    for p in params:
+        if p.dim() == 4 and p.shape[-1] == 3 and need.get(id(p), False):
+            n += p.numel() * 16 // 9 + 64
+    return n
+
+
 def generator_forward(gen, packs: PackCache, z, noise, steps, alpha, z2=None, crossover=None, keep_tape=True):
     """Generator.forward (gan.py:183-222).  Returns (image (B,3,R,R) fp32, tape)."""
+    B = z.shape[0]
+    with ZeroSlab(z.device, sum(2 * (2 * B * GEN_CHANNELS[k][1] + 16) for k in range(steps))):
+        return _generator_forward(gen, packs, z, noise, steps, alpha, z2, crossover, keep_tape)
+
+
+def _generator_forward(gen, packs: PackCache, z, noise, steps, alpha, z2=None, crossover=None, keep_tape=True):
     dev = z.device
     B = z.shape[0]
     fade = alpha is not None and steps > 1
@@ -387,7 +453,7 @@ def generator_forward(gen, packs: PackCache, z, noise, steps, alpha, z2=None, cr
             if k == 0 and j == 0:
                 a = _bf16(B, 4, 4, cout, device=dev)                             # gan.py:92,96-97
                 call("bg_const_noise_act", sc.conv.detach(), nz, nw, a, B, 16, cout, SLOPE)
-                stats = _f32(B, cout, 2, device=dev)
+                stats = _acc(B, cout, 2, device=dev)
                 call("bg_in_stats", a, stats, B, R * R, cout)
                 L["const"] = True
             else:
@@ -401,7 +467,7 @@ def generator_forward(gen, packs: PackCache, z, noise, steps, alpha, z2=None, cr
                     call("bg_style_modulate", sc.conv.weight.detach(), sc.conv.bias.detach(), P["stats"], P["style"],
                          wmod, btab, B, ci, cout, P["R"] * P["R"], coef_of(sc.conv.weight), IN_EPS)
                     a = _bf16(B, R, R, cout, device=dev)
-                    stats = _f32(B, cout, 2, device=dev)
+                    stats = _acc(B, cout, 2, device=dev)
                     call("bg_conv_style_fprop", P["a"], wmod, btab, a, B, R, R, ci, cout, 1 if L["up"] else 0, nz, nw,
                          SLOPE, stats)
                     del wmod, btab
@@ -443,6 +509,15 @@ def generator_forward(gen, packs: PackCache, z, noise, steps, alpha, z2=None, cr
 
 def generator_backward(gen, packs: PackCache, tape, g_img, need: Dict[int, bool], need_z=True, need_z2=False,
                        emit=None):
+    """See _generator_backward; runs it inside one pre-zeroed slab for all of the pass's accumulators."""
+    steps, B = tape["steps"], tape["B"]
+    small = sum(2 * (2 * B * GEN_CHANNELS[k][1] + 6 * GEN_CHANNELS[k][1] + 64) for k in range(steps)) + 4096
+    with ZeroSlab(g_img.device, small + _wgrad_scratch_floats(generator_params(gen, steps, tape["fade"]), need)):
+        return _generator_backward(gen, packs, tape, g_img, need, need_z, need_z2, emit)
+
+
+def _generator_backward(gen, packs: PackCache, tape, g_img, need: Dict[int, bool], need_z=True, need_z2=False,
+                        emit=None):
     """Backward of generator_forward.  `need[id(param)]` says which parameter gradients to produce.
     emit(id(param), grad): called the moment a parameter's TOTAL gradient has been queued (synthesis layers one by
     one, the mapping network at the end because both latents of a style-mixing pass accumulate into it).
@@ -493,14 +568,14 @@ def generator_backward(gen, packs: PackCache, tape, g_img, need: Dict[int, bool]
         L = layers[idx]
         sc, k, j, r, c = L["sc"], L["k"], L["j"], L["R"], L["C"]
         a, stats, style = L["a"], L["stats"], L["style"]
-        bs = _f32(B, c, 2, device=dev)
+        bs = _acc(B, c, 2, device=dev)
         call("bg_adain_bwd_reduce", gx, a, stats, bs, B, r * r, c, IN_EPS)
         gpre = torch.empty_like(a)
         is_const = L["const"]
         need_b = (not is_const) and want(sc.conv.bias)
         need_nw = want(sc.inject_noise.weights)
         # bias / noise-weight gradients (gan.py:30,52) are reduced while gpre is written
-        ws = _f32(2, c, device=dev) if (need_b or need_nw) else None
+        ws = _acc(2, c, device=dev) if (need_b or need_nw) else None
         call("bg_adain_bwd_apply", gx, a, stats, style, bs, gpre, B, r * r, c, IN_EPS, SLOPE, 1,
              L["noise"] if ws is not None else None, ws)
         # style FC (gan.py:60,66): dL/dgamma = sum g*ahat, dL/dbeta = sum g; the FC gradients of all layers are taken in
@@ -745,6 +820,14 @@ class _EmitDict(dict):
 
 def critic_backward(critic, packs: PackCache, tape, g_pred, need: Dict[int, bool], need_img: bool,
                     keep: Optional[dict] = None, r1: Optional[tuple] = None, emit=None, acc: Optional[dict] = None):
+    """See _critic_backward; runs it inside one pre-zeroed slab for all of the pass's accumulators."""
+    params = critic_params(critic, tape["steps"], tape["fade"])
+    with ZeroSlab(g_pred.device, 16384 + _wgrad_scratch_floats(params, need)):
+        return _critic_backward(critic, packs, tape, g_pred, need, need_img, keep, r1, emit, acc)
+
+
+def _critic_backward(critic, packs: PackCache, tape, g_pred, need: Dict[int, bool], need_img: bool,
+                     keep: Optional[dict] = None, r1: Optional[tuple] = None, emit=None, acc: Optional[dict] = None):
     """Reverse pass of critic_forward seeded with g_pred (B,1).
 
     need[id(p)] -> produce that parameter gradient.  keep: dict that receives the gated gradient at every
@@ -839,7 +922,7 @@ def critic_backward(critic, packs: PackCache, tape, g_pred, need: Dict[int, bool
             gy2 = axpby(gx, None, a_mix, 0.0)
         else:
             gy2 = gx
-        db1 = _f32(cout, device=dev) if want(c1b.bias) else None                               # bias grad of conv_1
+        db1 = _acc(cout, device=dev) if want(c1b.bias) else None                               # bias grad of conv_1
         gu = None
         if r >= 32:
             # conv_2 -> pool is handled as ONE 4x4 stride-2 conv in all three directions: everything works from the
@@ -862,7 +945,7 @@ def critic_backward(critic, packs: PackCache, tape, g_pred, need: Dict[int, bool
             del gpool
         else:
             gu = _bf16(B, r, r, cout, device=dev)
-            db2 = _f32(cout, device=dev) if want(c2b.bias) else None                           # bias grad of conv_2
+            db2 = _acc(cout, device=dev) if want(c2b.bias) else None                           # bias grad of conv_2
             call("bg_pool_act_bwd", gy2, e["y2"], gu, B, r // 2, r // 2, cout, SLOPE, db2)     # pool + LReLU adjoint
             if kk is not None:
                 kk["u"] = gu

@@ -46,6 +46,12 @@ int bg_get_deterministic(void);
  * data-parallel run the gradient all-reduce (train.py:71,79's nn.DataParallel reduce, here NCCL) runs UNDER the backward
  * and its CTAs occupy a few SMs; grids sized for all 148 SMs would then spill into a second wave. */
 int bg_set_sm_reserve(int sms);
+/* Entry points that ACCUMULATE into a caller buffer with atomics (fused statistics, split-K weight gradients, channel sums)
+ * zero that buffer first, one small launch each.  A caller that carves such buffers out of ONE slab it has already zeroed
+ * (a single memset per backward pass) registers the slab here (device pointer, bytes; bytes = 0 clears; per host thread):
+ * the zero fill is then skipped for every target that lies inside the range.  The caller must hand each carved buffer to
+ * at most one zero-expecting call. */
+int bg_set_prezeroed_range(const void* base, size_t bytes);
 
 /* ---- equalized-lr weight staging (gan.py:14,27,32: weight * sqrt(2/fan_in) every forward) -------------
  * w: fp32 (Cout,Cin,ks,ks).  w_fprop: bf16 [ks*ks][Cout][Cin_pad] or NULL.
