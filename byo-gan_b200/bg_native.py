@@ -54,6 +54,7 @@ SIGNATURES = {
     "bg_adain_bwd_apply": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _I, _P, _P, _P],
     "bg_linear_fwd": [_P, _P, _P, _P, _I, _I, _I, _F, _I, _F, _P],
     "bg_linear_bwd_weight": [_P, _P, _P, _P, _I, _I, _I, _F, _I, _P],
+    "bg_linear_bwd_input": [_P, _P, _P, _I, _I, _I, _F, _P],
     "bg_linear_fwd_grouped": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
     "bg_linear_bwd_weight_grouped": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "bg_linear_bwd_input_grouped": [_P, _P, _P, _P, _I, _I, _I, _P, _P],

@@ -28,6 +28,7 @@ int launch_planes3_to_nhwc(const float*, const float*, const float*, const void*
                            float, int, float, cudaStream_t);
 int launch_linear_fwd(const float*, const float*, const float*, float*, int, int, int, float, int, float, cudaStream_t);
 int launch_linear_bwd_weight(const float*, const float*, float*, float*, int, int, int, float, int, cudaStream_t);
+int launch_linear_bwd_input(const float*, const float*, float*, int, int, int, float, cudaStream_t);
 int launch_transpose_f32(const float*, float*, int, int, cudaStream_t);
 int launch_act_gate_f32(const float*, const float*, float*, size_t, float, cudaStream_t);
 int launch_axpby_f32(const float*, const float*, float*, size_t, float, float, cudaStream_t);
@@ -280,6 +281,9 @@ int bg_linear_bwd_input_grouped(float* const* gy, const float* const* Wt, const 
 int bg_linear_fwd(const float* x, const float* W, const float* bias, float* y, int M, int N, int K, float coef, int act,
                   float slope, void* stream) {
   return bg::launch_linear_fwd(x, W, bias, y, M, N, K, coef, act, slope, S(stream));
+}
+int bg_linear_bwd_input(const float* gy, const float* W, float* gx, int M, int N, int K, float coef, void* stream) {
+  return bg::launch_linear_bwd_input(gy, W, gx, M, N, K, coef, S(stream));
 }
 int bg_linear_bwd_weight(const float* gy, const float* x, float* dW, float* db, int M, int N, int K, float coef,
                          int accumulate, void* stream) {

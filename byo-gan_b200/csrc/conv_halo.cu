@@ -1152,8 +1152,13 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
   {
     static int cta2_on = -1;                                  // BG_CTA2=0: every layer with one CTA per tile (A/B switch)
     if (cta2_on < 0) { const char* e = getenv("BG_CTA2"); cta2_on = (e && e[0] == '0') ? 0 : 1; }
-    // pair mode for the wide layers: N = 128 per instruction, at least two tile columns, TMA halo feed
-    p.cta2 = (cta2_on && bn_ch == 128 && !upsample && (Wc / kTile) >= 2) ? 1 : 0;
+    static int cta2_min_n = -2;                               // BG_CTA2_MIN_N=n: pair every tile >= n wide (experiments)
+    if (cta2_min_n == -2) { const char* e = getenv("BG_CTA2_MIN_N"); cta2_min_n = e ? atoi(e) : -1; }
+    // pair mode (TMA halo feed, at least two tile columns) where halving the weight operand pays: N = 128 per
+    // instruction, and N = 64 with >= 128 input channels (measured on B200, 32 x 128^2: 128->64 88 -> 75 us; the
+    // 32/64-channel-input layers at 256^2 lose 15-25 % in pairs, profiles/r2_pair_mode_narrow_layers.txt)
+    const bool wide = cta2_min_n >= 0 ? (bn_ch >= cta2_min_n && bn_ch >= 32) : (bn_ch == 128 || (bn_ch == 64 && Cin >= 128));
+    p.cta2 = (cta2_on && wide && !upsample && (Wc / kTile) >= 2) ? 1 : 0;
   }
   p.b_tx_bytes = (uint32_t)(p.block_n >> p.cta2) * row_bytes;     // pair mode: each CTA holds half of the weight tile
   p.b_tile_bytes = (p.b_tx_bytes + 1023u) & ~1023u;

@@ -782,6 +782,63 @@ int launch_linear_fwd(const float* x, const float* W, const float* bias, float* 
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Input gradient of EqualizedLinear (gan.py:16-17) straight from the (N, K) row-major weight: gx[m][k] = coef * sum_n
+// gy[m][n] * W[n][k].  The forward kernel needs W^T for this (a cached fp32 transpose per layer, re-made after every
+// optimizer step: 25 transpose launches per iteration); here W rows are read as they lie — coalesced along k — each lane
+// owns 4 consecutive k, the 8 warps of a block split n and meet in shared memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int kLbiMT = 8;        // rows of gy per pass
+__global__ void __launch_bounds__(256)
+linear_bwd_input_kernel(const float* __restrict__ gy, const float* __restrict__ W, float* __restrict__ gx, int M, int N,
+                        int K, float coef) {
+  pdl_prologue();
+  __shared__ float4 part[8][kLbiMT][32];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int k = ((int)blockIdx.x * 32 + lane) * 4;
+  const int m0 = (int)blockIdx.y * kLbiMT;
+  const bool live = k < K;                                   // K % 4 == 0 (launcher)
+  float4 acc[kLbiMT];
+#pragma unroll
+  for (int i = 0; i < kLbiMT; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int nspan = (N + 7) / 8;
+  const int n_lo = wp * nspan, n_hi = min(N, n_lo + nspan);
+  for (int n = n_lo; n < n_hi; ++n) {
+    const float4 w4 = live ? *reinterpret_cast<const float4*>(W + (size_t)n * K + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < kLbiMT; ++i) {
+      const float g = gy[(size_t)min(m0 + i, M - 1) * N + n];
+      acc[i].x = fmaf(g, w4.x, acc[i].x);
+      acc[i].y = fmaf(g, w4.y, acc[i].y);
+      acc[i].z = fmaf(g, w4.z, acc[i].z);
+      acc[i].w = fmaf(g, w4.w, acc[i].w);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kLbiMT; ++i) part[wp][i][lane] = acc[i];
+  __syncthreads();
+  // 8 warps x 8 rows: warp w finishes row w
+  if (live && m0 + wp < M) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const float4 pv = part[w][wp][lane];
+      v.x += pv.x; v.y += pv.y; v.z += pv.z; v.w += pv.w;
+    }
+    v.x *= coef; v.y *= coef; v.z *= coef; v.w *= coef;
+    *reinterpret_cast<float4*>(gx + (size_t)(m0 + wp) * K + k) = v;
+  }
+}
+
+int launch_linear_bwd_input(const float* gy, const float* W, float* gx, int M, int N, int K, float coef, cudaStream_t s) {
+  BG_REQUIRE(M > 0 && N > 0 && K > 0 && K % 4 == 0, "linear_bwd_input: bad shape M %d N %d K %d", M, N, K);
+  BG_REQUIRE((reinterpret_cast<uintptr_t>(W) & 15) == 0 && (reinterpret_cast<uintptr_t>(gx) & 15) == 0,
+             "linear_bwd_input: W and gx must be 16-byte aligned");
+  dim3 grid((K / 4 + 31) / 32, (M + kLbiMT - 1) / kLbiMT);
+  BG_CHECK_CUDA(launch_pdl(linear_bwd_input_kernel, grid, 256, 0, s, gy, W, gx, M, N, K, coef));
+  return 0;
+}
+
 int launch_linear_bwd_weight(const float* gy, const float* x, float* dW, float* db, int M, int N, int K, float coef,
                              int accumulate, cudaStream_t s) {
   BG_REQUIRE(M > 0 && N > 0 && K > 0 && K % 4 == 0, "linear_bwd_weight: bad shape M %d N %d K %d", M, N, K);

@@ -225,12 +225,15 @@ def linear_fwd(x, w, bias, act, coef=None):
 
 
 def linear_bwd_input(gy, w, packs: PackCache):
-    """gx = coef * gy @ W  via the forward kernel on the cached transpose."""
-    wt = packs.linear_t(w)                      # (K, N)
-    m, n = gy.shape
-    k = wt.shape[0]
+    """gx = coef * gy @ W, read straight from the (N, K) weight (no cached transpose)."""
+    w2 = w.detach().reshape(w.shape[0], -1)
+    n, k = w2.shape
+    m = gy.shape[0]
     gx = _f32(m, k, device=gy.device)
-    call("bg_linear_fwd", gy, wt, None, gx, m, k, n, coef_of(w), 0, SLOPE)
+    if k % 4 == 0:
+        call("bg_linear_bwd_input", gy, w2, gx, m, n, k, coef_of(w))
+    else:
+        call("bg_linear_fwd", gy, packs.linear_t(w), None, gx, m, k, n, coef_of(w), 0, SLOPE)
     return gx
 
 

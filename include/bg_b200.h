@@ -200,6 +200,9 @@ int bg_adain_bwd_apply(const void* g, const void* a, const float* stats, const f
  * weight (bg_transpose_f32).  bwd_weight: dW[N,K] (+)= coef * gy^T x;  db[N] (+)= sum_m gy (db may be NULL). */
 int bg_linear_fwd(const float* x, const float* W, const float* bias, float* y, int M, int N, int K, float coef, int act,
                   float slope, void* stream);
+/* Input gradient of y = coef * x W^T + b straight from the (N, K) row-major weight: gx (M, K) = coef * gy (M, N) @ W.
+ * (autograd's addmm backward of gan.py:16-17; needs no transposed copy of W.)  K % 4 == 0. */
+int bg_linear_bwd_input(const float* gy, const float* W, float* gx, int M, int N, int K, float coef, void* stream);
 int bg_linear_bwd_weight(const float* gy, const float* x, float* dW, float* db, int M, int N, int K, float coef,
                          int accumulate, void* stream);
 /* Grouped forms for layers that share their input x (M,K): the 2*steps AdaIN style FCs of the generator all read the
