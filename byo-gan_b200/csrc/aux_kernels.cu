@@ -210,15 +210,15 @@ __global__ void pack_weight_grouped_kernel(const PackGroups G) {
 // 2-byte store per 128-byte line (154 us for a network's packs that move in ~40 us); since the pack cache was fixed to
 // notice fused optimizer steps this runs twice per iteration.
 constexpr int kPackTile = 64;
+constexpr int kPackStride = kPackTile + 8;                        // 144-byte rows: 16-byte aligned, conflict-free 16-byte reads
+constexpr int kPackTapStride = kPackTile * kPackStride + 8;       // 16-byte aligned, tap planes 4 banks apart
 __global__ void __launch_bounds__(256)
 pack_weight_grouped_tiled_kernel(const PackGroups G) {
   pdl_prologue();
-  extern __shared__ __nv_bfloat16 ptile[];                  // [9][64 co][66 ci], tap planes padded against bank conflicts
-  constexpr int kStride = kPackTile + 2;
-  constexpr int kTapStride = kPackTile * kStride + 2;       // odd number of 4-byte words
+  extern __shared__ __align__(16) __nv_bfloat16 ptile[];    // [9][64 co][72 ci]
   int g = 0;
   while (g + 1 < G.groups && (int)blockIdx.x >= G.blk0[g + 1]) ++g;
-  const int Cout = G.Cout[g], Cin = G.Cin[g], Cin_pad = G.Cin_pad[g];
+  const int Cout = G.Cout[g], Cin = G.Cin[g], Cin_pad = G.Cin_pad[g];      // Cout % 16 == 0, Cin_pad % 8 == 0 (launcher)
   const float coef = G.coef[g];
   const float* __restrict__ w = G.w[g];
   __nv_bfloat16* __restrict__ wf = G.wf[g];
@@ -226,27 +226,48 @@ pack_weight_grouped_tiled_kernel(const PackGroups G) {
   const int tiles_ci = (Cin_pad + kPackTile - 1) / kPackTile;
   const int tile = (int)blockIdx.x - G.blk0[g];
   const int co0 = (tile / tiles_ci) * kPackTile, ci0 = (tile % tiles_ci) * kPackTile;
-  const int nco = min(kPackTile, Cout - co0), nci = min(kPackTile, Cin_pad - ci0);
-  // read: for each co a run of nci * 9 floats (zero beyond Cin); ONE flat loop over (co, run position) so that every
-  // thread has many independent loads in flight (a per-co loop serialised 64 memory round trips per block)
-  const int per_col = nci * 9;
-#pragma unroll 4
-  for (int idx = threadIdx.x; idx < nco * per_col; idx += blockDim.x) {
-    const int col = idx / per_col, j = idx - col * per_col;
-    const int cil = j / 9, tap = j - cil * 9;
-    const float v = (ci0 + cil < Cin) ? w[((size_t)(co0 + col) * Cin + ci0) * 9 + j] * coef : 0.f;
-    ptile[tap * kTapStride + col * kStride + cil] = __float2bfloat16_rn(v);
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  // read: warp w takes the columns co0 + w, w + 8, ...; a column is one run of 64 * 9 floats (zero beyond Cin), 18 coalesced
+  // loads per lane, all in flight; every index division is by a constant
+  for (int col = wp; col < kPackTile; col += 8) {
+    if (co0 + col >= Cout) break;
+    const float* run = w + ((size_t)(co0 + col) * Cin + ci0) * 9;
+    float v[18];
+#pragma unroll
+    for (int it = 0; it < 18; ++it) {
+      const int j = it * 32 + lane;
+      v[it] = (ci0 + j / 9 < Cin) ? run[j] : 0.f;
+    }
+#pragma unroll
+    for (int it = 0; it < 18; ++it) {
+      const int j = it * 32 + lane;
+      const int cil = j / 9, tap = j - cil * 9;
+      ptile[tap * kPackTapStride + col * kPackStride + cil] = __float2bfloat16_rn(v[it] * coef);
+    }
   }
   __syncthreads();
-  // wf[tap][co][ci]: runs of nci along ci
-  for (int idx = threadIdx.x; idx < 9 * nco * nci; idx += blockDim.x) {
-    const int cil = idx % nci, col = (idx / nci) % nco, tap = idx / (nci * nco);
-    wf[((size_t)tap * Cout + co0 + col) * Cin_pad + ci0 + cil] = ptile[tap * kTapStride + col * kStride + cil];
+  // wf[tap][co][ci]: 16-byte stores, 8 lanes per 128-byte row
+  for (int idx = threadIdx.x; idx < 9 * kPackTile * 8; idx += 256) {
+    const int vq = idx & 7, col = (idx >> 3) & (kPackTile - 1), tap = idx >> 9;
+    if (co0 + col < Cout && ci0 + vq * 8 < Cin_pad)
+      *reinterpret_cast<uint4*>(wf + ((size_t)tap * Cout + co0 + col) * Cin_pad + ci0 + vq * 8) =
+          *reinterpret_cast<const uint4*>(ptile + tap * kPackTapStride + col * kPackStride + vq * 8);
   }
-  // wd[8 - tap][ci][co]: runs of nco along co
-  for (int idx = threadIdx.x; idx < 9 * nco * nci; idx += blockDim.x) {
-    const int col = idx % nco, cil = (idx / nco) % nci, tap = idx / (nci * nco);
-    wd[((size_t)(8 - tap) * Cin_pad + ci0 + cil) * Cout + co0 + col] = ptile[tap * kTapStride + col * kStride + cil];
+  // wd[8 - tap][ci][co]: a lane gathers 16 co of one ci (lanes along ci: conflict-free 2-byte reads) and stores 32 bytes
+  for (int idx = threadIdx.x; idx < 9 * 4 * kPackTile; idx += 256) {
+    const int cil = idx & (kPackTile - 1), cg = (idx >> 6) & 3, tap = idx >> 8;
+    if (ci0 + cil >= Cin_pad || co0 + cg * 16 >= Cout) continue;
+    const __nv_bfloat16* src = ptile + tap * kPackTapStride + (cg * 16) * kPackStride + cil;
+    uint32_t pk[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t lo = *reinterpret_cast<const unsigned short*>(src + (2 * i) * kPackStride);
+      const uint32_t hi = *reinterpret_cast<const unsigned short*>(src + (2 * i + 1) * kPackStride);
+      pk[i] = lo | (hi << 16);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(wd + ((size_t)(8 - tap) * Cin_pad + ci0 + cil) * Cout + co0 + cg * 16);
+    dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
   }
 }
 
@@ -481,50 +502,65 @@ __device__ __forceinline__ float up_weight(int r, int l, int L) {
   return wgt;
 }
 
-// adjoint of the above: gx[h,w] = sum_{r,s} up_weight(r,h) up_weight(s,w) gy[r,s]
+// adjoint of the above: gx[h,w] = sum_{r,s} up_weight(r,h) up_weight(s,w) gy[r,s].  Separable: a thread owns 8 channels of
+// kUpStrip vertically adjacent low-res pixels, walks the 2 * kUpStrip + 2 hi-res rows that reach them once, folds each row's
+// four columns with the horizontal weights and adds the result to the (at most two) outputs the row feeds:
+// (2S + 2) * 4 loads for S outputs instead of 16 per output.
+constexpr int kUpStrip = 4;
 __global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ gy, __nv_bfloat16* __restrict__ gx, int N,
                                       int H, int W, int C, Div32 dcv, Div32 dw, Div32 dh) {
   pdl_prologue();
   const int cv = C / 8;
   const int Ho = 2 * H, Wo = 2 * W;
-  const size_t total = (size_t)N * H * W * cv;
+  const size_t total = (size_t)N * (H / kUpStrip) * W * cv;           // dh divides by H / kUpStrip
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     uint32_t cg, uw, uh;
     const uint32_t p = divmod((uint32_t)i, dcv, cg);
     const uint32_t n = divmod(divmod(p, dw, uw), dh, uh);
-    const int c = (int)cg * 8, w = (int)uw, h = (int)uh;
-    F8 acc;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc.v[j] = 0.f;
+    const int c = (int)cg * 8, w = (int)uw, h0 = (int)uh * kUpStrip;
     const __nv_bfloat16* gb = gy + (size_t)n * Ho * Wo * C + c;
-    // the 4 x 4 window of hi-res gradients that read (h, w); out-of-range rows / columns are clamped onto a window
-    // member and given weight 0, so all 16 loads are unconditional and in flight together
-    float wsv[4], wrv[4];
-    int cx[4], ry[4];
+    float wsv[4];
+    int cx[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int sx = 2 * w - 1 + q, r = 2 * h - 1 + q;
-      wsv[q] = (sx >= 0 && sx < Wo) ? up_weight(sx, w, W) : 0.f;
-      wrv[q] = (r >= 0 && r < Ho) ? up_weight(r, h, H) : 0.f;
+      const int sx = 2 * w - 1 + q;
+      wsv[q] = (sx >= 0 && sx < Wo) ? up_weight(sx, w, W) : 0.f;     // out-of-range columns: clamped address, weight 0
       cx[q] = min(max(sx, 0), Wo - 1);
-      ry[q] = min(max(r, 0), Ho - 1);
     }
-    uint4 raw[4][4];
+    F8 acc[kUpStrip];
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
+    for (int k = 0; k < kUpStrip; ++k)
 #pragma unroll
-      for (int t = 0; t < 4; ++t) raw[q][t] = ld_raw8(gb + ((size_t)ry[q] * Wo + cx[t]) * C);
+      for (int j = 0; j < 8; ++j) acc[k].v[j] = 0.f;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int qq = 0; qq < 2 * kUpStrip + 2; ++qq) {
+      const int r = 2 * h0 - 1 + qq;
+      const bool live = r >= 0 && r < Ho;
+      const int rc = min(max(r, 0), Ho - 1);
+      uint4 raw[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) raw[t] = ld_raw8(gb + ((size_t)rc * Wo + cx[t]) * C);
+      F8 row;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) row.v[j] = 0.f;
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        const float ws = wsv[t] * wrv[q];
-        const F8 g = unpack8(raw[q][t]);
+        const F8 g = unpack8(raw[t]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc.v[j] += ws * g.v[j];
+        for (int j = 0; j < 8; ++j) row.v[j] += wsv[t] * g.v[j];
+      }
+      // hi-res row r = 2 * h0 - 1 + qq reaches the outputs k with 2k <= qq <= 2k + 3
+#pragma unroll
+      for (int k = 0; k < kUpStrip; ++k) {
+        if (qq >= 2 * k && qq <= 2 * k + 3) {
+          const float wr = live ? up_weight(r, h0 + k, H) : 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[k].v[j] += wr * row.v[j];
+        }
       }
     }
-    st8(gx + (size_t)p * C + c, acc);
+#pragma unroll
+    for (int k = 0; k < kUpStrip; ++k) st8(gx + (((size_t)n * H + h0 + k) * W + w) * C + c, acc[k]);
   }
 }
 
@@ -729,7 +765,11 @@ __global__ void planes3_to_nhwc_quad_kernel(const float* __restrict__ img, const
 // out[n, j, hw] = coef * sum_c x[p, c] * Wm[c * ws_c + j * ws_j] + bias[j]
 //   toRGB forward (gan.py:172-179,218,222): Wm = weight (3,C,1,1) -> ws_c = 1, ws_j = C, bias
 //   fromRGB input-grad:                     Wm = weight (C,3,1,1) -> ws_c = 3, ws_j = 1, no bias
-// One warp per pixel group: lanes split the channel vectors, shuffle-reduce the 3 dot products.
+// One warp per pixel group: lanes split the channel vectors, shuffle-reduce the 3 dot products.  kRegW (C <= 256: a lane
+// sees one channel vector only): its 24 weights live in registers; kNhwcUnroll pixel groups per trip keep that many
+// 16-byte loads in flight per lane.
+constexpr int kNhwcUnroll = 4;
+template <bool kRegW>
 __global__ void nhwc_to_planes3_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ Wm,
                                        const float* __restrict__ bias, float* __restrict__ out, size_t P, int HW,
                                        int C, int ws_c, int ws_j, float coef) {
@@ -750,31 +790,68 @@ __global__ void nhwc_to_planes3_kernel(const __nv_bfloat16* __restrict__ x, cons
   const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
   const size_t groups = (P + pix_per_warp - 1) / pix_per_warp;
   const float b0 = bias ? bias[0] : 0.f, b1 = bias ? bias[1] : 0.f, b2 = bias ? bias[2] : 0.f;
-  for (size_t gidx = warp_global; gidx < groups; gidx += nwarps) {
-    const size_t p = gidx * pix_per_warp + pw;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-    if (p < P) {
-      for (int v = sub; v < cv; v += lanes_per_pix) {
-        const F8 a = ld8(x + p * C + v * 8);
+  float w0[8], w1[8], w2[8];
+  if (kRegW) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      w0[j] = sw[sub * 8 + j];
+      w1[j] = sw[C + sub * 8 + j];
+      w2[j] = sw[2 * C + sub * 8 + j];
+    }
+  }
+  for (size_t g0 = warp_global; g0 < groups; g0 += nwarps * kNhwcUnroll) {
+    float s0[kNhwcUnroll], s1[kNhwcUnroll], s2[kNhwcUnroll];
+    if (kRegW) {
+      uint4 raw[kNhwcUnroll];
+#pragma unroll
+      for (int u = 0; u < kNhwcUnroll; ++u) {
+        const size_t p = (g0 + (size_t)u * nwarps) * pix_per_warp + pw;
+        raw[u] = p < P ? ld_raw8(x + p * C + sub * 8) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < kNhwcUnroll; ++u) {
+        const F8 a = unpack8(raw[u]);
+        s0[u] = s1[u] = s2[u] = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int c = v * 8 + j;
-          s0 += a.v[j] * sw[c];
-          s1 += a.v[j] * sw[C + c];
-          s2 += a.v[j] * sw[2 * C + c];
+          s0[u] += a.v[j] * w0[j];
+          s1[u] += a.v[j] * w1[j];
+          s2[u] += a.v[j] * w2[j];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < kNhwcUnroll; ++u) {
+        const size_t p = (g0 + (size_t)u * nwarps) * pix_per_warp + pw;
+        s0[u] = s1[u] = s2[u] = 0.f;
+        if (p < P) {
+          for (int v = sub; v < cv; v += lanes_per_pix) {
+            const F8 a = ld8(x + p * C + v * 8);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int c = v * 8 + j;
+              s0[u] += a.v[j] * sw[c];
+              s1[u] += a.v[j] * sw[C + c];
+              s2[u] += a.v[j] * sw[2 * C + c];
+            }
+          }
         }
       }
     }
-    for (int o = lanes_per_pix >> 1; o > 0; o >>= 1) {
-      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    }
-    if (p < P && sub == 0) {
-      const size_t b = (p / HW) * (size_t)(3 * HW) + (p % HW);
-      out[b] = s0 + b0;
-      out[b + HW] = s1 + b1;
-      out[b + 2 * (size_t)HW] = s2 + b2;
+#pragma unroll
+    for (int u = 0; u < kNhwcUnroll; ++u) {
+      for (int o = lanes_per_pix >> 1; o > 0; o >>= 1) {
+        s0[u] += __shfl_xor_sync(0xffffffffu, s0[u], o);
+        s1[u] += __shfl_xor_sync(0xffffffffu, s1[u], o);
+        s2[u] += __shfl_xor_sync(0xffffffffu, s2[u], o);
+      }
+      const size_t p = (g0 + (size_t)u * nwarps) * pix_per_warp + pw;
+      if (p < P && sub == 0) {
+        const size_t b = (p / HW) * (size_t)(3 * HW) + (p % HW);
+        out[b] = s0[u] + b0;
+        out[b + HW] = s1[u] + b1;
+        out[b + 2 * (size_t)HW] = s2[u] + b2;
+      }
     }
   }
 }
@@ -1212,11 +1289,11 @@ int launch_upsample2x_fwd(const void* x, void* y, int N, int H, int W, int C, cu
 }
 
 int launch_upsample2x_bwd(const void* gy, void* gx, int N, int H, int W, int C, cudaStream_t s) {
-  BG_REQUIRE(C % 8 == 0, "upsample2x_bwd: C must be a multiple of 8");
-  const size_t total = (size_t)N * H * W * (C / 8);
-  BG_REQUIRE(total < (1ull << 32), "upsample2x_bwd: map too large");
+  BG_REQUIRE(C % 8 == 0 && H % kUpStrip == 0, "upsample2x_bwd: C must be a multiple of 8 and H of %d", kUpStrip);
+  BG_REQUIRE((size_t)N * H * W * (C / 8) < (1ull << 32), "upsample2x_bwd: map too large");
+  const size_t total = (size_t)N * (H / kUpStrip) * W * (C / 8);
   BG_CHECK_CUDA(launch_pdl(upsample2x_bwd_kernel, grid_for(total), kBlock, 0, s, (const __nv_bfloat16*)gy,
-                           (__nv_bfloat16*)gx, N, H, W, C, make_div(C / 8), make_div(W), make_div(H)));
+                           (__nv_bfloat16*)gx, N, H, W, C, make_div(C / 8), make_div(W), make_div(H / kUpStrip)));
   return 0;
 }
 
@@ -1274,8 +1351,13 @@ int launch_nhwc_to_planes3(const void* x, const float* Wm, const float* bias, fl
   const int cv = C / 8;
   const int lanes_per_pix = cv < 32 ? cv : 32;
   const size_t groups = (P + (32 / lanes_per_pix) - 1) / (32 / lanes_per_pix);
-  BG_CHECK_CUDA(launch_pdl(nhwc_to_planes3_kernel, grid_for(groups * 32), kBlock, (size_t)C * 3 * sizeof(float), s,
-                           (const __nv_bfloat16*)x, Wm, bias, out, P, HW, C, ws_c, ws_j, coef));
+  const int grid = grid_for((groups + kNhwcUnroll - 1) / kNhwcUnroll * 32);
+  if (cv <= 32)
+    BG_CHECK_CUDA(launch_pdl(nhwc_to_planes3_kernel<true>, grid, kBlock, (size_t)C * 3 * sizeof(float), s,
+                             (const __nv_bfloat16*)x, Wm, bias, out, P, HW, C, ws_c, ws_j, coef));
+  else
+    BG_CHECK_CUDA(launch_pdl(nhwc_to_planes3_kernel<false>, grid, kBlock, (size_t)C * 3 * sizeof(float), s,
+                             (const __nv_bfloat16*)x, Wm, bias, out, P, HW, C, ws_c, ws_j, coef));
   return 0;
 }
 
@@ -1391,8 +1473,10 @@ int launch_pack_weight_grouped(const float* const* w, void* const* wf, void* con
     blocks += (int)b;
   }
   G.blk0[groups] = blocks;
-  bool all3 = true;
-  for (int g = 0; g < groups; ++g) all3 = all3 && ks[g] == 3;
+  bool all3 = true;                    // the tiled kernel: 3x3 layers with 16-byte-aligned rows on both packs
+  for (int g = 0; g < groups; ++g)
+    all3 = all3 && ks[g] == 3 && Cout[g] % 16 == 0 && Cin_pad[g] % 8 == 0 &&
+           ((reinterpret_cast<uintptr_t>(wf[g]) | reinterpret_cast<uintptr_t>(wd[g])) & 15) == 0;
   if (all3) {
     int tiles = 0;
     for (int g = 0; g < groups; ++g) {
@@ -1400,7 +1484,7 @@ int launch_pack_weight_grouped(const float* const* w, void* const* wf, void* con
       tiles += ((Cout[g] + kPackTile - 1) / kPackTile) * ((Cin_pad[g] + kPackTile - 1) / kPackTile);
     }
     G.blk0[groups] = tiles;
-    const size_t smem = (size_t)9 * (kPackTile * (kPackTile + 2) + 2) * sizeof(__nv_bfloat16);
+    const size_t smem = (size_t)9 * kPackTapStride * sizeof(__nv_bfloat16);
     static bool attr_set = false;
     if (!attr_set) {
       BG_CHECK_CUDA(cudaFuncSetAttribute(pack_weight_grouped_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -786,55 +786,70 @@ int launch_linear_fwd(const float* x, const float* W, const float* bias, float* 
 // Input gradient of EqualizedLinear (gan.py:16-17) straight from the (N, K) row-major weight: gx[m][k] = coef * sum_n
 // gy[m][n] * W[n][k].  The forward kernel needs W^T for this (a cached fp32 transpose per layer, re-made after every
 // optimizer step: 25 transpose launches per iteration); here W rows are read as they lie — coalesced along k — each lane
-// owns 4 consecutive k, the 8 warps of a block split n and meet in shared memory.
+// owns 2 consecutive k, the 8 warps of a block split n (gy staged in shared memory) and meet in shared memory.
 // ---------------------------------------------------------------------------------------------
-constexpr int kLbiMT = 8;        // rows of gy per pass
+constexpr int kLbiMT = 8;        // rows of gy per block
+constexpr int kLbiNC = 512;      // n per staged chunk of gy
 __global__ void __launch_bounds__(256)
 linear_bwd_input_kernel(const float* __restrict__ gy, const float* __restrict__ W, float* __restrict__ gx, int M, int N,
                         int K, float coef) {
   pdl_prologue();
-  __shared__ float4 part[8][kLbiMT][32];
+  __shared__ __align__(16) float gs[kLbiNC][kLbiMT];          // gy chunk, transposed: one n = two 16-byte broadcasts
+  __shared__ float2 part[8][kLbiMT][32];
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-  const int k = ((int)blockIdx.x * 32 + lane) * 4;
+  const int k = ((int)blockIdx.x * 32 + lane) * 2;            // two consecutive k per lane: 256-byte rows per warp
   const int m0 = (int)blockIdx.y * kLbiMT;
-  const bool live = k < K;                                   // K % 4 == 0 (launcher)
-  float4 acc[kLbiMT];
+  const bool live = k < K;                                    // K % 2 == 0 (launcher)
+  float2 acc[kLbiMT];
 #pragma unroll
-  for (int i = 0; i < kLbiMT; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int nspan = (N + 7) / 8;
-  const int n_lo = wp * nspan, n_hi = min(N, n_lo + nspan);
-  for (int n = n_lo; n < n_hi; ++n) {
-    const float4 w4 = live ? *reinterpret_cast<const float4*>(W + (size_t)n * K + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < kLbiMT; ++i) acc[i] = make_float2(0.f, 0.f);
+  for (int nc0 = 0; nc0 < N; nc0 += kLbiNC) {
+    const int cn = min(kLbiNC, N - nc0);
+    __syncthreads();
+    {
+      // warp w stages row m0 + w; 16 independent loads in flight per lane
+      const bool row_live = m0 + wp < M;
+      const float* grow = gy + (size_t)min(m0 + wp, M - 1) * N + nc0;
+#pragma unroll 16
+      for (int n = lane; n < cn; n += 32) gs[n][wp] = row_live ? grow[n] : 0.f;
+    }
+    __syncthreads();
+    const int per = (cn + 7) >> 3;
+    const int lo = wp * per, hi = min(cn, lo + per);
+    const float* wp0 = W + (size_t)nc0 * K + (live ? k : 0);
+#pragma unroll 16
+    for (int n = lo; n < hi; ++n) {                           // 16 independent weight rows in flight per lane
+      const float2 w2 = *reinterpret_cast<const float2*>(wp0 + (size_t)n * K);
+      const float4 ga = *reinterpret_cast<const float4*>(&gs[n][0]);
+      const float4 gb = *reinterpret_cast<const float4*>(&gs[n][4]);
+      const float g[kLbiMT] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
 #pragma unroll
-    for (int i = 0; i < kLbiMT; ++i) {
-      const float g = gy[(size_t)min(m0 + i, M - 1) * N + n];
-      acc[i].x = fmaf(g, w4.x, acc[i].x);
-      acc[i].y = fmaf(g, w4.y, acc[i].y);
-      acc[i].z = fmaf(g, w4.z, acc[i].z);
-      acc[i].w = fmaf(g, w4.w, acc[i].w);
+      for (int i = 0; i < kLbiMT; ++i) {
+        acc[i].x = fmaf(g[i], w2.x, acc[i].x);
+        acc[i].y = fmaf(g[i], w2.y, acc[i].y);
+      }
     }
   }
 #pragma unroll
   for (int i = 0; i < kLbiMT; ++i) part[wp][i][lane] = acc[i];
   __syncthreads();
-  // 8 warps x 8 rows: warp w finishes row w
-  if (live && m0 + wp < M) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (live && m0 + wp < M) {                                  // 8 warps x 8 rows: warp w finishes row w, fixed order
+    float2 v = make_float2(0.f, 0.f);
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
-      const float4 pv = part[w][wp][lane];
-      v.x += pv.x; v.y += pv.y; v.z += pv.z; v.w += pv.w;
+      const float2 pv = part[w][wp][lane];
+      v.x += pv.x;
+      v.y += pv.y;
     }
-    v.x *= coef; v.y *= coef; v.z *= coef; v.w *= coef;
-    *reinterpret_cast<float4*>(gx + (size_t)(m0 + wp) * K + k) = v;
+    *reinterpret_cast<float2*>(gx + (size_t)(m0 + wp) * K + k) = make_float2(v.x * coef, v.y * coef);
   }
 }
 
 int launch_linear_bwd_input(const float* gy, const float* W, float* gx, int M, int N, int K, float coef, cudaStream_t s) {
-  BG_REQUIRE(M > 0 && N > 0 && K > 0 && K % 4 == 0, "linear_bwd_input: bad shape M %d N %d K %d", M, N, K);
-  BG_REQUIRE((reinterpret_cast<uintptr_t>(W) & 15) == 0 && (reinterpret_cast<uintptr_t>(gx) & 15) == 0,
-             "linear_bwd_input: W and gx must be 16-byte aligned");
-  dim3 grid((K / 4 + 31) / 32, (M + kLbiMT - 1) / kLbiMT);
+  BG_REQUIRE(M > 0 && N > 0 && K > 0 && K % 2 == 0, "linear_bwd_input: bad shape M %d N %d K %d", M, N, K);
+  BG_REQUIRE((reinterpret_cast<uintptr_t>(W) & 7) == 0 && (reinterpret_cast<uintptr_t>(gx) & 7) == 0,
+             "linear_bwd_input: W and gx must be 8-byte aligned");
+  dim3 grid((K / 2 + 31) / 32, (M + kLbiMT - 1) / kLbiMT);
   BG_CHECK_CUDA(launch_pdl(linear_bwd_input_kernel, grid, 256, 0, s, gy, W, gx, M, N, K, coef));
   return 0;
 }

@@ -230,7 +230,7 @@ def linear_bwd_input(gy, w, packs: PackCache):
     n, k = w2.shape
     m = gy.shape[0]
     gx = _f32(m, k, device=gy.device)
-    if k % 4 == 0:
+    if k % 2 == 0:
         call("bg_linear_bwd_input", gy, w2, gx, m, n, k, coef_of(w))
     else:
         call("bg_linear_fwd", gy, packs.linear_t(w), None, gx, m, k, n, coef_of(w), 0, SLOPE)
@@ -572,13 +572,13 @@ def _generator_backward(gen, packs: PackCache, tape, g_img, need: Dict[int, bool
         sc, k, j, r, c = L["sc"], L["k"], L["j"], L["R"], L["C"]
         a, stats, style = L["a"], L["stats"], L["style"]
         bs = _acc(B, c, 2, device=dev)
-        call("bg_adain_bwd_reduce", gx, a, stats, bs, B, r * r, c, IN_EPS)
         gpre = torch.empty_like(a)
         is_const = L["const"]
         need_b = (not is_const) and want(sc.conv.bias)
         need_nw = want(sc.inject_noise.weights)
         # bias / noise-weight gradients (gan.py:30,52) are reduced while gpre is written
         ws = _acc(2, c, device=dev) if (need_b or need_nw) else None
+        call("bg_adain_bwd_reduce", gx, a, stats, bs, B, r * r, c, IN_EPS)
         call("bg_adain_bwd_apply", gx, a, stats, style, bs, gpre, B, r * r, c, IN_EPS, SLOPE, 1,
              L["noise"] if ws is not None else None, ws)
         # style FC (gan.py:60,66): dL/dgamma = sum g*ahat, dL/dbeta = sum g; the FC gradients of all layers are taken in

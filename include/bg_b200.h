@@ -201,7 +201,7 @@ int bg_adain_bwd_apply(const void* g, const void* a, const float* stats, const f
 int bg_linear_fwd(const float* x, const float* W, const float* bias, float* y, int M, int N, int K, float coef, int act,
                   float slope, void* stream);
 /* Input gradient of y = coef * x W^T + b straight from the (N, K) row-major weight: gx (M, K) = coef * gy (M, N) @ W.
- * (autograd's addmm backward of gan.py:16-17; needs no transposed copy of W.)  K % 4 == 0. */
+ * (autograd's addmm backward of gan.py:16-17; needs no transposed copy of W.)  K % 2 == 0. */
 int bg_linear_bwd_input(const float* gy, const float* W, float* gx, int M, int N, int K, float coef, void* stream);
 int bg_linear_bwd_weight(const float* gy, const float* x, float* dW, float* db, int M, int N, int K, float coef,
                          int accumulate, void* stream);

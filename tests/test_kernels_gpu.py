@@ -182,6 +182,13 @@ def test_upsample_pool_adain_aux():
     xr = nchw(x).requires_grad_()
     F.interpolate(xr, scale_factor=2, mode="bilinear").backward(nchw(gy))
     assert relerr(nchw(gx), xr.grad) < 4e-3
+    for (n2, c2, h2, w2) in [(2, 8, 4, 4), (1, 64, 4, 16), (2, 16, 32, 8), (1, 512, 16, 16)]:   # strips of 4 rows per thread
+        gy2 = nhwc(torch.randn(n2, c2, 2 * h2, 2 * w2, device=DEV))
+        gx2 = torch.full((n2, h2, w2, c2), float("nan"), dtype=torch.bfloat16, device=DEV)
+        bgn.call("bg_upsample2x_bwd", gy2, gx2, n2, h2, w2, c2)
+        xr2 = torch.zeros(n2, c2, h2, w2, device=DEV, requires_grad=True)
+        F.interpolate(xr2, scale_factor=2, mode="bilinear").backward(nchw(gy2))
+        assert relerr(nchw(gx2), xr2.grad) < 4e-3, (n2, c2, h2, w2)
     # pool + lrelu
     u = nhwc(torch.randn(n, c, 2 * h, 2 * w_, device=DEV))
     yo = torch.empty(n, h, w_, c, dtype=torch.bfloat16, device=DEV)
@@ -272,6 +279,32 @@ def test_to_rgb_adain():
         xo = style[:, :c, None, None] * F.instance_norm(af, eps=1e-8) + style[:, c:, None, None]
         ref = F.conv2d(xo, wm * coef, b)
         assert relerr(out, ref) < 2e-3, (n, c, h, relerr(out, ref))
+
+
+@pytest.mark.parametrize("n,c,h", [(3, 16, 8), (2, 32, 64), (5, 64, 16), (1, 256, 8), (2, 512, 4), (3, 1024, 4)])
+def test_rgb_1x1_maps(n, c, h):
+    """toRGB forward / fromRGB input gradient (gan.py:172-179, 351-355): NHWC bf16 features -> 3 fp32 planes, and the
+    reverse map (fromRGB forward with bias + LeakyReLU, toRGB input gradient)."""
+    torch.manual_seed(n * c + h)
+    x = nhwc(torch.randn(n, c, h, h, device=DEV))
+    coef = math.sqrt(2 / c)
+    w_to = torch.randn(3, c, 1, 1, device=DEV)
+    b = torch.randn(3, device=DEV)
+    out = torch.full((n, 3, h, h), float("nan"), device=DEV)
+    bgn.call("bg_nhwc_to_planes3", x, w_to, b, out, n * h * h, h * h, c, 1, c, coef)
+    xd = nchw(x).double()                                            # fp64 references: cuDNN's fp32 conv may use TF32
+    assert relerr(out, F.conv2d(xd, w_to.double() * coef, b.double())) < 1e-5
+    w_from = torch.randn(c, 3, 1, 1, device=DEV)
+    c3 = math.sqrt(2 / 3)
+    bgn.call("bg_nhwc_to_planes3", x, w_from, None, out, n * h * h, h * h, c, 3, 1, c3)
+    assert relerr(out, F.conv_transpose2d(xd, w_from.double() * c3)) < 1e-5
+    img = torch.randn(n, 3, h, h, device=DEV)
+    bc = torch.randn(c, device=DEV)
+    y = torch.empty(n, h, h, c, dtype=torch.bfloat16, device=DEV)
+    bgn.call("bg_planes3_to_nhwc", img, w_from, bc, None, y, n * h * h, h * h, c, 3, 1, c3, 1, 0.2)
+    assert relerr(nchw(y), F.leaky_relu(F.conv2d(img.double(), w_from.double() * c3, bc.double()), 0.2)) < 4e-3
+    bgn.call("bg_planes3_to_nhwc", img, w_to, None, None, y, n * h * h, h * h, c, 1, c, coef, 0, 0.2)
+    assert relerr(nchw(y), F.conv_transpose2d(img.double(), w_to.double() * coef)) < 4e-3
 
 
 @pytest.mark.parametrize("dims", [(3, 16, 8, 8), (2, 64, 32, 32), (2, 512, 4, 4), (1, 128, 64, 64)])
