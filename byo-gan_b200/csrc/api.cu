@@ -59,8 +59,9 @@ int launch_style_modulate(const float*, const float*, const float*, const float*
                           float, cudaStream_t);
 int launch_to_rgb_adain(const void*, const float*, const float*, const float*, const float*, float*, int, int, int, float,
                         float, cudaStream_t);
-int launch_linear_grouped(int, const float*, const float* const*, const float* const*, float* const*, float* const*,
-                          float* const*, const int*, const float*, int, int, int, int, float, float*, cudaStream_t);
+int launch_linear_grouped(int, const float*, const float* const*, const float* const*, const float* const*, float* const*,
+                          float* const*, float* const*, const int*, const float*, int, int, int, int, float, float*,
+                          cudaStream_t);
 int launch_pack_weight_grouped(const float* const*, void* const*, void* const*, const int*, const int*, const int*,
                                const int*, const float*, int, cudaStream_t);
 int launch_pack_weight_pool4(const float*, void*, int, int, float, cudaStream_t);
@@ -265,17 +266,17 @@ int bg_adain_bwd_apply(const void* g, const void* a, const float* stats, const f
 
 int bg_linear_fwd_grouped(const float* x, const float* const* W, const float* const* bias, float* const* y, const int* N,
                           const float* coef, int groups, int M, int K, int act, float slope, void* stream) {
-  return bg::launch_linear_grouped(0, x, W, bias, y, nullptr, nullptr, N, coef, groups, M, K, act, slope, nullptr,
+  return bg::launch_linear_grouped(0, x, nullptr, W, bias, y, nullptr, nullptr, N, coef, groups, M, K, act, slope, nullptr,
                                    S(stream));
 }
-int bg_linear_bwd_weight_grouped(const float* x, float* const* gy, float* const* dW, float* const* db, const int* N,
+int bg_linear_bwd_weight_grouped(const float* const* x, float* const* gy, float* const* dW, float* const* db, const int* N,
                                  const float* coef, int groups, int M, int K, void* stream) {
-  return bg::launch_linear_grouped(1, x, reinterpret_cast<const float* const*>(dW), nullptr, gy, dW, db, N, coef, groups, M,
-                                   K, 0, 0.f, nullptr, S(stream));
+  return bg::launch_linear_grouped(1, nullptr, x, reinterpret_cast<const float* const*>(dW), nullptr, gy, dW, db, N, coef,
+                                   groups, M, K, 0, 0.f, nullptr, S(stream));
 }
-int bg_linear_bwd_input_grouped(float* const* gy, const float* const* Wt, const int* N, const float* coef, int groups,
+int bg_linear_bwd_input_grouped(float* const* gy, const float* const* W, const int* N, const float* coef, int groups,
                                 int M, int K, float* gx, void* stream) {
-  return bg::launch_linear_grouped(2, nullptr, Wt, nullptr, gy, nullptr, nullptr, N, coef, groups, M, K, 0, 0.f, gx,
+  return bg::launch_linear_grouped(2, nullptr, nullptr, W, nullptr, gy, nullptr, nullptr, N, coef, groups, M, K, 0, 0.f, gx,
                                    S(stream));
 }
 int bg_linear_fwd(const float* x, const float* W, const float* bias, float* y, int M, int N, int K, float coef, int act,

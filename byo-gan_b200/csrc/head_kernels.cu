@@ -117,7 +117,8 @@ __global__ void linear_bwd_weight_kernel(const float* __restrict__ gy, const flo
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxLinGroups = 16;
 struct LinGroups {
-  const float* W[kMaxLinGroups];     // fwd / bwd_weight: (N_g, K) weights;  bwd_input: (K, N_g) TRANSPOSED weights
+  const float* W[kMaxLinGroups];     // (N_g, K) weights
+  const float* x[kMaxLinGroups];     // bwd_weight: the layer's input (M, K)
   const float* b[kMaxLinGroups];     // fwd: bias (may be null)
   float* y[kMaxLinGroups];           // fwd: output (M, N_g);  bwd_*: gy (M, N_g) (read)
   float* dW[kMaxLinGroups];          // bwd_weight: (N_g, K)
@@ -171,12 +172,13 @@ __global__ void linear_fwd_grouped_kernel(const float* __restrict__ x, const Lin
 }
 
 // bwd_weight: blocks of group g cover (K/4 threads) x (N_g / kLbwNT row groups); dW = coef * gy^T x, db = sum_m gy
-__global__ void linear_bwd_weight_grouped_kernel(const float* __restrict__ x, const LinGroups G, int M, int K) {
+__global__ void linear_bwd_weight_grouped_kernel(const LinGroups G, int M, int K) {
   pdl_prologue();
   int g = 0;
   while (g + 1 < G.groups && (int)blockIdx.x >= G.blk0[g + 1]) ++g;
   const int N = G.N[g];
   const float* __restrict__ gy = G.y[g];
+  const float* __restrict__ x = G.x[g];
   const int kblocks = (K / 4 + 127) / 128;
   const int local = (int)blockIdx.x - G.blk0[g];
   const int k = ((local % kblocks) * blockDim.x + threadIdx.x) * 4;
@@ -210,45 +212,6 @@ __global__ void linear_bwd_weight_grouped_kernel(const float* __restrict__ x, co
 #pragma unroll 8
     for (int m = 0; m < M; ++m) sacc += gy[(size_t)m * N + n0 + threadIdx.x];
     G.db[g][n0 + threadIdx.x] = sacc;
-  }
-}
-
-// bwd_input: gx[m,k] = sum_g coef_g * sum_n gy_g[m,n] * Wt_g[k,n]   (Wt_g = transposed weight (K, N_g)); one warp per
-// (k, group of kLinMT rows), looping over the groups: the sum over layers needs no separate accumulation pass
-__global__ void linear_bwd_input_grouped_kernel(const LinGroups G, float* __restrict__ gx, int M, int K) {
-  pdl_prologue();
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  const int mgroups = (M + kLinMT - 1) / kLinMT;
-  if (warp >= K * mgroups) return;
-  const int k = warp % K;
-  const int m0 = (warp / K) * kLinMT;
-  float acc[kLinMT];
-#pragma unroll
-  for (int i = 0; i < kLinMT; ++i) acc[i] = 0.f;
-  for (int g = 0; g < G.groups; ++g) {
-    const int N = G.N[g];
-    const float* wrow = G.W[g] + (size_t)k * N;
-    const float* gy = G.y[g];
-    const float coef = G.coef[g];
-    for (int n = lane * 4; n < N; n += 128) {
-      float4 wv = *reinterpret_cast<const float4*>(wrow + n);
-      wv.x *= coef; wv.y *= coef; wv.z *= coef; wv.w *= coef;
-#pragma unroll
-      for (int i = 0; i < kLinMT; ++i) {
-        if (m0 + i < M) {
-          const float4 gv = *reinterpret_cast<const float4*>(gy + (size_t)(m0 + i) * N + n);
-          acc[i] += gv.x * wv.x + gv.y * wv.y + gv.z * wv.z + gv.w * wv.w;
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < kLinMT; ++i) acc[i] = warp_sum(acc[i]);
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < kLinMT; ++i)
-      if (m0 + i < M) gx[(size_t)(m0 + i) * K + k] = acc[i];
   }
 }
 
@@ -783,75 +746,127 @@ int launch_linear_fwd(const float* x, const float* W, const float* bias, float* 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Input gradient of EqualizedLinear (gan.py:16-17) straight from the (N, K) row-major weight: gx[m][k] = coef * sum_n
-// gy[m][n] * W[n][k].  The forward kernel needs W^T for this (a cached fp32 transpose per layer, re-made after every
-// optimizer step: 25 transpose launches per iteration); here W rows are read as they lie — coalesced along k — each lane
-// owns 2 consecutive k, the 8 warps of a block split n (gy staged in shared memory) and meet in shared memory.
+// Input gradient of one or several EqualizedLinear layers that share their input (gan.py:16-17; the AdaIN style FCs,
+// gan.py:60,66), straight from the (N_g, K) row-major weights:  gx[m][k] = sum_g coef_g * sum_n gy_g[m][n] * W_g[n][k].
+// No transposed weight copies: rows of W are read as they lie (coalesced along k, two k per lane).  A block owns
+// (64 k) x (8 rows of gy); the concatenated n range of all groups is split over the `zsplit` CTAs of a cluster, inside a
+// CTA over its 8 warps (gy staged, pre-scaled, in shared memory).  Warp partials meet in shared memory, CTA partials in
+// the leader's registers through DSMEM in rank order: no atomics, the result does not depend on timing.
 // ---------------------------------------------------------------------------------------------
 constexpr int kLbiMT = 8;        // rows of gy per block
 constexpr int kLbiNC = 512;      // n per staged chunk of gy
+constexpr int kLbiMaxZ = 8;      // portable cluster size
+__device__ __forceinline__ float2 ld_dsmem_f2(uint32_t cluster_addr) {
+  float2 v;
+  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(cluster_addr));
+  return v;
+}
 __global__ void __launch_bounds__(256)
-linear_bwd_input_kernel(const float* __restrict__ gy, const float* __restrict__ W, float* __restrict__ gx, int M, int N,
-                        int K, float coef) {
+linear_bwd_input_kernel(const LinGroups G, float* __restrict__ gx, int M, int K, int total_n, int zsplit) {
   pdl_prologue();
   __shared__ __align__(16) float gs[kLbiNC][kLbiMT];          // gy chunk, transposed: one n = two 16-byte broadcasts
   __shared__ float2 part[8][kLbiMT][32];
+  __shared__ float2 cta_sum[kLbiMT][32];
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-  const int k = ((int)blockIdx.x * 32 + lane) * 2;            // two consecutive k per lane: 256-byte rows per warp
+  const int z = (int)blockIdx.x % zsplit;                     // rank in the cluster (cluster dims (zsplit, 1, 1))
+  const int k = (((int)blockIdx.x / zsplit) * 32 + lane) * 2; // two consecutive k per lane: 256-byte rows per warp
   const int m0 = (int)blockIdx.y * kLbiMT;
   const bool live = k < K;                                    // K % 2 == 0 (launcher)
   float2 acc[kLbiMT];
 #pragma unroll
   for (int i = 0; i < kLbiMT; ++i) acc[i] = make_float2(0.f, 0.f);
-  for (int nc0 = 0; nc0 < N; nc0 += kLbiNC) {
-    const int cn = min(kLbiNC, N - nc0);
-    __syncthreads();
-    {
-      // warp w stages row m0 + w; 16 independent loads in flight per lane
-      const bool row_live = m0 + wp < M;
-      const float* grow = gy + (size_t)min(m0 + wp, M - 1) * N + nc0;
+  const int share = (total_n + zsplit - 1) / zsplit;
+  const int z_lo = z * share, z_hi = min(total_n, z_lo + share);
+  int off = 0;
+  for (int g = 0; g < G.groups; ++g) {
+    const int N = G.N[g];
+    const int a = max(z_lo, off) - off, b = min(z_hi, off + N) - off;   // this CTA's rows [a, b) of group g
+    off += N;
+    if (a >= b) continue;
+    const float coef = G.coef[g];
+    const float* __restrict__ gy = G.y[g];
+    const float* __restrict__ W = G.W[g];
+    for (int nc0 = a; nc0 < b; nc0 += kLbiNC) {
+      const int cn = min(kLbiNC, b - nc0);
+      __syncthreads();
+      {
+        // warp w stages row m0 + w; 16 independent loads in flight per lane
+        const bool row_live = m0 + wp < M;
+        const float* grow = gy + (size_t)min(m0 + wp, M - 1) * N + nc0;
 #pragma unroll 16
-      for (int n = lane; n < cn; n += 32) gs[n][wp] = row_live ? grow[n] : 0.f;
-    }
-    __syncthreads();
-    const int per = (cn + 7) >> 3;
-    const int lo = wp * per, hi = min(cn, lo + per);
-    const float* wp0 = W + (size_t)nc0 * K + (live ? k : 0);
+        for (int n = lane; n < cn; n += 32) gs[n][wp] = row_live ? grow[n] * coef : 0.f;
+      }
+      __syncthreads();
+      const int per = (cn + 7) >> 3;
+      const int lo = wp * per, hi = min(cn, lo + per);
+      const float* wp0 = W + (size_t)nc0 * K + (live ? k : 0);
 #pragma unroll 16
-    for (int n = lo; n < hi; ++n) {                           // 16 independent weight rows in flight per lane
-      const float2 w2 = *reinterpret_cast<const float2*>(wp0 + (size_t)n * K);
-      const float4 ga = *reinterpret_cast<const float4*>(&gs[n][0]);
-      const float4 gb = *reinterpret_cast<const float4*>(&gs[n][4]);
-      const float g[kLbiMT] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+      for (int n = lo; n < hi; ++n) {                         // 16 independent weight rows in flight per lane
+        const float2 w2 = *reinterpret_cast<const float2*>(wp0 + (size_t)n * K);
+        const float4 ga = *reinterpret_cast<const float4*>(&gs[n][0]);
+        const float4 gb = *reinterpret_cast<const float4*>(&gs[n][4]);
+        const float gv[kLbiMT] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
 #pragma unroll
-      for (int i = 0; i < kLbiMT; ++i) {
-        acc[i].x = fmaf(g[i], w2.x, acc[i].x);
-        acc[i].y = fmaf(g[i], w2.y, acc[i].y);
+        for (int i = 0; i < kLbiMT; ++i) {
+          acc[i].x = fmaf(gv[i], w2.x, acc[i].x);
+          acc[i].y = fmaf(gv[i], w2.y, acc[i].y);
+        }
       }
     }
   }
 #pragma unroll
   for (int i = 0; i < kLbiMT; ++i) part[wp][i][lane] = acc[i];
   __syncthreads();
-  if (live && m0 + wp < M) {                                  // 8 warps x 8 rows: warp w finishes row w, fixed order
-    float2 v = make_float2(0.f, 0.f);
+  float2 v = make_float2(0.f, 0.f);                           // 8 warps x 8 rows: warp w finishes row w, fixed order
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
-      const float2 pv = part[w][wp][lane];
-      v.x += pv.x;
-      v.y += pv.y;
-    }
-    *reinterpret_cast<float2*>(gx + (size_t)(m0 + wp) * K + k) = make_float2(v.x * coef, v.y * coef);
+  for (int w = 0; w < 8; ++w) {
+    const float2 pv = part[w][wp][lane];
+    v.x += pv.x;
+    v.y += pv.y;
   }
+  if (zsplit > 1) {
+    cta_sum[wp][lane] = v;
+    cluster_sync_all();                                       // every CTA's partial is in its shared memory
+    if (z == 0) {
+      const uint32_t local = smem_u32(&cta_sum[wp][lane]);
+      for (int r = 1; r < zsplit; ++r) {
+        const float2 pv = ld_dsmem_f2(mapa_cta(local, (uint32_t)r));
+        v.x += pv.x;
+        v.y += pv.y;
+      }
+    }
+    cluster_sync_all();                                       // the leader is done reading its peers
+    if (z != 0) return;
+  }
+  if (live && m0 + wp < M) *reinterpret_cast<float2*>(gx + (size_t)(m0 + wp) * K + k) = v;
+}
+
+static int launch_linear_bwd_input_groups(const LinGroups& G, float* gx, int M, int K, cudaStream_t s) {
+  BG_REQUIRE(M > 0 && K > 0 && K % 2 == 0, "linear_bwd_input: bad shape M %d K %d", M, K);
+  BG_REQUIRE((reinterpret_cast<uintptr_t>(gx) & 7) == 0, "linear_bwd_input: gx must be 8-byte aligned");
+  int total_n = 0;
+  for (int g = 0; g < G.groups; ++g) {
+    BG_REQUIRE(G.N[g] > 0 && (reinterpret_cast<uintptr_t>(G.W[g]) & 7) == 0, "linear_bwd_input: bad group %d", g);
+    total_n += G.N[g];
+  }
+  const int ktiles = (K / 2 + 31) / 32, mtiles = (M + kLbiMT - 1) / kLbiMT;
+  // split n over a cluster while the grid is short of two waves and every CTA keeps >= 32 rows of W
+  int zsplit = 1;
+  while (zsplit < kLbiMaxZ && ktiles * mtiles * zsplit < 2 * num_sms() && total_n / (2 * zsplit) >= 32) zsplit *= 2;
+  dim3 grid(ktiles * zsplit, mtiles);
+  BG_CHECK_CUDA(launch_pdl_cluster(linear_bwd_input_kernel, grid, dim3(256), 0, s, zsplit, G, gx, M, K, total_n, zsplit));
+  return 0;
 }
 
 int launch_linear_bwd_input(const float* gy, const float* W, float* gx, int M, int N, int K, float coef, cudaStream_t s) {
-  BG_REQUIRE(M > 0 && N > 0 && K > 0 && K % 2 == 0, "linear_bwd_input: bad shape M %d N %d K %d", M, N, K);
-  BG_REQUIRE((reinterpret_cast<uintptr_t>(W) & 7) == 0 && (reinterpret_cast<uintptr_t>(gx) & 7) == 0,
-             "linear_bwd_input: W and gx must be 8-byte aligned");
-  dim3 grid((K / 2 + 31) / 32, (M + kLbiMT - 1) / kLbiMT);
-  BG_CHECK_CUDA(launch_pdl(linear_bwd_input_kernel, grid, 256, 0, s, gy, W, gx, M, N, K, coef));
-  return 0;
+  LinGroups G;
+  memset(&G, 0, sizeof(G));
+  G.groups = 1;
+  G.W[0] = W;
+  G.y[0] = const_cast<float*>(gy);
+  G.N[0] = N;
+  G.coef[0] = coef;
+  return launch_linear_bwd_input_groups(G, gx, M, K, s);
 }
 
 int launch_linear_bwd_weight(const float* gy, const float* x, float* dW, float* db, int M, int N, int K, float coef,
@@ -1052,11 +1067,12 @@ int launch_sumsq(const float* x, size_t n, float scale, float* out, cudaStream_t
 }
 
 // mode 0: forward, 1: weight gradient, 2: input gradient.  Pointer arrays are HOST arrays of device pointers.
-int launch_linear_grouped(int mode, const float* x, const float* const* W, const float* const* bias, float* const* y,
-                          float* const* dW, float* const* db, const int* N, const float* coef, int groups, int M, int K,
-                          int act, float slope, float* gx, cudaStream_t s) {
+int launch_linear_grouped(int mode, const float* x, const float* const* xs, const float* const* W,
+                          const float* const* bias, float* const* y, float* const* dW, float* const* db, const int* N,
+                          const float* coef, int groups, int M, int K, int act, float slope, float* gx, cudaStream_t s) {
   BG_REQUIRE(groups > 0 && groups <= kMaxLinGroups, "linear_grouped: 1..%d groups (got %d)", kMaxLinGroups, groups);
   BG_REQUIRE(M > 0 && K > 0 && K % 4 == 0, "linear_grouped: bad shape M %d K %d", M, K);
+  BG_REQUIRE(mode != 1 || xs != nullptr, "linear_grouped: the weight gradient needs one input per layer");
   LinGroups G;
   memset(&G, 0, sizeof(G));
   G.groups = groups;
@@ -1065,6 +1081,7 @@ int launch_linear_grouped(int mode, const float* x, const float* const* W, const
   for (int g = 0; g < groups; ++g) {
     BG_REQUIRE(N[g] > 0 && N[g] % 4 == 0, "linear_grouped: N[%d] = %d must be a positive multiple of 4", g, N[g]);
     G.W[g] = W[g];
+    G.x[g] = xs ? xs[g] : nullptr;
     G.b[g] = bias ? bias[g] : nullptr;
     G.y[g] = y[g];
     G.dW[g] = dW ? dW[g] : nullptr;
@@ -1079,12 +1096,10 @@ int launch_linear_grouped(int mode, const float* x, const float* const* W, const
   if (mode == 0) {
     BG_CHECK_CUDA(launch_pdl(linear_fwd_grouped_kernel, blocks, 256, 0, s, x, G, M, K, act, slope));
   } else if (mode == 1) {
-    BG_CHECK_CUDA(launch_pdl(linear_bwd_weight_grouped_kernel, blocks, 128, 0, s, x, G, M, K));
+    BG_CHECK_CUDA(launch_pdl(linear_bwd_weight_grouped_kernel, blocks, 128, 0, s, G, M, K));
   } else {
     BG_REQUIRE(gx != nullptr, "linear_grouped: gx is required for the input gradient");
-    const long warps = (long)K * mgroups;
-    BG_CHECK_CUDA(launch_pdl(linear_bwd_input_grouped_kernel, (unsigned)((warps * 32 + 255) / 256), 256, 0, s, G, gx, M,
-                             K));
+    return launch_linear_bwd_input_groups(G, gx, M, K, s);
   }
   BG_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -183,7 +183,7 @@ int make_tmap_bf16_strided(CUtensorMap* map, const void* base, int rank, const u
 }  // namespace bg
 
 extern "C" const char* bg_last_error(void) { return bg::last_error(); }
-extern "C" int bg_abi_version(void) { return 2; }
+extern "C" int bg_abi_version(void) { return 3; }
 extern "C" int bg_set_deterministic(int on) {
   bg::set_deterministic(on);
   return 0;

@@ -196,20 +196,6 @@ class PackCache:
             for (w, cin_pad), wf, wd in zip(grp, wfs, wds):
                 self._conv[id(w)] = (_tag(w, cin_pad), wf, wd)
 
-    def linear_t(self, w: torch.Tensor):
-        """fp32 transpose (K, N) of an (N, K) linear weight: the input-gradient pass is a forward on it."""
-        key = id(w)
-        tag = _tag(w)
-        hit = self._lin.get(key)
-        if hit is not None and hit[0] == tag:
-            return hit[1]
-        w2 = w.detach().reshape(w.shape[0], -1)
-        n, k = w2.shape
-        wt = _f32(k, n, device=w.device)
-        call("bg_transpose_f32", w2, wt, n, k)
-        self._lin[key] = (tag, wt)
-        return wt
-
 
 # ------------------------------------------------------------------------------------------------------
 # thin op helpers
@@ -224,16 +210,13 @@ def linear_fwd(x, w, bias, act, coef=None):
     return y
 
 
-def linear_bwd_input(gy, w, packs: PackCache):
-    """gx = coef * gy @ W, read straight from the (N, K) weight (no cached transpose)."""
+def linear_bwd_input(gy, w, packs: PackCache = None):
+    """gx = coef * gy @ W, read straight from the (N, K) weight (no transposed copy)."""
     w2 = w.detach().reshape(w.shape[0], -1)
     n, k = w2.shape
     m = gy.shape[0]
     gx = _f32(m, k, device=gy.device)
-    if k % 2 == 0:
-        call("bg_linear_bwd_input", gy, w2, gx, m, n, k, coef_of(w))
-    else:
-        call("bg_linear_fwd", gy, packs.linear_t(w), None, gx, m, k, n, coef_of(w), 0, SLOPE)
+    call("bg_linear_bwd_input", gy, w2, gx, m, n, k, coef_of(w))
     return gx
 
 
@@ -627,7 +610,7 @@ def _generator_backward(gen, packs: PackCache, tape, g_img, need: Dict[int, bool
             sel = [i for i, fc in enumerate(fcs) if want(fc.weight) or want(fc.bias)]
             dws = [_f32(*fcs[i].weight.shape, device=dev) for i in sel]
             dbs = [_f32(ns[i], device=dev) for i in sel]
-            call("bg_linear_bwd_weight_grouped", maps[wsel][-1], [gys[i] for i in sel], dws, dbs, [ns[i] for i in sel],
+            call("bg_linear_bwd_weight_grouped", [maps[wsel][-1]] * len(sel), [gys[i] for i in sel], dws, dbs, [ns[i] for i in sel],
                  [cf[i] for i in sel], len(sel), B, 512)
             for i, dw, db in zip(sel, dws, dbs):
                 if want(fcs[i].weight):
@@ -635,7 +618,7 @@ def _generator_backward(gen, packs: PackCache, tape, g_img, need: Dict[int, bool
                 if want(fcs[i].bias):
                     grads[id(fcs[i].bias)] = db
         gw = _f32(B, 512, device=dev)
-        call("bg_linear_bwd_input_grouped", gys, [packs.linear_t(fc.weight) for fc in fcs], ns, cf, len(fcs), B, 512, gw)
+        call("bg_linear_bwd_input_grouped", gys, [fc.weight.detach() for fc in fcs], ns, cf, len(fcs), B, 512, gw)
         g_w[wsel] = gw
 
     # mapping network backward (gan.py:130-148)
@@ -651,18 +634,33 @@ def _generator_backward(gen, packs: PackCache, tape, g_img, need: Dict[int, bool
         if g is None:
             g = torch.zeros(B, 512, device=dev)
         need_in = (need_z or need_z2) if tape.get("maps_cat") is not None else (need_z if which == 0 else need_z2)
+        pending = []                                  # (layer, gated gradient, layer input) of a single pass
         for i in reversed(range(8)):
             lin = gen.to_w_noise[0].layers[i][0]
             gp = gate_f32(g, hs[i + 1])
             if want(lin.weight) or want(lin.bias):
-                acc = id(lin.weight) in mgrads
-                dw, db = linear_bwd_weight(gp, hs[i], lin.weight, into=mgrads.get(id(lin.weight)),
-                                           into_b=mgrads.get(id(lin.bias)))
-                if not acc:
-                    mgrads[id(lin.weight)] = dw
-                    mgrads[id(lin.bias)] = db
+                if len(passes) == 1:
+                    pending.append((lin, gp, hs[i]))
+                else:
+                    acc = id(lin.weight) in mgrads
+                    dw, db = linear_bwd_weight(gp, hs[i], lin.weight, into=mgrads.get(id(lin.weight)),
+                                               into_b=mgrads.get(id(lin.bias)))
+                    if not acc:
+                        mgrads[id(lin.weight)] = dw
+                        mgrads[id(lin.bias)] = db
             if i > 0 or need_in:
                 g = linear_bwd_input(gp, lin.weight, packs)
+        if pending:
+            # the weight gradients of the whole mapping network in one launch (each layer is a 1 MB output from a
+            # 64-row batch: eight separate launches are latency, not work)
+            dws = [_f32(*lin.weight.shape, device=dev) for lin, _, _ in pending]
+            dbs = [_f32(lin.weight.shape[0], device=dev) for lin, _, _ in pending]
+            call("bg_linear_bwd_weight_grouped", [x for _, _, x in pending], [gp for _, gp, _ in pending], dws, dbs,
+                 [lin.weight.shape[0] for lin, _, _ in pending], [coef_of(lin.weight) for lin, _, _ in pending],
+                 len(pending), pending[0][1].shape[0], 512)
+            for (lin, _, _), dw, db in zip(pending, dws, dbs):
+                mgrads[id(lin.weight)] = dw
+                mgrads[id(lin.bias)] = db
         dzs[which] = g if need_in else None
     if tape.get("maps_cat") is not None and dzs[0] is not None:
         both = dzs[0]

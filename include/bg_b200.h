@@ -205,17 +205,19 @@ int bg_linear_fwd(const float* x, const float* W, const float* bias, float* y, i
 int bg_linear_bwd_input(const float* gy, const float* W, float* gx, int M, int N, int K, float coef, void* stream);
 int bg_linear_bwd_weight(const float* gy, const float* x, float* dW, float* db, int M, int N, int K, float coef,
                          int accumulate, void* stream);
-/* Grouped forms for layers that share their input x (M,K): the 2*steps AdaIN style FCs of the generator all read the
- * latent w (gan.py:60,66).  W / bias / y / gy / dW / db / Wt / N / coef are HOST arrays with one entry per layer
- * (<= 16): device pointers, output widths N[g] (multiples of 4) and equalized coefficients.
- *   fwd:        y[g] (M,N[g]) = act(coef[g] * x W[g]^T + bias[g])
- *   bwd_weight: dW[g] (N[g],K) = coef[g] * gy[g]^T x;  db[g] (N[g]) = sum_m gy[g]   (db or db[g] may be NULL)
- *   bwd_input:  gx (M,K) = sum_g coef[g] * gy[g] Wt[g]^T with Wt[g] the TRANSPOSED weight (K,N[g]) */
+/* Grouped forms: several small layers in one launch.  W / bias / y / gy / dW / db / x / N / coef are HOST arrays with one
+ * entry per layer (<= 16): device pointers, output widths N[g] (multiples of 4) and equalized coefficients.
+ *   fwd:        y[g] (M,N[g]) = act(coef[g] * x W[g]^T + bias[g])       layers sharing their input x (M,K): the 2*steps
+ *                                                                       AdaIN style FCs all read the latent w (gan.py:60,66)
+ *   bwd_weight: dW[g] (N[g],K) = coef[g] * gy[g]^T x[g];  db[g] (N[g]) = sum_m gy[g]   (db or db[g] may be NULL); one
+ *               input per layer (the same pointer 2*steps times for the style FCs; the 8 mapping layers, gan.py:130-148)
+ *   bwd_input:  gx (M,K) = sum_g coef[g] * gy[g] W[g], W[g] the (N[g],K) weight as stored (no transposed copies);
+ *               the n range is split over a thread-block cluster and reduced through DSMEM in rank order. */
 int bg_linear_fwd_grouped(const float* x, const float* const* W, const float* const* bias, float* const* y, const int* N,
                           const float* coef, int groups, int M, int K, int act, float slope, void* stream);
-int bg_linear_bwd_weight_grouped(const float* x, float* const* gy, float* const* dW, float* const* db, const int* N,
+int bg_linear_bwd_weight_grouped(const float* const* x, float* const* gy, float* const* dW, float* const* db, const int* N,
                                  const float* coef, int groups, int M, int K, void* stream);
-int bg_linear_bwd_input_grouped(float* const* gy, const float* const* Wt, const int* N, const float* coef, int groups,
+int bg_linear_bwd_input_grouped(float* const* gy, const float* const* W, const int* N, const float* coef, int groups,
                                 int M, int K, float* gx, void* stream);
 int bg_transpose_f32(const float* in, float* out, int R, int C, void* stream);
 int bg_act_gate_f32(const float* g, const float* y, float* out, size_t n, float slope, void* stream);

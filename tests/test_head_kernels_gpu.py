@@ -198,15 +198,39 @@ def test_grouped_style_linears():
     gys = [torch.randn(M, n, device=DEV) for n in Ns]
     dWs = [torch.empty(n, K, device=DEV) for n in Ns]
     dbs = [torch.empty(n, device=DEV) for n in Ns]
-    bgn.call("bg_linear_bwd_weight_grouped", x, gys, dWs, dbs, Ns, coefs, len(Ns), M, K)
+    bgn.call("bg_linear_bwd_weight_grouped", [x] * len(Ns), gys, dWs, dbs, Ns, coefs, len(Ns), M, K)
     for gy, dW, db, c in zip(gys, dWs, dbs, coefs):
         assert torch.allclose(dW, c * gy.t() @ x, rtol=1e-4, atol=1e-4)
         assert torch.allclose(db, gy.sum(0), rtol=1e-4, atol=1e-4)
-    Wts = [W.t().contiguous() for W in Ws]
-    gx = torch.empty(M, K, device=DEV)
-    bgn.call("bg_linear_bwd_input_grouped", gys, Wts, Ns, coefs, len(Ns), M, K, gx)
+    # one input per layer (the mapping network's eight 512 x 512 layers in one launch)
+    xs = [torch.randn(M, K, device=DEV) for _ in Ns]
+    bgn.call("bg_linear_bwd_weight_grouped", xs, gys, dWs, dbs, Ns, coefs, len(Ns), M, K)
+    for xg, gy, dW, db, c in zip(xs, gys, dWs, dbs, coefs):
+        assert torch.allclose(dW, c * gy.t() @ xg, rtol=1e-4, atol=1e-4)
+        assert torch.allclose(db, gy.sum(0), rtol=1e-4, atol=1e-4)
     want = sum(c * gy @ W for gy, W, c in zip(gys, Ws, coefs))
-    assert torch.allclose(gx, want, rtol=1e-4, atol=2e-3)
+    outs = []
+    for _ in range(3):                                  # the cluster / DSMEM reduction is ordered: bit-identical reruns
+        gx = torch.full((M, K), float("nan"), device=DEV)
+        bgn.call("bg_linear_bwd_input_grouped", gys, Ws, Ns, coefs, len(Ns), M, K, gx)
+        outs.append(gx)
+    assert torch.allclose(outs[0], want, rtol=1e-4, atol=2e-3)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+@pytest.mark.parametrize("M,K,Ns", [(64, 512, [1024] * 4 + [512, 256, 128, 64] * 2 + [32, 32]), (32, 512, [40, 4, 1000]),
+                                    (3, 68, [4, 8]), (70, 132, [516])])
+def test_grouped_linear_input_gradient_shapes(M, K, Ns):
+    """bg_linear_bwd_input_grouped on the training shape (14 style FCs of the 256x256 stage, both latents) and ragged ones:
+    group boundaries inside a CTA's share of the n range, n shares shorter than a warp span, K not a multiple of 64."""
+    torch.manual_seed(len(Ns) + M)
+    Ws = [torch.randn(n, K, device=DEV) for n in Ns]
+    gys = [torch.randn(M, n, device=DEV) for n in Ns]
+    coefs = [0.05 * (1 + 0.1 * i) for i in range(len(Ns))]
+    gx = torch.full((M, K), float("nan"), device=DEV)
+    bgn.call("bg_linear_bwd_input_grouped", gys, Ws, Ns, coefs, len(Ns), M, K, gx)
+    want = sum(c * gy.double() @ W.double() for gy, W, c in zip(gys, Ws, coefs))
+    assert rel(gx, want) < 1e-5
 
 
 def test_helper_truncated_noise_distribution():
