@@ -1,4 +1,4 @@
-"""Times bg_linear_fwd / bg_linear_bwd_weight on the model's FC shapes: python tools/bench_linear.py [batch]
+"""Times bg_linear_fwd / bg_linear_bwd_weight / bg_linear_bwd_input on the model's FC shapes: python tools/bench_linear.py [batch]
 Each measurement streams over enough distinct weight buffers to exceed L2, all launches inside one event pair
 (a single small launch measures the ~15 us host-side call latency, not the kernel)."""
 import os
@@ -31,7 +31,7 @@ def timeit(fns):
     return s.elapsed_time(e) / len(fns) * 1e3
 
 
-print(f"M={M}   (K -> N)      fwd us   bwd_w us   (weights streamed from HBM)")
+print(f"M={M}   (K -> N)      fwd us   bwd_w us   bwd_x us   (weights streamed from HBM)")
 for K, N in [(512, 512), (512, 1024), (512, 64), (8192, 512), (512, 8192)]:
     nbuf = max(4, min(200, int(300e6 / (N * K * 4))))
     x = torch.randn(M, K, device=DEV)
@@ -43,4 +43,6 @@ for K, N in [(512, 512), (512, 1024), (512, 64), (8192, 512), (512, 8192)]:
     db = torch.empty(N, device=DEV)
     tf = timeit([(lambda w=w: bgn.call("bg_linear_fwd", x, w, b, y, M, N, K, 0.1, 1, 0.2)) for w in ws])
     tb = timeit([(lambda d=d: bgn.call("bg_linear_bwd_weight", gy, x, d, db, M, N, K, 0.1, 0)) for d in dws * 8])
-    print(f"  {K:5d} -> {N:5d}   {tf:8.1f}  {tb:8.1f}   ({nbuf} weight buffers)")
+    gx = torch.empty(M, K, device=DEV)
+    ti = timeit([(lambda w=w: bgn.call("bg_linear_bwd_input", gy, w, gx, M, N, K, 0.1)) for w in ws]) if K % 2 == 0 else float("nan")
+    print(f"  {K:5d} -> {N:5d}   {tf:8.1f}  {tb:8.1f}  {ti:8.1f}   ({nbuf} weight buffers)")
