@@ -113,6 +113,7 @@ struct HaloParams {
   // 4 + 4 KB, which takes the operand fetch off the 128 B/clk shared-memory limit that N = 128 sits on.
   // b_tx_bytes / b_tile_bytes describe the per-CTA half tile.  Tile indices handed to decode_tile are PAIR indices.
   int cta2;
+  int up_packed;  // upsample producers blend on packed bf16x2 pairs (BG_UP_PACKED=0: fp32 blends, one rounding)
   int epi_templated;   // 1: epilogue specialised for the stage row width (default); BG_EPI_TEMPLATED=0: run-time widths
 };
 
@@ -540,6 +541,30 @@ __device__ __forceinline__ void halo_producer_upsample(const HaloParams& p, uint
           const uint32_t w00[4] = {r00.x, r00.y, r00.z, r00.w}, w01[4] = {r01.x, r01.y, r01.z, r01.w};
           const uint32_t w10[4] = {r10.x, r10.y, r10.z, r10.w}, w11[4] = {r11.x, r11.y, r11.z, r11.w};
           uint32_t oAP[4], oAQ[4], oBP[4], oBQ[4];
+          if (p.up_packed) {
+            // the four outputs of a quad straight from its four sources on PACKED bf16x2 pairs:
+            //   out = 9/16 near + 3/16 side + 3/16 other side + 1/16 far   (the product of the two .75/.25 blends),
+            // one HMUL2 + three HFMA2 per pair and output, smallest term first (each fma rounds a partial sum that is
+            // smaller than the result: ~1.1x the error of one final rounding) — 64 instead of ~176 instructions per
+            // quad and channel group, no bf16 <-> fp32 conversions; the producer warps were the kernel's issue limit
+            const __nv_bfloat162 k9 = __floats2bfloat162_rn(0.5625f, 0.5625f), k3 = __floats2bfloat162_rn(0.1875f, 0.1875f),
+                                 k1 = __floats2bfloat162_rn(0.0625f, 0.0625f);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&w00[j]);
+              const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&w01[j]);
+              const __nv_bfloat162 c = *reinterpret_cast<const __nv_bfloat162*>(&w10[j]);
+              const __nv_bfloat162 d = *reinterpret_cast<const __nv_bfloat162*>(&w11[j]);
+              const __nv_bfloat162 ap = __hfma2(a, k9, __hfma2(b, k3, __hfma2(c, k3, __hmul2(d, k1))));
+              const __nv_bfloat162 aq = __hfma2(b, k9, __hfma2(a, k3, __hfma2(d, k3, __hmul2(c, k1))));
+              const __nv_bfloat162 bp = __hfma2(c, k9, __hfma2(a, k3, __hfma2(d, k3, __hmul2(b, k1))));
+              const __nv_bfloat162 bq = __hfma2(d, k9, __hfma2(b, k3, __hfma2(c, k3, __hmul2(a, k1))));
+              oAP[j] = *reinterpret_cast<const uint32_t*>(&ap);
+              oAQ[j] = *reinterpret_cast<const uint32_t*>(&aq);
+              oBP[j] = *reinterpret_cast<const uint32_t*>(&bp);
+              oBQ[j] = *reinterpret_cast<const uint32_t*>(&bq);
+            }
+          } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float2 a = unpack_bf16x2(w00[j]), b = unpack_bf16x2(w01[j]);
@@ -554,6 +579,7 @@ __device__ __forceinline__ void halo_producer_upsample(const HaloParams& p, uint
             oAQ[j] = pack_bf16x2(0.75f * q0x + 0.25f * q1x, 0.75f * q0y + 0.25f * q1y);
             oBP[j] = pack_bf16x2(0.25f * p0x + 0.75f * p1x, 0.25f * p0y + 0.75f * p1y);
             oBQ[j] = pack_bf16x2(0.25f * q0x + 0.75f * q1x, 0.25f * q0y + 0.75f * q1y);
+          }
           }
           const int hy = 2 * qk, hx = 2 * ql;
           const bool rA = (unsigned)(hb + hy) < (unsigned)p.H, rB = (unsigned)(hb + hy + 1) < (unsigned)p.H;
@@ -1169,6 +1195,11 @@ int launch_conv_halo(const void* x, const void* wpack, void* out, int N, int H, 
   p.a_stage_bytes = pool4 ? 4u * p.phase_bytes : ((p.a_tx_bytes + 1023u) & ~1023u);
   p.epi_row_bytes = (uint32_t)(bn_ch >= 64 ? 64 : bn_ch) * 2u;
   p.upsample = upsample ? 1 : 0;
+  {
+    static int up_packed = -1;
+    if (up_packed < 0) { const char* e = getenv("BG_UP_PACKED"); up_packed = (e && e[0] == '0') ? 0 : 1; }
+    p.up_packed = up_packed;
+  }
   if (p.pool4_tma) {
     // the pipeline unit is one phase tile (4 per chunk); two epilogue sets: keep the transpose stages at 32 KB
     p.a_tx_bytes = (uint32_t)((kTile + 1) * (kTile + 1)) * row_bytes;
