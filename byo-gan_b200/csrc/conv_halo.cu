@@ -516,6 +516,28 @@ __device__ __forceinline__ void halo_producer_upsample(const HaloParams& p, uint
   issue_patch();
   issue_patch();
 
+  // Everything about a thread's quads that does not depend on the tile — patch offset of the 2x2 sources, halo
+  // coordinates, the four swizzled destination offsets — is worked out once (the per-quad index arithmetic was 140 of
+  // the ~330 instructions a producer warp spent per quad, profiles/r2_sass_mix_style512.txt)
+  uint32_t q_pa[kQuadIters], q_yx[kQuadIters], q_dst[kQuadIters][4];
+#pragma unroll
+  for (int i = 0; i < kQuadIters; ++i) {
+    const int u = min(pt + i * kProdThreads, kQuadUnits - 1);
+    const int q = u >> CPP_SHIFT, c8 = u & (kCpp - 1);
+    const int qk = q / 9, ql = q - qk * 9;
+    const int hy = 2 * qk, hx = 2 * ql;
+    q_pa[i] = (uint32_t)(qk * kPatch + ql) * kPixBytes + (uint32_t)c8 * 16u;
+    q_yx[i] = (uint32_t)hy | ((uint32_t)hx << 8);
+    // A stage = [halo pixel][kc channels] with the 128/64/32-byte swizzle UMMA expects: the 16-byte chunk index
+    // is XORed with address bits 7.. (stage bases are 1024-byte aligned, so offsets can stand in for addresses)
+    const uint32_t l0 = (uint32_t)(hy * kHalo + hx) * kPixBytes + (uint32_t)c8 * 16u;
+    const uint32_t l1 = l0 + kPixBytes, l2 = l0 + kHalo * kPixBytes, l3 = l2 + kPixBytes;
+    q_dst[i][0] = l0 ^ (((l0 >> 7) & kSwzMask) << 4);
+    q_dst[i][1] = l1 ^ (((l1 >> 7) & kSwzMask) << 4);
+    q_dst[i][2] = l2 ^ (((l2 >> 7) & kSwzMask) << 4);
+    q_dst[i][3] = l3 ^ (((l3 >> 7) & kSwzMask) << 4);
+  }
+
   int stage = 0;
   uint32_t phase = 0;
   int item = 0;
@@ -533,9 +555,7 @@ __device__ __forceinline__ void halo_producer_upsample(const HaloParams& p, uint
       for (int i = 0; i < kQuadIters; ++i) {
         const int u = pt + i * kProdThreads;
         if (i < kQuadIters - 1 || u < kQuadUnits) {
-          const int q = u >> CPP_SHIFT, c8 = u & (kCpp - 1);
-          const int qk = q / 9, ql = q - qk * 9;
-          const uint32_t pa = patch + (uint32_t)(qk * kPatch + ql) * kPixBytes + (uint32_t)c8 * 16u;
+          const uint32_t pa = patch + q_pa[i];
           const uint4 r00 = lds128(pa), r01 = lds128(pa + kPixBytes), r10 = lds128(pa + kPatch * kPixBytes),
                       r11 = lds128(pa + (kPatch + 1) * kPixBytes);
           const uint32_t w00[4] = {r00.x, r00.y, r00.z, r00.w}, w01[4] = {r01.x, r01.y, r01.z, r01.w};
@@ -581,18 +601,14 @@ __device__ __forceinline__ void halo_producer_upsample(const HaloParams& p, uint
             oBQ[j] = pack_bf16x2(0.25f * q0x + 0.75f * q1x, 0.25f * q0y + 0.75f * q1y);
           }
           }
-          const int hy = 2 * qk, hx = 2 * ql;
+          const int hy = (int)(q_yx[i] & 0xffu), hx = (int)(q_yx[i] >> 8);
           const bool rA = (unsigned)(hb + hy) < (unsigned)p.H, rB = (unsigned)(hb + hy + 1) < (unsigned)p.H;
           const bool cP = (unsigned)(wb + hx) < (unsigned)p.W, cQ = (unsigned)(wb + hx + 1) < (unsigned)p.W;
           const uint4 z = make_uint4(0, 0, 0, 0);
-          // A stage = [halo pixel][kc channels] with the 128/64/32-byte swizzle UMMA expects: the 16-byte chunk index
-          // is XORed with address bits 7.. (stage bases are 1024-byte aligned, so offsets can stand in for addresses)
-          const uint32_t l0 = (uint32_t)(hy * kHalo + hx) * kPixBytes + (uint32_t)c8 * 16u;
-          const uint32_t l1 = l0 + kPixBytes, l2 = l0 + kHalo * kPixBytes, l3 = l2 + kPixBytes;
-          sts128(sdst + (l0 ^ (((l0 >> 7) & kSwzMask) << 4)), (rA && cP) ? make_uint4(oAP[0], oAP[1], oAP[2], oAP[3]) : z);
-          sts128(sdst + (l1 ^ (((l1 >> 7) & kSwzMask) << 4)), (rA && cQ) ? make_uint4(oAQ[0], oAQ[1], oAQ[2], oAQ[3]) : z);
-          sts128(sdst + (l2 ^ (((l2 >> 7) & kSwzMask) << 4)), (rB && cP) ? make_uint4(oBP[0], oBP[1], oBP[2], oBP[3]) : z);
-          sts128(sdst + (l3 ^ (((l3 >> 7) & kSwzMask) << 4)), (rB && cQ) ? make_uint4(oBQ[0], oBQ[1], oBQ[2], oBQ[3]) : z);
+          sts128(sdst + q_dst[i][0], (rA && cP) ? make_uint4(oAP[0], oAP[1], oAP[2], oAP[3]) : z);
+          sts128(sdst + q_dst[i][1], (rA && cQ) ? make_uint4(oAQ[0], oAQ[1], oAQ[2], oAQ[3]) : z);
+          sts128(sdst + q_dst[i][2], (rB && cP) ? make_uint4(oBP[0], oBP[1], oBP[2], oBP[3]) : z);
+          sts128(sdst + q_dst[i][3], (rB && cQ) ? make_uint4(oBQ[0], oBQ[1], oBQ[2], oBQ[3]) : z);
         }
       }
       fence_proxy_async();
