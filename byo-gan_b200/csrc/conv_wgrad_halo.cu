@@ -43,6 +43,13 @@ struct WgradHaloParams {
   uint32_t a_layout, b_layout;
   uint32_t a_slab_bytes;
   int stack_taps;                  // 1: the three kx taps are ONE MMA (N = 3 * ci_sub, N-atoms one pixel apart)
+  // ky_stack (Cout <= 64, plain 3x3): the M = 128 rows of the instruction, of which Cout <= 64 are channels, carry
+  // SEVERAL kernel rows: M-atom a (co_slab channels) reads the G tile a image rows further down (LBO = one 16-pixel tile
+  // row), the X halo stays at row offset 0, so atom a holds kernel row ky = 2 - abase - a.  The G box starts one image row
+  // above the K block and has 10 rows.  Every (G row, X row) pair a shifted atom misses at the top / bottom of the map
+  // has its X row outside the image, i.e. contributes zero.  Units per (ci slab): 2 for Cout = 64 (ky {2,1}, ky {0}),
+  // 1 for Cout <= 32 (ky {2,1,0}).
+  int ky_stack, ky_units;
   // pool4: weight gradient of conv3x3 -> AvgPool2d(2) taken on the 4x4 stride-2 form: G is the POOLED gradient (H, W
   // below are its dims), X the full-resolution conv input (2H x 2W).  A CTA owns one tap row a (0..3); per K block it
   // loads two column-parity tiles of X (TMA boxes with element stride 2 along W and H): parity 1 serves taps b = 0, 2
@@ -78,8 +85,9 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
   // read from DRAM three times on the 256x256 layers, 1.83x over the whole family, profiles/r1_ncu_dram_*.)
   const int unit = blockIdx.x % p.units;
   const int split = blockIdx.x / p.units;
-  const int ntg = p.pool4 ? 4 : 3;
-  const int tg = unit % ntg;                     // ky (pool4: tap row a)
+  const int ntg = p.pool4 ? 4 : (p.ky_stack ? p.ky_units : 3);
+  const int tg = unit % ntg;                     // ky (pool4: tap row a; ky_stack: index of the kernel-row group)
+  const int abase = p.ky_stack ? 2 * tg : 0;     // ky_stack: first G tile row of M-atom 0, relative to the box
   const int cis = (unit / ntg) % p.ci_slabs;
   const int cot = unit / (ntg * p.ci_slabs);
   const int co0 = cot * 128;
@@ -118,7 +126,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
       if (lane == 0) {
         int stage = 0;
         uint32_t phase = 0;
-        const uint32_t tx = (uint32_t)p.co_nslabs * p.a_slab_bytes +
+        const uint32_t tx = (p.ky_stack ? (uint32_t)(kBw * (kBh + 2)) * p.a_row_bytes : (uint32_t)p.co_nslabs * p.a_slab_bytes) +
                             (p.pool4 ? 2u * (uint32_t)((kBw + 1) * kBh) * p.b_row_bytes
                                      : (uint32_t)p.ci_nsub * (uint32_t)(kHaloW * kBh) * p.b_row_bytes);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
@@ -130,8 +138,10 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
           uint8_t* sa = smem + (size_t)stage * kStageBytes;
           uint8_t* sb = sa + kARegion;
           mbar_expect_tx(&full_bar[stage], tx);
-          for (int s = 0; s < p.co_nslabs; ++s)
-            tma_load_4d(&tmap_g, &full_bar[stage], sa + (size_t)s * p.a_slab_bytes, co0 + s * p.co_slab, w0, h0, n);
+          if (p.ky_stack) tma_load_4d(&tmap_g, &full_bar[stage], sa, co0, w0, h0 - 1, n);     // 10 rows from h0 - 1
+          else
+            for (int s = 0; s < p.co_nslabs; ++s)
+              tma_load_4d(&tmap_g, &full_bar[stage], sa + (size_t)s * p.a_slab_bytes, co0 + s * p.co_slab, w0, h0, n);
           if (p.pool4) {
             // sub-region 0: odd full-resolution columns 2j-1 (j = w0..w0+16), sub-region 1: even columns 2j; rows
             // 2i + a - 1 for the 8 pooled rows i of the block (both with element stride 2)
@@ -139,7 +149,8 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
             tma_load_4d(&tmap_x, &full_bar[stage], sb + kBSub, ci0, 2 * w0, 2 * h0 + tg - 1, n);
           } else {
             for (int s = 0; s < p.ci_nsub; ++s)
-              tma_load_4d(&tmap_x, &full_bar[stage], sb + (size_t)s * kBSub, ci0 + s * p.ci_sub, w0 - 1, h0 + tg - 1, n);
+              tma_load_4d(&tmap_x, &full_bar[stage], sb + (size_t)s * kBSub, ci0 + s * p.ci_sub, w0 - 1,
+                          p.ky_stack ? h0 : h0 + tg - 1, n);
           }
           if (++stage == kStages) {
             stage = 0;
@@ -153,7 +164,9 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
       // taps are three N-atoms with LBO = one pixel row and run as ONE MMA with N = 3 * ci: a small-N tcgen05.mma
       // costs ~60 clk no matter how narrow it is, so fewer, wider instructions are what speeds the narrow layers up.
       const uint32_t idesc = umma_idesc_bf16(128, p.stack_taps ? 3 * p.ci_slab : p.ci_slab, 1, 1);
-      const uint64_t a_desc0 = umma_desc(smem_u32(smem), p.a_slab_bytes, 8u * p.a_row_bytes, p.a_layout);
+      const uint64_t a_desc0 =
+          umma_desc(smem_u32(smem) + (uint32_t)abase * (uint32_t)kBw * p.a_row_bytes,
+                    p.ky_stack ? (uint32_t)kBw * p.a_row_bytes : p.a_slab_bytes, 8u * p.a_row_bytes, p.a_layout);
       const uint64_t b_desc0 = umma_desc(smem_u32(smem) + kARegion, (p.stack_taps || p.pool4) ? p.b_row_bytes : kBSub,
                                          8u * p.b_row_bytes, p.b_layout);
       const uint32_t a_kstep = (16u * p.a_row_bytes) >> 4;          // 16 pixels (one image row of the tile) per K step
@@ -209,15 +222,18 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
       // ------------------------------ epilogue: TMEM -> vector reductions into dWp ------------------------------
       const int q = warp & 3;
       const int row = q * 32 + lane;
-      const int co = co0 + row;
+      // ky_stack: row = (M-atom a, channel); atom a holds kernel row 2 - abase - a (dead when that is not 0..2)
+      const int atom = p.ky_stack ? row / p.co_slab : 0;
+      const int ky = p.ky_stack ? 2 - abase - atom : tg;
+      const int co = p.ky_stack ? co0 + row - atom * p.co_slab : co0 + row;
       mbar_wait(done_bar, 0);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-      const bool live = row < p.co_slab * p.co_nslabs && co < p.Cout;
+      const bool live = p.ky_stack ? (ky >= 0 && ky <= 2 && co < p.Cout) : (row < p.co_slab * p.co_nslabs && co < p.Cout);
       const int ntaps = p.pool4 ? 4 : 3;
       for (int kx = 0; kx < ntaps; ++kx) {
         // pool4: TMEM holds the taps in the order b = 0, 2, 1, 3 (ci_slab columns each)
-        const int tap = p.pool4 ? tg * 4 + ((kx & 1) * 2 + (kx >> 1)) : tg * 3 + kx;
+        const int tap = p.pool4 ? tg * 4 + ((kx & 1) * 2 + (kx >> 1)) : ky * 3 + kx;
         float* drow = p.dw + ((size_t)tap * p.Cout + co) * p.Cin + ci0;
         for (int c = 0; c < p.ci_slab; c += 16) {
           uint32_t v[16];
@@ -283,7 +299,13 @@ int launch_conv_wgrad_halo(const void* x, const void* g, float* dw, int N, int H
     p.stack_taps = (p.ci_nsub == 1 && (mode == 2 || (mode == 1 && Cin <= 32))) ? 1 : 0;
   }
   if (p.pool4) p.stack_taps = 0;
-  const int units = p.co_tiles * p.ci_slabs * (p.pool4 ? 4 : 3);
+  {
+    static int ky_on = -1;    // BG_WGRAD_KYSTACK=0: one kernel row per CTA also for Cout <= 64 (A/B switch)
+    if (ky_on < 0) { const char* e = getenv("BG_WGRAD_KYSTACK"); ky_on = (e && e[0] == '0') ? 0 : 1; }
+    p.ky_stack = (ky_on && !p.pool4 && Cout <= 64) ? 1 : 0;
+    p.ky_units = Cout == 64 ? 2 : 1;
+  }
+  const int units = p.co_tiles * p.ci_slabs * (p.pool4 ? 4 : (p.ky_stack ? p.ky_units : 3));
   p.units = units;
   // one resident wave (1 CTA per SM: 3 x 68 KB stages): splits = floor(SMs / units), so that every CTA of the grid runs
   // concurrently with the others that read the same K range.  BG_WGRAD_WAVES=2 restores round 1's two waves.
@@ -300,7 +322,7 @@ int launch_conv_wgrad_halo(const void* x, const void* g, float* dw, int N, int H
   {
     uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)N};
     uint64_t str[3] = {(uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
-    uint32_t box[4] = {(uint32_t)p.co_slab, (uint32_t)kBw, (uint32_t)kBh, 1u};
+    uint32_t box[4] = {(uint32_t)p.co_slab, (uint32_t)kBw, (uint32_t)(p.ky_stack ? kBh + 2 : kBh), 1u};
     if (make_tmap_bf16(&tmg, g, 4, dims, str, box, (int)p.a_row_bytes) != 0) return 1;
   }
   {
