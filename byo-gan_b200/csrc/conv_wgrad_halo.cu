@@ -85,9 +85,13 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
   // read from DRAM three times on the 256x256 layers, 1.83x over the whole family, profiles/r1_ncu_dram_*.)
   const int unit = blockIdx.x % p.units;
   const int split = blockIdx.x / p.units;
-  const int ntg = p.pool4 ? 4 : (p.ky_stack ? p.ky_units : 3);
+  const int ntg = p.ky_stack ? p.ky_units : (p.pool4 ? 4 : 3);
   const int tg = unit % ntg;                     // ky (pool4: tap row a; ky_stack: index of the kernel-row group)
-  const int abase = p.ky_stack ? 2 * tg : 0;     // ky_stack: first G tile row of M-atom 0, relative to the box
+  // ky_stack: first G tile row of M-atom 0, relative to the box (which starts one image row above the K block).
+  // pool4 + ky_stack (Cout = 64): pooled row i of G meets X row 2i + s, so an atom shifted by sigma pooled rows holds tap
+  // row a = s - 2 sigma + 1: group 0 (s = 0, atoms sigma = -1, 0) -> a = 3, 1; group 1 (s = 1, sigma = 0, +1) -> a = 2, 0.
+  const int abase = p.ky_stack ? (p.pool4 ? tg : 2 * tg) : 0;
+  const int xrow = p.pool4 ? (p.ky_stack ? tg : tg - 1) : (p.ky_stack ? 0 : tg - 1);     // X row offset of the K block
   const int cis = (unit / ntg) % p.ci_slabs;
   const int cot = unit / (ntg * p.ci_slabs);
   const int co0 = cot * 128;
@@ -145,12 +149,11 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
           if (p.pool4) {
             // sub-region 0: odd full-resolution columns 2j-1 (j = w0..w0+16), sub-region 1: even columns 2j; rows
             // 2i + a - 1 for the 8 pooled rows i of the block (both with element stride 2)
-            tma_load_4d(&tmap_x, &full_bar[stage], sb, ci0, 2 * w0 - 1, 2 * h0 + tg - 1, n);
-            tma_load_4d(&tmap_x, &full_bar[stage], sb + kBSub, ci0, 2 * w0, 2 * h0 + tg - 1, n);
+            tma_load_4d(&tmap_x, &full_bar[stage], sb, ci0, 2 * w0 - 1, 2 * h0 + xrow, n);
+            tma_load_4d(&tmap_x, &full_bar[stage], sb + kBSub, ci0, 2 * w0, 2 * h0 + xrow, n);
           } else {
             for (int s = 0; s < p.ci_nsub; ++s)
-              tma_load_4d(&tmap_x, &full_bar[stage], sb + (size_t)s * kBSub, ci0 + s * p.ci_sub, w0 - 1,
-                          p.ky_stack ? h0 : h0 + tg - 1, n);
+              tma_load_4d(&tmap_x, &full_bar[stage], sb + (size_t)s * kBSub, ci0 + s * p.ci_sub, w0 - 1, h0 + xrow, n);
           }
           if (++stage == kStages) {
             stage = 0;
@@ -224,16 +227,18 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_
       const int row = q * 32 + lane;
       // ky_stack: row = (M-atom a, channel); atom a holds kernel row 2 - abase - a (dead when that is not 0..2)
       const int atom = p.ky_stack ? row / p.co_slab : 0;
-      const int ky = p.ky_stack ? 2 - abase - atom : tg;
+      // kernel row of this accumulator row (pool4: tap row of the 4x4 form)
+      const int ky = p.ky_stack ? (p.pool4 ? xrow - 2 * (abase + atom - 1) + 1 : 2 - abase - atom) : tg;
       const int co = p.ky_stack ? co0 + row - atom * p.co_slab : co0 + row;
       mbar_wait(done_bar, 0);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-      const bool live = p.ky_stack ? (ky >= 0 && ky <= 2 && co < p.Cout) : (row < p.co_slab * p.co_nslabs && co < p.Cout);
+      const bool live = p.ky_stack ? (ky >= 0 && ky <= (p.pool4 ? 3 : 2) && co < p.Cout)
+                                   : (row < p.co_slab * p.co_nslabs && co < p.Cout);
       const int ntaps = p.pool4 ? 4 : 3;
       for (int kx = 0; kx < ntaps; ++kx) {
         // pool4: TMEM holds the taps in the order b = 0, 2, 1, 3 (ci_slab columns each)
-        const int tap = p.pool4 ? tg * 4 + ((kx & 1) * 2 + (kx >> 1)) : ky * 3 + kx;
+        const int tap = p.pool4 ? ky * 4 + ((kx & 1) * 2 + (kx >> 1)) : ky * 3 + kx;
         float* drow = p.dw + ((size_t)tap * p.Cout + co) * p.Cin + ci0;
         for (int c = 0; c < p.ci_slab; c += 16) {
           uint32_t v[16];
@@ -302,10 +307,10 @@ int launch_conv_wgrad_halo(const void* x, const void* g, float* dw, int N, int H
   {
     static int ky_on = -1;    // BG_WGRAD_KYSTACK=0: one kernel row per CTA also for Cout <= 64 (A/B switch)
     if (ky_on < 0) { const char* e = getenv("BG_WGRAD_KYSTACK"); ky_on = (e && e[0] == '0') ? 0 : 1; }
-    p.ky_stack = (ky_on && !p.pool4 && Cout <= 64) ? 1 : 0;
+    p.ky_stack = (ky_on && (p.pool4 ? Cout == 64 : Cout <= 64)) ? 1 : 0;
     p.ky_units = Cout == 64 ? 2 : 1;
   }
-  const int units = p.co_tiles * p.ci_slabs * (p.pool4 ? 4 : (p.ky_stack ? p.ky_units : 3));
+  const int units = p.co_tiles * p.ci_slabs * (p.ky_stack ? p.ky_units : (p.pool4 ? 4 : 3));
   p.units = units;
   // one resident wave (1 CTA per SM: 3 x 68 KB stages): splits = floor(SMs / units), so that every CTA of the grid runs
   // concurrently with the others that read the same K range.  BG_WGRAD_WAVES=2 restores round 1's two waves.
