@@ -387,6 +387,7 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     copy_stream = torch.cuda.Stream(device=device)
+    RUNAHEAD = int(os.environ.get("BG_BENCH_RUNAHEAD", "2"))   # 0: unlimited
 
     def timed(n_steps, from_host):
         barrier()
@@ -407,8 +408,15 @@ def run_b200(args):
                 return r, z, ev
 
             nxt = upload(0)
+        # Device-resident leg: the host never reads anything back, so it would queue all K steps at once.  With several
+        # ranks per node that makes the step time noisy (launch queues fill, NCCL's kernels of step i + 1 are launched at
+        # different moments on different ranks): like a training loop that reads its losses one step late, the host stays
+        # at most RUNAHEAD steps in front of the device (an event wait; no effect on a GPU-bound single process).
+        marks = []
         for i in range(n_steps):
             j = i % POOL
+            if not from_host and RUNAHEAD > 0 and len(marks) >= RUNAHEAD:
+                marks.pop(0).synchronize()
             if from_host:
                 real, zz, ev = nxt
                 main.wait_event(ev)
@@ -419,6 +427,10 @@ def run_b200(args):
                 tr.iteration(real, zz[0], zz[1], read_losses=True)
             else:
                 tr.iteration(dev_real[j].clone(), dev_z[j][0].clone(), dev_z[j][1].clone(), read_losses=False)
+                if RUNAHEAD > 0:
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    marks.append(ev)
         if from_host:
             tr.flush_reads()                                 # the last iteration's losses, inside the timed region
         t1.record()
