@@ -536,6 +536,7 @@ def run_b200(args):
             "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": workload_config(args.workload, world, style_mixing, args.batch or None),
+            "host_runahead_steps": RUNAHEAD,
             "parity_variant": parity_variant,
             "clocks": clk,
             "e2e": {"value": round(e2e_value, 2), "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8, "loss_readback": "both losses copied to pinned host memory every step, consumed one step later (no queue drain)",
